@@ -1,0 +1,967 @@
+/*
+ * cg_host.cpp -- host side of the path above the kernels: device context, chunk-group
+ * skipping, staging of column chunks from 8 KB pages into HBM, the scan driver and the
+ * result fetch.  Mirrors the reader of backend/columnar/columnar_reader.c, batch-wise.
+ */
+#include <algorithm>
+#include <omp.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "cg_internal.h"
+
+static CgContext g_ctx;
+static bool g_ctx_ready = false;
+
+CgContext *cg_ctx(void)
+{
+	if (!g_ctx_ready)
+	{
+		cg_set_error(CG_EINVAL, "cg_init() has not been called");
+		return nullptr;
+	}
+	return &g_ctx;
+}
+
+extern "C" int cg_device_count(int *count)
+{
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess)
+	{
+		*count = 0;
+		return cg_set_error(CG_ECUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+	}
+	*count = n;
+	return CG_OK;
+}
+
+extern "C" int cg_init(int device)
+{
+	if (g_ctx_ready)
+	{
+		if (g_ctx.device != device)
+			return cg_set_error(CG_EINVAL, "already initialised on device %d", g_ctx.device);
+		return CG_OK;
+	}
+	CG_CUDA(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CG_CUDA(cudaGetDeviceProperties(&prop, device));
+	if (prop.major != 10)
+		return cg_set_error(CG_EUNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+							device, prop.major, prop.minor);
+	g_ctx.device = device;
+	g_ctx.sm_count = prop.multiProcessorCount;
+	CG_CUDA(cudaStreamCreateWithFlags(&g_ctx.compute, cudaStreamNonBlocking));
+	g_ctx.own_compute = g_ctx.compute;
+	CG_CUDA(cudaStreamCreateWithFlags(&g_ctx.copy, cudaStreamNonBlocking));
+	CG_CUDA(cudaEventCreate(&g_ctx.ev_a));
+	CG_CUDA(cudaEventCreate(&g_ctx.ev_b));
+	const char *t = getenv("CG_STAGE_THREADS");
+	int hw = omp_get_num_procs();
+	g_ctx.stage_threads = t ? atoi(t) : std::min(hw, 32);
+	if (g_ctx.stage_threads < 1) g_ctx.stage_threads = 1;
+	const char *b = getenv("CG_PINNED_BLOCK_MB");
+	g_ctx.pinned_block_bytes = (size_t) (b ? atoi(b) : 64) << 20;
+	g_ctx_ready = true;
+	return CG_OK;
+}
+
+int cg_ensure_pinned(CgContext *ctx)
+{
+	if (ctx->pinned[0]) return CG_OK;
+	for (int i = 0; i < CgContext::kPinnedBlocks; i++)
+	{
+		CG_CUDA(cudaHostAlloc((void **) &ctx->pinned[i], ctx->pinned_block_bytes, cudaHostAllocDefault));
+		CG_CUDA(cudaEventCreateWithFlags(&ctx->pinned_free[i], cudaEventDisableTiming));
+	}
+	return CG_OK;
+}
+
+extern "C" int cg_synchronize(void)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx) return CG_EINVAL;
+	CG_CUDA(cudaStreamSynchronize(ctx->copy));
+	CG_CUDA(cudaStreamSynchronize(ctx->compute));
+	return CG_OK;
+}
+
+extern "C" int cg_set_stream(void *cuda_stream)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx) return CG_EINVAL;
+	CG_CUDA(cudaStreamSynchronize(ctx->compute));
+	ctx->compute = cuda_stream ? (cudaStream_t) cuda_stream : ctx->own_compute;
+	return CG_OK;
+}
+
+int cg_prof_mark(CgContext *ctx, cudaStream_t stream)
+{
+	if (!ctx->profiling) return CG_OK;
+	if (ctx->prof_used == ctx->prof_events.size())
+	{
+		cudaEvent_t e;
+		CG_CUDA(cudaEventCreate(&e));
+		ctx->prof_events.push_back(e);
+	}
+	CG_CUDA(cudaEventRecord(ctx->prof_events[ctx->prof_used++], stream));
+	return CG_OK;
+}
+
+extern "C" int cg_profile_begin(void)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx) return CG_EINVAL;
+	ctx->profiling = true;
+	ctx->prof_used = 0;
+	return CG_OK;
+}
+
+extern "C" int cg_profile_collect(int32_t *launches, double *total_ms, double *max_ms)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx) return CG_EINVAL;
+	ctx->profiling = false;
+	double total = 0, mx = 0;
+	size_t n = ctx->prof_used / 2;
+	for (size_t i = 0; i < n; i++)
+	{
+		CG_CUDA(cudaEventSynchronize(ctx->prof_events[2 * i + 1]));
+		float ms = 0;
+		CG_CUDA(cudaEventElapsedTime(&ms, ctx->prof_events[2 * i], ctx->prof_events[2 * i + 1]));
+		total += ms;
+		if (ms > mx) mx = ms;
+	}
+	if (launches) *launches = (int32_t) n;
+	if (total_ms) *total_ms = total;
+	if (max_ms) *max_ms = mx;
+	ctx->prof_used = 0;
+	return CG_OK;
+}
+
+extern "C" void cg_shutdown(void)
+{
+	if (!g_ctx_ready) return;
+	cudaStreamSynchronize(g_ctx.copy);
+	cudaStreamSynchronize(g_ctx.compute);
+	for (int i = 0; i < CgContext::kPinnedBlocks; i++)
+	{
+		if (g_ctx.pinned[i]) cudaFreeHost(g_ctx.pinned[i]);
+		if (g_ctx.pinned_free[i]) cudaEventDestroy(g_ctx.pinned_free[i]);
+		g_ctx.pinned[i] = nullptr; g_ctx.pinned_free[i] = nullptr;
+	}
+	cudaEventDestroy(g_ctx.ev_a); cudaEventDestroy(g_ctx.ev_b);
+	for (cudaEvent_t e : g_ctx.prof_events) cudaEventDestroy(e);
+	g_ctx.prof_events.clear();
+	cudaStreamDestroy(g_ctx.copy); cudaStreamDestroy(g_ctx.own_compute);
+	g_ctx_ready = false;
+}
+
+/* ------------------------------------------------------------------------------ *
+ *  K2: chunk-group skipping.
+ * ------------------------------------------------------------------------------ */
+static int datum_cmp(int type_class, int64_t a, int64_t b)
+{
+	if (type_class == CG_TYPE_FLOAT)
+	{
+		double x, y;
+		memcpy(&x, &a, 8); memcpy(&y, &b, 8);
+		bool xn = x != x, yn = y != y;
+		if (xn || yn) return (int) xn - (int) yn;
+		return (x > y) - (x < y);
+	}
+	return (a > b) - (a < b);
+}
+
+/*
+ * [PG] predicate_refuted_by(base constraint, WHERE list) for an AND-list of
+ * "col <op> const": the chunk's (col >= min AND col <= max) is refuted when one conjunct
+ * on that column contradicts either half (backend/columnar/columnar_reader.c:1132-1187,
+ * 1234-1260, 1358-1384).  A chunk without min/max (all NULL) is never skipped.
+ */
+static bool chunk_refuted(const CgSkipNode &node, int type_class, int col, const CgScanDesc *d)
+{
+	if (!node.has_minmax) return false;
+	for (int q = 0; q < d->nquals; q++)
+	{
+		if (d->quals[q].column != col) continue;
+		int64_t k = d->quals[q].konst;
+		int cmin = datum_cmp(type_class, node.min_value, k);
+		int cmax = datum_cmp(type_class, node.max_value, k);
+		switch (d->quals[q].op)
+		{
+			case CG_OP_LT: if (cmin >= 0) return true; break;
+			case CG_OP_LE: if (cmin > 0) return true; break;
+			case CG_OP_EQ: if (cmin > 0 || cmax < 0) return true; break;
+			case CG_OP_GE: if (cmax < 0) return true; break;
+			case CG_OP_GT: if (cmax <= 0) return true; break;
+			default: break;   /* <> refutes nothing */
+		}
+	}
+	return false;
+}
+
+static int stripe_chunk_mask(const CgStripe &s, const CgSkipNode *nodes, const CgColumnDesc *columns, int natts,
+							 const CgScanDesc *d, uint8_t *mask, int64_t *filtered)
+{
+	for (uint32_t k = 0; k < s.chunk_count; k++) mask[k] = 1;
+	if (!d->enable_qual_pushdown || d->nquals == 0) return CG_OK;
+	bool has_qual[256] = {false};
+	for (int q = 0; q < d->nquals; q++) has_qual[d->quals[q].column] = true;
+	for (int c = 0; c < natts && c < 256; c++)      /* whereClauseVars, in attribute order */
+	{
+		if (!has_qual[c]) continue;
+		for (uint32_t k = 0; k < s.chunk_count; k++)
+		{
+			const CgSkipNode &node = nodes[s.skipnode_base + (uint32_t) c * s.chunk_count + k];
+			if (mask[k] && chunk_refuted(node, columns[c].type_class, c, d))
+			{
+				mask[k] = 0;
+				(*filtered)++;
+			}
+		}
+	}
+	return CG_OK;
+}
+
+static int validate_relation(const CgRelation *rel)
+{
+	if (!rel || !rel->columns || (rel->nstripes > 0 && (!rel->pages || !rel->stripes || !rel->nodes)))
+		return cg_set_error(CG_EINVAL, "NULL relation field");
+	if (rel->nstripes < 0 || rel->nnodes < 0) return cg_set_error(CG_EINVAL, "negative count");
+	if (rel->natts <= 0 || rel->natts > 256) return cg_set_error(CG_EUNSUPPORTED, "natts %d", rel->natts);
+	for (int i = 0; i < rel->nstripes; i++)
+	{
+		const CgStripe &s = rel->stripes[i];
+		if ((int) s.column_count > rel->natts)
+			return cg_set_error(CG_ECORRUPT, "stripe %d has %u columns, relation %d", i, s.column_count, rel->natts);
+		if ((uint64_t) s.skipnode_base + (uint64_t) s.column_count * s.chunk_count > (uint64_t) rel->nnodes)
+			return cg_set_error(CG_ECORRUPT, "stripe %d: skip list exceeds node array", i);
+		if (s.file_offset < CG_FIRST_LOGICAL_OFFSET)
+			return cg_set_error(CG_ECORRUPT, "stripe %d: invalid logical offset %llu", i, (unsigned long long) s.file_offset);
+	}
+	return CG_OK;
+}
+
+extern "C" int cg_selected_chunk_mask(const CgRelation *rel, int32_t stripe_index, const CgScanDesc *desc,
+									  uint8_t *mask, int64_t *filtered)
+{
+	int rc = validate_relation(rel);
+	if (rc) return rc;
+	if (stripe_index < 0 || stripe_index >= rel->nstripes) return cg_set_error(CG_EINVAL, "stripe index");
+	int64_t f = 0;
+	rc = stripe_chunk_mask(rel->stripes[stripe_index], rel->nodes, rel->columns, rel->natts, desc, mask, &f);
+	if (filtered) *filtered = f;
+	return rc;
+}
+
+/* interval arithmetic over the skip lists of the chunk groups that survive skipping */
+extern "C" int cg_relation_bounds(const CgRelation *rel, const CgScanDesc *desc, int64_t *key_min, int64_t *key_max,
+								  int64_t *term_abs_bound, int64_t *rows)
+{
+	int rc = validate_relation(rel);
+	if (rc) return rc;
+	std::vector<int64_t> cmin(rel->natts, INT64_MAX), cmax(rel->natts, INT64_MIN);
+	std::vector<uint8_t> unknown(rel->natts, 0);
+	int64_t nrows = 0;
+	std::vector<uint8_t> mask;
+	for (int si = 0; si < rel->nstripes; si++)
+	{
+		const CgStripe &s = rel->stripes[si];
+		mask.resize(s.chunk_count);
+		int64_t f = 0;
+		stripe_chunk_mask(s, rel->nodes, rel->columns, rel->natts, desc, mask.data(), &f);
+		for (uint32_t k = 0; k < s.chunk_count; k++)
+		{
+			if (!mask[k]) continue;
+			nrows += (int64_t) rel->nodes[s.skipnode_base + k].row_count;
+			for (uint32_t c = 0; c < s.column_count; c++)
+			{
+				const CgSkipNode &n = rel->nodes[s.skipnode_base + c * s.chunk_count + k];
+				if (rel->columns[c].type_class == CG_TYPE_FLOAT) { unknown[c] = 1; continue; }
+				if (!n.has_minmax)
+				{
+					/* all NULL chunk contributes no values */
+					if (n.decompressed_size != 0) unknown[c] = 1;
+					continue;
+				}
+				cmin[c] = std::min(cmin[c], n.min_value);
+				cmax[c] = std::max(cmax[c], n.max_value);
+			}
+		}
+	}
+	if (rows) *rows = nrows;
+	if (key_min && key_max)
+	{
+		*key_min = 0; *key_max = -1;
+		if (desc->ngroup_cols == 1)
+		{
+			int c = desc->group_cols[0];
+			if (!unknown[c] && cmin[c] <= cmax[c]) { *key_min = cmin[c]; *key_max = cmax[c]; }
+		}
+		/* packed two-column keys are sparse: leave min > max (hash table) */
+	}
+	if (term_abs_bound)
+		for (int a = 0; a < desc->naggs; a++)
+		{
+			const CgAggSpec &s = desc->aggs[a];
+			term_abs_bound[a] = 0;
+			if (s.kind != CG_AGG_SUM || s.is_float) continue;
+			__int128 bound = 1;
+			bool ok = true;
+			for (int f = 0; f < s.nfactors && ok; f++)
+			{
+				int c = s.column[f];
+				if (unknown[c]) { ok = false; break; }
+				if (cmin[c] > cmax[c]) { bound = 0; continue; }   /* no values at all */
+				__int128 lo = (__int128) s.a[f] + (__int128) s.b[f] * cmin[c];
+				__int128 hi = (__int128) s.a[f] + (__int128) s.b[f] * cmax[c];
+				__int128 m = std::max(lo < 0 ? -lo : lo, hi < 0 ? -hi : hi);
+				bound *= m;
+				if (bound > ((__int128) 1 << 62)) ok = false;
+			}
+			if (ok) term_abs_bound[a] = bound == 0 ? 1 : (int64_t) bound;
+		}
+	return CG_OK;
+}
+
+/* ------------------------------------------------------------------------------ *
+ *  R1/R4: staging.  ColumnarStorageRead (columnar_storage.c:463-492) copies `amount`
+ *  bytes at a logical offset out of consecutive pages, one memcpy per page, after
+ *  checking pd_lower (ReadFromBlock :669-689).
+ * ------------------------------------------------------------------------------ */
+static int storage_read(const uint8_t *pages, uint64_t nblocks, uint64_t logical, uint8_t *out, uint64_t amount)
+{
+	uint64_t done = 0;
+	while (done < amount)
+	{
+		uint64_t L = logical + done;
+		uint64_t blockno = L / CG_BYTES_PER_PAGE;
+		uint32_t offset = CG_PAGE_HEADER + (uint32_t) (L % CG_BYTES_PER_PAGE);
+		uint64_t n = std::min<uint64_t>(amount - done, CG_BLCKSZ - offset);
+		if (blockno >= nblocks) return -1;
+		const uint8_t *page = pages + blockno * CG_BLCKSZ;
+		uint16_t pd_lower;
+		memcpy(&pd_lower, page + 12, 2);
+		if (pd_lower < offset + n) return -1;
+		memcpy(out + done, page + offset, n);
+		done += n;
+	}
+	return 0;
+}
+
+static inline uint64_t pad16(uint64_t x) { return (x + 15) & ~15ull; }
+
+struct StageItem   /* one (chunk group, staged column) */
+{
+	uint64_t exists_logical, value_logical;
+	uint32_t exists_len, value_len;
+};
+
+struct StagePlan
+{
+	std::vector<DevChunkCol> cols;      /* [ncg][nstaged] */
+	std::vector<StageItem> items;
+	std::vector<uint32_t> cg_rows;
+	std::vector<uint64_t> cg_begin;     /* arena offset where each chunk group starts; [ncg+1] */
+	uint64_t arena_bytes = 0;
+	uint64_t rows = 0;
+	bool any_nulls = false;
+};
+
+/* lays out the arena for the chunk groups picked by `select` (NULL = all) */
+static int plan_staging(const CgRelation *rel, const std::vector<int32_t> &staged,
+						const std::vector<std::vector<uint8_t>> *select, StagePlan *sp)
+{
+	uint64_t off = 0;
+	size_t ns = staged.size();
+	for (int si = 0; si < rel->nstripes; si++)
+	{
+		const CgStripe &s = rel->stripes[si];
+		for (uint32_t k = 0; k < s.chunk_count; k++)
+		{
+			if (select && !(*select)[si][k]) continue;
+			uint32_t rows = (uint32_t) rel->nodes[s.skipnode_base + k].row_count;
+			sp->cg_begin.push_back(off);
+			sp->cg_rows.push_back(rows);
+			sp->rows += rows;
+			for (size_t j = 0; j < ns; j++)
+			{
+				int c = staged[j];
+				DevChunkCol d;
+				StageItem it;
+				memset(&d, 0, sizeof d);
+				d.row_count = rows;
+				if ((uint32_t) c >= s.column_count)
+				{
+					/* column added after the stripe was written and without a default: all NULL
+					 * (columnar_reader.c:1626-1650) */
+					it.exists_logical = it.value_logical = 0;
+					it.exists_len = it.value_len = 0;
+					d.value_count = 0;
+				}
+				else
+				{
+					const CgSkipNode &n = rel->nodes[s.skipnode_base + (uint32_t) c * s.chunk_count + k];
+					if (n.compression_type != CG_COMPRESSION_NONE)
+						return cg_set_error(CG_EUNSUPPORTED,
+											"stripe %d column %d chunk %u is compressed (type %d); this round stages compression=none only",
+											si, c, k, n.compression_type);
+					if (n.row_count != rows) return cg_set_error(CG_ECORRUPT, "row count mismatch in chunk group");
+					if (n.exists_length * 8 < rows) return cg_set_error(CG_ECORRUPT, "insufficient data for reading boolean array");
+					int len = rel->columns[c].attlen;
+					if (n.decompressed_size % len != 0 || n.decompressed_size / len > rows || n.value_length != n.decompressed_size)
+						return cg_set_error(CG_ECORRUPT, "value stream of %llu bytes does not fit %u rows of %d bytes",
+											(unsigned long long) n.decompressed_size, rows, len);
+					it.exists_logical = s.file_offset + n.exists_offset;
+					it.value_logical = s.file_offset + n.value_offset;
+					it.exists_len = (uint32_t) n.exists_length;
+					it.value_len = (uint32_t) n.value_length;
+					d.value_count = (uint32_t) (n.decompressed_size / len);
+				}
+				d.exists_off = off; off += pad16(std::max<uint64_t>((rows + 7) / 8, it.exists_len)) + 16;
+				d.values_off = off; off += pad16(it.value_len) + 16;
+				if (d.value_count != rows)
+				{
+					d.rank_off = off; off += pad16(4ull * ((rows + 63) / 64));
+					sp->any_nulls = true;
+				}
+				sp->cols.push_back(d);
+				sp->items.push_back(it);
+			}
+		}
+	}
+	sp->cg_begin.push_back(off);
+	sp->arena_bytes = off;
+	return CG_OK;
+}
+
+/* fills [cg0, cg1) of the plan into a host buffer laid out like the arena from cg_begin[cg0] */
+static int fill_block(const CgRelation *rel, const StagePlan &sp, size_t ns, uint64_t cg0, uint64_t cg1,
+					  uint8_t *host, int nthreads)
+{
+	uint64_t base = sp.cg_begin[cg0];
+	int failed = 0;
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads)
+	for (int64_t g = (int64_t) cg0; g < (int64_t) cg1; g++)
+	{
+		for (size_t j = 0; j < ns; j++)
+		{
+			const DevChunkCol &d = sp.cols[g * ns + j];
+			const StageItem &it = sp.items[g * ns + j];
+			uint8_t *ex = host + (d.exists_off - base);
+			uint8_t *va = host + (d.values_off - base);
+			uint64_t exspan = d.values_off - d.exists_off;
+			memset(ex + (it.exists_len & ~15ull), 0, exspan - (it.exists_len & ~15ull));
+			if (it.exists_len && storage_read(rel->pages, rel->nblocks, it.exists_logical, ex, it.exists_len)) failed = 1;
+			uint64_t vaspan = pad16(it.value_len) + 16;
+			memset(va + (it.value_len & ~15ull), 0, vaspan - (it.value_len & ~15ull));
+			if (it.value_len && storage_read(rel->pages, rel->nblocks, it.value_logical, va, it.value_len)) failed = 1;
+		}
+	}
+	if (failed) return cg_set_error(CG_ECORRUPT, "attempt to read columnar data past pd_lower / end of relation");
+	return CG_OK;
+}
+
+/*
+ * Streams the planned chunk groups to the device arena through the pinned ring:
+ * host threads de-frame pages into pinned block b while block b-1 is in flight on the
+ * copy stream.  after_block(cg0, cg1) is called (on the host) once the H2D of that
+ * range has been enqueued; it may enqueue kernels on ctx->compute after making that
+ * stream wait on the returned event.
+ */
+template <typename F>
+static int stream_to_device(CgContext *ctx, const CgRelation *rel, const StagePlan &sp, size_t ns,
+							uint8_t *d_arena, F after_block)
+{
+	int rc = cg_ensure_pinned(ctx);
+	if (rc) return rc;
+	uint64_t ncg = sp.cg_rows.size();
+	uint64_t cg = 0;
+	int slot = 0;
+	while (cg < ncg)
+	{
+		uint64_t cg1 = cg;
+		while (cg1 < ncg && sp.cg_begin[cg1 + 1] - sp.cg_begin[cg] <= ctx->pinned_block_bytes) cg1++;
+		if (cg1 == cg)
+			return cg_set_error(CG_EUNSUPPORTED, "one chunk group (%llu bytes) exceeds the pinned block size",
+								(unsigned long long) (sp.cg_begin[cg + 1] - sp.cg_begin[cg]));
+		CG_CUDA(cudaEventSynchronize(ctx->pinned_free[slot]));
+		rc = fill_block(rel, sp, ns, cg, cg1, ctx->pinned[slot], ctx->stage_threads);
+		if (rc) return rc;
+		uint64_t bytes = sp.cg_begin[cg1] - sp.cg_begin[cg];
+		CG_CUDA(cudaMemcpyAsync(d_arena + sp.cg_begin[cg], ctx->pinned[slot], bytes, cudaMemcpyHostToDevice, ctx->copy));
+		CG_CUDA(cudaEventRecord(ctx->pinned_free[slot], ctx->copy));
+		rc = after_block(cg, cg1, ctx->pinned_free[slot]);
+		if (rc) return rc;
+		cg = cg1;
+		slot = (slot + 1) % CgContext::kPinnedBlocks;
+	}
+	return CG_OK;
+}
+
+extern "C" int cg_shard_stage(const CgRelation *rel, const int32_t *columns, int32_t ncolumns, CgShard **out)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx) return CG_EINVAL;
+	int rc = validate_relation(rel);
+	if (rc) return rc;
+	CgShard *sh = new CgShard();
+	sh->natts = rel->natts;
+	sh->columns.assign(rel->columns, rel->columns + rel->natts);
+	sh->slot_of_att.assign(rel->natts, -1);
+	if (columns && ncolumns > 0)
+	{
+		for (int i = 0; i < ncolumns; i++)
+		{
+			if (columns[i] < 0 || columns[i] >= rel->natts) { delete sh; return cg_set_error(CG_EINVAL, "column %d", columns[i]); }
+			if (sh->slot_of_att[columns[i]] >= 0) continue;
+			sh->slot_of_att[columns[i]] = (int32_t) sh->staged.size();
+			sh->staged.push_back(columns[i]);
+		}
+	}
+	else
+		for (int c = 0; c < rel->natts; c++) { sh->slot_of_att[c] = c; sh->staged.push_back(c); }
+	if (sh->staged.size() > 255) { delete sh; return cg_set_error(CG_EUNSUPPORTED, "more than 255 staged columns"); }
+	for (int c : sh->staged)
+	{
+		int l = rel->columns[c].attlen;
+		if (l != 1 && l != 2 && l != 4 && l != 8) { delete sh; return cg_set_error(CG_EUNSUPPORTED, "column %d: attlen %d", c, l); }
+	}
+
+	StagePlan sp;
+	rc = plan_staging(rel, sh->staged, nullptr, &sp);
+	if (rc) { delete sh; return rc; }
+	size_t ns = sh->staged.size();
+	sh->rows = sp.rows;
+	sh->nchunkgroups = sp.cg_rows.size();
+	sh->cg_rows = sp.cg_rows;
+	sh->h_chunkcols = sp.cols;
+	sh->arena_bytes = sp.arena_bytes;
+	sh->stripes.assign(rel->stripes, rel->stripes + rel->nstripes);
+	sh->nodes.assign(rel->nodes, rel->nodes + rel->nnodes);
+	uint64_t first = 0;
+	for (int si = 0; si < rel->nstripes; si++) { sh->stripe_first_cg.push_back(first); first += rel->stripes[si].chunk_count; }
+
+	if (cudaMalloc(&sh->d_arena, std::max<uint64_t>(sp.arena_bytes, 16)) != cudaSuccess ||
+		cudaMalloc(&sh->d_chunkcols, std::max<size_t>(sp.cols.size(), 1) * sizeof(DevChunkCol)) != cudaSuccess ||
+		cudaMalloc(&sh->d_selected, std::max<uint64_t>(sh->nchunkgroups, 1) * sizeof(uint32_t)) != cudaSuccess)
+	{
+		cg_shard_free(sh);
+		return cg_set_error(CG_ENOMEM, "cudaMalloc of %llu bytes for the shard arena failed", (unsigned long long) sp.arena_bytes);
+	}
+	cudaError_t e = cudaMemcpyAsync(sh->d_chunkcols, sp.cols.data(), sp.cols.size() * sizeof(DevChunkCol), cudaMemcpyHostToDevice, ctx->copy);
+	if (e != cudaSuccess) { cg_shard_free(sh); return cg_set_error(CG_ECUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(e)); }
+	rc = stream_to_device(ctx, rel, sp, ns, sh->d_arena, [&](uint64_t, uint64_t, cudaEvent_t) { return CG_OK; });
+	if (rc == CG_OK && sp.any_nulls)
+	{
+		/* rank directories (K1 prefix popcount), once per staged shard */
+		cudaError_t e2 = cudaStreamSynchronize(ctx->copy);
+		if (e2 != cudaSuccess) rc = cg_set_error(CG_ECUDA, "%s", cudaGetErrorString(e2));
+		else rc = cg_launch_rank(ctx, sh->d_arena, sh->d_chunkcols, 0, sp.cols.size(), ctx->compute);
+	}
+	if (rc == CG_OK)
+	{
+		cudaError_t e2 = cudaStreamSynchronize(ctx->copy);
+		if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(ctx->compute);
+		if (e2 != cudaSuccess) rc = cg_set_error(CG_ECUDA, "%s", cudaGetErrorString(e2));
+	}
+	if (rc) { cg_shard_free(sh); return rc; }
+	*out = sh;
+	return CG_OK;
+}
+
+extern "C" void cg_shard_free(CgShard *sh)
+{
+	if (!sh) return;
+	cudaFree(sh->d_arena);
+	cudaFree(sh->d_chunkcols);
+	cudaFree(sh->d_selected);
+	delete sh;
+}
+
+extern "C" uint64_t cg_shard_device_bytes(const CgShard *sh) { return sh ? sh->arena_bytes : 0; }
+extern "C" uint64_t cg_shard_rows(const CgShard *sh) { return sh ? sh->rows : 0; }
+
+/* ------------------------------------------------------------------------------ *
+ *  Scan driver.
+ * ------------------------------------------------------------------------------ */
+static int check_error_flags(CgPartial *p, unsigned long long flags)
+{
+	if (flags & CG_ERRFLAG_TABLE_FULL)
+		return cg_set_error(CG_ETABLEFULL, "group table (%llu slots) is full: retry with a larger expected_groups",
+							(unsigned long long) p->capacity);
+	if (flags & CG_ERRFLAG_NULL_MULTIKEY)
+		return cg_set_error(CG_EUNSUPPORTED, "NULL in a two-column group key");
+	if (flags & CG_ERRFLAG_KEY_RANGE)
+		return cg_set_error(CG_EINVAL, "group key outside [key_min, key_max] given to cg_partial_create");
+	if (flags & CG_ERRFLAG_SUM_BOUND)
+		return cg_set_error(CG_EINVAL, "sum argument exceeds term_abs_bound");
+	return CG_OK;
+}
+
+static int read_stats(CgContext *ctx, CgPartial *p, unsigned long long before[3], CgScanStats *stats)
+{
+	unsigned long long after[3];
+	CG_CUDA(cudaMemcpyAsync(after, p->d_stats, sizeof after, cudaMemcpyDeviceToHost, ctx->compute));
+	CG_CUDA(cudaStreamSynchronize(ctx->compute));
+	int rc = check_error_flags(p, after[2]);
+	if (rc) return rc;
+	if (stats)
+	{
+		stats->rows_scanned = (int64_t) (after[0] - before[0]);
+		stats->rows_removed_by_filter = (int64_t) (after[1] - before[1]);
+		stats->rows_passed = stats->rows_scanned - stats->rows_removed_by_filter;
+	}
+	return CG_OK;
+}
+
+extern "C" int cg_scan_shard(const CgShard *sh, const CgScanDesc *desc, CgPartial *into, CgScanStats *stats)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx) return CG_EINVAL;
+	if (!sh || !desc || !into) return cg_set_error(CG_EINVAL, "NULL argument");
+	KPlan plan;
+	bool all8 = false;
+	int rc = cg_build_plan(desc, sh->columns.data(), sh->natts, &sh->slot_of_att, into, &plan, &all8);
+	if (rc) return rc;
+
+	/* K2 on the host: SelectedChunkMask per stripe.  The list of surviving chunk groups is
+	 * kept on the device and reused while the WHERE list stays the same. */
+	CgShard *msh = const_cast<CgShard *>(sh);
+	bool same = msh->sel_valid && msh->sel_pushdown == desc->enable_qual_pushdown && msh->sel_nquals == desc->nquals &&
+				memcmp(msh->sel_quals, desc->quals, sizeof(CgQual) * desc->nquals) == 0;
+	if (!same)
+	{
+		std::vector<uint32_t> selected;
+		selected.reserve(sh->nchunkgroups);
+		int64_t filtered = 0;
+		std::vector<uint8_t> mask;
+		for (size_t si = 0; si < sh->stripes.size(); si++)
+		{
+			const CgStripe &s = sh->stripes[si];
+			mask.resize(s.chunk_count);
+			stripe_chunk_mask(s, sh->nodes.data(), sh->columns.data(), sh->natts, desc, mask.data(), &filtered);
+			for (uint32_t k = 0; k < s.chunk_count; k++)
+				if (mask[k]) selected.push_back((uint32_t) (sh->stripe_first_cg[si] + k));
+		}
+		CG_CUDA(cudaStreamSynchronize(ctx->compute));     /* an earlier scan may still read the old list */
+		if (!selected.empty())
+			CG_CUDA(cudaMemcpy(msh->d_selected, selected.data(), selected.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+		msh->h_selected.swap(selected);
+		msh->sel_filtered = filtered;
+		msh->sel_pushdown = desc->enable_qual_pushdown;
+		msh->sel_nquals = desc->nquals;
+		memcpy(msh->sel_quals, desc->quals, sizeof(CgQual) * desc->nquals);
+		msh->sel_valid = true;
+	}
+	const std::vector<uint32_t> &selected = sh->h_selected;
+	int64_t filtered = sh->sel_filtered;
+	uint64_t bytes = 0;
+	if (stats)
+		for (uint32_t cg : selected)
+			for (int c = 0; c < plan.ncols; c++) bytes += sh->algorithmic_bytes_per_cg_col(cg, plan.slot[c]);
+	unsigned long long before[3] = {0, 0, 0};
+	if (stats)
+	{
+		CG_CUDA(cudaMemcpyAsync(before, into->d_stats, sizeof before, cudaMemcpyDeviceToHost, ctx->compute));
+		CG_CUDA(cudaStreamSynchronize(ctx->compute));
+	}
+	if (!selected.empty())
+	{
+		plan.arena = sh->d_arena;
+		plan.chunkcols = sh->d_chunkcols;
+		plan.nstaged = (int32_t) sh->staged.size();
+		plan.selected = sh->d_selected;
+		plan.nselected = (uint32_t) selected.size();
+		if (stats) CG_CUDA(cudaEventRecord(ctx->ev_a, ctx->compute));
+		rc = cg_prof_mark(ctx, ctx->compute);
+		if (rc) return rc;
+		rc = cg_launch_scan(ctx, plan, true, all8, ctx->compute);
+		if (rc) return rc;
+		rc = cg_prof_mark(ctx, ctx->compute);
+		if (rc) return rc;
+		if (stats) CG_CUDA(cudaEventRecord(ctx->ev_b, ctx->compute));
+	}
+	if (stats)
+	{
+		memset(stats, 0, sizeof *stats);
+		rc = read_stats(ctx, into, before, stats);
+		if (rc) return rc;
+		stats->chunk_groups_filtered = filtered;
+		stats->chunk_groups_scanned = (int64_t) selected.size();
+		stats->bytes_scanned = (int64_t) bytes;
+		if (!selected.empty())
+		{
+			float ms = 0;
+			CG_CUDA(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+			stats->kernel_ms = ms;
+		}
+	}
+	return CG_OK;
+}
+
+/*
+ * End to end on host buffers: skip -> stage only the plan's columns of the surviving
+ * chunk groups through the pinned ring -> one fused kernel launch per block, the
+ * kernel of block b overlapping the H2D of block b+1.
+ */
+extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, CgPartial *into, CgScanStats *stats)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx) return CG_EINVAL;
+	if (!desc || !into) return cg_set_error(CG_EINVAL, "NULL argument");
+	int rc = validate_relation(rel);
+	if (rc) return rc;
+
+	/* projection */
+	std::vector<int32_t> staged, slot_of_att(rel->natts, -1);
+	auto need = [&](int c) { if (slot_of_att[c] < 0) { slot_of_att[c] = (int32_t) staged.size(); staged.push_back(c); } };
+	for (int q = 0; q < desc->nquals; q++) if (desc->quals[q].column >= 0 && desc->quals[q].column < rel->natts) need(desc->quals[q].column);
+	for (int g = 0; g < desc->ngroup_cols; g++) if (desc->group_cols[g] >= 0 && desc->group_cols[g] < rel->natts) need(desc->group_cols[g]);
+	for (int a = 0; a < desc->naggs; a++)
+		for (int f = 0; f < desc->aggs[a].nfactors && f < 3; f++)
+			if (desc->aggs[a].column[f] >= 0 && desc->aggs[a].column[f] < rel->natts) need(desc->aggs[a].column[f]);
+	if (staged.empty()) need(0);   /* count(*) only: the reference still reads the first column's skip nodes; we read its chunk row counts */
+
+	KPlan plan;
+	bool all8 = false;
+	rc = cg_build_plan(desc, rel->columns, rel->natts, &slot_of_att, into, &plan, &all8);
+	if (rc) return rc;
+
+	std::vector<std::vector<uint8_t>> select(rel->nstripes);
+	int64_t filtered = 0;
+	for (int si = 0; si < rel->nstripes; si++)
+	{
+		select[si].resize(rel->stripes[si].chunk_count);
+		stripe_chunk_mask(rel->stripes[si], rel->nodes, rel->columns, rel->natts, desc, select[si].data(), &filtered);
+	}
+	StagePlan sp;
+	rc = plan_staging(rel, staged, &select, &sp);
+	if (rc) return rc;
+	size_t ns = staged.size();
+	uint64_t ncg = sp.cg_rows.size();
+
+	unsigned long long before[3] = {0, 0, 0};
+	if (stats)
+	{
+		CG_CUDA(cudaMemcpyAsync(before, into->d_stats, sizeof before, cudaMemcpyDeviceToHost, ctx->compute));
+		CG_CUDA(cudaStreamSynchronize(ctx->compute));
+	}
+	uint64_t bytes = 0;
+	for (uint64_t g = 0; g < ncg; g++)
+		for (int c = 0; c < plan.ncols; c++)
+		{
+			const DevChunkCol &d = sp.cols[g * ns + plan.slot[c]];
+			bytes += (uint64_t) d.value_count * plan.len[c] + (d.row_count + 7) / 8;
+		}
+
+	uint8_t *d_arena = nullptr;
+	DevChunkCol *d_cols = nullptr;
+	uint32_t *d_ids = nullptr;
+	if (ncg > 0)
+	{
+		CG_CUDA(cudaMallocAsync((void **) &d_arena, std::max<uint64_t>(sp.arena_bytes, 16), ctx->copy));
+		CG_CUDA(cudaMallocAsync((void **) &d_cols, sp.cols.size() * sizeof(DevChunkCol), ctx->copy));
+		CG_CUDA(cudaMallocAsync((void **) &d_ids, ncg * sizeof(uint32_t), ctx->copy));
+		std::vector<uint32_t> ids(ncg);
+		for (uint64_t g = 0; g < ncg; g++) ids[g] = (uint32_t) g;
+		CG_CUDA(cudaMemcpyAsync(d_cols, sp.cols.data(), sp.cols.size() * sizeof(DevChunkCol), cudaMemcpyHostToDevice, ctx->copy));
+		CG_CUDA(cudaMemcpyAsync(d_ids, ids.data(), ncg * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy));
+		CG_CUDA(cudaStreamSynchronize(ctx->copy));   /* ids / cols are pageable vectors about to go out of scope */
+		plan.arena = d_arena;
+		plan.chunkcols = d_cols;
+		plan.nstaged = (int32_t) ns;
+		if (stats) CG_CUDA(cudaEventRecord(ctx->ev_a, ctx->compute));
+		rc = stream_to_device(ctx, rel, sp, ns, d_arena, [&](uint64_t cg0, uint64_t cg1, cudaEvent_t copied) -> int {
+			CG_CUDA(cudaStreamWaitEvent(ctx->compute, copied, 0));
+			if (sp.any_nulls)
+			{
+				int r = cg_launch_rank(ctx, d_arena, d_cols, cg0 * ns, (cg1 - cg0) * ns, ctx->compute);
+				if (r) return r;
+			}
+			KPlan blk = plan;
+			blk.selected = d_ids + cg0;
+			blk.nselected = (uint32_t) (cg1 - cg0);
+			int r = cg_prof_mark(ctx, ctx->compute);
+			if (r) return r;
+			r = cg_launch_scan(ctx, blk, sp.any_nulls, all8, ctx->compute);
+			if (r) return r;
+			return cg_prof_mark(ctx, ctx->compute);
+		});
+		if (stats && rc == CG_OK) CG_CUDA(cudaEventRecord(ctx->ev_b, ctx->compute));
+		/* frees are ordered after the kernels on the compute stream */
+		cudaFreeAsync(d_arena, ctx->compute);
+		cudaFreeAsync(d_cols, ctx->compute);
+		cudaFreeAsync(d_ids, ctx->compute);
+		if (rc) return rc;
+	}
+	if (stats)
+	{
+		memset(stats, 0, sizeof *stats);
+		rc = read_stats(ctx, into, before, stats);
+		if (rc) return rc;
+		stats->chunk_groups_filtered = filtered;
+		stats->chunk_groups_scanned = (int64_t) ncg;
+		stats->bytes_scanned = (int64_t) bytes;
+		if (ncg > 0)
+		{
+			float ms = 0;
+			CG_CUDA(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+			stats->kernel_ms = ms;   /* here: first kernel start to last kernel end, H2D overlapped */
+			stats->h2d_bytes = (int64_t) (sp.arena_bytes + sp.cols.size() * sizeof(DevChunkCol) + ncg * sizeof(uint32_t));
+		}
+	}
+	return CG_OK;
+}
+
+/* ------------------------------------------------------------------------------ *
+ *  Results.
+ * ------------------------------------------------------------------------------ */
+static int ensure_out(CgPartial *p, uint64_t cap)
+{
+	if (p->out_capacity >= cap && p->d_out_keys) return CG_OK;
+	cudaFree(p->d_out_keys); cudaFree(p->d_out_words); cudaFree(p->d_out_nulls);
+	p->d_out_keys = nullptr; p->d_out_words = nullptr; p->d_out_nulls = nullptr;
+	if (cudaMalloc(&p->d_out_keys, cap * sizeof(int64_t)) != cudaSuccess ||
+		cudaMalloc(&p->d_out_words, cap * p->nwords * sizeof(uint64_t)) != cudaSuccess ||
+		cudaMalloc(&p->d_out_nulls, cap) != cudaSuccess)
+		return cg_set_error(CG_ENOMEM, "cudaMalloc for %llu result rows failed", (unsigned long long) cap);
+	p->out_capacity = cap;
+	return CG_OK;
+}
+
+static int pending_errors(CgContext *ctx, CgPartial *p)
+{
+	unsigned long long st[3];
+	CG_CUDA(cudaMemcpyAsync(st, p->d_stats, sizeof st, cudaMemcpyDeviceToHost, ctx->compute));
+	CG_CUDA(cudaStreamSynchronize(ctx->compute));
+	return check_error_flags(p, st[2]);
+}
+
+extern "C" int cg_partial_ngroups(CgPartial *p, int64_t *ngroups)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx || !p) return CG_EINVAL;
+	int rc = pending_errors(ctx, p);
+	if (rc) return rc;
+	rc = cg_launch_export(p, 0, nullptr, nullptr, nullptr, p->d_out_count, ctx->compute);
+	if (rc) return rc;
+	unsigned long long n = 0;
+	CG_CUDA(cudaMemcpyAsync(&n, p->d_out_count, sizeof n, cudaMemcpyDeviceToHost, ctx->compute));
+	CG_CUDA(cudaStreamSynchronize(ctx->compute));
+	*ngroups = (int64_t) n;
+	return CG_OK;
+}
+
+static inline uint64_t f8_unordered(uint64_t u)
+{
+	return (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+}
+
+extern "C" int cg_partial_fetch(CgPartial *p, int64_t capacity, int64_t *keys, uint8_t *key_nulls,
+								int64_t *sum_hi, uint64_t *sum_lo, int64_t *count, int64_t *minmax,
+								double *fsum, int64_t *ngroups)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx || !p) return CG_EINVAL;
+	int rc = pending_errors(ctx, p);
+	if (rc) return rc;
+	if (capacity < 0) return cg_set_error(CG_EINVAL, "negative capacity");
+	rc = ensure_out(p, std::max<uint64_t>((uint64_t) capacity, 1));
+	if (rc) return rc;
+	rc = cg_launch_export(p, (uint64_t) capacity, p->d_out_keys, p->d_out_nulls, p->d_out_words, p->d_out_count, ctx->compute);
+	if (rc) return rc;
+	unsigned long long n = 0;
+	CG_CUDA(cudaMemcpyAsync(&n, p->d_out_count, sizeof n, cudaMemcpyDeviceToHost, ctx->compute));
+	CG_CUDA(cudaStreamSynchronize(ctx->compute));
+	if (ngroups) *ngroups = (int64_t) n;
+	if ((int64_t) n > capacity)
+		return cg_set_error(CG_EINVAL, "%llu groups do not fit the caller's capacity %lld", n, (long long) capacity);
+	if (n == 0) return CG_OK;
+	std::vector<int64_t> hk(n);
+	std::vector<uint8_t> hn(n);
+	std::vector<uint64_t> hw((size_t) n * p->nwords);
+	CG_CUDA(cudaMemcpy(hk.data(), p->d_out_keys, n * sizeof(int64_t), cudaMemcpyDeviceToHost));
+	CG_CUDA(cudaMemcpy(hn.data(), p->d_out_nulls, n, cudaMemcpyDeviceToHost));
+	CG_CUDA(cudaMemcpy(hw.data(), p->d_out_words, (size_t) n * p->nwords * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+	int na = p->desc.naggs;
+	for (uint64_t i = 0; i < n; i++)
+	{
+		if (keys) keys[i] = hk[i];
+		if (key_nulls) key_nulls[i] = hn[i];
+		const uint64_t *w = &hw[i * p->nwords];
+		int64_t rows = (int64_t) w[0];
+		for (int a = 0; a < na; a++)
+		{
+			const KAgg &k = p->aggs[a];
+			size_t o = i * na + a;
+			int64_t hi = 0; uint64_t lo = 0; int64_t cnt = 0; int64_t mm = 0; double fs = 0;
+			switch (k.kind)
+			{
+				case CG_AGG_COUNT_STAR: cnt = rows; break;
+				case CG_AGG_COUNT: cnt = rows - (int64_t) w[k.nullword]; break;
+				case CG_AGG_SUM:
+					cnt = rows - (int64_t) w[k.nullword];
+					if (k.is_float) memcpy(&fs, &w[k.word0], 8);
+					else
+					{
+						__int128 s;
+						if (k.nlimbs == 1) s = (__int128) (int64_t) w[k.word0];
+						else s = (__int128) (unsigned __int128) w[k.word0] + ((__int128) (int64_t) w[k.word0 + 1] << 32);
+						hi = (int64_t) (s >> 64); lo = (uint64_t) s;
+					}
+					break;
+				default:
+					cnt = rows - (int64_t) w[k.nullword];
+					mm = k.is_float ? (int64_t) f8_unordered(w[k.word0]) : (int64_t) w[k.word0];
+					break;
+			}
+			if (sum_hi) sum_hi[o] = hi;
+			if (sum_lo) sum_lo[o] = lo;
+			if (count) count[o] = cnt;
+			if (minmax) minmax[o] = mm;
+			if (fsum) fsum[o] = fs;
+		}
+	}
+	return CG_OK;
+}
+
+extern "C" int cg_partial_export_device(CgPartial *p, int64_t capacity, int64_t *d_keys, uint8_t *d_key_nulls,
+										uint64_t *d_words, int64_t *nrows)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx || !p) return CG_EINVAL;
+	int rc = pending_errors(ctx, p);
+	if (rc) return rc;
+	rc = cg_launch_export(p, (uint64_t) capacity, d_keys, d_key_nulls, d_words, p->d_out_count, ctx->compute);
+	if (rc) return rc;
+	unsigned long long n = 0;
+	CG_CUDA(cudaMemcpyAsync(&n, p->d_out_count, sizeof n, cudaMemcpyDeviceToHost, ctx->compute));
+	CG_CUDA(cudaStreamSynchronize(ctx->compute));
+	if (nrows) *nrows = (int64_t) n;
+	if ((int64_t) n > capacity) return cg_set_error(CG_EINVAL, "%llu rows exceed capacity %lld", n, (long long) capacity);
+	return CG_OK;
+}
+
+extern "C" int cg_partial_merge_rows(CgPartial *p, const int64_t *d_keys, const uint8_t *d_key_nulls,
+									 const uint64_t *d_words, int64_t nrows)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx || !p) return CG_EINVAL;
+	int rc = cg_launch_merge(p, d_keys, d_key_nulls, d_words, nrows, ctx->compute);
+	if (rc) return rc;
+	CG_CUDA(cudaStreamSynchronize(ctx->compute));
+	return pending_errors(ctx, p);
+}
+
+extern "C" int cg_partial_dense_words(CgPartial *p, uint64_t **d_words, int64_t *total_words, int32_t *stride)
+{
+	if (!p) return cg_set_error(CG_EINVAL, "NULL partial");
+	if (p->mode == CG_MODE_HASH) return cg_set_error(CG_EINVAL, "not a direct-indexed table");
+	*d_words = p->d_table;
+	if (total_words) *total_words = (int64_t) (p->entries * (uint64_t) p->stride);
+	if (stride) *stride = p->stride;
+	return CG_OK;
+}

@@ -1,0 +1,210 @@
+/*
+ * cg_internal.h -- shared declarations of libcitus_gpu.so (host C++ and CUDA).
+ * Not part of the C-ABI (include/citus_gpu.h is).
+ */
+#ifndef CG_INTERNAL_H
+#define CG_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "citus_gpu.h"
+
+#define CG_BLCKSZ 8192
+#define CG_PAGE_HEADER 24
+#define CG_BYTES_PER_PAGE (CG_BLCKSZ - CG_PAGE_HEADER)
+#define CG_FIRST_LOGICAL_OFFSET (2ull * CG_BYTES_PER_PAGE)
+
+int cg_set_error(int code, const char *fmt, ...);
+
+#define CG_CUDA(call)                                                                        \
+	do {                                                                                     \
+		cudaError_t e__ = (call);                                                            \
+		if (e__ != cudaSuccess)                                                              \
+			return cg_set_error(CG_ECUDA, "%s failed: %s (%s:%d)", #call,                     \
+								cudaGetErrorString(e__), __FILE__, __LINE__);                 \
+	} while (0)
+
+struct CgContext
+{
+	int device = -1;
+	int sm_count = 0;
+	cudaStream_t compute = nullptr;  /* kernels */
+	cudaStream_t copy = nullptr;     /* side stream for H2D staging */
+	/* pinned staging ring */
+	static const int kPinnedBlocks = 4;
+	size_t pinned_block_bytes = 0;
+	uint8_t *pinned[kPinnedBlocks] = {nullptr, nullptr, nullptr, nullptr};
+	cudaEvent_t pinned_free[kPinnedBlocks] = {nullptr, nullptr, nullptr, nullptr};
+	cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+	int stage_threads = 16;
+	cudaStream_t own_compute = nullptr;
+	/* per-launch profiling */
+	bool profiling = false;
+	std::vector<cudaEvent_t> prof_events;   /* pairs */
+	size_t prof_used = 0;
+};
+int cg_prof_mark(CgContext *ctx, cudaStream_t stream);   /* records the next event of the pool when profiling */
+CgContext *cg_ctx(void);   /* NULL + error set if cg_init has not run */
+int cg_ensure_pinned(CgContext *ctx);
+
+/* ------------------------------------------------------------------------------ *
+ *  HBM layout of a staged shard.
+ *  arena: every (chunk group, staged column) owns
+ *     [exists bitmap, padded with zero bits to a multiple of 16 B]
+ *     [value stream, padded to a multiple of 16 B]
+ *     [rank directory: uint32 per 64 rows = number of non-NULL rows before the block]
+ *                                       (only when the chunk has NULLs)
+ *  all 16-byte aligned, in chunk-group-major order (so a block of consecutive chunk
+ *  groups is one contiguous H2D copy).
+ * ------------------------------------------------------------------------------ */
+struct DevChunkCol
+{
+	uint64_t values_off;
+	uint64_t exists_off;
+	uint64_t rank_off;      /* valid iff value_count != row_count */
+	uint32_t value_count;   /* non-NULL rows = decompressed_size / attlen */
+	uint32_t row_count;
+};
+
+struct CgShard
+{
+	int natts = 0;
+	std::vector<CgColumnDesc> columns;       /* all attributes */
+	std::vector<int32_t> staged;             /* staged attribute indexes */
+	std::vector<int32_t> slot_of_att;        /* att -> staged slot or -1 */
+	uint64_t rows = 0;
+	uint64_t nchunkgroups = 0;
+	uint8_t *d_arena = nullptr;
+	uint64_t arena_bytes = 0;
+	DevChunkCol *d_chunkcols = nullptr;      /* [nchunkgroups][nstaged] */
+	std::vector<DevChunkCol> h_chunkcols;
+	std::vector<uint32_t> cg_rows;           /* rows per chunk group */
+	/* host copy of the metadata needed for chunk-group skipping */
+	std::vector<CgStripe> stripes;
+	std::vector<CgSkipNode> nodes;
+	std::vector<uint64_t> stripe_first_cg;   /* first chunk-group id of each stripe */
+	/* chunk groups surviving the last WHERE list (SelectedChunkMask), cached on the device */
+	uint32_t *d_selected = nullptr;
+	std::vector<uint32_t> h_selected;
+	bool sel_valid = false;
+	int32_t sel_pushdown = 0, sel_nquals = 0;
+	CgQual sel_quals[CG_MAX_QUALS];
+	int64_t sel_filtered = 0;
+	uint64_t algorithmic_bytes_per_cg_col(uint64_t cg, int slot) const
+	{
+		const DevChunkCol &c = h_chunkcols[cg * staged.size() + slot];
+		return (uint64_t) c.value_count * columns[staged[slot]].attlen + (c.row_count + 7) / 8;
+	}
+};
+
+/* ------------------------------------------------------------------------------ *
+ *  Kernel plan (passed by value as a __grid_constant__ parameter).
+ * ------------------------------------------------------------------------------ */
+#define CG_KMAX_COLS 8
+#define CG_KMAX_WORDS 16
+
+enum { CG_MODE_GLOBAL = 0, CG_MODE_DENSE = 1, CG_MODE_HASH = 2 };
+
+/* word ops reuse CG_WORD_* from the public header */
+
+struct KAgg
+{
+	int8_t kind;        /* CG_AGG_* */
+	int8_t nfactors;
+	int8_t is_float;
+	int8_t nlimbs;      /* integer SUM: 1 = whole sum fits int64, 2 = (low32, high) limb words */
+	int8_t pcol[3];     /* plan-column index of every factor */
+	int8_t word0;       /* first accumulator word (count(x): its NULL-count word) */
+	int8_t nullword;    /* word counting NULL inputs among the group's rows:
+						 * non-NULL inputs = rows in group (word 0) - this word */
+	int8_t pad[3];
+	int64_t a[3];
+	int64_t b[3];
+	int64_t bound;      /* nlimbs == 1: every |term| must be <= bound */
+};
+
+struct KPlan
+{
+	const uint8_t *arena;
+	const DevChunkCol *chunkcols;
+	const uint32_t *selected;     /* chunk-group ids to scan */
+	uint32_t nselected;
+	int32_t nstaged;
+
+	int32_t ncols;                /* plan columns (deduplicated) */
+	uint8_t slot[CG_KMAX_COLS];   /* staged slot */
+	uint8_t len[CG_KMAX_COLS];
+	uint8_t isfloat[CG_KMAX_COLS];
+
+	int32_t nquals;
+	uint8_t qcol[CG_MAX_QUALS];
+	uint8_t qop[CG_MAX_QUALS];
+	int64_t qk[CG_MAX_QUALS];
+
+	int32_t ngroup;
+	uint8_t gcol[CG_MAX_GROUP_COLS];
+
+	int32_t naggs;
+	KAgg aggs[CG_MAX_AGGS];
+
+	/* group table */
+	int32_t mode;
+	int32_t nwords;               /* accumulator words per group; word 0 = rows in group */
+	int32_t stride;               /* 64-bit words per entry (hash: key + words, padded) */
+	uint64_t *table;              /* dense: [capacity+1][stride]; hash: [capacity+2][stride] */
+	uint64_t capacity;            /* hash: power of two */
+	int64_t key_min;              /* dense */
+	uint8_t wordop[CG_KMAX_WORDS];
+
+	unsigned long long *stats;    /* [0] rows scanned [1] rows removed [2] error flags */
+};
+
+#define CG_HASH_EMPTY ((int64_t) 0x8000000000000000ull)
+#define CG_ERRFLAG_TABLE_FULL 1ull
+#define CG_ERRFLAG_NULL_MULTIKEY 2ull
+#define CG_ERRFLAG_KEY_RANGE 4ull
+#define CG_ERRFLAG_SUM_BOUND 8ull
+
+struct CgPartial
+{
+	CgScanDesc desc;
+	std::vector<CgColumnDesc> columns;
+	int mode = CG_MODE_GLOBAL;
+	int nwords = 1;
+	int stride = 1;
+	uint64_t capacity = 0;      /* addressable slots (dense: domain size, hash: pow2) */
+	uint64_t entries = 0;       /* allocated entries incl. the special ones */
+	int64_t key_min = 0, key_max = -1;
+	int64_t max_rows = 0;
+	uint8_t wordop[CG_KMAX_WORDS];
+	KAgg aggs[CG_MAX_AGGS];
+	uint64_t *d_table = nullptr;
+	unsigned long long *d_stats = nullptr;   /* 8 words */
+	/* scratch for export */
+	int64_t *d_out_keys = nullptr;
+	uint64_t *d_out_words = nullptr;
+	uint8_t *d_out_nulls = nullptr;
+	unsigned long long *d_out_count = nullptr;
+	uint64_t out_capacity = 0;
+};
+
+/* cg_scan.cu */
+int cg_launch_scan(CgContext *ctx, const KPlan &plan, bool any_nulls, bool all8, cudaStream_t stream);
+int cg_launch_rank(CgContext *ctx, const uint8_t *arena, const DevChunkCol *chunkcols, uint64_t first,
+				   uint64_t count, cudaStream_t stream);
+int cg_launch_table_init(CgPartial *p, cudaStream_t stream);
+int cg_launch_export(CgPartial *p, uint64_t out_capacity, int64_t *d_keys, uint8_t *d_nulls, uint64_t *d_words,
+					 unsigned long long *d_count, cudaStream_t stream);
+int cg_launch_merge(CgPartial *p, const int64_t *d_keys, const uint8_t *d_nulls, const uint64_t *d_words,
+					int64_t nrows, cudaStream_t stream);
+
+/* cg_plan.cpp */
+int cg_build_plan(const CgScanDesc *desc, const CgColumnDesc *columns, int natts,
+				  const std::vector<int32_t> *slot_of_att, CgPartial *partial, KPlan *plan,
+				  bool *all8);
+
+#endif

@@ -1,0 +1,310 @@
+/*
+ * cg_plan.cpp -- turns a CgScanDesc into the kernel plan and the accumulator-word layout
+ * of a partial aggregate.
+ *
+ * The worker half of each aggregate follows planner/multi_logical_optimizer.c:3160-3484
+ * (WorkerAggregateExpressionList): count -> count, sum -> sum, min/max -> min/max,
+ * avg -> sum + count (the caller asks for sum; the non-NULL count rides along as the
+ * aggregate's count word).  Transition semantics follow PostgreSQL's nodeAgg:
+ * strict transition functions skip NULL inputs; sum/min/max over no non-NULL input is NULL.
+ */
+#include <stdarg.h>
+#include <string.h>
+
+#include "cg_internal.h"
+
+static thread_local char g_errbuf[512];
+
+int cg_set_error(int code, const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_errbuf, sizeof g_errbuf, fmt, ap);
+	va_end(ap);
+	return code;
+}
+
+extern "C" const char *cg_last_error(void) { return g_errbuf; }
+
+static int validate_desc(const CgScanDesc *d, const CgColumnDesc *columns, int natts)
+{
+	if (d->nquals < 0 || d->nquals > CG_MAX_QUALS) return cg_set_error(CG_EINVAL, "nquals %d out of range", d->nquals);
+	if (d->naggs < 0 || d->naggs > CG_MAX_AGGS) return cg_set_error(CG_EINVAL, "naggs %d out of range", d->naggs);
+	if (d->ngroup_cols < 0 || d->ngroup_cols > CG_MAX_GROUP_COLS)
+		return cg_set_error(CG_EINVAL, "ngroup_cols %d out of range", d->ngroup_cols);
+	for (int c = 0; c < natts; c++)
+	{
+		int l = columns[c].attlen;
+		if (l != 1 && l != 2 && l != 4 && l != 8)
+			return cg_set_error(CG_EUNSUPPORTED, "column %d: attlen %d (only fixed-width by-value types)", c, l);
+		if (columns[c].type_class == CG_TYPE_FLOAT && l != 4 && l != 8)
+			return cg_set_error(CG_EINVAL, "column %d: float with attlen %d", c, l);
+	}
+	for (int q = 0; q < d->nquals; q++)
+	{
+		if (d->quals[q].column < 0 || d->quals[q].column >= natts)
+			return cg_set_error(CG_EINVAL, "qual %d: column %d out of range", q, d->quals[q].column);
+		if (d->quals[q].op < CG_OP_LT || d->quals[q].op > CG_OP_NE)
+			return cg_set_error(CG_EINVAL, "qual %d: bad operator", q);
+	}
+	for (int g = 0; g < d->ngroup_cols; g++)
+	{
+		int c = d->group_cols[g];
+		if (c < 0 || c >= natts) return cg_set_error(CG_EINVAL, "group column %d out of range", c);
+		if (columns[c].type_class == CG_TYPE_FLOAT)
+			return cg_set_error(CG_EUNSUPPORTED, "GROUP BY on a float column");
+		if (d->ngroup_cols == 2 && columns[c].attlen > 4)
+			return cg_set_error(CG_EUNSUPPORTED, "two-column GROUP BY needs columns of at most 4 bytes");
+	}
+	for (int a = 0; a < d->naggs; a++)
+	{
+		const CgAggSpec &s = d->aggs[a];
+		if (s.kind < CG_AGG_COUNT_STAR || s.kind > CG_AGG_MAX) return cg_set_error(CG_EINVAL, "aggregate %d: bad kind", a);
+		if (s.nfactors < 0 || s.nfactors > 3) return cg_set_error(CG_EINVAL, "aggregate %d: nfactors", a);
+		if (s.kind != CG_AGG_COUNT_STAR && s.nfactors == 0)
+			return cg_set_error(CG_EINVAL, "aggregate %d needs an argument", a);
+		for (int f = 0; f < s.nfactors; f++)
+		{
+			if (s.column[f] < 0 || s.column[f] >= natts)
+				return cg_set_error(CG_EINVAL, "aggregate %d: column out of range", a);
+			bool colf = columns[s.column[f]].type_class == CG_TYPE_FLOAT;
+			if (colf != (s.is_float != 0))
+				return cg_set_error(CG_EINVAL, "aggregate %d: integer/float mismatch with column %d", a, s.column[f]);
+		}
+	}
+	return CG_OK;
+}
+
+/*
+ * Accumulator words of a group: word 0 = rows in the group (count(*) and occupancy);
+ * then per aggregate
+ *   count(x)      1 ADD word counting NULL inputs (count = rows - it)
+ *   sum(int)      1 ADD word if |term| * max_rows < 2^63 (term_abs_bound given), else the
+ *                 two-limb form (low 32 bits unsigned, term >> 32 signed), + NULL-input count
+ *   sum(float8)   1 FADD word + NULL-input count
+ *   min/max       1 MIN/MAX (FMIN/FMAX on the order-preserving float encoding) + NULL-input count
+ * Counting the NULL inputs instead of the non-NULL ones keeps NULL-free data (the common
+ * case) at one atomic per aggregate and row, while "no non-NULL input => SQL NULL" and
+ * count(x) stay exact: non-NULL inputs = rows in group - NULL inputs.
+ */
+static int layout_partial(CgPartial *p, const CgColumnDesc *columns)
+{
+	const CgScanDesc &d = p->desc;
+	int nw = 1;
+	memset(p->wordop, CG_WORD_ADD, sizeof p->wordop);
+	for (int a = 0; a < d.naggs; a++)
+	{
+		const CgAggSpec &s = d.aggs[a];
+		KAgg &k = p->aggs[a];
+		memset(&k, 0, sizeof k);
+		k.kind = (int8_t) s.kind;
+		k.nfactors = (int8_t) s.nfactors;
+		k.is_float = (int8_t) (s.is_float != 0);
+		for (int f = 0; f < 3; f++) { k.a[f] = s.a[f]; k.b[f] = s.b[f]; }
+		k.nlimbs = 1;
+		switch (s.kind)
+		{
+			case CG_AGG_COUNT_STAR:
+				k.word0 = 0;
+				break;
+			case CG_AGG_COUNT:
+				k.word0 = (int8_t) nw; k.nullword = (int8_t) nw; p->wordop[nw++] = CG_WORD_ADD;
+				break;
+			case CG_AGG_SUM:
+				k.word0 = (int8_t) nw;
+				if (s.is_float) p->wordop[nw++] = CG_WORD_FADD;
+				else
+				{
+					p->wordop[nw++] = CG_WORD_ADD;
+					bool one = false;
+					if (s.term_abs_bound > 0 && p->max_rows > 0)
+					{
+						__int128 worst = (__int128) s.term_abs_bound * (__int128) p->max_rows;
+						one = worst < ((__int128) 1 << 63);
+					}
+					if (one) { k.nlimbs = 1; k.bound = s.term_abs_bound; }
+					else { k.nlimbs = 2; p->wordop[nw++] = CG_WORD_ADD; }
+				}
+				k.nullword = (int8_t) nw; p->wordop[nw++] = CG_WORD_ADD;
+				break;
+			default:
+				k.word0 = (int8_t) nw;
+				if (s.kind == CG_AGG_MIN) p->wordop[nw++] = s.is_float ? CG_WORD_FMIN : CG_WORD_MIN;
+				else p->wordop[nw++] = s.is_float ? CG_WORD_FMAX : CG_WORD_MAX;
+				k.nullword = (int8_t) nw; p->wordop[nw++] = CG_WORD_ADD;
+				break;
+		}
+		if (nw > CG_KMAX_WORDS) return cg_set_error(CG_EUNSUPPORTED, "too many accumulator words (%d)", nw);
+	}
+	(void) columns;
+	p->nwords = nw;
+	return CG_OK;
+}
+
+extern "C" int cg_partial_create(const CgScanDesc *desc, const CgColumnDesc *columns, int32_t natts,
+								 int64_t key_min, int64_t key_max, int64_t max_rows, CgPartial **out)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx) return CG_EINVAL;
+	if (!desc || !columns || !out) return cg_set_error(CG_EINVAL, "NULL argument");
+	int rc = validate_desc(desc, columns, natts);
+	if (rc) return rc;
+	CgPartial *p = new CgPartial();
+	p->desc = *desc;
+	p->columns.assign(columns, columns + natts);
+	p->key_min = key_min;
+	p->key_max = key_max;
+	p->max_rows = max_rows;
+	rc = layout_partial(p, columns);
+	if (rc) { delete p; return rc; }
+
+	const uint64_t kDenseLimit = 1ull << 26;
+	if (desc->ngroup_cols == 0)
+	{
+		p->mode = CG_MODE_GLOBAL;
+		p->capacity = 1; p->entries = 1; p->stride = p->nwords;
+	}
+	else if (key_min <= key_max && (uint64_t) (key_max - key_min) < kDenseLimit)
+	{
+		p->mode = CG_MODE_DENSE;
+		p->capacity = (uint64_t) (key_max - key_min) + 1;
+		p->entries = p->capacity + 1;            /* + the NULL group */
+		int s = 1; while (s < p->nwords) s <<= 1;   /* power-of-two stride: an entry never straddles a sector pair */
+		p->stride = s;
+	}
+	else
+	{
+		p->mode = CG_MODE_HASH;
+		uint64_t want = desc->expected_groups > 0 ? (uint64_t) desc->expected_groups * 2 : (1ull << 22);
+		uint64_t cap = 1024; while (cap < want) cap <<= 1;
+		p->capacity = cap;
+		p->entries = cap + 2;                    /* + NULL group + the key equal to the EMPTY sentinel */
+		int s = 4; while (s < p->nwords + 1) s += 4;  /* key + words, padded to 32-byte sectors */
+		p->stride = s;
+	}
+	size_t bytes = (size_t) p->entries * p->stride * sizeof(uint64_t);
+	if (cudaMalloc(&p->d_table, bytes) != cudaSuccess)
+	{
+		delete p;
+		return cg_set_error(CG_ENOMEM, "cudaMalloc of %zu bytes for the group table failed", bytes);
+	}
+	if (cudaMalloc(&p->d_stats, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+		cudaMalloc(&p->d_out_count, sizeof(unsigned long long)) != cudaSuccess)
+	{
+		cg_partial_free(p);
+		return cg_set_error(CG_ENOMEM, "cudaMalloc failed");
+	}
+	rc = cg_launch_table_init(p, ctx->compute);
+	if (rc) { cg_partial_free(p); return rc; }
+	*out = p;
+	return CG_OK;
+}
+
+extern "C" void cg_partial_free(CgPartial *p)
+{
+	if (!p) return;
+	cudaFree(p->d_table); cudaFree(p->d_stats); cudaFree(p->d_out_keys); cudaFree(p->d_out_words);
+	cudaFree(p->d_out_nulls); cudaFree(p->d_out_count);
+	delete p;
+}
+
+extern "C" int cg_partial_reset(CgPartial *p)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx || !p) return CG_EINVAL;
+	return cg_launch_table_init(p, ctx->compute);
+}
+
+extern "C" int cg_partial_layout(const CgPartial *p, int32_t *nwords, int32_t *word_ops, int32_t *is_dense, int64_t *capacity)
+{
+	if (!p) return cg_set_error(CG_EINVAL, "NULL partial");
+	if (nwords) *nwords = p->nwords;
+	if (word_ops) for (int i = 0; i < p->nwords; i++) word_ops[i] = p->wordop[i];
+	if (is_dense) *is_dense = p->mode == CG_MODE_DENSE;
+	if (capacity) *capacity = (int64_t) p->capacity;
+	return CG_OK;
+}
+
+/*
+ * Kernel plan: deduplicated projection (columnar_customscan.c:1813-1851 ColumnarAttrNeeded:
+ * only the columns the quals, group keys and aggregate arguments reference are read).
+ */
+int cg_build_plan(const CgScanDesc *desc, const CgColumnDesc *columns, int natts,
+				  const std::vector<int32_t> *slot_of_att, CgPartial *partial, KPlan *plan, bool *all8)
+{
+	int rc = validate_desc(desc, columns, natts);
+	if (rc) return rc;
+	/* the partial must have been created for the same aggregate list */
+	if (partial->desc.naggs != desc->naggs || partial->desc.ngroup_cols != desc->ngroup_cols)
+		return cg_set_error(CG_EINVAL, "partial aggregate was created for a different query shape");
+	for (int a = 0; a < desc->naggs; a++)
+		if (memcmp(&partial->desc.aggs[a], &desc->aggs[a], sizeof(CgAggSpec)) != 0)
+			return cg_set_error(CG_EINVAL, "partial aggregate was created for a different aggregate list");
+
+	memset(plan, 0, sizeof *plan);
+	int pcol_of_att[256];
+	if (natts > 256) return cg_set_error(CG_EUNSUPPORTED, "more than 256 attributes");
+	for (int c = 0; c < natts; c++) pcol_of_att[c] = -1;
+	int ncols = 0;
+	auto use = [&](int att) -> int {
+		if (pcol_of_att[att] >= 0) return pcol_of_att[att];
+		if (ncols == CG_KMAX_COLS) return -1;
+		int slot = slot_of_att ? (*slot_of_att)[att] : att;
+		if (slot < 0) return -2;
+		plan->slot[ncols] = (uint8_t) slot;
+		plan->len[ncols] = (uint8_t) columns[att].attlen;
+		plan->isfloat[ncols] = (uint8_t) (columns[att].type_class == CG_TYPE_FLOAT);
+		pcol_of_att[att] = ncols;
+		return ncols++;
+	};
+#define USE_OR_FAIL(dst, att)                                                                       \
+	do {                                                                                            \
+		int pc__ = use(att);                                                                        \
+		if (pc__ == -1) return cg_set_error(CG_EUNSUPPORTED, "query reads more than %d columns", CG_KMAX_COLS); \
+		if (pc__ == -2) return cg_set_error(CG_EINVAL, "column %d is not staged in this shard", att);  \
+		dst = pc__;                                                                                 \
+	} while (0)
+
+	plan->nquals = desc->nquals;
+	for (int q = 0; q < desc->nquals; q++)
+	{
+		int pc; USE_OR_FAIL(pc, desc->quals[q].column);
+		plan->qcol[q] = (uint8_t) pc;
+		plan->qop[q] = (uint8_t) desc->quals[q].op;
+		plan->qk[q] = desc->quals[q].konst;
+		if (columns[desc->quals[q].column].type_class == CG_TYPE_FLOAT && columns[desc->quals[q].column].attlen == 4)
+		{
+			/* float4 column values are promoted to float8; so is the constant (already float8 bits) */
+		}
+	}
+	plan->ngroup = desc->ngroup_cols;
+	for (int g = 0; g < desc->ngroup_cols; g++)
+	{
+		int pc; USE_OR_FAIL(pc, desc->group_cols[g]);
+		plan->gcol[g] = (uint8_t) pc;
+	}
+	plan->naggs = desc->naggs;
+	for (int a = 0; a < desc->naggs; a++)
+	{
+		plan->aggs[a] = partial->aggs[a];
+		for (int f = 0; f < desc->aggs[a].nfactors; f++)
+		{
+			int pc; USE_OR_FAIL(pc, desc->aggs[a].column[f]);
+			plan->aggs[a].pcol[f] = (int8_t) pc;
+		}
+	}
+	plan->ncols = ncols;
+	bool a8 = true;
+	for (int c = 0; c < ncols; c++) if (plan->len[c] != 8) a8 = false;
+	*all8 = a8;
+
+	plan->mode = partial->mode;
+	plan->nwords = partial->nwords;
+	plan->stride = partial->stride;
+	plan->table = partial->d_table;
+	plan->capacity = partial->capacity;
+	plan->key_min = partial->key_min;
+	memcpy(plan->wordop, partial->wordop, sizeof plan->wordop);
+	plan->stats = partial->d_stats;
+	return CG_OK;
+}

@@ -1,0 +1,763 @@
+/*
+ * cg_scan.cu -- the fused columnar scan kernels (sm_100a).
+ *
+ * One launch does, for every selected chunk group of a staged shard, what the reference
+ * does one row and one function call at a time:
+ *   K1 decode      DeserializeBoolArray / DeserializeDatumArray
+ *                  backend/columnar/columnar_reader.c:1506-1572   (exists bitmap, NULL-compacted
+ *                  value stream -> row values; the prefix popcount lives in the rank directory)
+ *   K3 filter      [PG] ExecQual under ExecScan, backend/columnar/columnar_customscan.c:1907-1913
+ *   K4 aggregate   [PG] nodeAgg + transition functions for the worker half chosen by
+ *                  planner/multi_logical_optimizer.c:3160-3484
+ * reading every needed byte of HBM exactly once with 16-byte vector loads.  There is no
+ * dense contraction on this path, so no tensor cores: the roofline is HBM bandwidth.
+ *
+ * Accumulators are 64-bit "words" combined by one commutative op each (CG_WORD_*), so
+ * that per-thread registers (plain aggregate), global-memory group tables (GROUP BY)
+ * and other GPUs' partials all merge with the same code.  An exact 128-bit integer SUM
+ * is kept as two words: sum of the low 32 bits (unsigned) and sum of term >> 32
+ * (signed); no carries are needed until the value is read (sum = hi * 2^32 + lo).
+ */
+#include "cg_internal.h"
+
+#define CG_THREADS 256
+
+/* ------------------------------------------------------------------------------ *
+ *  streaming loads: read-only path, no L1 allocation (each byte is used once)
+ * ------------------------------------------------------------------------------ */
+__device__ __forceinline__ void ldg_stream16(const void *p, uint64_t &a, uint64_t &b)
+{
+	asm("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+}
+__device__ __forceinline__ uint64_t ldg_stream8(const void *p)
+{
+	uint64_t a;
+	asm("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(a) : "l"(p));
+	return a;
+}
+__device__ __forceinline__ uint32_t ldg_stream4(const void *p)
+{
+	uint32_t a;
+	asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(a) : "l"(p));
+	return a;
+}
+__device__ __forceinline__ uint32_t ldg_stream2(const void *p)
+{
+	uint16_t a;
+	asm("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(a) : "l"(p));
+	return a;
+}
+__device__ __forceinline__ uint32_t ldg_stream1(const void *p)
+{
+	uint32_t a;
+	asm("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(a) : "l"(p));
+	return a;
+}
+
+__device__ __forceinline__ int64_t f4_to_f8_bits(uint32_t u)
+{
+	return __double_as_longlong((double) __uint_as_float(u));
+}
+
+/* widen one stored datum (fetch_att for by-value types, columnar_reader.c:1557) */
+__device__ __forceinline__ int64_t widen(uint64_t raw, int len, bool isfloat)
+{
+	switch (len)
+	{
+		case 8: return (int64_t) raw;
+		case 4: return isfloat ? f4_to_f8_bits((uint32_t) raw) : (int64_t) (int32_t) (uint32_t) raw;
+		case 2: return (int64_t) (int16_t) (uint16_t) raw;
+		default: return (int64_t) (int8_t) (uint8_t) raw;
+	}
+}
+
+__device__ __forceinline__ int64_t load_scalar(const uint8_t *p, int len, bool isfloat)
+{
+	switch (len)
+	{
+		case 8: return (int64_t) ldg_stream8(p);
+		case 4: return widen(ldg_stream4(p), 4, isfloat);
+		case 2: return widen(ldg_stream2(p), 2, isfloat);
+		default: return widen(ldg_stream1(p), 1, isfloat);
+	}
+}
+
+/* two consecutive rows (r even) of a NULL-free column */
+__device__ __forceinline__ void load_pair(const uint8_t *vals, uint32_t r, int len, bool isfloat,
+										  int64_t &v0, int64_t &v1)
+{
+	switch (len)
+	{
+		case 8:
+		{
+			uint64_t a, b;
+			ldg_stream16(vals + (uint64_t) r * 8, a, b);
+			v0 = (int64_t) a; v1 = (int64_t) b;
+			break;
+		}
+		case 4:
+		{
+			uint64_t a = ldg_stream8(vals + (uint64_t) r * 4);
+			v0 = widen(a & 0xffffffffu, 4, isfloat); v1 = widen(a >> 32, 4, isfloat);
+			break;
+		}
+		case 2:
+		{
+			uint32_t a = ldg_stream4(vals + (uint64_t) r * 2);
+			v0 = widen(a & 0xffffu, 2, false); v1 = widen(a >> 16, 2, false);
+			break;
+		}
+		default:
+		{
+			uint32_t a = ldg_stream2(vals + r);
+			v0 = widen(a & 0xffu, 1, false); v1 = widen(a >> 8, 1, false);
+			break;
+		}
+	}
+}
+
+template <int N>
+__device__ __forceinline__ int64_t pick(const int64_t (&v)[N], int idx)
+{
+	int64_t r = v[0];
+#pragma unroll
+	for (int c = 1; c < N; c++) r = (idx == c) ? v[c] : r;
+	return r;
+}
+
+/* [PG] btree comparison result of "v <op> k" (int8 / float8 operators) */
+__device__ __forceinline__ bool qual_true(int64_t v, int op, int64_t k, bool isfloat)
+{
+	if (isfloat)
+	{
+		double x = __longlong_as_double(v), y = __longlong_as_double(k);
+		/* float8 btree order: NaN equals NaN and is greater than everything */
+		bool xn = x != x, yn = y != y;
+		int c = (xn || yn) ? ((int) xn - (int) yn) : ((x > y) - (x < y));
+		switch (op)
+		{
+			case CG_OP_LT: return c < 0;
+			case CG_OP_LE: return c <= 0;
+			case CG_OP_EQ: return c == 0;
+			case CG_OP_GE: return c >= 0;
+			case CG_OP_GT: return c > 0;
+			default: return c != 0;
+		}
+	}
+	switch (op)
+	{
+		case CG_OP_LT: return v < k;
+		case CG_OP_LE: return v <= k;
+		case CG_OP_EQ: return v == k;
+		case CG_OP_GE: return v >= k;
+		case CG_OP_GT: return v > k;
+		default: return v != k;
+	}
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x)
+{
+	x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+	return x;
+}
+
+/* order-preserving map of float8 bits to unsigned (for min/max words) */
+__device__ __forceinline__ uint64_t f8_ordered(int64_t bits)
+{
+	uint64_t u = (uint64_t) bits;
+	return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+
+__device__ __forceinline__ void word_apply_global(uint64_t *p, int op, uint64_t val)
+{
+	switch (op)
+	{
+		case CG_WORD_ADD: atomicAdd((unsigned long long *) p, (unsigned long long) val); break;
+		case CG_WORD_MIN: atomicMin((long long *) p, (long long) val); break;
+		case CG_WORD_MAX: atomicMax((long long *) p, (long long) val); break;
+		case CG_WORD_FADD: atomicAdd((double *) p, __longlong_as_double((long long) val)); break;
+		case CG_WORD_FMIN: atomicMin((unsigned long long *) p, (unsigned long long) val); break;
+		default: atomicMax((unsigned long long *) p, (unsigned long long) val); break;
+	}
+}
+
+__device__ __forceinline__ uint64_t word_identity(int op)
+{
+	switch (op)
+	{
+		case CG_WORD_MIN: return (uint64_t) INT64_MAX;
+		case CG_WORD_MAX: return (uint64_t) INT64_MIN;
+		case CG_WORD_FMIN: return ~0ull;
+		default: return 0ull;     /* ADD, FADD (+0.0), FMAX */
+	}
+}
+
+__device__ __forceinline__ uint64_t word_combine(int op, uint64_t a, uint64_t b)
+{
+	switch (op)
+	{
+		case CG_WORD_ADD: return a + b;
+		case CG_WORD_MIN: return (uint64_t) min((long long) a, (long long) b);
+		case CG_WORD_MAX: return (uint64_t) max((long long) a, (long long) b);
+		case CG_WORD_FADD: return (uint64_t) __double_as_longlong(__longlong_as_double((long long) a) + __longlong_as_double((long long) b));
+		case CG_WORD_FMIN: return a < b ? a : b;
+		default: return a > b ? a : b;
+	}
+}
+
+/*
+ * Find (or claim) the table entry of a group key.  Returns the word pointer of the
+ * entry (word 0 = rows in group) or NULL after raising an error flag.
+ *   dense: entry = key - key_min, NULL key -> entry `capacity`
+ *   hash : open addressing, linear probing, 64-bit CAS on the key word; the NULL group
+ *          and the key that collides with the EMPTY sentinel live in two extra entries
+ */
+template <int MODE>
+__device__ __forceinline__ uint64_t *find_entry(const KPlan &P, int64_t key, bool key_null)
+{
+	if (MODE == CG_MODE_DENSE)
+	{
+		uint64_t slot = key_null ? P.capacity : (uint64_t) (key - P.key_min);
+		if (slot > P.capacity || (!key_null && slot == P.capacity))
+		{
+			atomicOr(P.stats + 2, CG_ERRFLAG_KEY_RANGE);
+			return nullptr;
+		}
+		return P.table + slot * (uint64_t) P.stride;
+	}
+	else
+	{
+		if (key_null) return P.table + P.capacity * (uint64_t) P.stride + 1;
+		if (key == CG_HASH_EMPTY) return P.table + (P.capacity + 1) * (uint64_t) P.stride + 1;
+		uint64_t mask = P.capacity - 1;
+		uint64_t h = mix64((uint64_t) key) & mask;
+		for (uint32_t probes = 0; probes < 8192; probes++)
+		{
+			unsigned long long *kp = (unsigned long long *) (P.table + h * (uint64_t) P.stride);
+			long long cur = (long long) __ldcg(kp);     /* L2: keys only ever go EMPTY -> key */
+			if (cur == key) return (uint64_t *) kp + 1;
+			if (cur == CG_HASH_EMPTY)
+			{
+				long long old = (long long) atomicCAS(kp, (unsigned long long) CG_HASH_EMPTY, (unsigned long long) key);
+				if (old == CG_HASH_EMPTY || old == key) return (uint64_t *) kp + 1;
+			}
+			h = (h + 1) & mask;
+		}
+		atomicOr(P.stats + 2, CG_ERRFLAG_TABLE_FULL);
+		return nullptr;
+	}
+}
+
+/* per-thread accumulators of the plain-aggregate mode */
+template <int NAC>
+struct ThreadAcc
+{
+	uint64_t w[NAC][3];     /* [agg][word0, word0+1, NULL-input count] */
+	uint64_t rows;
+};
+
+template <int NCC, int NAC, int MODE>
+__device__ __forceinline__ void process_row(const KPlan &P, const int64_t (&v)[NCC], uint32_t nullmask,
+											ThreadAcc<NAC> &acc, uint32_t &removed)
+{
+	/* K3: WHERE list, three-valued: a NULL input makes the conjunct NULL and drops the row */
+	bool pass = true;
+#pragma unroll
+	for (int q = 0; q < CG_MAX_QUALS; q++)
+	{
+		if (q < P.nquals)
+		{
+			int c = P.qcol[q];
+			bool isnull = (nullmask >> c) & 1u;
+			pass = pass && !isnull && qual_true(pick<NCC>(v, c), P.qop[q], P.qk[q], P.isfloat[c]);
+		}
+	}
+	if (!pass)
+	{
+		removed++;
+		return;
+	}
+
+	uint64_t *entry = nullptr;
+	if (MODE != CG_MODE_GLOBAL)
+	{
+		int64_t key;
+		bool key_null;
+		if (P.ngroup == 1)
+		{
+			int c = P.gcol[0];
+			key_null = (nullmask >> c) & 1u;
+			key = pick<NCC>(v, c);
+		}
+		else
+		{
+			int c0 = P.gcol[0], c1 = P.gcol[1];
+			if (((nullmask >> c0) | (nullmask >> c1)) & 1u)
+			{
+				atomicOr(P.stats + 2, CG_ERRFLAG_NULL_MULTIKEY);
+				return;
+			}
+			key_null = false;
+			key = (int64_t) ((uint64_t) (uint32_t) pick<NCC>(v, c0) | ((uint64_t) (uint32_t) pick<NCC>(v, c1) << 32));
+		}
+		entry = find_entry<MODE>(P, key, key_null);
+		if (entry == nullptr) return;
+		atomicAdd((unsigned long long *) entry, 1ull);
+	}
+	else
+		acc.rows++;
+
+	/* K4: transition functions */
+#pragma unroll
+	for (int a = 0; a < NAC; a++)
+	{
+		if (a < P.naggs)
+		{
+			const KAgg &g = P.aggs[a];
+			if (g.kind == CG_AGG_COUNT_STAR) continue;
+			bool isnull = false;
+			int64_t it = 1;
+			double ft = 1.0;
+#pragma unroll
+			for (int f = 0; f < 3; f++)
+			{
+				if (f < g.nfactors)
+				{
+					int c = g.pcol[f];
+					isnull = isnull || ((nullmask >> c) & 1u);
+					int64_t x = pick<NCC>(v, c);
+					if (g.is_float)
+						ft *= __longlong_as_double(g.a[f]) + __longlong_as_double(g.b[f]) * __longlong_as_double(x);
+					else
+						it *= g.a[f] + g.b[f] * x;
+				}
+			}
+			if (isnull)
+			{
+				/* strict transition function: a NULL input is skipped, only counted */
+				if (MODE == CG_MODE_GLOBAL) acc.w[a][2]++;
+				else atomicAdd((unsigned long long *) entry + g.nullword, 1ull);
+				continue;
+			}
+			if (g.kind == CG_AGG_COUNT) continue;   /* count(x) = rows - NULL inputs */
+			uint64_t w0, w1 = 0;
+			if (g.kind == CG_AGG_SUM)
+			{
+				if (g.is_float) w0 = (uint64_t) __double_as_longlong(ft);
+				else if (g.nlimbs == 1)
+				{
+					if (it > g.bound || it < -g.bound) atomicOr(P.stats + 2, CG_ERRFLAG_SUM_BOUND);
+					w0 = (uint64_t) it;
+				}
+				else { w0 = (uint64_t) (uint32_t) it; w1 = (uint64_t) (it >> 32); }
+			}
+			else /* MIN / MAX */
+				w0 = g.is_float ? f8_ordered(__double_as_longlong(ft)) : (uint64_t) it;
+			const bool two = (g.kind == CG_AGG_SUM && !g.is_float && g.nlimbs == 2);
+			if (MODE == CG_MODE_GLOBAL)
+			{
+				acc.w[a][0] = word_combine(P.wordop[g.word0], acc.w[a][0], w0);
+				if (two) acc.w[a][1] += w1;
+			}
+			else
+			{
+				word_apply_global(entry + g.word0, P.wordop[g.word0], w0);
+				if (two) atomicAdd((unsigned long long *) entry + g.word0 + 1, (unsigned long long) w1);
+			}
+		}
+	}
+}
+
+__device__ __forceinline__ uint64_t warp_reduce_word(uint64_t x, int op)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+	{
+		uint64_t y = __shfl_xor_sync(0xffffffffu, x, o);
+		x = word_combine(op, x, y);
+	}
+	return x;
+}
+
+/*
+ * The fused kernel.  Persistent CTAs stride over the selected chunk groups; inside a
+ * chunk group every thread takes two consecutive rows per step (one 16-byte load per
+ * 8-byte column) and U steps are loaded before any is consumed.
+ *   NCC  capacity of the per-thread column register file (plan columns <= NCC)
+ *   NAC  capacity of the per-thread aggregate accumulators (plain aggregate mode)
+ *   ALL8 every plan column is 8 bytes wide (skips the width switch)
+ */
+template <int NCC, int NAC, int MODE, bool ALL8, int U>
+__global__ void __launch_bounds__(CG_THREADS)
+cg_scan_kernel(const __grid_constant__ KPlan P)
+{
+	ThreadAcc<NAC> acc;
+	acc.rows = 0;
+#pragma unroll
+	for (int a = 0; a < NAC; a++)
+	{
+		acc.w[a][0] = (a < P.naggs && P.aggs[a].kind != CG_AGG_COUNT_STAR) ? word_identity(P.wordop[P.aggs[a].word0]) : 0;
+		acc.w[a][1] = 0;
+		acc.w[a][2] = 0;
+	}
+	uint32_t removed = 0;
+	unsigned long long scanned = 0;
+	const uint32_t tid = threadIdx.x;
+
+	for (uint32_t ci = blockIdx.x; ci < P.nselected; ci += gridDim.x)
+	{
+		const DevChunkCol *cc = P.chunkcols + (uint64_t) P.selected[ci] * (uint64_t) P.nstaged;
+		const uint8_t *vptr[NCC];
+		const uint64_t *bptr[NCC];
+		const uint32_t *rptr[NCC];
+		uint32_t hasnull = 0;
+		uint32_t rows = __ldg(&cc[0].row_count);
+#pragma unroll
+		for (int c = 0; c < NCC; c++)
+		{
+			if (c < P.ncols)
+			{
+				const DevChunkCol *d = cc + P.slot[c];
+				vptr[c] = P.arena + __ldg(&d->values_off);
+				bptr[c] = (const uint64_t *) (P.arena + __ldg(&d->exists_off));
+				rptr[c] = (const uint32_t *) (P.arena + __ldg(&d->rank_off));
+				if (__ldg(&d->value_count) != rows) hasnull |= 1u << c;
+			}
+		}
+		scanned += (tid == 0) ? rows : 0;
+
+		if (hasnull == 0)
+		{
+			for (uint32_t base = 0; base < rows; base += CG_THREADS * 2 * U)
+			{
+				int64_t v0[U][NCC], v1[U][NCC];
+#pragma unroll
+				for (int u = 0; u < U; u++)
+				{
+					uint32_t r = base + (u * CG_THREADS + tid) * 2;
+					if (r < rows)
+					{
+#pragma unroll
+						for (int c = 0; c < NCC; c++)
+							if (c < P.ncols)
+							{
+								if (ALL8)
+								{
+									uint64_t a, b;
+									ldg_stream16(vptr[c] + (uint64_t) r * 8, a, b);
+									v0[u][c] = (int64_t) a; v1[u][c] = (int64_t) b;
+								}
+								else
+									load_pair(vptr[c], r, P.len[c], P.isfloat[c], v0[u][c], v1[u][c]);
+							}
+					}
+				}
+#pragma unroll
+				for (int u = 0; u < U; u++)
+				{
+					uint32_t r = base + (u * CG_THREADS + tid) * 2;
+					if (r < rows)
+					{
+						process_row<NCC, NAC, MODE>(P, v0[u], 0u, acc, removed);
+						if (r + 1 < rows) process_row<NCC, NAC, MODE>(P, v1[u], 0u, acc, removed);
+					}
+				}
+			}
+		}
+		else
+		{
+			/* chunk group with NULLs: row -> value index through the rank directory
+			 * (NULL rows occupy no bytes in the value stream, columnar_reader.c:1550-1555) */
+			for (uint32_t r = tid * 2; r < rows; r += CG_THREADS * 2)
+			{
+				int64_t v0[NCC], v1[NCC];
+				uint32_t n0 = 0, n1 = 0;
+#pragma unroll
+				for (int c = 0; c < NCC; c++)
+					if (c < P.ncols)
+					{
+						int len = ALL8 ? 8 : P.len[c];
+						bool isf = P.isfloat[c];
+						if ((hasnull >> c) & 1u)
+						{
+							uint64_t w = ldg_stream8(bptr[c] + (r >> 6));
+							uint32_t sh = r & 63u;
+							uint32_t before = __ldg(rptr[c] + (r >> 6)) + __popcll(w & ((1ull << sh) - 1ull));
+							uint32_t e0 = (uint32_t) (w >> sh) & 1u, e1 = (uint32_t) (w >> (sh + 1)) & 1u;
+							v0[c] = e0 ? load_scalar(vptr[c] + (uint64_t) before * len, len, isf) : 0;
+							v1[c] = (e1 && r + 1 < rows) ? load_scalar(vptr[c] + (uint64_t) (before + e0) * len, len, isf) : 0;
+							n0 |= (e0 ^ 1u) << c;
+							n1 |= (e1 ^ 1u) << c;
+						}
+						else
+							load_pair(vptr[c], r, len, isf, v0[c], v1[c]);
+					}
+				process_row<NCC, NAC, MODE>(P, v0, n0, acc, removed);
+				if (r + 1 < rows) process_row<NCC, NAC, MODE>(P, v1, n1, acc, removed);
+			}
+		}
+	}
+
+	/* counters and (plain aggregate) the block's accumulators: warp shuffle reduce, then one
+	 * atomic per warp and word */
+	unsigned long long rem = warp_reduce_word(removed, CG_WORD_ADD);
+	unsigned long long scn = warp_reduce_word(scanned, CG_WORD_ADD);
+	if ((tid & 31) == 0)
+	{
+		if (scn) atomicAdd(P.stats + 0, scn);
+		if (rem) atomicAdd(P.stats + 1, rem);
+	}
+	if (MODE == CG_MODE_GLOBAL)
+	{
+		uint64_t rows_passed = warp_reduce_word(acc.rows, CG_WORD_ADD);
+		if ((tid & 31) == 0 && rows_passed) atomicAdd((unsigned long long *) P.table, (unsigned long long) rows_passed);
+#pragma unroll
+		for (int a = 0; a < NAC; a++)
+		{
+			if (a < P.naggs && P.aggs[a].kind != CG_AGG_COUNT_STAR)
+			{
+				const KAgg &g = P.aggs[a];
+				uint64_t nulls = warp_reduce_word(acc.w[a][2], CG_WORD_ADD);
+				uint64_t x0 = warp_reduce_word(acc.w[a][0], P.wordop[g.word0]);
+				uint64_t x1 = warp_reduce_word(acc.w[a][1], CG_WORD_ADD);
+				if ((tid & 31) == 0)
+				{
+					if (nulls) atomicAdd((unsigned long long *) P.table + g.nullword, (unsigned long long) nulls);
+					if (g.kind != CG_AGG_COUNT)
+					{
+						if (x0 != word_identity(P.wordop[g.word0])) word_apply_global(P.table + g.word0, P.wordop[g.word0], x0);
+						if (g.kind == CG_AGG_SUM && !g.is_float && g.nlimbs == 2 && x1)
+							atomicAdd((unsigned long long *) P.table + g.word0 + 1, (unsigned long long) x1);
+					}
+				}
+			}
+		}
+	}
+}
+
+template <int NCC, int NAC, int MODE, bool ALL8, int U>
+static int launch_variant(CgContext *ctx, const KPlan &plan, cudaStream_t stream)
+{
+	int occ = 0;
+	CG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_scan_kernel<NCC, NAC, MODE, ALL8, U>, CG_THREADS, 0));
+	if (occ < 1) occ = 1;
+	uint32_t grid = (uint32_t) (ctx->sm_count * occ);
+	if (grid > plan.nselected) grid = plan.nselected;
+	if (grid == 0) return CG_OK;
+	cg_scan_kernel<NCC, NAC, MODE, ALL8, U><<<grid, CG_THREADS, 0, stream>>>(plan);
+	CG_CUDA(cudaGetLastError());
+	return CG_OK;
+}
+
+template <int NCC, int NAC, int MODE>
+static int launch_cols(CgContext *ctx, const KPlan &plan, bool all8, cudaStream_t stream)
+{
+	constexpr int U = (NCC <= 4) ? 2 : 1;
+	if (all8) return launch_variant<NCC, NAC, MODE, true, U>(ctx, plan, stream);
+	return launch_variant<NCC, NAC, MODE, false, U>(ctx, plan, stream);
+}
+
+template <int NCC>
+static int launch_mode(CgContext *ctx, const KPlan &plan, bool all8, cudaStream_t stream)
+{
+	switch (plan.mode)
+	{
+		case CG_MODE_GLOBAL:
+			if (plan.naggs <= 2) return launch_cols<NCC, 2, CG_MODE_GLOBAL>(ctx, plan, all8, stream);
+			return launch_cols<NCC, CG_MAX_AGGS, CG_MODE_GLOBAL>(ctx, plan, all8, stream);
+		case CG_MODE_DENSE:
+			return launch_cols<NCC, CG_MAX_AGGS, CG_MODE_DENSE>(ctx, plan, all8, stream);
+		default:
+			return launch_cols<NCC, CG_MAX_AGGS, CG_MODE_HASH>(ctx, plan, all8, stream);
+	}
+}
+
+int cg_launch_scan(CgContext *ctx, const KPlan &plan, bool any_nulls, bool all8, cudaStream_t stream)
+{
+	(void) any_nulls;
+	if (plan.ncols <= 2) return launch_mode<2>(ctx, plan, all8, stream);
+	if (plan.ncols <= 4) return launch_mode<4>(ctx, plan, all8, stream);
+	return launch_mode<CG_KMAX_COLS>(ctx, plan, all8, stream);
+}
+
+/* ------------------------------------------------------------------------------ *
+ *  Rank directory: for every (chunk group, staged column) that has NULLs,
+ *  rank[b] = number of set exists bits before row 64*b.  One warp per item.
+ *  (the prefix-popcount half of K1; DeserializeDatumArray's running offset)
+ * ------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(256)
+cg_rank_kernel(const uint8_t *arena, const DevChunkCol *chunkcols, uint64_t first, uint64_t count)
+{
+	uint64_t item = first + (uint64_t) blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+	if (item >= first + count) return;
+	const DevChunkCol d = chunkcols[item];
+	if (d.value_count == d.row_count) return;
+	const uint64_t *bm = (const uint64_t *) (arena + d.exists_off);
+	uint32_t *rank = (uint32_t *) (arena + d.rank_off);
+	uint32_t nblocks = (d.row_count + 63) / 64;
+	uint32_t lane = threadIdx.x & 31;
+	uint32_t running = 0;
+	for (uint32_t b0 = 0; b0 < nblocks; b0 += 32)
+	{
+		uint32_t b = b0 + lane;
+		uint32_t pc = (b < nblocks) ? (uint32_t) __popcll(bm[b]) : 0;
+		uint32_t incl = pc;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= (uint32_t) o) incl += y;
+		}
+		if (b < nblocks) rank[b] = running + incl - pc;
+		running += __shfl_sync(0xffffffffu, incl, 31);
+	}
+}
+
+int cg_launch_rank(CgContext *ctx, const uint8_t *arena, const DevChunkCol *chunkcols, uint64_t first,
+				   uint64_t count, cudaStream_t stream)
+{
+	(void) ctx;
+	if (count == 0) return CG_OK;
+	uint64_t blocks = (count + 7) / 8;
+	cg_rank_kernel<<<(unsigned) blocks, 256, 0, stream>>>(arena, chunkcols, first, count);
+	CG_CUDA(cudaGetLastError());
+	return CG_OK;
+}
+
+/* ------------------------------------------------------------------------------ *
+ *  Group table: init, export (compaction), merge (K5 combine).
+ * ------------------------------------------------------------------------------ */
+struct TableView
+{
+	uint64_t *table;
+	uint64_t capacity;
+	uint64_t entries;
+	int32_t stride;
+	int32_t nwords;
+	int32_t mode;
+	int64_t key_min;
+	uint8_t wordop[CG_KMAX_WORDS];
+};
+
+static TableView view_of(const CgPartial *p)
+{
+	TableView v;
+	v.table = p->d_table; v.capacity = p->capacity; v.entries = p->entries; v.stride = p->stride;
+	v.nwords = p->nwords; v.mode = p->mode; v.key_min = p->key_min;
+	for (int i = 0; i < CG_KMAX_WORDS; i++) v.wordop[i] = p->wordop[i];
+	return v;
+}
+
+__global__ void cg_table_init_kernel(const __grid_constant__ TableView T)
+{
+	uint64_t total = T.entries * (uint64_t) T.stride;
+	int keyw = (T.mode == CG_MODE_HASH) ? 1 : 0;
+	for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t) gridDim.x * blockDim.x)
+	{
+		int w = (int) (i % (uint64_t) T.stride);
+		uint64_t val = 0;
+		if (keyw && w == 0) val = (uint64_t) CG_HASH_EMPTY;
+		else if (w - keyw < T.nwords) val = word_identity(T.wordop[w - keyw]);
+		T.table[i] = val;
+	}
+}
+
+int cg_launch_table_init(CgPartial *p, cudaStream_t stream)
+{
+	TableView v = view_of(p);
+	uint64_t total = v.entries * (uint64_t) v.stride;
+	unsigned blocks = (unsigned) ((total + 255) / 256);
+	if (blocks > 148 * 16) blocks = 148 * 16;
+	if (blocks == 0) blocks = 1;
+	cg_table_init_kernel<<<blocks, 256, 0, stream>>>(v);
+	CG_CUDA(cudaGetLastError());
+	CG_CUDA(cudaMemsetAsync(p->d_stats, 0, 8 * sizeof(unsigned long long), stream));
+	return CG_OK;
+}
+
+__global__ void cg_export_kernel(const __grid_constant__ TableView T, uint64_t out_capacity, int64_t *keys,
+								 uint8_t *nulls, uint64_t *words, unsigned long long *count)
+{
+	int keyw = (T.mode == CG_MODE_HASH) ? 1 : 0;
+	for (uint64_t e = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; e < T.entries; e += (uint64_t) gridDim.x * blockDim.x)
+	{
+		const uint64_t *ent = T.table + e * (uint64_t) T.stride;
+		bool occupied;
+		int64_t key = 0;
+		bool key_null = false;
+		if (T.mode == CG_MODE_HASH)
+		{
+			if (e < T.capacity) { key = (int64_t) ent[0]; occupied = key != CG_HASH_EMPTY; }
+			else { occupied = ent[1] > 0; key_null = (e == T.capacity); key = key_null ? 0 : CG_HASH_EMPTY; }
+		}
+		else if (T.mode == CG_MODE_DENSE)
+		{
+			occupied = ent[0] > 0;
+			key_null = (e == T.capacity);
+			key = key_null ? 0 : T.key_min + (int64_t) e;
+		}
+		else
+			occupied = true;    /* plain aggregate: exactly one result row, even over no input */
+		if (!occupied) continue;
+		unsigned long long pos = atomicAdd(count, 1ull);
+		if (pos >= out_capacity) continue;
+		if (keys) keys[pos] = key;
+		if (nulls) nulls[pos] = key_null ? 1 : 0;
+		if (words)
+			for (int w = 0; w < T.nwords; w++) words[pos * (uint64_t) T.nwords + w] = ent[keyw + w];
+	}
+}
+
+int cg_launch_export(CgPartial *p, uint64_t out_capacity, int64_t *d_keys, uint8_t *d_nulls, uint64_t *d_words,
+					 unsigned long long *d_count, cudaStream_t stream)
+{
+	TableView v = view_of(p);
+	CG_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), stream));
+	unsigned blocks = (unsigned) ((v.entries + 255) / 256);
+	if (blocks > 148 * 16) blocks = 148 * 16;
+	if (blocks == 0) blocks = 1;
+	cg_export_kernel<<<blocks, 256, 0, stream>>>(v, out_capacity, d_keys, d_nulls, d_words, d_count);
+	CG_CUDA(cudaGetLastError());
+	return CG_OK;
+}
+
+/* K5: merge partial rows (from other shards / GPUs) into the table, word by word.
+ * This is the coordinator's HashAggregate over sum(sum), sum(count), min(min), max(max)
+ * (planner/multi_logical_optimizer.c:1807-1885, 2231-2275). */
+__global__ void cg_merge_kernel(const __grid_constant__ KPlan P, const int64_t *keys, const uint8_t *nulls,
+								const uint64_t *words, int64_t nrows)
+{
+	for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += (int64_t) gridDim.x * blockDim.x)
+	{
+		uint64_t *entry;
+		if (P.mode == CG_MODE_GLOBAL) entry = P.table;
+		else
+		{
+			bool kn = nulls ? nulls[i] != 0 : false;
+			entry = (P.mode == CG_MODE_DENSE) ? find_entry<CG_MODE_DENSE>(P, keys[i], kn)
+											  : find_entry<CG_MODE_HASH>(P, keys[i], kn);
+			if (entry == nullptr) continue;
+		}
+		for (int w = 0; w < P.nwords; w++)
+		{
+			uint64_t val = words[i * (int64_t) P.nwords + w];
+			if (val != word_identity(P.wordop[w])) word_apply_global(entry + w, P.wordop[w], val);
+		}
+	}
+}
+
+int cg_launch_merge(CgPartial *p, const int64_t *d_keys, const uint8_t *d_nulls, const uint64_t *d_words,
+					int64_t nrows, cudaStream_t stream)
+{
+	if (nrows <= 0) return CG_OK;
+	KPlan plan;
+	memset(&plan, 0, sizeof plan);
+	plan.mode = p->mode; plan.nwords = p->nwords; plan.stride = p->stride; plan.table = p->d_table;
+	plan.capacity = p->capacity; plan.key_min = p->key_min; plan.stats = p->d_stats;
+	for (int i = 0; i < CG_KMAX_WORDS; i++) plan.wordop[i] = p->wordop[i];
+	unsigned blocks = (unsigned) ((nrows + 255) / 256);
+	if (blocks > 148 * 8) blocks = 148 * 8;
+	cg_merge_kernel<<<blocks, 256, 0, stream>>>(plan, d_keys, d_nulls, d_words, nrows);
+	CG_CUDA(cudaGetLastError());
+	return CG_OK;
+}

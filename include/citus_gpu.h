@@ -1,0 +1,328 @@
+/*
+ * citus_gpu.h -- C-ABI of libcitus_gpu.so: the B200 (sm_100a) implementation of Citus's
+ * columnar shard-scan / partial-aggregate / combine / hash-repartition hot path.
+ *
+ * This is the drop-in boundary.  Plain C, plain pointers and
+ * sizes, no CUDA or torch types.  Every entry point returns 0 on success or a CG_E* code;
+ * the message is read with cg_last_error() (thread-local).  Nothing here longjmps: the
+ * PostgreSQL-side glue turns a non-zero return into ereport(ERROR).
+ *
+ * Reference interfaces each block replaces are cited as file:line under
+ * /root/reference/src.
+ */
+#ifndef CITUS_GPU_H
+#define CITUS_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CG_OK 0
+#define CG_EINVAL 1        /* bad argument / unsupported plan shape */
+#define CG_ECUDA 2         /* CUDA runtime error (message has the cudaError string) */
+#define CG_ENOMEM 3
+#define CG_ECORRUPT 4      /* relation image inconsistent with its metadata */
+#define CG_ETABLEFULL 5    /* group table too small: retry with a larger expected_groups */
+#define CG_EUNSUPPORTED 6  /* valid SQL, but outside what the GPU path handles: caller falls
+                            * back to the reference's row-at-a-time executor */
+
+const char *cg_last_error(void);
+
+/* ---------------------------------------------------------------------------------- *
+ *  Device context.  One per process (a PostgreSQL backend is one process; CUDA is
+ *  initialised lazily in the backend, never in the postmaster -- SURVEY.md 7.3).
+ * ---------------------------------------------------------------------------------- */
+int cg_init(int device_ordinal);          /* idempotent */
+int cg_device_count(int *count);
+int cg_synchronize(void);                 /* waits for the library's streams */
+/* Run the kernels on a stream owned by the caller (a CUstream / cudaStream_t handle passed as
+ * void *; NULL restores the library's own stream).  Lets a host that already has a stream --
+ * e.g. the one its NCCL collectives are ordered on -- keep everything in one queue. */
+int cg_set_stream(void *cuda_stream);
+/* Per-launch device timing of the fused scan kernels: between begin and collect every scan
+ * launch is bracketed by CUDA events on the launching stream (no host synchronisation);
+ * collect waits for them and returns the launch count and the summed / maximum duration. */
+int cg_profile_begin(void);
+int cg_profile_collect(int32_t *launches, double *total_ms, double *max_ms);
+void cg_shutdown(void);
+
+/* ---------------------------------------------------------------------------------- *
+ *  Relation metadata, binary-compatible with what the reference keeps per stripe/chunk.
+ * ---------------------------------------------------------------------------------- */
+
+/* include/columnar/columnar_compression.h:17-27 CompressionType */
+enum { CG_COMPRESSION_NONE = 0, CG_COMPRESSION_PGLZ = 1, CG_COMPRESSION_LZ4 = 2, CG_COMPRESSION_ZSTD = 3 };
+
+/* include/columnar/columnar.h:85-111 ColumnChunkSkipNode
+ * (catalog columnar.chunk, backend/columnar/sql/citus_columnar--11.1-1.sql:48-64) */
+typedef struct CgSkipNode
+{
+	int32_t has_minmax;
+	int32_t compression_type;
+	int64_t min_value;          /* by-value Datum: sign-extended integer or float8 bits */
+	int64_t max_value;
+	uint64_t row_count;
+	uint64_t value_offset;      /* valueChunkOffset, relative to the stripe's file_offset */
+	uint64_t value_length;
+	uint64_t exists_offset;
+	uint64_t exists_length;
+	uint64_t decompressed_size; /* decompressedValueSize */
+	int32_t compression_level;
+	int32_t reserved;
+} CgSkipNode;
+
+/* include/columnar/columnar_metadata.h:21-42 StripeMetadata (catalog columnar.stripe) */
+typedef struct CgStripe
+{
+	uint64_t id;
+	uint64_t file_offset;       /* logical offset of the stripe (page aligned) */
+	uint64_t data_length;
+	uint64_t row_count;
+	uint64_t first_row_number;
+	uint32_t column_count;
+	uint32_t chunk_row_count;   /* chunk_group_row_limit the stripe was written with */
+	uint32_t chunk_count;
+	uint32_t skipnode_base;     /* node(col,chunk) = nodes[skipnode_base + col*chunk_count + chunk] */
+} CgStripe;
+
+enum { CG_TYPE_INT = 0, CG_TYPE_FLOAT = 1 };
+
+/* the slice of the TupleDesc the path needs (Form_pg_attribute attlen / attalign / type class) */
+typedef struct CgColumnDesc
+{
+	int32_t attlen;     /* 1, 2, 4, 8: fixed-width by-value types */
+	int32_t type_class; /* CG_TYPE_* */
+} CgColumnDesc;
+
+/* A columnar relation as the reader sees it: the main fork's 8 KB pages (as they sit in
+ * shared_buffers / the file: 24-byte page header + 8168-byte payload, metapage in block 0,
+ * data from block 2 -- backend/columnar/columnar_storage.c:21-31,117-126) + its visible
+ * stripes and their skip lists (backend/columnar/columnar_metadata.c:717 ReadStripeSkipList). */
+typedef struct CgRelation
+{
+	const uint8_t *pages;
+	uint64_t nblocks;
+	const CgStripe *stripes;
+	int32_t nstripes;
+	const CgSkipNode *nodes;
+	int32_t nnodes;
+	const CgColumnDesc *columns;
+	int32_t natts;
+} CgRelation;
+
+/* ---------------------------------------------------------------------------------- *
+ *  Query description: what the worker task's  Agg <- ColumnarScan  subtree computes
+ *  (SURVEY.md 3.3).  Replaces ColumnarBeginRead(projectedColumnList, qualConditions)
+ *  include/columnar/columnar.h:251-258 + the plan quals applied by ExecScan
+ *  backend/columnar/columnar_customscan.c:1907-1913 + the worker half of the aggregate
+ *  split planner/multi_logical_optimizer.c:3160-3484.
+ * ---------------------------------------------------------------------------------- */
+enum { CG_OP_LT = 0, CG_OP_LE = 1, CG_OP_EQ = 2, CG_OP_GE = 3, CG_OP_GT = 4, CG_OP_NE = 5 };
+
+/* one conjunct "column <op> constant" of the WHERE list (btree operators) */
+typedef struct CgQual
+{
+	int32_t column;   /* 0-based attribute index */
+	int32_t op;       /* CG_OP_* */
+	int64_t konst;    /* integer, or float8 bits for float columns */
+} CgQual;
+
+enum { CG_AGG_COUNT_STAR = 0, CG_AGG_COUNT = 1, CG_AGG_SUM = 2, CG_AGG_MIN = 3, CG_AGG_MAX = 4 };
+
+/* aggregate argument = product over factors of (a + b * column); covers sum(x),
+ * sum(x*y), sum(x*(1-d)), sum(x*(1-d)*(1+t)) on scaled-integer decimals (TPC-H Q1/Q6) */
+typedef struct CgAggSpec
+{
+	int32_t kind;        /* CG_AGG_* */
+	int32_t nfactors;    /* 0 (count(*)) .. 3 */
+	int32_t column[3];
+	int32_t is_float;    /* float8 arithmetic (sum is order dependent: tolerance, not bit-exact) */
+	int64_t a[3];        /* integers, or float8 bits when is_float */
+	int64_t b[3];
+	int64_t term_abs_bound; /* integer SUM: caller-proven bound on |argument| (from the skip lists'
+							 * min/max), 0 = unknown.  When bound * max_rows < 2^63 the sum is kept in
+							 * one 64-bit word instead of two; a row that violates the bound fails the
+							 * scan with CG_EINVAL (never a wrong answer). */
+} CgAggSpec;
+
+#define CG_MAX_QUALS 8
+#define CG_MAX_AGGS 8
+#define CG_MAX_GROUP_COLS 2
+
+typedef struct CgScanDesc
+{
+	int32_t nquals;
+	CgQual quals[CG_MAX_QUALS];
+	int32_t enable_qual_pushdown;   /* columnar.enable_qual_pushdown (columnar_customscan.c:225-236) */
+	int32_t ngroup_cols;            /* 0 = plain aggregate */
+	int32_t group_cols[CG_MAX_GROUP_COLS];
+	int32_t naggs;
+	CgAggSpec aggs[CG_MAX_AGGS];
+	int64_t expected_groups;        /* planner's group estimate; 0 = let the library size the table */
+} CgScanDesc;
+
+/* EXPLAIN ANALYZE counters (columnar_customscan.c:1966-1999 and ExecScan instrumentation) */
+typedef struct CgScanStats
+{
+	int64_t rows_scanned;            /* rows handed to the qual */
+	int64_t rows_removed_by_filter;  /* "Rows Removed by Filter" */
+	int64_t chunk_groups_filtered;   /* "Columnar Chunk Groups Removed by Filter" */
+	int64_t rows_passed;
+	int64_t chunk_groups_scanned;
+	int64_t bytes_scanned;           /* algorithmic bytes: sum over projected columns of
+									  * value bytes + exists bytes of the scanned chunk groups */
+	double kernel_ms;                /* device time of the fused kernel(s), CUDA events */
+	int64_t h2d_bytes;               /* cg_scan_relation: bytes copied host -> device */
+} CgScanStats;
+
+/* ---------------------------------------------------------------------------------- *
+ *  Staged shards: the projected column chunks of a relation resident in HBM.
+ *  Replaces LoadFilteredStripeBuffers / LoadColumnBuffers / ColumnarStorageRead
+ *  (backend/columnar/columnar_reader.c:1007-1124, columnar_storage.c:463-492): each
+ *  (column, chunk) exists/value buffer is copied out of the 8 KB pages into pinned
+ *  memory at a 16-byte aligned slot and sent with cudaMemcpyAsync on a side stream.
+ * ---------------------------------------------------------------------------------- */
+typedef struct CgShard CgShard;
+
+/* columns: attribute indexes to stage (NULL/0 = all).  The call returns when the shard
+ * is resident.  Only CG_COMPRESSION_NONE chunks are accepted in this round
+ * (CG_EUNSUPPORTED otherwise). */
+int cg_shard_stage(const CgRelation *rel, const int32_t *columns, int32_t ncolumns, CgShard **out);
+void cg_shard_free(CgShard *shard);
+uint64_t cg_shard_device_bytes(const CgShard *shard);
+uint64_t cg_shard_rows(const CgShard *shard);
+
+/* ---------------------------------------------------------------------------------- *
+ *  Partial aggregate state: the device-resident group table a worker task accumulates
+ *  (PostgreSQL nodeAgg's hash table + transition values, and on the coordinator the
+ *  combine HashAggregate over sum(sum)/sum(count), multi_logical_optimizer.c:1807-1885,
+ *  2231-2275).  One CgPartial may accumulate several shards of the same GPU (legal for
+ *  the commutative/associative built-ins) or exactly one (a per-task result).
+ * ---------------------------------------------------------------------------------- */
+typedef struct CgPartial CgPartial;
+
+/* key_min/key_max: exact bounds of the (packed) group key over the data to be scanned,
+ * taken from the skip lists; when the domain is small the table is direct-indexed.
+ * Pass key_min > key_max to force the general hash table. */
+int cg_partial_create(const CgScanDesc *desc, const CgColumnDesc *columns, int32_t natts,
+					  int64_t key_min, int64_t key_max, int64_t max_rows, CgPartial **out);
+void cg_partial_free(CgPartial *p);
+int cg_partial_reset(CgPartial *p);
+
+/* Fused decode + filter + partial aggregate of one staged shard into `into`.
+ * Chunk-group skipping (SelectedChunkMask, columnar_reader.c:1132-1187) runs on the host
+ * from the skip nodes; surviving chunk groups are scanned by one kernel launch.
+ * stats may be NULL. The call is asynchronous with respect to the host unless stats is
+ * given (counters need the kernel to finish). */
+int cg_scan_shard(const CgShard *shard, const CgScanDesc *desc, CgPartial *into, CgScanStats *stats);
+
+/* End-to-end call on HOST buffers: stage (pipelined through pinned blocks) + scan.
+ * This is what a GpuColumnarAgg CustomScan node calls once per shard task. */
+int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, CgPartial *into, CgScanStats *stats);
+
+/* Result rows.  Group order is unspecified (it is a hash aggregate).
+ * For aggregate j of group i (index i*naggs + j):
+ *   sum_hi/sum_lo  128-bit integer sum (two's complement), or float8 sum in fsum
+ *   count          count(*) / count(x) value, or for sum/min/max the number of non-NULL
+ *                  inputs (0 => the SQL result is NULL)
+ *   minmax         min or max (integer, or float8 bits)
+ * Any output pointer may be NULL. */
+int cg_partial_ngroups(CgPartial *p, int64_t *ngroups);
+int cg_partial_fetch(CgPartial *p, int64_t capacity, int64_t *keys, uint8_t *key_nulls,
+					 int64_t *sum_hi, uint64_t *sum_lo, int64_t *count, int64_t *minmax,
+					 double *fsum, int64_t *ngroups);
+
+/* Raw accumulator export / merge, for the combine step and for collectives.
+ * A partial is `nwords` 64-bit accumulator words per group; every word is combined
+ * with one commutative op (add / min / max / float add), so partials of different
+ * shards or GPUs are merged word by word -- by this library (cg_partial_merge_rows)
+ * or by ncclReduce on the dense layout. */
+int cg_partial_layout(const CgPartial *p, int32_t *nwords, int32_t *word_ops /* [nwords] CG_WORD_* */,
+					  int32_t *is_dense, int64_t *capacity);
+enum { CG_WORD_ADD = 0, CG_WORD_MIN = 1, CG_WORD_MAX = 2, CG_WORD_FADD = 3, CG_WORD_FMIN = 4, CG_WORD_FMAX = 5 };
+
+/* Compact occupied groups into device arrays owned by the caller (e.g. torch tensors):
+ * d_keys[capacity], d_key_nulls[capacity] (may be NULL), d_words[capacity*nwords];
+ * *nrows on the host. */
+int cg_partial_export_device(CgPartial *p, int64_t capacity, int64_t *d_keys, uint8_t *d_key_nulls,
+							 uint64_t *d_words, int64_t *nrows);
+/* Merge rows (device arrays) into p: the coordinator-side combine kernel (K5). */
+int cg_partial_merge_rows(CgPartial *p, const int64_t *d_keys, const uint8_t *d_key_nulls,
+						  const uint64_t *d_words, int64_t nrows);
+/* Plain-aggregate and direct-indexed tables only: device pointer and length (in 64-bit
+ * words) of the whole accumulator array, laid out [entry][stride].  Two partials created
+ * with the same arguments have identical layouts, so when every word op is CG_WORD_ADD a
+ * collective (ncclReduce / ncclAllReduce, sum, int64) combines them in place. */
+int cg_partial_dense_words(CgPartial *p, uint64_t **d_words, int64_t *total_words, int32_t *stride);
+
+/* ---------------------------------------------------------------------------------- *
+ *  Hash repartition (map side): worker_partition_query_result's per-row routing
+ *  executor/partitioned_intermediate_results.c:493-553 + FindShardInterval
+ *  utils/shardinterval_utils.c:260-452.  Keys and payload are device arrays.
+ * ---------------------------------------------------------------------------------- */
+/* partition index of every row: NULL key -> 0, else binary search of hashint4/8(key) (or of
+ * the raw value for range partitioning) over [mins[i], maxs[i]].  key_len 4 or 8.
+ * d_index[n] (int32), d_counts[P] (int64).  Returns CG_EINVAL if a hash falls in no range. */
+int cg_partition_index(const int64_t *d_keys, const uint8_t *d_nulls, int64_t n, int32_t key_len,
+					   int32_t by_hash, const int32_t *mins, const int32_t *maxs, int32_t P,
+					   int32_t *d_index, int64_t *d_counts);
+/* Stable scatter of `ncols` int64 payload columns into partition-contiguous order:
+ * d_out[c][offsets[p] .. offsets[p+1]) holds partition p's rows in input order. */
+int cg_partition_scatter(const int32_t *d_index, int64_t n, int32_t P, const int64_t *const *d_cols,
+						 int32_t ncols, int64_t *const *d_out, int64_t *h_offsets /* [P+1] */);
+
+/* exact bounds from the skip lists (min/max of every chunk that survives chunk-group
+ * skipping): the packed group key range and |argument| of every aggregate (0 = unknown,
+ * e.g. a chunk without min/max).  Feed them to cg_partial_create / CgAggSpec.term_abs_bound. */
+int cg_relation_bounds(const CgRelation *rel, const CgScanDesc *desc, int64_t *key_min, int64_t *key_max,
+					   int64_t *term_abs_bound /* [naggs] */, int64_t *rows);
+
+/* ---------------------------------------------------------------------------------- *
+ *  Host-side helpers that belong to the path.
+ * ---------------------------------------------------------------------------------- */
+/* SelectedChunkMask (columnar_reader.c:1132-1187): mask[chunk] for one stripe; returns the
+ * number of chunk groups filtered through *filtered. */
+int cg_selected_chunk_mask(const CgRelation *rel, int32_t stripe_index, const CgScanDesc *desc,
+						   uint8_t *mask, int64_t *filtered);
+
+/* numeric text of a 128-bit integer with `scale` fractional digits (sum(numeric) output) and
+ * of the quotient sum/count with PostgreSQL's select_div_scale rule (avg output, the
+ * master-side sum(sum)/sum(count), multi_logical_optimizer.c:1807-1830).  buf >= 64 bytes. */
+int cg_numeric_out(int64_t hi, uint64_t lo, int32_t scale, char *buf, size_t buflen);
+int cg_numeric_div_out(int64_t hi, uint64_t lo, int32_t scale, int64_t count, char *buf, size_t buflen);
+
+/* ---------------------------------------------------------------------------------- *
+ *  Synthetic shard writer (bench / test tooling; the on-disk encoding of
+ *  backend/columnar/columnar_writer.c:391-654, compression none).
+ * ---------------------------------------------------------------------------------- */
+enum { CG_GEN_UNIFORM = 0, CG_GEN_SEQUENCE = 1 };
+typedef struct CgGenColumn
+{
+	int32_t attlen;
+	int32_t kind;           /* CG_GEN_* */
+	int64_t lo;             /* uniform in [lo, hi) / sequence start */
+	int64_t hi;
+	uint32_t null_ppm;      /* NULL probability in parts per million */
+	uint32_t reserved;
+} CgGenColumn;
+
+typedef struct CgGenRelation CgGenRelation;
+/* value(row, col) = lo + splitmix64(seed ^ col<<56 ^ (first_row+row)) % (hi-lo)
+ * null(row, col)  = splitmix64(~seed ^ col<<56 ^ (first_row+row)) % 1000000 < null_ppm */
+int cg_gen_relation(const CgGenColumn *cols, int32_t natts, uint64_t nrows, uint64_t first_row,
+					uint64_t seed, uint64_t stripe_row_limit, uint32_t chunk_row_limit,
+					int32_t nthreads, CgGenRelation **out);
+/* Encode caller-supplied columns (values[c][row] int64 / float8 bits, nulls[c] may be NULL). */
+int cg_write_relation(const CgColumnDesc *cols, int32_t natts, const int64_t *const *values,
+					  const uint8_t *const *nulls, uint64_t nrows, uint64_t stripe_row_limit,
+					  uint32_t chunk_row_limit, CgGenRelation **out);
+int cg_gen_relation_view(const CgGenRelation *g, CgRelation *view);
+void cg_gen_relation_free(CgGenRelation *g);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CITUS_GPU_H */

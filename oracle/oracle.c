@@ -290,6 +290,7 @@ typedef struct OrcTable
 	OrcSkipNode **w_nodes;   /* [col][chunk] */
 	uint32_t w_max_chunks;
 	uint32_t w_chunk_count;
+	int borrowed;               /* pages / stripes / nodes belong to the caller */
 } OrcTable;
 
 /* --- liblz4 / libzstd through dlopen (headers are not installed here) --- */
@@ -474,7 +475,7 @@ void orc_table_free(OrcTable *t)
 	free(t->w_exists); free(t->w_chunk_values); free(t->w_chunk_len); free(t->w_chunk_cap);
 	free(t->w_exists_buf); free(t->w_exists_len); free(t->w_value_buf); free(t->w_value_len); free(t->w_nodes);
 	free(t->attlen); free(t->atttype); free(t->attalign);
-	free(t->pages); free(t->stripes); free(t->nodes);
+	if (!t->borrowed) { free(t->pages); free(t->stripes); free(t->nodes); }
 	free(t);
 }
 
@@ -1209,4 +1210,47 @@ uint64_t orc_splitmix64(uint64_t x)
 	x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ULL;
 	x = (x ^ (x >> 27)) * 0x94d049bb133111ebULL;
 	return x ^ (x >> 31);
+}
+
+/* ------------------------------------------------------------------------- *
+ *  Attach to a relation image written by someone else (the product-side shard
+ *  writer): the oracle's reader then decodes / scans it independently.
+ *  OrcStripe / OrcSkipNode are field-for-field the reference's StripeMetadata /
+ *  ColumnChunkSkipNode subset, the same layout include/citus_gpu.h uses.
+ * ------------------------------------------------------------------------- */
+OrcTable *orc_table_attach(const uint8_t *pages, uint64_t nblocks, const OrcStripe *stripes, int nstripes,
+						   const OrcSkipNode *nodes, int nnodes, int natts, const int *attlen,
+						   const int *atttype, uint32_t chunk_row_limit)
+{
+	OrcTable *t = orc_table_create(natts, attlen, atttype, 150000, chunk_row_limit, ORC_COMP_NONE, 3);
+	free(t->pages);
+	t->pages = malloc(nblocks * ORC_BLCKSZ);
+	memcpy(t->pages, pages, nblocks * ORC_BLCKSZ);
+	t->nblocks = nblocks; t->cap_blocks = nblocks;
+	t->stripes = malloc(sizeof(OrcStripe) * (size_t) (nstripes ? nstripes : 1));
+	memcpy(t->stripes, stripes, sizeof(OrcStripe) * (size_t) nstripes);
+	t->nstripes = nstripes; t->cap_stripes = nstripes;
+	t->nodes = malloc(sizeof(OrcSkipNode) * (size_t) (nnodes ? nnodes : 1));
+	memcpy(t->nodes, nodes, sizeof(OrcSkipNode) * (size_t) nnodes);
+	t->nnodes = nnodes; t->cap_nodes = nnodes;
+	return t;
+}
+
+/* Same, without copying: the caller keeps the image alive (bench.py's cpu_baseline leg
+ * attaches to the 2 GB shard images the product-side generator already holds).
+ * nstripes may be smaller than the relation's stripe count: a bounded sample. */
+OrcTable *orc_table_attach_view(const uint8_t *pages, uint64_t nblocks, const OrcStripe *stripes, int nstripes,
+								const OrcSkipNode *nodes, int nnodes, int natts, const int *attlen,
+								const int *atttype, uint32_t chunk_row_limit)
+{
+	OrcTable *t = orc_table_create(natts, attlen, atttype, 150000, chunk_row_limit, ORC_COMP_NONE, 3);
+	free(t->pages);
+	t->pages = (uint8_t *) pages;
+	t->nblocks = nblocks; t->cap_blocks = nblocks;
+	t->stripes = (OrcStripe *) stripes;
+	t->nstripes = nstripes; t->cap_stripes = nstripes;
+	t->nodes = (OrcSkipNode *) nodes;
+	t->nnodes = nnodes; t->cap_nodes = nnodes;
+	t->borrowed = 1;
+	return t;
 }

@@ -110,6 +110,9 @@ def lib():
         L.orc_combine.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_decode_all.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_storage_read.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64]
+        L.orc_table_attach.restype = C.c_void_p
+        L.orc_table_attach.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_void_p, C.c_uint32]
         L.orc_splitmix64.restype = C.c_uint64
         L.orc_splitmix64.argtypes = [C.c_uint64]
         _lib = L
@@ -231,6 +234,43 @@ class Table:
         self.chunk_row_limit = chunk_row_limit
         self.h = lib().orc_table_create(self.natts, al, at, stripe_row_limit, chunk_row_limit,
                                         compression, compression_level)
+
+    @classmethod
+    def attach(cls, pages, stripes_bytes, nodes_bytes, attlen, atttype=None, chunk_row_limit=10000):
+        """read an image written by another writer (same struct layouts as the C-ABI)"""
+        self = cls.__new__(cls)
+        self.natts = len(attlen)
+        self.attlen = list(attlen)
+        self.atttype = list(atttype) if atttype is not None else [T_INT] * self.natts
+        self.chunk_row_limit = chunk_row_limit
+        pages = np.ascontiguousarray(pages, np.uint8)
+        sb = np.ascontiguousarray(stripes_bytes, np.uint8)
+        nb = np.ascontiguousarray(nodes_bytes, np.uint8)
+        al = (C.c_int * self.natts)(*self.attlen)
+        at = (C.c_int * self.natts)(*self.atttype)
+        self.h = lib().orc_table_attach(pages.ctypes.data, pages.shape[0] // 8192, sb.ctypes.data,
+                                        sb.shape[0] // C.sizeof(Stripe), nb.ctypes.data,
+                                        nb.shape[0] // C.sizeof(SkipNode), self.natts, al, at, chunk_row_limit)
+        return self
+
+    @classmethod
+    def attach_view(cls, pages_ptr, nblocks, stripes_ptr, nstripes, nodes_ptr, nnodes, attlen, atttype=None,
+                    chunk_row_limit=10000):
+        """borrow a resident image by raw pointers (no copy); nstripes may be a bounded sample"""
+        self = cls.__new__(cls)
+        self.natts = len(attlen)
+        self.attlen = list(attlen)
+        self.atttype = list(atttype) if atttype is not None else [T_INT] * self.natts
+        self.chunk_row_limit = chunk_row_limit
+        al = (C.c_int * self.natts)(*self.attlen)
+        at = (C.c_int * self.natts)(*self.atttype)
+        L = lib()
+        L.orc_table_attach_view.restype = C.c_void_p
+        L.orc_table_attach_view.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                            C.c_void_p, C.c_void_p, C.c_uint32]
+        self.h = L.orc_table_attach_view(pages_ptr, nblocks, stripes_ptr, nstripes, nodes_ptr, nnodes, self.natts,
+                                         al, at, chunk_row_limit)
+        return self
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -1,0 +1,426 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on the same
+inputs, and against the reference's golden vectors.  Bit-exact for COUNT / integer SUM /
+MIN / MAX / counters / partition indexes; float SUM within 1e-12 relative."""
+import ctypes as C
+import datetime
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+FLOAT_RTOL = 1e-12
+
+
+def pgdate(s):
+    y, m, d = map(int, s.split("-"))
+    return (datetime.date(y, m, d) - datetime.date(2000, 1, 1)).days
+
+
+@pytest.fixture(scope="module")
+def cg():
+    import torch
+    assert torch.cuda.is_available(), "these tests need the B200"
+    from citus_b200 import build
+    build.build()
+    from citus_b200 import columnar
+    columnar.init(0)
+    return columnar
+
+
+def oracle_table(oracle, rel, chunk_row_limit=10000):
+    descs = rel.column_descs()
+    return oracle.Table.attach(rel.pages(), rel.stripes_bytes(), rel.nodes_bytes(), [l for l, _ in descs],
+                               [t for _, t in descs], chunk_row_limit=chunk_row_limit)
+
+
+def to_oracle_aggs(oracle, aggs):
+    return [oracle.Agg(a.kind, list(a.factors), a.is_float) for a in aggs]
+
+
+def assert_same_groups(got, want, aggs, float_rtol=FLOAT_RTOL):
+    assert set(got.keys()) == set(want.keys())
+    for k in want:
+        for a, spec in enumerate(aggs):
+            g, w = got[k][a], want[k][a]
+            kind = spec.kind
+            if kind in (0, 1):                                  # count(*), count(x)
+                assert g["count"] == w["count"], (k, a)
+            elif kind == 2:                                     # sum
+                assert g["count"] == w["count"], (k, a)
+                if w["count"] == 0:
+                    continue
+                if spec.is_float:
+                    assert g["fsum"] == pytest.approx(w["fsum"], rel=float_rtol, abs=1e-300), (k, a)
+                else:
+                    assert g["sum"] == w["sum"], (k, a)
+            else:                                               # min / max
+                assert g["count"] == w["count"], (k, a)
+                if w["count"] == 0:
+                    continue
+                if spec.is_float:
+                    got_f = np.int64(g["minmax"]).view(np.float64)
+                    assert got_f == (w["fmin"] if kind == 3 else w["fmax"]), (k, a)
+                else:
+                    assert g["minmax"] == (w["min"] if kind == 3 else w["max"]), (k, a)
+
+
+def run_both(cg, oracle, rel, quals=(), group_cols=(), aggs=(), chunk_row_limit=10000, force_hash=False,
+             pushdown=True, float_cols=(), use_bounds=True, e2e=False, expected_groups=0):
+    d = cg.make_desc(quals, group_cols, aggs, qual_pushdown=pushdown, float_cols=float_cols,
+                     expected_groups=expected_groups)
+    kmin, kmax, bounds, rows = cg.relation_bounds(rel, d)
+    if use_bounds:
+        for i, a in enumerate(aggs):
+            a.term_abs_bound = bounds[i]
+        d = cg.make_desc(quals, group_cols, aggs, qual_pushdown=pushdown, float_cols=float_cols,
+                         expected_groups=expected_groups)
+    if force_hash:
+        kmin, kmax = 0, -1
+    agg = cg.GpuColumnarAgg(d, rel.column_descs(), kmin, kmax, max(rows, 1))
+    if e2e:
+        st = agg.scan_relation(rel)
+    else:
+        shard = cg.Shard(rel)
+        st = agg.scan_shard(shard)
+        shard.free()
+    t = oracle_table(oracle, rel, chunk_row_limit)
+    r = t.scan(list(quals), list(group_cols), to_oracle_aggs(oracle, aggs), qual_pushdown=pushdown)
+    assert st.rows_scanned == r.rows_scanned
+    assert st.rows_removed_by_filter == r.rows_removed_by_filter
+    assert st.chunk_groups_filtered == r.chunk_groups_filtered
+    assert st.rows_passed == r.rows_passed
+    got = agg.groups()
+    want = r.groups()
+    if not group_cols:
+        want = {0: want.get(0, [dict(sum=0, count=0, min=0, max=0, fsum=0.0, fmin=0.0, fmax=0.0)] * len(aggs))}
+        got = {0: list(got.values())[0]}
+    assert_same_groups(got, want, aggs)
+    agg.free()
+    return st, got
+
+
+# --------------------------------------------------------------------------- C1 shape
+@pytest.mark.parametrize("sorted_b", [False, True])
+def test_c1_sum_where_four_shards(cg, oracle, sorted_b):
+    """BASELINE config 1 at 1/10 scale: t(a,b,c,d int8) hash-distributed on d into 4 shards,
+    SELECT sum(a) WHERE b < k; workers produce partial sums, the coordinator sums them."""
+    n = 1_000_000
+    rng = np.random.default_rng(20260921)
+    a = rng.integers(-2**31, 2**31, n)
+    b = rng.integers(0, 10**6, n)
+    if sorted_b:
+        b = np.sort(b)
+    c = rng.integers(-2**62, 2**62, n)
+    d = np.arange(n)
+    mins, maxs = oracle.synthetic_intervals(4)
+    shard_of, _ = oracle.partition_rows(d, None, 8, "h", mins, maxs)
+    aggs = [cg.sum_(0), cg.count_star()]
+    total = 0
+    total_cnt = 0
+    want_total = 0
+    for s in range(4):
+        sel = shard_of == s
+        rel = cg.Relation.write([8, 8, 8, 8], [a[sel], b[sel], c[sel], d[sel]])
+        st, got = run_both(cg, oracle, rel, quals=[(1, "<", 250000)], aggs=aggs)
+        if sorted_b:
+            assert st.chunk_groups_filtered > 0
+        total += got[0][0]["sum"]
+        total_cnt += got[0][1]["count"]
+        want_total += int(a[sel][b[sel] < 250000].sum())
+    assert total == want_total == int(a[b < 250000].sum())
+    assert total_cnt == int((b < 250000).sum())
+
+
+def test_plain_aggregate_int128_and_empty_input(cg, oracle):
+    big = np.full(5000, 2**62, dtype=np.int64)
+    rel = cg.Relation.write([8, 8], [big, np.arange(5000)], chunk_row_limit=1000)
+    st, got = run_both(cg, oracle, rel, aggs=[cg.sum_(0), cg.min_(0), cg.max_(1)], chunk_row_limit=1000)
+    assert got[0][0]["sum"] == 5000 * 2**62
+    st, got = run_both(cg, oracle, rel, quals=[(1, "<", 0)], aggs=[cg.sum_(0), cg.count_star(), cg.count(0)],
+                       chunk_row_limit=1000)
+    assert got[0][0]["count"] == 0 and got[0][1]["count"] == 0       # sum over no rows is NULL
+    rel = cg.Relation.write([8], [np.zeros(0, np.int64)])
+    d = cg.make_desc(aggs=[cg.count_star(), cg.sum_(0)])
+    agg = cg.GpuColumnarAgg(d, rel.column_descs())
+    st = agg.scan_shard(cg.Shard(rel))
+    assert st.rows_scanned == 0
+    g = agg.groups()
+    assert list(g.values())[0][0]["count"] == 0
+
+
+# --------------------------------------------------------------------------- C2 shape
+@pytest.mark.parametrize("force_hash", [False, True])
+@pytest.mark.parametrize("null_ppm", [0, 50000])
+def test_c2_filter_group_by(cg, oracle, force_hash, null_ppm):
+    """BASELINE config 2 scaled down: 8 int8 columns, SELECT key, sum(v), count(*) WHERE f < 50 GROUP BY key"""
+    cols = [(8, 0, 0, 5000, 0), (8, 0, 0, 100, 0), (8, 0, -10**9, 10**9, null_ppm)] + [(8, 0, 0, 1 << 40, 0)] * 5
+    rel = cg.Relation.generate(cols, 345_678, seed=20260922)
+    run_both(cg, oracle, rel, quals=[(1, "<", 50)], group_cols=[0], aggs=[cg.sum_(2), cg.count_star()],
+             force_hash=force_hash, expected_groups=5000)
+    # same through the end-to-end call on host buffers
+    run_both(cg, oracle, rel, quals=[(1, "<", 50)], group_cols=[0], aggs=[cg.sum_(2), cg.count_star()],
+             force_hash=force_hash, expected_groups=5000, e2e=True)
+
+
+def test_group_by_wide_keys_null_keys_and_two_limb_sums(cg, oracle):
+    rng = np.random.default_rng(4)
+    n = 200_000
+    pool = rng.integers(-2**63, 2**63 - 1, 3000)
+    pool[0] = -2**63                                            # collides with the table's EMPTY sentinel
+    key = pool[rng.integers(0, 3000, n)]
+    keyn = (rng.random(n) < 0.01).astype(np.uint8)
+    v = rng.integers(-2**62, 2**62, n)                          # sums overflow int64: needs the two-word form
+    vn = (rng.random(n) < 0.3).astype(np.uint8)
+    rel = cg.Relation.write([8, 8], [key, v], [keyn, vn], stripe_row_limit=50000, chunk_row_limit=7000)
+    run_both(cg, oracle, rel, group_cols=[0], chunk_row_limit=7000, expected_groups=4000,
+             aggs=[cg.sum_(1), cg.count(1), cg.count_star(), cg.min_(1), cg.max_(1)])
+
+
+def test_hash_table_full_is_reported(cg):
+    from citus_b200 import capi
+    n = 100_000
+    rel = cg.Relation.write([8], [np.arange(n) * 7919])
+    d = cg.make_desc(group_cols=[0], aggs=[cg.count_star()], expected_groups=100)
+    agg = cg.GpuColumnarAgg(d, rel.column_descs())                # 1024 slots for 100000 groups
+    with pytest.raises(capi.CitusGpuError) as e:
+        agg.scan_shard(cg.Shard(rel))
+        agg.ngroups()
+    assert e.value.code == capi.CG_ETABLEFULL
+
+
+# --------------------------------------------------------------------------- goldens through the GPU
+def _filter_quals(where):
+    where = where.replace("WHERE", "").strip()
+    if not where:
+        return []
+    if "BETWEEN" in where:
+        lo, hi = where.split("BETWEEN")[1].split("AND")
+        return [(0, ">=", int(lo)), (0, "<=", int(hi))]
+    col, op, k = where.split()
+    return [(0, op, int(k))]
+
+
+def test_chunk_filtering_goldens(cg, oracle, expected):
+    one = np.arange(1, 10001)
+    rel1 = cg.Relation.write([4], [one], stripe_row_limit=2000, chunk_row_limit=1000)
+    for where, want in expected["chunk_filtering"][:9]:
+        st, _ = run_both(cg, oracle, rel1, quals=_filter_quals(where), aggs=[cg.count_star()], chunk_row_limit=1000)
+        assert st.rows_removed_by_filter == want, where
+    # the second INSERT starts a new stripe sequence: two images of 5 stripes each scanned into one partial
+    for where, want in expected["chunk_filtering"][9:]:
+        d = cg.make_desc(_filter_quals(where), aggs=[cg.count_star()])
+        agg = cg.GpuColumnarAgg(d, rel1.column_descs())
+        removed = 0
+        for _ in range(2):
+            removed += agg.scan_relation(rel1).rows_removed_by_filter
+        assert removed == want, where
+    for case in expected["simple_chunk_filtering"]:
+        rel = cg.Relation.write([4], [np.arange(0, case["max"] + 1)])
+        st, got = run_both(cg, oracle, rel, quals=[(0, ">", case["gt"])], aggs=[cg.count_star()])
+        assert (st.chunk_groups_filtered, st.rows_removed_by_filter, got[0][0]["count"]) == \
+            (case["groups_removed"], case["rows_removed"], case["actual_rows"])
+    st, _ = run_both(cg, oracle, rel, quals=[(0, ">", 123456)], aggs=[cg.count_star()], pushdown=False)
+    assert st.chunk_groups_filtered == 0
+
+
+def _lineitem_rels(cg, oracle, li):
+    mins, maxs = oracle.synthetic_intervals(2)
+    idx, _ = oracle.partition_rows(li["l_orderkey"], None, 8, "h", mins, maxs)
+    cols = ["l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_returnflag", "l_linestatus",
+            "l_shipdate", "l_suppkey"]
+    return [cg.Relation.write([8, 8, 8, 8, 1, 1, 4, 4], [li[c][idx == s] for c in cols],
+                              stripe_row_limit=2000, chunk_row_limit=1000) for s in range(2)]
+
+
+def test_tpch_q6_golden(cg, oracle, expected, lineitem):
+    quals = [(6, ">=", pgdate("1994-01-01")), (6, "<", pgdate("1995-01-01")), (2, ">=", 5), (2, "<=", 7), (0, "<", 2400)]
+    aggs = [cg.Agg(2, [(1, 0, 1), (2, 0, 1)])]
+    total = 0
+    for rel in _lineitem_rels(cg, oracle, lineitem):
+        _, got = run_both(cg, oracle, rel, quals=quals, aggs=aggs, chunk_row_limit=1000)
+        total += got[0][0]["sum"]                                # coordinator: sum(partial sums)
+    assert cg.numeric_out(total, 4) == expected["tpch_q6"]
+
+
+def test_tpch_q1_golden(cg, oracle, expected, lineitem):
+    quals = [(6, "<=", pgdate("1998-09-02"))]
+    aggs = [cg.sum_(0), cg.sum_(1), cg.Agg(2, [(1, 0, 1), (2, 100, -1)]),
+            cg.Agg(2, [(1, 0, 1), (2, 100, -1), (3, 100, 1)]), cg.sum_(2), cg.count_star()]
+    merged = {}
+    for rel in _lineitem_rels(cg, oracle, lineitem):
+        _, got = run_both(cg, oracle, rel, quals=quals, group_cols=[4, 5], aggs=aggs, chunk_row_limit=1000,
+                          expected_groups=16)
+        for k, per in got.items():
+            acc = merged.setdefault(k, [dict(sum=0, count=0) for _ in aggs])
+            for a in range(len(aggs)):
+                acc[a]["sum"] += per[a]["sum"]
+                acc[a]["count"] += per[a]["count"]
+    rows = []
+    for key, v in sorted(merged.items(), key=lambda kv: (kv[0] & 0xffffffff, kv[0] >> 32)):
+        rows.append([chr(key & 0xff), chr((key >> 32) & 0xff),
+                     cg.numeric_out(v[0]["sum"], 2), cg.numeric_out(v[1]["sum"], 2),
+                     cg.numeric_out(v[2]["sum"], 4), cg.numeric_out(v[3]["sum"], 6),
+                     cg.numeric_div_out(v[0]["sum"], 2, v[0]["count"]),
+                     cg.numeric_div_out(v[1]["sum"], 2, v[1]["count"]),
+                     cg.numeric_div_out(v[4]["sum"], 2, v[4]["count"]), str(v[5]["count"])])
+    assert rows == expected["tpch_q1"]
+
+
+def test_sum_int4_and_float_goldens(cg, oracle, expected, lineitem):
+    total = 0
+    for rel in _lineitem_rels(cg, oracle, lineitem):
+        _, got = run_both(cg, oracle, rel, aggs=[cg.sum_(7)], chunk_row_limit=1000)
+        total += got[0][0]["sum"]
+    assert str(total) == expected["sum_l_suppkey"]
+    f = np.array([float(r[0]) for r in expected["agg_type_data"]])
+    dd = np.array([float(r[1]) for r in expected["agg_type_data"]])
+    rel = cg.Relation.write([4, 8], [f, dd], type_classes=[1, 1])
+    for col, exp in ((0, expected["agg_type_float"]), (1, expected["agg_type_double"])):
+        aggs = [cg.min_(col, True), cg.max_(col, True), cg.sum_(col, True), cg.count(col)]
+        _, got = run_both(cg, oracle, rel, aggs=aggs, float_cols=(0, 1))
+        g = got[0]
+        assert np.int64(g[0]["minmax"]).view(np.float64) == pytest.approx(float(exp[0]), rel=1e-12)
+        assert np.int64(g[1]["minmax"]).view(np.float64) == pytest.approx(float(exp[1]), rel=1e-12)
+        assert g[2]["fsum"] == pytest.approx(float(exp[2]), rel=1e-12)
+        assert g[3]["count"] == int(exp[3])
+
+
+# --------------------------------------------------------------------------- types, NULLs, ragged shapes
+def test_mixed_widths_with_nulls(cg, oracle):
+    rng = np.random.default_rng(8)
+    n = 123_457
+    c8 = rng.integers(-2**50, 2**50, n)
+    c4 = rng.integers(-2**31, 2**31, n)
+    c2 = rng.integers(-2**15, 2**15, n)
+    c1 = rng.integers(-128, 128, n)
+    f8 = rng.normal(size=n)
+    f4 = rng.normal(size=n).astype(np.float32).astype(np.float64)
+    nulls = [(rng.random(n) < p).astype(np.uint8) for p in (0.1, 0.5, 0.0, 0.9, 0.2, 0.05)]
+    nulls[2] = None
+    nulls[0][20000:31000] = 1                                   # a chunk group that is entirely NULL
+    rel = cg.Relation.write([8, 4, 2, 1, 8, 4], [c8, c4, c2, c1, f8, f4], nulls, type_classes=[0, 0, 0, 0, 1, 1])
+    aggs = [cg.sum_(0), cg.min_(1), cg.max_(1), cg.sum_(3), cg.count(3), cg.sum_(4, True), cg.min_(5, True), cg.max_(4, True)]
+    run_both(cg, oracle, rel, quals=[(2, ">", -20000), (4, "<", 1.5)], aggs=aggs, float_cols=(4, 5))
+    run_both(cg, oracle, rel, quals=[(5, ">=", -0.25)], group_cols=[3], aggs=aggs[:5] + [cg.count_star()], float_cols=(4, 5))
+    run_both(cg, oracle, rel, quals=[(1, "<>", 0)], group_cols=[3], aggs=[cg.count_star(), cg.sum_(1)],
+             float_cols=(4, 5), force_hash=True, expected_groups=300)
+
+
+def test_ragged_chunks_and_max_chunk_size(cg, oracle):
+    rng = np.random.default_rng(12)
+    for n, stripe, chunk in ((1, 1000, 1000), (999, 1000, 1000), (1001, 1000, 1000), (250_001, 200_000, 100_000)):
+        a = rng.integers(-1000, 1000, n)
+        b = rng.integers(0, 10, n)
+        nb = (rng.random(n) < 0.3).astype(np.uint8)
+        rel = cg.Relation.write([8, 8], [a, b], [None, nb], stripe_row_limit=stripe, chunk_row_limit=chunk)
+        run_both(cg, oracle, rel, quals=[(0, ">=", -500)], group_cols=[1], aggs=[cg.count_star(), cg.sum_(0)],
+                 chunk_row_limit=chunk)
+        run_both(cg, oracle, rel, aggs=[cg.count_star(), cg.sum_(0), cg.count(1)], chunk_row_limit=chunk, e2e=True)
+
+
+def test_unsupported_inputs_are_refused(cg, oracle):
+    from citus_b200 import capi
+    t = oracle.Table([8], compression=oracle.COMP_LZ4)
+    t.insert([np.arange(50000) % 7])
+    rel = cg.Relation.from_image(t.pages(), t.stripes_array(), t.nodes_array(), [8])
+    with pytest.raises(capi.CitusGpuError) as e:
+        cg.Shard(rel)
+    assert e.value.code == capi.CG_EUNSUPPORTED
+    rel = cg.Relation.write([8], [np.arange(10)])
+    with pytest.raises(capi.CitusGpuError):
+        cg.GpuColumnarAgg(cg.make_desc(aggs=[cg.sum_(3)]), rel.column_descs())     # column out of range
+    corrupt = rel.pages().copy()
+    corrupt[2 * 8192 + 12: 2 * 8192 + 14] = 0                                    # pd_lower of the first data page
+    bad = cg.Relation.from_image(corrupt, rel.stripes_bytes(), rel.nodes_bytes(), [8])
+    with pytest.raises(capi.CitusGpuError) as e:
+        cg.Shard(bad)
+    assert e.value.code == capi.CG_ECORRUPT
+
+
+# --------------------------------------------------------------------------- combine (K5)
+def test_combine_partials_of_four_shards(cg, oracle):
+    import torch
+    cols = [(8, 0, 0, 3000, 0), (8, 0, 0, 100, 0), (8, 0, -10**12, 10**12, 20000)]
+    aggs = [cg.sum_(2), cg.count_star(), cg.min_(2), cg.max_(2)]
+    for force_hash in (False, True):
+        d = cg.make_desc([(1, "<", 50)], [0], aggs, expected_groups=4000)
+        rels = [cg.Relation.generate(cols, 100_000 + s, seed=77, first_row=s * 10**6) for s in range(4)]
+        kmin, kmax = (0, 2999) if not force_hash else (0, -1)
+        final = cg.GpuColumnarAgg(d, rels[0].column_descs(), kmin, kmax, 10**6)
+        want = None
+        for rel in rels:
+            part = cg.GpuColumnarAgg(d, rel.column_descs(), kmin, kmax, 10**6)      # one worker task
+            part.scan_shard(cg.Shard(rel))
+            nw, ops, dense, cap = part.layout()
+            n = part.ngroups()
+            keys = torch.empty(n, dtype=torch.int64, device="cuda")
+            kn = torch.empty(n, dtype=torch.uint8, device="cuda")
+            words = torch.empty(n * nw, dtype=torch.int64, device="cuda")
+            assert part.export_device(keys.data_ptr(), kn.data_ptr(), words.data_ptr(), n) == n
+            final.merge_rows(keys.data_ptr(), kn.data_ptr(), words.data_ptr(), n)   # coordinator combine
+            r = oracle_table(oracle, rel).scan([(1, "<", 50)], [0], to_oracle_aggs(oracle, aggs))
+            if want is None:
+                want = r
+            else:
+                want.combine(r)
+        assert_same_groups(final.groups(), want.groups(), aggs)
+
+
+# --------------------------------------------------------------------------- hash repartition (K6)
+def _partition(cg, keys, nulls, key_len, method, mins, maxs):
+    import torch
+    dk = torch.from_numpy(np.ascontiguousarray(keys, np.int64)).cuda()
+    dn = torch.from_numpy(np.ascontiguousarray(nulls, np.uint8)).cuda() if nulls is not None else None
+    idx = torch.empty(len(keys), dtype=torch.int32, device="cuda")
+    cnt = torch.empty(len(mins), dtype=torch.int64, device="cuda")
+    cg.worker_partition_query_result(dk.data_ptr(), dn.data_ptr() if dn is not None else None, len(keys), key_len,
+                                     method, mins, maxs, idx.data_ptr(), cnt.data_ptr())
+    torch.cuda.synchronize()
+    return idx, cnt, dk
+
+
+def test_partition_goldens(cg, oracle, expected):
+    i = np.arange(1, 11)
+    idx, cnt, _ = _partition(cg, i, None, 4, "hash", expected["squares_hash_mins"], expected["squares_hash_maxs"])
+    idx = idx.cpu().numpy()
+    for p in range(4):
+        assert i[idx == p].tolist() == expected["squares_hash_members"][p]
+    i = np.arange(1, 1000001)
+    idx, cnt, _ = _partition(cg, i, None, 4, "hash", expected["squares_hash_mins"], expected["squares_hash_maxs"])
+    assert cnt.cpu().tolist() == [r[1] for r in expected["doubles_hash_text"]]
+    idx, cnt, _ = _partition(cg, i, None, 4, "range", [0, 250001, 500001, 750001], [250000, 500000, 750000, 1000000])
+    assert cnt.cpu().tolist() == [r[1] for r in expected["doubles_range_binary"]]
+    # edge keys that hash to INT32_MAX / INT32_MIN (distributed_planning.out:12-33)
+    mins, maxs = oracle.synthetic_intervals(32)
+    idx, cnt, _ = _partition(cg, np.array([2608474032, 963809240]), None, 8, "hash", mins, maxs)
+    assert idx.cpu().tolist() == [31, 0]
+
+
+def test_partition_parity_and_scatter(cg, oracle):
+    import torch
+    rng = np.random.default_rng(6)
+    n = 1_234_567
+    keys = rng.integers(-2**63, 2**63 - 1, n)
+    nulls = (rng.random(n) < 0.01).astype(np.uint8)
+    payload = rng.integers(-2**40, 2**40, n)
+    for P in (1, 3, 32, 257):
+        mins, maxs = oracle.synthetic_intervals(P)
+        idx, cnt, dk = _partition(cg, keys, nulls, 8, "hash", mins, maxs)
+        want_idx, want_rows = oracle.partition_rows(keys, nulls, 8, "h", mins, maxs)
+        assert np.array_equal(idx.cpu().numpy(), want_idx)
+        assert np.array_equal(cnt.cpu().numpy(), want_rows)
+        dp = torch.from_numpy(payload).cuda()
+        ok = torch.empty_like(dk)
+        op = torch.empty_like(dp)
+        offs = cg.partition_scatter(idx.data_ptr(), n, P, [dk.data_ptr(), dp.data_ptr()], [ok.data_ptr(), op.data_ptr()])
+        assert np.array_equal(np.diff(offs), want_rows)
+        ok, op = ok.cpu().numpy(), op.cpu().numpy()
+        for p in (0, P // 2, P - 1):
+            sel = want_idx == p                                   # stable: input order inside a partition
+            assert np.array_equal(ok[offs[p]:offs[p + 1]], keys[sel])
+            assert np.array_equal(op[offs[p]:offs[p + 1]], payload[sel])
+    # a hash that falls in no interval is an error, like the reference's ereport
+    from citus_b200 import capi
+    with pytest.raises(capi.CitusGpuError):
+        _partition(cg, np.arange(100), None, 8, "hash", [0], [10])
