@@ -275,7 +275,7 @@ class GpuColumnarAgg:
 
     def layout(self):
         nw, dense, cap = C.c_int32(), C.c_int32(), C.c_int64()
-        ops = (C.c_int32 * 16)()
+        ops = (C.c_int32 * 32)()
         check(lib().cg_partial_layout(self.h, C.byref(nw), ops, C.byref(dense), C.byref(cap)))
         return nw.value, [ops[i] for i in range(nw.value)], bool(dense.value), cap.value
 

@@ -587,6 +587,13 @@ extern "C" uint64_t cg_shard_rows(const CgShard *sh) { return sh ? sh->rows : 0;
 /* ------------------------------------------------------------------------------ *
  *  Scan driver.
  * ------------------------------------------------------------------------------ */
+static bool cg_force_general(void)
+{
+	static int v = -1;
+	if (v < 0) { const char *e = getenv("CG_FORCE_GENERAL_KERNEL"); v = (e && atoi(e)) ? 1 : 0; }
+	return v == 1;
+}
+
 static int check_error_flags(CgPartial *p, unsigned long long flags)
 {
 	if (flags & CG_ERRFLAG_TABLE_FULL)
@@ -630,30 +637,45 @@ extern "C" int cg_scan_shard(const CgShard *sh, const CgScanDesc *desc, CgPartia
 	/* K2 on the host: SelectedChunkMask per stripe.  The list of surviving chunk groups is
 	 * kept on the device and reused while the WHERE list stays the same. */
 	CgShard *msh = const_cast<CgShard *>(sh);
+	std::vector<uint8_t> slots(plan.slot, plan.slot + plan.ncols);
 	bool same = msh->sel_valid && msh->sel_pushdown == desc->enable_qual_pushdown && msh->sel_nquals == desc->nquals &&
-				memcmp(msh->sel_quals, desc->quals, sizeof(CgQual) * desc->nquals) == 0;
+				memcmp(msh->sel_quals, desc->quals, sizeof(CgQual) * desc->nquals) == 0 && msh->sel_slots == slots;
 	if (!same)
 	{
-		std::vector<uint32_t> selected;
-		selected.reserve(sh->nchunkgroups);
-		int64_t filtered = 0;
+		std::vector<uint32_t> fastl, slowl;
+		fastl.reserve(sh->nchunkgroups);
+		int64_t nfiltered = 0;
 		std::vector<uint8_t> mask;
+		size_t ns = sh->staged.size();
 		for (size_t si = 0; si < sh->stripes.size(); si++)
 		{
 			const CgStripe &s = sh->stripes[si];
 			mask.resize(s.chunk_count);
-			stripe_chunk_mask(s, sh->nodes.data(), sh->columns.data(), sh->natts, desc, mask.data(), &filtered);
+			stripe_chunk_mask(s, sh->nodes.data(), sh->columns.data(), sh->natts, desc, mask.data(), &nfiltered);
 			for (uint32_t k = 0; k < s.chunk_count; k++)
-				if (mask[k]) selected.push_back((uint32_t) (sh->stripe_first_cg[si] + k));
+			{
+				if (!mask[k]) continue;
+				uint64_t cg = sh->stripe_first_cg[si] + k;
+				bool nulls = false;
+				for (int c = 0; c < plan.ncols; c++)
+				{
+					const DevChunkCol &d = sh->h_chunkcols[cg * ns + plan.slot[c]];
+					if (d.value_count != d.row_count) nulls = true;
+				}
+				(nulls ? slowl : fastl).push_back((uint32_t) cg);
+			}
 		}
+		msh->sel_nfast = (uint32_t) fastl.size();
+		fastl.insert(fastl.end(), slowl.begin(), slowl.end());
 		CG_CUDA(cudaStreamSynchronize(ctx->compute));     /* an earlier scan may still read the old list */
-		if (!selected.empty())
-			CG_CUDA(cudaMemcpy(msh->d_selected, selected.data(), selected.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-		msh->h_selected.swap(selected);
-		msh->sel_filtered = filtered;
+		if (!fastl.empty())
+			CG_CUDA(cudaMemcpy(msh->d_selected, fastl.data(), fastl.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+		msh->h_selected.swap(fastl);
+		msh->sel_filtered = nfiltered;
 		msh->sel_pushdown = desc->enable_qual_pushdown;
 		msh->sel_nquals = desc->nquals;
 		memcpy(msh->sel_quals, desc->quals, sizeof(CgQual) * desc->nquals);
+		msh->sel_slots = slots;
 		msh->sel_valid = true;
 	}
 	const std::vector<uint32_t> &selected = sh->h_selected;
@@ -675,11 +697,25 @@ extern "C" int cg_scan_shard(const CgShard *sh, const CgScanDesc *desc, CgPartia
 		plan.nstaged = (int32_t) sh->staged.size();
 		plan.selected = sh->d_selected;
 		plan.nselected = (uint32_t) selected.size();
+		FPlan fast;
+		bool use_fast = !cg_force_general() && cg_build_fast_plan(desc, plan, all8, &fast);
+		uint32_t nfast = use_fast ? sh->sel_nfast : 0;
 		if (stats) CG_CUDA(cudaEventRecord(ctx->ev_a, ctx->compute));
 		rc = cg_prof_mark(ctx, ctx->compute);
 		if (rc) return rc;
-		rc = cg_launch_scan(ctx, plan, true, all8, ctx->compute);
-		if (rc) return rc;
+		if (nfast > 0)
+		{
+			fast.nselected = nfast;
+			rc = cg_launch_scan_fast(ctx, fast, ctx->compute);
+			if (rc) return rc;
+		}
+		if (nfast < plan.nselected)
+		{
+			plan.selected = sh->d_selected + nfast;
+			plan.nselected -= nfast;
+			rc = cg_launch_scan(ctx, plan, true, all8, ctx->compute);
+			if (rc) return rc;
+		}
 		rc = cg_prof_mark(ctx, ctx->compute);
 		if (rc) return rc;
 		if (stats) CG_CUDA(cudaEventRecord(ctx->ev_b, ctx->compute));
@@ -773,6 +809,8 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 		plan.arena = d_arena;
 		plan.chunkcols = d_cols;
 		plan.nstaged = (int32_t) ns;
+		FPlan fast;
+		const bool use_fast = !sp.any_nulls && !cg_force_general() && cg_build_fast_plan(desc, plan, all8, &fast);
 		if (stats) CG_CUDA(cudaEventRecord(ctx->ev_a, ctx->compute));
 		rc = stream_to_device(ctx, rel, sp, ns, d_arena, [&](uint64_t cg0, uint64_t cg1, cudaEvent_t copied) -> int {
 			CG_CUDA(cudaStreamWaitEvent(ctx->compute, copied, 0));
@@ -781,12 +819,22 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 				int r = cg_launch_rank(ctx, d_arena, d_cols, cg0 * ns, (cg1 - cg0) * ns, ctx->compute);
 				if (r) return r;
 			}
-			KPlan blk = plan;
-			blk.selected = d_ids + cg0;
-			blk.nselected = (uint32_t) (cg1 - cg0);
 			int r = cg_prof_mark(ctx, ctx->compute);
 			if (r) return r;
-			r = cg_launch_scan(ctx, blk, sp.any_nulls, all8, ctx->compute);
+			if (use_fast)
+			{
+				FPlan blk = fast;
+				blk.selected = d_ids + cg0;
+				blk.nselected = (uint32_t) (cg1 - cg0);
+				r = cg_launch_scan_fast(ctx, blk, ctx->compute);
+			}
+			else
+			{
+				KPlan blk = plan;
+				blk.selected = d_ids + cg0;
+				blk.nselected = (uint32_t) (cg1 - cg0);
+				r = cg_launch_scan(ctx, blk, sp.any_nulls, all8, ctx->compute);
+			}
 			if (r) return r;
 			return cg_prof_mark(ctx, ctx->compute);
 		});

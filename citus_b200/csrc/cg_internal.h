@@ -94,6 +94,9 @@ struct CgShard
 	int32_t sel_pushdown = 0, sel_nquals = 0;
 	CgQual sel_quals[CG_MAX_QUALS];
 	int64_t sel_filtered = 0;
+	/* the list is ordered [chunk groups without NULLs in the plan columns | the rest] */
+	std::vector<uint8_t> sel_slots;
+	uint32_t sel_nfast = 0;
 	uint64_t algorithmic_bytes_per_cg_col(uint64_t cg, int slot) const
 	{
 		const DevChunkCol &c = h_chunkcols[cg * staged.size() + slot];
@@ -105,7 +108,7 @@ struct CgShard
  *  Kernel plan (passed by value as a __grid_constant__ parameter).
  * ------------------------------------------------------------------------------ */
 #define CG_KMAX_COLS 8
-#define CG_KMAX_WORDS 16
+#define CG_KMAX_WORDS 32
 
 enum { CG_MODE_GLOBAL = 0, CG_MODE_DENSE = 1, CG_MODE_HASH = 2 };
 
@@ -163,6 +166,33 @@ struct KPlan
 	unsigned long long *stats;    /* [0] rows scanned [1] rows removed [2] error flags */
 };
 
+/* plan of the specialised kernel (cg_scan_fast.cu): column roles in fixed order
+ * [range quals..., group key, summed columns...] */
+struct FPlan
+{
+	const uint8_t *arena;
+	const DevChunkCol *chunkcols;
+	const uint32_t *selected;
+	uint32_t nselected;
+	int32_t nstaged;
+	int32_t nquals, nsums, mode;
+	uint32_t flags;               /* CG_FAST_* */
+	uint8_t slot[6];
+	uint8_t qneg[2];
+	uint8_t slimbs[3];
+	uint8_t sword[3];
+	int64_t qlo[2], qhi[2];
+	int64_t sbound[3];
+	uint64_t *table;
+	uint64_t capacity;
+	int32_t stride;
+	int64_t key_min;
+	unsigned long long *stats;
+};
+
+#define CG_FAST_PAIRED 1u       /* pair lanes so that one reduction instruction covers both words of a group */
+#define CG_FAST_NO_HINTS 2u     /* disable the L2 eviction hints (A/B measurements) */
+
 #define CG_HASH_EMPTY ((int64_t) 0x8000000000000000ull)
 #define CG_ERRFLAG_TABLE_FULL 1ull
 #define CG_ERRFLAG_NULL_MULTIKEY 2ull
@@ -194,6 +224,8 @@ struct CgPartial
 
 /* cg_scan.cu */
 int cg_launch_scan(CgContext *ctx, const KPlan &plan, bool any_nulls, bool all8, cudaStream_t stream);
+/* cg_scan_fast.cu */
+int cg_launch_scan_fast(CgContext *ctx, const FPlan &plan, cudaStream_t stream);
 int cg_launch_rank(CgContext *ctx, const uint8_t *arena, const DevChunkCol *chunkcols, uint64_t first,
 				   uint64_t count, cudaStream_t stream);
 int cg_launch_table_init(CgPartial *p, cudaStream_t stream);
@@ -203,6 +235,7 @@ int cg_launch_merge(CgPartial *p, const int64_t *d_keys, const uint8_t *d_nulls,
 					int64_t nrows, cudaStream_t stream);
 
 /* cg_plan.cpp */
+bool cg_build_fast_plan(const CgScanDesc *desc, const KPlan &plan, bool all8, FPlan *fast);
 int cg_build_plan(const CgScanDesc *desc, const CgColumnDesc *columns, int natts,
 				  const std::vector<int32_t> *slot_of_att, CgPartial *partial, KPlan *plan,
 				  bool *all8);

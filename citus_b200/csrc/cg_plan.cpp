@@ -9,7 +9,10 @@
  * strict transition functions skip NULL inputs; sum/min/max over no non-NULL input is NULL.
  */
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <algorithm>
 
 #include "cg_internal.h"
 
@@ -68,7 +71,7 @@ static int validate_desc(const CgScanDesc *d, const CgColumnDesc *columns, int n
 			if (s.column[f] < 0 || s.column[f] >= natts)
 				return cg_set_error(CG_EINVAL, "aggregate %d: column out of range", a);
 			bool colf = columns[s.column[f]].type_class == CG_TYPE_FLOAT;
-			if (colf != (s.is_float != 0))
+			if (s.kind != CG_AGG_COUNT && colf != (s.is_float != 0))
 				return cg_set_error(CG_EINVAL, "aggregate %d: integer/float mismatch with column %d", a, s.column[f]);
 		}
 	}
@@ -164,10 +167,10 @@ extern "C" int cg_partial_create(const CgScanDesc *desc, const CgColumnDesc *col
 		p->mode = CG_MODE_GLOBAL;
 		p->capacity = 1; p->entries = 1; p->stride = p->nwords;
 	}
-	else if (key_min <= key_max && (uint64_t) (key_max - key_min) < kDenseLimit)
+	else if (key_min <= key_max && ((uint64_t) key_max - (uint64_t) key_min) < kDenseLimit)
 	{
 		p->mode = CG_MODE_DENSE;
-		p->capacity = (uint64_t) (key_max - key_min) + 1;
+		p->capacity = ((uint64_t) key_max - (uint64_t) key_min) + 1;
 		p->entries = p->capacity + 1;            /* + the NULL group */
 		int s = 1; while (s < p->nwords) s <<= 1;   /* power-of-two stride: an entry never straddles a sector pair */
 		p->stride = s;
@@ -307,4 +310,93 @@ int cg_build_plan(const CgScanDesc *desc, const CgColumnDesc *columns, int natts
 	memcpy(plan->wordop, partial->wordop, sizeof plan->wordop);
 	plan->stats = partial->d_stats;
 	return CG_OK;
+}
+
+
+/*
+ * Specialised-kernel eligibility: 8-byte integer columns only; the WHERE list reduces to at
+ * most two column ranges (btree conjuncts on one column intersect; a lone <> is a negated
+ * point range); at most one group column; aggregates are count(*) and up to three
+ * sum(column); every column plays exactly one role.  Anything else runs on the general
+ * kernel.  NULLs are handled outside: the fast kernel only sees chunk groups whose plan
+ * columns have none.
+ */
+bool cg_build_fast_plan(const CgScanDesc *desc, const KPlan &plan, bool all8, FPlan *fast)
+{
+	if (!all8 || plan.ngroup > 1) return false;
+	for (int c = 0; c < plan.ncols; c++) if (plan.isfloat[c]) return false;
+	memset(fast, 0, sizeof *fast);
+	bool used[CG_KMAX_COLS] = {false};
+	int role = 0;
+
+	/* ranges per plan column */
+	int qcols[CG_KMAX_COLS]; int nqc = 0;
+	int64_t lo[CG_KMAX_COLS], hi[CG_KMAX_COLS]; bool neg[CG_KMAX_COLS]; int nconj[CG_KMAX_COLS];
+	for (int q = 0; q < plan.nquals; q++)
+	{
+		int c = plan.qcol[q], i;
+		for (i = 0; i < nqc; i++) if (qcols[i] == c) break;
+		if (i == nqc) { qcols[nqc] = c; lo[i] = INT64_MIN; hi[i] = INT64_MAX; neg[i] = false; nconj[i] = 0; nqc++; }
+		int64_t k = plan.qk[q];
+		if (neg[i]) return false;
+		nconj[i]++;
+		switch (plan.qop[q])
+		{
+			case CG_OP_LT: if (k == INT64_MIN) { lo[i] = 1; hi[i] = 0; } else hi[i] = std::min(hi[i], k - 1); break;
+			case CG_OP_LE: hi[i] = std::min(hi[i], k); break;
+			case CG_OP_EQ: lo[i] = std::max(lo[i], k); hi[i] = std::min(hi[i], k); break;
+			case CG_OP_GE: lo[i] = std::max(lo[i], k); break;
+			case CG_OP_GT: if (k == INT64_MAX) { lo[i] = 1; hi[i] = 0; } else lo[i] = std::max(lo[i], k + 1); break;
+			default:
+				if (nconj[i] != 1) return false;
+				neg[i] = true; lo[i] = hi[i] = k;
+				break;
+		}
+	}
+	if (nqc > 2) return false;
+	for (int i = 0; i < nqc; i++)
+	{
+		if (lo[i] > hi[i]) { lo[i] = 1; hi[i] = 0; }     /* empty range: nothing passes */
+		fast->slot[role++] = plan.slot[qcols[i]];
+		fast->qlo[i] = lo[i]; fast->qhi[i] = hi[i]; fast->qneg[i] = neg[i];
+		used[qcols[i]] = true;
+	}
+	fast->nquals = nqc;
+	if (plan.ngroup == 1)
+	{
+		if (used[plan.gcol[0]]) return false;
+		used[plan.gcol[0]] = true;
+		fast->slot[role++] = plan.slot[plan.gcol[0]];
+	}
+	int ns = 0;
+	for (int a = 0; a < plan.naggs; a++)
+	{
+		const KAgg &g = plan.aggs[a];
+		if (g.kind == CG_AGG_COUNT_STAR) continue;
+		if (g.kind != CG_AGG_SUM || g.is_float || g.nfactors != 1 || g.a[0] != 0 || g.b[0] != 1) return false;
+		if (ns == 3 || used[g.pcol[0]]) return false;
+		used[g.pcol[0]] = true;
+		fast->slot[role++] = plan.slot[g.pcol[0]];
+		fast->sword[ns] = (uint8_t) g.word0;
+		fast->slimbs[ns] = (uint8_t) g.nlimbs;
+		fast->sbound[ns] = g.bound;
+		ns++;
+	}
+	fast->nsums = ns;
+	fast->mode = plan.mode;
+	{
+		/* tuning switches (measurements only): CG_FAST_FLAGS overrides the default */
+		static int env_flags = -1;
+		if (env_flags < 0) { const char *e = getenv("CG_FAST_FLAGS"); env_flags = e ? atoi(e) : (int) CG_FAST_PAIRED; }
+		fast->flags = (uint32_t) env_flags;
+		bool single = true;
+		for (int i = 0; i < ns; i++) if (fast->slimbs[i] != 1) single = false;
+		if (!single) fast->flags &= ~CG_FAST_PAIRED;
+	}
+	fast->arena = plan.arena; fast->chunkcols = plan.chunkcols; fast->selected = plan.selected;
+	fast->nselected = plan.nselected; fast->nstaged = plan.nstaged;
+	fast->table = plan.table; fast->capacity = plan.capacity; fast->stride = plan.stride;
+	fast->key_min = plan.key_min; fast->stats = plan.stats;
+	(void) desc;
+	return true;
 }

@@ -1,0 +1,392 @@
+/*
+ * cg_scan_fast.cu -- the specialised form of the fused scan kernel for the shape that
+ * dominates analytic shard tasks (BASELINE configs 1-3):
+ *
+ *     SELECT [key,] count(*), sum(c1) [, sum(c2), sum(c3)] FROM shard
+ *     WHERE q0 BETWEEN lo0 AND hi0 [AND q1 BETWEEN lo1 AND hi1] [GROUP BY key]
+ *
+ * over 8-byte integer columns, for chunk groups without NULLs in the columns read
+ * (chunk groups that have NULLs go through the general kernel in cg_scan.cu into the same
+ * accumulators).  Same semantics and same reference citations as cg_scan.cu (K1 decode of
+ * the NULL-free value stream = a dense int8 array, columnar_reader.c:1542-1572; K3 ExecQual;
+ * K4 nodeAgg transition functions), but the plan shape is a template parameter, so the
+ * per-row work is a handful of instructions: the kernel is bound by HBM loads and by the
+ * L2 atomic units, not by instruction issue.
+ *
+ *   NQ    range conjuncts, each on its own column (several btree conjuncts on one column
+ *         are intersected into one [lo, hi] on the host)
+ *   MODE  plain aggregate / direct-indexed table / hash table
+ *   NS    sum(column) aggregates
+ * Column roles map to fixed register positions: quals first, then the key, then the sums.
+ */
+#include "cg_internal.h"
+
+#define CGF_THREADS 256
+
+/* streaming column data: read-only path, no L1 allocation, first to leave L2 -- each byte is
+ * used once and must not push the group table out of the 126 MB L2 */
+__device__ __forceinline__ void ldg16(const void *p, uint64_t &a, uint64_t &b, uint64_t policy)
+{
+	asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(a), "=l"(b) : "l"(p), "l"(policy));
+}
+
+/* group-table update: fire-and-forget reduction at the L2 atomic unit, line kept in L2 */
+__device__ __forceinline__ void red_add_u64(uint64_t *p, uint64_t v, uint64_t policy)
+{
+	asm volatile("red.global.add.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(policy) : "memory");
+}
+
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+	uint64_t pol;
+	asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_last()
+{
+	uint64_t pol;
+	asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_normal()
+{
+	uint64_t pol;
+	asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
+
+__device__ __forceinline__ uint64_t mix64f(uint64_t x)
+{
+	x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+	return x;
+}
+
+template <int MODE>
+__device__ __forceinline__ uint64_t *fast_entry(const FPlan &P, int64_t key)
+{
+	if (MODE == CG_MODE_DENSE)
+	{
+		uint64_t slot = (uint64_t) key - (uint64_t) P.key_min;
+		if (slot >= P.capacity)
+		{
+			atomicOr(P.stats + 2, CG_ERRFLAG_KEY_RANGE);
+			return nullptr;
+		}
+		return P.table + slot * (uint64_t) P.stride;
+	}
+	else
+	{
+		if (key == CG_HASH_EMPTY) return P.table + (P.capacity + 1) * (uint64_t) P.stride + 1;
+		uint64_t mask = P.capacity - 1;
+		uint64_t h = mix64f((uint64_t) key) & mask;
+		for (uint32_t probes = 0; probes < 8192; probes++)
+		{
+			unsigned long long *kp = (unsigned long long *) (P.table + h * (uint64_t) P.stride);
+			long long cur = (long long) __ldcg(kp);
+			if (cur == key) return (uint64_t *) kp + 1;
+			if (cur == CG_HASH_EMPTY)
+			{
+				long long old = (long long) atomicCAS(kp, (unsigned long long) CG_HASH_EMPTY, (unsigned long long) key);
+				if (old == CG_HASH_EMPTY || old == key) return (uint64_t *) kp + 1;
+			}
+			h = (h + 1) & mask;
+		}
+		atomicOr(P.stats + 2, CG_ERRFLAG_TABLE_FULL);
+		return nullptr;
+	}
+}
+
+template <int NS>
+struct FastAcc
+{
+	uint64_t rows;
+	uint64_t lo[NS > 0 ? NS : 1];
+	int64_t hi[NS > 0 ? NS : 1];
+};
+
+template <int NQ>
+__device__ __forceinline__ bool fast_pass(const FPlan &P, const int64_t *v)
+{
+	bool pass = true;
+#pragma unroll
+	for (int q = 0; q < NQ; q++)
+	{
+		bool in = v[q] >= P.qlo[q] && v[q] <= P.qhi[q];
+		pass = pass && (in != (bool) P.qneg[q]);
+	}
+	return pass;
+}
+
+/*
+ * Paired table update (all sums single-word).  The accumulator words of one group are
+ * adjacent (one 32-byte sector); instead of every lane issuing one reduction per word --
+ * 32 sectors per instruction and word -- lanes work in pairs: in round 0 both lanes of a
+ * pair update the row of the even lane (even lane: word 0, odd lane: word 1, ...), in
+ * round 1 the row of the odd lane.  One reduction instruction then carries both words of
+ * 16 groups in 16 sectors, halving the L2 atomic transactions per row.
+ * Must be called by all 32 lanes.
+ */
+template <int NS>
+__device__ __forceinline__ void paired_update(const FPlan &P, bool pass, uint64_t *e, const int64_t *sums, uint64_t pol)
+{
+	const unsigned lane = threadIdx.x & 31u;
+	const bool odd = lane & 1u;
+	__syncwarp();
+	uint64_t pe = __shfl_xor_sync(0xffffffffu, (uint64_t) e, 1);
+	bool ppass = __shfl_xor_sync(0xffffffffu, (int) pass, 1) != 0;
+	int64_t ps[NS > 0 ? NS : 1];
+#pragma unroll
+	for (int s = 0; s < NS; s++) ps[s] = __shfl_xor_sync(0xffffffffu, sums[s], 1);
+#pragma unroll
+	for (int round = 0; round < 2; round++)
+	{
+		const bool mine = (odd == (round == 1));
+		uint64_t *te = mine ? e : (uint64_t *) pe;
+		const bool tpass = mine ? pass : ppass;
+		if (tpass)
+		{
+#pragma unroll
+			for (int j = 0; j < (NS + 2) / 2; j++)
+			{
+				const int w = 2 * j + (odd ? 1 : 0);     /* 0 = row count, 1.. = sums */
+				if (w == 0) red_add_u64(te, 1ull, pol);
+				else if (w <= NS)
+				{
+					int64_t x = 0;
+					int wordidx = 0;
+#pragma unroll
+					for (int s = 0; s < NS; s++)
+						if (s == w - 1) { x = mine ? sums[s] : ps[s]; wordidx = P.sword[s]; }
+					red_add_u64(te + wordidx, (uint64_t) x, pol);
+				}
+			}
+		}
+	}
+}
+
+template <int NQ, int MODE, int NS>
+__device__ __forceinline__ void fast_row(const FPlan &P, const int64_t *v, FastAcc<NS> &acc, uint32_t &removed, uint64_t pol)
+{
+	constexpr int KEYPOS = NQ;
+	constexpr int SUMPOS = NQ + (MODE != CG_MODE_GLOBAL ? 1 : 0);
+	if (!fast_pass<NQ>(P, v))
+	{
+		removed++;
+		return;
+	}
+	if (MODE == CG_MODE_GLOBAL)
+	{
+		acc.rows++;
+#pragma unroll
+		for (int s = 0; s < NS; s++)
+		{
+			int64_t x = v[SUMPOS + s];
+			acc.lo[s] += (uint64_t) (uint32_t) x;
+			acc.hi[s] += x >> 32;
+		}
+	}
+	else
+	{
+		uint64_t *e = fast_entry<MODE>(P, v[KEYPOS]);
+		if (e == nullptr) return;
+		red_add_u64(e, 1ull, pol);
+#pragma unroll
+		for (int s = 0; s < NS; s++)
+		{
+			int64_t x = v[SUMPOS + s];
+			if (P.slimbs[s] == 1)
+			{
+				if (x > P.sbound[s] || x < -P.sbound[s]) atomicOr(P.stats + 2, CG_ERRFLAG_SUM_BOUND);
+				red_add_u64(e + P.sword[s], (uint64_t) x, pol);
+			}
+			else
+			{
+				red_add_u64(e + P.sword[s], (uint64_t) (uint32_t) x, pol);
+				red_add_u64(e + P.sword[s] + 1, (uint64_t) (x >> 32), pol);
+			}
+		}
+	}
+}
+
+__device__ __forceinline__ uint64_t warp_sum(uint64_t x)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+	return x;
+}
+
+template <int NQ, int MODE, int NS, int U>
+__global__ void __launch_bounds__(CGF_THREADS)
+cg_scan_fast_kernel(const __grid_constant__ FPlan P)
+{
+	constexpr int NC = NQ + (MODE != CG_MODE_GLOBAL ? 1 : 0) + NS;
+	FastAcc<NS> acc;
+	acc.rows = 0;
+#pragma unroll
+	for (int s = 0; s < NS; s++) { acc.lo[s] = 0; acc.hi[s] = 0; }
+	uint32_t removed = 0;
+	unsigned long long scanned = 0;
+	const uint32_t tid = threadIdx.x;
+	const uint64_t pol_stream = (P.flags & CG_FAST_NO_HINTS) ? policy_evict_normal() : policy_evict_first();
+	const uint64_t pol_table = (P.flags & CG_FAST_NO_HINTS) ? policy_evict_normal() : policy_evict_last();
+	const bool paired = (MODE != CG_MODE_GLOBAL) && NS > 0 && (P.flags & CG_FAST_PAIRED);
+	constexpr int KEYPOS = NQ;
+	constexpr int SUMPOS = NQ + (MODE != CG_MODE_GLOBAL ? 1 : 0);
+
+	for (uint32_t ci = blockIdx.x; ci < P.nselected; ci += gridDim.x)
+	{
+		const DevChunkCol *cc = P.chunkcols + (uint64_t) P.selected[ci] * (uint64_t) P.nstaged;
+		const uint32_t rows = __ldg(&cc[0].row_count);
+		const uint8_t *vp[NC > 0 ? NC : 1];
+#pragma unroll
+		for (int c = 0; c < NC; c++) vp[c] = P.arena + __ldg(&cc[P.slot[c]].values_off);
+		scanned += (tid == 0) ? rows : 0;
+		if (NC == 0)
+		{
+			/* count(*) without any column: every row of the chunk group passes */
+			if (tid == 0)
+			{
+				if (MODE == CG_MODE_GLOBAL) acc.rows += rows;
+			}
+			continue;
+		}
+		for (uint32_t base = 0; base < rows; base += CGF_THREADS * 2 * U)
+		{
+			int64_t v0[U][NC > 0 ? NC : 1], v1[U][NC > 0 ? NC : 1];
+#pragma unroll
+			for (int u = 0; u < U; u++)
+			{
+				uint32_t r = base + (u * CGF_THREADS + tid) * 2;
+				if (r < rows)
+				{
+#pragma unroll
+					for (int c = 0; c < NC; c++)
+					{
+						uint64_t a, b;
+						ldg16(vp[c] + (uint64_t) r * 8, a, b, pol_stream);
+						v0[u][c] = (int64_t) a; v1[u][c] = (int64_t) b;
+					}
+				}
+			}
+#pragma unroll
+			for (int u = 0; u < U; u++)
+			{
+				uint32_t r = base + (u * CGF_THREADS + tid) * 2;
+				if (paired)
+				{
+					/* warp-converged: lanes past the end of the chunk group take part with pass = false */
+#pragma unroll
+					for (int half = 0; half < 2; half++)
+					{
+						const int64_t *v = half ? v1[u] : v0[u];
+						const bool valid = r + half < rows;
+						bool pass = valid && fast_pass<NQ>(P, v);
+						removed += (valid && !pass) ? 1u : 0u;
+						uint64_t *e = nullptr;
+						if (pass)
+						{
+							e = fast_entry<MODE>(P, v[KEYPOS]);
+							pass = e != nullptr;
+#pragma unroll
+							for (int s = 0; s < NS; s++)
+								if (v[SUMPOS + s] > P.sbound[s] || v[SUMPOS + s] < -P.sbound[s])
+									atomicOr(P.stats + 2, CG_ERRFLAG_SUM_BOUND);
+						}
+						paired_update<NS>(P, pass, e, v + SUMPOS, pol_table);
+					}
+				}
+				else if (r < rows)
+				{
+					fast_row<NQ, MODE, NS>(P, v0[u], acc, removed, pol_table);
+					if (r + 1 < rows) fast_row<NQ, MODE, NS>(P, v1[u], acc, removed, pol_table);
+				}
+			}
+		}
+	}
+
+	unsigned long long rem = warp_sum(removed);
+	unsigned long long scn = warp_sum(scanned);
+	if ((tid & 31) == 0)
+	{
+		if (scn) atomicAdd(P.stats + 0, scn);
+		if (rem) atomicAdd(P.stats + 1, rem);
+	}
+	if (MODE == CG_MODE_GLOBAL)
+	{
+		uint64_t rows_passed = warp_sum(acc.rows);
+		if ((tid & 31) == 0 && rows_passed) red_add_u64(P.table, rows_passed, pol_table);
+#pragma unroll
+		for (int s = 0; s < NS; s++)
+		{
+			uint64_t lo = warp_sum(acc.lo[s]);
+			uint64_t hi = warp_sum((uint64_t) acc.hi[s]);
+			if ((tid & 31) == 0 && (lo | hi))
+			{
+				if (P.slimbs[s] == 1) red_add_u64(P.table + P.sword[s], lo + (hi << 32), pol_table);
+				else
+				{
+					red_add_u64(P.table + P.sword[s], lo, pol_table);
+					red_add_u64(P.table + P.sword[s] + 1, hi, pol_table);
+				}
+			}
+		}
+	}
+}
+
+struct FastVariant
+{
+	void (*kernel)(FPlan);
+	int occupancy;
+};
+
+template <int NQ, int MODE, int NS>
+static int launch_fast_variant(CgContext *ctx, const FPlan &plan, cudaStream_t stream)
+{
+	constexpr int NC = NQ + (MODE != CG_MODE_GLOBAL ? 1 : 0) + NS;
+	constexpr int U = NC <= 3 ? 2 : 1;
+	static int occ = 0;
+	if (occ == 0)
+	{
+		CG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_scan_fast_kernel<NQ, MODE, NS, U>, CGF_THREADS, 0));
+		if (occ < 1) occ = 1;
+	}
+	uint32_t grid = (uint32_t) (ctx->sm_count * occ);
+	if (grid > plan.nselected) grid = plan.nselected;
+	if (grid == 0) return CG_OK;
+	cg_scan_fast_kernel<NQ, MODE, NS, U><<<grid, CGF_THREADS, 0, stream>>>(plan);
+	CG_CUDA(cudaGetLastError());
+	return CG_OK;
+}
+
+template <int NQ, int MODE>
+static int launch_fast_ns(CgContext *ctx, const FPlan &plan, cudaStream_t stream)
+{
+	switch (plan.nsums)
+	{
+		case 0: return launch_fast_variant<NQ, MODE, 0>(ctx, plan, stream);
+		case 1: return launch_fast_variant<NQ, MODE, 1>(ctx, plan, stream);
+		case 2: return launch_fast_variant<NQ, MODE, 2>(ctx, plan, stream);
+		default: return launch_fast_variant<NQ, MODE, 3>(ctx, plan, stream);
+	}
+}
+
+template <int NQ>
+static int launch_fast_mode(CgContext *ctx, const FPlan &plan, cudaStream_t stream)
+{
+	switch (plan.mode)
+	{
+		case CG_MODE_GLOBAL: return launch_fast_ns<NQ, CG_MODE_GLOBAL>(ctx, plan, stream);
+		case CG_MODE_DENSE: return launch_fast_ns<NQ, CG_MODE_DENSE>(ctx, plan, stream);
+		default: return launch_fast_ns<NQ, CG_MODE_HASH>(ctx, plan, stream);
+	}
+}
+
+int cg_launch_scan_fast(CgContext *ctx, const FPlan &plan, cudaStream_t stream)
+{
+	switch (plan.nquals)
+	{
+		case 0: return launch_fast_mode<0>(ctx, plan, stream);
+		case 1: return launch_fast_mode<1>(ctx, plan, stream);
+		default: return launch_fast_mode<2>(ctx, plan, stream);
+	}
+}

@@ -75,6 +75,8 @@ def allgather_rows(keys: torch.Tensor, key_nulls: torch.Tensor, words: torch.Ten
 def combine_partials(agg, dst: int = 0, group=None):
     """coord_combine over the ranks: after the call rank `dst`'s partial holds the combined
     aggregate.  `agg` is a columnar.GpuColumnarAgg."""
+    if not dist.is_initialized():
+        return
     world = dist.get_world_size(group)
     if world == 1:
         return

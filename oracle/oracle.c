@@ -813,6 +813,7 @@ typedef struct OrcScanResult
 	int64_t rows_passed;
 	/* host hash table */
 	OrcGroup *slots; int64_t *slot_index; int64_t cap;
+	int64_t group_cap;
 } OrcScanResult;
 
 static int orc_qual_cmp_true(int atttype, int64_t v, int op, int64_t k)
@@ -899,9 +900,13 @@ static int64_t orc_group_lookup(OrcScanResult *r, int64_t key, int key_null)
 	r->slots[h].used = 1; r->slots[h].key = key; r->slots[h].key_null = key_null;
 	int64_t g = r->ngroups++;
 	r->slot_index[h] = g;
-	r->keys = realloc(r->keys, sizeof(int64_t) * (size_t) r->ngroups);
-	r->key_nulls = realloc(r->key_nulls, (size_t) r->ngroups);
-	r->states = realloc(r->states, sizeof(OrcAggState) * (size_t) r->ngroups * (size_t) r->nagg);
+	if (r->ngroups > r->group_cap)
+	{
+		r->group_cap = r->group_cap ? r->group_cap * 2 : 1024;
+		r->keys = realloc(r->keys, sizeof(int64_t) * (size_t) r->group_cap);
+		r->key_nulls = realloc(r->key_nulls, (size_t) r->group_cap);
+		r->states = realloc(r->states, sizeof(OrcAggState) * (size_t) r->group_cap * (size_t) (r->nagg ? r->nagg : 1));
+	}
 	r->keys[g] = key; r->key_nulls[g] = (uint8_t) key_null;
 	for (int a = 0; a < r->nagg; a++)
 	{
