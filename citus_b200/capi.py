@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libcitus_gpu.so")
 
-CG_OK, CG_EINVAL, CG_ECUDA, CG_ENOMEM, CG_ECORRUPT, CG_ETABLEFULL, CG_EUNSUPPORTED = range(7)
+CG_OK, CG_EINVAL, CG_ECUDA, CG_ENOMEM, CG_ECORRUPT, CG_ETABLEFULL, CG_EUNSUPPORTED, CG_ERETRY_UNPACKED = range(8)
 CG_TYPE_INT, CG_TYPE_FLOAT = 0, 1
 CG_OP = {"<": 0, "<=": 1, "=": 2, ">=": 3, ">": 4, "<>": 5}
 CG_AGG_COUNT_STAR, CG_AGG_COUNT, CG_AGG_SUM, CG_AGG_MIN, CG_AGG_MAX = range(5)
@@ -103,6 +103,7 @@ SYMBOLS = [
                                     C.c_int64, C.c_int64, C.POINTER(_P)]),
     ("cg_partial_free", None, [_P]),
     ("cg_partial_reset", C.c_int, [_P]),
+    ("cg_partial_set_packing", C.c_int, [_P, C.c_int32]),
     ("cg_scan_shard", C.c_int, [_P, C.POINTER(CgScanDesc), _P, C.POINTER(CgScanStats)]),
     ("cg_scan_relation", C.c_int, [C.POINTER(CgRelation), C.POINTER(CgScanDesc), _P, C.POINTER(CgScanStats)]),
     ("cg_partial_ngroups", C.c_int, [_P, C.POINTER(C.c_int64)]),

@@ -258,6 +258,9 @@ class GpuColumnarAgg:
     def reset(self):
         check(lib().cg_partial_reset(self.h))
 
+    def set_packing(self, enable: bool):
+        check(lib().cg_partial_set_packing(self.h, 1 if enable else 0))
+
     def scan_shard(self, shard: Shard, want_stats=True):
         st = CgScanStats()
         check(lib().cg_scan_shard(shard.h, C.byref(self.desc), self.h, C.byref(st) if want_stats else None))

@@ -4,6 +4,7 @@
  * result fetch.  Mirrors the reader of backend/columnar/columnar_reader.c, batch-wise.
  */
 #include <algorithm>
+#include <chrono>
 #include <omp.h>
 #include <stdlib.h>
 #include <string.h>
@@ -480,6 +481,12 @@ static int stream_to_device(CgContext *ctx, const CgRelation *rel, const StagePl
 	uint64_t ncg = sp.cg_rows.size();
 	uint64_t cg = 0;
 	int slot = 0;
+	static int trace = -1;
+	if (trace < 0) { const char *e = getenv("CG_TRACE"); trace = (e && atoi(e)) ? 1 : 0; }
+	double t_wait = 0, t_fill = 0, t_enq = 0;
+	uint64_t nblk = 0;
+	auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	double t_begin = now();
 	while (cg < ncg)
 	{
 		uint64_t cg1 = cg;
@@ -487,17 +494,26 @@ static int stream_to_device(CgContext *ctx, const CgRelation *rel, const StagePl
 		if (cg1 == cg)
 			return cg_set_error(CG_EUNSUPPORTED, "one chunk group (%llu bytes) exceeds the pinned block size",
 								(unsigned long long) (sp.cg_begin[cg + 1] - sp.cg_begin[cg]));
+		double t0 = now();
 		CG_CUDA(cudaEventSynchronize(ctx->pinned_free[slot]));
+		double t1 = now();
 		rc = fill_block(rel, sp, ns, cg, cg1, ctx->pinned[slot], ctx->stage_threads);
 		if (rc) return rc;
+		double t2 = now();
 		uint64_t bytes = sp.cg_begin[cg1] - sp.cg_begin[cg];
 		CG_CUDA(cudaMemcpyAsync(d_arena + sp.cg_begin[cg], ctx->pinned[slot], bytes, cudaMemcpyHostToDevice, ctx->copy));
 		CG_CUDA(cudaEventRecord(ctx->pinned_free[slot], ctx->copy));
 		rc = after_block(cg, cg1, ctx->pinned_free[slot]);
 		if (rc) return rc;
+		double t3 = now();
+		t_wait += t1 - t0; t_fill += t2 - t1; t_enq += t3 - t2; nblk++;
 		cg = cg1;
 		slot = (slot + 1) % CgContext::kPinnedBlocks;
 	}
+	if (trace)
+		fprintf(stderr, "[cg] staged %.1f MB in %llu blocks: total %.1f ms (wait-for-slot %.1f, de-frame %.1f = %.1f GB/s, enqueue %.1f)\n",
+				sp.arena_bytes / 1e6, (unsigned long long) nblk, (now() - t_begin) * 1e3, t_wait * 1e3, t_fill * 1e3,
+				sp.arena_bytes / 1e9 / (t_fill > 0 ? t_fill : 1), t_enq * 1e3);
 	return CG_OK;
 }
 
@@ -608,6 +624,22 @@ static int check_error_flags(CgPartial *p, unsigned long long flags)
 	return CG_OK;
 }
 
+static int drain_every(void)
+{
+	static int v = -1;
+	if (v < 0) { const char *e = getenv("CG_PACK_DRAIN_EVERY"); v = e ? atoi(e) : 4; if (v < 1) v = 1; }
+	return v;
+}
+
+/* bookkeeping after a scan launch that may have used the packed words */
+static int after_packed_launch(CgContext *ctx, CgPartial *p, bool used_packed)
+{
+	if (!used_packed) return CG_OK;
+	p->packed_dirty = true;
+	if (++p->launches_since_drain >= drain_every()) return cg_launch_drain(p, ctx->compute);
+	return CG_OK;
+}
+
 static int read_stats(CgContext *ctx, CgPartial *p, unsigned long long before[3], CgScanStats *stats)
 {
 	unsigned long long after[3];
@@ -707,6 +739,8 @@ extern "C" int cg_scan_shard(const CgShard *sh, const CgScanDesc *desc, CgPartia
 		{
 			fast.nselected = nfast;
 			rc = cg_launch_scan_fast(ctx, fast, ctx->compute);
+			if (rc) return rc;
+			rc = after_packed_launch(ctx, into, fast.packed != nullptr);
 			if (rc) return rc;
 		}
 		if (nfast < plan.nselected)
@@ -827,6 +861,7 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 				blk.selected = d_ids + cg0;
 				blk.nselected = (uint32_t) (cg1 - cg0);
 				r = cg_launch_scan_fast(ctx, blk, ctx->compute);
+				if (r == CG_OK && blk.packed) into->packed_dirty = true;
 			}
 			else
 			{
@@ -880,12 +915,22 @@ static int ensure_out(CgPartial *p, uint64_t cap)
 	return CG_OK;
 }
 
+/* makes the exact accumulators current (drains packed words), then surfaces kernel-side errors */
 static int pending_errors(CgContext *ctx, CgPartial *p)
 {
-	unsigned long long st[3];
+	int rc = cg_launch_drain(p, ctx->compute);
+	if (rc) return rc;
+	unsigned long long st[5];
 	CG_CUDA(cudaMemcpyAsync(st, p->d_stats, sizeof st, cudaMemcpyDeviceToHost, ctx->compute));
 	CG_CUDA(cudaStreamSynchronize(ctx->compute));
-	return check_error_flags(p, st[2]);
+	rc = check_error_flags(p, st[2]);
+	if (rc) return rc;
+	if (st[CG_STAT_PACKED_ADDED] != st[CG_STAT_PACKED_DRAINED])
+		return cg_set_error(CG_ERETRY_UNPACKED,
+							"packed accumulators overflowed (%llu rows added, %llu drained): a group received >= 2^%d rows "
+							"between drains; disable packing, reset and rescan",
+							st[CG_STAT_PACKED_ADDED], st[CG_STAT_PACKED_DRAINED], p->pack_shift);
+	return CG_OK;
 }
 
 extern "C" int cg_partial_ngroups(CgPartial *p, int64_t *ngroups)
@@ -1008,6 +1053,10 @@ extern "C" int cg_partial_dense_words(CgPartial *p, uint64_t **d_words, int64_t 
 {
 	if (!p) return cg_set_error(CG_EINVAL, "NULL partial");
 	if (p->mode == CG_MODE_HASH) return cg_set_error(CG_EINVAL, "not a direct-indexed table");
+	CgContext *ctx = cg_ctx();
+	if (!ctx) return CG_EINVAL;
+	int rc = pending_errors(ctx, p);
+	if (rc) return rc;
 	*d_words = p->d_table;
 	if (total_words) *total_words = (int64_t) (p->entries * (uint64_t) p->stride);
 	if (stride) *stride = p->stride;

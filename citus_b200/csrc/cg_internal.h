@@ -163,7 +163,12 @@ struct KPlan
 	int64_t key_min;              /* dense */
 	uint8_t wordop[CG_KMAX_WORDS];
 
-	unsigned long long *stats;    /* [0] rows scanned [1] rows removed [2] error flags */
+	unsigned long long *stats;    /* [0] rows scanned [1] rows removed [2] error flags
+								   * [3] rows added to packed words [4] rows drained from packed words */
+	/* optimistic packed accumulators (direct-indexed tables): packed[slot] += (term << shift) + 1 */
+	uint64_t *packed;
+	int32_t pack_shift;
+	int32_t pack_word;            /* accumulator word the packed sum belongs to */
 };
 
 /* plan of the specialised kernel (cg_scan_fast.cu): column roles in fixed order
@@ -188,6 +193,9 @@ struct FPlan
 	int32_t stride;
 	int64_t key_min;
 	unsigned long long *stats;
+	uint64_t *packed;             /* non-NULL: count(*) and sum number pack_sum share one word */
+	int32_t pack_shift;
+	int32_t pack_sum;
 };
 
 #define CG_FAST_PAIRED 1u       /* pair lanes so that one reduction instruction covers both words of a group */
@@ -198,6 +206,8 @@ struct FPlan
 #define CG_ERRFLAG_NULL_MULTIKEY 2ull
 #define CG_ERRFLAG_KEY_RANGE 4ull
 #define CG_ERRFLAG_SUM_BOUND 8ull
+#define CG_STAT_PACKED_ADDED 3
+#define CG_STAT_PACKED_DRAINED 4
 
 struct CgPartial
 {
@@ -214,6 +224,13 @@ struct CgPartial
 	KAgg aggs[CG_MAX_AGGS];
 	uint64_t *d_table = nullptr;
 	unsigned long long *d_stats = nullptr;   /* 8 words */
+	/* optimistic packing */
+	uint64_t *d_packed = nullptr;
+	int pack_shift = 0;
+	int pack_word = 0;
+	bool packing_enabled = false;
+	bool packed_dirty = false;
+	int launches_since_drain = 0;
 	/* scratch for export */
 	int64_t *d_out_keys = nullptr;
 	uint64_t *d_out_words = nullptr;
@@ -226,6 +243,7 @@ struct CgPartial
 int cg_launch_scan(CgContext *ctx, const KPlan &plan, bool any_nulls, bool all8, cudaStream_t stream);
 /* cg_scan_fast.cu */
 int cg_launch_scan_fast(CgContext *ctx, const FPlan &plan, cudaStream_t stream);
+int cg_launch_drain(CgPartial *p, cudaStream_t stream);
 int cg_launch_rank(CgContext *ctx, const uint8_t *arena, const DevChunkCol *chunkcols, uint64_t first,
 				   uint64_t count, cudaStream_t stream);
 int cg_launch_table_init(CgPartial *p, cudaStream_t stream);

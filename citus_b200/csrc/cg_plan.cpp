@@ -197,6 +197,32 @@ extern "C" int cg_partial_create(const CgScanDesc *desc, const CgColumnDesc *col
 		cg_partial_free(p);
 		return cg_set_error(CG_ENOMEM, "cudaMalloc failed");
 	}
+	/* optimistic packing: direct-indexed table, count + the first single-word integer sum.
+	 * |term| <= bound < 2^R and at most 2^C - 1 rows per group between drains keep
+	 * (sum << C) + count inside 64 bits when R + 2C <= 63. */
+	if (p->mode == CG_MODE_DENSE)
+	{
+		static int env_pack = -1;
+		if (env_pack < 0) { const char *e = getenv("CG_PACKING"); env_pack = e ? atoi(e) : 1; }
+		for (int a = 0; a < desc->naggs && env_pack && !p->d_packed; a++)
+		{
+			const KAgg &k = p->aggs[a];
+			if (k.kind != CG_AGG_SUM || k.is_float || k.nlimbs != 1 || k.bound <= 0) continue;
+			int R = 0;
+			while (R < 62 && ((int64_t) 1 << R) <= k.bound) R++;
+			int Cbits = (63 - R) / 2;
+			if (Cbits < 12) continue;
+			if (Cbits > 24) Cbits = 24;
+			if (cudaMalloc(&p->d_packed, (size_t) p->entries * sizeof(uint64_t)) != cudaSuccess)
+			{
+				cg_partial_free(p);
+				return cg_set_error(CG_ENOMEM, "cudaMalloc for the packed accumulators failed");
+			}
+			p->pack_shift = Cbits;
+			p->pack_word = k.word0;
+			p->packing_enabled = true;
+		}
+	}
 	rc = cg_launch_table_init(p, ctx->compute);
 	if (rc) { cg_partial_free(p); return rc; }
 	*out = p;
@@ -206,7 +232,7 @@ extern "C" int cg_partial_create(const CgScanDesc *desc, const CgColumnDesc *col
 extern "C" void cg_partial_free(CgPartial *p)
 {
 	if (!p) return;
-	cudaFree(p->d_table); cudaFree(p->d_stats); cudaFree(p->d_out_keys); cudaFree(p->d_out_words);
+	cudaFree(p->d_table); cudaFree(p->d_stats); cudaFree(p->d_out_keys); cudaFree(p->d_out_words); cudaFree(p->d_packed);
 	cudaFree(p->d_out_nulls); cudaFree(p->d_out_count);
 	delete p;
 }
@@ -216,6 +242,14 @@ extern "C" int cg_partial_reset(CgPartial *p)
 	CgContext *ctx = cg_ctx();
 	if (!ctx || !p) return CG_EINVAL;
 	return cg_launch_table_init(p, ctx->compute);
+}
+
+extern "C" int cg_partial_set_packing(CgPartial *p, int32_t enable)
+{
+	if (!p) return cg_set_error(CG_EINVAL, "NULL partial");
+	if (p->packed_dirty) return cg_set_error(CG_EINVAL, "reset the partial before changing its packing mode");
+	p->packing_enabled = enable != 0 && p->d_packed != nullptr;
+	return CG_OK;
 }
 
 extern "C" int cg_partial_layout(const CgPartial *p, int32_t *nwords, int32_t *word_ops, int32_t *is_dense, int64_t *capacity)
@@ -309,6 +343,9 @@ int cg_build_plan(const CgScanDesc *desc, const CgColumnDesc *columns, int natts
 	plan->key_min = partial->key_min;
 	memcpy(plan->wordop, partial->wordop, sizeof plan->wordop);
 	plan->stats = partial->d_stats;
+	plan->packed = partial->packing_enabled ? partial->d_packed : nullptr;
+	plan->pack_shift = partial->pack_shift;
+	plan->pack_word = partial->pack_word;
 	return CG_OK;
 }
 
@@ -384,6 +421,16 @@ bool cg_build_fast_plan(const CgScanDesc *desc, const KPlan &plan, bool all8, FP
 	}
 	fast->nsums = ns;
 	fast->mode = plan.mode;
+	fast->packed = nullptr;
+	fast->pack_sum = -1;
+	if (plan.packed && plan.mode == CG_MODE_DENSE)
+		for (int i = 0; i < ns; i++)
+			if (fast->sword[i] == plan.pack_word && fast->slimbs[i] == 1)
+			{
+				fast->packed = plan.packed;
+				fast->pack_shift = plan.pack_shift;
+				fast->pack_sum = i;
+			}
 	{
 		/* tuning switches (measurements only): CG_FAST_FLAGS overrides the default */
 		static int env_flags = -1;

@@ -672,6 +672,9 @@ int cg_launch_table_init(CgPartial *p, cudaStream_t stream)
 	cg_table_init_kernel<<<blocks, 256, 0, stream>>>(v);
 	CG_CUDA(cudaGetLastError());
 	CG_CUDA(cudaMemsetAsync(p->d_stats, 0, 8 * sizeof(unsigned long long), stream));
+	if (p->d_packed) CG_CUDA(cudaMemsetAsync(p->d_packed, 0, (size_t) p->entries * sizeof(uint64_t), stream));
+	p->packed_dirty = false;
+	p->launches_since_drain = 0;
 	return CG_OK;
 }
 

@@ -189,12 +189,21 @@ __device__ __forceinline__ void fast_row(const FPlan &P, const int64_t *v, FastA
 	{
 		uint64_t *e = fast_entry<MODE>(P, v[KEYPOS]);
 		if (e == nullptr) return;
-		red_add_u64(e, 1ull, pol);
+		const bool packed = MODE == CG_MODE_DENSE && NS > 0 && P.packed != nullptr;
+		if (!packed) red_add_u64(e, 1ull, pol);
 #pragma unroll
 		for (int s = 0; s < NS; s++)
 		{
 			int64_t x = v[SUMPOS + s];
-			if (P.slimbs[s] == 1)
+			if (packed && s == P.pack_sum)
+			{
+				/* one reduction for count(*) and this sum: word += (x << C) + 1 (mod 2^64) */
+				if (x > P.sbound[s] || x < -P.sbound[s]) atomicOr(P.stats + 2, CG_ERRFLAG_SUM_BOUND);
+				uint64_t slot = (uint64_t) (e - P.table) / (uint64_t) P.stride;
+				red_add_u64(P.packed + slot, ((uint64_t) x << P.pack_shift) + 1ull, pol);
+				acc.rows++;      /* rows added to packed words (verified against the drains) */
+			}
+			else if (P.slimbs[s] == 1)
 			{
 				if (x > P.sbound[s] || x < -P.sbound[s]) atomicOr(P.stats + 2, CG_ERRFLAG_SUM_BOUND);
 				red_add_u64(e + P.sword[s], (uint64_t) x, pol);
@@ -229,7 +238,7 @@ cg_scan_fast_kernel(const __grid_constant__ FPlan P)
 	const uint32_t tid = threadIdx.x;
 	const uint64_t pol_stream = (P.flags & CG_FAST_NO_HINTS) ? policy_evict_normal() : policy_evict_first();
 	const uint64_t pol_table = (P.flags & CG_FAST_NO_HINTS) ? policy_evict_normal() : policy_evict_last();
-	const bool paired = (MODE != CG_MODE_GLOBAL) && NS > 0 && (P.flags & CG_FAST_PAIRED);
+	const bool paired = (MODE != CG_MODE_GLOBAL) && NS > 0 && (P.flags & CG_FAST_PAIRED) && P.packed == nullptr;
 	constexpr int KEYPOS = NQ;
 	constexpr int SUMPOS = NQ + (MODE != CG_MODE_GLOBAL ? 1 : 0);
 
@@ -311,6 +320,11 @@ cg_scan_fast_kernel(const __grid_constant__ FPlan P)
 		if (scn) atomicAdd(P.stats + 0, scn);
 		if (rem) atomicAdd(P.stats + 1, rem);
 	}
+	if (MODE == CG_MODE_DENSE)
+	{
+		uint64_t added = warp_sum(acc.rows);
+		if ((tid & 31) == 0 && added) atomicAdd(P.stats + CG_STAT_PACKED_ADDED, (unsigned long long) added);
+	}
 	if (MODE == CG_MODE_GLOBAL)
 	{
 		uint64_t rows_passed = warp_sum(acc.rows);
@@ -331,6 +345,45 @@ cg_scan_fast_kernel(const __grid_constant__ FPlan P)
 			}
 		}
 	}
+}
+
+/*
+ * Drain of the packed words into the exact accumulators: word = (sum << C) + n (mod 2^64) with
+ * n < 2^C, so n = word mod 2^C and sum = (word - n) >> C (arithmetic).  The drained counts are
+ * added up; cg_host.cpp compares them with the rows the scan kernels added.
+ */
+__global__ void __launch_bounds__(256)
+cg_drain_kernel(uint64_t *packed, uint64_t *table, uint64_t entries, int stride, int pack_word, int shift,
+				unsigned long long *stats)
+{
+	const uint64_t mask = (1ull << shift) - 1ull;
+	unsigned long long local = 0;
+	for (uint64_t slot = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; slot < entries; slot += (uint64_t) gridDim.x * blockDim.x)
+	{
+		uint64_t w = packed[slot];
+		if (w == 0) continue;
+		uint64_t n = w & mask;
+		int64_t sum = (int64_t) (w - n) >> shift;
+		uint64_t *ent = table + slot * (uint64_t) stride;
+		ent[0] += n;
+		ent[pack_word] += (uint64_t) sum;
+		packed[slot] = 0;
+		local += n;
+	}
+	local = warp_sum(local);
+	if ((threadIdx.x & 31) == 0 && local) atomicAdd(stats + CG_STAT_PACKED_DRAINED, local);
+}
+
+int cg_launch_drain(CgPartial *p, cudaStream_t stream)
+{
+	if (!p->d_packed || !p->packed_dirty) return CG_OK;
+	unsigned blocks = (unsigned) ((p->entries + 255) / 256);
+	if (blocks > 148 * 8) blocks = 148 * 8;
+	cg_drain_kernel<<<blocks, 256, 0, stream>>>(p->d_packed, p->d_table, p->entries, p->stride, p->pack_word, p->pack_shift, p->d_stats);
+	CG_CUDA(cudaGetLastError());
+	p->packed_dirty = false;
+	p->launches_since_drain = 0;
+	return CG_OK;
 }
 
 struct FastVariant

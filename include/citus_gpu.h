@@ -28,6 +28,9 @@ extern "C" {
 #define CG_ETABLEFULL 5    /* group table too small: retry with a larger expected_groups */
 #define CG_EUNSUPPORTED 6  /* valid SQL, but outside what the GPU path handles: caller falls
                             * back to the reference's row-at-a-time executor */
+#define CG_ERETRY_UNPACKED 7 /* an optimistic packed accumulator overflowed (see cg_partial_set_packing):
+                            * nothing wrong was returned; call cg_partial_set_packing(p, 0),
+                            * cg_partial_reset(p) and scan again */
 
 const char *cg_last_error(void);
 
@@ -211,6 +214,14 @@ int cg_partial_create(const CgScanDesc *desc, const CgColumnDesc *columns, int32
 					  int64_t key_min, int64_t key_max, int64_t max_rows, CgPartial **out);
 void cg_partial_free(CgPartial *p);
 int cg_partial_reset(CgPartial *p);
+/* Optimistic packing (on by default when the plan allows it): for a direct-indexed GROUP BY
+ * with count(*) and a bounded integer sum, a row updates ONE 64-bit word
+ * (sum << C | count) with one L2 reduction instead of two; packed words are drained into
+ * the exact wide accumulators between launches.  A group that receives 2^C or more rows
+ * between two drains would overflow its count field: this is detected exactly (the drained
+ * counts must add up to the rows added) and reported as CG_ERETRY_UNPACKED by the calls that
+ * read the partial -- never as a wrong result. */
+int cg_partial_set_packing(CgPartial *p, int32_t enable);
 
 /* Fused decode + filter + partial aggregate of one staged shard into `into`.
  * Chunk-group skipping (SelectedChunkMask, columnar_reader.c:1132-1187) runs on the host

@@ -424,3 +424,44 @@ def test_partition_parity_and_scatter(cg, oracle):
     from citus_b200 import capi
     with pytest.raises(capi.CitusGpuError):
         _partition(cg, np.arange(100), None, 8, "hash", [0], [10])
+
+
+# --------------------------------------------------------------------------- optimistic packing
+def test_packed_accumulators_overflow_is_detected_and_retry_is_exact(cg, oracle):
+    """count(*) + bounded sum share one 64-bit word per group; a group that receives >= 2^C
+    rows between drains must be reported (CG_ERETRY_UNPACKED), never answered wrongly."""
+    from citus_b200 import capi
+    rng = np.random.default_rng(21)
+    n = 400_000
+    key = rng.integers(0, 1000, n)
+    key[:150_000] = 7                                           # one hot group: 150 000 rows > 2^16
+    v = rng.integers(-10**9, 10**9, n)
+    rel = cg.Relation.write([8, 8], [key, v])
+    aggs = [cg.sum_(1), cg.count_star()]
+    d = cg.make_desc(group_cols=[0], aggs=aggs)
+    kmin, kmax, bounds, rows = cg.relation_bounds(rel, d)
+    aggs[0].term_abs_bound = bounds[0]
+    d = cg.make_desc(group_cols=[0], aggs=aggs)
+    agg = cg.GpuColumnarAgg(d, rel.column_descs(), kmin, kmax, rows)
+    shard = cg.Shard(rel)
+    agg.scan_shard(shard, want_stats=False)
+    with pytest.raises(capi.CitusGpuError) as e:
+        agg.groups()
+    assert e.value.code == capi.CG_ERETRY_UNPACKED
+    agg.reset()
+    agg.set_packing(False)
+    agg.scan_shard(shard, want_stats=False)
+    want = oracle_table(oracle, rel).scan([], [0], to_oracle_aggs(oracle, aggs)).groups()
+    assert_same_groups(agg.groups(), want, aggs)
+    # moderate skew below the threshold stays on the packed path and is exact
+    key2 = rng.integers(0, 1000, n)
+    key2[:60_000] = 7
+    rel2 = cg.Relation.write([8, 8], [key2, v])
+    agg2 = cg.GpuColumnarAgg(d, rel2.column_descs(), kmin, kmax, rows)
+    for _ in range(3):                                          # drained between launches: 3 x 60 400 rows is fine
+        agg2.scan_shard(cg.Shard(rel2), want_stats=False)
+        agg2.ngroups()
+    want = oracle.Result(to_oracle_aggs(oracle, aggs))
+    for _ in range(3):
+        oracle_table(oracle, rel2).scan([], [0], to_oracle_aggs(oracle, aggs), into=want)
+    assert_same_groups(agg2.groups(), want.groups(), aggs)
