@@ -107,7 +107,18 @@ class Relation:
         v.natts = natts
         return self
 
+    def register(self):
+        """pin the page image (cudaHostRegister): cg_scan_relation then uses DMA staging"""
+        check(lib().cg_relation_register(C.byref(self.view)))
+        self._registered = True
+
+    def unregister(self):
+        if getattr(self, "_registered", False):
+            lib().cg_relation_unregister(C.byref(self.view))
+            self._registered = False
+
     def __del__(self):
+        self.unregister()
         if getattr(self, "_gen", None):
             lib().cg_gen_relation_free(self._gen)
             self._gen = None

@@ -55,6 +55,15 @@ extern "C" int cg_init(int device)
 	g_ctx.sm_count = prop.multiProcessorCount;
 	CG_CUDA(cudaStreamCreateWithFlags(&g_ctx.compute, cudaStreamNonBlocking));
 	g_ctx.own_compute = g_ctx.compute;
+	{
+		/* keep freed blocks of the stream-ordered allocator: the per-scan arenas are reused */
+		cudaMemPool_t pool;
+		if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+		{
+			uint64_t keep = UINT64_MAX;
+			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+		}
+	}
 	CG_CUDA(cudaStreamCreateWithFlags(&g_ctx.copy, cudaStreamNonBlocking));
 	CG_CUDA(cudaEventCreate(&g_ctx.ev_a));
 	CG_CUDA(cudaEventCreate(&g_ctx.ev_b));
@@ -772,6 +781,108 @@ extern "C" int cg_scan_shard(const CgShard *sh, const CgScanDesc *desc, CgPartia
 	return CG_OK;
 }
 
+/* ------------------------------------------------------------------------------ *
+ *  DMA staging: when the relation's pages sit in pinned (registered) host memory the copy
+ *  engine de-frames them itself -- cudaMemcpy2DAsync with a source pitch of 8192 and a width
+ *  of 8168 bytes drops the 24-byte page headers -- so no host core touches the data.  One
+ *  2-D copy per (stripe, projected column) lands the column's byte range in a raw device
+ *  buffer; cg_realign_kernel then moves every chunk buffer to its 16-byte aligned arena slot
+ *  (the GPU half of ColumnarStorageRead's page de-framing, columnar_storage.c:463-492).
+ * ------------------------------------------------------------------------------ */
+extern "C" int cg_relation_register(const CgRelation *rel)
+{
+	if (!cg_ctx()) return CG_EINVAL;
+	if (!rel || !rel->pages || rel->nblocks == 0) return cg_set_error(CG_EINVAL, "empty relation");
+	CG_CUDA(cudaHostRegister((void *) rel->pages, (size_t) rel->nblocks * CG_BLCKSZ, cudaHostRegisterDefault));
+	return CG_OK;
+}
+
+extern "C" int cg_relation_unregister(const CgRelation *rel)
+{
+	if (!cg_ctx()) return CG_EINVAL;
+	if (!rel || !rel->pages) return cg_set_error(CG_EINVAL, "empty relation");
+	CG_CUDA(cudaHostUnregister((void *) rel->pages));
+	return CG_OK;
+}
+
+static bool pages_are_pinned(const CgRelation *rel)
+{
+	static int disabled = -1;
+	if (disabled < 0) { const char *e = getenv("CG_NO_DMA_STAGING"); disabled = (e && atoi(e)) ? 1 : 0; }
+	if (disabled || !rel->pages) return false;
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, rel->pages) != cudaSuccess)
+	{
+		cudaGetLastError();
+		return false;
+	}
+	return a.type == cudaMemoryTypeHost;
+}
+
+struct DmaCopy { uint64_t raw_off; uint64_t first_block; uint64_t nblocks; };
+
+/* builds the 2-D copies and the realign items for the chunk groups of `sp` (same iteration
+ * order as plan_staging) */
+static int plan_dma(const CgRelation *rel, const std::vector<int32_t> &staged,
+					const std::vector<std::vector<uint8_t>> &select, const StagePlan &sp,
+					std::vector<DmaCopy> *copies, std::vector<RealignItem> *items, uint64_t *raw_bytes)
+{
+	size_t ns = staged.size();
+	uint64_t raw_off = 0, g = 0;
+	for (int si = 0; si < rel->nstripes; si++)
+	{
+		const CgStripe &s = rel->stripes[si];
+		uint32_t first = UINT32_MAX, last = 0;
+		for (uint32_t k = 0; k < s.chunk_count; k++)
+			if (select[si][k]) { if (first == UINT32_MAX) first = k; last = k; }
+		if (first == UINT32_MAX) continue;
+		std::vector<uint64_t> base(ns, 0), p0(ns, 0);
+		for (size_t j = 0; j < ns; j++)
+		{
+			int c = staged[j];
+			if ((uint32_t) c >= s.column_count) continue;
+			const CgSkipNode &nf = rel->nodes[s.skipnode_base + (uint32_t) c * s.chunk_count + first];
+			const CgSkipNode &nl = rel->nodes[s.skipnode_base + (uint32_t) c * s.chunk_count + last];
+			uint64_t lb = s.file_offset + nf.exists_offset;
+			uint64_t le = s.file_offset + nl.value_offset + nl.value_length;
+			if (le <= lb) le = lb + 1;
+			uint64_t b0 = lb / CG_BYTES_PER_PAGE, b1 = (le - 1) / CG_BYTES_PER_PAGE;
+			if (b1 >= rel->nblocks) return cg_set_error(CG_ECORRUPT, "attempt to read columnar data past end of relation");
+			/* pd_lower of the first and last page of the span (ReadFromBlock checks every page) */
+			uint16_t lower;
+			memcpy(&lower, rel->pages + b1 * CG_BLCKSZ + 12, 2);
+			if (lower < CG_PAGE_HEADER + ((le - 1) % CG_BYTES_PER_PAGE) + 1)
+				return cg_set_error(CG_ECORRUPT, "attempt to read columnar data past pd_lower of block %llu", (unsigned long long) b1);
+			memcpy(&lower, rel->pages + b0 * CG_BLCKSZ + 12, 2);
+			if (b0 != b1 && lower != CG_BLCKSZ)
+				return cg_set_error(CG_ECORRUPT, "attempt to read columnar data past pd_lower of block %llu", (unsigned long long) b0);
+			base[j] = raw_off;
+			p0[j] = b0;
+			copies->push_back(DmaCopy{raw_off, b0, b1 - b0 + 1});
+			raw_off += (b1 - b0 + 1) * CG_BYTES_PER_PAGE;
+			raw_off = (raw_off + 15) & ~15ull;
+		}
+		for (uint32_t k = 0; k < s.chunk_count; k++)
+		{
+			if (!select[si][k]) continue;
+			for (size_t j = 0; j < ns; j++)
+			{
+				const DevChunkCol &d = sp.cols[g * ns + j];
+				const StageItem &it = sp.items[g * ns + j];
+				uint64_t exspan = d.values_off - d.exists_off;
+				uint64_t vaspan = pad16(it.value_len) + 16;
+				uint64_t esrc = it.exists_len ? base[j] + (it.exists_logical - p0[j] * CG_BYTES_PER_PAGE) : 0;
+				uint64_t vsrc = it.value_len ? base[j] + (it.value_logical - p0[j] * CG_BYTES_PER_PAGE) : 0;
+				items->push_back(RealignItem{esrc, d.exists_off, it.exists_len, (uint32_t) exspan});
+				items->push_back(RealignItem{vsrc, d.values_off, it.value_len, (uint32_t) vaspan});
+			}
+			g++;
+		}
+	}
+	*raw_bytes = raw_off + 64;
+	return CG_OK;
+}
+
 /*
  * End to end on host buffers: skip -> stage only the plan's columns of the surviving
  * chunk groups through the pinned ring -> one fused kernel launch per block, the
@@ -830,23 +941,56 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 	uint8_t *d_arena = nullptr;
 	DevChunkCol *d_cols = nullptr;
 	uint32_t *d_ids = nullptr;
+	uint64_t dma_bytes = 0;
+	bool used_dma = false;
 	if (ncg > 0)
 	{
+		/* small per-call metadata goes through a pinned ring so that its upload is truly
+		 * asynchronous (a pageable source would make cudaMemcpyAsync wait for the copy stream) */
+		const bool dma = pages_are_pinned(rel);
+		std::vector<DmaCopy> copies;
+		std::vector<RealignItem> items;
+		uint64_t raw_bytes = 0;
+		if (dma)
+		{
+			rc = plan_dma(rel, staged, select, sp, &copies, &items, &raw_bytes);
+			if (rc) return rc;
+		}
+		const size_t cols_bytes = sp.cols.size() * sizeof(DevChunkCol);
+		const size_t ids_bytes = ncg * sizeof(uint32_t);
+		const size_t items_bytes = items.size() * sizeof(RealignItem);
+		const size_t meta_bytes = ((cols_bytes + 15) & ~15ull) + ((ids_bytes + 15) & ~15ull) + items_bytes + 64;
+		const int mslot = ctx->dma_slot;
+		ctx->dma_slot = (mslot + 1) % CgContext::kDmaDepth;
+		if (!ctx->dma_done[mslot]) CG_CUDA(cudaEventCreateWithFlags(&ctx->dma_done[mslot], cudaEventDisableTiming));
+		if (!ctx->dma_copied) CG_CUDA(cudaEventCreateWithFlags(&ctx->dma_copied, cudaEventDisableTiming));
+		CG_CUDA(cudaEventSynchronize(ctx->dma_done[mslot]));      /* bounds the shards in flight; frees the slot */
+		if (ctx->meta_cap[mslot] < meta_bytes)
+		{
+			if (ctx->meta_pinned[mslot]) CG_CUDA(cudaFreeHost(ctx->meta_pinned[mslot]));
+			ctx->meta_pinned[mslot] = nullptr;
+			size_t cap = std::max<size_t>(meta_bytes * 2, 4u << 20);
+			CG_CUDA(cudaHostAlloc((void **) &ctx->meta_pinned[mslot], cap, cudaHostAllocDefault));
+			ctx->meta_cap[mslot] = cap;
+		}
+		uint8_t *hm = ctx->meta_pinned[mslot];
+		uint8_t *d_meta = nullptr;
 		CG_CUDA(cudaMallocAsync((void **) &d_arena, std::max<uint64_t>(sp.arena_bytes, 16), ctx->copy));
-		CG_CUDA(cudaMallocAsync((void **) &d_cols, sp.cols.size() * sizeof(DevChunkCol), ctx->copy));
-		CG_CUDA(cudaMallocAsync((void **) &d_ids, ncg * sizeof(uint32_t), ctx->copy));
-		std::vector<uint32_t> ids(ncg);
-		for (uint64_t g = 0; g < ncg; g++) ids[g] = (uint32_t) g;
-		CG_CUDA(cudaMemcpyAsync(d_cols, sp.cols.data(), sp.cols.size() * sizeof(DevChunkCol), cudaMemcpyHostToDevice, ctx->copy));
-		CG_CUDA(cudaMemcpyAsync(d_ids, ids.data(), ncg * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy));
-		CG_CUDA(cudaStreamSynchronize(ctx->copy));   /* ids / cols are pageable vectors about to go out of scope */
+		CG_CUDA(cudaMallocAsync((void **) &d_meta, meta_bytes, ctx->copy));
+		size_t off_ids = (cols_bytes + 15) & ~15ull, off_items = off_ids + ((ids_bytes + 15) & ~15ull);
+		memcpy(hm, sp.cols.data(), cols_bytes);
+		for (uint64_t g = 0; g < ncg; g++) ((uint32_t *) (hm + off_ids))[g] = (uint32_t) g;
+		if (items_bytes) memcpy(hm + off_items, items.data(), items_bytes);
+		CG_CUDA(cudaMemcpyAsync(d_meta, hm, meta_bytes, cudaMemcpyHostToDevice, ctx->copy));
+		d_cols = (DevChunkCol *) d_meta;
+		d_ids = (uint32_t *) (d_meta + off_ids);
 		plan.arena = d_arena;
 		plan.chunkcols = d_cols;
 		plan.nstaged = (int32_t) ns;
 		FPlan fast;
 		const bool use_fast = !sp.any_nulls && !cg_force_general() && cg_build_fast_plan(desc, plan, all8, &fast);
 		if (stats) CG_CUDA(cudaEventRecord(ctx->ev_a, ctx->compute));
-		rc = stream_to_device(ctx, rel, sp, ns, d_arena, [&](uint64_t cg0, uint64_t cg1, cudaEvent_t copied) -> int {
+		auto launch_block = [&](uint64_t cg0, uint64_t cg1, cudaEvent_t copied) -> int {
 			CG_CUDA(cudaStreamWaitEvent(ctx->compute, copied, 0));
 			if (sp.any_nulls)
 			{
@@ -872,12 +1016,32 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 			}
 			if (r) return r;
 			return cg_prof_mark(ctx, ctx->compute);
-		});
+		};
+		uint8_t *d_raw = nullptr;
+		if (dma)
+		{
+			/* the copy engine de-frames the pages */
+			CG_CUDA(cudaMallocAsync((void **) &d_raw, raw_bytes, ctx->copy));
+			for (const DmaCopy &c : copies)
+			{
+				CG_CUDA(cudaMemcpy2DAsync(d_raw + c.raw_off, CG_BYTES_PER_PAGE, rel->pages + c.first_block * CG_BLCKSZ + CG_PAGE_HEADER,
+										  CG_BLCKSZ, CG_BYTES_PER_PAGE, c.nblocks, cudaMemcpyHostToDevice, ctx->copy));
+				dma_bytes += c.nblocks * CG_BYTES_PER_PAGE;
+			}
+			CG_CUDA(cudaEventRecord(ctx->dma_copied, ctx->copy));
+			CG_CUDA(cudaStreamWaitEvent(ctx->compute, ctx->dma_copied, 0));
+			rc = cg_launch_realign(d_raw, d_arena, (const RealignItem *) (d_meta + off_items), items.size(), ctx->compute);
+			if (rc == CG_OK) rc = launch_block(0, ncg, ctx->dma_copied);
+			used_dma = true;
+		}
+		else
+			rc = stream_to_device(ctx, rel, sp, ns, d_arena, launch_block);
 		if (stats && rc == CG_OK) CG_CUDA(cudaEventRecord(ctx->ev_b, ctx->compute));
 		/* frees are ordered after the kernels on the compute stream */
+		if (d_raw) cudaFreeAsync(d_raw, ctx->compute);
 		cudaFreeAsync(d_arena, ctx->compute);
-		cudaFreeAsync(d_cols, ctx->compute);
-		cudaFreeAsync(d_ids, ctx->compute);
+		cudaFreeAsync(d_meta, ctx->compute);
+		CG_CUDA(cudaEventRecord(ctx->dma_done[mslot], ctx->compute));
 		if (rc) return rc;
 	}
 	if (stats)
@@ -893,7 +1057,8 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 			float ms = 0;
 			CG_CUDA(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
 			stats->kernel_ms = ms;   /* here: first kernel start to last kernel end, H2D overlapped */
-			stats->h2d_bytes = (int64_t) (sp.arena_bytes + sp.cols.size() * sizeof(DevChunkCol) + ncg * sizeof(uint32_t));
+			stats->h2d_bytes = (int64_t) ((used_dma ? dma_bytes + 2 * ncg * ns * sizeof(RealignItem) : sp.arena_bytes) +
+										  sp.cols.size() * sizeof(DevChunkCol) + ncg * sizeof(uint32_t));
 		}
 	}
 	return CG_OK;

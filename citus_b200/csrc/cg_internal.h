@@ -42,6 +42,13 @@ struct CgContext
 	cudaEvent_t ev_a = nullptr, ev_b = nullptr;
 	int stage_threads = 16;
 	cudaStream_t own_compute = nullptr;
+	/* DMA staging: shards in flight */
+	static const int kDmaDepth = 3;
+	cudaEvent_t dma_done[kDmaDepth] = {nullptr, nullptr, nullptr};
+	cudaEvent_t dma_copied = nullptr;
+	int dma_slot = 0;
+	uint8_t *meta_pinned[kDmaDepth] = {nullptr, nullptr, nullptr};   /* pinned ring for per-scan metadata */
+	size_t meta_cap[kDmaDepth] = {0, 0, 0};
 	/* per-launch profiling */
 	bool profiling = false;
 	std::vector<cudaEvent_t> prof_events;   /* pairs */
@@ -241,6 +248,16 @@ struct CgPartial
 
 /* cg_scan.cu */
 int cg_launch_scan(CgContext *ctx, const KPlan &plan, bool any_nulls, bool all8, cudaStream_t stream);
+/* one chunk buffer to move from the raw (page-payload) device buffer to its aligned arena slot */
+struct RealignItem
+{
+	uint64_t src;       /* byte offset in the raw buffer (any alignment) */
+	uint64_t dst;       /* arena offset, 16-byte aligned */
+	uint32_t len;       /* bytes to copy */
+	uint32_t padded;    /* slot size: bytes beyond len are zeroed */
+};
+int cg_launch_realign(const uint8_t *raw, uint8_t *arena, const RealignItem *items, uint64_t nitems, cudaStream_t stream);
+
 /* cg_scan_fast.cu */
 int cg_launch_scan_fast(CgContext *ctx, const FPlan &plan, cudaStream_t stream);
 int cg_launch_drain(CgPartial *p, cudaStream_t stream);

@@ -625,6 +625,56 @@ int cg_launch_rank(CgContext *ctx, const uint8_t *arena, const DevChunkCol *chun
 }
 
 /* ------------------------------------------------------------------------------ *
+ *  Realign: chunk buffers arrive from the copy engine at arbitrary byte offsets (exists
+ *  bitmaps are ceil(rows/8) bytes long, so value streams are not even 8-byte aligned in
+ *  the logical byte stream); every block moves one buffer to its 16-byte aligned slot with
+ *  aligned 4-byte loads + byte permutes, and zero-fills the slot's padding.
+ * ------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(128)
+cg_realign_kernel(const uint8_t *raw, uint8_t *arena, const RealignItem *items)
+{
+	const RealignItem it = items[blockIdx.x];
+	const uint8_t *src = raw + it.src;
+	const uint32_t mis = (uint32_t) ((uintptr_t) src & 3u);
+	const uint32_t *s32 = (const uint32_t *) (src - mis);
+	const uint32_t sel = 0x3210u + 0x1111u * mis;
+	uint4 *dst = (uint4 *) (arena + it.dst);
+	const uint32_t nvec = it.padded / 16;
+	for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x)
+	{
+		uint32_t o[4] = {0, 0, 0, 0};
+		if (16 * i < it.len)
+		{
+			uint32_t w[5];
+#pragma unroll
+			for (int k = 0; k < 5; k++) w[k] = __ldg(s32 + 4 * i + k);
+#pragma unroll
+			for (int k = 0; k < 4; k++) o[k] = __byte_perm(w[k], w[k + 1], sel);
+			if (16 * i + 16 > it.len)
+			{
+				/* the slot's tail: keep only the bytes that belong to the buffer */
+#pragma unroll
+				for (int k = 0; k < 4; k++)
+				{
+					int keep = (int) it.len - (int) (16 * i + 4 * k);
+					if (keep <= 0) o[k] = 0;
+					else if (keep < 4) o[k] &= (1u << (8 * keep)) - 1u;
+				}
+			}
+		}
+		dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+	}
+}
+
+int cg_launch_realign(const uint8_t *raw, uint8_t *arena, const RealignItem *items, uint64_t nitems, cudaStream_t stream)
+{
+	if (nitems == 0) return CG_OK;
+	cg_realign_kernel<<<(unsigned) nitems, 128, 0, stream>>>(raw, arena, items);
+	CG_CUDA(cudaGetLastError());
+	return CG_OK;
+}
+
+/* ------------------------------------------------------------------------------ *
  *  Group table: init, export (compaction), merge (K5 combine).
  * ------------------------------------------------------------------------------ */
 struct TableView

@@ -230,8 +230,14 @@ int cg_partial_set_packing(CgPartial *p, int32_t enable);
  * given (counters need the kernel to finish). */
 int cg_scan_shard(const CgShard *shard, const CgScanDesc *desc, CgPartial *into, CgScanStats *stats);
 
-/* End-to-end call on HOST buffers: stage (pipelined through pinned blocks) + scan.
- * This is what a GpuColumnarAgg CustomScan node calls once per shard task. */
+/* End-to-end call on HOST buffers: stage + scan.  This is what a GpuColumnarAgg CustomScan
+ * node calls once per shard task.  Pageable pages (shared_buffers as it is today) are
+ * de-framed by host threads into pinned blocks and sent with cudaMemcpyAsync; pages in
+ * pinned memory (cg_relation_register, or a shared_buffers segment registered once at
+ * startup) are sent by the copy engine itself with strided 2-D copies that skip the page
+ * headers, and re-aligned on the GPU. */
+int cg_relation_register(const CgRelation *rel);      /* cudaHostRegister of the page image */
+int cg_relation_unregister(const CgRelation *rel);
 int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, CgPartial *into, CgScanStats *stats);
 
 /* Result rows.  Group order is unspecified (it is a hash aggregate).

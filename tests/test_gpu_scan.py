@@ -79,7 +79,12 @@ def run_both(cg, oracle, rel, quals=(), group_cols=(), aggs=(), chunk_row_limit=
         kmin, kmax = 0, -1
     agg = cg.GpuColumnarAgg(d, rel.column_descs(), kmin, kmax, max(rows, 1))
     if e2e:
+        if e2e == "dma":
+            rel.register()                       # pinned pages: copy-engine de-framing + GPU realign
         st = agg.scan_relation(rel)
+        if e2e == "dma":
+            assert st.h2d_bytes > 0
+            rel.unregister()
     else:
         shard = cg.Shard(rel)
         st = agg.scan_shard(shard)
@@ -161,6 +166,8 @@ def test_c2_filter_group_by(cg, oracle, force_hash, null_ppm):
     # same through the end-to-end call on host buffers
     run_both(cg, oracle, rel, quals=[(1, "<", 50)], group_cols=[0], aggs=[cg.sum_(2), cg.count_star()],
              force_hash=force_hash, expected_groups=5000, e2e=True)
+    run_both(cg, oracle, rel, quals=[(1, "<", 50)], group_cols=[0], aggs=[cg.sum_(2), cg.count_star()],
+             force_hash=force_hash, expected_groups=5000, e2e="dma")
 
 
 def test_group_by_wide_keys_null_keys_and_two_limb_sums(cg, oracle):
@@ -305,6 +312,11 @@ def test_mixed_widths_with_nulls(cg, oracle):
     run_both(cg, oracle, rel, quals=[(5, ">=", -0.25)], group_cols=[3], aggs=aggs[:5] + [cg.count_star()], float_cols=(4, 5))
     run_both(cg, oracle, rel, quals=[(1, "<>", 0)], group_cols=[3], aggs=[cg.count_star(), cg.sum_(1)],
              float_cols=(4, 5), force_hash=True, expected_groups=300)
+    # odd-length exists bitmaps put every value stream at an odd byte offset: the DMA path's realign kernel
+    run_both(cg, oracle, rel, quals=[(2, ">", -20000), (4, "<", 1.5)], aggs=aggs, float_cols=(4, 5), e2e="dma")
+    sorted_rel = cg.Relation.write([8, 4], [np.sort(c8), c4], [None, nulls[1]], stripe_row_limit=20000, chunk_row_limit=1111)
+    run_both(cg, oracle, sorted_rel, quals=[(0, ">", 0)], group_cols=[], aggs=[cg.count_star(), cg.sum_(1), cg.min_(0)],
+             chunk_row_limit=1111, e2e="dma")                   # chunk-group skipping + DMA spans
 
 
 def test_ragged_chunks_and_max_chunk_size(cg, oracle):
@@ -317,6 +329,8 @@ def test_ragged_chunks_and_max_chunk_size(cg, oracle):
         run_both(cg, oracle, rel, quals=[(0, ">=", -500)], group_cols=[1], aggs=[cg.count_star(), cg.sum_(0)],
                  chunk_row_limit=chunk)
         run_both(cg, oracle, rel, aggs=[cg.count_star(), cg.sum_(0), cg.count(1)], chunk_row_limit=chunk, e2e=True)
+        run_both(cg, oracle, rel, quals=[(0, "<", 900)], group_cols=[1], aggs=[cg.count_star(), cg.sum_(0)],
+                 chunk_row_limit=chunk, e2e="dma")
 
 
 def test_unsupported_inputs_are_refused(cg, oracle):
