@@ -108,7 +108,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.002)
 
     def result(self):
         self.stop_flag.set()
@@ -215,7 +215,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU restatement of the reference path (oracle/oracle.c): PostgreSQL/Citus cannot be built here",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, where):
@@ -422,10 +422,24 @@ def run_ours(args, rank, world, local_rank):
         }
         if parity is not None:
             line["parity_full_size"] = parity
-        print(json.dumps(line), flush=True)
+        emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """the ONE JSON line goes to the real stdout; everything else (NCCL banners, library
+    chatter) was redirected to stderr at start-up"""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
