@@ -431,6 +431,16 @@ bool cg_build_fast_plan(const CgScanDesc *desc, const KPlan &plan, bool all8, FP
 				fast->pack_shift = plan.pack_shift;
 				fast->pack_sum = i;
 			}
+	if (fast->pack_sum > 0)
+	{
+		/* the kernel packs sum number 0: move the packed sum to the front of the sum roles */
+		int i = fast->pack_sum, base = role - ns;
+		std::swap(fast->slot[base], fast->slot[base + i]);
+		std::swap(fast->sword[0], fast->sword[i]);
+		std::swap(fast->slimbs[0], fast->slimbs[i]);
+		std::swap(fast->sbound[0], fast->sbound[i]);
+		fast->pack_sum = 0;
+	}
 	{
 		/* tuning switches (measurements only): CG_FAST_FLAGS overrides the default */
 		static int env_flags = -1;

@@ -11,12 +11,14 @@
  * the NULL-free value stream = a dense int8 array, columnar_reader.c:1542-1572; K3 ExecQual;
  * K4 nodeAgg transition functions), but the plan shape is a template parameter, so the
  * per-row work is a handful of instructions: the kernel is bound by HBM loads and by the
- * L2 atomic units, not by instruction issue.
+ * L2 reduction requests, not by instruction issue.
  *
  *   NQ    range conjuncts, each on its own column (several btree conjuncts on one column
  *         are intersected into one [lo, hi] on the host)
  *   MODE  plain aggregate / direct-indexed table / hash table
  *   NS    sum(column) aggregates
+ *   PACK  direct-indexed only: count(*) and sum number 0 share one 64-bit word
+ *         (optimistic packing, see include/citus_gpu.h cg_partial_set_packing)
  * Column roles map to fixed register positions: quals first, then the key, then the sums.
  */
 #include "cg_internal.h"
@@ -30,28 +32,16 @@ __device__ __forceinline__ void ldg16(const void *p, uint64_t &a, uint64_t &b, u
 	asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(a), "=l"(b) : "l"(p), "l"(policy));
 }
 
-/* group-table update: fire-and-forget reduction at the L2 atomic unit, line kept in L2 */
-__device__ __forceinline__ void red_add_u64(uint64_t *p, uint64_t v, uint64_t policy)
+/* group-table update: fire-and-forget reduction at the L2 atomic unit */
+__device__ __forceinline__ void red_add_u64(uint64_t *p, uint64_t v)
 {
-	asm volatile("red.global.add.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(policy) : "memory");
+	asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 __device__ __forceinline__ uint64_t policy_evict_first()
 {
 	uint64_t pol;
 	asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-	return pol;
-}
-__device__ __forceinline__ uint64_t policy_evict_last()
-{
-	uint64_t pol;
-	asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-	return pol;
-}
-__device__ __forceinline__ uint64_t policy_evict_normal()
-{
-	uint64_t pol;
-	asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
 	return pol;
 }
 
@@ -61,6 +51,12 @@ __device__ __forceinline__ uint64_t mix64f(uint64_t x)
 	return x;
 }
 
+__device__ __noinline__ void raise_flag(unsigned long long *stats, unsigned long long flag)
+{
+	atomicOr(stats + 2, flag);
+}
+
+/* word pointer of the group's entry, or NULL after raising an error flag */
 template <int MODE>
 __device__ __forceinline__ uint64_t *fast_entry(const FPlan &P, int64_t key)
 {
@@ -69,7 +65,7 @@ __device__ __forceinline__ uint64_t *fast_entry(const FPlan &P, int64_t key)
 		uint64_t slot = (uint64_t) key - (uint64_t) P.key_min;
 		if (slot >= P.capacity)
 		{
-			atomicOr(P.stats + 2, CG_ERRFLAG_KEY_RANGE);
+			raise_flag(P.stats, CG_ERRFLAG_KEY_RANGE);
 			return nullptr;
 		}
 		return P.table + slot * (uint64_t) P.stride;
@@ -82,7 +78,7 @@ __device__ __forceinline__ uint64_t *fast_entry(const FPlan &P, int64_t key)
 		for (uint32_t probes = 0; probes < 8192; probes++)
 		{
 			unsigned long long *kp = (unsigned long long *) (P.table + h * (uint64_t) P.stride);
-			long long cur = (long long) __ldcg(kp);
+			long long cur = (long long) __ldcg(kp);        /* keys only ever go EMPTY -> key */
 			if (cur == key) return (uint64_t *) kp + 1;
 			if (cur == CG_HASH_EMPTY)
 			{
@@ -91,18 +87,10 @@ __device__ __forceinline__ uint64_t *fast_entry(const FPlan &P, int64_t key)
 			}
 			h = (h + 1) & mask;
 		}
-		atomicOr(P.stats + 2, CG_ERRFLAG_TABLE_FULL);
+		raise_flag(P.stats, CG_ERRFLAG_TABLE_FULL);
 		return nullptr;
 	}
 }
-
-template <int NS>
-struct FastAcc
-{
-	uint64_t rows;
-	uint64_t lo[NS > 0 ? NS : 1];
-	int64_t hi[NS > 0 ? NS : 1];
-};
 
 template <int NQ>
 __device__ __forceinline__ bool fast_pass(const FPlan &P, const int64_t *v)
@@ -117,17 +105,30 @@ __device__ __forceinline__ bool fast_pass(const FPlan &P, const int64_t *v)
 	return pass;
 }
 
+/* wide (exact) update of one sum word / word pair */
+__device__ __forceinline__ void wide_sum(const FPlan &P, uint64_t *e, int s, int64_t x)
+{
+	if (P.slimbs[s] == 1)
+	{
+		if (x > P.sbound[s] || x < -P.sbound[s]) raise_flag(P.stats, CG_ERRFLAG_SUM_BOUND);
+		red_add_u64(e + P.sword[s], (uint64_t) x);
+	}
+	else
+	{
+		red_add_u64(e + P.sword[s], (uint64_t) (uint32_t) x);
+		red_add_u64(e + P.sword[s] + 1, (uint64_t) (x >> 32));
+	}
+}
+
 /*
- * Paired table update (all sums single-word).  The accumulator words of one group are
- * adjacent (one 32-byte sector); instead of every lane issuing one reduction per word --
- * 32 sectors per instruction and word -- lanes work in pairs: in round 0 both lanes of a
- * pair update the row of the even lane (even lane: word 0, odd lane: word 1, ...), in
- * round 1 the row of the odd lane.  One reduction instruction then carries both words of
- * 16 groups in 16 sectors, halving the L2 atomic transactions per row.
- * Must be called by all 32 lanes.
+ * Paired table update, hash tables with single-word sums.  The accumulator words of one
+ * group are adjacent (one 32-byte sector, right behind the key the lookup just read); lanes
+ * work in pairs: in round 0 both lanes of a pair update the row of the even lane (even lane:
+ * word 0, odd lane: word 1, ...), in round 1 the row of the odd lane.  Must be called by all
+ * 32 lanes.
  */
 template <int NS>
-__device__ __forceinline__ void paired_update(const FPlan &P, bool pass, uint64_t *e, const int64_t *sums, uint64_t pol)
+__device__ __forceinline__ void paired_update(const FPlan &P, bool pass, uint64_t *e, const int64_t *sums)
 {
 	const unsigned lane = threadIdx.x & 31u;
 	const bool odd = lane & 1u;
@@ -149,7 +150,7 @@ __device__ __forceinline__ void paired_update(const FPlan &P, bool pass, uint64_
 			for (int j = 0; j < (NS + 2) / 2; j++)
 			{
 				const int w = 2 * j + (odd ? 1 : 0);     /* 0 = row count, 1.. = sums */
-				if (w == 0) red_add_u64(te, 1ull, pol);
+				if (w == 0) red_add_u64(te, 1ull);
 				else if (w <= NS)
 				{
 					int64_t x = 0;
@@ -157,15 +158,24 @@ __device__ __forceinline__ void paired_update(const FPlan &P, bool pass, uint64_
 #pragma unroll
 					for (int s = 0; s < NS; s++)
 						if (s == w - 1) { x = mine ? sums[s] : ps[s]; wordidx = P.sword[s]; }
-					red_add_u64(te + wordidx, (uint64_t) x, pol);
+					red_add_u64(te + wordidx, (uint64_t) x);
 				}
 			}
 		}
 	}
 }
 
-template <int NQ, int MODE, int NS>
-__device__ __forceinline__ void fast_row(const FPlan &P, const int64_t *v, FastAcc<NS> &acc, uint32_t &removed, uint64_t pol)
+template <int NS>
+struct FastAcc
+{
+	uint64_t rows;                      /* plain aggregate: rows passed; PACK: rows added to packed words */
+	uint64_t lo[NS > 0 ? NS : 1];
+	int64_t hi[NS > 0 ? NS : 1];
+};
+
+/* one row of a plain aggregate or of a direct-indexed / unpaired table */
+template <int NQ, int MODE, int NS, bool PACK>
+__device__ __forceinline__ void fast_row(const FPlan &P, const int64_t *v, FastAcc<NS> &acc, uint32_t &removed)
 {
 	constexpr int KEYPOS = NQ;
 	constexpr int SUMPOS = NQ + (MODE != CG_MODE_GLOBAL ? 1 : 0);
@@ -184,37 +194,34 @@ __device__ __forceinline__ void fast_row(const FPlan &P, const int64_t *v, FastA
 			acc.lo[s] += (uint64_t) (uint32_t) x;
 			acc.hi[s] += x >> 32;
 		}
+		return;
 	}
-	else
+	if (PACK)
 	{
-		uint64_t *e = fast_entry<MODE>(P, v[KEYPOS]);
-		if (e == nullptr) return;
-		const bool packed = MODE == CG_MODE_DENSE && NS > 0 && P.packed != nullptr;
-		if (!packed) red_add_u64(e, 1ull, pol);
-#pragma unroll
-		for (int s = 0; s < NS; s++)
+		/* one reduction for count(*) and sum 0: word += (x << C) + 1 (mod 2^64) */
+		uint64_t slot = (uint64_t) v[KEYPOS] - (uint64_t) P.key_min;
+		if (slot >= P.capacity)
 		{
-			int64_t x = v[SUMPOS + s];
-			if (packed && s == P.pack_sum)
-			{
-				/* one reduction for count(*) and this sum: word += (x << C) + 1 (mod 2^64) */
-				if (x > P.sbound[s] || x < -P.sbound[s]) atomicOr(P.stats + 2, CG_ERRFLAG_SUM_BOUND);
-				uint64_t slot = (uint64_t) (e - P.table) / (uint64_t) P.stride;
-				red_add_u64(P.packed + slot, ((uint64_t) x << P.pack_shift) + 1ull, pol);
-				acc.rows++;      /* rows added to packed words (verified against the drains) */
-			}
-			else if (P.slimbs[s] == 1)
-			{
-				if (x > P.sbound[s] || x < -P.sbound[s]) atomicOr(P.stats + 2, CG_ERRFLAG_SUM_BOUND);
-				red_add_u64(e + P.sword[s], (uint64_t) x, pol);
-			}
-			else
-			{
-				red_add_u64(e + P.sword[s], (uint64_t) (uint32_t) x, pol);
-				red_add_u64(e + P.sword[s] + 1, (uint64_t) (x >> 32), pol);
-			}
+			raise_flag(P.stats, CG_ERRFLAG_KEY_RANGE);
+			return;
 		}
+		int64_t x = v[SUMPOS];
+		if (x > P.sbound[0] || x < -P.sbound[0]) raise_flag(P.stats, CG_ERRFLAG_SUM_BOUND);
+		red_add_u64(P.packed + slot, ((uint64_t) x << P.pack_shift) + 1ull);
+		acc.rows++;
+		if (NS > 1)
+		{
+			uint64_t *e = P.table + slot * (uint64_t) P.stride;
+#pragma unroll
+			for (int s = 1; s < NS; s++) wide_sum(P, e, s, v[SUMPOS + s]);
+		}
+		return;
 	}
+	uint64_t *e = fast_entry<MODE>(P, v[KEYPOS]);
+	if (e == nullptr) return;
+	red_add_u64(e, 1ull);
+#pragma unroll
+	for (int s = 0; s < NS; s++) wide_sum(P, e, s, v[SUMPOS + s]);
 }
 
 __device__ __forceinline__ uint64_t warp_sum(uint64_t x)
@@ -224,11 +231,14 @@ __device__ __forceinline__ uint64_t warp_sum(uint64_t x)
 	return x;
 }
 
-template <int NQ, int MODE, int NS, int U>
+template <int NQ, int MODE, int NS, bool PACK, int U>
 __global__ void __launch_bounds__(CGF_THREADS)
 cg_scan_fast_kernel(const __grid_constant__ FPlan P)
 {
 	constexpr int NC = NQ + (MODE != CG_MODE_GLOBAL ? 1 : 0) + NS;
+	constexpr int NCA = NC > 0 ? NC : 1;
+	constexpr int KEYPOS = NQ;
+	constexpr int SUMPOS = NQ + (MODE != CG_MODE_GLOBAL ? 1 : 0);
 	FastAcc<NS> acc;
 	acc.rows = 0;
 #pragma unroll
@@ -236,32 +246,27 @@ cg_scan_fast_kernel(const __grid_constant__ FPlan P)
 	uint32_t removed = 0;
 	unsigned long long scanned = 0;
 	const uint32_t tid = threadIdx.x;
-	const uint64_t pol_stream = (P.flags & CG_FAST_NO_HINTS) ? policy_evict_normal() : policy_evict_first();
-	const uint64_t pol_table = (P.flags & CG_FAST_NO_HINTS) ? policy_evict_normal() : policy_evict_last();
-	const bool paired = (MODE != CG_MODE_GLOBAL) && NS > 0 && (P.flags & CG_FAST_PAIRED) && P.packed == nullptr;
-	constexpr int KEYPOS = NQ;
-	constexpr int SUMPOS = NQ + (MODE != CG_MODE_GLOBAL ? 1 : 0);
+	const uint64_t pol_stream = policy_evict_first();
+	/* hash tables with single-word sums: lane-paired updates (decided per launch, uniform) */
+	const bool paired = (MODE == CG_MODE_HASH) && NS > 0 && (P.flags & CG_FAST_PAIRED);
 
 	for (uint32_t ci = blockIdx.x; ci < P.nselected; ci += gridDim.x)
 	{
 		const DevChunkCol *cc = P.chunkcols + (uint64_t) P.selected[ci] * (uint64_t) P.nstaged;
 		const uint32_t rows = __ldg(&cc[0].row_count);
-		const uint8_t *vp[NC > 0 ? NC : 1];
+		const uint8_t *vp[NCA];
 #pragma unroll
 		for (int c = 0; c < NC; c++) vp[c] = P.arena + __ldg(&cc[P.slot[c]].values_off);
 		scanned += (tid == 0) ? rows : 0;
 		if (NC == 0)
 		{
 			/* count(*) without any column: every row of the chunk group passes */
-			if (tid == 0)
-			{
-				if (MODE == CG_MODE_GLOBAL) acc.rows += rows;
-			}
+			if (tid == 0) acc.rows += rows;
 			continue;
 		}
 		for (uint32_t base = 0; base < rows; base += CGF_THREADS * 2 * U)
 		{
-			int64_t v0[U][NC > 0 ? NC : 1], v1[U][NC > 0 ? NC : 1];
+			int64_t v0[U][NCA], v1[U][NCA];
 #pragma unroll
 			for (int u = 0; u < U; u++)
 			{
@@ -281,7 +286,7 @@ cg_scan_fast_kernel(const __grid_constant__ FPlan P)
 			for (int u = 0; u < U; u++)
 			{
 				uint32_t r = base + (u * CGF_THREADS + tid) * 2;
-				if (paired)
+				if (MODE == CG_MODE_HASH && paired)
 				{
 					/* warp-converged: lanes past the end of the chunk group take part with pass = false */
 #pragma unroll
@@ -299,15 +304,15 @@ cg_scan_fast_kernel(const __grid_constant__ FPlan P)
 #pragma unroll
 							for (int s = 0; s < NS; s++)
 								if (v[SUMPOS + s] > P.sbound[s] || v[SUMPOS + s] < -P.sbound[s])
-									atomicOr(P.stats + 2, CG_ERRFLAG_SUM_BOUND);
+									raise_flag(P.stats, CG_ERRFLAG_SUM_BOUND);
 						}
-						paired_update<NS>(P, pass, e, v + SUMPOS, pol_table);
+						paired_update<NS>(P, pass, e, v + SUMPOS);
 					}
 				}
 				else if (r < rows)
 				{
-					fast_row<NQ, MODE, NS>(P, v0[u], acc, removed, pol_table);
-					if (r + 1 < rows) fast_row<NQ, MODE, NS>(P, v1[u], acc, removed, pol_table);
+					fast_row<NQ, MODE, NS, PACK>(P, v0[u], acc, removed);
+					if (r + 1 < rows) fast_row<NQ, MODE, NS, PACK>(P, v1[u], acc, removed);
 				}
 			}
 		}
@@ -320,7 +325,7 @@ cg_scan_fast_kernel(const __grid_constant__ FPlan P)
 		if (scn) atomicAdd(P.stats + 0, scn);
 		if (rem) atomicAdd(P.stats + 1, rem);
 	}
-	if (MODE == CG_MODE_DENSE)
+	if (PACK)
 	{
 		uint64_t added = warp_sum(acc.rows);
 		if ((tid & 31) == 0 && added) atomicAdd(P.stats + CG_STAT_PACKED_ADDED, (unsigned long long) added);
@@ -328,7 +333,7 @@ cg_scan_fast_kernel(const __grid_constant__ FPlan P)
 	if (MODE == CG_MODE_GLOBAL)
 	{
 		uint64_t rows_passed = warp_sum(acc.rows);
-		if ((tid & 31) == 0 && rows_passed) red_add_u64(P.table, rows_passed, pol_table);
+		if ((tid & 31) == 0 && rows_passed) red_add_u64(P.table, rows_passed);
 #pragma unroll
 		for (int s = 0; s < NS; s++)
 		{
@@ -336,11 +341,11 @@ cg_scan_fast_kernel(const __grid_constant__ FPlan P)
 			uint64_t hi = warp_sum((uint64_t) acc.hi[s]);
 			if ((tid & 31) == 0 && (lo | hi))
 			{
-				if (P.slimbs[s] == 1) red_add_u64(P.table + P.sword[s], lo + (hi << 32), pol_table);
+				if (P.slimbs[s] == 1) red_add_u64(P.table + P.sword[s], lo + (hi << 32));
 				else
 				{
-					red_add_u64(P.table + P.sword[s], lo, pol_table);
-					red_add_u64(P.table + P.sword[s] + 1, hi, pol_table);
+					red_add_u64(P.table + P.sword[s], lo);
+					red_add_u64(P.table + P.sword[s] + 1, hi);
 				}
 			}
 		}
@@ -386,13 +391,7 @@ int cg_launch_drain(CgPartial *p, cudaStream_t stream)
 	return CG_OK;
 }
 
-struct FastVariant
-{
-	void (*kernel)(FPlan);
-	int occupancy;
-};
-
-template <int NQ, int MODE, int NS>
+template <int NQ, int MODE, int NS, bool PACK>
 static int launch_fast_variant(CgContext *ctx, const FPlan &plan, cudaStream_t stream)
 {
 	constexpr int NC = NQ + (MODE != CG_MODE_GLOBAL ? 1 : 0) + NS;
@@ -400,13 +399,13 @@ static int launch_fast_variant(CgContext *ctx, const FPlan &plan, cudaStream_t s
 	static int occ = 0;
 	if (occ == 0)
 	{
-		CG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_scan_fast_kernel<NQ, MODE, NS, U>, CGF_THREADS, 0));
+		CG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_scan_fast_kernel<NQ, MODE, NS, PACK, U>, CGF_THREADS, 0));
 		if (occ < 1) occ = 1;
 	}
 	uint32_t grid = (uint32_t) (ctx->sm_count * occ);
 	if (grid > plan.nselected) grid = plan.nselected;
 	if (grid == 0) return CG_OK;
-	cg_scan_fast_kernel<NQ, MODE, NS, U><<<grid, CGF_THREADS, 0, stream>>>(plan);
+	cg_scan_fast_kernel<NQ, MODE, NS, PACK, U><<<grid, CGF_THREADS, 0, stream>>>(plan);
 	CG_CUDA(cudaGetLastError());
 	return CG_OK;
 }
@@ -414,12 +413,21 @@ static int launch_fast_variant(CgContext *ctx, const FPlan &plan, cudaStream_t s
 template <int NQ, int MODE>
 static int launch_fast_ns(CgContext *ctx, const FPlan &plan, cudaStream_t stream)
 {
+	if (MODE == CG_MODE_DENSE && plan.packed)
+	{
+		switch (plan.nsums)
+		{
+			case 1: return launch_fast_variant<NQ, CG_MODE_DENSE, 1, true>(ctx, plan, stream);
+			case 2: return launch_fast_variant<NQ, CG_MODE_DENSE, 2, true>(ctx, plan, stream);
+			default: return launch_fast_variant<NQ, CG_MODE_DENSE, 3, true>(ctx, plan, stream);
+		}
+	}
 	switch (plan.nsums)
 	{
-		case 0: return launch_fast_variant<NQ, MODE, 0>(ctx, plan, stream);
-		case 1: return launch_fast_variant<NQ, MODE, 1>(ctx, plan, stream);
-		case 2: return launch_fast_variant<NQ, MODE, 2>(ctx, plan, stream);
-		default: return launch_fast_variant<NQ, MODE, 3>(ctx, plan, stream);
+		case 0: return launch_fast_variant<NQ, MODE, 0, false>(ctx, plan, stream);
+		case 1: return launch_fast_variant<NQ, MODE, 1, false>(ctx, plan, stream);
+		case 2: return launch_fast_variant<NQ, MODE, 2, false>(ctx, plan, stream);
+		default: return launch_fast_variant<NQ, MODE, 3, false>(ctx, plan, stream);
 	}
 }
 
