@@ -238,8 +238,10 @@ def run_ours(args, rank, world, local_rank):
     from citus_b200 import distributed as cgd
     torch.cuda.set_device(local_rank)
     cg.init(local_rank)
-    stream = torch.cuda.current_stream()
-    capi.check(capi.lib().cg_set_stream(C.c_void_p(stream.cuda_stream)))
+    # one non-default torch stream for everything: the library's kernels, torch ops, the events that
+    # time them and (through torch's stream dependencies) the NCCL collectives
+    torch.cuda.set_stream(torch.cuda.Stream())
+    cg.use_torch_stream()
 
     rows_per_shard = args.rows // NSHARDS
     total_rows = rows_per_shard * NSHARDS

@@ -30,6 +30,15 @@ def init(device: int = 0):
     _initialised = True
 
 
+def use_torch_stream():
+    """run the library's kernels on torch's current stream, so that torch ops, NCCL collectives and
+    the library's kernels are ordered in one queue (torch's default stream is CUDA's legacy default
+    stream, whose handle is 0: it is passed as cudaStreamLegacy = 1)"""
+    import torch
+    h = torch.cuda.current_stream().cuda_stream
+    check(lib().cg_set_stream(C.c_void_p(h if h else 1)))
+
+
 class Relation:
     """Owns (or borrows) a relation image and exposes it as a CgRelation."""
 

@@ -42,8 +42,9 @@ int cg_init(int device_ordinal);          /* idempotent */
 int cg_device_count(int *count);
 int cg_synchronize(void);                 /* waits for the library's streams */
 /* Run the kernels on a stream owned by the caller (a CUstream / cudaStream_t handle passed as
- * void *; NULL restores the library's own stream).  Lets a host that already has a stream --
- * e.g. the one its NCCL collectives are ordered on -- keep everything in one queue. */
+ * void *; NULL restores the library's own stream; (void *) 1 is CUDA's legacy default stream,
+ * cudaStreamLegacy).  Lets a host that already has a stream -- e.g. the one its NCCL
+ * collectives are ordered on -- keep everything in one queue. */
 int cg_set_stream(void *cuda_stream);
 /* Per-launch device timing of the fused scan kernels: between begin and collect every scan
  * launch is bracketed by CUDA events on the launching stream (no host synchronisation);

@@ -19,6 +19,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from citus_b200 import columnar as cg, distributed as cgd
     cg.init(local)
+    cg.use_torch_stream()
     nshards, rows = 8, 200_000
     cols = [(8, 0, 0, 5000, 0), (8, 0, 0, 100, 0), (8, 0, -10**9, 10**9, 20000)]
     ok = True

