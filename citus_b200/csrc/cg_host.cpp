@@ -310,7 +310,16 @@ extern "C" int cg_relation_bounds(const CgRelation *rel, const CgScanDesc *desc,
 			int c = desc->group_cols[0];
 			if (!unknown[c] && cmin[c] <= cmax[c]) { *key_min = cmin[c]; *key_max = cmax[c]; }
 		}
-		/* packed two-column keys are sparse: leave min > max (hash table) */
+		if (desc->ngroup_cols == 2)
+		{
+			/* per-column bounds packed like the key (low 32 bits: first column) */
+			int c0 = desc->group_cols[0], c1 = desc->group_cols[1];
+			if (!unknown[c0] && !unknown[c1] && cmin[c0] <= cmax[c0] && cmin[c1] <= cmax[c1])
+			{
+				*key_min = (int64_t) ((uint64_t) (uint32_t) cmin[c0] | ((uint64_t) (uint32_t) cmin[c1] << 32));
+				*key_max = (int64_t) ((uint64_t) (uint32_t) cmax[c0] | ((uint64_t) (uint32_t) cmax[c1] << 32));
+			}
+		}
 	}
 	if (term_abs_bound)
 		for (int a = 0; a < desc->naggs; a++)
@@ -739,12 +748,20 @@ extern "C" int cg_scan_shard(const CgShard *sh, const CgScanDesc *desc, CgPartia
 		plan.selected = sh->d_selected;
 		plan.nselected = (uint32_t) selected.size();
 		FPlan fast;
-		bool use_fast = !cg_force_general() && cg_build_fast_plan(desc, plan, all8, &fast);
+		const bool use_small = cg_small_eligible(plan) && !cg_force_general();
+		bool use_fast = !use_small && !cg_force_general() && cg_build_fast_plan(desc, plan, all8, &fast);
 		uint32_t nfast = use_fast ? sh->sel_nfast : 0;
 		if (stats) CG_CUDA(cudaEventRecord(ctx->ev_a, ctx->compute));
 		rc = cg_prof_mark(ctx, ctx->compute);
 		if (rc) return rc;
-		if (nfast > 0)
+		if (use_small)
+		{
+			/* tiny key domain: shared-memory tables + warp-level pre-aggregation, all chunk groups */
+			rc = cg_launch_scan_small(ctx, plan, all8, ctx->compute);
+			if (rc) return rc;
+			nfast = plan.nselected;
+		}
+		else if (nfast > 0)
 		{
 			fast.nselected = nfast;
 			rc = cg_launch_scan_fast(ctx, fast, ctx->compute);
@@ -988,7 +1005,8 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 		plan.chunkcols = d_cols;
 		plan.nstaged = (int32_t) ns;
 		FPlan fast;
-		const bool use_fast = !sp.any_nulls && !cg_force_general() && cg_build_fast_plan(desc, plan, all8, &fast);
+		const bool use_small = cg_small_eligible(plan) && !cg_force_general();
+		const bool use_fast = !use_small && !sp.any_nulls && !cg_force_general() && cg_build_fast_plan(desc, plan, all8, &fast);
 		if (stats) CG_CUDA(cudaEventRecord(ctx->ev_a, ctx->compute));
 		auto launch_block = [&](uint64_t cg0, uint64_t cg1, cudaEvent_t copied) -> int {
 			CG_CUDA(cudaStreamWaitEvent(ctx->compute, copied, 0));
@@ -999,7 +1017,14 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 			}
 			int r = cg_prof_mark(ctx, ctx->compute);
 			if (r) return r;
-			if (use_fast)
+			if (use_small)
+			{
+				KPlan blk = plan;
+				blk.selected = d_ids + cg0;
+				blk.nselected = (uint32_t) (cg1 - cg0);
+				r = cg_launch_scan_small(ctx, blk, all8, ctx->compute);
+			}
+			else if (use_fast)
 			{
 				FPlan blk = fast;
 				blk.selected = d_ids + cg0;

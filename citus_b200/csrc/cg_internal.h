@@ -154,6 +154,10 @@ struct KPlan
 	uint8_t qcol[CG_MAX_QUALS];
 	uint8_t qop[CG_MAX_QUALS];
 	int64_t qk[CG_MAX_QUALS];
+	/* integer conjuncts in range form: pass iff ((x >= qlo && x <= qhi) != qneg) */
+	int64_t qlo[CG_MAX_QUALS];
+	int64_t qhi[CG_MAX_QUALS];
+	uint8_t qneg[CG_MAX_QUALS];
 
 	int32_t ngroup;
 	uint8_t gcol[CG_MAX_GROUP_COLS];
@@ -165,9 +169,13 @@ struct KPlan
 	int32_t mode;
 	int32_t nwords;               /* accumulator words per group; word 0 = rows in group */
 	int32_t stride;               /* 64-bit words per entry (hash: key + words, padded) */
-	uint64_t *table;              /* dense: [capacity+1][stride]; hash: [capacity+2][stride] */
+	uint64_t *table;              /* accumulator words: dense [capacity+1][stride]; hash [capacity+2][stride] */
+	int64_t *hkeys;               /* hash: key of every slot, [capacity+2] */
 	uint64_t capacity;            /* hash: power of two */
-	int64_t key_min;              /* dense */
+	int32_t hash_shift;           /* hash: 64 - log2(capacity) */
+	int64_t key_min;              /* dense (two group columns: minimum of the first) */
+	int64_t key_min1;             /* dense, two group columns: minimum of the second */
+	uint64_t range1;              /* ... and its range; slot = (k0 - key_min) * range1 + (k1 - key_min1) */
 	uint8_t wordop[CG_KMAX_WORDS];
 
 	unsigned long long *stats;    /* [0] rows scanned [1] rows removed [2] error flags
@@ -196,7 +204,9 @@ struct FPlan
 	int64_t qlo[2], qhi[2];
 	int64_t sbound[3];
 	uint64_t *table;
+	int64_t *hkeys;
 	uint64_t capacity;
+	int32_t hash_shift;
 	int32_t stride;
 	int64_t key_min;
 	unsigned long long *stats;
@@ -226,10 +236,13 @@ struct CgPartial
 	uint64_t capacity = 0;      /* addressable slots (dense: domain size, hash: pow2) */
 	uint64_t entries = 0;       /* allocated entries incl. the special ones */
 	int64_t key_min = 0, key_max = -1;
+	int64_t key_min1 = 0;        /* two group columns, direct-indexed: second column's minimum and range */
+	uint64_t range1 = 0;
 	int64_t max_rows = 0;
 	uint8_t wordop[CG_KMAX_WORDS];
 	KAgg aggs[CG_MAX_AGGS];
 	uint64_t *d_table = nullptr;
+	int64_t *d_hkeys = nullptr;            /* hash mode: separate key array (same allocation as d_table) */
 	unsigned long long *d_stats = nullptr;   /* 8 words */
 	/* optimistic packing */
 	uint64_t *d_packed = nullptr;
@@ -258,6 +271,9 @@ struct RealignItem
 };
 int cg_launch_realign(const uint8_t *raw, uint8_t *arena, const RealignItem *items, uint64_t nitems, cudaStream_t stream);
 
+/* cg_scan_small.cu */
+bool cg_small_eligible(const KPlan &plan);
+int cg_launch_scan_small(CgContext *ctx, const KPlan &plan, bool all8, cudaStream_t stream);
 /* cg_scan_fast.cu */
 int cg_launch_scan_fast(CgContext *ctx, const FPlan &plan, cudaStream_t stream);
 int cg_launch_drain(CgPartial *p, cudaStream_t stream);

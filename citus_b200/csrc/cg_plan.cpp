@@ -167,7 +167,26 @@ extern "C" int cg_partial_create(const CgScanDesc *desc, const CgColumnDesc *col
 		p->mode = CG_MODE_GLOBAL;
 		p->capacity = 1; p->entries = 1; p->stride = p->nwords;
 	}
-	else if (key_min <= key_max && ((uint64_t) key_max - (uint64_t) key_min) < kDenseLimit)
+	else if (desc->ngroup_cols == 2 && key_min <= key_max &&
+			 (int32_t) (uint32_t) key_min <= (int32_t) (uint32_t) key_max &&
+			 (int32_t) ((uint64_t) key_min >> 32) <= (int32_t) ((uint64_t) key_max >> 32) &&
+			 ((uint64_t) ((int64_t) (int32_t) (uint32_t) key_max - (int32_t) (uint32_t) key_min) + 1) *
+				 ((uint64_t) ((int64_t) (int32_t) ((uint64_t) key_max >> 32) - (int32_t) ((uint64_t) key_min >> 32)) + 1) < kDenseLimit)
+	{
+		/* two group columns: key_min / key_max carry the per-column bounds packed like the key
+		 * (low 32 bits: first column); composite direct index */
+		int64_t min0 = (int32_t) (uint32_t) key_min, max0 = (int32_t) (uint32_t) key_max;
+		int64_t min1 = (int32_t) ((uint64_t) key_min >> 32), max1 = (int32_t) ((uint64_t) key_max >> 32);
+		p->mode = CG_MODE_DENSE;
+		p->key_min = min0;
+		p->key_min1 = min1;
+		p->range1 = (uint64_t) (max1 - min1) + 1;
+		p->capacity = ((uint64_t) (max0 - min0) + 1) * p->range1;
+		p->entries = p->capacity + 1;
+		int s = 1; while (s < p->nwords) s <<= 1;
+		p->stride = s;
+	}
+	else if (desc->ngroup_cols == 1 && key_min <= key_max && ((uint64_t) key_max - (uint64_t) key_min) < kDenseLimit)
 	{
 		p->mode = CG_MODE_DENSE;
 		p->capacity = ((uint64_t) key_max - (uint64_t) key_min) + 1;
@@ -178,19 +197,22 @@ extern "C" int cg_partial_create(const CgScanDesc *desc, const CgColumnDesc *col
 	else
 	{
 		p->mode = CG_MODE_HASH;
-		uint64_t want = desc->expected_groups > 0 ? (uint64_t) desc->expected_groups * 2 : (1ull << 22);
+		/* load factor <= 1/4: ~7 of 8 lookups end at the home slot (the probe loop diverges a warp) */
+		uint64_t want = desc->expected_groups > 0 ? (uint64_t) desc->expected_groups * 4 : (1ull << 22);
 		uint64_t cap = 1024; while (cap < want) cap <<= 1;
 		p->capacity = cap;
 		p->entries = cap + 2;                    /* + NULL group + the key equal to the EMPTY sentinel */
-		int s = 4; while (s < p->nwords + 1) s += 4;  /* key + words, padded to 32-byte sectors */
+		int s = 1; while (s < p->nwords) s <<= 1;
 		p->stride = s;
 	}
 	size_t bytes = (size_t) p->entries * p->stride * sizeof(uint64_t);
-	if (cudaMalloc(&p->d_table, bytes) != cudaSuccess)
+	size_t key_bytes = p->mode == CG_MODE_HASH ? (((size_t) p->entries * sizeof(int64_t) + 255) & ~(size_t) 255) : 0;
+	if (cudaMalloc(&p->d_table, bytes + key_bytes) != cudaSuccess)
 	{
 		delete p;
-		return cg_set_error(CG_ENOMEM, "cudaMalloc of %zu bytes for the group table failed", bytes);
+		return cg_set_error(CG_ENOMEM, "cudaMalloc of %zu bytes for the group table failed", bytes + key_bytes);
 	}
+	if (key_bytes) p->d_hkeys = (int64_t *) ((uint8_t *) p->d_table + bytes);
 	if (cudaMalloc(&p->d_stats, 8 * sizeof(unsigned long long)) != cudaSuccess ||
 		cudaMalloc(&p->d_out_count, sizeof(unsigned long long)) != cudaSuccess)
 	{
@@ -200,7 +222,7 @@ extern "C" int cg_partial_create(const CgScanDesc *desc, const CgColumnDesc *col
 	/* optimistic packing: direct-indexed table, count + the first single-word integer sum.
 	 * |term| <= bound < 2^R and at most 2^C - 1 rows per group between drains keep
 	 * (sum << C) + count inside 64 bits when R + 2C <= 63. */
-	if (p->mode == CG_MODE_DENSE)
+	if (p->mode == CG_MODE_DENSE || p->mode == CG_MODE_HASH)
 	{
 		static int env_pack = -1;
 		if (env_pack < 0) { const char *e = getenv("CG_PACKING"); env_pack = e ? atoi(e) : 1; }
@@ -309,6 +331,20 @@ int cg_build_plan(const CgScanDesc *desc, const CgColumnDesc *columns, int natts
 		plan->qcol[q] = (uint8_t) pc;
 		plan->qop[q] = (uint8_t) desc->quals[q].op;
 		plan->qk[q] = desc->quals[q].konst;
+		{
+			int64_t k = desc->quals[q].konst, lo = INT64_MIN, hi = INT64_MAX;
+			bool neg = false;
+			switch (desc->quals[q].op)
+			{
+				case CG_OP_LT: if (k == INT64_MIN) { lo = 1; hi = 0; } else hi = k - 1; break;
+				case CG_OP_LE: hi = k; break;
+				case CG_OP_EQ: lo = hi = k; break;
+				case CG_OP_GE: lo = k; break;
+				case CG_OP_GT: if (k == INT64_MAX) { lo = 1; hi = 0; } else lo = k + 1; break;
+				default: lo = hi = k; neg = true; break;
+			}
+			plan->qlo[q] = lo; plan->qhi[q] = hi; plan->qneg[q] = neg;
+		}
 		if (columns[desc->quals[q].column].type_class == CG_TYPE_FLOAT && columns[desc->quals[q].column].attlen == 4)
 		{
 			/* float4 column values are promoted to float8; so is the constant (already float8 bits) */
@@ -339,8 +375,13 @@ int cg_build_plan(const CgScanDesc *desc, const CgColumnDesc *columns, int natts
 	plan->nwords = partial->nwords;
 	plan->stride = partial->stride;
 	plan->table = partial->d_table;
+	plan->hkeys = partial->d_hkeys;
 	plan->capacity = partial->capacity;
+	plan->hash_shift = 64;
+	for (uint64_t c = partial->capacity; c > 1; c >>= 1) plan->hash_shift--;
 	plan->key_min = partial->key_min;
+	plan->key_min1 = partial->key_min1;
+	plan->range1 = partial->range1;
 	memcpy(plan->wordop, partial->wordop, sizeof plan->wordop);
 	plan->stats = partial->d_stats;
 	plan->packed = partial->packing_enabled ? partial->d_packed : nullptr;
@@ -423,7 +464,7 @@ bool cg_build_fast_plan(const CgScanDesc *desc, const KPlan &plan, bool all8, FP
 	fast->mode = plan.mode;
 	fast->packed = nullptr;
 	fast->pack_sum = -1;
-	if (plan.packed && plan.mode == CG_MODE_DENSE)
+	if (plan.packed && plan.mode != CG_MODE_GLOBAL)
 		for (int i = 0; i < ns; i++)
 			if (fast->sword[i] == plan.pack_word && fast->slimbs[i] == 1)
 			{
@@ -452,7 +493,8 @@ bool cg_build_fast_plan(const CgScanDesc *desc, const KPlan &plan, bool all8, FP
 	}
 	fast->arena = plan.arena; fast->chunkcols = plan.chunkcols; fast->selected = plan.selected;
 	fast->nselected = plan.nselected; fast->nstaged = plan.nstaged;
-	fast->table = plan.table; fast->capacity = plan.capacity; fast->stride = plan.stride;
+	fast->table = plan.table; fast->hkeys = plan.hkeys; fast->capacity = plan.capacity; fast->stride = plan.stride;
+	fast->hash_shift = plan.hash_shift;
 	fast->key_min = plan.key_min; fast->stats = plan.stats;
 	(void) desc;
 	return true;

@@ -22,203 +22,24 @@
 
 #define CG_THREADS 256
 
-/* ------------------------------------------------------------------------------ *
- *  streaming loads: read-only path, no L1 allocation (each byte is used once)
- * ------------------------------------------------------------------------------ */
-__device__ __forceinline__ void ldg_stream16(const void *p, uint64_t &a, uint64_t &b)
-{
-	asm("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
-}
-__device__ __forceinline__ uint64_t ldg_stream8(const void *p)
-{
-	uint64_t a;
-	asm("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(a) : "l"(p));
-	return a;
-}
-__device__ __forceinline__ uint32_t ldg_stream4(const void *p)
-{
-	uint32_t a;
-	asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(a) : "l"(p));
-	return a;
-}
-__device__ __forceinline__ uint32_t ldg_stream2(const void *p)
-{
-	uint16_t a;
-	asm("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(a) : "l"(p));
-	return a;
-}
-__device__ __forceinline__ uint32_t ldg_stream1(const void *p)
-{
-	uint32_t a;
-	asm("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(a) : "l"(p));
-	return a;
-}
-
-__device__ __forceinline__ int64_t f4_to_f8_bits(uint32_t u)
-{
-	return __double_as_longlong((double) __uint_as_float(u));
-}
-
-/* widen one stored datum (fetch_att for by-value types, columnar_reader.c:1557) */
-__device__ __forceinline__ int64_t widen(uint64_t raw, int len, bool isfloat)
-{
-	switch (len)
-	{
-		case 8: return (int64_t) raw;
-		case 4: return isfloat ? f4_to_f8_bits((uint32_t) raw) : (int64_t) (int32_t) (uint32_t) raw;
-		case 2: return (int64_t) (int16_t) (uint16_t) raw;
-		default: return (int64_t) (int8_t) (uint8_t) raw;
-	}
-}
-
-__device__ __forceinline__ int64_t load_scalar(const uint8_t *p, int len, bool isfloat)
-{
-	switch (len)
-	{
-		case 8: return (int64_t) ldg_stream8(p);
-		case 4: return widen(ldg_stream4(p), 4, isfloat);
-		case 2: return widen(ldg_stream2(p), 2, isfloat);
-		default: return widen(ldg_stream1(p), 1, isfloat);
-	}
-}
-
-/* two consecutive rows (r even) of a NULL-free column */
-__device__ __forceinline__ void load_pair(const uint8_t *vals, uint32_t r, int len, bool isfloat,
-										  int64_t &v0, int64_t &v1)
-{
-	switch (len)
-	{
-		case 8:
-		{
-			uint64_t a, b;
-			ldg_stream16(vals + (uint64_t) r * 8, a, b);
-			v0 = (int64_t) a; v1 = (int64_t) b;
-			break;
-		}
-		case 4:
-		{
-			uint64_t a = ldg_stream8(vals + (uint64_t) r * 4);
-			v0 = widen(a & 0xffffffffu, 4, isfloat); v1 = widen(a >> 32, 4, isfloat);
-			break;
-		}
-		case 2:
-		{
-			uint32_t a = ldg_stream4(vals + (uint64_t) r * 2);
-			v0 = widen(a & 0xffffu, 2, false); v1 = widen(a >> 16, 2, false);
-			break;
-		}
-		default:
-		{
-			uint32_t a = ldg_stream2(vals + r);
-			v0 = widen(a & 0xffu, 1, false); v1 = widen(a >> 8, 1, false);
-			break;
-		}
-	}
-}
-
-template <int N>
-__device__ __forceinline__ int64_t pick(const int64_t (&v)[N], int idx)
-{
-	int64_t r = v[0];
-#pragma unroll
-	for (int c = 1; c < N; c++) r = (idx == c) ? v[c] : r;
-	return r;
-}
-
-/* [PG] btree comparison result of "v <op> k" (int8 / float8 operators) */
-__device__ __forceinline__ bool qual_true(int64_t v, int op, int64_t k, bool isfloat)
-{
-	if (isfloat)
-	{
-		double x = __longlong_as_double(v), y = __longlong_as_double(k);
-		/* float8 btree order: NaN equals NaN and is greater than everything */
-		bool xn = x != x, yn = y != y;
-		int c = (xn || yn) ? ((int) xn - (int) yn) : ((x > y) - (x < y));
-		switch (op)
-		{
-			case CG_OP_LT: return c < 0;
-			case CG_OP_LE: return c <= 0;
-			case CG_OP_EQ: return c == 0;
-			case CG_OP_GE: return c >= 0;
-			case CG_OP_GT: return c > 0;
-			default: return c != 0;
-		}
-	}
-	switch (op)
-	{
-		case CG_OP_LT: return v < k;
-		case CG_OP_LE: return v <= k;
-		case CG_OP_EQ: return v == k;
-		case CG_OP_GE: return v >= k;
-		case CG_OP_GT: return v > k;
-		default: return v != k;
-	}
-}
-
-__device__ __forceinline__ uint64_t mix64(uint64_t x)
-{
-	x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
-	return x;
-}
-
-/* order-preserving map of float8 bits to unsigned (for min/max words) */
-__device__ __forceinline__ uint64_t f8_ordered(int64_t bits)
-{
-	uint64_t u = (uint64_t) bits;
-	return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
-}
-
-__device__ __forceinline__ void word_apply_global(uint64_t *p, int op, uint64_t val)
-{
-	switch (op)
-	{
-		case CG_WORD_ADD: atomicAdd((unsigned long long *) p, (unsigned long long) val); break;
-		case CG_WORD_MIN: atomicMin((long long *) p, (long long) val); break;
-		case CG_WORD_MAX: atomicMax((long long *) p, (long long) val); break;
-		case CG_WORD_FADD: atomicAdd((double *) p, __longlong_as_double((long long) val)); break;
-		case CG_WORD_FMIN: atomicMin((unsigned long long *) p, (unsigned long long) val); break;
-		default: atomicMax((unsigned long long *) p, (unsigned long long) val); break;
-	}
-}
-
-__device__ __forceinline__ uint64_t word_identity(int op)
-{
-	switch (op)
-	{
-		case CG_WORD_MIN: return (uint64_t) INT64_MAX;
-		case CG_WORD_MAX: return (uint64_t) INT64_MIN;
-		case CG_WORD_FMIN: return ~0ull;
-		default: return 0ull;     /* ADD, FADD (+0.0), FMAX */
-	}
-}
-
-__device__ __forceinline__ uint64_t word_combine(int op, uint64_t a, uint64_t b)
-{
-	switch (op)
-	{
-		case CG_WORD_ADD: return a + b;
-		case CG_WORD_MIN: return (uint64_t) min((long long) a, (long long) b);
-		case CG_WORD_MAX: return (uint64_t) max((long long) a, (long long) b);
-		case CG_WORD_FADD: return (uint64_t) __double_as_longlong(__longlong_as_double((long long) a) + __longlong_as_double((long long) b));
-		case CG_WORD_FMIN: return a < b ? a : b;
-		default: return a > b ? a : b;
-	}
-}
+#include "cg_device.cuh"
 
 /*
  * Find (or claim) the table entry of a group key.  Returns the word pointer of the
  * entry (word 0 = rows in group) or NULL after raising an error flag.
  *   dense: entry = key - key_min, NULL key -> entry `capacity`
- *   hash : open addressing, linear probing, 64-bit CAS on the key word; the NULL group
- *          and the key that collides with the EMPTY sentinel live in two extra entries
+ *   hash : open addressing, linear probing over a separate key array (8 B per slot, so the
+ *          probed working set is a quarter of an array-of-structs table), 64-bit CAS to claim
+ *          a slot; the NULL group and the key equal to the EMPTY sentinel live in two extra
+ *          entries behind the addressable ones
  */
 template <int MODE>
 __device__ __forceinline__ uint64_t *find_entry(const KPlan &P, int64_t key, bool key_null)
 {
 	if (MODE == CG_MODE_DENSE)
 	{
-		uint64_t slot = key_null ? P.capacity : (uint64_t) (key - P.key_min);
-		if (slot > P.capacity || (!key_null && slot == P.capacity))
+		uint64_t slot = dense_slot_of_packed(P, key, key_null);
+		if (slot == ~0ull)
 		{
 			atomicOr(P.stats + 2, CG_ERRFLAG_KEY_RANGE);
 			return nullptr;
@@ -227,19 +48,19 @@ __device__ __forceinline__ uint64_t *find_entry(const KPlan &P, int64_t key, boo
 	}
 	else
 	{
-		if (key_null) return P.table + P.capacity * (uint64_t) P.stride + 1;
-		if (key == CG_HASH_EMPTY) return P.table + (P.capacity + 1) * (uint64_t) P.stride + 1;
+		if (key_null) return P.table + P.capacity * (uint64_t) P.stride;
+		if (key == CG_HASH_EMPTY) return P.table + (P.capacity + 1) * (uint64_t) P.stride;
 		uint64_t mask = P.capacity - 1;
-		uint64_t h = mix64((uint64_t) key) & mask;
+		uint64_t h = cg_home_slot(key, P.hash_shift);
 		for (uint32_t probes = 0; probes < 8192; probes++)
 		{
-			unsigned long long *kp = (unsigned long long *) (P.table + h * (uint64_t) P.stride);
+			unsigned long long *kp = (unsigned long long *) (P.hkeys + h);
 			long long cur = (long long) __ldcg(kp);     /* L2: keys only ever go EMPTY -> key */
-			if (cur == key) return (uint64_t *) kp + 1;
+			if (cur == key) return P.table + h * (uint64_t) P.stride;
 			if (cur == CG_HASH_EMPTY)
 			{
 				long long old = (long long) atomicCAS(kp, (unsigned long long) CG_HASH_EMPTY, (unsigned long long) key);
-				if (old == CG_HASH_EMPTY || old == key) return (uint64_t *) kp + 1;
+				if (old == CG_HASH_EMPTY || old == key) return P.table + h * (uint64_t) P.stride;
 			}
 			h = (h + 1) & mask;
 		}
@@ -269,7 +90,10 @@ __device__ __forceinline__ void process_row(const KPlan &P, const int64_t (&v)[N
 		{
 			int c = P.qcol[q];
 			bool isnull = (nullmask >> c) & 1u;
-			pass = pass && !isnull && qual_true(pick<NCC>(v, c), P.qop[q], P.qk[q], P.isfloat[c]);
+			int64_t x = pick<NCC>(v, c);
+			bool t = P.isfloat[c] ? qual_true(x, P.qop[q], P.qk[q], true)
+								  : (((x >= P.qlo[q]) && (x <= P.qhi[q])) != (bool) P.qneg[q]);
+			pass = pass && !isnull && t;
 		}
 	}
 	if (!pass)
@@ -679,6 +503,7 @@ int cg_launch_realign(const uint8_t *raw, uint8_t *arena, const RealignItem *ite
  * ------------------------------------------------------------------------------ */
 struct TableView
 {
+	int64_t *hkeys;
 	uint64_t *table;
 	uint64_t capacity;
 	uint64_t entries;
@@ -686,14 +511,18 @@ struct TableView
 	int32_t nwords;
 	int32_t mode;
 	int64_t key_min;
+	int64_t key_min1;
+	uint64_t range1;
+	int32_t ngroup;
 	uint8_t wordop[CG_KMAX_WORDS];
 };
 
 static TableView view_of(const CgPartial *p)
 {
 	TableView v;
-	v.table = p->d_table; v.capacity = p->capacity; v.entries = p->entries; v.stride = p->stride;
+	v.hkeys = p->d_hkeys; v.table = p->d_table; v.capacity = p->capacity; v.entries = p->entries; v.stride = p->stride;
 	v.nwords = p->nwords; v.mode = p->mode; v.key_min = p->key_min;
+	v.key_min1 = p->key_min1; v.range1 = p->range1; v.ngroup = p->desc.ngroup_cols;
 	for (int i = 0; i < CG_KMAX_WORDS; i++) v.wordop[i] = p->wordop[i];
 	return v;
 }
@@ -701,14 +530,11 @@ static TableView view_of(const CgPartial *p)
 __global__ void cg_table_init_kernel(const __grid_constant__ TableView T)
 {
 	uint64_t total = T.entries * (uint64_t) T.stride;
-	int keyw = (T.mode == CG_MODE_HASH) ? 1 : 0;
 	for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t) gridDim.x * blockDim.x)
 	{
 		int w = (int) (i % (uint64_t) T.stride);
-		uint64_t val = 0;
-		if (keyw && w == 0) val = (uint64_t) CG_HASH_EMPTY;
-		else if (w - keyw < T.nwords) val = word_identity(T.wordop[w - keyw]);
-		T.table[i] = val;
+		T.table[i] = w < T.nwords ? word_identity(T.wordop[w]) : 0ull;
+		if (T.mode == CG_MODE_HASH && w == 0) T.hkeys[i / (uint64_t) T.stride] = CG_HASH_EMPTY;
 	}
 }
 
@@ -731,7 +557,6 @@ int cg_launch_table_init(CgPartial *p, cudaStream_t stream)
 __global__ void cg_export_kernel(const __grid_constant__ TableView T, uint64_t out_capacity, int64_t *keys,
 								 uint8_t *nulls, uint64_t *words, unsigned long long *count)
 {
-	int keyw = (T.mode == CG_MODE_HASH) ? 1 : 0;
 	for (uint64_t e = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; e < T.entries; e += (uint64_t) gridDim.x * blockDim.x)
 	{
 		const uint64_t *ent = T.table + e * (uint64_t) T.stride;
@@ -740,14 +565,20 @@ __global__ void cg_export_kernel(const __grid_constant__ TableView T, uint64_t o
 		bool key_null = false;
 		if (T.mode == CG_MODE_HASH)
 		{
-			if (e < T.capacity) { key = (int64_t) ent[0]; occupied = key != CG_HASH_EMPTY; }
-			else { occupied = ent[1] > 0; key_null = (e == T.capacity); key = key_null ? 0 : CG_HASH_EMPTY; }
+			if (e < T.capacity) { key = T.hkeys[e]; occupied = key != CG_HASH_EMPTY; }
+			else { occupied = ent[0] > 0; key_null = (e == T.capacity); key = key_null ? 0 : CG_HASH_EMPTY; }
 		}
 		else if (T.mode == CG_MODE_DENSE)
 		{
 			occupied = ent[0] > 0;
 			key_null = (e == T.capacity);
-			key = key_null ? 0 : T.key_min + (int64_t) e;
+			if (key_null) key = 0;
+			else if (T.ngroup == 2)
+			{
+				int64_t k0 = T.key_min + (int64_t) (e / T.range1), k1 = T.key_min1 + (int64_t) (e % T.range1);
+				key = (int64_t) ((uint64_t) (uint32_t) k0 | ((uint64_t) (uint32_t) k1 << 32));
+			}
+			else key = T.key_min + (int64_t) e;
 		}
 		else
 			occupied = true;    /* plain aggregate: exactly one result row, even over no input */
@@ -757,7 +588,7 @@ __global__ void cg_export_kernel(const __grid_constant__ TableView T, uint64_t o
 		if (keys) keys[pos] = key;
 		if (nulls) nulls[pos] = key_null ? 1 : 0;
 		if (words)
-			for (int w = 0; w < T.nwords; w++) words[pos * (uint64_t) T.nwords + w] = ent[keyw + w];
+			for (int w = 0; w < T.nwords; w++) words[pos * (uint64_t) T.nwords + w] = ent[w];
 	}
 }
 
@@ -805,8 +636,11 @@ int cg_launch_merge(CgPartial *p, const int64_t *d_keys, const uint8_t *d_nulls,
 	if (nrows <= 0) return CG_OK;
 	KPlan plan;
 	memset(&plan, 0, sizeof plan);
-	plan.mode = p->mode; plan.nwords = p->nwords; plan.stride = p->stride; plan.table = p->d_table;
+	plan.mode = p->mode; plan.nwords = p->nwords; plan.stride = p->stride; plan.table = p->d_table; plan.hkeys = p->d_hkeys;
 	plan.capacity = p->capacity; plan.key_min = p->key_min; plan.stats = p->d_stats;
+	plan.key_min1 = p->key_min1; plan.range1 = p->range1; plan.ngroup = p->desc.ngroup_cols;
+	plan.hash_shift = 64;
+	for (uint64_t c = p->capacity; c > 1; c >>= 1) plan.hash_shift--;
 	for (int i = 0; i < CG_KMAX_WORDS; i++) plan.wordop[i] = p->wordop[i];
 	unsigned blocks = (unsigned) ((nrows + 255) / 256);
 	if (blocks > 148 * 8) blocks = 148 * 8;

@@ -17,7 +17,7 @@
  *         are intersected into one [lo, hi] on the host)
  *   MODE  plain aggregate / direct-indexed table / hash table
  *   NS    sum(column) aggregates
- *   PACK  direct-indexed only: count(*) and sum number 0 share one 64-bit word
+ *   PACK  grouped modes: count(*) and sum number 0 share one 64-bit word
  *         (optimistic packing, see include/citus_gpu.h cg_partial_set_packing)
  * Column roles map to fixed register positions: quals first, then the key, then the sums.
  */
@@ -45,10 +45,10 @@ __device__ __forceinline__ uint64_t policy_evict_first()
 	return pol;
 }
 
-__device__ __forceinline__ uint64_t mix64f(uint64_t x)
+/* must match cg_home_slot() in cg_device.cuh */
+__device__ __forceinline__ uint64_t home_slot(int64_t key, int hash_shift)
 {
-	x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
-	return x;
+	return ((uint64_t) key * 0x9E3779B97F4A7C15ull) >> hash_shift;
 }
 
 __device__ __noinline__ void raise_flag(unsigned long long *stats, unsigned long long flag)
@@ -56,9 +56,30 @@ __device__ __noinline__ void raise_flag(unsigned long long *stats, unsigned long
 	atomicOr(stats + 2, flag);
 }
 
-/* word pointer of the group's entry, or NULL after raising an error flag */
+/* slot of the group's entry, or ~0 after raising an error flag */
+#define CGF_NOSLOT (~0ull)
+
+__device__ __noinline__ uint64_t hash_slot_slow(const FPlan &P, int64_t key, uint64_t h)
+{
+	if (key == CG_HASH_EMPTY) return P.capacity + 1;
+	const uint64_t mask = P.capacity - 1;
+	for (uint32_t probes = 0; probes < 8192; probes++)
+	{
+		unsigned long long *kp = (unsigned long long *) (P.hkeys + h);
+		long long cur = (long long) __ldcg(kp);
+		if (cur == key) return h;
+		if (cur == CG_HASH_EMPTY)
+		{
+			long long old = (long long) atomicCAS(kp, (unsigned long long) CG_HASH_EMPTY, (unsigned long long) key);
+			if (old == CG_HASH_EMPTY || old == key) return h;
+		}
+		h = (h + 1) & mask;
+	}
+	raise_flag(P.stats, CG_ERRFLAG_TABLE_FULL);
+	return CGF_NOSLOT;
+}
 template <int MODE>
-__device__ __forceinline__ uint64_t *fast_entry(const FPlan &P, int64_t key)
+__device__ __forceinline__ uint64_t fast_slot(const FPlan &P, int64_t key)
 {
 	if (MODE == CG_MODE_DENSE)
 	{
@@ -66,30 +87,27 @@ __device__ __forceinline__ uint64_t *fast_entry(const FPlan &P, int64_t key)
 		if (slot >= P.capacity)
 		{
 			raise_flag(P.stats, CG_ERRFLAG_KEY_RANGE);
-			return nullptr;
+			return CGF_NOSLOT;
 		}
-		return P.table + slot * (uint64_t) P.stride;
+		return slot;
 	}
 	else
 	{
-		if (key == CG_HASH_EMPTY) return P.table + (P.capacity + 1) * (uint64_t) P.stride + 1;
-		uint64_t mask = P.capacity - 1;
-		uint64_t h = mix64f((uint64_t) key) & mask;
-		for (uint32_t probes = 0; probes < 8192; probes++)
-		{
-			unsigned long long *kp = (unsigned long long *) (P.table + h * (uint64_t) P.stride);
-			long long cur = (long long) __ldcg(kp);        /* keys only ever go EMPTY -> key */
-			if (cur == key) return (uint64_t *) kp + 1;
-			if (cur == CG_HASH_EMPTY)
-			{
-				long long old = (long long) atomicCAS(kp, (unsigned long long) CG_HASH_EMPTY, (unsigned long long) key);
-				if (old == CG_HASH_EMPTY || old == key) return (uint64_t *) kp + 1;
-			}
-			h = (h + 1) & mask;
-		}
-		raise_flag(P.stats, CG_ERRFLAG_TABLE_FULL);
-		return nullptr;
+		/* the home-slot probe is straight-line code (all lanes of the warp issue it together);
+		 * only a miss enters the probing / claiming loop */
+		uint64_t h = home_slot(key, P.hash_shift);
+		long long cur = (long long) __ldcg((unsigned long long *) (P.hkeys + h));   /* keys only ever go EMPTY -> key */
+		if (cur == key && key != CG_HASH_EMPTY) return h;
+		return hash_slot_slow(P, key, h);
 	}
+}
+
+/* word pointer of the group's entry, or NULL after raising an error flag */
+template <int MODE>
+__device__ __forceinline__ uint64_t *fast_entry(const FPlan &P, int64_t key)
+{
+	uint64_t slot = fast_slot<MODE>(P, key);
+	return slot == CGF_NOSLOT ? nullptr : P.table + slot * (uint64_t) P.stride;
 }
 
 template <int NQ>
@@ -199,12 +217,8 @@ __device__ __forceinline__ void fast_row(const FPlan &P, const int64_t *v, FastA
 	if (PACK)
 	{
 		/* one reduction for count(*) and sum 0: word += (x << C) + 1 (mod 2^64) */
-		uint64_t slot = (uint64_t) v[KEYPOS] - (uint64_t) P.key_min;
-		if (slot >= P.capacity)
-		{
-			raise_flag(P.stats, CG_ERRFLAG_KEY_RANGE);
-			return;
-		}
+		uint64_t slot = fast_slot<MODE>(P, v[KEYPOS]);
+		if (slot == CGF_NOSLOT) return;
 		int64_t x = v[SUMPOS];
 		if (x > P.sbound[0] || x < -P.sbound[0]) raise_flag(P.stats, CG_ERRFLAG_SUM_BOUND);
 		red_add_u64(P.packed + slot, ((uint64_t) x << P.pack_shift) + 1ull);
@@ -248,7 +262,7 @@ cg_scan_fast_kernel(const __grid_constant__ FPlan P)
 	const uint32_t tid = threadIdx.x;
 	const uint64_t pol_stream = policy_evict_first();
 	/* hash tables with single-word sums: lane-paired updates (decided per launch, uniform) */
-	const bool paired = (MODE == CG_MODE_HASH) && NS > 0 && (P.flags & CG_FAST_PAIRED);
+	const bool paired = (MODE == CG_MODE_HASH) && !PACK && NS > 0 && (P.flags & CG_FAST_PAIRED);
 
 	for (uint32_t ci = blockIdx.x; ci < P.nselected; ci += gridDim.x)
 	{
@@ -413,13 +427,14 @@ static int launch_fast_variant(CgContext *ctx, const FPlan &plan, cudaStream_t s
 template <int NQ, int MODE>
 static int launch_fast_ns(CgContext *ctx, const FPlan &plan, cudaStream_t stream)
 {
-	if (MODE == CG_MODE_DENSE && plan.packed)
+	if (MODE != CG_MODE_GLOBAL && plan.packed)
 	{
+		constexpr int PM = MODE == CG_MODE_GLOBAL ? CG_MODE_DENSE : MODE;
 		switch (plan.nsums)
 		{
-			case 1: return launch_fast_variant<NQ, CG_MODE_DENSE, 1, true>(ctx, plan, stream);
-			case 2: return launch_fast_variant<NQ, CG_MODE_DENSE, 2, true>(ctx, plan, stream);
-			default: return launch_fast_variant<NQ, CG_MODE_DENSE, 3, true>(ctx, plan, stream);
+			case 1: return launch_fast_variant<NQ, PM, 1, true>(ctx, plan, stream);
+			case 2: return launch_fast_variant<NQ, PM, 2, true>(ctx, plan, stream);
+			default: return launch_fast_variant<NQ, PM, 3, true>(ctx, plan, stream);
 		}
 	}
 	switch (plan.nsums)
