@@ -116,6 +116,7 @@ SYMBOLS = [
     ("cg_partial_dense_words", C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     ("cg_partition_index", C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P]),
     ("cg_partition_scatter", C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int32, _P, _P]),
+    ("cg_partition_scatter_ordered", C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, C.c_int32, _P, _P]),
     ("cg_relation_bounds", C.c_int, [C.POINTER(CgRelation), C.POINTER(CgScanDesc), C.POINTER(C.c_int64),
                                      C.POINTER(C.c_int64), _P, C.POINTER(C.c_int64)]),
     ("cg_selected_chunk_mask", C.c_int, [C.POINTER(CgRelation), C.c_int32, C.POINTER(CgScanDesc), _P,

@@ -373,9 +373,15 @@ def worker_partition_query_result(d_keys_ptr, d_nulls_ptr, n, key_len, method, m
                                    mins.ctypes.data, maxs.ctypes.data, len(mins), d_index_ptr, d_counts_ptr))
 
 
-def partition_scatter(d_index_ptr, n, P, d_col_ptrs, d_out_ptrs):
+def partition_scatter(d_index_ptr, n, P, d_col_ptrs, d_out_ptrs, order=None):
+    """stable scatter into partition-contiguous order; order[p] = output position of partition p"""
     cols = (C.c_void_p * len(d_col_ptrs))(*d_col_ptrs)
     outs = (C.c_void_p * len(d_out_ptrs))(*d_out_ptrs)
     offs = np.zeros(P + 1, np.int64)
-    check(lib().cg_partition_scatter(d_index_ptr, n, P, cols, len(d_col_ptrs), outs, offs.ctypes.data))
+    if order is None:
+        check(lib().cg_partition_scatter(d_index_ptr, n, P, cols, len(d_col_ptrs), outs, offs.ctypes.data))
+    else:
+        order = np.ascontiguousarray(order, np.int32)
+        check(lib().cg_partition_scatter_ordered(d_index_ptr, n, P, order.ctypes.data, cols, len(d_col_ptrs), outs,
+                                                 offs.ctypes.data))
     return offs

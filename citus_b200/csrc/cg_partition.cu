@@ -13,7 +13,7 @@
  * Here: one pass computes the partition index of every row and a histogram (per-block
  * counts in shared memory, one global atomic per block and partition), a second pass
  * scatters the payload columns into partition-contiguous order -- stable inside a
- * partition, like the reference's append order -- using per-block offsets.
+ * partition, like the reference's append order -- using per-block and per-warp offsets.
  *
  * [PG] hash_bytes_uint32 / hashint4 / hashint8: src/common/hashfn.c,
  * src/backend/access/hash/hashfunc.c (Jenkins lookup3 final mix); pinned by the
@@ -140,53 +140,73 @@ struct ScatterParams
 	int64_t n;
 	int32_t P;
 	int32_t ncols;
-	const unsigned long long *block_offsets;   /* [nblocks][P] */
+	const unsigned long long *block_offsets;   /* [nblocks][P]: start of the block inside its partition */
+	const unsigned long long *part_base;       /* [P]: start of the partition in the output */
+	const int32_t *order;                      /* [P] output position of partition p, or NULL (identity) */
 	const int64_t *cols[8];
 	int64_t *out[8];
 };
 
-/* stable scatter: inside a block, rows of the same partition keep their order (rank by a
- * warp-ordered count over the block's rows) */
+/*
+ * Stable scatter.  A block owns 4096 consecutive rows, each of its 8 warps a contiguous
+ * segment of 512.  Pass A: every warp histograms its segment into its own row of shared
+ * memory (match.any groups the lanes of a step by partition; the group's first lane adds the
+ * group size -- the row is warp-private, no atomics).  One barrier, then the per-(warp,
+ * partition) start offsets = block offset + counts of the warps before.  Pass B: every warp
+ * walks its segment again in input order; a row's destination is its partition's running
+ * offset + its rank among the lanes of the same partition in this step.  Output order inside
+ * a partition therefore equals input order, like the reference's append-to-file loop
+ * (executor/partitioned_intermediate_results.c:493-553), with two block barriers in total.
+ */
 __global__ void __launch_bounds__(CGP_THREADS)
 cg_partition_scatter_kernel(const __grid_constant__ ScatterParams A)
 {
-	extern __shared__ unsigned int s_run[];    /* [P] running count inside this block */
-	for (int p = threadIdx.x; p < A.P; p += CGP_THREADS) s_run[p] = 0;
-	__syncthreads();
-	int64_t base = (int64_t) blockIdx.x * CGP_ROWS_PER_BLOCK;
+	extern __shared__ unsigned long long s_off[];     /* [warps][P] running destination offsets */
+	constexpr int WARPS = CGP_THREADS / 32;
+	constexpr int SEG = CGP_ROWS_PER_BLOCK / WARPS;
 	const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	/* process the block's rows in order, 256 at a time; inside a step warps are serialised
-	 * through shared memory counters so that the output order equals the input order */
-	for (int step = 0; step < CGP_ROWS_PER_BLOCK; step += CGP_THREADS)
+	unsigned long long *mine = s_off + warp * A.P;
+	for (int p = lane; p < A.P; p += 32) mine[p] = 0;
+	__syncwarp();
+	const int64_t seg0 = (int64_t) blockIdx.x * CGP_ROWS_PER_BLOCK + (int64_t) warp * SEG;
+	/* pass A: segment histogram */
+	for (int step = 0; step < SEG; step += 32)
 	{
-		int64_t r = base + step + threadIdx.x;
-		bool valid = r < A.n;
-		int idx = valid ? A.index[r] : -1;
-		/* rank among the lanes of my warp with the same partition and a lower lane id */
+		int64_t r = seg0 + step + lane;
+		int idx = r < A.n ? A.index[r] : -1;
+		if (idx >= 0 && A.order) idx = A.order[idx];
 		unsigned peers = __match_any_sync(0xffffffffu, idx);
-		unsigned rank_in_warp = __popc(peers & ((1u << lane) - 1u));
-		unsigned leader = __ffs(peers) - 1;
-		unsigned warp_count = __popc(peers);
-		for (unsigned w = 0; w < CGP_THREADS / 32; w++)
+		if (idx >= 0 && lane == (unsigned) (__ffs(peers) - 1)) mine[idx] += __popc(peers);
+		__syncwarp();
+	}
+	__syncthreads();
+	/* counts -> start offsets: thread (p) walks the warps in order */
+	for (int p = threadIdx.x; p < A.P; p += CGP_THREADS)
+	{
+		unsigned long long run = A.part_base[p] + A.block_offsets[(uint64_t) blockIdx.x * A.P + p];
+		for (int w = 0; w < WARPS; w++)
 		{
-			unsigned mybase = 0;
-			if (w == warp && valid && lane == leader)
-			{
-				mybase = s_run[idx];
-				s_run[idx] = mybase + warp_count;
-			}
-			__syncthreads();
-			if (w == warp)
-			{
-				mybase = __shfl_sync(0xffffffffu, mybase, leader);
-				if (valid)
-				{
-					unsigned long long dst = A.block_offsets[(uint64_t) blockIdx.x * A.P + idx] + mybase + rank_in_warp;
-					for (int c = 0; c < A.ncols; c++) A.out[c][dst] = A.cols[c][r];
-				}
-			}
+			unsigned long long c = s_off[w * A.P + p];
+			s_off[w * A.P + p] = run;
+			run += c;
 		}
-		if (base + step + CGP_THREADS >= A.n) break;
+	}
+	__syncthreads();
+	/* pass B: scatter in input order */
+	for (int step = 0; step < SEG; step += 32)
+	{
+		int64_t r = seg0 + step + lane;
+		int idx = r < A.n ? A.index[r] : -1;
+		if (idx >= 0 && A.order) idx = A.order[idx];
+		unsigned peers = __match_any_sync(0xffffffffu, idx);
+		if (idx >= 0)
+		{
+			unsigned long long dst = mine[idx] + __popc(peers & ((1u << lane) - 1u));
+			for (int c = 0; c < A.ncols; c++) A.out[c][dst] = A.cols[c][r];
+		}
+		__syncwarp();
+		if (idx >= 0 && lane == (unsigned) (__ffs(peers) - 1)) mine[idx] += __popc(peers);
+		__syncwarp();
 	}
 }
 
@@ -233,7 +253,48 @@ extern "C" int cg_partition_index(const int64_t *d_keys, const uint8_t *d_nulls,
 	return CG_OK;
 }
 
-__global__ void cg_block_count_kernel(const int32_t *index, int64_t n, int P, unsigned long long *block_counts)
+/* per-partition exclusive scan of the block counts (one CTA per partition): every thread sums a
+ * contiguous run of blocks, the run sums are scanned in shared memory, then the run is rewritten as
+ * offsets; the partition total goes to totals[p] */
+__global__ void __launch_bounds__(1024)
+cg_partition_scan2_kernel(unsigned long long *block_counts, unsigned long long *totals, int64_t nblocks, int P)
+{
+	__shared__ unsigned long long s_sum[1024];
+	const int p = blockIdx.x;
+	const int64_t per = (nblocks + 1023) / 1024;
+	const int64_t b0 = (int64_t) threadIdx.x * per, b1 = b0 + per < nblocks ? b0 + per : nblocks;
+	unsigned long long local = 0;
+	for (int64_t b = b0; b < b1; b++) local += block_counts[b * P + p];
+	s_sum[threadIdx.x] = local;
+	__syncthreads();
+	for (int off = 1; off < 1024; off <<= 1)
+	{
+		unsigned long long v = threadIdx.x >= (unsigned) off ? s_sum[threadIdx.x - off] : 0;
+		__syncthreads();
+		s_sum[threadIdx.x] += v;
+		__syncthreads();
+	}
+	unsigned long long run = s_sum[threadIdx.x] - local;
+	for (int64_t b = b0; b < b1; b++)
+	{
+		unsigned long long c = block_counts[b * P + p];
+		block_counts[b * P + p] = run;
+		run += c;
+	}
+	if (threadIdx.x == 1023) totals[p] = s_sum[1023];
+}
+
+__global__ void cg_partition_base_kernel(const unsigned long long *totals, unsigned long long *base, int P)
+{
+	if (threadIdx.x == 0 && blockIdx.x == 0)
+	{
+		unsigned long long run = 0;
+		for (int p = 0; p < P; p++) { base[p] = run; run += totals[p]; }
+		base[P] = run;
+	}
+}
+
+__global__ void cg_block_count_kernel(const int32_t *index, const int32_t *order, int64_t n, int P, unsigned long long *block_counts)
 {
 	extern __shared__ unsigned int s_count[];
 	for (int p = threadIdx.x; p < P; p += CGP_THREADS) s_count[p] = 0;
@@ -243,55 +304,78 @@ __global__ void cg_block_count_kernel(const int32_t *index, int64_t n, int P, un
 	{
 		int64_t r = base + i;
 		if (r >= n) break;
-		atomicAdd(&s_count[index[r]], 1u);
+		int idx = index[r];
+		if (order) idx = order[idx];
+		atomicAdd(&s_count[idx], 1u);
 	}
 	__syncthreads();
 	for (int p = threadIdx.x; p < P; p += CGP_THREADS) block_counts[(uint64_t) blockIdx.x * P + p] = s_count[p];
 }
 
-extern "C" int cg_partition_scatter(const int32_t *d_index, int64_t n, int32_t P, const int64_t *const *d_cols,
-									int32_t ncols, int64_t *const *d_out, int64_t *h_offsets)
+extern "C" int cg_partition_scatter_ordered(const int32_t *d_index, int64_t n, int32_t P, const int32_t *h_order,
+											const int64_t *const *d_cols, int32_t ncols, int64_t *const *d_out,
+											int64_t *h_offsets)
 {
 	CgContext *ctx = cg_ctx();
 	if (!ctx) return CG_EINVAL;
 	if (P <= 0 || P > CGP_MAX_P) return cg_set_error(CG_EINVAL, "bad partition count %d", P);
 	if (ncols < 0 || ncols > 8) return cg_set_error(CG_EUNSUPPORTED, "at most 8 payload columns per call");
 	if (n < 0) return cg_set_error(CG_EINVAL, "negative row count");
-	int64_t nblocks = (n + CGP_ROWS_PER_BLOCK - 1) / CGP_ROWS_PER_BLOCK;
-	unsigned long long *d_block = nullptr, *d_base = nullptr;
-	CG_CUDA(cudaMallocAsync((void **) &d_block, sizeof(unsigned long long) * (size_t) std::max<int64_t>(nblocks, 1) * P, ctx->compute));
-	CG_CUDA(cudaMallocAsync((void **) &d_base, sizeof(unsigned long long) * P, ctx->compute));
-	std::vector<unsigned long long> totals(P, 0), base(P, 0);
-	if (n > 0)
+	if (h_order)
 	{
-		cg_block_count_kernel<<<(unsigned) nblocks, CGP_THREADS, P * sizeof(unsigned int), ctx->compute>>>(d_index, n, P, d_block);
-		CG_CUDA(cudaGetLastError());
-		/* totals per partition: run the scan with zero bases first, reading the last block's end */
-		CG_CUDA(cudaMemsetAsync(d_base, 0, sizeof(unsigned long long) * P, ctx->compute));
-		/* column sums on the host for the partition bases (P is small) */
-		std::vector<unsigned long long> bc((size_t) nblocks * P);
-		CG_CUDA(cudaMemcpyAsync(bc.data(), d_block, bc.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->compute));
-		CG_CUDA(cudaStreamSynchronize(ctx->compute));
-		for (int64_t b = 0; b < nblocks; b++)
-			for (int p = 0; p < P; p++) totals[p] += bc[(size_t) b * P + p];
+		std::vector<uint8_t> seen(P, 0);
+		for (int p = 0; p < P; p++)
+		{
+			if (h_order[p] < 0 || h_order[p] >= P || seen[h_order[p]]) return cg_set_error(CG_EINVAL, "order is not a permutation");
+			seen[h_order[p]] = 1;
+		}
 	}
-	unsigned long long run = 0;
-	for (int p = 0; p < P; p++) { base[p] = run; h_offsets[p] = (int64_t) run; run += totals[p]; }
-	h_offsets[P] = (int64_t) run;
+	int64_t nblocks = (n + CGP_ROWS_PER_BLOCK - 1) / CGP_ROWS_PER_BLOCK;
+	unsigned long long *d_block = nullptr, *d_tot = nullptr;
+	int32_t *d_order = nullptr;
+	CG_CUDA(cudaMallocAsync((void **) &d_block, sizeof(unsigned long long) * (size_t) std::max<int64_t>(nblocks, 1) * P, ctx->compute));
+	CG_CUDA(cudaMallocAsync((void **) &d_tot, sizeof(unsigned long long) * (2 * P + 1), ctx->compute));
+	unsigned long long *d_base = d_tot + P;
+	CG_CUDA(cudaMemsetAsync(d_tot, 0, sizeof(unsigned long long) * (2 * P + 1), ctx->compute));
+	if (h_order)
+	{
+		CG_CUDA(cudaMallocAsync((void **) &d_order, sizeof(int32_t) * P, ctx->compute));
+		CG_CUDA(cudaMemcpyAsync(d_order, h_order, sizeof(int32_t) * P, cudaMemcpyHostToDevice, ctx->compute));
+	}
 	if (n > 0)
 	{
-		CG_CUDA(cudaMemcpyAsync(d_base, base.data(), sizeof(unsigned long long) * P, cudaMemcpyHostToDevice, ctx->compute));
-		cg_partition_scan_kernel<<<(P + 127) / 128, 128, 0, ctx->compute>>>(d_block, d_base, nblocks, P);
+		cg_block_count_kernel<<<(unsigned) nblocks, CGP_THREADS, P * sizeof(unsigned int), ctx->compute>>>(d_index, d_order, n, P, d_block);
+		CG_CUDA(cudaGetLastError());
+		cg_partition_scan2_kernel<<<P, 1024, 0, ctx->compute>>>(d_block, d_tot, nblocks, P);
+		CG_CUDA(cudaGetLastError());
+		cg_partition_base_kernel<<<1, 32, 0, ctx->compute>>>(d_tot, d_base, P);
 		CG_CUDA(cudaGetLastError());
 		ScatterParams S;
 		memset(&S, 0, sizeof S);
-		S.index = d_index; S.n = n; S.P = P; S.ncols = ncols; S.block_offsets = d_block;
+		S.index = d_index; S.n = n; S.P = P; S.ncols = ncols; S.block_offsets = d_block; S.part_base = d_base; S.order = d_order;
 		for (int c = 0; c < ncols; c++) { S.cols[c] = d_cols[c]; S.out[c] = d_out[c]; }
-		cg_partition_scatter_kernel<<<(unsigned) nblocks, CGP_THREADS, P * sizeof(unsigned int), ctx->compute>>>(S);
+		static bool smem_configured = false;
+		if (!smem_configured)
+		{
+			CG_CUDA(cudaFuncSetAttribute(cg_partition_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+										 (int) ((CGP_THREADS / 32) * CGP_MAX_P * sizeof(unsigned long long))));
+			smem_configured = true;
+		}
+		cg_partition_scatter_kernel<<<(unsigned) nblocks, CGP_THREADS, (CGP_THREADS / 32) * P * sizeof(unsigned long long), ctx->compute>>>(S);
 		CG_CUDA(cudaGetLastError());
 	}
+	std::vector<unsigned long long> base(P + 1, 0);
+	CG_CUDA(cudaMemcpyAsync(base.data(), d_base, sizeof(unsigned long long) * (P + 1), cudaMemcpyDeviceToHost, ctx->compute));
 	CG_CUDA(cudaStreamSynchronize(ctx->compute));
+	for (int p = 0; p <= P; p++) h_offsets[p] = (int64_t) base[p];
 	CG_CUDA(cudaFreeAsync(d_block, ctx->compute));
-	CG_CUDA(cudaFreeAsync(d_base, ctx->compute));
+	CG_CUDA(cudaFreeAsync(d_tot, ctx->compute));
+	if (d_order) CG_CUDA(cudaFreeAsync(d_order, ctx->compute));
 	return CG_OK;
+}
+
+extern "C" int cg_partition_scatter(const int32_t *d_index, int64_t n, int32_t P, const int64_t *const *d_cols,
+									int32_t ncols, int64_t *const *d_out, int64_t *h_offsets)
+{
+	return cg_partition_scatter_ordered(d_index, n, P, nullptr, d_cols, ncols, d_out, h_offsets);
 }

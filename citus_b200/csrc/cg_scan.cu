@@ -83,18 +83,15 @@ __device__ __forceinline__ void process_row(const KPlan &P, const int64_t (&v)[N
 {
 	/* K3: WHERE list, three-valued: a NULL input makes the conjunct NULL and drops the row */
 	bool pass = true;
-#pragma unroll
-	for (int q = 0; q < CG_MAX_QUALS; q++)
+#pragma unroll 1
+	for (int q = 0; q < P.nquals; q++)
 	{
-		if (q < P.nquals)
-		{
-			int c = P.qcol[q];
-			bool isnull = (nullmask >> c) & 1u;
-			int64_t x = pick<NCC>(v, c);
-			bool t = P.isfloat[c] ? qual_true(x, P.qop[q], P.qk[q], true)
-								  : (((x >= P.qlo[q]) && (x <= P.qhi[q])) != (bool) P.qneg[q]);
-			pass = pass && !isnull && t;
-		}
+		int c = P.qcol[q];
+		bool isnull = (nullmask >> c) & 1u;
+		int64_t x = pick<NCC>(v, c);
+		bool t = P.isfloat[c] ? qual_true(x, P.qop[q], P.qk[q], true)
+							  : (((x >= P.qlo[q]) && (x <= P.qhi[q])) != (bool) P.qneg[q]);
+		pass = pass && !isnull && t;
 	}
 	if (!pass)
 	{
@@ -212,7 +209,7 @@ __device__ __forceinline__ uint64_t warp_reduce_word(uint64_t x, int op)
  *   ALL8 every plan column is 8 bytes wide (skips the width switch)
  */
 template <int NCC, int NAC, int MODE, bool ALL8, int U>
-__global__ void __launch_bounds__(CG_THREADS)
+__global__ void __launch_bounds__(CG_THREADS, 4)
 cg_scan_kernel(const __grid_constant__ KPlan P)
 {
 	ThreadAcc<NAC> acc;

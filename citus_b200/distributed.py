@@ -133,11 +133,11 @@ def repartition_all_to_all(keys: torch.Tensor, key_nulls, payload: list, partiti
     cols = [keys] + list(payload)
     # destination-major order: partitions owned by rank 0 first, then rank 1, ...  (p -> p mod world)
     order = [p for r in range(world) for p in range(P) if p % world == r]
-    remap = torch.empty(P, dtype=torch.int32, device=keys.device)
-    remap[torch.tensor(order, device=keys.device)] = torch.arange(P, dtype=torch.int32, device=keys.device)
-    idx2 = remap[idx.long()].contiguous()
+    position = np.empty(P, np.int32)
+    position[np.asarray(order)] = np.arange(P, dtype=np.int32)
     outs = [torch.empty_like(c) for c in cols]
-    offs = cg.partition_scatter(idx2.data_ptr(), n, P, [c.data_ptr() for c in cols], [o.data_ptr() for o in outs])
+    offs = cg.partition_scatter(idx.data_ptr(), n, P, [c.data_ptr() for c in cols], [o.data_ptr() for o in outs],
+                                order=position)
     sizes_by_part = np.diff(offs)                          # rows per (reordered) partition
     per_rank = [len([p for p in range(P) if p % world == r]) for r in range(world)]
     bounds = np.cumsum([0] + per_rank)

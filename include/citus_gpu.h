@@ -291,6 +291,12 @@ int cg_partition_index(const int64_t *d_keys, const uint8_t *d_nulls, int64_t n,
  * d_out[c][offsets[p] .. offsets[p+1]) holds partition p's rows in input order. */
 int cg_partition_scatter(const int32_t *d_index, int64_t n, int32_t P, const int64_t *const *d_cols,
 						 int32_t ncols, int64_t *const *d_out, int64_t *h_offsets /* [P+1] */);
+/* Same, with the partitions laid out in a caller-chosen order: h_order[p] = output position of
+ * partition p (a permutation; e.g. destination-rank-major for an all-to-all);
+ * h_offsets[i] .. h_offsets[i+1] then delimit the partition whose position is i. */
+int cg_partition_scatter_ordered(const int32_t *d_index, int64_t n, int32_t P, const int32_t *h_order,
+								 const int64_t *const *d_cols, int32_t ncols, int64_t *const *d_out,
+								 int64_t *h_offsets /* [P+1] */);
 
 /* exact bounds from the skip lists (min/max of every chunk that survives chunk-group
  * skipping): the packed group key range and |argument| of every aggregate (0 = unknown,
