@@ -180,6 +180,10 @@ struct KPlan
 
 	unsigned long long *stats;    /* [0] rows scanned [1] rows removed [2] error flags
 								   * [3] rows added to packed words [4] rows drained from packed words */
+	/* shared-memory kernel (cg_scan_small.cu): accumulator words that get a private cell per lane;
+	 * the NULL-input counters and the NULL-key group stay on (rare) global atomics */
+	int8_t hot_of_word[CG_KMAX_WORDS];   /* word -> cell index or -1 */
+	int32_t nhot;
 	/* optimistic packed accumulators (direct-indexed tables): packed[slot] += (term << shift) + 1 */
 	uint64_t *packed;
 	int32_t pack_shift;

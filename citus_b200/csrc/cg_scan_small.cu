@@ -125,15 +125,36 @@ __device__ __forceinline__ void eval_terms(const KPlan &P, const int64_t (&v)[NC
 
 /*
  * Accumulate one row into the lane's PRIVATE accumulators in shared memory, laid out
- * [entry][word][lane] so that the 32 lanes of a warp always touch 32 consecutive words (no
+ * [group][hot word][lane] so that the 32 lanes of a warp always touch 32 consecutive words (no
  * bank conflicts) and never each other's: plain load / combine / store, no atomics, no
  * warp collectives.  (64-bit shared-memory atomics are CAS spin loops on this part --
  * ATOMS.CAST.SPIN -- and warp-level segmented reductions cost ~100 instructions per row.)
+ * Only the words every row touches get a cell; NULL-input counters and the NULL-key group
+ * are rare and go straight to the global table.
  */
 template <int NCC>
 __device__ __forceinline__ void small_accumulate(const KPlan &P, uint64_t *mine, uint32_t slot, const RowTerms<NCC> &t)
 {
-	uint64_t *e = mine + (size_t) slot * (uint32_t) P.nwords * CGS_THREADS;
+	if (slot >= (uint32_t) P.capacity)
+	{
+		/* the NULL-key group */
+		uint64_t *ge = P.table + (uint64_t) slot * (uint64_t) P.stride;
+		atomicAdd((unsigned long long *) ge, 1ull);
+#pragma unroll
+		for (int a = 0; a < CG_MAX_AGGS; a++)
+			if (a < P.naggs)
+			{
+				const KAgg &g = P.aggs[a];
+				if (g.kind == CG_AGG_COUNT_STAR) continue;
+				if ((t.nullbits >> a) & 1u) { atomicAdd((unsigned long long *) ge + g.nullword, 1ull); continue; }
+				if (g.kind == CG_AGG_COUNT) continue;
+				word_apply_global(ge + g.word0, P.wordop[g.word0], t.w0[a]);
+				if (g.kind == CG_AGG_SUM && !g.is_float && g.nlimbs == 2)
+					atomicAdd((unsigned long long *) ge + g.word0 + 1, (unsigned long long) t.w1[a]);
+			}
+		return;
+	}
+	uint64_t *e = mine + (size_t) slot * (uint32_t) P.nhot * CGS_THREADS;
 	e[0] += 1ull;
 #pragma unroll
 	for (int a = 0; a < CG_MAX_AGGS; a++)
@@ -141,9 +162,13 @@ __device__ __forceinline__ void small_accumulate(const KPlan &P, uint64_t *mine,
 		{
 			const KAgg &g = P.aggs[a];
 			if (g.kind == CG_AGG_COUNT_STAR) continue;
-			if ((t.nullbits >> a) & 1u) { e[g.nullword * CGS_THREADS] += 1ull; continue; }
+			if ((t.nullbits >> a) & 1u)
+			{
+				atomicAdd((unsigned long long *) P.table + (uint64_t) slot * (uint64_t) P.stride + g.nullword, 1ull);
+				continue;
+			}
 			if (g.kind == CG_AGG_COUNT) continue;
-			uint64_t *w = e + g.word0 * CGS_THREADS;
+			uint64_t *w = e + P.hot_of_word[g.word0] * CGS_THREADS;
 			if (g.kind == CG_AGG_SUM && !g.is_float)
 			{
 				*w += t.w0[a];
@@ -158,10 +183,16 @@ template <int NCC, bool ALL8>
 __global__ void __launch_bounds__(CGS_THREADS)
 cg_scan_small_kernel(const __grid_constant__ KPlan P)
 {
-	extern __shared__ uint64_t s_acc[];        /* [capacity + 1][nwords][CGS_THREADS] */
+	extern __shared__ uint64_t s_acc[];        /* [capacity][nhot][CGS_THREADS] */
 	const uint32_t tid = threadIdx.x;
-	const uint32_t cells = (uint32_t) (P.capacity + 1) * (uint32_t) P.nwords;
-	for (uint32_t i = 0; i < cells; i++) s_acc[(size_t) i * CGS_THREADS + tid] = word_identity(P.wordop[i % (uint32_t) P.nwords]);
+	const uint32_t cells = (uint32_t) P.capacity * (uint32_t) P.nhot;
+	for (uint32_t i = 0; i < cells; i++)
+	{
+		/* cell -> word: the hot words are in ascending word order */
+		uint32_t hw = i % (uint32_t) P.nhot, word = 0;
+		for (uint32_t w = 0; w < (uint32_t) P.nwords; w++) if (P.hot_of_word[w] == (int) hw) word = w;
+		s_acc[(size_t) i * CGS_THREADS + tid] = word_identity(P.wordop[word]);
+	}
 	uint64_t *mine = s_acc + tid;               /* this lane's private accumulators */
 
 	uint32_t removed = 0;
@@ -245,12 +276,14 @@ cg_scan_small_kernel(const __grid_constant__ KPlan P)
 	__syncthreads();
 	for (uint32_t i = tid; i < cells; i += CGS_THREADS)
 	{
-		const int op = P.wordop[i % (uint32_t) P.nwords];
+		uint32_t hw = i % (uint32_t) P.nhot, word = 0;
+		for (uint32_t w = 0; w < (uint32_t) P.nwords; w++) if (P.hot_of_word[w] == (int) hw) word = w;
+		const int op = P.wordop[word];
 		const uint64_t *col = s_acc + (size_t) i * CGS_THREADS;
 		uint64_t x = word_identity(op);
 		for (uint32_t k = 0; k < CGS_THREADS; k++) x = word_combine(op, x, col[(k + tid) % CGS_THREADS]);
 		if (x != word_identity(op))
-			word_apply_global(P.table + (uint64_t) (i / (uint32_t) P.nwords) * (uint64_t) P.stride + (i % (uint32_t) P.nwords), op, x);
+			word_apply_global(P.table + (uint64_t) (i / (uint32_t) P.nhot) * (uint64_t) P.stride + word, op, x);
 	}
 	unsigned long long rem = warp_reduce_op(removed, CG_WORD_ADD);
 	unsigned long long scn = warp_reduce_op(scanned, CG_WORD_ADD);
@@ -264,18 +297,18 @@ cg_scan_small_kernel(const __grid_constant__ KPlan P)
 template <int NCC, bool ALL8>
 static int launch_small_variant(CgContext *ctx, const KPlan &plan, size_t smem, cudaStream_t stream)
 {
-	static size_t configured = 0;
+	static size_t configured = 0, occ_smem = ~(size_t) 0;
 	static int occ = 0;
 	if (smem > configured)
 	{
 		CG_CUDA(cudaFuncSetAttribute(cg_scan_small_kernel<NCC, ALL8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 		configured = smem;
-		occ = 0;
 	}
-	if (occ == 0)
+	if (smem != occ_smem)
 	{
-		CG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_scan_small_kernel<NCC, ALL8>, CGS_THREADS, configured));
+		CG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_scan_small_kernel<NCC, ALL8>, CGS_THREADS, smem));
 		if (occ < 1) occ = 1;
+		occ_smem = smem;
 	}
 	uint32_t grid = (uint32_t) (ctx->sm_count * occ);
 	if (grid > plan.nselected) grid = plan.nselected;
@@ -285,18 +318,37 @@ static int launch_small_variant(CgContext *ctx, const KPlan &plan, size_t smem, 
 	return CG_OK;
 }
 
-/* true when the plan's table fits the shared-memory strategy */
+/* the words that get per-lane cells: word 0 and every aggregate's value words */
+static int hot_words(const KPlan &plan, int8_t *hot)
+{
+	bool is_hot[CG_KMAX_WORDS] = {false};
+	is_hot[0] = true;
+	for (int a = 0; a < plan.naggs; a++)
+	{
+		const KAgg &g = plan.aggs[a];
+		if (g.kind == CG_AGG_COUNT_STAR || g.kind == CG_AGG_COUNT) continue;
+		is_hot[g.word0] = true;
+		if (g.kind == CG_AGG_SUM && !g.is_float && g.nlimbs == 2) is_hot[g.word0 + 1] = true;
+	}
+	int n = 0;
+	for (int w = 0; w < CG_KMAX_WORDS; w++) hot[w] = (w < plan.nwords && is_hot[w]) ? (int8_t) n++ : (int8_t) -1;
+	return n;
+}
+
+/* true when private accumulators for every lane fit the CTA's shared memory */
 bool cg_small_eligible(const KPlan &plan)
 {
 	if (plan.mode != CG_MODE_DENSE) return false;
-	/* private accumulators for every lane must fit the CTA's shared memory */
-	size_t bytes = (size_t) (plan.capacity + 1) * plan.nwords * sizeof(uint64_t) * CGS_THREADS;
+	int8_t hot[CG_KMAX_WORDS];
+	size_t bytes = (size_t) plan.capacity * hot_words(plan, hot) * sizeof(uint64_t) * CGS_THREADS;
 	return bytes <= 200 * 1024;
 }
 
-int cg_launch_scan_small(CgContext *ctx, const KPlan &plan, bool all8, cudaStream_t stream)
+int cg_launch_scan_small(CgContext *ctx, const KPlan &plan_in, bool all8, cudaStream_t stream)
 {
-	size_t smem = (size_t) (plan.capacity + 1) * plan.nwords * sizeof(uint64_t) * CGS_THREADS;
+	KPlan plan = plan_in;
+	plan.nhot = hot_words(plan, plan.hot_of_word);
+	size_t smem = (size_t) plan.capacity * plan.nhot * sizeof(uint64_t) * CGS_THREADS;
 	if (plan.ncols <= 4)
 		return all8 ? launch_small_variant<4, true>(ctx, plan, smem, stream) : launch_small_variant<4, false>(ctx, plan, smem, stream);
 	return all8 ? launch_small_variant<CG_KMAX_COLS, true>(ctx, plan, smem, stream)
