@@ -318,6 +318,7 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     sampler.start()
     capi.check(capi.lib().cg_profile_begin())
+    launches_before = capi.lib().cg_kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     ngroups = 0
@@ -326,6 +327,7 @@ def run_ours(args, rank, world, local_rank):
     ev1.record()
     barrier()
     clocks = sampler.result()
+    all_launches = capi.lib().cg_kernel_launches() - launches_before
     launches, ktotal, kmax_ms = C.c_int32(), C.c_double(), C.c_double()
     capi.check(capi.lib().cg_profile_collect(C.byref(launches), C.byref(ktotal), C.byref(kmax_ms)))
     ms = ev0.elapsed_time(ev1) / args.steps
@@ -419,7 +421,8 @@ def run_ours(args, rank, world, local_rank):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64",
             "data": "synthetic", "config": workload_config(args, f"shard s -> GPU s mod {world}"),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches.value), "roofline": roofline,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(all_launches), "scan_kernel_launches": int(launches.value),
+            "roofline": roofline,
             "cpu_baseline": cpu, "groups": int(ngroups), "resident_bytes_rank0": int(resident),
             "hbm_gbs_whole_step": total_rows * 24.375 / (ms / 1e3) / 1e9 / world,
         }

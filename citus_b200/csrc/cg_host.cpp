@@ -11,6 +11,10 @@
 
 #include "cg_internal.h"
 
+unsigned long long g_cg_launches = 0;
+
+extern "C" uint64_t cg_kernel_launches(void) { return g_cg_launches; }
+
 static CgContext g_ctx;
 static bool g_ctx_ready = false;
 

@@ -19,6 +19,7 @@
 #define CG_FIRST_LOGICAL_OFFSET (2ull * CG_BYTES_PER_PAGE)
 
 int cg_set_error(int code, const char *fmt, ...);
+extern unsigned long long g_cg_launches;   /* kernels launched by this library (every <<<>>> site) */
 
 #define CG_CUDA(call)                                                                        \
 	do {                                                                                     \

@@ -243,7 +243,7 @@ extern "C" int cg_partition_index(const int64_t *d_keys, const uint8_t *d_nulls,
 		A.counts = (unsigned long long *) d_counts; A.block_counts = nullptr; A.errors = d_err;
 		int64_t nblocks = (n + CGP_ROWS_PER_BLOCK - 1) / CGP_ROWS_PER_BLOCK;
 		cg_partition_index_kernel<<<(unsigned) nblocks, CGP_THREADS, 3 * P * sizeof(int32_t), ctx->compute>>>(A);
-		CG_CUDA(cudaGetLastError());
+		CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	}
 	unsigned long long err = 0;
 	CG_CUDA(cudaMemcpyAsync(&err, d_err, sizeof err, cudaMemcpyDeviceToHost, ctx->compute));
@@ -345,11 +345,11 @@ extern "C" int cg_partition_scatter_ordered(const int32_t *d_index, int64_t n, i
 	if (n > 0)
 	{
 		cg_block_count_kernel<<<(unsigned) nblocks, CGP_THREADS, P * sizeof(unsigned int), ctx->compute>>>(d_index, d_order, n, P, d_block);
-		CG_CUDA(cudaGetLastError());
+		CG_CUDA(cudaGetLastError()); g_cg_launches++;
 		cg_partition_scan2_kernel<<<P, 1024, 0, ctx->compute>>>(d_block, d_tot, nblocks, P);
-		CG_CUDA(cudaGetLastError());
+		CG_CUDA(cudaGetLastError()); g_cg_launches++;
 		cg_partition_base_kernel<<<1, 32, 0, ctx->compute>>>(d_tot, d_base, P);
-		CG_CUDA(cudaGetLastError());
+		CG_CUDA(cudaGetLastError()); g_cg_launches++;
 		ScatterParams S;
 		memset(&S, 0, sizeof S);
 		S.index = d_index; S.n = n; S.P = P; S.ncols = ncols; S.block_offsets = d_block; S.part_base = d_base; S.order = d_order;
@@ -362,7 +362,7 @@ extern "C" int cg_partition_scatter_ordered(const int32_t *d_index, int64_t n, i
 			smem_configured = true;
 		}
 		cg_partition_scatter_kernel<<<(unsigned) nblocks, CGP_THREADS, (CGP_THREADS / 32) * P * sizeof(unsigned long long), ctx->compute>>>(S);
-		CG_CUDA(cudaGetLastError());
+		CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	}
 	std::vector<unsigned long long> base(P + 1, 0);
 	CG_CUDA(cudaMemcpyAsync(base.data(), d_base, sizeof(unsigned long long) * (P + 1), cudaMemcpyDeviceToHost, ctx->compute));

@@ -366,7 +366,7 @@ static int launch_variant(CgContext *ctx, const KPlan &plan, cudaStream_t stream
 	if (grid > plan.nselected) grid = plan.nselected;
 	if (grid == 0) return CG_OK;
 	cg_scan_kernel<NCC, NAC, MODE, ALL8, U><<<grid, CG_THREADS, 0, stream>>>(plan);
-	CG_CUDA(cudaGetLastError());
+	CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	return CG_OK;
 }
 
@@ -441,7 +441,7 @@ int cg_launch_rank(CgContext *ctx, const uint8_t *arena, const DevChunkCol *chun
 	if (count == 0) return CG_OK;
 	uint64_t blocks = (count + 7) / 8;
 	cg_rank_kernel<<<(unsigned) blocks, 256, 0, stream>>>(arena, chunkcols, first, count);
-	CG_CUDA(cudaGetLastError());
+	CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	return CG_OK;
 }
 
@@ -491,7 +491,7 @@ int cg_launch_realign(const uint8_t *raw, uint8_t *arena, const RealignItem *ite
 {
 	if (nitems == 0) return CG_OK;
 	cg_realign_kernel<<<(unsigned) nitems, 128, 0, stream>>>(raw, arena, items);
-	CG_CUDA(cudaGetLastError());
+	CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	return CG_OK;
 }
 
@@ -543,7 +543,7 @@ int cg_launch_table_init(CgPartial *p, cudaStream_t stream)
 	if (blocks > 148 * 16) blocks = 148 * 16;
 	if (blocks == 0) blocks = 1;
 	cg_table_init_kernel<<<blocks, 256, 0, stream>>>(v);
-	CG_CUDA(cudaGetLastError());
+	CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	CG_CUDA(cudaMemsetAsync(p->d_stats, 0, 8 * sizeof(unsigned long long), stream));
 	if (p->d_packed) CG_CUDA(cudaMemsetAsync(p->d_packed, 0, (size_t) p->entries * sizeof(uint64_t), stream));
 	p->packed_dirty = false;
@@ -598,7 +598,7 @@ int cg_launch_export(CgPartial *p, uint64_t out_capacity, int64_t *d_keys, uint8
 	if (blocks > 148 * 16) blocks = 148 * 16;
 	if (blocks == 0) blocks = 1;
 	cg_export_kernel<<<blocks, 256, 0, stream>>>(v, out_capacity, d_keys, d_nulls, d_words, d_count);
-	CG_CUDA(cudaGetLastError());
+	CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	return CG_OK;
 }
 
@@ -642,6 +642,6 @@ int cg_launch_merge(CgPartial *p, const int64_t *d_keys, const uint8_t *d_nulls,
 	unsigned blocks = (unsigned) ((nrows + 255) / 256);
 	if (blocks > 148 * 8) blocks = 148 * 8;
 	cg_merge_kernel<<<blocks, 256, 0, stream>>>(plan, d_keys, d_nulls, d_words, nrows);
-	CG_CUDA(cudaGetLastError());
+	CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	return CG_OK;
 }

@@ -399,7 +399,7 @@ int cg_launch_drain(CgPartial *p, cudaStream_t stream)
 	unsigned blocks = (unsigned) ((p->entries + 255) / 256);
 	if (blocks > 148 * 8) blocks = 148 * 8;
 	cg_drain_kernel<<<blocks, 256, 0, stream>>>(p->d_packed, p->d_table, p->entries, p->stride, p->pack_word, p->pack_shift, p->d_stats);
-	CG_CUDA(cudaGetLastError());
+	CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	p->packed_dirty = false;
 	p->launches_since_drain = 0;
 	return CG_OK;
@@ -420,7 +420,7 @@ static int launch_fast_variant(CgContext *ctx, const FPlan &plan, cudaStream_t s
 	if (grid > plan.nselected) grid = plan.nselected;
 	if (grid == 0) return CG_OK;
 	cg_scan_fast_kernel<NQ, MODE, NS, PACK, U><<<grid, CGF_THREADS, 0, stream>>>(plan);
-	CG_CUDA(cudaGetLastError());
+	CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	return CG_OK;
 }
 

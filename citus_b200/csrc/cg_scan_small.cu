@@ -314,7 +314,7 @@ static int launch_small_variant(CgContext *ctx, const KPlan &plan, size_t smem, 
 	if (grid > plan.nselected) grid = plan.nselected;
 	if (grid == 0) return CG_OK;
 	cg_scan_small_kernel<NCC, ALL8><<<grid, CGS_THREADS, smem, stream>>>(plan);
-	CG_CUDA(cudaGetLastError());
+	CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	return CG_OK;
 }
 

@@ -51,6 +51,8 @@ int cg_set_stream(void *cuda_stream);
  * collect waits for them and returns the launch count and the summed / maximum duration. */
 int cg_profile_begin(void);
 int cg_profile_collect(int32_t *launches, double *total_ms, double *max_ms);
+/* number of CUDA kernels this library has launched so far (all kernels, all entry points) */
+uint64_t cg_kernel_launches(void);
 void cg_shutdown(void);
 
 /* ---------------------------------------------------------------------------------- *
