@@ -61,6 +61,7 @@ def parse():
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--pageable", action="store_true", help="e2e from pageable host pages (host de-framing) instead of pinned pages (DMA)")
     p.add_argument("--gen-threads", type=int, default=0)
+    p.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to the CPUs of its GPU's NUMA node")
     return p.parse_args()
 
 
@@ -239,6 +240,7 @@ def run_ours(args, rank, world, local_rank):
     from citus_b200 import distributed as cgd
     torch.cuda.set_device(local_rank)
     cg.init(local_rank)
+    numa_node = -1 if args.no_numa_bind else cg.numa_bind()    # page images are first-touched on the GPU's socket
     # one non-default torch stream for everything: the library's kernels, torch ops, the events that
     # time them and (through torch's stream dependencies) the NCCL collectives
     torch.cuda.set_stream(torch.cuda.Stream())
@@ -388,12 +390,13 @@ def run_ours(args, rank, world, local_rank):
         e2e = {"value": total_rows / (ems / 1e3), "unit": "rows/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": ems, "steps": args.e2e_steps,
                "host_buffers": "pageable pages -> host de-frame into pinned blocks -> cudaMemcpyAsync" if args.pageable else
-                               "pinned (cudaHostRegister) page images -> strided 2-D DMA that drops the page headers -> GPU realign",
-               "api": "cg_scan_relation + cg_partial_fetch"}
+                               "pinned (cudaHostRegister) page images -> 1-D DMA of whole pages -> GPU drops page headers + realigns",
+               "api": "cg_scan_relation + cg_partial_fetch", "numa_node": numa_node}
 
     # ---- CPU baseline + full-size parity (rank 0, N = 1 only)
     cpu = None
     parity = None
+    cg.numa_unbind()                          # the CPU leg may use every core of the box
     if rank == 0 and world == 1 and not args.no_cpu:
         nthreads = min(NSHARDS, max(1, ncpu // 2))
         rows, secs, results, sample = cpu_scan(rels, rows_per_shard, nthreads)

@@ -94,6 +94,8 @@ SYMBOLS = [
     ("cg_shutdown", None, []),
     ("cg_set_stream", C.c_int, [C.c_void_p]),
     ("cg_kernel_launches", C.c_uint64, []),
+    ("cg_numa_bind", C.c_int, [C.POINTER(C.c_int32)]),
+    ("cg_numa_unbind", C.c_int, []),
     ("cg_profile_begin", C.c_int, []),
     ("cg_profile_collect", C.c_int, [C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("cg_shard_stage", C.c_int, [C.POINTER(CgRelation), _P, C.c_int32, C.POINTER(_P)]),

@@ -30,6 +30,18 @@ def init(device: int = 0):
     _initialised = True
 
 
+def numa_bind() -> int:
+    """pin this thread (and the staging/generator threads created after it) to the CPUs of the
+    device's NUMA node; returns the node or -1"""
+    node = C.c_int32(-1)
+    check(lib().cg_numa_bind(C.byref(node)))
+    return node.value
+
+
+def numa_unbind():
+    check(lib().cg_numa_unbind())
+
+
 def use_torch_stream():
     """run the library's kernels on torch's current stream, so that torch ops, NCCL collectives and
     the library's kernels are ordered in one queue (torch's default stream is CUDA's legacy default

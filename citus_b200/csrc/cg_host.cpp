@@ -5,7 +5,10 @@
  */
 #include <algorithm>
 #include <chrono>
+#include <ctype.h>
 #include <omp.h>
+#include <sched.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -71,6 +74,8 @@ extern "C" int cg_init(int device)
 	CG_CUDA(cudaStreamCreateWithFlags(&g_ctx.copy, cudaStreamNonBlocking));
 	CG_CUDA(cudaEventCreate(&g_ctx.ev_a));
 	CG_CUDA(cudaEventCreate(&g_ctx.ev_b));
+	CG_CUDA(cudaMalloc((void **) &g_ctx.d_stage_err, sizeof(unsigned long long)));
+	CG_CUDA(cudaMemset(g_ctx.d_stage_err, 0, sizeof(unsigned long long)));
 	const char *t = getenv("CG_STAGE_THREADS");
 	int hw = omp_get_num_procs();
 	g_ctx.stage_threads = t ? atoi(t) : std::min(hw, 32);
@@ -78,6 +83,61 @@ extern "C" int cg_init(int device)
 	const char *b = getenv("CG_PINNED_BLOCK_MB");
 	g_ctx.pinned_block_bytes = (size_t) (b ? atoi(b) : 64) << 20;
 	g_ctx_ready = true;
+	return CG_OK;
+}
+
+/* ------------------------------------------------------------------------------ *
+ *  NUMA placement.  On a two-socket host a GPU's PCIe root hangs off one socket; host pages
+ *  first touched (and staging threads run) on the other socket cross the inter-socket link on
+ *  every DMA read.  cg_numa_bind pins the calling thread -- and the threads it creates later --
+ *  to the CPUs of the device's NUMA node, read from sysfs; cg_numa_unbind restores the mask.
+ * ------------------------------------------------------------------------------ */
+static cpu_set_t g_saved_mask;
+static bool g_mask_saved = false;
+
+extern "C" int cg_numa_bind(int32_t *node_out)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx) return CG_EINVAL;
+	if (node_out) *node_out = -1;
+	char bus[32] = {0};
+	CG_CUDA(cudaDeviceGetPCIBusId(bus, sizeof bus, ctx->device));
+	for (char *c = bus; *c; c++) *c = (char) tolower(*c);
+	char path[256];
+	snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+	FILE *f = fopen(path, "r");
+	int node = -1;
+	if (f) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+	if (node < 0) return CG_OK;                   /* single node or unknown: nothing to do */
+	snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+	f = fopen(path, "r");
+	if (!f) return CG_OK;
+	char list[4096] = {0};
+	if (!fgets(list, sizeof list, f)) { fclose(f); return CG_OK; }
+	fclose(f);
+	cpu_set_t want, have;
+	CPU_ZERO(&want);
+	if (sched_getaffinity(0, sizeof have, &have) != 0) return CG_OK;
+	int n = 0;
+	for (char *tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n"))
+	{
+		int a = 0, b = 0;
+		int k = sscanf(tok, "%d-%d", &a, &b);
+		if (k == 1) b = a;
+		if (k < 1) continue;
+		for (int c = a; c <= b && c < CPU_SETSIZE; c++)
+			if (CPU_ISSET(c, &have)) { CPU_SET(c, &want); n++; }
+	}
+	if (n == 0) return CG_OK;                     /* the cgroup/cpuset excludes that node: keep what we have */
+	if (!g_mask_saved) { g_saved_mask = have; g_mask_saved = true; }
+	if (sched_setaffinity(0, sizeof want, &want) != 0) return CG_OK;
+	if (node_out) *node_out = node;
+	return CG_OK;
+}
+
+extern "C" int cg_numa_unbind(void)
+{
+	if (g_mask_saved) { sched_setaffinity(0, sizeof g_saved_mask, &g_saved_mask); g_mask_saved = false; }
 	return CG_OK;
 }
 
@@ -166,6 +226,21 @@ extern "C" void cg_shutdown(void)
 		g_ctx.pinned[i] = nullptr; g_ctx.pinned_free[i] = nullptr;
 	}
 	cudaEventDestroy(g_ctx.ev_a); cudaEventDestroy(g_ctx.ev_b);
+	cudaFree(g_ctx.d_stage_err); g_ctx.d_stage_err = nullptr;
+	for (int i = 0; i < CgContext::kDmaDepth; i++)
+	{
+		for (CgContext::DevBuf *b : {&g_ctx.slot_arena[i], &g_ctx.slot_raw[i], &g_ctx.slot_meta[i]})
+		{
+			cudaFree(b->p);
+			b->p = nullptr; b->cap = 0;
+		}
+		if (g_ctx.meta_pinned[i]) cudaFreeHost(g_ctx.meta_pinned[i]);
+		g_ctx.meta_pinned[i] = nullptr; g_ctx.meta_cap[i] = 0;
+		if (g_ctx.dma_done[i]) cudaEventDestroy(g_ctx.dma_done[i]);
+		g_ctx.dma_done[i] = nullptr;
+	}
+	if (g_ctx.dma_copied) cudaEventDestroy(g_ctx.dma_copied);
+	g_ctx.dma_copied = nullptr;
 	for (cudaEvent_t e : g_ctx.prof_events) cudaEventDestroy(e);
 	g_ctx.prof_events.clear();
 	cudaStreamDestroy(g_ctx.copy); cudaStreamDestroy(g_ctx.own_compute);
@@ -379,7 +454,8 @@ static inline uint64_t pad16(uint64_t x) { return (x + 15) & ~15ull; }
 struct StageItem   /* one (chunk group, staged column) */
 {
 	uint64_t exists_logical, value_logical;
-	uint32_t exists_len, value_len;
+	uint64_t wire_value_off;            /* arena slot of the on-disk value bytes (compressed or not) */
+	uint32_t exists_len, value_len;     /* on-disk lengths */
 };
 
 struct StagePlan
@@ -388,7 +464,10 @@ struct StagePlan
 	std::vector<StageItem> items;
 	std::vector<uint32_t> cg_rows;
 	std::vector<uint64_t> cg_begin;     /* arena offset where each chunk group starts; [ncg+1] */
-	uint64_t arena_bytes = 0;
+	std::vector<DecodeItem> decode;     /* compressed value streams, in chunk-group order */
+	std::vector<uint32_t> dec_first;    /* first decode item of each chunk group; [ncg+1] */
+	uint64_t wire_bytes = 0;            /* the chunk-group regions: what travels host -> device */
+	uint64_t arena_bytes = 0;           /* wire_bytes + the decompressed value slots */
 	uint64_t rows = 0;
 	bool any_nulls = false;
 };
@@ -407,6 +486,7 @@ static int plan_staging(const CgRelation *rel, const std::vector<int32_t> &stage
 			if (select && !(*select)[si][k]) continue;
 			uint32_t rows = (uint32_t) rel->nodes[s.skipnode_base + k].row_count;
 			sp->cg_begin.push_back(off);
+			sp->dec_first.push_back((uint32_t) sp->decode.size());
 			sp->cg_rows.push_back(rows);
 			sp->rows += rows;
 			for (size_t j = 0; j < ns; j++)
@@ -416,6 +496,8 @@ static int plan_staging(const CgRelation *rel, const std::vector<int32_t> &stage
 				StageItem it;
 				memset(&d, 0, sizeof d);
 				d.row_count = rows;
+				int comp = CG_COMPRESSION_NONE;
+				uint64_t rawlen = 0;
 				if ((uint32_t) c >= s.column_count)
 				{
 					/* column added after the stripe was written and without a default: all NULL
@@ -427,16 +509,23 @@ static int plan_staging(const CgRelation *rel, const std::vector<int32_t> &stage
 				else
 				{
 					const CgSkipNode &n = rel->nodes[s.skipnode_base + (uint32_t) c * s.chunk_count + k];
-					if (n.compression_type != CG_COMPRESSION_NONE)
+					comp = n.compression_type;
+					if (comp == CG_COMPRESSION_ZSTD)
 						return cg_set_error(CG_EUNSUPPORTED,
-											"stripe %d column %d chunk %u is compressed (type %d); this round stages compression=none only",
-											si, c, k, n.compression_type);
+											"stripe %d column %d chunk %u is zstd-compressed: only none, lz4 and pglz chunks are decoded on the GPU",
+											si, c, k);
+					if (comp != CG_COMPRESSION_NONE && comp != CG_COMPRESSION_LZ4 && comp != CG_COMPRESSION_PGLZ)
+						return cg_set_error(CG_ECORRUPT, "unexpected compression type: %d", comp);
 					if (n.row_count != rows) return cg_set_error(CG_ECORRUPT, "row count mismatch in chunk group");
 					if (n.exists_length * 8 < rows) return cg_set_error(CG_ECORRUPT, "insufficient data for reading boolean array");
 					int len = rel->columns[c].attlen;
-					if (n.decompressed_size % len != 0 || n.decompressed_size / len > rows || n.value_length != n.decompressed_size)
+					if (n.decompressed_size % len != 0 || n.decompressed_size / len > rows ||
+						(comp == CG_COMPRESSION_NONE && n.value_length != n.decompressed_size))
 						return cg_set_error(CG_ECORRUPT, "value stream of %llu bytes does not fit %u rows of %d bytes",
 											(unsigned long long) n.decompressed_size, rows, len);
+					if (n.value_length > UINT32_MAX - 64 || n.decompressed_size > UINT32_MAX - 64)
+						return cg_set_error(CG_EUNSUPPORTED, "chunk buffer of %llu bytes", (unsigned long long) n.value_length);
+					rawlen = n.decompressed_size;
 					it.exists_logical = s.file_offset + n.exists_offset;
 					it.value_logical = s.file_offset + n.value_offset;
 					it.exists_len = (uint32_t) n.exists_length;
@@ -445,6 +534,16 @@ static int plan_staging(const CgRelation *rel, const std::vector<int32_t> &stage
 				}
 				d.exists_off = off; off += pad16(std::max<uint64_t>((rows + 7) / 8, it.exists_len)) + 16;
 				d.values_off = off; off += pad16(it.value_len) + 16;
+				it.wire_value_off = d.values_off;
+				if (comp != CG_COMPRESSION_NONE)
+				{
+					/* dst is assigned below, behind the chunk-group regions */
+					DecodeItem di;
+					di.src = it.wire_value_off; di.dst = sp->cols.size();
+					di.comp_len = it.value_len; di.raw_len = (uint32_t) rawlen;
+					di.padded = (uint32_t) (pad16(rawlen) + 16); di.kind = (uint32_t) comp;
+					sp->decode.push_back(di);
+				}
 				if (d.value_count != rows)
 				{
 					d.rank_off = off; off += pad16(4ull * ((rows + 63) / 64));
@@ -456,6 +555,15 @@ static int plan_staging(const CgRelation *rel, const std::vector<int32_t> &stage
 		}
 	}
 	sp->cg_begin.push_back(off);
+	sp->dec_first.push_back((uint32_t) sp->decode.size());
+	sp->wire_bytes = off;
+	for (DecodeItem &di : sp->decode)
+	{
+		DevChunkCol &d = sp->cols[di.dst];
+		d.values_off = off;
+		di.dst = off;
+		off += di.padded;
+	}
 	sp->arena_bytes = off;
 	return CG_OK;
 }
@@ -474,8 +582,8 @@ static int fill_block(const CgRelation *rel, const StagePlan &sp, size_t ns, uin
 			const DevChunkCol &d = sp.cols[g * ns + j];
 			const StageItem &it = sp.items[g * ns + j];
 			uint8_t *ex = host + (d.exists_off - base);
-			uint8_t *va = host + (d.values_off - base);
-			uint64_t exspan = d.values_off - d.exists_off;
+			uint8_t *va = host + (it.wire_value_off - base);
+			uint64_t exspan = it.wire_value_off - d.exists_off;
 			memset(ex + (it.exists_len & ~15ull), 0, exspan - (it.exists_len & ~15ull));
 			if (it.exists_len && storage_read(rel->pages, rel->nblocks, it.exists_logical, ex, it.exists_len)) failed = 1;
 			uint64_t vaspan = pad16(it.value_len) + 16;
@@ -534,8 +642,8 @@ static int stream_to_device(CgContext *ctx, const CgRelation *rel, const StagePl
 	}
 	if (trace)
 		fprintf(stderr, "[cg] staged %.1f MB in %llu blocks: total %.1f ms (wait-for-slot %.1f, de-frame %.1f = %.1f GB/s, enqueue %.1f)\n",
-				sp.arena_bytes / 1e6, (unsigned long long) nblk, (now() - t_begin) * 1e3, t_wait * 1e3, t_fill * 1e3,
-				sp.arena_bytes / 1e9 / (t_fill > 0 ? t_fill : 1), t_enq * 1e3);
+				sp.wire_bytes / 1e6, (unsigned long long) nblk, (now() - t_begin) * 1e3, t_wait * 1e3, t_fill * 1e3,
+				sp.wire_bytes / 1e9 / (t_fill > 0 ? t_fill : 1), t_enq * 1e3);
 	return CG_OK;
 }
 
@@ -591,7 +699,25 @@ extern "C" int cg_shard_stage(const CgRelation *rel, const int32_t *columns, int
 	}
 	cudaError_t e = cudaMemcpyAsync(sh->d_chunkcols, sp.cols.data(), sp.cols.size() * sizeof(DevChunkCol), cudaMemcpyHostToDevice, ctx->copy);
 	if (e != cudaSuccess) { cg_shard_free(sh); return cg_set_error(CG_ECUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(e)); }
-	rc = stream_to_device(ctx, rel, sp, ns, sh->d_arena, [&](uint64_t, uint64_t, cudaEvent_t) { return CG_OK; });
+	/* compressed value streams are decoded block by block behind the H2D copies (K7) */
+	DecodeItem *d_decode = nullptr;
+	if (!sp.decode.empty())
+	{
+		if (cudaMalloc(&d_decode, sp.decode.size() * sizeof(DecodeItem)) != cudaSuccess ||
+			cudaMemcpy(d_decode, sp.decode.data(), sp.decode.size() * sizeof(DecodeItem), cudaMemcpyHostToDevice) != cudaSuccess ||
+			cudaMemsetAsync(ctx->d_stage_err, 0, sizeof(unsigned long long), ctx->compute) != cudaSuccess)
+		{
+			cudaFree(d_decode);
+			cg_shard_free(sh);
+			return cg_set_error(CG_ECUDA, "staging the decode list failed: %s", cudaGetErrorString(cudaGetLastError()));
+		}
+	}
+	rc = stream_to_device(ctx, rel, sp, ns, sh->d_arena, [&](uint64_t cg0, uint64_t cg1, cudaEvent_t copied) -> int {
+		uint32_t f = sp.dec_first[cg0], l = sp.dec_first[cg1];
+		if (f == l) return CG_OK;
+		CG_CUDA(cudaStreamWaitEvent(ctx->compute, copied, 0));
+		return cg_launch_decompress(sh->d_arena, d_decode + f, l - f, ctx->d_stage_err, CG_ERRFLAG_DECOMPRESS, ctx->compute);
+	});
 	if (rc == CG_OK && sp.any_nulls)
 	{
 		/* rank directories (K1 prefix popcount), once per staged shard */
@@ -605,6 +731,19 @@ extern "C" int cg_shard_stage(const CgRelation *rel, const int32_t *columns, int
 		if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(ctx->compute);
 		if (e2 != cudaSuccess) rc = cg_set_error(CG_ECUDA, "%s", cudaGetErrorString(e2));
 	}
+	else
+	{
+		cudaStreamSynchronize(ctx->copy);
+		cudaStreamSynchronize(ctx->compute);
+	}
+	if (rc == CG_OK && d_decode)
+	{
+		unsigned long long flags = 0;
+		cudaError_t e2 = cudaMemcpy(&flags, ctx->d_stage_err, sizeof flags, cudaMemcpyDeviceToHost);
+		if (e2 != cudaSuccess) rc = cg_set_error(CG_ECUDA, "%s", cudaGetErrorString(e2));
+		else if (flags & CG_ERRFLAG_DECOMPRESS) rc = cg_set_error(CG_ECORRUPT, "cannot decompress the buffer");
+	}
+	cudaFree(d_decode);
 	if (rc) { cg_shard_free(sh); return rc; }
 	*out = sh;
 	return CG_OK;
@@ -643,6 +782,8 @@ static int check_error_flags(CgPartial *p, unsigned long long flags)
 		return cg_set_error(CG_EINVAL, "group key outside [key_min, key_max] given to cg_partial_create");
 	if (flags & CG_ERRFLAG_SUM_BOUND)
 		return cg_set_error(CG_EINVAL, "sum argument exceeds term_abs_bound");
+	if (flags & CG_ERRFLAG_DECOMPRESS)
+		return cg_set_error(CG_ECORRUPT, "cannot decompress the buffer");
 	return CG_OK;
 }
 
@@ -804,12 +945,28 @@ extern "C" int cg_scan_shard(const CgShard *sh, const CgScanDesc *desc, CgPartia
 
 /* ------------------------------------------------------------------------------ *
  *  DMA staging: when the relation's pages sit in pinned (registered) host memory the copy
- *  engine de-frames them itself -- cudaMemcpy2DAsync with a source pitch of 8192 and a width
- *  of 8168 bytes drops the 24-byte page headers -- so no host core touches the data.  One
- *  2-D copy per (stripe, projected column) lands the column's byte range in a raw device
- *  buffer; cg_realign_kernel then moves every chunk buffer to its 16-byte aligned arena slot
- *  (the GPU half of ColumnarStorageRead's page de-framing, columnar_storage.c:463-492).
+ *  engine moves them itself, so no host core touches the data: one 1-D cudaMemcpyAsync per
+ *  run of pages that holds a (stripe, projected column) byte range lands whole pages in a
+ *  raw device buffer; cg_realign_kernel then drops the 24-byte page headers and moves every
+ *  chunk buffer to its 16-byte aligned arena slot (the GPU half of ColumnarStorageRead's
+ *  page de-framing, columnar_storage.c:463-492).
  * ------------------------------------------------------------------------------ */
+/* grows one of the context's reusable device buffers; the caller has made sure nothing uses it */
+static int devbuf_reserve(CgContext::DevBuf *b, size_t bytes)
+{
+	if (b->cap >= bytes) return CG_OK;
+	if (b->p) CG_CUDA(cudaFree(b->p));
+	b->p = nullptr; b->cap = 0;
+	size_t cap = bytes + bytes / 8 + 4096;
+	if (cudaMalloc((void **) &b->p, cap) != cudaSuccess)
+	{
+		cudaGetLastError();
+		return cg_set_error(CG_ENOMEM, "cudaMalloc of %zu bytes for a staging buffer failed", cap);
+	}
+	b->cap = cap;
+	return CG_OK;
+}
+
 extern "C" int cg_relation_register(const CgRelation *rel)
 {
 	if (!cg_ctx()) return CG_EINVAL;
@@ -842,8 +999,10 @@ static bool pages_are_pinned(const CgRelation *rel)
 
 struct DmaCopy { uint64_t raw_off; uint64_t first_block; uint64_t nblocks; };
 
-/* builds the 2-D copies and the realign items for the chunk groups of `sp` (same iteration
- * order as plan_staging) */
+/* builds the page copies and the realign items for the chunk groups of `sp` (same iteration
+ * order as plan_staging).  A copy is a run of whole pages sent with one 1-D cudaMemcpyAsync
+ * (55 GB/s; the strided 2-D form that drops the headers in the copy engine measured 38-47 GB/s,
+ * profiles/r01_pcie_probe.txt); column spans that touch or overlap share one copy. */
 static int plan_dma(const CgRelation *rel, const std::vector<int32_t> &staged,
 					const std::vector<std::vector<uint8_t>> &select, const StagePlan &sp,
 					std::vector<DmaCopy> *copies, std::vector<RealignItem> *items, uint64_t *raw_bytes)
@@ -857,7 +1016,10 @@ static int plan_dma(const CgRelation *rel, const std::vector<int32_t> &staged,
 		for (uint32_t k = 0; k < s.chunk_count; k++)
 			if (select[si][k]) { if (first == UINT32_MAX) first = k; last = k; }
 		if (first == UINT32_MAX) continue;
+		/* raw offset of logical byte 0 of page p0[j] for staged column j */
 		std::vector<uint64_t> base(ns, 0), p0(ns, 0);
+		struct Span { uint64_t b0, b1; size_t j; };
+		std::vector<Span> spans;
 		for (size_t j = 0; j < ns; j++)
 		{
 			int c = staged[j];
@@ -877,11 +1039,22 @@ static int plan_dma(const CgRelation *rel, const std::vector<int32_t> &staged,
 			memcpy(&lower, rel->pages + b0 * CG_BLCKSZ + 12, 2);
 			if (b0 != b1 && lower != CG_BLCKSZ)
 				return cg_set_error(CG_ECORRUPT, "attempt to read columnar data past pd_lower of block %llu", (unsigned long long) b0);
-			base[j] = raw_off;
-			p0[j] = b0;
+			spans.push_back(Span{b0, b1, j});
+		}
+		std::sort(spans.begin(), spans.end(), [](const Span &a, const Span &b) { return a.b0 < b.b0; });
+		for (size_t i = 0; i < spans.size();)
+		{
+			uint64_t b0 = spans[i].b0, b1 = spans[i].b1;
+			size_t e = i + 1;
+			while (e < spans.size() && spans[e].b0 <= b1 + 1) { b1 = std::max(b1, spans[e].b1); e++; }
+			for (size_t q = i; q < e; q++)
+			{
+				p0[spans[q].j] = spans[q].b0;
+				base[spans[q].j] = raw_off + (spans[q].b0 - b0) * CG_BLCKSZ;
+			}
 			copies->push_back(DmaCopy{raw_off, b0, b1 - b0 + 1});
-			raw_off += (b1 - b0 + 1) * CG_BYTES_PER_PAGE;
-			raw_off = (raw_off + 15) & ~15ull;
+			raw_off += (b1 - b0 + 1) * CG_BLCKSZ;
+			i = e;
 		}
 		for (uint32_t k = 0; k < s.chunk_count; k++)
 		{
@@ -890,17 +1063,21 @@ static int plan_dma(const CgRelation *rel, const std::vector<int32_t> &staged,
 			{
 				const DevChunkCol &d = sp.cols[g * ns + j];
 				const StageItem &it = sp.items[g * ns + j];
-				uint64_t exspan = d.values_off - d.exists_off;
+				uint64_t exspan = it.wire_value_off - d.exists_off;
 				uint64_t vaspan = pad16(it.value_len) + 16;
-				uint64_t esrc = it.exists_len ? base[j] + (it.exists_logical - p0[j] * CG_BYTES_PER_PAGE) : 0;
-				uint64_t vsrc = it.value_len ? base[j] + (it.value_logical - p0[j] * CG_BYTES_PER_PAGE) : 0;
+				auto phys = [&](uint64_t logical) {
+					uint64_t rel0 = logical - p0[j] * CG_BYTES_PER_PAGE;
+					return base[j] + (rel0 / CG_BYTES_PER_PAGE) * CG_BLCKSZ + CG_PAGE_HEADER + rel0 % CG_BYTES_PER_PAGE;
+				};
+				uint64_t esrc = it.exists_len ? phys(it.exists_logical) : CG_PAGE_HEADER;
+				uint64_t vsrc = it.value_len ? phys(it.value_logical) : CG_PAGE_HEADER;
 				items->push_back(RealignItem{esrc, d.exists_off, it.exists_len, (uint32_t) exspan});
-				items->push_back(RealignItem{vsrc, d.values_off, it.value_len, (uint32_t) vaspan});
+				items->push_back(RealignItem{vsrc, it.wire_value_off, it.value_len, (uint32_t) vaspan});
 			}
 			g++;
 		}
 	}
-	*raw_bytes = raw_off + 64;
+	*raw_bytes = raw_off + 2 * CG_BLCKSZ;   /* the realign kernel's last vector reads one word past a buffer */
 	return CG_OK;
 }
 
@@ -980,7 +1157,10 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 		const size_t cols_bytes = sp.cols.size() * sizeof(DevChunkCol);
 		const size_t ids_bytes = ncg * sizeof(uint32_t);
 		const size_t items_bytes = items.size() * sizeof(RealignItem);
-		const size_t meta_bytes = ((cols_bytes + 15) & ~15ull) + ((ids_bytes + 15) & ~15ull) + items_bytes + 64;
+		const size_t dec_bytes = sp.decode.size() * sizeof(DecodeItem);
+		const size_t off_ids = (cols_bytes + 15) & ~15ull, off_items = off_ids + ((ids_bytes + 15) & ~15ull);
+		const size_t off_dec = off_items + ((items_bytes + 15) & ~15ull);
+		const size_t meta_bytes = off_dec + dec_bytes + 64;
 		const int mslot = ctx->dma_slot;
 		ctx->dma_slot = (mslot + 1) % CgContext::kDmaDepth;
 		if (!ctx->dma_done[mslot]) CG_CUDA(cudaEventCreateWithFlags(&ctx->dma_done[mslot], cudaEventDisableTiming));
@@ -995,16 +1175,21 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 			ctx->meta_cap[mslot] = cap;
 		}
 		uint8_t *hm = ctx->meta_pinned[mslot];
-		uint8_t *d_meta = nullptr;
-		CG_CUDA(cudaMallocAsync((void **) &d_arena, std::max<uint64_t>(sp.arena_bytes, 16), ctx->copy));
-		CG_CUDA(cudaMallocAsync((void **) &d_meta, meta_bytes, ctx->copy));
-		size_t off_ids = (cols_bytes + 15) & ~15ull, off_items = off_ids + ((ids_bytes + 15) & ~15ull);
+		/* the slot's device buffers: everything that used them has finished (dma_done above) */
+		rc = devbuf_reserve(&ctx->slot_arena[mslot], std::max<uint64_t>(sp.arena_bytes, 16));
+		if (rc == CG_OK) rc = devbuf_reserve(&ctx->slot_meta[mslot], meta_bytes);
+		if (rc == CG_OK && dma) rc = devbuf_reserve(&ctx->slot_raw[mslot], raw_bytes);
+		if (rc) return rc;
+		d_arena = ctx->slot_arena[mslot].p;
+		uint8_t *d_meta = ctx->slot_meta[mslot].p;
 		memcpy(hm, sp.cols.data(), cols_bytes);
 		for (uint64_t g = 0; g < ncg; g++) ((uint32_t *) (hm + off_ids))[g] = (uint32_t) g;
 		if (items_bytes) memcpy(hm + off_items, items.data(), items_bytes);
+		if (dec_bytes) memcpy(hm + off_dec, sp.decode.data(), dec_bytes);
 		CG_CUDA(cudaMemcpyAsync(d_meta, hm, meta_bytes, cudaMemcpyHostToDevice, ctx->copy));
 		d_cols = (DevChunkCol *) d_meta;
 		d_ids = (uint32_t *) (d_meta + off_ids);
+		const DecodeItem *d_decode = (const DecodeItem *) (d_meta + off_dec);
 		plan.arena = d_arena;
 		plan.chunkcols = d_cols;
 		plan.nstaged = (int32_t) ns;
@@ -1014,12 +1199,16 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 		if (stats) CG_CUDA(cudaEventRecord(ctx->ev_a, ctx->compute));
 		auto launch_block = [&](uint64_t cg0, uint64_t cg1, cudaEvent_t copied) -> int {
 			CG_CUDA(cudaStreamWaitEvent(ctx->compute, copied, 0));
+			/* K7: compressed value streams of the block -> their value slots */
+			int r = cg_launch_decompress(d_arena, d_decode + sp.dec_first[cg0], sp.dec_first[cg1] - sp.dec_first[cg0],
+										 into->d_stats + 2, CG_ERRFLAG_DECOMPRESS, ctx->compute);
+			if (r) return r;
 			if (sp.any_nulls)
 			{
-				int r = cg_launch_rank(ctx, d_arena, d_cols, cg0 * ns, (cg1 - cg0) * ns, ctx->compute);
+				r = cg_launch_rank(ctx, d_arena, d_cols, cg0 * ns, (cg1 - cg0) * ns, ctx->compute);
 				if (r) return r;
 			}
-			int r = cg_prof_mark(ctx, ctx->compute);
+			r = cg_prof_mark(ctx, ctx->compute);
 			if (r) return r;
 			if (use_small)
 			{
@@ -1046,30 +1235,56 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 			if (r) return r;
 			return cg_prof_mark(ctx, ctx->compute);
 		};
-		uint8_t *d_raw = nullptr;
 		if (dma)
 		{
-			/* the copy engine de-frames the pages */
-			CG_CUDA(cudaMallocAsync((void **) &d_raw, raw_bytes, ctx->copy));
+			/* whole pages by DMA; the GPU de-frames them */
+			static int trace = -1;
+			if (trace < 0) { const char *e = getenv("CG_TRACE"); trace = (e && atoi(e)) ? 1 : 0; }
+			cudaEvent_t t0 = nullptr, t1 = nullptr;
+			auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+			double h0 = now();
+			uint8_t *d_raw = ctx->slot_raw[mslot].p;
+			if (trace) { cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventRecord(t0, ctx->copy); }
 			for (const DmaCopy &c : copies)
 			{
-				CG_CUDA(cudaMemcpy2DAsync(d_raw + c.raw_off, CG_BYTES_PER_PAGE, rel->pages + c.first_block * CG_BLCKSZ + CG_PAGE_HEADER,
-										  CG_BLCKSZ, CG_BYTES_PER_PAGE, c.nblocks, cudaMemcpyHostToDevice, ctx->copy));
-				dma_bytes += c.nblocks * CG_BYTES_PER_PAGE;
+				CG_CUDA(cudaMemcpyAsync(d_raw + c.raw_off, rel->pages + c.first_block * CG_BLCKSZ, c.nblocks * CG_BLCKSZ,
+										cudaMemcpyHostToDevice, ctx->copy));
+				dma_bytes += c.nblocks * CG_BLCKSZ;
+			}
+			if (trace)
+			{
+				double h1 = now();
+				cudaEventRecord(t1, ctx->copy);
+				cudaEventSynchronize(t1);
+				float ms = 0;
+				cudaEventElapsedTime(&ms, t0, t1);
+				fprintf(stderr, "[cg] dma: %zu copies, %.1f MB, issue %.2f ms, copy-stream %.2f ms = %.1f GB/s\n", copies.size(),
+						dma_bytes / 1e6, (h1 - h0) * 1e3, ms, dma_bytes / 1e6 / ms);
+				cudaEventDestroy(t0); cudaEventDestroy(t1);
 			}
 			CG_CUDA(cudaEventRecord(ctx->dma_copied, ctx->copy));
 			CG_CUDA(cudaStreamWaitEvent(ctx->compute, ctx->dma_copied, 0));
+			cudaEvent_t k0 = nullptr, k1 = nullptr, k2 = nullptr;
+			if (trace) { cudaEventCreate(&k0); cudaEventCreate(&k1); cudaEventCreate(&k2); cudaEventRecord(k0, ctx->compute); }
 			rc = cg_launch_realign(d_raw, d_arena, (const RealignItem *) (d_meta + off_items), items.size(), ctx->compute);
+			if (trace) cudaEventRecord(k1, ctx->compute);
 			if (rc == CG_OK) rc = launch_block(0, ncg, ctx->dma_copied);
+			if (trace)
+			{
+				cudaEventRecord(k2, ctx->compute);
+				cudaEventSynchronize(k2);
+				float a = 0, b = 0;
+				cudaEventElapsedTime(&a, k0, k1);
+				cudaEventElapsedTime(&b, k1, k2);
+				fprintf(stderr, "[cg] dma: realign %.3f ms (%zu items), decode (%zu streams) + scan %.3f ms\n", a, items.size(),
+						sp.decode.size(), b);
+				cudaEventDestroy(k0); cudaEventDestroy(k1); cudaEventDestroy(k2);
+			}
 			used_dma = true;
 		}
 		else
 			rc = stream_to_device(ctx, rel, sp, ns, d_arena, launch_block);
 		if (stats && rc == CG_OK) CG_CUDA(cudaEventRecord(ctx->ev_b, ctx->compute));
-		/* frees are ordered after the kernels on the compute stream */
-		if (d_raw) cudaFreeAsync(d_raw, ctx->compute);
-		cudaFreeAsync(d_arena, ctx->compute);
-		cudaFreeAsync(d_meta, ctx->compute);
 		CG_CUDA(cudaEventRecord(ctx->dma_done[mslot], ctx->compute));
 		if (rc) return rc;
 	}
@@ -1086,8 +1301,9 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 			float ms = 0;
 			CG_CUDA(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
 			stats->kernel_ms = ms;   /* here: first kernel start to last kernel end, H2D overlapped */
-			stats->h2d_bytes = (int64_t) ((used_dma ? dma_bytes + 2 * ncg * ns * sizeof(RealignItem) : sp.arena_bytes) +
-										  sp.cols.size() * sizeof(DevChunkCol) + ncg * sizeof(uint32_t));
+			stats->h2d_bytes = (int64_t) ((used_dma ? dma_bytes + 2 * ncg * ns * sizeof(RealignItem) : sp.wire_bytes) +
+										  sp.cols.size() * sizeof(DevChunkCol) + ncg * sizeof(uint32_t) +
+										  sp.decode.size() * sizeof(DecodeItem));
 		}
 	}
 	return CG_OK;

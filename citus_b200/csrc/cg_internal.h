@@ -50,6 +50,10 @@ struct CgContext
 	int dma_slot = 0;
 	uint8_t *meta_pinned[kDmaDepth] = {nullptr, nullptr, nullptr};   /* pinned ring for per-scan metadata */
 	size_t meta_cap[kDmaDepth] = {0, 0, 0};
+	/* device buffers of the shards in flight (grown on demand, reused: no allocator in the scan loop) */
+	struct DevBuf { uint8_t *p = nullptr; size_t cap = 0; };
+	DevBuf slot_arena[kDmaDepth], slot_raw[kDmaDepth], slot_meta[kDmaDepth];
+	unsigned long long *d_stage_err = nullptr;   /* error flags raised by staging kernels of cg_shard_stage */
 	/* per-launch profiling */
 	bool profiling = false;
 	std::vector<cudaEvent_t> prof_events;   /* pairs */
@@ -67,7 +71,9 @@ int cg_ensure_pinned(CgContext *ctx);
  *     [rank directory: uint32 per 64 rows = number of non-NULL rows before the block]
  *                                       (only when the chunk has NULLs)
  *  all 16-byte aligned, in chunk-group-major order (so a block of consecutive chunk
- *  groups is one contiguous H2D copy).
+ *  groups is one contiguous H2D copy).  A compressed value stream (lz4 / pglz) keeps its
+ *  on-disk bytes in that place; its decompressed value slot lives in a second area behind
+ *  the chunk-group regions, filled by cg_decompress_kernel, and values_off points there.
  * ------------------------------------------------------------------------------ */
 struct DevChunkCol
 {
@@ -228,6 +234,7 @@ struct FPlan
 #define CG_ERRFLAG_NULL_MULTIKEY 2ull
 #define CG_ERRFLAG_KEY_RANGE 4ull
 #define CG_ERRFLAG_SUM_BOUND 8ull
+#define CG_ERRFLAG_DECOMPRESS 16ull
 #define CG_STAT_PACKED_ADDED 3
 #define CG_STAT_PACKED_DRAINED 4
 
@@ -275,6 +282,20 @@ struct RealignItem
 	uint32_t padded;    /* slot size: bytes beyond len are zeroed */
 };
 int cg_launch_realign(const uint8_t *raw, uint8_t *arena, const RealignItem *items, uint64_t nitems, cudaStream_t stream);
+
+/* cg_decompress.cu: one compressed value stream (arena offset src, comp_len bytes) to decode into its
+ * value slot (arena offset dst, raw_len bytes, zero padding up to `padded`) */
+struct DecodeItem
+{
+	uint64_t src;
+	uint64_t dst;
+	uint32_t comp_len;
+	uint32_t raw_len;
+	uint32_t padded;
+	uint32_t kind;      /* CG_COMPRESSION_LZ4 / CG_COMPRESSION_PGLZ */
+};
+int cg_launch_decompress(uint8_t *arena, const DecodeItem *items, uint64_t nitems, unsigned long long *err,
+						 unsigned long long flag, cudaStream_t stream);
 
 /* cg_scan_small.cu */
 bool cg_small_eligible(const KPlan &plan);

@@ -446,18 +446,23 @@ int cg_launch_rank(CgContext *ctx, const uint8_t *arena, const DevChunkCol *chun
 }
 
 /* ------------------------------------------------------------------------------ *
- *  Realign: chunk buffers arrive from the copy engine at arbitrary byte offsets (exists
- *  bitmaps are ceil(rows/8) bytes long, so value streams are not even 8-byte aligned in
- *  the logical byte stream); every block moves one buffer to its 16-byte aligned slot with
- *  aligned 4-byte loads + byte permutes, and zero-fills the slot's padding.
+ *  Realign: the copy engine delivers whole 8 KB pages (24-byte header + 8168-byte payload,
+ *  columnar_storage.c:21-31) with plain 1-D copies; chunk buffers sit in them at arbitrary
+ *  byte offsets (exists bitmaps are ceil(rows/8) bytes long, so value streams are not even
+ *  8-byte aligned in the logical byte stream) and run across page headers.  Every block moves
+ *  one buffer to its 16-byte aligned arena slot -- the GPU half of ColumnarStorageRead's
+ *  de-framing (columnar_storage.c:463-492, ReadFromBlock :669-689) -- with aligned 4-byte loads
+ *  + byte permutes, and zero-fills the slot's padding.  Header, payload and page sizes are all
+ *  multiples of 4, so an aligned word never straddles a header.
  * ------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(128)
 cg_realign_kernel(const uint8_t *raw, uint8_t *arena, const RealignItem *items)
 {
 	const RealignItem it = items[blockIdx.x];
-	const uint8_t *src = raw + it.src;
-	const uint32_t mis = (uint32_t) ((uintptr_t) src & 3u);
-	const uint32_t *s32 = (const uint32_t *) (src - mis);
+	const uint32_t mis = (uint32_t) (it.src & 3u);
+	const uint64_t w0 = it.src - mis;                                  /* first aligned word (raw offsets of page starts are multiples of 8192) */
+	const uint32_t t0 = (uint32_t) (w0 % CG_BLCKSZ) - CG_PAGE_HEADER;    /* its payload coordinate in its page */
+	const uint8_t *page0 = raw + (w0 - (w0 % CG_BLCKSZ));
 	const uint32_t sel = 0x3210u + 0x1111u * mis;
 	uint4 *dst = (uint4 *) (arena + it.dst);
 	const uint32_t nvec = it.padded / 16;
@@ -467,8 +472,16 @@ cg_realign_kernel(const uint8_t *raw, uint8_t *arena, const RealignItem *items)
 		if (16 * i < it.len)
 		{
 			uint32_t w[5];
+			uint32_t t = t0 + 16 * i;
+			uint32_t pg = t / CG_BYTES_PER_PAGE, within = t - pg * CG_BYTES_PER_PAGE;
+			const uint8_t *p = page0 + (uint64_t) pg * CG_BLCKSZ + CG_PAGE_HEADER;
 #pragma unroll
-			for (int k = 0; k < 5; k++) w[k] = __ldg(s32 + 4 * i + k);
+			for (int k = 0; k < 5; k++)
+			{
+				w[k] = __ldg((const uint32_t *) (p + within));
+				within += 4;
+				if (within == CG_BYTES_PER_PAGE) { within = 0; p += CG_BLCKSZ; }
+			}
 #pragma unroll
 			for (int k = 0; k < 4; k++) o[k] = __byte_perm(w[k], w[k + 1], sel);
 			if (16 * i + 16 > it.len)

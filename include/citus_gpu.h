@@ -53,6 +53,12 @@ int cg_profile_begin(void);
 int cg_profile_collect(int32_t *launches, double *total_ms, double *max_ms);
 /* number of CUDA kernels this library has launched so far (all kernels, all entry points) */
 uint64_t cg_kernel_launches(void);
+/* Pin the calling thread (and threads it creates afterwards: the staging threads) to the CPUs
+ * of the device's NUMA node, so that host pages it first-touches and the DMA reads of them stay
+ * on the socket the GPU hangs off.  *node = the node, or -1 when nothing was changed (single
+ * node, sysfs unreadable, cpuset excludes the node).  cg_numa_unbind restores the old mask. */
+int cg_numa_bind(int32_t *node);
+int cg_numa_unbind(void);
 void cg_shutdown(void);
 
 /* ---------------------------------------------------------------------------------- *
@@ -237,8 +243,8 @@ int cg_scan_shard(const CgShard *shard, const CgScanDesc *desc, CgPartial *into,
  * node calls once per shard task.  Pageable pages (shared_buffers as it is today) are
  * de-framed by host threads into pinned blocks and sent with cudaMemcpyAsync; pages in
  * pinned memory (cg_relation_register, or a shared_buffers segment registered once at
- * startup) are sent by the copy engine itself with strided 2-D copies that skip the page
- * headers, and re-aligned on the GPU. */
+ * startup) are sent by the copy engine itself as runs of whole pages (1-D copies);
+ * the GPU drops the page headers and re-aligns the chunk buffers. */
 int cg_relation_register(const CgRelation *rel);      /* cudaHostRegister of the page image */
 int cg_relation_unregister(const CgRelation *rel);
 int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, CgPartial *into, CgScanStats *stats);

@@ -13,7 +13,8 @@
  * columnar_query aggregates, TPC-H Q1/Q6 over the 12 000-row lineitem fixture,
  * sum(l_suppkey)) -- see SURVEY.md section 4 / 8(c).  Compressed chunk BYTES
  * (lz4/zstd) are round-trip-only ("parity unpinned" for the encoded bytes, the
- * reference holds no golden compressed buffers); pglz is not restated.
+ * reference holds no golden compressed buffers); pglz's stream format is restated
+ * with a stand-in matcher (see orc_pglz_compress).
  *
  * The arithmetic of this path mostly lives in PostgreSQL core (16-18), which is
  * not vendored under /root/reference; the pieces restated from its published
@@ -331,6 +332,108 @@ static int orc_load_codecs(void)
 int orc_have_lz4(void) { orc_load_codecs(); return p_lz4_comp != NULL; }
 int orc_have_zstd(void) { orc_load_codecs(); return p_zstd_comp != NULL; }
 
+/* ------------------------------------------------------------------------------
+ * pglz: [PG] src/common/pg_lzcompress.c (PostgreSQL is not part of /root/reference;
+ * the stream format is restated from its published description).  A stream is a
+ * sequence of control bytes, each followed by up to 8 items, LSB first: bit clear =
+ * one literal byte; bit set = a tag of 2 bytes [ (off >> 8) << 4 | (len - 3) ]
+ * [ off & 0xff ], followed by one more byte (len - 18) when len - 3 == 15.
+ * off in 1..4095, len in 3..273.
+ *
+ * orc_pglz_decompress restates pglz_decompress(source, slen, dest, rawsize,
+ * check_complete = true) as the reference calls it (columnar_compression.c:245-250).
+ * orc_pglz_compress is a plain greedy hash-chain matcher that emits the same format; it
+ * is NOT PostgreSQL's matcher, so the compressed BYTES are "parity unpinned" (the
+ * reference holds no golden pglz buffers); only decode(encode(x)) == x and the failure
+ * rule of PGLZ_strategy_always (output must be smaller than (slen/100)*100) are kept.
+ * ------------------------------------------------------------------------------ */
+static int32_t orc_pglz_decompress(const uint8_t *source, int32_t slen, uint8_t *dest, int32_t rawsize)
+{
+	const uint8_t *sp = source, *srcend = source + slen;
+	uint8_t *dp = dest, *destend = dest + rawsize;
+	while (sp < srcend && dp < destend)
+	{
+		uint8_t ctrl = *sp++;
+		for (int ctrlc = 0; ctrlc < 8 && sp < srcend && dp < destend; ctrlc++)
+		{
+			if (ctrl & 1)
+			{
+				int32_t len = (sp[0] & 0x0f) + 3;
+				int32_t off = ((sp[0] & 0xf0) << 4) | sp[1];
+				sp += 2;
+				if (len == 18) len += *sp++;
+				if (sp > srcend || off == 0 || off > (dp - dest)) return -1;
+				if (len > destend - dp) len = (int32_t) (destend - dp);
+				for (int32_t i = 0; i < len; i++) dp[i] = dp[i - off];   /* overlapping forward copy */
+				dp += len;
+			}
+			else
+				*dp++ = *sp++;
+			ctrl >>= 1;
+		}
+	}
+	if (dp != destend || sp != srcend) return -1;
+	return (int32_t) (dp - dest);
+}
+
+static int32_t orc_pglz_compress(const uint8_t *src, int32_t slen, uint8_t *dst)
+{
+	enum { HSIZE = 8192, MAXOFF = 4095, MAXLEN = 273, CHAIN = 32 };
+	if (slen <= 0) return -1;
+	int32_t result_max = (slen / 100) * 100;
+	int32_t *head = malloc(sizeof(int32_t) * HSIZE), *prev = malloc(sizeof(int32_t) * (size_t) slen);
+	for (int i = 0; i < HSIZE; i++) head[i] = -1;
+	uint8_t *bp = dst, *ctrlp = NULL;
+	uint8_t ctrlb = 0, ctrl = 0;
+	int32_t i = 0;
+	int ok = 1;
+#define ORC_PGLZ_HASH(p) ((((p)[0] << 6) ^ ((p)[1] << 3) ^ (p)[2]) & (HSIZE - 1))
+	while (i < slen)
+	{
+		if (bp - dst >= result_max) { ok = 0; break; }
+		if (ctrl == 0) { if (ctrlp) *ctrlp = ctrlb; ctrlp = bp++; ctrlb = 0; ctrl = 1; }
+		int32_t best_len = 0, best_off = 0;
+		if (i + 3 <= slen)
+		{
+			int h = ORC_PGLZ_HASH(src + i);
+			int32_t cand = head[h];
+			for (int depth = 0; cand >= 0 && i - cand <= MAXOFF && depth < CHAIN; depth++, cand = prev[cand])
+			{
+				int32_t l = 0, maxl = slen - i < MAXLEN ? slen - i : MAXLEN;
+				while (l < maxl && src[cand + l] == src[i + l]) l++;
+				if (l > best_len) { best_len = l; best_off = i - cand; }
+			}
+		}
+		int32_t step = 1;
+		if (best_len >= 3)
+		{
+			ctrlb |= ctrl;
+			if (best_len > 17)
+			{
+				*bp++ = (uint8_t) (((best_off & 0xf00) >> 4) | 0x0f);
+				*bp++ = (uint8_t) (best_off & 0xff);
+				*bp++ = (uint8_t) (best_len - 18);
+			}
+			else
+			{
+				*bp++ = (uint8_t) (((best_off & 0xf00) >> 4) | (best_len - 3));
+				*bp++ = (uint8_t) (best_off & 0xff);
+			}
+			step = best_len;
+		}
+		else
+			*bp++ = src[i];
+		ctrl = (uint8_t) (ctrl << 1);
+		for (int32_t k = 0; k < step; k++, i++)
+			if (i + 3 <= slen) { int h = ORC_PGLZ_HASH(src + i); prev[i] = head[h]; head[h] = i; }
+	}
+#undef ORC_PGLZ_HASH
+	if (ctrlp) *ctrlp = ctrlb;
+	free(head); free(prev);
+	if (!ok || bp - dst >= result_max) return -1;
+	return (int32_t) (bp - dst);
+}
+
 /* columnar/columnar_compression.c:62-157 CompressBuffer.  Returns compressed
  * length (>0) and sets *out, or 0 when "not compressed" (stored raw). */
 static uint64_t orc_compress(const uint8_t *in, uint64_t len, int type, int level, uint8_t **out)
@@ -344,6 +447,19 @@ static uint64_t orc_compress(const uint8_t *in, uint64_t len, int type, int leve
 		if (n <= 0) { free(buf); return 0; }
 		*out = buf;
 		return (uint64_t) n;
+	}
+	if (type == ORC_COMP_PGLZ)
+	{
+		/* :120-150: PGLZ_MAX_OUTPUT(len) = len + 4, behind the 8-byte ColumnarCompressHeader
+		 * {vl_len_ = SET_VARSIZE_COMPRESSED(total) (little endian: total << 2 | 0x02), rawsize} */
+		uint8_t *buf = malloc((size_t) len + 4 + 8 + 16);
+		int32_t n = orc_pglz_compress(in, (int32_t) len, buf + 8);
+		if (n < 0) { free(buf); return 0; }
+		uint32_t total = (uint32_t) n + 8, hdr = (total << 2) | 0x02u, raw = (uint32_t) len;
+		memcpy(buf, &hdr, 4);
+		memcpy(buf + 4, &raw, 4);
+		*out = buf;
+		return total;
 	}
 	if (type == ORC_COMP_ZSTD && p_zstd_comp)
 	{
@@ -381,9 +497,40 @@ static int orc_decompress(const uint8_t *in, uint64_t len, int type, uint64_t ra
 			if (n != rawlen) ORC_FAIL("unexpected decompressed size");
 			return 0;
 		}
+		case ORC_COMP_PGLZ:
+		{
+			/* :240-267 */
+			uint32_t hdr, raw;
+			if (len < 8) ORC_FAIL("cannot decompress the buffer");
+			memcpy(&hdr, in, 4);
+			memcpy(&raw, in + 4, 4);
+			uint32_t varsize = (hdr >> 2) & 0x3FFFFFFFu;            /* VARSIZE of a 4-byte varlena header */
+			if (varsize != len) ORC_FAIL("cannot decompress the buffer");
+			if (raw != rawlen) ORC_FAIL("cannot decompress the buffer");
+			if (orc_pglz_decompress(in + 8, (int32_t) (varsize - 8), out, (int32_t) raw) < 0)
+				ORC_FAIL("cannot decompress the buffer");
+			return 0;
+		}
 		default:
 			ORC_FAIL("unexpected compression type: %d", type);
 	}
+}
+
+/* the codecs alone, for known-answer tests of the stream formats */
+int64_t orc_codec_compress(int type, int level, const uint8_t *in, uint64_t len, uint8_t *out, uint64_t cap)
+{
+	uint8_t *buf = NULL;
+	uint64_t n = orc_compress(in, len, type, level, &buf);
+	if (n == 0) return 0;
+	if (n > cap) { free(buf); return -1; }
+	memcpy(out, buf, n);
+	free(buf);
+	return (int64_t) n;
+}
+
+int orc_codec_decompress(int type, const uint8_t *in, uint64_t len, uint64_t rawlen, uint8_t *out)
+{
+	return orc_decompress(in, len, type, rawlen, out);
 }
 
 static int orc_align_of(char attalign)

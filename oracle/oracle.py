@@ -82,6 +82,9 @@ def lib():
         L.orc_copy_file_bytes.restype = C.c_int64
         L.orc_copy_file_bytes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                           C.c_int, C.c_int64, C.c_int]
+        L.orc_codec_compress.restype = C.c_int64
+        L.orc_codec_compress.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+        L.orc_codec_decompress.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
         L.orc_table_create.restype = C.c_void_p
         L.orc_table_create.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_int]
         L.orc_table_free.argtypes = [C.c_void_p]
@@ -218,6 +221,25 @@ def min_(col, is_float=False):
 
 def max_(col, is_float=False):
     return Agg(AGG_MAX, [(col, 0, 1)], is_float)
+
+
+def codec_compress(comp, data: bytes, level=3):
+    """CompressBuffer of one value stream; None when the codec declines (stored raw)"""
+    src = np.frombuffer(data, np.uint8)
+    out = np.empty(len(data) * 2 + 1024, np.uint8)
+    n = lib().orc_codec_compress(comp, level, src.ctypes.data if len(data) else None, len(data), out.ctypes.data, out.shape[0])
+    if n < 0:
+        raise OracleError("compressed output too large")
+    return None if n == 0 else out[:n].tobytes()
+
+
+def codec_decompress(comp, data: bytes, rawlen: int) -> bytes:
+    """DecompressBuffer of one value stream"""
+    src = np.frombuffer(data, np.uint8)
+    out = np.zeros(max(rawlen, 1), np.uint8)
+    if lib().orc_codec_decompress(comp, src.ctypes.data, len(data), rawlen, out.ctypes.data):
+        raise OracleError(lib().orc_last_error().decode())
+    return out[:rawlen].tobytes()
 
 
 class Table:

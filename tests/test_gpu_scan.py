@@ -333,14 +333,81 @@ def test_ragged_chunks_and_max_chunk_size(cg, oracle):
                  chunk_row_limit=chunk, e2e="dma")
 
 
+# --------------------------------------------------------------------------- compressed chunks (K7)
+def _compressed_relation(cg, oracle, comp, n, seed, stripe=150000, chunk=10000):
+    """a table written by the oracle's writer (columnar_writer.c:590-654) with lz4 / pglz value streams:
+    long overlapping matches, short matches, long literal runs, NULLs, narrow columns"""
+    rng = np.random.default_rng(seed)
+    cols = [
+        (np.arange(n) % 7, 8, None),                                   # one long match with overlap
+        (rng.integers(0, 100, n), 8, None),                            # short sequences
+        (rng.integers(-2**62, 2**62, n), 8, None),                     # incompressible: lz4 = literal runs, pglz = stored raw
+        (rng.integers(-10**9, 10**9, n), 8, (rng.random(n) < 0.1)),    # NULLs: the stream holds only non-NULL values
+        (rng.integers(0, 20000, n) // 100, 4, None),
+        (rng.integers(0, 3, n), 2, (rng.random(n) < 0.5)),
+        (np.repeat(rng.integers(0, 100, (n + 499) // 500), 500)[:n], 1, None),
+    ]
+    t = oracle.Table([c[1] for c in cols], stripe_row_limit=stripe, chunk_row_limit=chunk, compression=comp)
+    t.insert([c[0] for c in cols], [None if c[2] is None else c[2].astype(np.uint8) for c in cols])
+    rel = cg.Relation.from_image(t.pages(), t.stripes_array(), t.nodes_array(), [c[1] for c in cols])
+    kinds = {nd.compression_type for nd in t.nodes()}
+    return t, rel, kinds
+
+
+@pytest.mark.parametrize("path", ["shard", "e2e", "dma"])
+@pytest.mark.parametrize("comp", ["lz4", "pglz"])
+def test_compressed_chunks(cg, oracle, comp, path):
+    if comp == "lz4" and not oracle.lib().orc_have_lz4():
+        pytest.skip("liblz4 missing")
+    code = oracle.COMP_LZ4 if comp == "lz4" else oracle.COMP_PGLZ
+    for n, stripe, chunk in ((123_457, 50_000, 10_000), (2_001, 1_000, 1_000)):
+        t, rel, kinds = _compressed_relation(cg, oracle, code, n, seed=n, stripe=stripe, chunk=chunk)
+        assert code in kinds
+        if comp == "pglz":
+            assert oracle.COMP_NONE in kinds        # the incompressible column is stored raw: mixed relation
+        e2e = {"shard": False, "e2e": True, "dma": "dma"}[path]
+        run_both(cg, oracle, rel, quals=[(1, "<", 50)], group_cols=[0],
+                 aggs=[cg.count_star(), cg.sum_(2), cg.sum_(3), cg.count(3), cg.min_(4), cg.max_(6)],
+                 chunk_row_limit=chunk, e2e=e2e)
+        run_both(cg, oracle, rel, quals=[(4, ">=", 20), (6, "<", 90)], group_cols=[5],
+                 aggs=[cg.count_star(), cg.sum_(1), cg.sum_(6)], chunk_row_limit=chunk, e2e=e2e)
+        run_both(cg, oracle, rel, aggs=[cg.count_star(), cg.sum_(2), cg.count(5), cg.sum_(0)], chunk_row_limit=chunk, e2e=e2e)
+
+
+@pytest.mark.parametrize("comp", ["lz4", "pglz"])
+def test_corrupt_compressed_stream_is_reported(cg, oracle, comp):
+    from citus_b200 import capi
+    if comp == "lz4" and not oracle.lib().orc_have_lz4():
+        pytest.skip("liblz4 missing")
+    code = oracle.COMP_LZ4 if comp == "lz4" else oracle.COMP_PGLZ
+    t = oracle.Table([8], compression=code)
+    t.insert([np.arange(30000) % 11])
+    nodes = t.nodes_array().copy()
+    assert nodes.shape[0] % 80 == 0
+    vl = nodes[40:48].view(np.uint64)
+    vl[0] -= 1                                             # truncated stream: "cannot decompress the buffer"
+    bad = cg.Relation.from_image(t.pages(), t.stripes_array(), nodes, [8])
+    with pytest.raises(capi.CitusGpuError) as e:
+        cg.Shard(bad)
+    assert e.value.code == capi.CG_ECORRUPT
+    d = cg.make_desc(aggs=[cg.count_star(), cg.sum_(0)])
+    agg = cg.GpuColumnarAgg(d, bad.column_descs())
+    with pytest.raises(capi.CitusGpuError) as e:
+        agg.scan_relation(bad)
+        agg.groups()
+    assert e.value.code == capi.CG_ECORRUPT
+    agg.free()
+
+
 def test_unsupported_inputs_are_refused(cg, oracle):
     from citus_b200 import capi
-    t = oracle.Table([8], compression=oracle.COMP_LZ4)
-    t.insert([np.arange(50000) % 7])
-    rel = cg.Relation.from_image(t.pages(), t.stripes_array(), t.nodes_array(), [8])
-    with pytest.raises(capi.CitusGpuError) as e:
-        cg.Shard(rel)
-    assert e.value.code == capi.CG_EUNSUPPORTED
+    if oracle.lib().orc_have_zstd():
+        t = oracle.Table([8], compression=oracle.COMP_ZSTD)
+        t.insert([np.arange(50000) % 7])
+        rel = cg.Relation.from_image(t.pages(), t.stripes_array(), t.nodes_array(), [8])
+        with pytest.raises(capi.CitusGpuError) as e:
+            cg.Shard(rel)
+        assert e.value.code == capi.CG_EUNSUPPORTED
     rel = cg.Relation.write([8], [np.arange(10)])
     with pytest.raises(capi.CitusGpuError):
         cg.GpuColumnarAgg(cg.make_desc(aggs=[cg.sum_(3)]), rel.column_descs())     # column out of range

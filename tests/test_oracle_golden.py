@@ -182,7 +182,36 @@ def test_stripe_layout_and_page_framing(oracle):
     assert nd.decompressed_size == 4 * int((~nulls_b[:1000]).sum())
 
 
-@pytest.mark.parametrize("comp", ["lz4", "zstd"])
+def test_codec_stream_formats(oracle):
+    """hand-assembled streams of the two LZ77 formats the GPU decoder implements (the reference holds no
+    golden compressed buffers, so these pin the FORMAT, not an encoder)"""
+    # pglz: control byte 0b10 = [literal 'a'][tag len 9 off 1]; 8-byte ColumnarCompressHeader in front
+    body = bytes([0b00000010, 0x61, (0 << 4) | (9 - 3), 0x01])
+    total = len(body) + 8
+    hdr = ((total << 2) | 2).to_bytes(4, "little") + (10).to_bytes(4, "little")
+    assert oracle.codec_decompress(oracle.COMP_PGLZ, hdr + body, 10) == b"a" * 10
+    # a tag with the extension byte: len 18 + 7 = 25 copies of "ab" pattern (off 2)
+    body = bytes([0b00000100, 0x61, 0x62, (0 << 4) | 0x0f, 0x02, 7])
+    total = len(body) + 8
+    hdr = ((total << 2) | 2).to_bytes(4, "little") + (27).to_bytes(4, "little")
+    assert oracle.codec_decompress(oracle.COMP_PGLZ, hdr + body, 27) == (b"ab" * 14)[:27]
+    with pytest.raises(oracle.OracleError):     # VARSIZE must equal the buffer length
+        oracle.codec_decompress(oracle.COMP_PGLZ, hdr + body + b"\0", 27)
+    with pytest.raises(oracle.OracleError):     # check_complete: the stream must produce exactly rawsize bytes
+        oracle.codec_decompress(oracle.COMP_PGLZ, hdr[:4] + (28).to_bytes(4, "little") + body, 28)
+    if oracle.lib().orc_have_lz4():
+        # lz4 block: [token 1 literal | match 10-4]['a'][offset 1] [token 5 literals]['aaaaa']
+        blk = bytes([0x16, 0x61, 0x01, 0x00, 0x50]) + b"a" * 5
+        assert oracle.codec_decompress(oracle.COMP_LZ4, blk, 16) == b"a" * 16
+        # 300 literals need two length-extension bytes (15 + 255 + 30), then the stream ends
+        lit = bytes(range(256)) + bytes(range(44))
+        blk = bytes([0xF0, 255, 30]) + lit
+        assert oracle.codec_decompress(oracle.COMP_LZ4, blk, 300) == lit
+        with pytest.raises(oracle.OracleError):
+            oracle.codec_decompress(oracle.COMP_LZ4, blk, 299)
+
+
+@pytest.mark.parametrize("comp", ["lz4", "zstd", "pglz"])
 def test_compressed_roundtrip(oracle, comp):
     if comp == "lz4" and not oracle.lib().orc_have_lz4():
         pytest.skip("liblz4 missing")
@@ -192,7 +221,7 @@ def test_compressed_roundtrip(oracle, comp):
     n = 30000
     a = rng.integers(0, 50, n)
     b = np.arange(n)
-    t = oracle.Table([8, 8], compression=oracle.COMP_LZ4 if comp == "lz4" else oracle.COMP_ZSTD)
+    t = oracle.Table([8, 8], compression={"lz4": oracle.COMP_LZ4, "zstd": oracle.COMP_ZSTD, "pglz": oracle.COMP_PGLZ}[comp])
     t.insert([a, b])
     nodes = t.nodes()
     assert any(nd.compression_type != 0 and nd.value_length < nd.decompressed_size for nd in nodes)
