@@ -377,7 +377,7 @@ def run_ours(args, rank, world, local_rank):
                 partial.scan_relation(rels[s], want_stats=False)
             cgd.combine_partials(partial, dst=0)
             if rank == 0:
-                res = partial.fetch()         # device -> host read of the result rows
+                res = partial.fetch(reuse=True)   # device -> host read of the result rows, into caller-owned buffers
                 d2h = res["n"] * (9 + 8 * nw)
         e1.record()
         barrier()

@@ -314,20 +314,31 @@ class GpuColumnarAgg:
         check(lib().cg_partial_layout(self.h, C.byref(nw), ops, C.byref(dense), C.byref(cap)))
         return nw.value, [ops[i] for i in range(nw.value)], bool(dense.value), cap.value
 
-    def fetch(self):
-        """dict: keys, key_nulls, sum (python ints [ngroups][naggs]), count, minmax, fsum"""
-        n = self.ngroups()
+    def fetch(self, reuse=False):
+        """dict: keys, key_nulls, sum (python ints [ngroups][naggs]), count, minmax, fsum.
+        reuse=True returns views of buffers owned by this object (overwritten by the next fetch):
+        what a caller with its own result memory -- a tuplestore -- does"""
         na = max(self.naggs, 1)
-        keys = np.zeros(max(n, 1), np.int64)
-        kn = np.zeros(max(n, 1), np.uint8)
-        hi = np.zeros(max(n, 1) * na, np.int64)
-        lo = np.zeros(max(n, 1) * na, np.uint64)
-        cnt = np.zeros(max(n, 1) * na, np.int64)
-        mm = np.zeros(max(n, 1) * na, np.int64)
-        fs = np.zeros(max(n, 1) * na, np.float64)
-        got = C.c_int64()
-        check(lib().cg_partial_fetch(self.h, n, keys.ctypes.data, kn.ctypes.data, hi.ctypes.data, lo.ctypes.data,
-                                     cnt.ctypes.data, mm.ctypes.data, fs.ctypes.data, C.byref(got)))
+        bufs = getattr(self, "_fetch_bufs", None) if reuse else None
+        cap = bufs[0].shape[0] if bufs else 0
+        if not bufs:
+            cap = max(self.ngroups(), 1)
+        while True:
+            if not bufs or bufs[0].shape[0] < cap:
+                bufs = (np.zeros(cap, np.int64), np.zeros(cap, np.uint8), np.zeros(cap * na, np.int64),
+                        np.zeros(cap * na, np.uint64), np.zeros(cap * na, np.int64), np.zeros(cap * na, np.int64),
+                        np.zeros(cap * na, np.float64))
+            keys, kn, hi, lo, cnt, mm, fs = bufs
+            got = C.c_int64()
+            rc = lib().cg_partial_fetch(self.h, keys.shape[0], keys.ctypes.data, kn.ctypes.data, hi.ctypes.data, lo.ctypes.data,
+                                        cnt.ctypes.data, mm.ctypes.data, fs.ctypes.data, C.byref(got))
+            if rc != 0 and reuse and got.value > keys.shape[0]:      # cached buffers too small for this result: grow once
+                cap, bufs = got.value, None
+                continue
+            check(rc)
+            break
+        if reuse:
+            self._fetch_bufs = bufs
         n = got.value
         return dict(n=n, keys=keys[:n], key_nulls=kn[:n], sum_hi=hi[:n * na].reshape(n, na),
                     sum_lo=lo[:n * na].reshape(n, na), count=cnt[:n * na].reshape(n, na),

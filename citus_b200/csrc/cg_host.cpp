@@ -1383,14 +1383,29 @@ extern "C" int cg_partial_fetch(CgPartial *p, int64_t capacity, int64_t *keys, u
 	if ((int64_t) n > capacity)
 		return cg_set_error(CG_EINVAL, "%llu groups do not fit the caller's capacity %lld", n, (long long) capacity);
 	if (n == 0) return CG_OK;
-	std::vector<int64_t> hk(n);
-	std::vector<uint8_t> hn(n);
-	std::vector<uint64_t> hw((size_t) n * p->nwords);
-	CG_CUDA(cudaMemcpy(hk.data(), p->d_out_keys, n * sizeof(int64_t), cudaMemcpyDeviceToHost));
-	CG_CUDA(cudaMemcpy(hn.data(), p->d_out_nulls, n, cudaMemcpyDeviceToHost));
-	CG_CUDA(cudaMemcpy(hw.data(), p->d_out_words, (size_t) n * p->nwords * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-	int na = p->desc.naggs;
-	for (uint64_t i = 0; i < n; i++)
+	/* result rows come back through a pinned buffer owned by the partial (DMA at link rate,
+	 * no page faults on fresh memory), then are unpacked by the staging threads */
+	const size_t kbytes = (n * sizeof(int64_t) + 15) & ~15ull, nbytes = (n + 15) & ~15ull;
+	const size_t wbytes = (size_t) n * p->nwords * sizeof(uint64_t);
+	if (p->h_out_cap < kbytes + nbytes + wbytes)
+	{
+		if (p->h_out) cudaFreeHost(p->h_out);
+		p->h_out = nullptr; p->h_out_cap = 0;
+		size_t cap = kbytes + nbytes + wbytes + (1u << 16);
+		CG_CUDA(cudaHostAlloc((void **) &p->h_out, cap, cudaHostAllocDefault));
+		p->h_out_cap = cap;
+	}
+	const int64_t *hk = (const int64_t *) p->h_out;
+	const uint8_t *hn = p->h_out + kbytes;
+	const uint64_t *hw = (const uint64_t *) (p->h_out + kbytes + nbytes);
+	CG_CUDA(cudaMemcpyAsync((void *) hk, p->d_out_keys, n * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->compute));
+	CG_CUDA(cudaMemcpyAsync((void *) hn, p->d_out_nulls, n, cudaMemcpyDeviceToHost, ctx->compute));
+	CG_CUDA(cudaMemcpyAsync((void *) hw, p->d_out_words, wbytes, cudaMemcpyDeviceToHost, ctx->compute));
+	CG_CUDA(cudaStreamSynchronize(ctx->compute));
+	const int na = p->desc.naggs;
+	const int nthreads = n >= 65536 ? std::max(1, std::min(ctx->stage_threads, 16)) : 1;
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+	for (int64_t i = 0; i < (int64_t) n; i++)
 	{
 		if (keys) keys[i] = hk[i];
 		if (key_nulls) key_nulls[i] = hn[i];

@@ -269,6 +269,9 @@ struct CgPartial
 	uint8_t *d_out_nulls = nullptr;
 	unsigned long long *d_out_count = nullptr;
 	uint64_t out_capacity = 0;
+	/* pinned host buffer the result rows are fetched through */
+	uint8_t *h_out = nullptr;
+	size_t h_out_cap = 0;
 };
 
 /* cg_scan.cu */
