@@ -94,6 +94,10 @@ SYMBOLS = [
     ("cg_shutdown", None, []),
     ("cg_set_stream", C.c_int, [C.c_void_p]),
     ("cg_kernel_launches", C.c_uint64, []),
+    ("cg_jit_launches", C.c_uint64, []),
+    ("cg_jit_compiles", C.c_uint64, []),
+    ("cg_jit_compile_check", C.c_int, [C.POINTER(CgScanDesc), C.POINTER(CgColumnDesc), C.c_int32, C.c_int64, C.c_int64, C.c_int64,
+                                      C.POINTER(C.c_int32), C.c_char_p, C.c_size_t]),
     ("cg_numa_bind", C.c_int, [C.POINTER(C.c_int32)]),
     ("cg_numa_unbind", C.c_int, []),
     ("cg_profile_begin", C.c_int, []),

@@ -894,19 +894,13 @@ extern "C" int cg_scan_shard(const CgShard *sh, const CgScanDesc *desc, CgPartia
 		plan.nselected = (uint32_t) selected.size();
 		FPlan fast;
 		const bool use_small = cg_small_eligible(plan) && !cg_force_general();
-		bool use_fast = !use_small && !cg_force_general() && cg_build_fast_plan(desc, plan, all8, &fast);
-		uint32_t nfast = use_fast ? sh->sel_nfast : 0;
+		bool use_fast = !use_small && !cg_force_general() && cg_jit_level() < 2 && cg_build_fast_plan(desc, plan, all8, &fast);
+		/* the chunk groups without NULLs in the plan columns come first in the selection */
+		uint32_t nfast = sh->sel_nfast;
 		if (stats) CG_CUDA(cudaEventRecord(ctx->ev_a, ctx->compute));
 		rc = cg_prof_mark(ctx, ctx->compute);
 		if (rc) return rc;
-		if (use_small)
-		{
-			/* tiny key domain: shared-memory tables + warp-level pre-aggregation, all chunk groups */
-			rc = cg_launch_scan_small(ctx, plan, all8, ctx->compute);
-			if (rc) return rc;
-			nfast = plan.nselected;
-		}
-		else if (nfast > 0)
+		if (use_fast && nfast > 0)
 		{
 			fast.nselected = nfast;
 			rc = cg_launch_scan_fast(ctx, fast, ctx->compute);
@@ -914,11 +908,31 @@ extern "C" int cg_scan_shard(const CgShard *sh, const CgScanDesc *desc, CgPartia
 			rc = after_packed_launch(ctx, into, fast.packed != nullptr);
 			if (rc) return rc;
 		}
+		else if (nfast > 0 && !cg_force_general())
+		{
+			/* no ahead-of-time specialisation for this shape: the plan-specialised (NVRTC) kernel */
+			KPlan piece = plan;
+			piece.nselected = nfast;
+			bool launched = false, packed = false;
+			rc = cg_launch_scan_jit(ctx, piece, ctx->compute, &launched, &packed);
+			if (rc) return rc;
+			if (launched && packed)
+			{
+				into->packed_dirty = true;
+				rc = after_packed_launch(ctx, into, true);
+				if (rc) return rc;
+			}
+			if (!launched) nfast = 0;
+		}
+		else
+			nfast = 0;
 		if (nfast < plan.nselected)
 		{
+			/* chunk groups with NULLs (or everything, without the JIT): the interpretive kernels */
 			plan.selected = sh->d_selected + nfast;
 			plan.nselected -= nfast;
-			rc = cg_launch_scan(ctx, plan, true, all8, ctx->compute);
+			if (use_small) rc = cg_launch_scan_small(ctx, plan, all8, ctx->compute);
+			else rc = cg_launch_scan(ctx, plan, true, all8, ctx->compute);
 			if (rc) return rc;
 		}
 		rc = cg_prof_mark(ctx, ctx->compute);
@@ -1195,7 +1209,9 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 		plan.nstaged = (int32_t) ns;
 		FPlan fast;
 		const bool use_small = cg_small_eligible(plan) && !cg_force_general();
-		const bool use_fast = !use_small && !sp.any_nulls && !cg_force_general() && cg_build_fast_plan(desc, plan, all8, &fast);
+		const bool use_fast = !use_small && !sp.any_nulls && !cg_force_general() && cg_jit_level() < 2 &&
+							  cg_build_fast_plan(desc, plan, all8, &fast);
+		const bool try_jit = !use_fast && !sp.any_nulls && !cg_force_general();
 		if (stats) CG_CUDA(cudaEventRecord(ctx->ev_a, ctx->compute));
 		auto launch_block = [&](uint64_t cg0, uint64_t cg1, cudaEvent_t copied) -> int {
 			CG_CUDA(cudaStreamWaitEvent(ctx->compute, copied, 0));
@@ -1210,7 +1226,19 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 			}
 			r = cg_prof_mark(ctx, ctx->compute);
 			if (r) return r;
-			if (use_small)
+			bool jitted = false;
+			if (try_jit)
+			{
+				KPlan blk = plan;
+				blk.selected = d_ids + cg0;
+				blk.nselected = (uint32_t) (cg1 - cg0);
+				bool packed = false;
+				r = cg_launch_scan_jit(ctx, blk, ctx->compute, &jitted, &packed);
+				if (r) return r;
+				if (jitted && packed) into->packed_dirty = true;
+			}
+			if (jitted) { }
+			else if (use_small)
 			{
 				KPlan blk = plan;
 				blk.selected = d_ids + cg0;

@@ -142,6 +142,7 @@ struct KAgg
 	int64_t a[3];
 	int64_t b[3];
 	int64_t bound;      /* nlimbs == 1: every |term| must be <= bound */
+	int64_t tbound;     /* integer SUM: the caller-proven bound on |term| whatever nlimbs is (0 = unknown) */
 };
 
 struct KPlan
@@ -314,7 +315,13 @@ int cg_launch_export(CgPartial *p, uint64_t out_capacity, int64_t *d_keys, uint8
 int cg_launch_merge(CgPartial *p, const int64_t *d_keys, const uint8_t *d_nulls, const uint64_t *d_words,
 					int64_t nrows, cudaStream_t stream);
 
+/* cg_jit.cpp: plan-specialised kernels through NVRTC */
+int cg_jit_level(void);     /* CG_JIT: 0 = off, 1 = where no specialised ahead-of-time kernel applies (default), 2 = always */
+int cg_launch_scan_jit(CgContext *ctx, const KPlan &plan, cudaStream_t stream, bool *launched, bool *used_packed);
+
 /* cg_plan.cpp */
+int cg_partial_shape(CgPartial *p, const CgScanDesc *desc, const CgColumnDesc *columns, int32_t natts,
+					 int64_t key_min, int64_t key_max, int64_t max_rows);
 bool cg_build_fast_plan(const CgScanDesc *desc, const KPlan &plan, bool all8, FPlan *fast);
 int cg_build_plan(const CgScanDesc *desc, const CgColumnDesc *columns, int natts,
 				  const std::vector<int32_t> *slot_of_att, CgPartial *partial, KPlan *plan,

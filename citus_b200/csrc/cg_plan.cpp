@@ -105,6 +105,7 @@ static int layout_partial(CgPartial *p, const CgColumnDesc *columns)
 		k.is_float = (int8_t) (s.is_float != 0);
 		for (int f = 0; f < 3; f++) { k.a[f] = s.a[f]; k.b[f] = s.b[f]; }
 		k.nlimbs = 1;
+		k.tbound = (s.kind == CG_AGG_SUM && !s.is_float && s.term_abs_bound > 0) ? s.term_abs_bound : 0;
 		switch (s.kind)
 		{
 			case CG_AGG_COUNT_STAR:
@@ -144,22 +145,19 @@ static int layout_partial(CgPartial *p, const CgColumnDesc *columns)
 	return CG_OK;
 }
 
-extern "C" int cg_partial_create(const CgScanDesc *desc, const CgColumnDesc *columns, int32_t natts,
-								 int64_t key_min, int64_t key_max, int64_t max_rows, CgPartial **out)
+/* host-only part of cg_partial_create: accumulator layout, table kind and capacity */
+int cg_partial_shape(CgPartial *p, const CgScanDesc *desc, const CgColumnDesc *columns, int32_t natts,
+					 int64_t key_min, int64_t key_max, int64_t max_rows)
 {
-	CgContext *ctx = cg_ctx();
-	if (!ctx) return CG_EINVAL;
-	if (!desc || !columns || !out) return cg_set_error(CG_EINVAL, "NULL argument");
 	int rc = validate_desc(desc, columns, natts);
 	if (rc) return rc;
-	CgPartial *p = new CgPartial();
 	p->desc = *desc;
 	p->columns.assign(columns, columns + natts);
 	p->key_min = key_min;
 	p->key_max = key_max;
 	p->max_rows = max_rows;
 	rc = layout_partial(p, columns);
-	if (rc) { delete p; return rc; }
+	if (rc) return rc;
 
 	const uint64_t kDenseLimit = 1ull << 26;
 	if (desc->ngroup_cols == 0)
@@ -205,6 +203,18 @@ extern "C" int cg_partial_create(const CgScanDesc *desc, const CgColumnDesc *col
 		int s = 1; while (s < p->nwords) s <<= 1;
 		p->stride = s;
 	}
+	return CG_OK;
+}
+
+extern "C" int cg_partial_create(const CgScanDesc *desc, const CgColumnDesc *columns, int32_t natts,
+								 int64_t key_min, int64_t key_max, int64_t max_rows, CgPartial **out)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx) return CG_EINVAL;
+	if (!desc || !columns || !out) return cg_set_error(CG_EINVAL, "NULL argument");
+	CgPartial *p = new CgPartial();
+	int rc = cg_partial_shape(p, desc, columns, natts, key_min, key_max, max_rows);
+	if (rc) { delete p; return rc; }
 	size_t bytes = (size_t) p->entries * p->stride * sizeof(uint64_t);
 	size_t key_bytes = p->mode == CG_MODE_HASH ? (((size_t) p->entries * sizeof(int64_t) + 255) & ~(size_t) 255) : 0;
 	if (cudaMalloc(&p->d_table, bytes + key_bytes) != cudaSuccess)

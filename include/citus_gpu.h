@@ -53,6 +53,17 @@ int cg_profile_begin(void);
 int cg_profile_collect(int32_t *launches, double *total_ms, double *max_ms);
 /* number of CUDA kernels this library has launched so far (all kernels, all entry points) */
 uint64_t cg_kernel_launches(void);
+/* Plan-specialised kernels (cg_jit.cpp): query shapes without an ahead-of-time specialisation are
+ * written out as straight-line CUDA and compiled with NVRTC the first time they are seen (CG_JIT=0
+ * turns this off; the interpretive kernels then run everything).  Counters, and a GPU-less check that
+ * a query shape generates valid sm_100a code: kind = 0 plain aggregate / 1 shared-memory cells /
+ * 2 global table; source (may be NULL) receives the generated CUDA. */
+uint64_t cg_jit_launches(void);
+uint64_t cg_jit_compiles(void);
+struct CgScanDesc;
+struct CgColumnDesc;
+int cg_jit_compile_check(const struct CgScanDesc *desc, const struct CgColumnDesc *columns, int32_t natts, int64_t key_min,
+						 int64_t key_max, int64_t max_rows, int32_t *kind, char *source, size_t source_len);
 /* Pin the calling thread (and threads it creates afterwards: the staging threads) to the CPUs
  * of the device's NUMA node, so that host pages it first-touches and the DMA reads of them stay
  * on the socket the GPU hangs off.  *node = the node, or -1 when nothing was changed (single

@@ -193,3 +193,48 @@ def test_numeric_text_goldens(cg, expected, oracle):
         c = int(rng.integers(1, 10**9))
         assert cg.numeric_div_out(v, s, c) == oracle.numeric_div_str(v, s, c, 0), (v, s, c)
         assert cg.numeric_out(v, s) == oracle.numeric_str(v, s)
+
+
+# --------------------------------------------------------------------------- plan-specialised kernels (NVRTC)
+def _jit_check(cg, quals, group, aggs, lens, kmin, kmax, rows, float_cols=()):
+    from citus_b200 import capi
+    d = cg.make_desc(quals, group, aggs, float_cols=float_cols)
+    cols = (capi.CgColumnDesc * len(lens))()
+    for i, l in enumerate(lens):
+        cols[i].attlen, cols[i].type_class = l, (1 if i in float_cols else 0)
+    kind = C.c_int32(-1)
+    buf = C.create_string_buffer(1 << 18)
+    rc = capi.lib().cg_jit_compile_check(C.byref(d), cols, len(lens), kmin, kmax, rows, C.byref(kind), buf, len(buf))
+    assert rc == 0, capi.lib().cg_last_error().decode()
+    return kind.value, buf.value.decode()
+
+
+def test_jit_generates_valid_sm100a_code_for_every_plan_form(cg):
+    """cg_jit.cpp: the CUDA generated for a query shape compiles (NVRTC cross-compiles without a GPU);
+    the struct text inside it must match the host's KPlan (static_assert on the sizes)"""
+    try:
+        C.CDLL("libnvrtc.so.12")
+    except OSError:
+        pytest.skip("libnvrtc missing")
+    # C2 shape: direct-indexed table in global memory
+    kind, src = _jit_check(cg, [(1, "<", 50)], [0], [cg.sum_(2), cg.count_star()], [8] * 8, 0, 999_999, 10**9)
+    assert kind == 2 and "red_add(e" in src and "cg_jit_scan" in src
+    # hash table, min/max, <> qual
+    kind, src = _jit_check(cg, [(1, "<", 50), (3, "<>", 7)], [0], [cg.sum_(2), cg.count_star(), cg.min_(2), cg.max_(3)],
+                           [8] * 8, 0, -1, 10**9)
+    assert kind == 2 and "hash_slot_slow(P, key, h)" in src and "atomicMin" in src
+    # plain aggregate over mixed widths: thread registers + warp shuffles
+    kind, src = _jit_check(cg, [(1, "<", 50)], [], [cg.sum_(2), cg.count_star(), cg.count(3), cg.min_(4), cg.max_(5)],
+                           [8, 4, 2, 1, 8, 8], 0, -1, 10**9)
+    assert kind == 0 and "__shfl_xor_sync" in src
+    # TPC-H Q1 shape: 6 slots x (rows + 5 bounded sums) -> one shared-memory cell per lane and word
+    q1 = [cg.sum_(0), cg.sum_(1), cg.Agg(2, [(1, 0, 1), (2, 100, -1)]), cg.Agg(2, [(1, 0, 1), (2, 100, -1), (3, 100, 1)]),
+          cg.sum_(2), cg.count_star()]
+    for a, b in zip(q1, (5100, 10_500_000, 10**9, 2 * 10**11, 11, 0)):
+        a.term_abs_bound = b
+    kind, src = _jit_check(cg, [(6, "<=", -486)], [4, 5], q1, [8, 8, 8, 8, 1, 1, 4, 4], 65 | (70 << 32), 67 | (71 << 32), 6 * 10**8)
+    assert kind == 1 and "s_acc" in src and "P.aggs[3].b[2]" in src
+    # float4 / float8 columns: btree comparison with NaN ordering, ordered min/max
+    kind, src = _jit_check(cg, [(1, ">=", 0)], [0], [cg.sum_(1, True), cg.min_(1, True), cg.max_(2, True), cg.count_star()],
+                           [4, 8, 4], 0, 10**6, 10**6, float_cols=(1, 2))
+    assert "fcmp(v" in src and "f8_ordered" in src and "__uint_as_float" in src
