@@ -61,6 +61,8 @@ def parse():
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--pageable", action="store_true", help="e2e from pageable host pages (host de-framing) instead of pinned pages (DMA)")
     p.add_argument("--gen-threads", type=int, default=0)
+    p.add_argument("--compression", default="none", choices=["none", "lz4"],
+                   help="columnar.compression of the synthetic shards (BASELINE configs use none; lz4 exercises the GPU decoder)")
     p.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to the CPUs of its GPU's NUMA node")
     return p.parse_args()
 
@@ -192,7 +194,9 @@ def run_reference(args, rank, world):
     from citus_b200 import columnar as cg     # host-side generator only (no GPU call)
     rows_per_shard = args.rows // NSHARDS
     ncpu = os.cpu_count() or 8
+    cg.set_writer_compression(args.compression)
     rels = generate_shards(cg, range(NSHARDS), rows_per_shard, args.gen_threads or min(64, ncpu))
+    cg.set_writer_compression("none")
     nthreads = min(NSHARDS, max(1, ncpu // 2))
     budget = 12.0
     times = []
@@ -223,7 +227,7 @@ def run_reference(args, rank, world):
 def workload_config(args, where):
     return {"workload": "C2: 32 columnar shards, 1B rows x 8 int8 cols, WHERE f<50 GROUP BY key (1M keys), sum(v), count(*)",
             "rows": args.rows, "shards": NSHARDS, "stripe_row_limit": STRIPE_ROWS, "chunk_group_row_limit": CHUNK_ROWS,
-            "groups": NKEYS, "selectivity": 0.5, "compression": "none", "parallelism": where,
+            "groups": NKEYS, "selectivity": 0.5, "compression": args.compression, "parallelism": where,
             "l2_policy": "inputs (24.4 GB/step) are far larger than the 126 MB L2; no explicit flush"}
 
 
@@ -251,7 +255,9 @@ def run_ours(args, rank, world, local_rank):
     my_shards = cgd.shards_of_rank(NSHARDS, rank, world)
     ncpu = os.cpu_count() or 8
     gen_threads = args.gen_threads or max(4, min(64, ncpu // max(world, 1)))
+    cg.set_writer_compression(args.compression)
     rels = generate_shards(cg, my_shards, rows_per_shard, gen_threads)
+    cg.set_writer_compression("none")
 
     aggs = [cg.sum_(2), cg.count_star()]
     desc = cg.make_desc(QUALS, GROUP, aggs)

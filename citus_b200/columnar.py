@@ -139,10 +139,13 @@ class Relation:
             self._registered = False
 
     def __del__(self):
-        self.unregister()
-        if getattr(self, "_gen", None):
-            lib().cg_gen_relation_free(self._gen)
-            self._gen = None
+        try:
+            self.unregister()
+            if getattr(self, "_gen", None):
+                lib().cg_gen_relation_free(self._gen)
+                self._gen = None
+        except TypeError:           # interpreter shutdown: module globals are already gone
+            pass
 
     # -- accessors ----------------------------------------------------------
     @property
@@ -285,7 +288,11 @@ class GpuColumnarAgg:
             lib().cg_partial_free(self.h)
             self.h = None
 
-    __del__ = free
+    def __del__(self):
+        try:
+            self.free()
+        except TypeError:           # interpreter shutdown
+            pass
 
     def reset(self):
         check(lib().cg_partial_reset(self.h))
@@ -394,6 +401,23 @@ def worker_partition_query_result(d_keys_ptr, d_nulls_ptr, n, key_len, method, m
         raise capi.CitusGpuError(capi.CG_EINVAL, "min values and max values must have the same number of elements")
     check(lib().cg_partition_index(d_keys_ptr, d_nulls_ptr, n, key_len, 1 if method == "hash" else 0,
                                    mins.ctypes.data, maxs.ctypes.data, len(mins), d_index_ptr, d_counts_ptr))
+
+
+def set_writer_compression(name: str):
+    """columnar.compression for Relation.generate / Relation.write: "none" or "lz4"""
+    check(lib().cg_gen_set_compression({"none": 0, "lz4": 2}[name]))
+
+
+def partition_copy_bytes(d_index_ptr, n, P, d_col_ptrs, col_lens, binary, d_null_ptrs=None, generate_empty_results=False):
+    """(rows_written[P], bytes_written[P]) of worker_partition_query_result's return rows"""
+    cols = (C.c_void_p * len(d_col_ptrs))(*d_col_ptrs)
+    nulls = (C.c_void_p * len(d_col_ptrs))(*(d_null_ptrs or [None] * len(d_col_ptrs)))
+    lens = (C.c_int32 * len(d_col_ptrs))(*col_lens)
+    rows = np.zeros(P, np.int64)
+    nbytes = np.zeros(P, np.int64)
+    check(lib().cg_partition_copy_bytes(d_index_ptr, n, P, cols, nulls, lens, len(d_col_ptrs), 1 if binary else 0,
+                                        1 if generate_empty_results else 0, rows.ctypes.data, nbytes.ctypes.data))
+    return rows, nbytes
 
 
 def partition_scatter(d_index_ptr, n, P, d_col_ptrs, d_out_ptrs, order=None):

@@ -20,13 +20,17 @@
  * The exists bitmap is never compressed (columnar_writer.c:606-653); zstd chunks are refused at
  * staging (CG_EUNSUPPORTED).
  *
- * One warp decodes one chunk buffer (a C2 relation has ~10^5 of them per column, so the grid
- * is wide).  The compressed stream is pulled through a 256-byte shared-memory ring per warp
- * (aligned 4-byte loads, one refill per 128 bytes consumed), so tokens, lengths and offsets are
- * shared-memory broadcasts instead of dependent global loads.  A match of any length and any
- * overlap is copied in parallel: byte i of the match is out[pos - off + (i mod off)], which
- * only reads bytes written before the match began.  Lanes communicate through the output buffer,
- * ordered by __syncwarp().
+ * Eight lanes decode one chunk buffer, four streams per warp (a C2 relation has ~10^5 streams per
+ * column, so the grid is wide; sequences of columnar value streams are a few bytes long, so
+ * eight lanes fill a copy and a full warp per stream only wastes issue slots: 37 -> see
+ * profiles/).  A stream is a chain of dependent steps -- token, lengths, literal copy, offset,
+ * match copy -- so its rate is set by the latency of one step; both ends of the copy therefore
+ * stay in shared memory: the compressed stream is pulled through a 256-byte ring per stream
+ * (aligned 16-byte loads, one refill per 128 bytes consumed) and the decoded bytes go through a
+ * 2 KB window per stream that is written to the arena in aligned 16-byte vectors (see struct Out).
+ * A match of any length and any overlap is copied in parallel: byte i of the match is
+ * out[pos - off + (i mod off)], which only reads bytes written before the match began.  Lanes
+ * communicate through shared memory, ordered by __syncwarp(group mask).
  *
  * A malformed stream never writes outside the item's slot; it raises `flag` in *err and the
  * host reports CG_ECORRUPT ("cannot decompress the buffer") at its next synchronisation.
@@ -34,7 +38,11 @@
 #include "cg_internal.h"
 
 #define CGD_WARPS 4
+#define CGD_GROUP 8u                    /* lanes per stream */
+#define CGD_GROUPS (32u / CGD_GROUP)    /* streams per warp */
 #define CGD_RING 256u
+#define CGD_WIN 2048u
+#define CGD_CHUNK 256u
 
 struct Stream
 {
@@ -43,60 +51,127 @@ struct Stream
 	uint32_t loadable;      /* bytes that may be read (the slot, a multiple of 16) */
 	uint32_t base;          /* ring holds [base, base + CGD_RING) */
 	volatile uint8_t *ring;
-	int lane;
+	uint32_t glane, mask;   /* lane inside the group, the group's lanes */
 
 	__device__ __forceinline__ void fill(uint32_t from)   /* 128 bytes at stream position `from` */
 	{
-		uint32_t p = from + 4u * lane;
-		uint32_t w = p < loadable ? *(const uint32_t *) (src + p) : 0u;
-		*(volatile uint32_t *) (ring + (p & (CGD_RING - 1))) = w;
+		uint32_t p = from + 16u * glane;
+		uint4 w = make_uint4(0, 0, 0, 0);
+		if (p < loadable) w = *(const uint4 *) (src + p);
+		*(uint4 *) ((uint8_t *) ring + (p & (CGD_RING - 1))) = w;
 	}
 	__device__ __forceinline__ void open()
 	{
 		base = 0;
 		fill(0);
 		fill(128);
-		__syncwarp();
+		__syncwarp(mask);
 	}
 	/* after the call [ip, ip + 128) is in the ring */
 	__device__ __forceinline__ void ensure(uint32_t ip)
 	{
 		while (ip >= base + 128u)
 		{
-			__syncwarp();                 /* every lane is done reading the half being replaced */
+			__syncwarp(mask);             /* every lane is done reading the half being replaced */
 			fill(base + CGD_RING);
 			base += 128u;
-			__syncwarp();
+			__syncwarp(mask);
 		}
 	}
 	__device__ __forceinline__ uint32_t at(uint32_t p) const { return ring[p & (CGD_RING - 1)]; }
 };
 
-/* out[op .. op + n) = the n bytes at stream position ip (n may be large) */
-__device__ __forceinline__ void copy_literals(Stream &s, uint32_t ip, uint8_t *out, uint32_t op, uint32_t n)
+/*
+ * The output goes through a per-stream window in shared memory: the last CGD_WIN bytes of the
+ * decoded stream live in a ring, matches whose source is still in the ring are shared-memory
+ * copies (the common case: columnar value streams repeat at distances of a few values), and the
+ * ring is written to the arena in aligned 16-byte vectors when it is full.  Only a match that
+ * reaches further back than the ring reads the arena (after a flush).
+ */
+struct Out
+{
+	volatile uint8_t *ring;
+	uint8_t *dst;           /* 16-byte aligned arena slot */
+	uint32_t op;            /* bytes decoded so far */
+	uint32_t flushed;       /* bytes already in dst (multiple of 16) */
+	uint32_t glane, mask;
+
+	/* ring -> dst for [flushed, upto & ~15) */
+	__device__ __forceinline__ void flush(uint32_t upto)
+	{
+		upto &= ~15u;
+		__syncwarp(mask);                 /* every lane has finished writing the ring */
+		for (uint32_t pos = flushed + 16u * glane; pos < upto; pos += 16u * CGD_GROUP)
+			*(uint4 *) (dst + pos) = *(const uint4 *) ((const uint8_t *) ring + (pos & (CGD_WIN - 1)));
+		flushed = upto;
+		__syncwarp(mask);                 /* the flushed part of the ring may be overwritten from here on */
+	}
+	/* before writing m more bytes (m <= CGD_CHUNK): nothing unflushed may be overwritten */
+	__device__ __forceinline__ void make_room(uint32_t m)
+	{
+		if (op + m - flushed > CGD_WIN) flush(op);
+	}
+};
+
+/* the n bytes at stream position ip (n may be large) */
+__device__ __forceinline__ void put_literals(Stream &s, Out &o, uint32_t ip, uint32_t n)
 {
 	while (n)
 	{
 		s.ensure(ip);
-		uint32_t m = min(n, s.base + CGD_RING - ip);
-		for (uint32_t i = s.lane; i < m; i += 32) out[op + i] = (uint8_t) s.at(ip + i);
-		ip += m; op += m; n -= m;
+		uint32_t m = min(min(n, s.base + CGD_RING - ip), CGD_CHUNK);
+		o.make_room(m);
+		for (uint32_t i = o.glane; i < m; i += CGD_GROUP) o.ring[(o.op + i) & (CGD_WIN - 1)] = (uint8_t) s.at(ip + i);
+		ip += m; o.op += m; n -= m;
 	}
 }
 
-/* out[op .. op + n) = out[op - off ...] with LZ77 overlap semantics */
-__device__ __forceinline__ void copy_match(uint8_t *out, uint32_t op, uint32_t off, uint32_t n, int lane)
+/* n bytes starting `off` bytes back, LZ77 overlap semantics: byte i is out[op - off + (i mod off)] */
+__device__ __forceinline__ void put_match(Out &o, uint32_t off, uint32_t n)
 {
-	const uint8_t *m = out + op - off;
-	if (off >= n)
-		for (uint32_t i = lane; i < n; i += 32) out[op + i] = m[i];
-	else
-		for (uint32_t i = lane; i < n; i += 32) out[op + i] = m[i % off];
+	/* i mod off for i = glane, glane + 8, ... kept incrementally (no division) */
+	uint32_t k0 = o.glane, step = CGD_GROUP;
+	if (off <= CGD_GROUP)
+	{
+		while (k0 >= off) k0 -= off;
+		while (step >= off) step -= off;
+	}
+	while (n)
+	{
+		const uint32_t m = min(n, CGD_CHUNK);
+		o.make_room(m);
+		uint32_t k = k0;
+		if (off + m <= CGD_WIN)
+		{
+			__syncwarp(o.mask);                          /* the bytes the match reads are in the ring */
+			const uint32_t from = o.op - off;
+			for (uint32_t i = o.glane; i < m; i += CGD_GROUP)
+			{
+				o.ring[(o.op + i) & (CGD_WIN - 1)] = o.ring[(from + k) & (CGD_WIN - 1)];
+				k += step; if (k >= off) k -= off;
+			}
+		}
+		else
+		{
+			/* far match: its source left the ring long ago and is in the arena once the ring is flushed
+			 * (off > CGD_WIN - CGD_CHUNK, so the source ends before the unflushed tail) */
+			o.flush(o.op);
+			const uint8_t *from = o.dst + (o.op - off);
+			for (uint32_t i = o.glane; i < m; i += CGD_GROUP)
+			{
+				o.ring[(o.op + i) & (CGD_WIN - 1)] = from[k];
+				k += step; if (k >= off) k -= off;
+			}
+		}
+		o.op += m; n -= m;
+		__syncwarp(o.mask);               /* no lane runs ahead and overwrites ring bytes another lane still reads */
+		/* a chunk that overlaps itself continues the same periodic pattern: (i + m) mod off */
+	}
 }
 
-static __device__ bool lz4_block(Stream &s, uint8_t *out, uint32_t rawlen)
+static __device__ bool lz4_block(Stream &s, Out &o, uint32_t rawlen)
 {
-	uint32_t ip = 0, op = 0;
+	uint32_t ip = 0;
 	const uint32_t clen = s.len;
 	if (clen == 0) return false;
 	for (;;)
@@ -117,9 +192,9 @@ static __device__ bool lz4_block(Stream &s, uint8_t *out, uint32_t rawlen)
 				if (lit > rawlen) return false;
 			} while (b == 255);
 		}
-		if (lit > clen - ip || lit > rawlen - op) return false;
-		copy_literals(s, ip, out, op, lit);
-		ip += lit; op += lit;
+		if (lit > clen - ip || lit > rawlen - o.op) return false;
+		put_literals(s, o, ip, lit);
+		ip += lit;
 		if (ip == clen) break;                       /* the last sequence stops after its literals */
 		s.ensure(ip);
 		if (clen - ip < 2) return false;
@@ -139,16 +214,13 @@ static __device__ bool lz4_block(Stream &s, uint8_t *out, uint32_t rawlen)
 			} while (b == 255);
 		}
 		ml += 4;
-		if (off == 0 || off > op || ml > rawlen - op) return false;
-		__syncwarp();                                /* the bytes the match reads are visible */
-		copy_match(out, op, off, ml, s.lane);
-		op += ml;
-		__syncwarp();
+		if (off == 0 || off > o.op || ml > rawlen - o.op) return false;
+		put_match(o, off, ml);
 	}
-	return op == rawlen;
+	return o.op == rawlen;
 }
 
-static __device__ bool pglz_stream(Stream &s, uint8_t *out, uint32_t rawlen)
+static __device__ bool pglz_stream(Stream &s, Out &o, uint32_t rawlen)
 {
 	/* ColumnarCompressHeader: int32 vl_len_ (4-byte varlena header, little endian: length << 2 | flags), int32 rawsize */
 	if (s.len < 8) return false;
@@ -156,13 +228,13 @@ static __device__ bool pglz_stream(Stream &s, uint8_t *out, uint32_t rawlen)
 	uint32_t raw = s.at(4) | (s.at(5) << 8) | (s.at(6) << 16) | (s.at(7) << 24);
 	if (((hdr >> 2) & 0x3FFFFFFFu) != s.len) return false;     /* compressedDataSize + HDRSZ != buffer->len */
 	if (raw != rawlen) return false;
-	uint32_t sp = 8, dp = 0;
+	uint32_t sp = 8;
 	const uint32_t srcend = s.len;
-	while (sp < srcend && dp < rawlen)
+	while (sp < srcend && o.op < rawlen)
 	{
 		s.ensure(sp);
 		uint32_t ctrl = s.at(sp++);
-		for (int c = 0; c < 8 && sp < srcend && dp < rawlen; c++, ctrl >>= 1)
+		for (int c = 0; c < 8 && sp < srcend && o.op < rawlen; c++, ctrl >>= 1)
 		{
 			s.ensure(sp);
 			if (ctrl & 1)
@@ -172,54 +244,71 @@ static __device__ bool pglz_stream(Stream &s, uint8_t *out, uint32_t rawlen)
 				uint32_t off = ((b0 & 0xf0) << 4) | b1;
 				sp += 2;
 				if (len == 18) len += s.at(sp++);
-				if (sp > srcend || off == 0 || off > dp) return false;
-				len = min(len, rawlen - dp);
-				__syncwarp();
-				copy_match(out, dp, off, len, s.lane);
-				dp += len;
-				__syncwarp();
+				if (sp > srcend || off == 0 || off > o.op) return false;
+				len = min(len, rawlen - o.op);
+				put_match(o, off, len);
 			}
 			else
 			{
-				if (s.lane == 0) out[dp] = (uint8_t) s.at(sp);
-				sp++; dp++;
+				o.make_room(1);
+				if (o.glane == 0) o.ring[o.op & (CGD_WIN - 1)] = (uint8_t) s.at(sp);
+				sp++; o.op++;
 			}
 		}
 	}
-	return dp == rawlen && sp == srcend;             /* check_complete */
+	return o.op == rawlen && sp == srcend;           /* check_complete */
 }
 
+/* The four groups of a warp run the same code on different streams.  Their masks are run-time
+ * values on purpose: giving each group its own copy of the code with a constant mask (one WARPSYNC
+ * per barrier instead of a MATCH/VOTE sequence) made the groups diverge for good and was 10x slower
+ * (124 ms vs 11.7 ms per 9375-stream shard); with one copy the groups mostly stay converged. */
 __global__ void __launch_bounds__(CGD_WARPS * 32)
 cg_decompress_kernel(uint8_t *arena, const DecodeItem *items, uint32_t nitems, unsigned long long *err,
 					 unsigned long long flag)
 {
-	__shared__ __align__(16) uint8_t rings[CGD_WARPS][CGD_RING];
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const uint32_t idx = blockIdx.x * CGD_WARPS + warp;
+	__shared__ __align__(16) uint8_t rings[CGD_WARPS * CGD_GROUPS][CGD_RING];
+	__shared__ __align__(16) uint8_t wins[CGD_WARPS * CGD_GROUPS][CGD_WIN];
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t group = threadIdx.x / CGD_GROUP;                 /* within the CTA */
+	const uint32_t idx = blockIdx.x * (CGD_WARPS * CGD_GROUPS) + group;
 	if (idx >= nitems) return;
 	const DecodeItem it = items[idx];
 	Stream s;
 	s.src = arena + it.src;
 	s.len = it.comp_len;
 	s.loadable = (it.comp_len + 15u) & ~15u;
-	s.ring = rings[warp];
-	s.lane = lane;
+	s.ring = rings[group];
+	s.glane = lane % CGD_GROUP;
+	s.mask = ((1u << CGD_GROUP) - 1u) << (lane - s.glane);
 	s.open();
-	uint8_t *out = arena + it.dst;
+	Out o;
+	o.ring = wins[group];
+	o.dst = arena + it.dst;
+	o.op = 0;
+	o.flushed = 0;
+	o.glane = s.glane;
+	o.mask = s.mask;
 	bool ok;
-	if (it.kind == CG_COMPRESSION_LZ4) ok = lz4_block(s, out, it.raw_len);
-	else if (it.kind == CG_COMPRESSION_PGLZ) ok = pglz_stream(s, out, it.raw_len);
+	if (it.kind == CG_COMPRESSION_LZ4) ok = lz4_block(s, o, it.raw_len);
+	else if (it.kind == CG_COMPRESSION_PGLZ) ok = pglz_stream(s, o, it.raw_len);
 	else ok = false;
-	/* the slot's padding is zero, like every other arena slot */
-	for (uint32_t i = it.raw_len + lane; i < it.padded; i += 32) out[i] = 0;
-	if (!ok && lane == 0) atomicOr(err, flag);
+	if (ok)
+	{
+		/* what is left in the ring, then the slot's zero padding (like every other arena slot) */
+		o.flush(o.op);
+		for (uint32_t i = o.flushed + o.glane; i < it.raw_len; i += CGD_GROUP) o.dst[i] = o.ring[i & (CGD_WIN - 1)];
+	}
+	for (uint32_t i = (ok ? it.raw_len : 0u) + o.glane; i < it.padded; i += CGD_GROUP) o.dst[i] = 0;
+	if (!ok && o.glane == 0) atomicOr(err, flag);
 }
 
 int cg_launch_decompress(uint8_t *arena, const DecodeItem *items, uint64_t nitems, unsigned long long *err,
 						 unsigned long long flag, cudaStream_t stream)
 {
 	if (nitems == 0) return CG_OK;
-	unsigned blocks = (unsigned) ((nitems + CGD_WARPS - 1) / CGD_WARPS);
+	const unsigned per_block = CGD_WARPS * CGD_GROUPS;
+	unsigned blocks = (unsigned) ((nitems + per_block - 1) / per_block);
 	cg_decompress_kernel<<<blocks, CGD_WARPS * 32, 0, stream>>>(arena, items, (uint32_t) nitems, err, flag);
 	CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	return CG_OK;

@@ -1,7 +1,9 @@
 /*
  * cg_gen.cpp -- writes columnar relation images (bench / test tooling).
  *
- * Produces exactly the bytes the reference's writer would for compression = none:
+ * Produces exactly the bytes the reference's writer would for compression = none, and for
+ * compression = lz4 when liblz4 is the library the reference links (value streams go through
+ * the same LZ4_compress_default, columnar_compression.c:75-97):
  *   exists bitmap   SerializeBoolArray       backend/columnar/columnar_writer.c:523-545
  *   value stream    SerializeSingleDatum     :555-585 (store_att_byval, NULL rows take no bytes)
  *   stripe layout   FlushStripe              :425-502 (per column: all exists buffers, then all
@@ -15,6 +17,7 @@
  * oracle's independent row-at-a-time reader and compares them byte for byte with the
  * oracle's writer.
  */
+#include <dlfcn.h>
 #include <omp.h>
 #include <stdlib.h>
 #include <string.h>
@@ -22,6 +25,28 @@
 #include <algorithm>
 
 #include "cg_internal.h"
+
+/* liblz4 through dlopen (its header is not installed): the same LZ4_compress_default the reference's
+ * CompressBuffer calls (columnar_compression.c:75-97), so the bytes are the reference writer's */
+typedef int (*lz4_bound_fn)(int);
+typedef int (*lz4_comp_fn)(const char *, char *, int, int);
+static lz4_bound_fn g_lz4_bound;
+static lz4_comp_fn g_lz4_compress;
+static bool load_lz4()
+{
+	static int state = 0;
+	if (state == 0)
+	{
+		void *h = dlopen("liblz4.so.1", RTLD_NOW);
+		if (h)
+		{
+			g_lz4_bound = (lz4_bound_fn) dlsym(h, "LZ4_compressBound");
+			g_lz4_compress = (lz4_comp_fn) dlsym(h, "LZ4_compress_default");
+		}
+		state = (g_lz4_bound && g_lz4_compress) ? 1 : -1;
+	}
+	return state == 1;
+}
 
 struct CgGenRelation
 {
@@ -31,6 +56,8 @@ struct CgGenRelation
 	std::vector<CgStripe> stripes;
 	std::vector<CgSkipNode> nodes;
 };
+
+static int g_gen_compression = CG_COMPRESSION_NONE;
 
 static inline uint64_t splitmix64(uint64_t x)
 {
@@ -95,10 +122,68 @@ static void init_page_header(uint8_t *page, uint16_t pd_lower)
 	memcpy(page + 18, &psv, 2);
 }
 
+/* one column chunk: exists bitmap (SerializeBoolArray :523-545), NULL-compacted value stream
+ * (SerializeSingleDatum :555-585) and the skip node's min/max (UpdateChunkSkipNodeMinMax :663-718).
+ * n.row_count is set by the caller; returns the number of value bytes written to vbuf. */
+template <typename Source>
+static uint64_t encode_chunk(const Source &src, int c, int len, bool isf, uint64_t c0, CgSkipNode &n, uint8_t *ebuf, uint8_t *vbuf)
+{
+	uint32_t rows = (uint32_t) n.row_count;
+	memset(ebuf, 0, n.exists_length);
+	uint8_t *vp = vbuf;
+	bool has = false;
+	int64_t mn = 0, mx = 0;
+	double fmn = 0, fmx = 0;
+	const bool nullable = src.nullable(c);
+	for (uint32_t i = 0; i < rows; i++)
+	{
+		if (nullable && src.isnull(c, c0 + i)) continue;
+		ebuf[i >> 3] |= (uint8_t) (1u << (i & 7));
+		int64_t v = src.value(c, c0 + i);
+		if (isf)
+		{
+			double d;
+			memcpy(&d, &v, 8);
+			if (len == 4) { float f = (float) d; memcpy(vp, &f, 4); d = f; }
+			else memcpy(vp, &d, 8);
+			/* float8 btree order: NaN above everything */
+			auto fcmp = [](double x, double y) {
+				bool xn = x != x, yn = y != y;
+				if (xn || yn) return (int) xn - (int) yn;
+				return (int) (x > y) - (int) (x < y);
+			};
+			if (!has) { fmn = fmx = d; has = true; }
+			else
+			{
+				if (fcmp(d, fmn) < 0) fmn = d;
+				if (fcmp(d, fmx) > 0) fmx = d;
+			}
+		}
+		else
+		{
+			memcpy(vp, &v, (size_t) len);
+			if (!has) { mn = mx = v; has = true; }
+			else { if (v < mn) mn = v; if (v > mx) mx = v; }
+		}
+		vp += len;
+	}
+	n.has_minmax = has ? 1 : 0;
+	if (has)
+	{
+		if (isf) { memcpy(&n.min_value, &fmn, 8); memcpy(&n.max_value, &fmx, 8); }
+		else { n.min_value = mn; n.max_value = mx; }
+	}
+	return (uint64_t) (vp - vbuf);
+}
+
 template <typename Source>
 static int write_relation(const Source &src, const CgColumnDesc *cols, int natts, uint64_t nrows,
-						  uint64_t stripe_row_limit, uint32_t chunk_row_limit, int nthreads, CgGenRelation **out)
+						  uint64_t stripe_row_limit, uint32_t chunk_row_limit, int nthreads, int compression, CgGenRelation **out)
 {
+	if (compression != CG_COMPRESSION_NONE && compression != CG_COMPRESSION_LZ4)
+		return cg_set_error(CG_EUNSUPPORTED, "the shard writer compresses with none or lz4");
+	if (compression == CG_COMPRESSION_LZ4 && !load_lz4())
+		return cg_set_error(CG_EUNSUPPORTED, "liblz4.so.1 is not available");
 	if (natts <= 0 || natts > 256) return cg_set_error(CG_EINVAL, "natts %d", natts);
 	/* include/columnar/columnar.h:42-45 limits */
 	if (stripe_row_limit < 1000 || stripe_row_limit > 10000000) return cg_set_error(CG_EINVAL, "stripe_row_limit out of range");
@@ -135,44 +220,105 @@ static int write_relation(const Source &src, const CgColumnDesc *cols, int natts
 	if (total_nodes > 0x7fffffffull) { delete g; return cg_set_error(CG_EUNSUPPORTED, "too many chunks"); }
 	g->nodes.resize(total_nodes);
 
-	/* pass 1: value counts per (stripe, column, chunk) -> sizes and offsets */
-#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
-	for (int64_t s = 0; s < (int64_t) nstripes; s++)
+	/* compressed relations: every chunk is encoded and compressed first (its size decides the
+	 * layout, columnar_writer.c:590-654: the value buffer is replaced by the compressor's output
+	 * whenever CompressBuffer succeeds, even if that is larger); the stripe's bytes wait in
+	 * `staged` until the offsets are known */
+	std::vector<std::vector<uint8_t>> staged(compression != CG_COMPRESSION_NONE ? nstripes : 0);
+	if (compression != CG_COMPRESSION_NONE)
 	{
-		CgStripe &st = g->stripes[s];
-		uint64_t r0 = (uint64_t) s * stripe_row_limit;
-		uint64_t off = 0;
-		for (int c = 0; c < natts; c++)
+#pragma omp parallel num_threads(nthreads)
 		{
-			for (uint32_t k = 0; k < st.chunk_count; k++)
+			std::vector<uint8_t> vbuf((size_t) chunk_row_limit * 8 + 16), ebuf(chunk_row_limit / 8 + 16);
+			std::vector<uint8_t> cbuf((size_t) g_lz4_bound((int) chunk_row_limit * 8) + 16);
+#pragma omp for schedule(dynamic, 1)
+			for (int64_t s = 0; s < (int64_t) nstripes; s++)
 			{
-				CgSkipNode &n = g->nodes[st.skipnode_base + (uint32_t) c * st.chunk_count + k];
-				memset(&n, 0, sizeof n);
-				uint64_t c0 = r0 + (uint64_t) k * chunk_row_limit;
-				uint64_t c1 = std::min(r0 + st.row_count, c0 + chunk_row_limit);
-				n.row_count = c1 - c0;
-				uint64_t nonnull = n.row_count;
-				if (src.nullable(c))
+				CgStripe &st = g->stripes[s];
+				uint64_t r0 = (uint64_t) s * stripe_row_limit;
+				std::vector<uint8_t> &buf = staged[s];
+				for (int c = 0; c < natts; c++)
 				{
-					nonnull = 0;
-					for (uint64_t r = c0; r < c1; r++) nonnull += !src.isnull(c, r);
+					const int len = cols[c].attlen;
+					const bool isf = cols[c].type_class == CG_TYPE_FLOAT;
+					std::vector<uint8_t> values;     /* this column's value buffers, behind its exists buffers */
+					for (uint32_t k = 0; k < st.chunk_count; k++)
+					{
+						CgSkipNode &n = g->nodes[st.skipnode_base + (uint32_t) c * st.chunk_count + k];
+						memset(&n, 0, sizeof n);
+						uint64_t c0 = r0 + (uint64_t) k * chunk_row_limit;
+						uint64_t c1 = std::min(r0 + st.row_count, c0 + chunk_row_limit);
+						n.row_count = c1 - c0;
+						n.exists_length = (n.row_count + 7) / 8;
+						n.compression_level = 3;
+						uint64_t raw = encode_chunk(src, c, len, isf, c0, n, ebuf.data(), vbuf.data());
+						n.decompressed_size = raw;
+						n.exists_offset = buf.size();
+						buf.insert(buf.end(), ebuf.data(), ebuf.data() + n.exists_length);
+						int clen = g_lz4_compress((const char *) vbuf.data(), (char *) cbuf.data(), (int) raw, (int) cbuf.size());
+						n.value_offset = values.size();             /* rebased below */
+						if (clen > 0)
+						{
+							n.compression_type = CG_COMPRESSION_LZ4;
+							n.value_length = (uint64_t) clen;
+							values.insert(values.end(), cbuf.data(), cbuf.data() + clen);
+						}
+						else
+						{
+							n.compression_type = CG_COMPRESSION_NONE;
+							n.value_length = raw;
+							values.insert(values.end(), vbuf.data(), vbuf.data() + raw);
+						}
+					}
+					for (uint32_t k = 0; k < st.chunk_count; k++)
+						g->nodes[st.skipnode_base + (uint32_t) c * st.chunk_count + k].value_offset += buf.size();
+					buf.insert(buf.end(), values.begin(), values.end());
 				}
-				n.decompressed_size = nonnull * cols[c].attlen;
-				n.value_length = n.decompressed_size;
-				n.exists_length = (n.row_count + 7) / 8;
-				n.compression_type = CG_COMPRESSION_NONE;
-				n.compression_level = 3;     /* columnar.c:43 default, recorded even for none */
-				n.exists_offset = off;
-				off += n.exists_length;
-			}
-			for (uint32_t k = 0; k < st.chunk_count; k++)
-			{
-				CgSkipNode &n = g->nodes[st.skipnode_base + (uint32_t) c * st.chunk_count + k];
-				n.value_offset = off;
-				off += n.value_length;
+				st.data_length = buf.size();
 			}
 		}
-		st.data_length = off;
+	}
+	else
+	{
+		/* pass 1: value counts per (stripe, column, chunk) -> sizes and offsets */
+	#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+		for (int64_t s = 0; s < (int64_t) nstripes; s++)
+		{
+			CgStripe &st = g->stripes[s];
+			uint64_t r0 = (uint64_t) s * stripe_row_limit;
+			uint64_t off = 0;
+			for (int c = 0; c < natts; c++)
+			{
+				for (uint32_t k = 0; k < st.chunk_count; k++)
+				{
+					CgSkipNode &n = g->nodes[st.skipnode_base + (uint32_t) c * st.chunk_count + k];
+					memset(&n, 0, sizeof n);
+					uint64_t c0 = r0 + (uint64_t) k * chunk_row_limit;
+					uint64_t c1 = std::min(r0 + st.row_count, c0 + chunk_row_limit);
+					n.row_count = c1 - c0;
+					uint64_t nonnull = n.row_count;
+					if (src.nullable(c))
+					{
+						nonnull = 0;
+						for (uint64_t r = c0; r < c1; r++) nonnull += !src.isnull(c, r);
+					}
+					n.decompressed_size = nonnull * cols[c].attlen;
+					n.value_length = n.decompressed_size;
+					n.exists_length = (n.row_count + 7) / 8;
+					n.compression_type = CG_COMPRESSION_NONE;
+					n.compression_level = 3;     /* columnar.c:43 default, recorded even for none */
+					n.exists_offset = off;
+					off += n.exists_length;
+				}
+				for (uint32_t k = 0; k < st.chunk_count; k++)
+				{
+					CgSkipNode &n = g->nodes[st.skipnode_base + (uint32_t) c * st.chunk_count + k];
+					n.value_offset = off;
+					off += n.value_length;
+				}
+			}
+			st.data_length = off;
+		}
 	}
 	uint64_t reserved = CG_FIRST_LOGICAL_OFFSET;
 	for (uint64_t s = 0; s < nstripes; s++)
@@ -217,6 +363,12 @@ static int write_relation(const Source &src, const CgColumnDesc *cols, int natts
 					memset(g->pages + b * CG_BLCKSZ + CG_PAGE_HEADER + n, 0, CG_BYTES_PER_PAGE - n);
 				left -= n;
 			}
+			if (compression != CG_COMPRESSION_NONE)
+			{
+				storage_write(g->pages, st.file_offset, staged[s].data(), staged[s].size());
+				std::vector<uint8_t>().swap(staged[s]);
+				continue;
+			}
 			for (int c = 0; c < natts; c++)
 			{
 				const int len = cols[c].attlen;
@@ -225,51 +377,7 @@ static int write_relation(const Source &src, const CgColumnDesc *cols, int natts
 				{
 					CgSkipNode &n = g->nodes[st.skipnode_base + (uint32_t) c * st.chunk_count + k];
 					uint64_t c0 = r0 + (uint64_t) k * chunk_row_limit;
-					uint32_t rows = (uint32_t) n.row_count;
-					memset(ebuf.data(), 0, n.exists_length);
-					uint8_t *vp = vbuf.data();
-					bool has = false;
-					int64_t mn = 0, mx = 0;
-					double fmn = 0, fmx = 0;
-					const bool nullable = src.nullable(c);
-					for (uint32_t i = 0; i < rows; i++)
-					{
-						if (nullable && src.isnull(c, c0 + i)) continue;
-						ebuf[i >> 3] |= (uint8_t) (1u << (i & 7));
-						int64_t v = src.value(c, c0 + i);
-						if (isf)
-						{
-							double d;
-							memcpy(&d, &v, 8);
-							if (len == 4) { float f = (float) d; memcpy(vp, &f, 4); d = f; }
-							else memcpy(vp, &d, 8);
-							/* float8 btree order: NaN above everything */
-							auto fcmp = [](double x, double y) {
-								bool xn = x != x, yn = y != y;
-								if (xn || yn) return (int) xn - (int) yn;
-								return (int) (x > y) - (int) (x < y);
-							};
-							if (!has) { fmn = fmx = d; has = true; }
-							else
-							{
-								if (fcmp(d, fmn) < 0) fmn = d;
-								if (fcmp(d, fmx) > 0) fmx = d;
-							}
-						}
-						else
-						{
-							memcpy(vp, &v, (size_t) len);
-							if (!has) { mn = mx = v; has = true; }
-							else { if (v < mn) mn = v; if (v > mx) mx = v; }
-						}
-						vp += len;
-					}
-					n.has_minmax = has ? 1 : 0;
-					if (has)
-					{
-						if (isf) { memcpy(&n.min_value, &fmn, 8); memcpy(&n.max_value, &fmx, 8); }
-						else { n.min_value = mn; n.max_value = mx; }
-					}
+					encode_chunk(src, c, len, isf, c0, n, ebuf.data(), vbuf.data());
 					storage_write(g->pages, st.file_offset + n.exists_offset, ebuf.data(), n.exists_length);
 					storage_write(g->pages, st.file_offset + n.value_offset, vbuf.data(), n.value_length);
 				}
@@ -293,7 +401,16 @@ extern "C" int cg_gen_relation(const CgGenColumn *cols, int32_t natts, uint64_t 
 		if (cols[c].kind == CG_GEN_UNIFORM && cols[c].hi < cols[c].lo) return cg_set_error(CG_EINVAL, "column %d: hi < lo", c);
 	}
 	SynthSource src{cols, seed, first_row};
-	return write_relation(src, desc.data(), natts, nrows, stripe_row_limit, chunk_row_limit, nthreads, out);
+	return write_relation(src, desc.data(), natts, nrows, stripe_row_limit, chunk_row_limit, nthreads, g_gen_compression, out);
+}
+
+/* columnar.compression for the relations written after the call (none or lz4; tooling, not thread safe) */
+extern "C" int cg_gen_set_compression(int32_t compression)
+{
+	if (compression != CG_COMPRESSION_NONE && compression != CG_COMPRESSION_LZ4)
+		return cg_set_error(CG_EUNSUPPORTED, "the shard writer compresses with none or lz4");
+	g_gen_compression = compression;
+	return CG_OK;
 }
 
 extern "C" int cg_write_relation(const CgColumnDesc *cols, int32_t natts, const int64_t *const *values,
@@ -302,7 +419,7 @@ extern "C" int cg_write_relation(const CgColumnDesc *cols, int32_t natts, const 
 {
 	if (!cols || !values || !out) return cg_set_error(CG_EINVAL, "NULL argument");
 	ArraySource src{values, nulls};
-	return write_relation(src, cols, natts, nrows, stripe_row_limit, chunk_row_limit, omp_get_num_procs() > 8 ? 8 : omp_get_num_procs(), out);
+	return write_relation(src, cols, natts, nrows, stripe_row_limit, chunk_row_limit, omp_get_num_procs() > 8 ? 8 : omp_get_num_procs(), g_gen_compression, out);
 }
 
 extern "C" int cg_gen_relation_view(const CgGenRelation *g, CgRelation *view)

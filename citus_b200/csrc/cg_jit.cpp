@@ -150,11 +150,10 @@ static bool agg_two_limbs(const KAgg &g) { return g.kind == CG_AGG_SUM && !g.is_
 static void choose_shape(const KPlan &plan, JitShape *sh)
 {
 	sh->kind = plan.mode == CG_MODE_GLOBAL ? JK_GLOBAL : JK_TABLE;
-	bool narrow = false;
-	for (int c = 0; c < plan.ncols; c++) if (plan.len[c] != 8) narrow = true;
-	sh->R = narrow ? 4 : 2;
-	sh->U = narrow ? 1 : 2;
-	if (plan.ncols > 5 && !narrow) sh->U = 1;
+	/* two rows per thread and step (one 16-byte load per 8-byte column), two steps loaded before any is
+	 * consumed: the best of the (R, U) grid on every probed shape (profiles/r01_probe_jit.txt) */
+	sh->R = 2;
+	sh->U = 2;
 	{
 		const char *r = getenv("CG_JIT_R"), *u = getenv("CG_JIT_U");
 		if (r && (atoi(r) == 2 || atoi(r) == 4)) sh->R = atoi(r);

@@ -24,6 +24,7 @@
 #define CGP_THREADS 256
 #define CGP_ROWS_PER_BLOCK 4096
 #define CGP_MAX_P 1024
+#define CGP_MAX_COLS 16
 
 __device__ __forceinline__ uint32_t rot32(uint32_t x, int k) { return (x << k) | (x >> (32 - k)); }
 
@@ -378,4 +379,122 @@ extern "C" int cg_partition_scatter(const int32_t *d_index, int64_t n, int32_t P
 									int32_t ncols, int64_t *const *d_out, int64_t *h_offsets)
 {
 	return cg_partition_scatter_ordered(d_index, n, P, nullptr, d_cols, ncols, d_out, h_offsets);
+}
+
+/* ------------------------------------------------------------------------------ *
+ *  Return rows of worker_partition_query_result: (partition_index, rows_written,
+ *  bytes_written), executor/partitioned_intermediate_results.c:270-291.  bytes_written is what
+ *  the partition's file would hold in PostgreSQL's COPY format as TaskFileDestReceiver writes it
+ *  (worker/worker_sql_task_protocol.c:91-251, commands/multi_copy.c AppendCopyRowData /
+ *  AppendCopyBinaryHeaders / AppendCopyBinaryFooters):
+ *    text   fields separated by '\t', row ended by '\n', NULL as "\N", integers in decimal
+ *    binary 19-byte header ("PGCOPY\n\377\r\n\0" + int32 flags + int32 extension length) when the
+ *           receiver starts, per row int16 field count + per field int32 length and the value
+ *           bytes (NULL: length -1 and no bytes), int16 -1 trailer at shutdown
+ *  With lazy start-up (generate_empty_results = false, :234) a partition that receives no row
+ *  never starts its receiver: 0 bytes.  The rows themselves stay on the GPU (NCCL instead of
+ *  files); only these counters are computed.
+ * ------------------------------------------------------------------------------ */
+struct CopyBytesParams
+{
+	const int32_t *index;
+	int64_t n;
+	int32_t P, ncols, binary;
+	const int64_t *cols[CGP_MAX_COLS];
+	const uint8_t *nulls[CGP_MAX_COLS];
+	int32_t len[CGP_MAX_COLS];
+	unsigned long long *bytes;     /* [P] */
+	unsigned long long *rows;      /* [P] */
+};
+
+__constant__ unsigned long long cg_pow10[20] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull,
+												1000000000ull, 10000000000ull, 100000000000ull, 1000000000000ull, 10000000000000ull,
+												100000000000000ull, 1000000000000000ull, 10000000000000000ull, 100000000000000000ull,
+												1000000000000000000ull, 10000000000000000000ull};
+
+__device__ __forceinline__ unsigned int decimal_text_len(int64_t v)
+{
+	/* strlen of pg_lltoa(v): digits + 1 for '-' */
+	unsigned long long a = v < 0 ? 0ull - (unsigned long long) v : (unsigned long long) v;
+	unsigned int bits = 64u - (unsigned int) __clzll((long long) (a | 1ull));
+	unsigned int t = (bits * 1233u) >> 12;             /* floor(log10(2^bits)) or one less */
+	unsigned int digits = t + (a >= cg_pow10[t] ? 1u : 0u);
+	if (digits == 0) digits = 1;
+	return digits + (v < 0 ? 1u : 0u);
+}
+
+__global__ void __launch_bounds__(CGP_THREADS)
+cg_partition_copy_bytes_kernel(const __grid_constant__ CopyBytesParams A)
+{
+	extern __shared__ unsigned int s_copy[];            /* [P] bytes, [P] rows of this block (< 2^32: 4096 rows) */
+	unsigned int *s_bytes = s_copy, *s_rows = s_copy + A.P;
+	for (int p = threadIdx.x; p < 2 * A.P; p += CGP_THREADS) s_copy[p] = 0;
+	__syncthreads();
+	int64_t base = (int64_t) blockIdx.x * CGP_ROWS_PER_BLOCK;
+	for (int i = threadIdx.x; i < CGP_ROWS_PER_BLOCK; i += CGP_THREADS)
+	{
+		int64_t r = base + i;
+		if (r >= A.n) break;
+		unsigned int b = A.binary ? 2u : 0u;
+		for (int c = 0; c < A.ncols; c++)
+		{
+			bool isnull = A.nulls[c] && A.nulls[c][r];
+			if (A.binary) b += 4u + (isnull ? 0u : (unsigned int) A.len[c]);
+			else b += 1u + (isnull ? 2u : decimal_text_len(A.cols[c][r]));
+		}
+		int p = A.index[r];
+		atomicAdd(&s_bytes[p], b);
+		atomicAdd(&s_rows[p], 1u);
+	}
+	__syncthreads();
+	for (int p = threadIdx.x; p < A.P; p += CGP_THREADS)
+	{
+		if (s_rows[p])
+		{
+			atomicAdd(A.bytes + p, (unsigned long long) s_bytes[p]);
+			atomicAdd(A.rows + p, (unsigned long long) s_rows[p]);
+		}
+	}
+}
+
+extern "C" int cg_partition_copy_bytes(const int32_t *d_index, int64_t n, int32_t P, const int64_t *const *d_cols,
+									   const uint8_t *const *d_nulls, const int32_t *col_len, int32_t ncols, int32_t binary,
+									   int32_t generate_empty_results, int64_t *rows_written, int64_t *bytes_written)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx) return CG_EINVAL;
+	if (P < 1 || P > CGP_MAX_P) return cg_set_error(CG_EINVAL, "partition count %d out of range", P);
+	if (ncols < 1 || ncols > CGP_MAX_COLS) return cg_set_error(CG_EUNSUPPORTED, "1..%d columns", CGP_MAX_COLS);
+	if (n < 0 || !d_cols || !col_len || !rows_written || !bytes_written) return cg_set_error(CG_EINVAL, "bad argument");
+	unsigned long long *d_acc = nullptr;
+	CG_CUDA(cudaMallocAsync((void **) &d_acc, 2 * (size_t) P * sizeof(unsigned long long), ctx->compute));
+	CG_CUDA(cudaMemsetAsync(d_acc, 0, 2 * (size_t) P * sizeof(unsigned long long), ctx->compute));
+	if (n > 0)
+	{
+		CopyBytesParams A;
+		memset(&A, 0, sizeof A);
+		A.index = d_index; A.n = n; A.P = P; A.ncols = ncols; A.binary = binary ? 1 : 0;
+		for (int c = 0; c < ncols; c++)
+		{
+			A.cols[c] = d_cols[c];
+			A.nulls[c] = d_nulls ? d_nulls[c] : nullptr;
+			A.len[c] = col_len[c];
+		}
+		A.bytes = d_acc; A.rows = d_acc + P;
+		int64_t nblocks = (n + CGP_ROWS_PER_BLOCK - 1) / CGP_ROWS_PER_BLOCK;
+		cg_partition_copy_bytes_kernel<<<(unsigned) nblocks, CGP_THREADS, 2 * P * sizeof(unsigned int), ctx->compute>>>(A);
+		CG_CUDA(cudaGetLastError()); g_cg_launches++;
+	}
+	std::vector<unsigned long long> h(2 * (size_t) P, 0);
+	CG_CUDA(cudaMemcpyAsync(h.data(), d_acc, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->compute));
+	CG_CUDA(cudaStreamSynchronize(ctx->compute));
+	CG_CUDA(cudaFreeAsync(d_acc, ctx->compute));
+	for (int p = 0; p < P; p++)
+	{
+		rows_written[p] = (int64_t) h[P + p];
+		int64_t b = (int64_t) h[p];
+		if (binary && (h[P + p] > 0 || generate_empty_results)) b += 19 + 2;   /* header at start-up, trailer at shutdown */
+		bytes_written[p] = b;
+	}
+	return CG_OK;
 }

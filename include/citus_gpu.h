@@ -317,6 +317,16 @@ int cg_partition_scatter_ordered(const int32_t *d_index, int64_t n, int32_t P, c
 								 const int64_t *const *d_cols, int32_t ncols, int64_t *const *d_out,
 								 int64_t *h_offsets /* [P+1] */);
 
+/* The return rows of worker_partition_query_result (partitioned_intermediate_results.c:270-291):
+ * rows_written[P] and bytes_written[P] (host arrays), the bytes being what each partition's file
+ * would hold in COPY text or binary format (worker/worker_sql_task_protocol.c:91-251).  d_cols:
+ * ncols device arrays of int64 values; d_nulls: per column a device byte array or NULL; col_len:
+ * the binary width of every column (4 for int4, 8 for int8).  A partition without rows has 0
+ * bytes unless generate_empty_results (then a binary file still holds header + trailer). */
+int cg_partition_copy_bytes(const int32_t *d_index, int64_t n, int32_t P, const int64_t *const *d_cols,
+							const uint8_t *const *d_nulls, const int32_t *col_len, int32_t ncols, int32_t binary,
+							int32_t generate_empty_results, int64_t *rows_written, int64_t *bytes_written);
+
 /* exact bounds from the skip lists (min/max of every chunk that survives chunk-group
  * skipping): the packed group key range and |argument| of every aggregate (0 = unknown,
  * e.g. a chunk without min/max).  Feed them to cg_partial_create / CgAggSpec.term_abs_bound. */
@@ -362,6 +372,9 @@ int cg_gen_relation(const CgGenColumn *cols, int32_t natts, uint64_t nrows, uint
 int cg_write_relation(const CgColumnDesc *cols, int32_t natts, const int64_t *const *values,
 					  const uint8_t *const *nulls, uint64_t nrows, uint64_t stripe_row_limit,
 					  uint32_t chunk_row_limit, CgGenRelation **out);
+/* columnar.compression of the relations written after the call: CG_COMPRESSION_NONE or
+ * CG_COMPRESSION_LZ4 (liblz4's LZ4_compress_default, as the reference's CompressBuffer) */
+int cg_gen_set_compression(int32_t compression);
 int cg_gen_relation_view(const CgGenRelation *g, CgRelation *view);
 void cg_gen_relation_free(CgGenRelation *g);
 

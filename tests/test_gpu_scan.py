@@ -472,6 +472,24 @@ def test_partition_goldens(cg, oracle, expected):
     assert cnt.cpu().tolist() == [r[1] for r in expected["doubles_hash_text"]]
     idx, cnt, _ = _partition(cg, i, None, 4, "range", [0, 250001, 500001, 750001], [250000, 500000, 750000, 1000000])
     assert cnt.cpu().tolist() == [r[1] for r in expected["doubles_range_binary"]]
+    # bytes_written of the COPY text / binary files (partitioned_intermediate_results.out: 21/14/5/9 and 93/57/39/75)
+    import torch
+    i = np.arange(1, 11)
+    di, dsq = torch.from_numpy(i).cuda(), torch.from_numpy(i * i).cuda()
+    idx, cnt, _ = _partition(cg, i, None, 4, "hash", expected["squares_hash_mins"], expected["squares_hash_maxs"])
+    rows, nbytes = cg.partition_copy_bytes(idx.data_ptr(), 10, 4, [di.data_ptr(), dsq.data_ptr()], [4, 4], binary=False)
+    assert [[p, int(rows[p]), int(nbytes[p])] for p in range(4)] == expected["squares_hash_text"]
+    idx, cnt, _ = _partition(cg, i * i, None, 4, "range", [0, 21, 41, 61], [20, 40, 60, 100])
+    rows, nbytes = cg.partition_copy_bytes(idx.data_ptr(), 10, 4, [di.data_ptr(), dsq.data_ptr()], [4, 4], binary=True)
+    assert [[p, int(rows[p]), int(nbytes[p])] for p in range(4)] == expected["squares_range_binary"]
+    i = np.arange(1, 1000001)
+    di, d2 = torch.from_numpy(i).cuda(), torch.from_numpy(i * 2).cuda()
+    idx, cnt, _ = _partition(cg, i, None, 4, "hash", expected["squares_hash_mins"], expected["squares_hash_maxs"])
+    rows, nbytes = cg.partition_copy_bytes(idx.data_ptr(), len(i), 4, [di.data_ptr(), d2.data_ptr()], [4, 4], binary=False)
+    assert [[p, int(rows[p]), int(nbytes[p])] for p in range(4)] == expected["doubles_hash_text"]
+    idx, cnt, _ = _partition(cg, i, None, 4, "range", [0, 250001, 500001, 750001], [250000, 500000, 750000, 1000000])
+    rows, nbytes = cg.partition_copy_bytes(idx.data_ptr(), len(i), 4, [di.data_ptr(), d2.data_ptr()], [4, 4], binary=True)
+    assert [[p, int(rows[p]), int(nbytes[p])] for p in range(4)] == expected["doubles_range_binary"]
     # edge keys that hash to INT32_MAX / INT32_MIN (distributed_planning.out:12-33)
     mins, maxs = oracle.synthetic_intervals(32)
     idx, cnt, _ = _partition(cg, np.array([2608474032, 963809240]), None, 8, "hash", mins, maxs)
@@ -492,6 +510,17 @@ def test_partition_parity_and_scatter(cg, oracle):
         assert np.array_equal(idx.cpu().numpy(), want_idx)
         assert np.array_equal(cnt.cpu().numpy(), want_rows)
         dp = torch.from_numpy(payload).cuda()
+        # the UDF's return rows: COPY text and binary byte counts with NULLs, negative and 19-digit values
+        dn = torch.from_numpy(nulls).cuda()
+        for binary in (False, True):
+            rows, nbytes = cg.partition_copy_bytes(idx.data_ptr(), n, P, [dk.data_ptr(), dp.data_ptr()], [8, 8], binary,
+                                                   d_null_ptrs=[dn.data_ptr(), None])
+            assert np.array_equal(rows, want_rows)
+            for p in (0, P // 2, P - 1):
+                want_bytes = oracle.copy_file_bytes([keys, payload], [8, 8], want_idx, p, binary, colnulls=[nulls, None])
+                if binary and want_rows[p] == 0:
+                    want_bytes = 0                      # lazy start-up: the receiver of an empty partition never starts
+                assert int(nbytes[p]) == want_bytes, (P, p, binary)
         ok = torch.empty_like(dk)
         op = torch.empty_like(dp)
         offs = cg.partition_scatter(idx.data_ptr(), n, P, [dk.data_ptr(), dp.data_ptr()], [ok.data_ptr(), op.data_ptr()])

@@ -80,6 +80,18 @@ def test_writer_matches_oracle_writer_byte_for_byte(cg, oracle):
     assert np.array_equal(vals[0], a) and np.array_equal(vals[2], c)
     assert np.array_equal(nulls[1], nb) and np.array_equal(vals[1][nb == 0], b[nb == 0])
     assert np.array_equal(nulls[3], nd)
+    # columnar.compression = lz4: both writers hand every value stream to the same LZ4_compress_default
+    if oracle.lib().orc_have_lz4():
+        cg.set_writer_compression("lz4")
+        try:
+            rel = cg.Relation.write([8, 4, 2, 1], [a, b, c, d % 100], [None, nb, None, nd],
+                                    stripe_row_limit=5000, chunk_row_limit=1000)
+        finally:
+            cg.set_writer_compression("none")
+        t = oracle.Table([8, 4, 2, 1], stripe_row_limit=5000, chunk_row_limit=1000, compression=oracle.COMP_LZ4)
+        t.insert([a, b, c, d % 100], nulls=[None, nb, None, nd])
+        assert any(nd_.compression_type == oracle.COMP_LZ4 for nd_ in t.nodes())
+        _same_image(rel, t)
 
 
 def test_float_columns_and_default_limits(cg, oracle):
