@@ -239,6 +239,8 @@ extern "C" void cg_shutdown(void)
 		if (g_ctx.dma_done[i]) cudaEventDestroy(g_ctx.dma_done[i]);
 		g_ctx.dma_done[i] = nullptr;
 	}
+	for (int i = 0; i < 2; i++) { if (g_ctx.decode_stream[i]) cudaStreamDestroy(g_ctx.decode_stream[i]); g_ctx.decode_stream[i] = nullptr; }
+	for (int i = 0; i < CgContext::kDmaDepth; i++) { if (g_ctx.decoded[i]) cudaEventDestroy(g_ctx.decoded[i]); g_ctx.decoded[i] = nullptr; }
 	if (g_ctx.dma_copied) cudaEventDestroy(g_ctx.dma_copied);
 	g_ctx.dma_copied = nullptr;
 	for (cudaEvent_t e : g_ctx.prof_events) cudaEventDestroy(e);
@@ -1213,10 +1215,13 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 							  cg_build_fast_plan(desc, plan, all8, &fast);
 		const bool try_jit = !use_fast && !sp.any_nulls && !cg_force_general();
 		if (stats) CG_CUDA(cudaEventRecord(ctx->ev_a, ctx->compute));
+		bool decode_done = false;          /* the DMA path may decode on a side stream before launch_block runs */
 		auto launch_block = [&](uint64_t cg0, uint64_t cg1, cudaEvent_t copied) -> int {
 			CG_CUDA(cudaStreamWaitEvent(ctx->compute, copied, 0));
 			/* K7: compressed value streams of the block -> their value slots */
-			int r = cg_launch_decompress(d_arena, d_decode + sp.dec_first[cg0], sp.dec_first[cg1] - sp.dec_first[cg0],
+			int r = CG_OK;
+			if (!decode_done)
+				r = cg_launch_decompress(d_arena, d_decode + sp.dec_first[cg0], sp.dec_first[cg1] - sp.dec_first[cg0],
 										 into->d_stats + 2, CG_ERRFLAG_DECOMPRESS, ctx->compute);
 			if (r) return r;
 			if (sp.any_nulls)
@@ -1291,12 +1296,33 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 				cudaEventDestroy(t0); cudaEventDestroy(t1);
 			}
 			CG_CUDA(cudaEventRecord(ctx->dma_copied, ctx->copy));
-			CG_CUDA(cudaStreamWaitEvent(ctx->compute, ctx->dma_copied, 0));
 			cudaEvent_t k0 = nullptr, k1 = nullptr, k2 = nullptr;
 			if (trace) { cudaEventCreate(&k0); cudaEventCreate(&k1); cudaEventCreate(&k2); cudaEventRecord(k0, ctx->compute); }
-			rc = cg_launch_realign(d_raw, d_arena, (const RealignItem *) (d_meta + off_items), items.size(), ctx->compute);
+			cudaEvent_t ready = ctx->dma_copied;
+			if (!sp.decode.empty() && !trace)
+			{
+				/* de-framing and decompression run on one of two side streams, the scan follows on the
+				 * compute stream: the decode of this shard overlaps the decode (and scan) of the previous one */
+				const int ds = (int) (ctx->decode_rr++ & 1u);
+				if (!ctx->decode_stream[ds]) CG_CUDA(cudaStreamCreateWithFlags(&ctx->decode_stream[ds], cudaStreamNonBlocking));
+				if (!ctx->decoded[mslot]) CG_CUDA(cudaEventCreateWithFlags(&ctx->decoded[mslot], cudaEventDisableTiming));
+				cudaStream_t side = ctx->decode_stream[ds];
+				CG_CUDA(cudaStreamWaitEvent(side, ctx->dma_copied, 0));
+				rc = cg_launch_realign(d_raw, d_arena, (const RealignItem *) (d_meta + off_items), items.size(), side);
+				if (rc == CG_OK)
+					rc = cg_launch_decompress(d_arena, d_decode, sp.decode.size(), into->d_stats + 2, CG_ERRFLAG_DECOMPRESS, side);
+				if (rc) return rc;
+				CG_CUDA(cudaEventRecord(ctx->decoded[mslot], side));
+				ready = ctx->decoded[mslot];
+				decode_done = true;
+			}
+			else
+			{
+				CG_CUDA(cudaStreamWaitEvent(ctx->compute, ctx->dma_copied, 0));
+				rc = cg_launch_realign(d_raw, d_arena, (const RealignItem *) (d_meta + off_items), items.size(), ctx->compute);
+			}
 			if (trace) cudaEventRecord(k1, ctx->compute);
-			if (rc == CG_OK) rc = launch_block(0, ncg, ctx->dma_copied);
+			if (rc == CG_OK) rc = launch_block(0, ncg, ready);
 			if (trace)
 			{
 				cudaEventRecord(k2, ctx->compute);
