@@ -95,6 +95,8 @@ SYMBOLS = [
     ("cg_set_stream", C.c_int, [C.c_void_p]),
     ("cg_kernel_launches", C.c_uint64, []),
     ("cg_partition_copy_bytes", C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    ("cg_join_count_sum", C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                   C.POINTER(C.c_uint64)]),
     ("cg_gen_set_compression", C.c_int, [C.c_int32]),
     ("cg_jit_launches", C.c_uint64, []),
     ("cg_jit_compiles", C.c_uint64, []),

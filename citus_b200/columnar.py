@@ -403,6 +403,15 @@ def worker_partition_query_result(d_keys_ptr, d_nulls_ptr, n, key_len, method, m
                                    mins.ctypes.data, maxs.ctypes.data, len(mins), d_index_ptr, d_counts_ptr))
 
 
+def join_count_sum(d_build_keys, d_build_payload, nbuild, d_probe_keys, d_probe_payload, nprobe, d_build_nulls=None,
+                   d_probe_nulls=None):
+    """(joined rows, exact sum(b.payload + p.payload)) of the equi-join of two device-resident partitions"""
+    rows, hi, lo = C.c_int64(), C.c_int64(), C.c_uint64()
+    check(lib().cg_join_count_sum(d_build_keys, d_build_nulls, d_build_payload, nbuild, d_probe_keys, d_probe_nulls,
+                                  d_probe_payload, nprobe, C.byref(rows), C.byref(hi), C.byref(lo)))
+    return rows.value, (hi.value << 64) + lo.value
+
+
 def set_writer_compression(name: str):
     """columnar.compression for Relation.generate / Relation.write: "none" or "lz4"""
     check(lib().cg_gen_set_compression({"none": 0, "lz4": 2}[name]))

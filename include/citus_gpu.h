@@ -327,6 +327,17 @@ int cg_partition_copy_bytes(const int32_t *d_index, int64_t n, int32_t P, const 
 							const uint8_t *const *d_nulls, const int32_t *col_len, int32_t ncols, int32_t binary,
 							int32_t generate_empty_results, int64_t *rows_written, int64_t *bytes_written);
 
+/* The merge side of a dual-repartition join for the aggregate query
+ *     SELECT count(*), sum(b.payload + p.payload) FROM build b JOIN probe p USING (key)
+ * over two co-located partitions that are already device arrays (what the MERGE task computes with
+ * read_intermediate_results() + PostgreSQL's HashJoin + Agg, planner/multi_physical_planner.c:
+ * 4304-4328, executor/intermediate_results.c:789-1045).  NULL keys join nothing; the sum is exact
+ * (128-bit two's complement in sum_hi:sum_lo).  The joined rows are never materialised. */
+int cg_join_count_sum(const int64_t *d_build_keys, const uint8_t *d_build_nulls, const int64_t *d_build_payload,
+					  int64_t nbuild, const int64_t *d_probe_keys, const uint8_t *d_probe_nulls,
+					  const int64_t *d_probe_payload, int64_t nprobe, int64_t *joined_rows, int64_t *sum_hi,
+					  uint64_t *sum_lo);
+
 /* exact bounds from the skip lists (min/max of every chunk that survives chunk-group
  * skipping): the packed group key range and |argument| of every aggregate (0 = unknown,
  * e.g. a chunk without min/max).  Feed them to cg_partial_create / CgAggSpec.term_abs_bound. */

@@ -516,6 +516,51 @@ static int orc_decompress(const uint8_t *in, uint64_t len, int type, uint64_t ra
 	}
 }
 
+/* ------------------------------------------------------------------------------
+ * The MERGE task of a dual-repartition join (planner/multi_physical_planner.c:4304-4328:
+ * both inputs come back through read_intermediate_results() and are joined by [PG]
+ * nodeHashjoin, then aggregated by nodeAgg):
+ *     SELECT count(*), sum(b.payload + p.payload) FROM build b JOIN probe p USING (key)
+ * restated row-at-a-time: every probe row is matched against every build row with an
+ * equal key (NULL keys never match), each joined row adds 1 and b.payload + p.payload
+ * (int8 + int8 -> numeric sum: exact, kept in 128 bits).
+ * ------------------------------------------------------------------------------ */
+typedef struct { int64_t key; int64_t payload; } OrcJoinRow;
+static int orc_join_row_cmp(const void *a, const void *b)
+{
+	int64_t x = ((const OrcJoinRow *) a)->key, y = ((const OrcJoinRow *) b)->key;
+	return (x > y) - (x < y);
+}
+
+int orc_join_count_sum(const int64_t *bkeys, const uint8_t *bnulls, const int64_t *bpay, int64_t nb,
+					   const int64_t *pkeys, const uint8_t *pnulls, const int64_t *ppay, int64_t np,
+					   int64_t *joined, int64_t *sum_hi, uint64_t *sum_lo)
+{
+	OrcJoinRow *rows = malloc(sizeof(OrcJoinRow) * (size_t) (nb > 0 ? nb : 1));
+	int64_t n = 0;
+	for (int64_t i = 0; i < nb; i++)
+		if (!(bnulls && bnulls[i])) { rows[n].key = bkeys[i]; rows[n].payload = bpay[i]; n++; }
+	qsort(rows, (size_t) n, sizeof(OrcJoinRow), orc_join_row_cmp);
+	__int128 sum = 0;
+	int64_t count = 0;
+	for (int64_t i = 0; i < np; i++)
+	{
+		if (pnulls && pnulls[i]) continue;
+		int64_t lo = 0, hi = n;
+		while (lo < hi) { int64_t mid = lo + (hi - lo) / 2; if (rows[mid].key < pkeys[i]) lo = mid + 1; else hi = mid; }
+		for (int64_t j = lo; j < n && rows[j].key == pkeys[i]; j++)
+		{
+			count++;
+			sum += (__int128) rows[j].payload + (__int128) ppay[i];
+		}
+	}
+	free(rows);
+	*joined = count;
+	*sum_lo = (uint64_t) sum;
+	*sum_hi = (int64_t) (sum >> 64);
+	return 0;
+}
+
 /* the codecs alone, for known-answer tests of the stream formats */
 int64_t orc_codec_compress(int type, int level, const uint8_t *in, uint64_t len, uint8_t *out, uint64_t cap)
 {

@@ -163,6 +163,20 @@ def partition_rows(keys, nulls, keytype, method, mins, maxs):
     return idx, rows
 
 
+def join_count_sum(bkeys, bpay, pkeys, ppay, bnulls=None, pnulls=None):
+    """(joined rows, exact sum(b.payload + p.payload)) of the MERGE task's hash join, row at a time"""
+    arrs = [np.ascontiguousarray(a, np.int64) for a in (bkeys, bpay, pkeys, ppay)]
+    nl = [None if a is None else np.ascontiguousarray(a, np.uint8) for a in (bnulls, pnulls)]
+    joined, hi, lo = C.c_int64(), C.c_int64(), C.c_uint64()
+    L = lib()
+    L.orc_join_count_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                     C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_uint64)]
+    _check(L.orc_join_count_sum(arrs[0].ctypes.data, None if nl[0] is None else nl[0].ctypes.data, arrs[1].ctypes.data, len(arrs[0]),
+                                arrs[2].ctypes.data, None if nl[1] is None else nl[1].ctypes.data, arrs[3].ctypes.data, len(arrs[2]),
+                                C.byref(joined), C.byref(hi), C.byref(lo)))
+    return joined.value, (hi.value << 64) + lo.value
+
+
 def copy_file_bytes(cols, collens, row_partition, partition, binary, colnulls=None):
     cols = [np.ascontiguousarray(c, np.int64) for c in cols]
     n = cols[0].shape[0]

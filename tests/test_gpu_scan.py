@@ -575,3 +575,25 @@ def test_packed_accumulators_overflow_is_detected_and_retry_is_exact(cg, oracle)
     for _ in range(3):
         oracle_table(oracle, rel2).scan([], [0], to_oracle_aggs(oracle, aggs), into=want)
     assert_same_groups(agg2.groups(), want.groups(), aggs)
+
+
+# --------------------------------------------------------------------------- merge-side join (K8)
+def test_join_count_sum_matches_row_at_a_time_join(cg, oracle):
+    import torch
+    rng = np.random.default_rng(21)
+    for nb, npr, domain in ((1, 1, 1), (1000, 0, 10), (50_000, 70_000, 5_000), (300_000, 250_000, 1 << 28)):
+        bk = rng.integers(0, domain, nb)
+        pk = rng.integers(0, domain, npr)
+        if nb > 10:
+            bk[:5] = [-2**63, 2**63 - 1, 0, -1, -2**63]           # the table's EMPTY sentinel is a legal key
+        if npr > 10:
+            pk[:4] = [-2**63, 2**63 - 1, -1, 7]
+        bx = rng.integers(-2**62, 2**62, nb)
+        py = rng.integers(-2**62, 2**62, npr)
+        bn = (rng.random(nb) < 0.05).astype(np.uint8)
+        pn = (rng.random(npr) < 0.05).astype(np.uint8)
+        want = oracle.join_count_sum(bk, bx, pk, py, bn, pn)
+        d = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (bk, bx, pk, py, bn, pn)]
+        got = cg.join_count_sum(d[0].data_ptr(), d[1].data_ptr(), nb, d[2].data_ptr(), d[3].data_ptr(), npr,
+                                d_build_nulls=d[4].data_ptr(), d_probe_nulls=d[5].data_ptr())
+        assert got == want, (nb, npr, domain)

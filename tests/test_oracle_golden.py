@@ -348,3 +348,19 @@ def test_int128_sum(oracle):
     t = oracle.Table([8])
     t.insert([-big])
     assert t.scan(aggs=[oracle.sum_(0)]).groups()[0][0]["sum"] == -1000 * 2**62
+
+
+def test_join_restatement_against_brute_force(oracle):
+    rng = np.random.default_rng(2)
+    bk, bx = rng.integers(0, 40, 300), rng.integers(-2**62, 2**62, 300)
+    pk, py = rng.integers(0, 50, 400), rng.integers(-2**62, 2**62, 400)
+    bn, pn = (rng.random(300) < 0.1), (rng.random(400) < 0.1)
+    joined, total = oracle.join_count_sum(bk, bx, pk, py, bn, pn)
+    cnt, tot = 0, 0
+    for k, y, isnull in zip(pk, py, pn):
+        if isnull:
+            continue
+        m = bx[(bk == k) & ~bn]
+        cnt += len(m)
+        tot += sum(int(x) + int(y) for x in m)
+    assert joined == cnt and total == tot
