@@ -88,6 +88,24 @@ class ClockSampler(threading.Thread):
         except Exception as e:          # noqa
             log("clock sampling unavailable:", e)
 
+    def sample_once(self):
+        """one NVML sample from the calling thread (used while the GPU is still executing the timed steps)"""
+        if not self.ok:
+            return
+        nv = self.nv
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"),
+                              (0x4, "sw_power_cap"), (0x80, "hw_power_brake")):
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
     def run(self):
         if not self.ok:
             return
@@ -333,6 +351,9 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(args.steps):
         ngroups = step()
     ev1.record()
+    sampler.sample_once()                      # the steps are short: sample while the device is still inside them
+    while not ev1.query():
+        sampler.sample_once()
     barrier()
     clocks = sampler.result()
     all_launches = capi.lib().cg_kernel_launches() - launches_before

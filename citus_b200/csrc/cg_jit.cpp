@@ -681,11 +681,9 @@ int cg_launch_scan_jit(CgContext *ctx, const KPlan &plan, cudaStream_t stream, b
 	JitShape sh;
 	choose_shape(plan, &sh);
 	std::string src = gen_source(plan, sh);
-	JitKernel *k;
-	{
-		std::lock_guard<std::mutex> lock(g_cache_mutex);
-		k = &g_cache[src];
-	}
+	/* one compilation per distinct source, also when several host threads scan at once */
+	std::unique_lock<std::mutex> lock(g_cache_mutex);
+	JitKernel *k = &g_cache[src];
 	if (k->failed) return CG_OK;
 	if (!k->fn)
 	{
@@ -714,6 +712,7 @@ int cg_launch_scan_jit(CgContext *ctx, const KPlan &plan, cudaStream_t stream, b
 		if (g_api.occupancy(&occ, k->fn, JIT_THREADS, sh.smem) != 0 || occ < 1) occ = 1;
 		k->occupancy = occ;
 	}
+	lock.unlock();
 	const uint32_t grid_full = (uint32_t) (ctx->sm_count * k->occupancy);
 	/* SMALL with single-cell sums: bound the rows a lane can see in one launch */
 	uint32_t max_cgs_per_launch = UINT32_MAX;
