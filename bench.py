@@ -61,7 +61,7 @@ def parse():
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--pageable", action="store_true", help="e2e from pageable host pages (host de-framing) instead of pinned pages (DMA)")
     p.add_argument("--gen-threads", type=int, default=0)
-    p.add_argument("--compression", default="none", choices=["none", "lz4"],
+    p.add_argument("--compression", default="none", choices=["none", "lz4", "zstd"],
                    help="columnar.compression of the synthetic shards (BASELINE configs use none; lz4 exercises the GPU decoder)")
     p.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to the CPUs of its GPU's NUMA node")
     return p.parse_args()

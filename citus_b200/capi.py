@@ -98,6 +98,7 @@ SYMBOLS = [
     ("cg_join_count_sum", C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                    C.POINTER(C.c_uint64)]),
     ("cg_gen_set_compression", C.c_int, [C.c_int32]),
+    ("cg_test_zstd_decode_host", C.c_int64, [_P, C.c_uint32, _P, C.c_uint32]),
     ("cg_jit_launches", C.c_uint64, []),
     ("cg_jit_compiles", C.c_uint64, []),
     ("cg_jit_compile_check", C.c_int, [C.POINTER(CgScanDesc), C.POINTER(CgColumnDesc), C.c_int32, C.c_int64, C.c_int64, C.c_int64,

@@ -413,8 +413,8 @@ def join_count_sum(d_build_keys, d_build_payload, nbuild, d_probe_keys, d_probe_
 
 
 def set_writer_compression(name: str):
-    """columnar.compression for Relation.generate / Relation.write: "none" or "lz4"""
-    check(lib().cg_gen_set_compression({"none": 0, "lz4": 2}[name]))
+    """columnar.compression for Relation.generate / Relation.write: "none", "lz4" or "zstd" (level 3)"""
+    check(lib().cg_gen_set_compression({"none": 0, "lz4": 2, "zstd": 3}[name]))
 
 
 def partition_copy_bytes(d_index_ptr, n, P, d_col_ptrs, col_lens, binary, d_null_ptrs=None, generate_empty_results=False):

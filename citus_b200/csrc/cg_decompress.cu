@@ -17,8 +17,8 @@
  *                               [len-3 | off>>8 <<4][off & 0xff][+1 length byte when len == 18],
  *                               bit clear = one literal byte).
  *
- * The exists bitmap is never compressed (columnar_writer.c:606-653); zstd chunks are refused at
- * staging (CG_EUNSUPPORTED).
+ * The exists bitmap is never compressed (columnar_writer.c:606-653).  Zstandard streams have their
+ * own kernel at the end of this file (cg_zstd.cuh holds the decoder).
  *
  * Eight lanes decode one chunk buffer, four streams per warp (a C2 relation has ~10^5 streams per
  * column, so the grid is wide; sequences of columnar value streams are a few bytes long, so
@@ -35,7 +35,10 @@
  * A malformed stream never writes outside the item's slot; it raises `flag` in *err and the
  * host reports CG_ECORRUPT ("cannot decompress the buffer") at its next synchronisation.
  */
+#include <algorithm>
+
 #include "cg_internal.h"
+#include "cg_zstd.cuh"
 
 #define CGD_WARPS 4
 #define CGD_GROUP 8u                    /* lanes per stream */
@@ -274,6 +277,7 @@ cg_decompress_kernel(uint8_t *arena, const DecodeItem *items, uint32_t nitems, u
 	const uint32_t idx = blockIdx.x * (CGD_WARPS * CGD_GROUPS) + group;
 	if (idx >= nitems) return;
 	const DecodeItem it = items[idx];
+	if (it.kind == CG_COMPRESSION_ZSTD) return;                     /* cg_zstd_kernel's */
 	Stream s;
 	s.src = arena + it.src;
 	s.len = it.comp_len;
@@ -303,13 +307,96 @@ cg_decompress_kernel(uint8_t *arena, const DecodeItem *items, uint32_t nitems, u
 	if (!ok && o.glane == 0) atomicOr(err, flag);
 }
 
-int cg_launch_decompress(uint8_t *arena, const DecodeItem *items, uint64_t nitems, unsigned long long *err,
-						 unsigned long long flag, cudaStream_t stream)
+/*
+ * Zstandard (cg_zstd.cuh): entropy decoding (FSE state machines, Huffman bit streams) is a serial
+ * dependency chain per stream, so a stream is decoded by ONE lane running ordinary sequential code
+ * -- the same source the CPU-side format tests run on the host -- and the parallelism comes from
+ * the number of streams (a C2 shard has ~10^4).  One warp per CTA; its tables (ZstdTables, ~10 KB)
+ * live in shared memory, its literals buffer (128 KB) in a context-owned scratch area; persistent
+ * CTAs stride over the decode list.  The other lanes only help with the slot's zero padding.
+ */
+__global__ void __launch_bounds__(32)
+cg_zstd_kernel(uint8_t *arena, const DecodeItem *items, uint32_t nitems, uint8_t *lit_scratch, unsigned long long *err,
+			   unsigned long long flag)
+{
+	__shared__ ZstdTables T;
+	__shared__ int s_ok;
+	const uint32_t lane = threadIdx.x;
+	uint8_t *lit = lit_scratch + (size_t) blockIdx.x * (ZSTD_BLOCK_MAX + 64);
+	for (uint32_t idx = blockIdx.x; idx < nitems; idx += gridDim.x)
+	{
+		const DecodeItem it = items[idx];
+		if (it.kind != CG_COMPRESSION_ZSTD) continue;
+		uint8_t *dst = arena + it.dst;
+		if (lane == 0)
+		{
+			int64_t n = zs_decode_frame(T, arena + it.src, it.comp_len, dst, it.raw_len, lit);
+			/* "unexpected decompressed size" (columnar_compression.c:226-232) */
+			s_ok = n == (int64_t) it.raw_len;
+			if (!s_ok) atomicOr(err, flag);
+		}
+		__syncwarp();
+		const bool ok = s_ok != 0;
+		for (uint32_t i = (ok ? it.raw_len : 0u) + lane; i < it.padded; i += 32) dst[i] = 0;
+		__syncwarp();
+	}
+}
+
+/* the same decoder on the host: lets the -m "not gpu" tests check the bit-level format logic against
+ * libzstd-compressed streams.  Test hook only: nothing in the library's data path calls it. */
+extern "C" int64_t cg_test_zstd_decode_host(const uint8_t *src, uint32_t len, uint8_t *dst, uint32_t cap)
+{
+	ZstdTables *T = new ZstdTables();
+	uint8_t *lit = new uint8_t[ZSTD_BLOCK_MAX + 64];
+	int64_t n = zs_decode_frame(*T, src, len, dst, cap, lit);
+	delete[] lit;
+	delete T;
+	return n;
+}
+
+/* h_items: the host copy of the same items (which kernels are needed) */
+int cg_launch_decompress(CgContext *ctx, uint8_t *arena, const DecodeItem *items, const DecodeItem *h_items, uint64_t nitems,
+						 unsigned long long *err, unsigned long long flag, cudaStream_t stream)
 {
 	if (nitems == 0) return CG_OK;
-	const unsigned per_block = CGD_WARPS * CGD_GROUPS;
-	unsigned blocks = (unsigned) ((nitems + per_block - 1) / per_block);
-	cg_decompress_kernel<<<blocks, CGD_WARPS * 32, 0, stream>>>(arena, items, (uint32_t) nitems, err, flag);
-	CG_CUDA(cudaGetLastError()); g_cg_launches++;
+	bool any_lz = false, any_zstd = false;
+	for (uint64_t i = 0; i < nitems; i++)
+	{
+		if (h_items[i].kind == CG_COMPRESSION_ZSTD) any_zstd = true; else any_lz = true;
+	}
+	if (any_lz)
+	{
+		const unsigned per_block = CGD_WARPS * CGD_GROUPS;
+		unsigned blocks = (unsigned) ((nitems + per_block - 1) / per_block);
+		cg_decompress_kernel<<<blocks, CGD_WARPS * 32, 0, stream>>>(arena, items, (uint32_t) nitems, err, flag);
+		CG_CUDA(cudaGetLastError()); g_cg_launches++;
+	}
+	if (any_zstd)
+	{
+		static int occ = 0;
+		if (occ == 0)
+		{
+			CG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_zstd_kernel, 32, 0));
+			if (occ < 1) occ = 1;
+		}
+		const unsigned max_blocks = (unsigned) (ctx->sm_count * occ);
+		const size_t need = (size_t) max_blocks * (ZSTD_BLOCK_MAX + 64);
+		if (ctx->zstd_scratch_bytes < need)
+		{
+			/* grown once; every launch uses block-indexed slices, launches on different streams would
+			 * share them, so zstd decoding always runs on the stream it was first used with or after a sync */
+			if (ctx->zstd_scratch) CG_CUDA(cudaFree(ctx->zstd_scratch));
+			ctx->zstd_scratch = nullptr; ctx->zstd_scratch_bytes = 0;
+			if (cudaMalloc((void **) &ctx->zstd_scratch, need) != cudaSuccess)
+			{
+				cudaGetLastError();
+				return cg_set_error(CG_ENOMEM, "cudaMalloc of %zu bytes of zstd literal scratch failed", need);
+			}
+			ctx->zstd_scratch_bytes = need;
+		}
+		unsigned blocks = (unsigned) std::min<uint64_t>(nitems, max_blocks);
+		cg_zstd_kernel<<<blocks, 32, 0, stream>>>(arena, items, (uint32_t) nitems, ctx->zstd_scratch, err, flag);
+		CG_CUDA(cudaGetLastError()); g_cg_launches++;
+	}
 	return CG_OK;
 }

@@ -32,6 +32,30 @@ typedef int (*lz4_bound_fn)(int);
 typedef int (*lz4_comp_fn)(const char *, char *, int, int);
 static lz4_bound_fn g_lz4_bound;
 static lz4_comp_fn g_lz4_compress;
+/* libzstd likewise: ZSTD_compress(dst, cap, src, len, level) as columnar_compression.c:103-123 */
+typedef size_t (*zstd_bound_fn)(size_t);
+typedef size_t (*zstd_comp_fn)(void *, size_t, const void *, size_t, int);
+typedef unsigned (*zstd_iserr_fn)(size_t);
+static zstd_bound_fn g_zstd_bound;
+static zstd_comp_fn g_zstd_compress;
+static zstd_iserr_fn g_zstd_iserr;
+static bool load_zstd()
+{
+	static int state = 0;
+	if (state == 0)
+	{
+		void *h = dlopen("libzstd.so.1", RTLD_NOW);
+		if (h)
+		{
+			g_zstd_bound = (zstd_bound_fn) dlsym(h, "ZSTD_compressBound");
+			g_zstd_compress = (zstd_comp_fn) dlsym(h, "ZSTD_compress");
+			g_zstd_iserr = (zstd_iserr_fn) dlsym(h, "ZSTD_isError");
+		}
+		state = (g_zstd_bound && g_zstd_compress && g_zstd_iserr) ? 1 : -1;
+	}
+	return state == 1;
+}
+
 static bool load_lz4()
 {
 	static int state = 0;
@@ -180,10 +204,12 @@ template <typename Source>
 static int write_relation(const Source &src, const CgColumnDesc *cols, int natts, uint64_t nrows,
 						  uint64_t stripe_row_limit, uint32_t chunk_row_limit, int nthreads, int compression, CgGenRelation **out)
 {
-	if (compression != CG_COMPRESSION_NONE && compression != CG_COMPRESSION_LZ4)
-		return cg_set_error(CG_EUNSUPPORTED, "the shard writer compresses with none or lz4");
+	if (compression != CG_COMPRESSION_NONE && compression != CG_COMPRESSION_LZ4 && compression != CG_COMPRESSION_ZSTD)
+		return cg_set_error(CG_EUNSUPPORTED, "the shard writer compresses with none, lz4 or zstd");
 	if (compression == CG_COMPRESSION_LZ4 && !load_lz4())
 		return cg_set_error(CG_EUNSUPPORTED, "liblz4.so.1 is not available");
+	if (compression == CG_COMPRESSION_ZSTD && !load_zstd())
+		return cg_set_error(CG_EUNSUPPORTED, "libzstd.so.1 is not available");
 	if (natts <= 0 || natts > 256) return cg_set_error(CG_EINVAL, "natts %d", natts);
 	/* include/columnar/columnar.h:42-45 limits */
 	if (stripe_row_limit < 1000 || stripe_row_limit > 10000000) return cg_set_error(CG_EINVAL, "stripe_row_limit out of range");
@@ -230,7 +256,8 @@ static int write_relation(const Source &src, const CgColumnDesc *cols, int natts
 #pragma omp parallel num_threads(nthreads)
 		{
 			std::vector<uint8_t> vbuf((size_t) chunk_row_limit * 8 + 16), ebuf(chunk_row_limit / 8 + 16);
-			std::vector<uint8_t> cbuf((size_t) g_lz4_bound((int) chunk_row_limit * 8) + 16);
+			const size_t raw_max = (size_t) chunk_row_limit * 8;
+			std::vector<uint8_t> cbuf((compression == CG_COMPRESSION_LZ4 ? (size_t) g_lz4_bound((int) raw_max) : g_zstd_bound(raw_max)) + 16);
 #pragma omp for schedule(dynamic, 1)
 			for (int64_t s = 0; s < (int64_t) nstripes; s++)
 			{
@@ -255,11 +282,18 @@ static int write_relation(const Source &src, const CgColumnDesc *cols, int natts
 						n.decompressed_size = raw;
 						n.exists_offset = buf.size();
 						buf.insert(buf.end(), ebuf.data(), ebuf.data() + n.exists_length);
-						int clen = g_lz4_compress((const char *) vbuf.data(), (char *) cbuf.data(), (int) raw, (int) cbuf.size());
+						int clen;
+					if (compression == CG_COMPRESSION_LZ4)
+						clen = g_lz4_compress((const char *) vbuf.data(), (char *) cbuf.data(), (int) raw, (int) cbuf.size());
+					else
+					{
+						size_t zn = g_zstd_compress(cbuf.data(), cbuf.size(), vbuf.data(), raw, 3);   /* columnar.compression_level default */
+						clen = g_zstd_iserr(zn) ? 0 : (int) zn;
+					}
 						n.value_offset = values.size();             /* rebased below */
 						if (clen > 0)
 						{
-							n.compression_type = CG_COMPRESSION_LZ4;
+							n.compression_type = compression;
 							n.value_length = (uint64_t) clen;
 							values.insert(values.end(), cbuf.data(), cbuf.data() + clen);
 						}
@@ -407,8 +441,8 @@ extern "C" int cg_gen_relation(const CgGenColumn *cols, int32_t natts, uint64_t 
 /* columnar.compression for the relations written after the call (none or lz4; tooling, not thread safe) */
 extern "C" int cg_gen_set_compression(int32_t compression)
 {
-	if (compression != CG_COMPRESSION_NONE && compression != CG_COMPRESSION_LZ4)
-		return cg_set_error(CG_EUNSUPPORTED, "the shard writer compresses with none or lz4");
+	if (compression != CG_COMPRESSION_NONE && compression != CG_COMPRESSION_LZ4 && compression != CG_COMPRESSION_ZSTD)
+		return cg_set_error(CG_EUNSUPPORTED, "the shard writer compresses with none, lz4 or zstd");
 	g_gen_compression = compression;
 	return CG_OK;
 }

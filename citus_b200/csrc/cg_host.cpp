@@ -227,6 +227,7 @@ extern "C" void cg_shutdown(void)
 	}
 	cudaEventDestroy(g_ctx.ev_a); cudaEventDestroy(g_ctx.ev_b);
 	cudaFree(g_ctx.d_stage_err); g_ctx.d_stage_err = nullptr;
+	cudaFree(g_ctx.zstd_scratch); g_ctx.zstd_scratch = nullptr; g_ctx.zstd_scratch_bytes = 0;
 	for (int i = 0; i < CgContext::kDmaDepth; i++)
 	{
 		for (CgContext::DevBuf *b : {&g_ctx.slot_arena[i], &g_ctx.slot_raw[i], &g_ctx.slot_meta[i]})
@@ -512,11 +513,7 @@ static int plan_staging(const CgRelation *rel, const std::vector<int32_t> &stage
 				{
 					const CgSkipNode &n = rel->nodes[s.skipnode_base + (uint32_t) c * s.chunk_count + k];
 					comp = n.compression_type;
-					if (comp == CG_COMPRESSION_ZSTD)
-						return cg_set_error(CG_EUNSUPPORTED,
-											"stripe %d column %d chunk %u is zstd-compressed: only none, lz4 and pglz chunks are decoded on the GPU",
-											si, c, k);
-					if (comp != CG_COMPRESSION_NONE && comp != CG_COMPRESSION_LZ4 && comp != CG_COMPRESSION_PGLZ)
+					if (comp != CG_COMPRESSION_NONE && comp != CG_COMPRESSION_LZ4 && comp != CG_COMPRESSION_PGLZ && comp != CG_COMPRESSION_ZSTD)
 						return cg_set_error(CG_ECORRUPT, "unexpected compression type: %d", comp);
 					if (n.row_count != rows) return cg_set_error(CG_ECORRUPT, "row count mismatch in chunk group");
 					if (n.exists_length * 8 < rows) return cg_set_error(CG_ECORRUPT, "insufficient data for reading boolean array");
@@ -718,7 +715,8 @@ extern "C" int cg_shard_stage(const CgRelation *rel, const int32_t *columns, int
 		uint32_t f = sp.dec_first[cg0], l = sp.dec_first[cg1];
 		if (f == l) return CG_OK;
 		CG_CUDA(cudaStreamWaitEvent(ctx->compute, copied, 0));
-		return cg_launch_decompress(sh->d_arena, d_decode + f, l - f, ctx->d_stage_err, CG_ERRFLAG_DECOMPRESS, ctx->compute);
+		return cg_launch_decompress(ctx, sh->d_arena, d_decode + f, sp.decode.data() + f, l - f, ctx->d_stage_err, CG_ERRFLAG_DECOMPRESS,
+									ctx->compute);
 	});
 	if (rc == CG_OK && sp.any_nulls)
 	{
@@ -1221,8 +1219,8 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 			/* K7: compressed value streams of the block -> their value slots */
 			int r = CG_OK;
 			if (!decode_done)
-				r = cg_launch_decompress(d_arena, d_decode + sp.dec_first[cg0], sp.dec_first[cg1] - sp.dec_first[cg0],
-										 into->d_stats + 2, CG_ERRFLAG_DECOMPRESS, ctx->compute);
+				r = cg_launch_decompress(ctx, d_arena, d_decode + sp.dec_first[cg0], sp.decode.data() + sp.dec_first[cg0],
+										 sp.dec_first[cg1] - sp.dec_first[cg0], into->d_stats + 2, CG_ERRFLAG_DECOMPRESS, ctx->compute);
 			if (r) return r;
 			if (sp.any_nulls)
 			{
@@ -1299,7 +1297,10 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 			cudaEvent_t k0 = nullptr, k1 = nullptr, k2 = nullptr;
 			if (trace) { cudaEventCreate(&k0); cudaEventCreate(&k1); cudaEventCreate(&k2); cudaEventRecord(k0, ctx->compute); }
 			cudaEvent_t ready = ctx->dma_copied;
-			if (!sp.decode.empty() && !trace)
+			/* zstd decoders share one literal scratch area: they stay on the compute stream */
+			bool has_zstd = false;
+			for (const DecodeItem &di : sp.decode) if (di.kind == CG_COMPRESSION_ZSTD) { has_zstd = true; break; }
+			if (!sp.decode.empty() && !trace && !has_zstd)
 			{
 				/* de-framing and decompression run on one of two side streams, the scan follows on the
 				 * compute stream: the decode of this shard overlaps the decode (and scan) of the previous one */
@@ -1310,7 +1311,8 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 				CG_CUDA(cudaStreamWaitEvent(side, ctx->dma_copied, 0));
 				rc = cg_launch_realign(d_raw, d_arena, (const RealignItem *) (d_meta + off_items), items.size(), side);
 				if (rc == CG_OK)
-					rc = cg_launch_decompress(d_arena, d_decode, sp.decode.size(), into->d_stats + 2, CG_ERRFLAG_DECOMPRESS, side);
+					rc = cg_launch_decompress(ctx, d_arena, d_decode, sp.decode.data(), sp.decode.size(), into->d_stats + 2,
+											  CG_ERRFLAG_DECOMPRESS, side);
 				if (rc) return rc;
 				CG_CUDA(cudaEventRecord(ctx->decoded[mslot], side));
 				ready = ctx->decoded[mslot];

@@ -58,6 +58,8 @@ struct CgContext
 	cudaStream_t decode_stream[2] = {nullptr, nullptr};
 	unsigned decode_rr = 0;
 	cudaEvent_t decoded[kDmaDepth] = {nullptr, nullptr, nullptr};
+	uint8_t *zstd_scratch = nullptr;             /* literal buffers of the resident zstd decoders */
+	size_t zstd_scratch_bytes = 0;
 	unsigned long long *d_stage_err = nullptr;   /* error flags raised by staging kernels of cg_shard_stage */
 	/* per-launch profiling */
 	bool profiling = false;
@@ -301,10 +303,10 @@ struct DecodeItem
 	uint32_t comp_len;
 	uint32_t raw_len;
 	uint32_t padded;
-	uint32_t kind;      /* CG_COMPRESSION_LZ4 / CG_COMPRESSION_PGLZ */
+	uint32_t kind;      /* CG_COMPRESSION_LZ4 / CG_COMPRESSION_PGLZ / CG_COMPRESSION_ZSTD */
 };
-int cg_launch_decompress(uint8_t *arena, const DecodeItem *items, uint64_t nitems, unsigned long long *err,
-						 unsigned long long flag, cudaStream_t stream);
+int cg_launch_decompress(CgContext *ctx, uint8_t *arena, const DecodeItem *items, const DecodeItem *h_items, uint64_t nitems,
+						 unsigned long long *err, unsigned long long flag, cudaStream_t stream);
 
 /* cg_scan_small.cu */
 bool cg_small_eligible(const KPlan &plan);

@@ -1,0 +1,581 @@
+/*
+ * cg_zstd.cuh -- a Zstandard frame decoder that runs as ordinary sequential code on one GPU
+ * lane (and, for the CPU-side format tests, on the host: every function is __host__ __device__).
+ *
+ * Replaces the COMPRESSION_ZSTD arm of DecompressBuffer, backend/columnar/columnar_compression.c:
+ * 210-238: ZSTD_decompress(out, decompressedSize, buffer, len) must succeed and return exactly
+ * decompressedSize.  libzstd is not part of the reference tree; the frame format is the published
+ * one (RFC 8878): frame header, raw / RLE / compressed blocks, literals section (raw, RLE,
+ * Huffman with 1 or 4 streams, tree described by direct or FSE-compressed weights, "treeless"
+ * reuse), sequences section (predefined / RLE / FSE / repeat tables for literal lengths, offsets
+ * and match lengths, backward bitstream, repeat-offset history).  Not supported (the columnar
+ * writer never produces them, columnar_compression.c:103-123 calls plain ZSTD_compress): dictionaries
+ * and skippable frames; a content checksum, if present, is skipped, not verified.
+ *
+ * Work memory: the FSE / Huffman tables (ZstdTables, ~11 KB, shared memory on the GPU) and one
+ * literals buffer of up to 128 KB per stream being decoded (global memory).
+ */
+#ifndef CG_ZSTD_CUH
+#define CG_ZSTD_CUH
+
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define CG_HD __host__ __device__ __forceinline__
+#define CG_HDN __host__ __device__
+#else
+#define CG_HD inline
+#define CG_HDN
+#endif
+
+#define ZSTD_BLOCK_MAX (128u * 1024u)
+#define ZSTD_LL_LOG_MAX 9
+#define ZSTD_OF_LOG_MAX 8
+#define ZSTD_ML_LOG_MAX 9
+#define ZSTD_HUF_LOG_MAX 11
+#define ZSTD_ERR (-1)
+
+struct FseEntry { uint8_t symbol; uint8_t nbits; uint16_t base; };     /* next state = base + read(nbits) */
+struct FseTable { int log; FseEntry e[1 << ZSTD_LL_LOG_MAX]; };
+struct FseTableOf { int log; FseEntry e[1 << ZSTD_OF_LOG_MAX]; };
+struct HufEntry { uint8_t symbol; uint8_t nbits; };
+
+struct ZstdTables
+{
+	FseTable ll, ml;
+	FseTableOf of;
+	HufEntry huf[1 << ZSTD_HUF_LOG_MAX];
+	int huf_log;                /* 0 = no Huffman table yet */
+	int have_ll, have_of, have_ml;
+	uint32_t rep[3];
+	int16_t norm[256];          /* scratch: normalized counts / Huffman weights */
+	uint16_t next[256];         /* scratch: per-symbol state counters / rank starts */
+};
+
+CG_HD int zs_highbit(uint32_t v) { int r = -1; while (v) { v >>= 1; r++; } return r; }
+
+/* ---- forward bit reader (FSE table descriptions): LSB first ---- */
+struct ZsFwd { const uint8_t *p; uint32_t len; uint32_t bit; };
+CG_HD uint32_t zs_fwd_read(ZsFwd &r, int n)
+{
+	uint32_t v = 0;
+	for (int i = 0; i < n; i++)
+	{
+		uint32_t b = r.bit + (uint32_t) i, byte = b >> 3;
+		uint32_t x = byte < r.len ? (uint32_t) (r.p[byte] >> (b & 7u)) & 1u : 0u;
+		v |= x << i;
+	}
+	r.bit += (uint32_t) n;
+	return v;
+}
+
+/* ---- backward bit reader: the stream is a little-endian bit array whose highest set bit (in the
+ * last byte) is the end mark; read(n) returns the n bits just below the cursor, top bit first ---- */
+struct ZsBack { const uint8_t *p; int64_t pos; };    /* pos = number of unread bits; may go negative (zeros) */
+CG_HD bool zs_back_init(ZsBack &r, const uint8_t *p, uint32_t len)
+{
+	if (len == 0 || p[len - 1] == 0) return false;
+	r.p = p;
+	r.pos = (int64_t) (len - 1) * 8 + zs_highbit(p[len - 1]);
+	return true;
+}
+CG_HD uint32_t zs_back_peek_at(const ZsBack &r, int64_t pos, int n)   /* bits [pos - n, pos), zero below bit 0 */
+{
+	uint32_t v = 0;
+	for (int i = 0; i < n; i++)
+	{
+		int64_t b = pos - 1 - i;
+		uint32_t x = b >= 0 ? (uint32_t) (r.p[b >> 3] >> (b & 7)) & 1u : 0u;
+		v = (v << 1) | x;
+	}
+	return v;
+}
+CG_HD uint32_t zs_back_read(ZsBack &r, int n)
+{
+	/* fast path: the n bits lie inside one aligned-free 64-bit window */
+	uint32_t v;
+	if (n == 0) return 0;
+	if (r.pos - n >= 0)
+	{
+		int64_t lo = r.pos - n;
+		uint64_t w = 0;
+		int64_t byte = lo >> 3;
+		int need = (int) ((lo & 7) + n + 7) >> 3;
+		for (int i = 0; i < need; i++) w |= (uint64_t) r.p[byte + i] << (8 * i);
+		v = (uint32_t) ((w >> (lo & 7)) & ((1ull << n) - 1ull));
+	}
+	else
+		v = zs_back_peek_at(r, r.pos, n);
+	r.pos -= n;
+	return v;
+}
+
+/* ---- FSE ---- */
+/* reads a normalized-count description; returns bytes consumed or ZSTD_ERR.  norm[] gets the counts (-1 = "less than 1") */
+CG_HDN inline int zs_read_ncount(const uint8_t *src, uint32_t len, int max_log, int max_symbol, int16_t *norm, int *log_out, int *nsym_out)
+{
+	ZsFwd r{src, len, 0};
+	int log = 5 + (int) zs_fwd_read(r, 4);
+	if (log > max_log) return ZSTD_ERR;
+	int remaining = 1 << log, symb = 0;
+	while (remaining > 0 && symb <= max_symbol)
+	{
+		int bits = zs_highbit((uint32_t) (remaining + 1)) + 1;
+		uint32_t val = zs_fwd_read(r, bits);
+		uint32_t lower_mask = (1u << (bits - 1)) - 1u;
+		uint32_t threshold = (1u << bits) - 1u - (uint32_t) (remaining + 1);
+		if ((val & lower_mask) < threshold) { r.bit--; val &= lower_mask; }
+		else if (val > lower_mask) val -= threshold;
+		int proba = (int) val - 1;
+		remaining -= proba < 0 ? -proba : proba;
+		norm[symb++] = (int16_t) proba;
+		if (proba == 0)
+		{
+			uint32_t repeat = zs_fwd_read(r, 2);
+			for (;;)
+			{
+				for (uint32_t i = 0; i < repeat && symb <= max_symbol; i++) norm[symb++] = 0;
+				if (repeat == 3) repeat = zs_fwd_read(r, 2); else break;
+			}
+		}
+		if ((r.bit >> 3) > len) return ZSTD_ERR;
+	}
+	if (remaining != 0 || symb > max_symbol + 1) return ZSTD_ERR;
+	*log_out = log;
+	*nsym_out = symb;
+	uint32_t used = (r.bit + 7) >> 3;
+	if (used > len) return ZSTD_ERR;
+	return (int) used;
+}
+
+/* decoding table from normalized counts (spread with step (size>>1)+(size>>3)+3, "less than 1" symbols at the top) */
+CG_HDN inline int zs_build_fse(FseEntry *e, int log, const int16_t *norm, int nsym, uint16_t *next)
+{
+	const uint32_t size = 1u << log;
+	uint32_t high = size;
+	for (int s = 0; s < nsym; s++)
+		if (norm[s] == -1) { e[--high].symbol = (uint8_t) s; next[s] = 1; }
+	const uint32_t step = (size >> 1) + (size >> 3) + 3, mask = size - 1;
+	uint32_t pos = 0;
+	for (int s = 0; s < nsym; s++)
+	{
+		if (norm[s] <= 0) continue;
+		next[s] = (uint16_t) norm[s];
+		for (int i = 0; i < norm[s]; i++)
+		{
+			e[pos].symbol = (uint8_t) s;
+			do { pos = (pos + step) & mask; } while (pos >= high);
+		}
+	}
+	if (pos != 0) return ZSTD_ERR;
+	for (uint32_t i = 0; i < size; i++)
+	{
+		uint32_t ns = next[e[i].symbol]++;
+		int nb = log - zs_highbit(ns);
+		e[i].nbits = (uint8_t) nb;
+		e[i].base = (uint16_t) ((ns << nb) - size);
+	}
+	return 0;
+}
+
+CG_HDN inline void zs_build_rle(FseEntry *e, int *log, uint8_t symbol)
+{
+	*log = 0;
+	e[0].symbol = symbol; e[0].nbits = 0; e[0].base = 0;
+}
+
+/* ---- Huffman ---- */
+/* weights[0..n) given (n < 256): derive the last weight, build the single-symbol decoding table */
+CG_HDN inline int zs_build_huf(ZstdTables &T, int n)
+{
+	int16_t *w = T.norm;
+	uint32_t total = 0;
+	for (int i = 0; i < n; i++)
+	{
+		if (w[i] > ZSTD_HUF_LOG_MAX) return ZSTD_ERR;
+		if (w[i] > 0) total += 1u << (w[i] - 1);
+	}
+	if (total == 0) return ZSTD_ERR;
+	int log = zs_highbit(total) + 1;
+	if (log > ZSTD_HUF_LOG_MAX) return ZSTD_ERR;
+	uint32_t rest = (1u << log) - total;
+	if (rest == 0 || (rest & (rest - 1)) != 0) return ZSTD_ERR;
+	w[n] = (int16_t) (zs_highbit(rest) + 1);
+	n++;
+	/* entries in order of increasing weight, symbols in natural order inside one weight */
+	uint32_t pos = 0;
+	for (int weight = 1; weight <= log; weight++)
+		for (int s = 0; s < n; s++)
+			if (w[s] == weight)
+			{
+				uint32_t span = 1u << (weight - 1);
+				for (uint32_t i = 0; i < span; i++) { T.huf[pos + i].symbol = (uint8_t) s; T.huf[pos + i].nbits = (uint8_t) (log + 1 - weight); }
+				pos += span;
+			}
+	if (pos != (1u << log)) return ZSTD_ERR;
+	T.huf_log = log;
+	return 0;
+}
+
+/* Huffman tree description; returns bytes consumed or ZSTD_ERR */
+CG_HDN inline int zs_read_huf_tree(ZstdTables &T, const uint8_t *src, uint32_t len)
+{
+	if (len < 1) return ZSTD_ERR;
+	uint32_t hb = src[0];
+	int n = 0;
+	uint32_t used;
+	if (hb >= 128)
+	{
+		n = (int) hb - 127;
+		uint32_t bytes = (uint32_t) (n + 1) / 2;
+		if (1 + bytes > len) return ZSTD_ERR;
+		for (int i = 0; i < n; i++)
+		{
+			uint8_t b = src[1 + i / 2];
+			T.norm[i] = (int16_t) ((i & 1) ? (b & 15) : (b >> 4));
+		}
+		used = 1 + bytes;
+	}
+	else
+	{
+		/* FSE-compressed weights: table (accuracy <= 6) + two interleaved states over a backward bitstream */
+		if (hb == 0 || 1 + hb > len) return ZSTD_ERR;
+		const uint8_t *p = src + 1;
+		int16_t norm[16];
+		uint16_t next[16];
+		int log = 0, nsym = 0;
+		int hdr = zs_read_ncount(p, hb, 6, 12, norm, &log, &nsym);
+		if (hdr < 0) return ZSTD_ERR;
+		FseEntry e[64];
+		if (zs_build_fse(e, log, norm, nsym, next) < 0) return ZSTD_ERR;
+		ZsBack r;
+		if ((uint32_t) hdr >= hb || !zs_back_init(r, p + hdr, hb - (uint32_t) hdr)) return ZSTD_ERR;
+		uint32_t s1 = zs_back_read(r, log), s2 = zs_back_read(r, log);
+		if (r.pos < 0) return ZSTD_ERR;
+		for (;;)
+		{
+			if (n >= 254) return ZSTD_ERR;
+			T.norm[n++] = e[s1].symbol;
+			s1 = e[s1].base + zs_back_read(r, e[s1].nbits);
+			if (r.pos < 0) { T.norm[n++] = e[s2].symbol; break; }
+			if (n >= 254) return ZSTD_ERR;
+			T.norm[n++] = e[s2].symbol;
+			s2 = e[s2].base + zs_back_read(r, e[s2].nbits);
+			if (r.pos < 0) { T.norm[n++] = e[s1].symbol; break; }
+		}
+		used = 1 + hb;
+	}
+	if (n < 1 || n > 255) return ZSTD_ERR;
+	if (zs_build_huf(T, n) < 0) return ZSTD_ERR;
+	return (int) used;
+}
+
+/* one Huffman stream: exactly `count` symbols, every bit consumed */
+CG_HDN inline int zs_huf_stream(const ZstdTables &T, const uint8_t *src, uint32_t len, uint8_t *out, uint32_t count)
+{
+	ZsBack r;
+	if (!zs_back_init(r, src, len)) return ZSTD_ERR;
+	const int log = T.huf_log;
+	for (uint32_t i = 0; i < count; i++)
+	{
+		uint32_t idx;
+		if (r.pos >= log)
+		{
+			int64_t lo = r.pos - log;
+			int64_t byte = lo >> 3;
+			uint32_t w = (uint32_t) r.p[byte] | ((uint32_t) (byte + 1 < (int64_t) len ? r.p[byte + 1] : 0) << 8) |
+						 ((uint32_t) (byte + 2 < (int64_t) len ? r.p[byte + 2] : 0) << 16);
+			idx = (w >> (lo & 7)) & ((1u << log) - 1u);
+		}
+		else
+			idx = zs_back_peek_at(r, r.pos, log);
+		const HufEntry h = T.huf[idx];
+		out[i] = h.symbol;
+		r.pos -= h.nbits;
+		if (r.pos < 0) return ZSTD_ERR;
+	}
+	return r.pos == 0 ? 0 : ZSTD_ERR;
+}
+
+/* literals section: fills lit[0..*nlit); returns bytes consumed or ZSTD_ERR */
+CG_HDN inline int zs_literals(ZstdTables &T, const uint8_t *src, uint32_t len, uint8_t *lit, uint32_t *nlit)
+{
+	if (len < 1) return ZSTD_ERR;
+	const uint32_t type = src[0] & 3u, fmt = (src[0] >> 2) & 3u;
+	uint32_t regen, comp = 0, hdr;
+	if (type < 2)
+	{
+		if ((fmt & 1u) == 0) { regen = src[0] >> 3; hdr = 1; }
+		else if (fmt == 1) { if (len < 2) return ZSTD_ERR; regen = (src[0] >> 4) + ((uint32_t) src[1] << 4); hdr = 2; }
+		else { if (len < 3) return ZSTD_ERR; regen = (src[0] >> 4) + ((uint32_t) src[1] << 4) + ((uint32_t) src[2] << 12); hdr = 3; }
+		if (regen > ZSTD_BLOCK_MAX) return ZSTD_ERR;
+		if (type == 0)
+		{
+			if (hdr + regen > len) return ZSTD_ERR;
+			for (uint32_t i = 0; i < regen; i++) lit[i] = src[hdr + i];
+			*nlit = regen;
+			return (int) (hdr + regen);
+		}
+		if (hdr + 1 > len) return ZSTD_ERR;
+		for (uint32_t i = 0; i < regen; i++) lit[i] = src[hdr];
+		*nlit = regen;
+		return (int) (hdr + 1);
+	}
+	int streams = 4;
+	if (fmt < 2)
+	{
+		if (len < 3) return ZSTD_ERR;
+		uint32_t h = src[0] | ((uint32_t) src[1] << 8) | ((uint32_t) src[2] << 16);
+		regen = (h >> 4) & 0x3FFu; comp = (h >> 14) & 0x3FFu; hdr = 3;
+		if (fmt == 0) streams = 1;
+	}
+	else if (fmt == 2)
+	{
+		if (len < 4) return ZSTD_ERR;
+		uint32_t h = src[0] | ((uint32_t) src[1] << 8) | ((uint32_t) src[2] << 16) | ((uint32_t) src[3] << 24);
+		regen = (h >> 4) & 0x3FFFu; comp = (h >> 18) & 0x3FFFu; hdr = 4;
+	}
+	else
+	{
+		if (len < 5) return ZSTD_ERR;
+		uint64_t h = (uint64_t) src[0] | ((uint64_t) src[1] << 8) | ((uint64_t) src[2] << 16) | ((uint64_t) src[3] << 24) | ((uint64_t) src[4] << 32);
+		regen = (uint32_t) ((h >> 4) & 0x3FFFFu); comp = (uint32_t) ((h >> 22) & 0x3FFFFu); hdr = 5;
+	}
+	if (regen > ZSTD_BLOCK_MAX || hdr + comp > len) return ZSTD_ERR;
+	const uint8_t *p = src + hdr;
+	uint32_t left = comp;
+	if (type == 2)
+	{
+		int used = zs_read_huf_tree(T, p, left);
+		if (used < 0) return ZSTD_ERR;
+		p += used; left -= (uint32_t) used;
+	}
+	else if (T.huf_log == 0) return ZSTD_ERR;       /* treeless without a previous table */
+	if (streams == 1)
+	{
+		if (zs_huf_stream(T, p, left, lit, regen) < 0) return ZSTD_ERR;
+	}
+	else
+	{
+		if (left < 6) return ZSTD_ERR;
+		uint32_t s1 = p[0] | ((uint32_t) p[1] << 8), s2 = p[2] | ((uint32_t) p[3] << 8), s3 = p[4] | ((uint32_t) p[5] << 8);
+		if (6 + s1 + s2 + s3 > left) return ZSTD_ERR;
+		uint32_t s4 = left - 6 - s1 - s2 - s3;
+		uint32_t per = (regen + 3) / 4;
+		if (3 * per > regen) return ZSTD_ERR;
+		const uint8_t *q = p + 6;
+		if (zs_huf_stream(T, q, s1, lit, per) < 0) return ZSTD_ERR;
+		if (zs_huf_stream(T, q + s1, s2, lit + per, per) < 0) return ZSTD_ERR;
+		if (zs_huf_stream(T, q + s1 + s2, s3, lit + 2 * per, per) < 0) return ZSTD_ERR;
+		if (zs_huf_stream(T, q + s1 + s2 + s3, s4, lit + 3 * per, regen - 3 * per) < 0) return ZSTD_ERR;
+	}
+	*nlit = regen;
+	return (int) (hdr + comp);
+}
+
+/* ---- sequences ---- */
+CG_HD void zs_ll_code(uint32_t code, uint32_t *base, int *bits)
+{
+	if (code < 16) { *base = code; *bits = 0; return; }
+	static const uint32_t b[20] = {16, 18, 20, 22, 24, 28, 32, 40, 48, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536};
+	static const uint8_t n[20] = {1, 1, 1, 1, 2, 2, 3, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
+	*base = b[code - 16]; *bits = n[code - 16];
+}
+CG_HD void zs_ml_code(uint32_t code, uint32_t *base, int *bits)
+{
+	if (code < 32) { *base = code + 3; *bits = 0; return; }
+	static const uint32_t b[21] = {35, 37, 39, 41, 43, 47, 51, 59, 67, 83, 99, 131, 259, 515, 1027, 2051, 4099, 8195, 16387, 32771, 65539};
+	static const uint8_t n[21] = {1, 1, 1, 1, 2, 2, 3, 3, 4, 4, 5, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
+	*base = b[code - 32]; *bits = n[code - 32];
+}
+
+/* one of the three symbol tables: mode 0 predefined, 1 RLE, 2 FSE description, 3 repeat; returns bytes consumed */
+CG_HDN inline int zs_seq_table(ZstdTables &T, int which, int mode, const uint8_t *src, uint32_t len)
+{
+	FseEntry *e = which == 0 ? T.ll.e : which == 1 ? T.of.e : T.ml.e;
+	int *log = which == 0 ? &T.ll.log : which == 1 ? &T.of.log : &T.ml.log;
+	int *have = which == 0 ? &T.have_ll : which == 1 ? &T.have_of : &T.have_ml;
+	const int max_log = which == 0 ? ZSTD_LL_LOG_MAX : which == 1 ? ZSTD_OF_LOG_MAX : ZSTD_ML_LOG_MAX;
+	const int max_sym = which == 0 ? 35 : which == 1 ? 31 : 52;
+	if (mode == 3) return *have ? 0 : ZSTD_ERR;
+	*have = 1;
+	if (mode == 1)
+	{
+		if (len < 1 || src[0] > max_sym) return ZSTD_ERR;
+		zs_build_rle(e, log, src[0]);
+		return 1;
+	}
+	int nsym = 0, used = 0;
+	if (mode == 0)
+	{
+		static const int8_t ll_def[36] = {4, 3, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2, 1, 1, 1, 1, 1, -1, -1, -1, -1};
+		static const int8_t of_def[29] = {1, 1, 1, 1, 1, 1, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1};
+		static const int8_t ml_def[53] = {1, 4, 3, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1,
+								   1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1, -1, -1};
+		if (which == 0) { nsym = 36; *log = 6; for (int i = 0; i < nsym; i++) T.norm[i] = ll_def[i]; }
+		else if (which == 1) { nsym = 29; *log = 5; for (int i = 0; i < nsym; i++) T.norm[i] = of_def[i]; }
+		else { nsym = 53; *log = 6; for (int i = 0; i < nsym; i++) T.norm[i] = ml_def[i]; }
+	}
+	else
+	{
+		used = zs_read_ncount(src, len, max_log, max_sym, T.norm, log, &nsym);
+		if (used < 0) return ZSTD_ERR;
+	}
+	if (zs_build_fse(e, *log, T.norm, nsym, T.next) < 0) return ZSTD_ERR;
+	return used;
+}
+
+/* overlapping forward copy (LZ77 semantics) */
+CG_HD void zs_copy_match(uint8_t *dst, uint32_t op, uint32_t off, uint32_t n)
+{
+	const uint8_t *m = dst + op - off;
+	uint8_t *d = dst + op;
+	for (uint32_t i = 0; i < n; i++) d[i] = m[i];
+}
+
+/* one compressed block; dst/op: the frame's output so far; returns the new op or ZSTD_ERR */
+CG_HDN inline int64_t zs_compressed_block(ZstdTables &T, const uint8_t *src, uint32_t len, uint8_t *dst, uint32_t op, uint32_t cap,
+										  uint8_t *lit)
+{
+	uint32_t nlit = 0;
+	int used = zs_literals(T, src, len, lit, &nlit);
+	if (used < 0) return ZSTD_ERR;
+	const uint8_t *p = src + used;
+	uint32_t left = len - (uint32_t) used;
+	if (left < 1) return ZSTD_ERR;
+	uint32_t nseq;
+	if (p[0] == 0) { nseq = 0; p += 1; left -= 1; }
+	else if (p[0] < 128) { nseq = p[0]; p += 1; left -= 1; }
+	else if (p[0] < 255) { if (left < 2) return ZSTD_ERR; nseq = ((uint32_t) (p[0] - 128) << 8) + p[1]; p += 2; left -= 2; }
+	else { if (left < 3) return ZSTD_ERR; nseq = (uint32_t) p[1] + ((uint32_t) p[2] << 8) + 0x7F00u; p += 3; left -= 3; }
+	uint32_t litpos = 0;
+	if (nseq > 0)
+	{
+		if (left < 1) return ZSTD_ERR;
+		const uint32_t modes = p[0];
+		if (modes & 3u) return ZSTD_ERR;
+		p += 1; left -= 1;
+		for (int which = 0; which < 3; which++)
+		{
+			int mode = (int) (modes >> (6 - 2 * which)) & 3;
+			int u = zs_seq_table(T, which, mode, p, left);
+			if (u < 0) return ZSTD_ERR;
+			p += u; left -= (uint32_t) u;
+		}
+		ZsBack r;
+		if (!zs_back_init(r, p, left)) return ZSTD_ERR;
+		uint32_t sl = zs_back_read(r, T.ll.log), so = zs_back_read(r, T.of.log), sm = zs_back_read(r, T.ml.log);
+		if (r.pos < 0) return ZSTD_ERR;
+		for (uint32_t s = 0; s < nseq; s++)
+		{
+			const uint32_t of_code = T.of.e[so].symbol, ml_sym = T.ml.e[sm].symbol, ll_sym = T.ll.e[sl].symbol;
+			if (of_code > 31) return ZSTD_ERR;
+			uint32_t ofv = (1u << of_code) + zs_back_read(r, (int) of_code);
+			uint32_t mbase, lbase; int mbits, lbits;
+			zs_ml_code(ml_sym, &mbase, &mbits);
+			zs_ll_code(ll_sym, &lbase, &lbits);
+			const uint32_t mlen = mbase + zs_back_read(r, mbits);
+			const uint32_t llen = lbase + zs_back_read(r, lbits);
+			if (s + 1 < nseq)
+			{
+				sl = T.ll.e[sl].base + zs_back_read(r, T.ll.e[sl].nbits);
+				sm = T.ml.e[sm].base + zs_back_read(r, T.ml.e[sm].nbits);
+				so = T.of.e[so].base + zs_back_read(r, T.of.e[so].nbits);
+			}
+			if (r.pos < 0) return ZSTD_ERR;
+			/* repeat-offset history */
+			uint32_t offset;
+			if (ofv > 3)
+			{
+				offset = ofv - 3;
+				T.rep[2] = T.rep[1]; T.rep[1] = T.rep[0]; T.rep[0] = offset;
+			}
+			else
+			{
+				uint32_t idx = ofv - 1 + (llen == 0 ? 1u : 0u);       /* 0..3 */
+				if (idx == 0) offset = T.rep[0];
+				else
+				{
+					offset = idx < 3 ? T.rep[idx] : T.rep[0] - 1;
+					if (offset == 0) return ZSTD_ERR;
+					if (idx > 1) T.rep[2] = T.rep[1];
+					T.rep[1] = T.rep[0];
+					T.rep[0] = offset;
+				}
+			}
+			if (llen > nlit - litpos || llen > cap - op) return ZSTD_ERR;
+			for (uint32_t i = 0; i < llen; i++) dst[op + i] = lit[litpos + i];
+			op += llen; litpos += llen;
+			if (offset > op || mlen > cap - op) return ZSTD_ERR;
+			zs_copy_match(dst, op, offset, mlen);
+			op += mlen;
+		}
+		if (r.pos != 0) return ZSTD_ERR;
+	}
+	const uint32_t rest = nlit - litpos;
+	if (rest > cap - op) return ZSTD_ERR;
+	for (uint32_t i = 0; i < rest; i++) dst[op + i] = lit[litpos + i];
+	return (int64_t) op + rest;
+}
+
+/*
+ * One frame (what ZSTD_compress emits): returns the number of bytes produced (the caller compares it
+ * with decompressedValueSize, like columnar_compression.c:226-232) or ZSTD_ERR.  lit: scratch of
+ * ZSTD_BLOCK_MAX bytes.
+ */
+CG_HDN inline int64_t zs_decode_frame(ZstdTables &T, const uint8_t *src, uint32_t len, uint8_t *dst, uint32_t cap, uint8_t *lit)
+{
+	if (len < 6) return ZSTD_ERR;
+	if (src[0] != 0x28 || src[1] != 0xB5 || src[2] != 0x2F || src[3] != 0xFD) return ZSTD_ERR;
+	const uint32_t fhd = src[4];
+	const uint32_t fcs_flag = fhd >> 6, single = (fhd >> 5) & 1u, checksum = (fhd >> 2) & 1u, dict_flag = fhd & 3u;
+	if (fhd & 0x08u) return ZSTD_ERR;                 /* reserved bit */
+	if (dict_flag) return ZSTD_ERR;                   /* dictionaries: never used by the columnar writer */
+	uint32_t pos = 5;
+	if (!single) pos += 1;                            /* window descriptor: the whole output is addressable here */
+	const uint32_t fcs_bytes = fcs_flag == 0 ? (single ? 1u : 0u) : fcs_flag == 1 ? 2u : fcs_flag == 2 ? 4u : 8u;
+	if (pos + fcs_bytes > len) return ZSTD_ERR;
+	uint64_t fcs = 0;
+	for (uint32_t i = 0; i < fcs_bytes; i++) fcs |= (uint64_t) src[pos + i] << (8 * i);
+	if (fcs_bytes == 2) fcs += 256;
+	pos += fcs_bytes;
+	if (fcs_bytes && fcs > cap) return ZSTD_ERR;
+	T.huf_log = 0; T.have_ll = T.have_of = T.have_ml = 0;
+	T.rep[0] = 1; T.rep[1] = 4; T.rep[2] = 8;
+	uint32_t op = 0;
+	for (;;)
+	{
+		if (pos + 3 > len) return ZSTD_ERR;
+		const uint32_t bh = src[pos] | ((uint32_t) src[pos + 1] << 8) | ((uint32_t) src[pos + 2] << 16);
+		pos += 3;
+		const uint32_t last = bh & 1u, type = (bh >> 1) & 3u, bsize = bh >> 3;
+		if (type == 0)
+		{
+			if (bsize > ZSTD_BLOCK_MAX || pos + bsize > len || bsize > cap - op) return ZSTD_ERR;
+			for (uint32_t i = 0; i < bsize; i++) dst[op + i] = src[pos + i];
+			op += bsize; pos += bsize;
+		}
+		else if (type == 1)
+		{
+			if (bsize > ZSTD_BLOCK_MAX || pos + 1 > len || bsize > cap - op) return ZSTD_ERR;
+			for (uint32_t i = 0; i < bsize; i++) dst[op + i] = src[pos];
+			op += bsize; pos += 1;
+		}
+		else if (type == 2)
+		{
+			if (bsize > ZSTD_BLOCK_MAX || pos + bsize > len) return ZSTD_ERR;
+			int64_t nop = zs_compressed_block(T, src + pos, bsize, dst, op, cap, lit);
+			if (nop < 0 || nop - (int64_t) op > (int64_t) ZSTD_BLOCK_MAX) return ZSTD_ERR;
+			op = (uint32_t) nop; pos += bsize;
+		}
+		else
+			return ZSTD_ERR;
+		if (last) break;
+	}
+	if (checksum) { if (pos + 4 > len) return ZSTD_ERR; pos += 4; }
+	if (pos != len) return ZSTD_ERR;                   /* one frame, nothing behind it */
+	if (fcs_bytes && fcs != op) return ZSTD_ERR;
+	return (int64_t) op;
+}
+
+#endif

@@ -211,8 +211,7 @@ typedef struct CgScanStats
 typedef struct CgShard CgShard;
 
 /* columns: attribute indexes to stage (NULL/0 = all).  The call returns when the shard
- * is resident.  Only CG_COMPRESSION_NONE chunks are accepted in this round
- * (CG_EUNSUPPORTED otherwise). */
+ * is resident.  Compressed value streams (lz4, pglz, zstd) are decoded on the GPU behind the copies. */
 int cg_shard_stage(const CgRelation *rel, const int32_t *columns, int32_t ncolumns, CgShard **out);
 void cg_shard_free(CgShard *shard);
 uint64_t cg_shard_device_bytes(const CgShard *shard);
@@ -383,9 +382,14 @@ int cg_gen_relation(const CgGenColumn *cols, int32_t natts, uint64_t nrows, uint
 int cg_write_relation(const CgColumnDesc *cols, int32_t natts, const int64_t *const *values,
 					  const uint8_t *const *nulls, uint64_t nrows, uint64_t stripe_row_limit,
 					  uint32_t chunk_row_limit, CgGenRelation **out);
-/* columnar.compression of the relations written after the call: CG_COMPRESSION_NONE or
- * CG_COMPRESSION_LZ4 (liblz4's LZ4_compress_default, as the reference's CompressBuffer) */
+/* columnar.compression of the relations written after the call: CG_COMPRESSION_NONE,
+ * CG_COMPRESSION_LZ4 or CG_COMPRESSION_ZSTD (liblz4's LZ4_compress_default / libzstd's
+ * ZSTD_compress at level 3, as the reference's CompressBuffer) */
 int cg_gen_set_compression(int32_t compression);
+/* Test hook: the library's Zstandard decoder (the code cg_zstd_kernel runs on one GPU lane) executed on
+ * the host, so that the bit-level format logic can be checked against libzstd without a GPU.  Returns the
+ * decoded size or -1.  Nothing in the data path calls it. */
+int64_t cg_test_zstd_decode_host(const uint8_t *src, uint32_t len, uint8_t *dst, uint32_t cap);
 int cg_gen_relation_view(const CgGenRelation *g, CgRelation *view);
 void cg_gen_relation_free(CgGenRelation *g);
 

@@ -355,11 +355,13 @@ def _compressed_relation(cg, oracle, comp, n, seed, stripe=150000, chunk=10000):
 
 
 @pytest.mark.parametrize("path", ["shard", "e2e", "dma"])
-@pytest.mark.parametrize("comp", ["lz4", "pglz"])
+@pytest.mark.parametrize("comp", ["lz4", "pglz", "zstd"])
 def test_compressed_chunks(cg, oracle, comp, path):
     if comp == "lz4" and not oracle.lib().orc_have_lz4():
         pytest.skip("liblz4 missing")
-    code = oracle.COMP_LZ4 if comp == "lz4" else oracle.COMP_PGLZ
+    if comp == "zstd" and not oracle.lib().orc_have_zstd():
+        pytest.skip("libzstd missing")
+    code = {"lz4": oracle.COMP_LZ4, "pglz": oracle.COMP_PGLZ, "zstd": oracle.COMP_ZSTD}[comp]
     for n, stripe, chunk in ((123_457, 50_000, 10_000), (2_001, 1_000, 1_000)):
         t, rel, kinds = _compressed_relation(cg, oracle, code, n, seed=n, stripe=stripe, chunk=chunk)
         assert code in kinds
@@ -374,12 +376,14 @@ def test_compressed_chunks(cg, oracle, comp, path):
         run_both(cg, oracle, rel, aggs=[cg.count_star(), cg.sum_(2), cg.count(5), cg.sum_(0)], chunk_row_limit=chunk, e2e=e2e)
 
 
-@pytest.mark.parametrize("comp", ["lz4", "pglz"])
+@pytest.mark.parametrize("comp", ["lz4", "pglz", "zstd"])
 def test_corrupt_compressed_stream_is_reported(cg, oracle, comp):
     from citus_b200 import capi
     if comp == "lz4" and not oracle.lib().orc_have_lz4():
         pytest.skip("liblz4 missing")
-    code = oracle.COMP_LZ4 if comp == "lz4" else oracle.COMP_PGLZ
+    if comp == "zstd" and not oracle.lib().orc_have_zstd():
+        pytest.skip("libzstd missing")
+    code = {"lz4": oracle.COMP_LZ4, "pglz": oracle.COMP_PGLZ, "zstd": oracle.COMP_ZSTD}[comp]
     t = oracle.Table([8], compression=code)
     t.insert([np.arange(30000) % 11])
     nodes = t.nodes_array().copy()
@@ -401,13 +405,14 @@ def test_corrupt_compressed_stream_is_reported(cg, oracle, comp):
 
 def test_unsupported_inputs_are_refused(cg, oracle):
     from citus_b200 import capi
-    if oracle.lib().orc_have_zstd():
-        t = oracle.Table([8], compression=oracle.COMP_ZSTD)
-        t.insert([np.arange(50000) % 7])
-        rel = cg.Relation.from_image(t.pages(), t.stripes_array(), t.nodes_array(), [8])
-        with pytest.raises(capi.CitusGpuError) as e:
-            cg.Shard(rel)
-        assert e.value.code == capi.CG_EUNSUPPORTED
+    t = oracle.Table([8])
+    t.insert([np.arange(50000) % 7])
+    nodes = t.nodes_array().copy()
+    nodes[4:8].view(np.int32)[0] = 7                                            # no such CompressionType
+    rel = cg.Relation.from_image(t.pages(), t.stripes_array(), nodes, [8])
+    with pytest.raises(capi.CitusGpuError) as e:
+        cg.Shard(rel)
+    assert e.value.code == capi.CG_ECORRUPT
     rel = cg.Relation.write([8], [np.arange(10)])
     with pytest.raises(capi.CitusGpuError):
         cg.GpuColumnarAgg(cg.make_desc(aggs=[cg.sum_(3)]), rel.column_descs())     # column out of range

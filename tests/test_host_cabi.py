@@ -92,6 +92,17 @@ def test_writer_matches_oracle_writer_byte_for_byte(cg, oracle):
         t.insert([a, b, c, d % 100], nulls=[None, nb, None, nd])
         assert any(nd_.compression_type == oracle.COMP_LZ4 for nd_ in t.nodes())
         _same_image(rel, t)
+    if oracle.lib().orc_have_zstd():
+        cg.set_writer_compression("zstd")
+        try:
+            rel = cg.Relation.write([8, 4, 2, 1], [a, b, c, d % 100], [None, nb, None, nd],
+                                    stripe_row_limit=5000, chunk_row_limit=1000)
+        finally:
+            cg.set_writer_compression("none")
+        t = oracle.Table([8, 4, 2, 1], stripe_row_limit=5000, chunk_row_limit=1000, compression=oracle.COMP_ZSTD)
+        t.insert([a, b, c, d % 100], nulls=[None, nb, None, nd])
+        assert any(nd_.compression_type == oracle.COMP_ZSTD for nd_ in t.nodes())
+        _same_image(rel, t)
 
 
 def test_float_columns_and_default_limits(cg, oracle):
@@ -250,3 +261,40 @@ def test_jit_generates_valid_sm100a_code_for_every_plan_form(cg):
     kind, src = _jit_check(cg, [(1, ">=", 0)], [0], [cg.sum_(1, True), cg.min_(1, True), cg.max_(2, True), cg.count_star()],
                            [4, 8, 4], 0, 10**6, 10**6, float_cols=(1, 2))
     assert "fcmp(v" in src and "f8_ordered" in src and "__uint_as_float" in src
+
+
+# --------------------------------------------------------------------------- Zstandard decoder (format logic on the host)
+def test_zstd_decoder_against_libzstd(cg, oracle):
+    """cg_zstd.cuh is sequential code one GPU lane runs; the same source is executed here on the host
+    against streams produced by libzstd's ZSTD_compress (what the reference's CompressBuffer calls)"""
+    from citus_b200 import capi
+    if not oracle.lib().orc_have_zstd():
+        pytest.skip("libzstd missing")
+    rng = np.random.default_rng(0)
+    cases = {
+        "empty": b"", "one byte": b"x", "zeros": bytes(100_000),
+        "arange%7 int64": (np.arange(10_000) % 7).astype(np.int64).tobytes(),
+        "uniform<100 int64": rng.integers(0, 100, 10_000).astype(np.int64).tobytes(),
+        "uniform<1e6 int64": rng.integers(0, 10**6, 10_000).astype(np.int64).tobytes(),
+        "incompressible": rng.integers(0, 256, 80_000).astype(np.uint8).tobytes(),          # raw blocks
+        "signed int64": rng.integers(-10**9, 10**9, 10_000).astype(np.int64).tobytes(),
+        "text": (b"the quick brown fox jumps over the lazy dog. " * 3000)[:100_000],
+        "800 KB, several blocks": rng.integers(0, 1000, 100_000).astype(np.int64).tobytes(),  # repeat modes / treeless literals
+        "skewed bytes": rng.choice(np.arange(256, dtype=np.uint8), 200_000, p=np.r_[0.5, np.full(255, 0.5 / 255)]).tobytes(),
+        "runs": np.repeat(rng.integers(0, 100, 200), 500).astype(np.int8).tobytes(),         # RLE blocks / long matches
+    }
+    for n in (2, 3, 17, 255, 256, 257, 4095, 65_536, 131_071, 131_072, 131_073, 262_145):
+        cases[f"mixed n={n}"] = (rng.integers(0, 50, n) * rng.integers(0, 2, n)).astype(np.uint8).tobytes()
+    for name, data in cases.items():
+        for level in ((1, 3, 9, 19) if len(data) <= 200_000 and not name.startswith("mixed") else (3,)):
+            comp = oracle.codec_compress(oracle.COMP_ZSTD, data, level)
+            assert comp is not None
+            src = np.frombuffer(comp, np.uint8)
+            dst = np.zeros(len(data) + 64, np.uint8)
+            n = capi.lib().cg_test_zstd_decode_host(src.ctypes.data, len(comp), dst.ctypes.data, len(data))
+            assert n == len(data) and dst[:len(data)].tobytes() == data, (name, level)
+            # damaged streams are rejected, never decoded to something else of the right size silently ... except
+            # where the damage lands in unused bits; a truncated stream always fails
+            if len(comp) > 12:
+                n = capi.lib().cg_test_zstd_decode_host(src.ctypes.data, len(comp) - 1, dst.ctypes.data, len(data))
+                assert n != len(data), (name, level, "truncated")
