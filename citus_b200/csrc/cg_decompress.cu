@@ -311,10 +311,12 @@ cg_decompress_kernel(uint8_t *arena, const DecodeItem *items, uint32_t nitems, u
  * Zstandard (cg_zstd.cuh): entropy decoding (FSE state machines, Huffman bit streams) is a serial
  * dependency chain per stream, so a stream is decoded by ONE lane running ordinary sequential code
  * -- the same source the CPU-side format tests run on the host -- and the parallelism comes from
- * the number of streams (a C2 shard has ~10^4).  One warp per CTA; its tables (ZstdTables, ~10 KB)
- * live in shared memory, its literals buffer (128 KB) in a context-owned scratch area; persistent
+ * the number of streams (a C2 shard has ~10^4).  One warp per CTA; its FSE tables (ZstdTables, ~7 KB)
+ * live in shared memory, its Huffman table and literals buffer (132 KB) in a context-owned scratch area; persistent
  * CTAs stride over the decode list.  The other lanes only help with the slot's zero padding.
  */
+#define CGD_ZSTD_SCRATCH (ZSTD_BLOCK_MAX + 64 + sizeof(HufEntry) * (1u << ZSTD_HUF_LOG_MAX))   /* literals + Huffman table */
+
 __global__ void __launch_bounds__(32)
 cg_zstd_kernel(uint8_t *arena, const DecodeItem *items, uint32_t nitems, uint8_t *lit_scratch, unsigned long long *err,
 			   unsigned long long flag)
@@ -322,7 +324,9 @@ cg_zstd_kernel(uint8_t *arena, const DecodeItem *items, uint32_t nitems, uint8_t
 	__shared__ ZstdTables T;
 	__shared__ int s_ok;
 	const uint32_t lane = threadIdx.x;
-	uint8_t *lit = lit_scratch + (size_t) blockIdx.x * (ZSTD_BLOCK_MAX + 64);
+	uint8_t *lit = lit_scratch + (size_t) blockIdx.x * CGD_ZSTD_SCRATCH;
+	if (lane == 0) T.huf = (HufEntry *) (lit + ZSTD_BLOCK_MAX + 64);
+	__syncwarp();
 	for (uint32_t idx = blockIdx.x; idx < nitems; idx += gridDim.x)
 	{
 		const DecodeItem it = items[idx];
@@ -347,7 +351,8 @@ cg_zstd_kernel(uint8_t *arena, const DecodeItem *items, uint32_t nitems, uint8_t
 extern "C" int64_t cg_test_zstd_decode_host(const uint8_t *src, uint32_t len, uint8_t *dst, uint32_t cap)
 {
 	ZstdTables *T = new ZstdTables();
-	uint8_t *lit = new uint8_t[ZSTD_BLOCK_MAX + 64];
+	uint8_t *lit = new uint8_t[CGD_ZSTD_SCRATCH];
+	T->huf = (HufEntry *) (lit + ZSTD_BLOCK_MAX + 64);
 	int64_t n = zs_decode_frame(*T, src, len, dst, cap, lit);
 	delete[] lit;
 	delete T;
@@ -380,7 +385,7 @@ int cg_launch_decompress(CgContext *ctx, uint8_t *arena, const DecodeItem *items
 			if (occ < 1) occ = 1;
 		}
 		const unsigned max_blocks = (unsigned) (ctx->sm_count * occ);
-		const size_t need = (size_t) max_blocks * (ZSTD_BLOCK_MAX + 64);
+		const size_t need = (size_t) max_blocks * CGD_ZSTD_SCRATCH;
 		if (ctx->zstd_scratch_bytes < need)
 		{
 			/* grown once; every launch uses block-indexed slices, launches on different streams would

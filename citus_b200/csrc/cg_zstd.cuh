@@ -12,8 +12,8 @@
  * writer never produces them, columnar_compression.c:103-123 calls plain ZSTD_compress): dictionaries
  * and skippable frames; a content checksum, if present, is skipped, not verified.
  *
- * Work memory: the FSE / Huffman tables (ZstdTables, ~11 KB, shared memory on the GPU) and one
- * literals buffer of up to 128 KB per stream being decoded (global memory).
+ * Work memory: the FSE tables (ZstdTables, ~7 KB, shared memory on the GPU), the Huffman table
+ * (4 KB) and one literals buffer of up to 128 KB per stream being decoded (global memory).
  */
 #ifndef CG_ZSTD_CUH
 #define CG_ZSTD_CUH
@@ -44,7 +44,8 @@ struct ZstdTables
 {
 	FseTable ll, ml;
 	FseTableOf of;
-	HufEntry huf[1 << ZSTD_HUF_LOG_MAX];
+	HufEntry *huf;              /* [1 << ZSTD_HUF_LOG_MAX], caller-provided (global memory on the GPU: keeps the
+								 * shared-memory footprint of a decoder at ~7 KB, 31 decoders per SM instead of 20) */
 	int huf_log;                /* 0 = no Huffman table yet */
 	int have_ll, have_of, have_ml;
 	uint32_t rep[3];
@@ -71,41 +72,76 @@ CG_HD uint32_t zs_fwd_read(ZsFwd &r, int n)
 
 /* ---- backward bit reader: the stream is a little-endian bit array whose highest set bit (in the
  * last byte) is the end mark; read(n) returns the n bits just below the cursor, top bit first ---- */
-struct ZsBack { const uint8_t *p; int64_t pos; };    /* pos = number of unread bits; may go negative (zeros) */
+struct ZsBack
+{
+	const uint8_t *p;
+	uint32_t len;
+	int32_t pos;        /* number of unread bits; may go negative (zeros).  Streams are < 2^20 bytes. */
+	uint32_t w0, w1;    /* bits [win_lo, win_lo + 64) of the stream, so that most reads touch no memory */
+	int32_t win_lo;     /* multiple of 8 */
+};
+/* 32 bits starting `sh` (< 32) bits into the 64-bit pair hi:lo */
+CG_HD uint32_t zs_extract(uint32_t lo, uint32_t hi, uint32_t sh)
+{
+#ifdef __CUDA_ARCH__
+	return __funnelshift_r(lo, hi, sh);
+#else
+	return (uint32_t) ((((uint64_t) hi << 32) | lo) >> sh);
+#endif
+}
+CG_HD void zs_back_refill(ZsBack &r, int32_t top)      /* make [top - 56, top) available (as far as the stream reaches) */
+{
+	int32_t lo = ((top + 7) & ~7) - 64;                /* the window ends at the first byte boundary at or above `top` */
+	if (lo < 0) lo = 0;
+	const uint32_t byte = (uint32_t) lo >> 3;
+	r.win_lo = lo;
+#ifdef __CUDA_ARCH__
+	if (byte + 8 <= r.len)
+	{
+		/* 8 bytes at any alignment from three aligned words (arena slots are padded, the over-read stays inside) */
+		const uintptr_t a = (uintptr_t) (r.p + byte);
+		const uint32_t *aw = (const uint32_t *) (a & ~(uintptr_t) 3);
+		const uint32_t sh = (uint32_t) (a & 3u) * 8u;
+		const uint32_t x0 = aw[0], x1 = aw[1], x2 = aw[2];
+		r.w0 = __funnelshift_r(x0, x1, sh);
+		r.w1 = __funnelshift_r(x1, x2, sh);
+		return;
+	}
+#endif
+	uint32_t w0 = 0, w1 = 0;
+	for (uint32_t i = 0; i < 4 && byte + i < r.len; i++) w0 |= (uint32_t) r.p[byte + i] << (8 * i);
+	for (uint32_t i = 0; i < 4 && byte + 4 + i < r.len; i++) w1 |= (uint32_t) r.p[byte + 4 + i] << (8 * i);
+	r.w0 = w0; r.w1 = w1;
+}
 CG_HD bool zs_back_init(ZsBack &r, const uint8_t *p, uint32_t len)
 {
-	if (len == 0 || p[len - 1] == 0) return false;
+	if (len == 0 || len > (1u << 24) || p[len - 1] == 0) return false;
 	r.p = p;
-	r.pos = (int64_t) (len - 1) * 8 + zs_highbit(p[len - 1]);
+	r.len = len;
+	r.pos = (int32_t) (len - 1) * 8 + zs_highbit(p[len - 1]);
+	zs_back_refill(r, r.pos);
 	return true;
 }
-CG_HD uint32_t zs_back_peek_at(const ZsBack &r, int64_t pos, int n)   /* bits [pos - n, pos), zero below bit 0 */
+/* bits [pos - n, pos), top bit first, zero below bit 0; n <= 31 */
+CG_HD uint32_t zs_back_peek_at(ZsBack &r, int32_t pos, int n)
 {
-	uint32_t v = 0;
-	for (int i = 0; i < n; i++)
+	const int32_t lo = pos - n;
+	if (lo < 0)
 	{
-		int64_t b = pos - 1 - i;
-		uint32_t x = b >= 0 ? (uint32_t) (r.p[b >> 3] >> (b & 7)) & 1u : 0u;
-		v = (v << 1) | x;
+		/* the read runs off the start of the stream: the missing low bits are zeros */
+		if (pos <= 0 || n == 0) return 0;
+		if (r.win_lo != 0) zs_back_refill(r, pos);
+		const uint32_t have = r.w0 & ((1u << pos) - 1u);          /* pos < n <= 31 */
+		return (have << (uint32_t) (-lo)) & ((1u << n) - 1u);
 	}
-	return v;
+	if (lo < r.win_lo || pos > r.win_lo + 64) zs_back_refill(r, pos);
+	const uint32_t off = (uint32_t) (lo - r.win_lo);
+	const uint32_t v = off < 32u ? zs_extract(r.w0, r.w1, off) : (r.w1 >> (off - 32u));
+	return v & ((1u << n) - 1u);
 }
 CG_HD uint32_t zs_back_read(ZsBack &r, int n)
 {
-	/* fast path: the n bits lie inside one aligned-free 64-bit window */
-	uint32_t v;
-	if (n == 0) return 0;
-	if (r.pos - n >= 0)
-	{
-		int64_t lo = r.pos - n;
-		uint64_t w = 0;
-		int64_t byte = lo >> 3;
-		int need = (int) ((lo & 7) + n + 7) >> 3;
-		for (int i = 0; i < need; i++) w |= (uint64_t) r.p[byte + i] << (8 * i);
-		v = (uint32_t) ((w >> (lo & 7)) & ((1ull << n) - 1ull));
-	}
-	else
-		v = zs_back_peek_at(r, r.pos, n);
+	uint32_t v = zs_back_peek_at(r, r.pos, n);
 	r.pos -= n;
 	return v;
 }
@@ -276,23 +312,31 @@ CG_HDN inline int zs_huf_stream(const ZstdTables &T, const uint8_t *src, uint32_
 	ZsBack r;
 	if (!zs_back_init(r, src, len)) return ZSTD_ERR;
 	const int log = T.huf_log;
-	for (uint32_t i = 0; i < count; i++)
+	uint32_t i = 0;
+	/* bytes up to a 4-byte boundary of `out`, then four symbols per store */
+	while (i < count && (((uintptr_t) (out + i)) & 3u) != 0)
 	{
-		uint32_t idx;
-		if (r.pos >= log)
+		const HufEntry h = T.huf[zs_back_peek_at(r, r.pos, log)];
+		out[i++] = h.symbol;
+		r.pos -= h.nbits;
+	}
+	for (; i + 4 <= count; i += 4)
+	{
+		uint32_t w = 0;
+		for (int k = 0; k < 4; k++)
 		{
-			int64_t lo = r.pos - log;
-			int64_t byte = lo >> 3;
-			uint32_t w = (uint32_t) r.p[byte] | ((uint32_t) (byte + 1 < (int64_t) len ? r.p[byte + 1] : 0) << 8) |
-						 ((uint32_t) (byte + 2 < (int64_t) len ? r.p[byte + 2] : 0) << 16);
-			idx = (w >> (lo & 7)) & ((1u << log) - 1u);
+			const HufEntry h = T.huf[zs_back_peek_at(r, r.pos, log)];
+			w |= (uint32_t) h.symbol << (8 * k);
+			r.pos -= h.nbits;
 		}
-		else
-			idx = zs_back_peek_at(r, r.pos, log);
-		const HufEntry h = T.huf[idx];
+		*(uint32_t *) (out + i) = w;
+		if (r.pos < 0) return ZSTD_ERR;
+	}
+	for (; i < count; i++)
+	{
+		const HufEntry h = T.huf[zs_back_peek_at(r, r.pos, log)];
 		out[i] = h.symbol;
 		r.pos -= h.nbits;
-		if (r.pos < 0) return ZSTD_ERR;
 	}
 	return r.pos == 0 ? 0 : ZSTD_ERR;
 }
@@ -374,19 +418,26 @@ CG_HDN inline int zs_literals(ZstdTables &T, const uint8_t *src, uint32_t len, u
 }
 
 /* ---- sequences ---- */
+/* code -> baseline (low 24 bits) and number of extra bits (high 8 bits) */
 CG_HD void zs_ll_code(uint32_t code, uint32_t *base, int *bits)
 {
-	if (code < 16) { *base = code; *bits = 0; return; }
-	static const uint32_t b[20] = {16, 18, 20, 22, 24, 28, 32, 40, 48, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536};
-	static const uint8_t n[20] = {1, 1, 1, 1, 2, 2, 3, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
-	*base = b[code - 16]; *bits = n[code - 16];
+	static const uint32_t t[36] = {
+		0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15,
+		16 | 1u << 24, 18 | 1u << 24, 20 | 1u << 24, 22 | 1u << 24, 24 | 2u << 24, 28 | 2u << 24, 32 | 3u << 24, 40 | 3u << 24,
+		48 | 4u << 24, 64 | 6u << 24, 128 | 7u << 24, 256 | 8u << 24, 512 | 9u << 24, 1024 | 10u << 24, 2048 | 11u << 24,
+		4096 | 12u << 24, 8192 | 13u << 24, 16384 | 14u << 24, 32768 | 15u << 24, 65536 | 16u << 24};
+	const uint32_t v = t[code];
+	*base = v & 0xFFFFFFu; *bits = (int) (v >> 24);
 }
 CG_HD void zs_ml_code(uint32_t code, uint32_t *base, int *bits)
 {
-	if (code < 32) { *base = code + 3; *bits = 0; return; }
-	static const uint32_t b[21] = {35, 37, 39, 41, 43, 47, 51, 59, 67, 83, 99, 131, 259, 515, 1027, 2051, 4099, 8195, 16387, 32771, 65539};
-	static const uint8_t n[21] = {1, 1, 1, 1, 2, 2, 3, 3, 4, 4, 5, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
-	*base = b[code - 32]; *bits = n[code - 32];
+	static const uint32_t t[53] = {
+		3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34,
+		35 | 1u << 24, 37 | 1u << 24, 39 | 1u << 24, 41 | 1u << 24, 43 | 2u << 24, 47 | 2u << 24, 51 | 3u << 24, 59 | 3u << 24,
+		67 | 4u << 24, 83 | 4u << 24, 99 | 5u << 24, 131 | 7u << 24, 259 | 8u << 24, 515 | 9u << 24, 1027 | 10u << 24,
+		2051 | 11u << 24, 4099 | 12u << 24, 8195 | 13u << 24, 16387 | 14u << 24, 32771 | 15u << 24, 65539 | 16u << 24};
+	const uint32_t v = t[code];
+	*base = v & 0xFFFFFFu; *bits = (int) (v >> 24);
 }
 
 /* one of the three symbol tables: mode 0 predefined, 1 RLE, 2 FSE description, 3 repeat; returns bytes consumed */
@@ -423,6 +474,16 @@ CG_HDN inline int zs_seq_table(ZstdTables &T, int which, int mode, const uint8_t
 	}
 	if (zs_build_fse(e, *log, T.norm, nsym, T.next) < 0) return ZSTD_ERR;
 	return used;
+}
+
+CG_HD uint32_t zs_entry(const FseEntry *e, uint32_t state)
+{
+	const uint8_t *q = (const uint8_t *) (e + state);
+#ifdef __CUDA_ARCH__
+	return *(const uint32_t *) q;
+#else
+	return (uint32_t) q[0] | ((uint32_t) q[1] << 8) | ((uint32_t) q[2] << 16) | ((uint32_t) q[3] << 24);
+#endif
 }
 
 /* overlapping forward copy (LZ77 semantics) */
@@ -468,8 +529,10 @@ CG_HDN inline int64_t zs_compressed_block(ZstdTables &T, const uint8_t *src, uin
 		if (r.pos < 0) return ZSTD_ERR;
 		for (uint32_t s = 0; s < nseq; s++)
 		{
-			const uint32_t of_code = T.of.e[so].symbol, ml_sym = T.ml.e[sm].symbol, ll_sym = T.ll.e[sl].symbol;
-			if (of_code > 31) return ZSTD_ERR;
+			/* one 32-bit load per table entry: symbol | nbits << 8 | base << 16 */
+			const uint32_t eo = zs_entry(T.of.e, so), em = zs_entry(T.ml.e, sm), el = zs_entry(T.ll.e, sl);
+			const uint32_t of_code = eo & 0xffu, ml_sym = em & 0xffu, ll_sym = el & 0xffu;
+			if (of_code > 31 || ml_sym > 52 || ll_sym > 35) return ZSTD_ERR;
 			uint32_t ofv = (1u << of_code) + zs_back_read(r, (int) of_code);
 			uint32_t mbase, lbase; int mbits, lbits;
 			zs_ml_code(ml_sym, &mbase, &mbits);
@@ -478,9 +541,9 @@ CG_HDN inline int64_t zs_compressed_block(ZstdTables &T, const uint8_t *src, uin
 			const uint32_t llen = lbase + zs_back_read(r, lbits);
 			if (s + 1 < nseq)
 			{
-				sl = T.ll.e[sl].base + zs_back_read(r, T.ll.e[sl].nbits);
-				sm = T.ml.e[sm].base + zs_back_read(r, T.ml.e[sm].nbits);
-				so = T.of.e[so].base + zs_back_read(r, T.of.e[so].nbits);
+				sl = (el >> 16) + zs_back_read(r, (int) ((el >> 8) & 0xffu));
+				sm = (em >> 16) + zs_back_read(r, (int) ((em >> 8) & 0xffu));
+				so = (eo >> 16) + zs_back_read(r, (int) ((eo >> 8) & 0xffu));
 			}
 			if (r.pos < 0) return ZSTD_ERR;
 			/* repeat-offset history */

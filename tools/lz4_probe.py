@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Decode-kernel probe: stages lz4-compressed C2 shards from pinned pages (DMA path) with CG_TRACE-style
-timing of the decompression kernel alone, via cg_scan_relation on one shard at a time."""
+"""Decode-path probe: end-to-end scan of compressed C2 shards from pinned pages (DMA path), a few full-size
+shards, per codec.  CG_TRACE=1 adds the per-shard kernel times (realign, decode + scan)."""
 import os
 import sys
 import time
@@ -12,13 +12,14 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 from citus_b200 import columnar as cg  # noqa: E402
 
-nshards = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+codec = sys.argv[1] if len(sys.argv) > 1 else "lz4"
+nshards = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 rows = 31_250_000
 cg.init(0)
 cg.numa_bind()
 torch.cuda.set_stream(torch.cuda.Stream())
 cg.use_torch_stream()
-cg.set_writer_compression("lz4")
+cg.set_writer_compression(codec)
 rels = bench.generate_shards(cg, list(range(nshards)), rows, 32)
 cg.set_writer_compression("none")
 aggs = [cg.sum_(2), cg.count_star()]
@@ -38,4 +39,4 @@ for rep in range(3):
         h2d += st.h2d_bytes
     torch.cuda.synchronize()
     dt = time.time() - t0
-    print(f"rep {rep}: {nshards} shards in {dt * 1e3:.1f} ms = {nshards * rows / dt / 1e9:.2f} G rows/s, h2d {h2d / 1e9:.2f} GB", flush=True)
+    print(f"{codec} rep {rep}: {nshards} shards in {dt * 1e3:.1f} ms = {nshards * rows / dt / 1e9:.2f} G rows/s, h2d {h2d / 1e9:.2f} GB", flush=True)
