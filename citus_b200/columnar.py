@@ -22,6 +22,7 @@ from .capi import (CG_AGG_COUNT, CG_AGG_COUNT_STAR, CG_AGG_MAX, CG_AGG_MIN, CG_A
                    CgScanStats, CgSkipNode, CgStripe, check, lib)
 
 _initialised = False
+_on_torch_stream = None      # handle of the torch stream the library was put on (use_torch_stream)
 
 
 def init(device: int = 0):
@@ -47,8 +48,10 @@ def use_torch_stream():
     the library's kernels are ordered in one queue (torch's default stream is CUDA's legacy default
     stream, whose handle is 0: it is passed as cudaStreamLegacy = 1)"""
     import torch
+    global _on_torch_stream
     h = torch.cuda.current_stream().cuda_stream
     check(lib().cg_set_stream(C.c_void_p(h if h else 1)))
+    _on_torch_stream = h
 
 
 class Relation:
@@ -372,6 +375,16 @@ class GpuColumnarAgg:
 
     def merge_rows(self, d_keys_ptr, d_nulls_ptr, d_words_ptr, nrows):
         check(lib().cg_partial_merge_rows(self.h, d_keys_ptr, d_nulls_ptr, d_words_ptr, nrows))
+
+    def dense_words_enqueue(self):
+        """like dense_words, but only enqueues the table maintenance (no host sync, no error check)"""
+        p, total, stride = C.c_void_p(), C.c_int64(), C.c_int32()
+        check(lib().cg_partial_dense_words_enqueue(self.h, C.byref(p), C.byref(total), C.byref(stride)))
+        return p.value, total.value, stride.value
+
+    def check(self):
+        """wait for the partial's pending work and raise what its kernels flagged"""
+        check(lib().cg_partial_check(self.h))
 
     def dense_words(self):
         p, total, stride = C.c_void_p(), C.c_int64(), C.c_int32()

@@ -1530,6 +1530,32 @@ extern "C" int cg_partial_merge_rows(CgPartial *p, const int64_t *d_keys, const 
 	return pending_errors(ctx, p);
 }
 
+/* the same without waiting: the drain of the packed words is enqueued on the library's stream, work
+ * the caller enqueues behind it on that stream (a collective) sees the drained table; the scan's error
+ * flags are NOT looked at here -- cg_partial_check (or any call that reads the partial) does that */
+extern "C" int cg_partial_dense_words_enqueue(CgPartial *p, uint64_t **d_words, int64_t *total_words, int32_t *stride)
+{
+	if (!p || !d_words) return cg_set_error(CG_EINVAL, "NULL partial");
+	if (p->mode == CG_MODE_HASH) return cg_set_error(CG_EINVAL, "not a direct-indexed table");
+	CgContext *ctx = cg_ctx();
+	if (!ctx) return CG_EINVAL;
+	int rc = cg_launch_drain(p, ctx->compute);
+	if (rc) return rc;
+	*d_words = p->d_table;
+	if (total_words) *total_words = (int64_t) (p->entries * (uint64_t) p->stride);
+	if (stride) *stride = p->stride;
+	return CG_OK;
+}
+
+/* waits for the partial's pending work and reports what its kernels flagged (table full, key range,
+ * sum bound, corrupt compressed stream, packed overflow -> CG_ERETRY_UNPACKED) */
+extern "C" int cg_partial_check(CgPartial *p)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx || !p) return CG_EINVAL;
+	return pending_errors(ctx, p);
+}
+
 extern "C" int cg_partial_dense_words(CgPartial *p, uint64_t **d_words, int64_t *total_words, int32_t *stride)
 {
 	if (!p) return cg_set_error(CG_EINVAL, "NULL partial");

@@ -72,6 +72,11 @@ def allgather_rows(keys: torch.Tensor, key_nulls: torch.Tensor, words: torch.Ten
     return ks, ns, ws, counts
 
 
+def library_uses_torch_stream() -> bool:
+    from . import columnar
+    return getattr(columnar, "_on_torch_stream", None) == torch.cuda.current_stream().cuda_stream
+
+
 def combine_partials(agg, dst: int = 0, group=None):
     """coord_combine over the ranks: after the call rank `dst`'s partial holds the combined
     aggregate.  `agg` is a columnar.GpuColumnarAgg."""
@@ -83,9 +88,16 @@ def combine_partials(agg, dst: int = 0, group=None):
     rank = dist.get_rank(group)
     nw, ops, dense, cap = agg.layout()
     if (dense or agg.desc.ngroup_cols == 0) and all(o == CG_WORD_ADD for o in ops):
+        if library_uses_torch_stream():
+            # one queue: table maintenance, the collective and whatever reads the result are stream ordered, so the
+            # host only waits once, after the collective is on its way (every rank: a worker error fails the query)
+            ptr, total, stride = agg.dense_words_enqueue()
+            reduce_dense_words(device_view(ptr, total), dst, group)
+            agg.check()
+            return
         ptr, total, stride = agg.dense_words()          # drains + verifies packed words, syncs the library's stream
         reduce_dense_words(device_view(ptr, total), dst, group)
-        # the collective runs on torch's stream; the library may be on its own stream
+        # the collective runs on torch's stream; the library is on its own stream
         torch.cuda.current_stream().synchronize()
         return
     n = agg.ngroups()

@@ -293,6 +293,13 @@ int cg_partial_merge_rows(CgPartial *p, const int64_t *d_keys, const uint8_t *d_
  * with the same arguments have identical layouts, so when every word op is CG_WORD_ADD a
  * collective (ncclReduce / ncclAllReduce, sum, int64) combines them in place. */
 int cg_partial_dense_words(CgPartial *p, uint64_t **d_words, int64_t *total_words, int32_t *stride);
+/* The same without a host synchronisation: pending table maintenance is only enqueued on the library's
+ * stream (cg_set_stream), so a collective enqueued behind it on that stream reduces the finished table
+ * and the host runs ahead.  The scan's error flags are not examined: call cg_partial_check (every rank,
+ * after enqueuing the collective) before trusting the combined result. */
+int cg_partial_dense_words_enqueue(CgPartial *p, uint64_t **d_words, int64_t *total_words, int32_t *stride);
+/* Waits for the partial's pending work and reports what its kernels flagged. */
+int cg_partial_check(CgPartial *p);
 
 /* ---------------------------------------------------------------------------------- *
  *  Hash repartition (map side): worker_partition_query_result's per-row routing
