@@ -240,7 +240,7 @@ extern "C" void cg_shutdown(void)
 		if (g_ctx.dma_done[i]) cudaEventDestroy(g_ctx.dma_done[i]);
 		g_ctx.dma_done[i] = nullptr;
 	}
-	for (int i = 0; i < 2; i++) { if (g_ctx.decode_stream[i]) cudaStreamDestroy(g_ctx.decode_stream[i]); g_ctx.decode_stream[i] = nullptr; }
+	for (int i = 0; i < CgContext::kDmaDepth; i++) { if (g_ctx.decode_stream[i]) cudaStreamDestroy(g_ctx.decode_stream[i]); g_ctx.decode_stream[i] = nullptr; }
 	for (int i = 0; i < CgContext::kDmaDepth; i++) { if (g_ctx.decoded[i]) cudaEventDestroy(g_ctx.decoded[i]); g_ctx.decoded[i] = nullptr; }
 	if (g_ctx.dma_copied) cudaEventDestroy(g_ctx.dma_copied);
 	g_ctx.dma_copied = nullptr;
@@ -1304,7 +1304,7 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 			{
 				/* de-framing and decompression run on one of two side streams, the scan follows on the
 				 * compute stream: the decode of this shard overlaps the decode (and scan) of the previous one */
-				const int ds = (int) (ctx->decode_rr++ & 1u);
+				const int ds = (int) (ctx->decode_rr++ % (unsigned) CgContext::kDmaDepth);
 				if (!ctx->decode_stream[ds]) CG_CUDA(cudaStreamCreateWithFlags(&ctx->decode_stream[ds], cudaStreamNonBlocking));
 				if (!ctx->decoded[mslot]) CG_CUDA(cudaEventCreateWithFlags(&ctx->decoded[mslot], cudaEventDisableTiming));
 				cudaStream_t side = ctx->decode_stream[ds];

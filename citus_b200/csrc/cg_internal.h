@@ -53,9 +53,9 @@ struct CgContext
 	/* device buffers of the shards in flight (grown on demand, reused: no allocator in the scan loop) */
 	struct DevBuf { uint8_t *p = nullptr; size_t cap = 0; };
 	DevBuf slot_arena[kDmaDepth], slot_raw[kDmaDepth], slot_meta[kDmaDepth];
-	/* decode streams: the decompression of consecutive shards alternates between two streams, so that
-	 * two decode kernels (each a latency-bound chain per stream) can be resident together */
-	cudaStream_t decode_stream[2] = {nullptr, nullptr};
+	/* decode streams: the decompression of consecutive shards rotates over kDmaDepth streams, so that the
+	 * decode kernels of all shards in flight (each a latency-bound chain per value stream) can be resident together */
+	cudaStream_t decode_stream[kDmaDepth] = {nullptr, nullptr, nullptr};
 	unsigned decode_rr = 0;
 	cudaEvent_t decoded[kDmaDepth] = {nullptr, nullptr, nullptr};
 	uint8_t *zstd_scratch = nullptr;             /* literal buffers of the resident zstd decoders */
