@@ -36,6 +36,7 @@
  * host reports CG_ECORRUPT ("cannot decompress the buffer") at its next synchronisation.
  */
 #include <algorithm>
+#include <stdlib.h>
 
 #include "cg_internal.h"
 #include "cg_zstd.cuh"
@@ -309,19 +310,170 @@ cg_decompress_kernel(uint8_t *arena, const DecodeItem *items, uint32_t nitems, u
 
 /*
  * Zstandard (cg_zstd.cuh): entropy decoding (FSE state machines, Huffman bit streams) is a serial
- * dependency chain per stream, so a stream is decoded by ONE lane running ordinary sequential code
+ * dependency chain per stream, so the serial parts run on ONE lane as ordinary sequential code
  * -- the same source the CPU-side format tests run on the host -- and the parallelism comes from
- * the number of streams (a C2 shard has ~10^4).  One warp per CTA; its FSE tables (ZstdTables, ~7 KB)
+ * the number of streams (a C2 shard has ~10^4) plus the warp-cooperative parts below.  One warp per CTA; its FSE tables (ZstdTables, ~7 KB)
  * live in shared memory, its Huffman table and literals buffer (132 KB) in a context-owned scratch area; persistent
  * CTAs stride over the decode list.  The other lanes only help with the slot's zero padding.
  */
 #define CGD_ZSTD_SCRATCH (ZSTD_BLOCK_MAX + 64 + sizeof(HufEntry) * (1u << ZSTD_HUF_LOG_MAX))   /* literals + Huffman table */
 
+/*
+ * The warp-cooperative form of one frame.  What is serial stays on lane 0 and is the very code the
+ * host tests exercise (headers, Huffman tree, FSE tables, zs_sequences_next: the entropy-coded
+ * sequence stream is one dependency chain); what is not serial is spread over the warp:
+ *   - raw / RLE blocks and literal sections: lane-parallel copies and fills
+ *   - the four Huffman streams of a literals section: one lane each
+ *   - sequence execution in batches of 32: lane 0 decodes 32 (literal length, match length, offset)
+ *     triples into shared memory, a warp prefix sum gives every sequence its literal and output
+ *     positions, the literal runs are copied one per lane, the matches in order with all lanes on
+ *     each (byte i of a match is out[start - off + i mod off], as in the lz4 decoder).
+ */
+struct ZsShared
+{
+	ZsLitPlan L;
+	ZsSeq S;
+	uint32_t ll[32], ml[32], off[32];
+	int status;
+	uint32_t hdr_pos, has_fcs, fcs_lo, checksum;
+};
+
+static __device__ int64_t zstd_block_coop(ZstdTables &T, ZsShared &C, const uint8_t *src, uint32_t len, uint8_t *dst, uint32_t op,
+										   uint32_t cap, uint8_t *lit, uint32_t lane)
+{
+	if (lane == 0) C.status = zs_literals_prepare(T, src, len, &C.L);
+	__syncwarp();
+	if (C.status < 0) return ZSTD_ERR;
+	const uint32_t nlit = C.L.regen;
+	if (C.L.kind == 0) { for (uint32_t i = lane; i < nlit; i += 32) lit[i] = C.L.raw[i]; }
+	else if (C.L.kind == 1) { const uint8_t b = C.L.raw[0]; for (uint32_t i = lane; i < nlit; i += 32) lit[i] = b; }
+	else if (lane < (uint32_t) C.L.nstreams)
+	{
+		if (zs_huf_stream(T, C.L.sptr[lane], C.L.slen[lane], lit + C.L.sout[lane], C.L.scount[lane]) < 0) C.status = ZSTD_ERR;
+	}
+	__syncwarp();
+	if (C.status < 0) return ZSTD_ERR;
+	if (lane == 0) C.status = zs_sequences_begin(T, src + C.L.consumed, len - C.L.consumed, &C.S);
+	__syncwarp();
+	if (C.status < 0) return ZSTD_ERR;
+	const uint32_t nseq = C.S.nseq;
+	uint32_t litpos = 0;
+	for (uint32_t base = 0; base < nseq; base += 32)
+	{
+		const uint32_t nb = min(32u, nseq - base);
+		if (lane == 0)
+		{
+			int st = 0;
+			for (uint32_t j = 0; j < nb && st == 0; j++) st = zs_sequences_next(T, &C.S, &C.ll[j], &C.ml[j], &C.off[j]);
+			C.status = st;
+		}
+		__syncwarp();
+		if (C.status < 0) return ZSTD_ERR;
+		const uint32_t l = lane < nb ? C.ll[lane] : 0u, m = lane < nb ? C.ml[lane] : 0u, o = lane < nb ? C.off[lane] : 1u;
+		uint32_t pl = l, pt = l + m;                                 /* inclusive prefix sums over the batch */
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+		{
+			const uint32_t a = __shfl_up_sync(0xffffffffu, pl, d), b = __shfl_up_sync(0xffffffffu, pt, d);
+			if (lane >= (uint32_t) d) { pl += a; pt += b; }
+		}
+		const uint32_t tot_l = __shfl_sync(0xffffffffu, pl, 31), tot_t = __shfl_sync(0xffffffffu, pt, 31);
+		if (tot_l > nlit - litpos || tot_t > cap - op) return ZSTD_ERR;
+		const uint32_t my_lit = litpos + pl - l;                     /* where my literals come from */
+		const uint32_t my_out = op + pt - (l + m);                   /* where they go; my match starts l bytes later */
+		if (__any_sync(0xffffffffu, lane < nb && o > my_out + l)) return ZSTD_ERR;     /* offset beyond the output so far */
+		for (uint32_t i = 0; i < l; i++) dst[my_out + i] = lit[my_lit + i];
+		__syncwarp();
+		for (uint32_t j = 0; j < nb; j++)
+		{
+			const uint32_t mj = __shfl_sync(0xffffffffu, m, j), oj = __shfl_sync(0xffffffffu, o, j);
+			const uint32_t start = __shfl_sync(0xffffffffu, my_out + l, j);
+			uint32_t k = lane, step = 32u;
+			if (oj <= 32u)
+			{
+				while (k >= oj) k -= oj;
+				while (step >= oj) step -= oj;
+			}
+			const uint8_t *from = dst + start - oj;
+			for (uint32_t i = lane; i < mj; i += 32)
+			{
+				dst[start + i] = from[k];
+				k += step; if (k >= oj) k -= oj;
+			}
+			__syncwarp();
+		}
+		litpos += tot_l; op += tot_t;
+	}
+	if (lane == 0) C.status = zs_sequences_end(&C.S);
+	__syncwarp();
+	if (C.status < 0) return ZSTD_ERR;
+	const uint32_t rest = nlit - litpos;
+	if (rest > cap - op) return ZSTD_ERR;
+	for (uint32_t i = lane; i < rest; i += 32) dst[op + i] = lit[litpos + i];
+	__syncwarp();
+	return (int64_t) op + rest;
+}
+
+static __device__ int64_t zstd_frame_coop(ZstdTables &T, ZsShared &C, const uint8_t *src, uint32_t len, uint8_t *dst, uint32_t cap,
+										   uint8_t *lit, uint32_t lane)
+{
+	if (lane == 0)
+	{
+		uint64_t fcs = 0;
+		int checksum = 0;
+		int hp = zs_frame_header(src, len, cap, &fcs, &checksum);
+		C.status = hp < 0 ? ZSTD_ERR : 0;
+		C.hdr_pos = (uint32_t) hp; C.has_fcs = fcs != ~0ull; C.fcs_lo = (uint32_t) fcs; C.checksum = (uint32_t) checksum;
+		T.huf_log = 0; T.have_ll = T.have_of = T.have_ml = 0;
+		T.rep[0] = 1; T.rep[1] = 4; T.rep[2] = 8;
+	}
+	__syncwarp();
+	if (C.status < 0) return ZSTD_ERR;
+	uint32_t pos = C.hdr_pos, op = 0;
+	for (;;)
+	{
+		if (pos + 3 > len) return ZSTD_ERR;
+		const uint32_t bh = src[pos] | ((uint32_t) src[pos + 1] << 8) | ((uint32_t) src[pos + 2] << 16);
+		pos += 3;
+		const uint32_t last = bh & 1u, type = (bh >> 1) & 3u, bsize = bh >> 3;
+		if (type == 0)
+		{
+			if (bsize > ZSTD_BLOCK_MAX || pos + bsize > len || bsize > cap - op) return ZSTD_ERR;
+			for (uint32_t i = lane; i < bsize; i += 32) dst[op + i] = src[pos + i];
+			op += bsize; pos += bsize;
+			__syncwarp();
+		}
+		else if (type == 1)
+		{
+			if (bsize > ZSTD_BLOCK_MAX || pos + 1 > len || bsize > cap - op) return ZSTD_ERR;
+			const uint8_t b = src[pos];
+			for (uint32_t i = lane; i < bsize; i += 32) dst[op + i] = b;
+			op += bsize; pos += 1;
+			__syncwarp();
+		}
+		else if (type == 2)
+		{
+			if (bsize > ZSTD_BLOCK_MAX || pos + bsize > len) return ZSTD_ERR;
+			const int64_t nop = zstd_block_coop(T, C, src + pos, bsize, dst, op, cap, lit, lane);
+			if (nop < 0 || nop - (int64_t) op > (int64_t) ZSTD_BLOCK_MAX) return ZSTD_ERR;
+			op = (uint32_t) nop; pos += bsize;
+		}
+		else
+			return ZSTD_ERR;
+		if (last) break;
+	}
+	if (C.checksum) { if (pos + 4 > len) return ZSTD_ERR; pos += 4; }
+	if (pos != len) return ZSTD_ERR;
+	if (C.has_fcs && C.fcs_lo != op) return ZSTD_ERR;
+	return (int64_t) op;
+}
+
 __global__ void __launch_bounds__(32)
 cg_zstd_kernel(uint8_t *arena, const DecodeItem *items, uint32_t nitems, uint8_t *lit_scratch, unsigned long long *err,
-			   unsigned long long flag)
+			   unsigned long long flag, int coop)
 {
 	__shared__ ZstdTables T;
+	__shared__ ZsShared C;
 	__shared__ int s_ok;
 	const uint32_t lane = threadIdx.x;
 	uint8_t *lit = lit_scratch + (size_t) blockIdx.x * CGD_ZSTD_SCRATCH;
@@ -332,15 +484,20 @@ cg_zstd_kernel(uint8_t *arena, const DecodeItem *items, uint32_t nitems, uint8_t
 		const DecodeItem it = items[idx];
 		if (it.kind != CG_COMPRESSION_ZSTD) continue;
 		uint8_t *dst = arena + it.dst;
-		if (lane == 0)
+		bool ok;
+		if (coop)
 		{
-			int64_t n = zs_decode_frame(T, arena + it.src, it.comp_len, dst, it.raw_len, lit);
 			/* "unexpected decompressed size" (columnar_compression.c:226-232) */
-			s_ok = n == (int64_t) it.raw_len;
-			if (!s_ok) atomicOr(err, flag);
+			ok = zstd_frame_coop(T, C, arena + it.src, it.comp_len, dst, it.raw_len, lit, lane) == (int64_t) it.raw_len;
+			__syncwarp();
 		}
-		__syncwarp();
-		const bool ok = s_ok != 0;
+		else
+		{
+			if (lane == 0) s_ok = zs_decode_frame(T, arena + it.src, it.comp_len, dst, it.raw_len, lit) == (int64_t) it.raw_len;
+			__syncwarp();
+			ok = s_ok != 0;
+		}
+		if (!ok && lane == 0) atomicOr(err, flag);
 		for (uint32_t i = (ok ? it.raw_len : 0u) + lane; i < it.padded; i += 32) dst[i] = 0;
 		__syncwarp();
 	}
@@ -400,7 +557,9 @@ int cg_launch_decompress(CgContext *ctx, uint8_t *arena, const DecodeItem *items
 			ctx->zstd_scratch_bytes = need;
 		}
 		unsigned blocks = (unsigned) std::min<uint64_t>(nitems, max_blocks);
-		cg_zstd_kernel<<<blocks, 32, 0, stream>>>(arena, items, (uint32_t) nitems, ctx->zstd_scratch, err, flag);
+		static int coop = -1;
+		if (coop < 0) { const char *e = getenv("CG_ZSTD_COOP"); coop = e ? atoi(e) : 1; }
+		cg_zstd_kernel<<<blocks, 32, 0, stream>>>(arena, items, (uint32_t) nitems, ctx->zstd_scratch, err, flag, coop);
 		CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	}
 	return CG_OK;

@@ -341,29 +341,43 @@ CG_HDN inline int zs_huf_stream(const ZstdTables &T, const uint8_t *src, uint32_
 	return r.pos == 0 ? 0 : ZSTD_ERR;
 }
 
-/* literals section: fills lit[0..*nlit); returns bytes consumed or ZSTD_ERR */
-CG_HDN inline int zs_literals(ZstdTables &T, const uint8_t *src, uint32_t len, uint8_t *lit, uint32_t *nlit)
+/* a literals section after its headers (and Huffman tree) have been read: what is left to do is copy,
+ * fill, or decode 1 / 4 independent Huffman streams -- work that can be split over lanes */
+struct ZsLitPlan
+{
+	int kind;                   /* 0 raw copy, 1 RLE fill, 2 Huffman streams */
+	uint32_t regen;             /* literals produced */
+	uint32_t consumed;          /* bytes of the block taken by the whole literals section */
+	const uint8_t *raw;         /* kind 0: the bytes; kind 1: the byte */
+	int nstreams;
+	const uint8_t *sptr[4];
+	uint32_t slen[4], scount[4], sout[4];
+};
+
+/* literals section headers (+ Huffman tree description into T); returns 0 or ZSTD_ERR */
+CG_HDN inline int zs_literals_prepare(ZstdTables &T, const uint8_t *src, uint32_t len, ZsLitPlan *L)
 {
 	if (len < 1) return ZSTD_ERR;
 	const uint32_t type = src[0] & 3u, fmt = (src[0] >> 2) & 3u;
 	uint32_t regen, comp = 0, hdr;
+	L->nstreams = 0;
 	if (type < 2)
 	{
 		if ((fmt & 1u) == 0) { regen = src[0] >> 3; hdr = 1; }
 		else if (fmt == 1) { if (len < 2) return ZSTD_ERR; regen = (src[0] >> 4) + ((uint32_t) src[1] << 4); hdr = 2; }
 		else { if (len < 3) return ZSTD_ERR; regen = (src[0] >> 4) + ((uint32_t) src[1] << 4) + ((uint32_t) src[2] << 12); hdr = 3; }
 		if (regen > ZSTD_BLOCK_MAX) return ZSTD_ERR;
+		L->regen = regen;
+		L->raw = src + hdr;
 		if (type == 0)
 		{
 			if (hdr + regen > len) return ZSTD_ERR;
-			for (uint32_t i = 0; i < regen; i++) lit[i] = src[hdr + i];
-			*nlit = regen;
-			return (int) (hdr + regen);
+			L->kind = 0; L->consumed = hdr + regen;
+			return 0;
 		}
 		if (hdr + 1 > len) return ZSTD_ERR;
-		for (uint32_t i = 0; i < regen; i++) lit[i] = src[hdr];
-		*nlit = regen;
-		return (int) (hdr + 1);
+		L->kind = 1; L->consumed = hdr + 1;
+		return 0;
 	}
 	int streams = 4;
 	if (fmt < 2)
@@ -395,26 +409,37 @@ CG_HDN inline int zs_literals(ZstdTables &T, const uint8_t *src, uint32_t len, u
 		p += used; left -= (uint32_t) used;
 	}
 	else if (T.huf_log == 0) return ZSTD_ERR;       /* treeless without a previous table */
+	L->kind = 2; L->regen = regen; L->consumed = hdr + comp; L->nstreams = streams;
 	if (streams == 1)
 	{
-		if (zs_huf_stream(T, p, left, lit, regen) < 0) return ZSTD_ERR;
+		L->sptr[0] = p; L->slen[0] = left; L->scount[0] = regen; L->sout[0] = 0;
+		return 0;
 	}
+	if (left < 6) return ZSTD_ERR;
+	const uint32_t s1 = p[0] | ((uint32_t) p[1] << 8), s2 = p[2] | ((uint32_t) p[3] << 8), s3 = p[4] | ((uint32_t) p[5] << 8);
+	if (6 + s1 + s2 + s3 > left) return ZSTD_ERR;
+	const uint32_t per = (regen + 3) / 4;
+	if (3 * per > regen) return ZSTD_ERR;
+	const uint8_t *q = p + 6;
+	L->sptr[0] = q; L->slen[0] = s1; L->scount[0] = per; L->sout[0] = 0;
+	L->sptr[1] = q + s1; L->slen[1] = s2; L->scount[1] = per; L->sout[1] = per;
+	L->sptr[2] = q + s1 + s2; L->slen[2] = s3; L->scount[2] = per; L->sout[2] = 2 * per;
+	L->sptr[3] = q + s1 + s2 + s3; L->slen[3] = left - 6 - s1 - s2 - s3; L->scount[3] = regen - 3 * per; L->sout[3] = 3 * per;
+	return 0;
+}
+
+/* literals section, sequentially: fills lit[0..*nlit); returns bytes consumed or ZSTD_ERR */
+CG_HDN inline int zs_literals(ZstdTables &T, const uint8_t *src, uint32_t len, uint8_t *lit, uint32_t *nlit)
+{
+	ZsLitPlan L;
+	if (zs_literals_prepare(T, src, len, &L) < 0) return ZSTD_ERR;
+	if (L.kind == 0) for (uint32_t i = 0; i < L.regen; i++) lit[i] = L.raw[i];
+	else if (L.kind == 1) for (uint32_t i = 0; i < L.regen; i++) lit[i] = L.raw[0];
 	else
-	{
-		if (left < 6) return ZSTD_ERR;
-		uint32_t s1 = p[0] | ((uint32_t) p[1] << 8), s2 = p[2] | ((uint32_t) p[3] << 8), s3 = p[4] | ((uint32_t) p[5] << 8);
-		if (6 + s1 + s2 + s3 > left) return ZSTD_ERR;
-		uint32_t s4 = left - 6 - s1 - s2 - s3;
-		uint32_t per = (regen + 3) / 4;
-		if (3 * per > regen) return ZSTD_ERR;
-		const uint8_t *q = p + 6;
-		if (zs_huf_stream(T, q, s1, lit, per) < 0) return ZSTD_ERR;
-		if (zs_huf_stream(T, q + s1, s2, lit + per, per) < 0) return ZSTD_ERR;
-		if (zs_huf_stream(T, q + s1 + s2, s3, lit + 2 * per, per) < 0) return ZSTD_ERR;
-		if (zs_huf_stream(T, q + s1 + s2 + s3, s4, lit + 3 * per, regen - 3 * per) < 0) return ZSTD_ERR;
-	}
-	*nlit = regen;
-	return (int) (hdr + comp);
+		for (int k = 0; k < L.nstreams; k++)
+			if (zs_huf_stream(T, L.sptr[k], L.slen[k], lit + L.sout[k], L.scount[k]) < 0) return ZSTD_ERR;
+	*nlit = L.regen;
+	return (int) L.consumed;
 }
 
 /* ---- sequences ---- */
@@ -494,104 +519,126 @@ CG_HD void zs_copy_match(uint8_t *dst, uint32_t op, uint32_t off, uint32_t n)
 	for (uint32_t i = 0; i < n; i++) d[i] = m[i];
 }
 
-/* one compressed block; dst/op: the frame's output so far; returns the new op or ZSTD_ERR */
-CG_HDN inline int64_t zs_compressed_block(ZstdTables &T, const uint8_t *src, uint32_t len, uint8_t *dst, uint32_t op, uint32_t cap,
-										  uint8_t *lit)
+/* the sequences section as an iterator: begin() reads the header and the three tables and primes the
+ * backward bitstream, next() decodes one (literal length, match length, offset) applying the
+ * repeat-offset history, end() checks that the bitstream was used up exactly */
+struct ZsSeq
 {
-	uint32_t nlit = 0;
-	int used = zs_literals(T, src, len, lit, &nlit);
-	if (used < 0) return ZSTD_ERR;
-	const uint8_t *p = src + used;
-	uint32_t left = len - (uint32_t) used;
+	ZsBack r;
+	uint32_t sl, so, sm;
+	uint32_t nseq, done;
+};
+
+CG_HDN inline int zs_sequences_begin(ZstdTables &T, const uint8_t *p, uint32_t left, ZsSeq *S)
+{
+	S->done = 0;
 	if (left < 1) return ZSTD_ERR;
 	uint32_t nseq;
 	if (p[0] == 0) { nseq = 0; p += 1; left -= 1; }
 	else if (p[0] < 128) { nseq = p[0]; p += 1; left -= 1; }
 	else if (p[0] < 255) { if (left < 2) return ZSTD_ERR; nseq = ((uint32_t) (p[0] - 128) << 8) + p[1]; p += 2; left -= 2; }
 	else { if (left < 3) return ZSTD_ERR; nseq = (uint32_t) p[1] + ((uint32_t) p[2] << 8) + 0x7F00u; p += 3; left -= 3; }
-	uint32_t litpos = 0;
-	if (nseq > 0)
+	S->nseq = nseq;
+	if (nseq == 0) return left == 0 ? 0 : ZSTD_ERR;
+	if (left < 1) return ZSTD_ERR;
+	const uint32_t modes = p[0];
+	if (modes & 3u) return ZSTD_ERR;
+	p += 1; left -= 1;
+	for (int which = 0; which < 3; which++)
 	{
-		if (left < 1) return ZSTD_ERR;
-		const uint32_t modes = p[0];
-		if (modes & 3u) return ZSTD_ERR;
-		p += 1; left -= 1;
-		for (int which = 0; which < 3; which++)
-		{
-			int mode = (int) (modes >> (6 - 2 * which)) & 3;
-			int u = zs_seq_table(T, which, mode, p, left);
-			if (u < 0) return ZSTD_ERR;
-			p += u; left -= (uint32_t) u;
-		}
-		ZsBack r;
-		if (!zs_back_init(r, p, left)) return ZSTD_ERR;
-		uint32_t sl = zs_back_read(r, T.ll.log), so = zs_back_read(r, T.of.log), sm = zs_back_read(r, T.ml.log);
-		if (r.pos < 0) return ZSTD_ERR;
-		for (uint32_t s = 0; s < nseq; s++)
-		{
-			/* one 32-bit load per table entry: symbol | nbits << 8 | base << 16 */
-			const uint32_t eo = zs_entry(T.of.e, so), em = zs_entry(T.ml.e, sm), el = zs_entry(T.ll.e, sl);
-			const uint32_t of_code = eo & 0xffu, ml_sym = em & 0xffu, ll_sym = el & 0xffu;
-			if (of_code > 31 || ml_sym > 52 || ll_sym > 35) return ZSTD_ERR;
-			uint32_t ofv = (1u << of_code) + zs_back_read(r, (int) of_code);
-			uint32_t mbase, lbase; int mbits, lbits;
-			zs_ml_code(ml_sym, &mbase, &mbits);
-			zs_ll_code(ll_sym, &lbase, &lbits);
-			const uint32_t mlen = mbase + zs_back_read(r, mbits);
-			const uint32_t llen = lbase + zs_back_read(r, lbits);
-			if (s + 1 < nseq)
-			{
-				sl = (el >> 16) + zs_back_read(r, (int) ((el >> 8) & 0xffu));
-				sm = (em >> 16) + zs_back_read(r, (int) ((em >> 8) & 0xffu));
-				so = (eo >> 16) + zs_back_read(r, (int) ((eo >> 8) & 0xffu));
-			}
-			if (r.pos < 0) return ZSTD_ERR;
-			/* repeat-offset history */
-			uint32_t offset;
-			if (ofv > 3)
-			{
-				offset = ofv - 3;
-				T.rep[2] = T.rep[1]; T.rep[1] = T.rep[0]; T.rep[0] = offset;
-			}
-			else
-			{
-				uint32_t idx = ofv - 1 + (llen == 0 ? 1u : 0u);       /* 0..3 */
-				if (idx == 0) offset = T.rep[0];
-				else
-				{
-					offset = idx < 3 ? T.rep[idx] : T.rep[0] - 1;
-					if (offset == 0) return ZSTD_ERR;
-					if (idx > 1) T.rep[2] = T.rep[1];
-					T.rep[1] = T.rep[0];
-					T.rep[0] = offset;
-				}
-			}
-			if (llen > nlit - litpos || llen > cap - op) return ZSTD_ERR;
-			for (uint32_t i = 0; i < llen; i++) dst[op + i] = lit[litpos + i];
-			op += llen; litpos += llen;
-			if (offset > op || mlen > cap - op) return ZSTD_ERR;
-			zs_copy_match(dst, op, offset, mlen);
-			op += mlen;
-		}
-		if (r.pos != 0) return ZSTD_ERR;
+		int mode = (int) (modes >> (6 - 2 * which)) & 3;
+		int u = zs_seq_table(T, which, mode, p, left);
+		if (u < 0) return ZSTD_ERR;
+		p += u; left -= (uint32_t) u;
 	}
+	if (!zs_back_init(S->r, p, left)) return ZSTD_ERR;
+	S->sl = zs_back_read(S->r, T.ll.log);
+	S->so = zs_back_read(S->r, T.of.log);
+	S->sm = zs_back_read(S->r, T.ml.log);
+	return S->r.pos < 0 ? ZSTD_ERR : 0;
+}
+
+CG_HDN inline int zs_sequences_next(ZstdTables &T, ZsSeq *S, uint32_t *llen_out, uint32_t *mlen_out, uint32_t *offset_out)
+{
+	ZsBack &r = S->r;
+	/* one 32-bit load per table entry: symbol | nbits << 8 | base << 16 */
+	const uint32_t eo = zs_entry(T.of.e, S->so), em = zs_entry(T.ml.e, S->sm), el = zs_entry(T.ll.e, S->sl);
+	const uint32_t of_code = eo & 0xffu, ml_sym = em & 0xffu, ll_sym = el & 0xffu;
+	if (of_code > 31 || ml_sym > 52 || ll_sym > 35) return ZSTD_ERR;
+	const uint32_t ofv = (1u << of_code) + zs_back_read(r, (int) of_code);
+	uint32_t mbase, lbase; int mbits, lbits;
+	zs_ml_code(ml_sym, &mbase, &mbits);
+	zs_ll_code(ll_sym, &lbase, &lbits);
+	const uint32_t mlen = mbase + zs_back_read(r, mbits);
+	const uint32_t llen = lbase + zs_back_read(r, lbits);
+	if (++S->done < S->nseq)
+	{
+		S->sl = (el >> 16) + zs_back_read(r, (int) ((el >> 8) & 0xffu));
+		S->sm = (em >> 16) + zs_back_read(r, (int) ((em >> 8) & 0xffu));
+		S->so = (eo >> 16) + zs_back_read(r, (int) ((eo >> 8) & 0xffu));
+	}
+	if (r.pos < 0) return ZSTD_ERR;
+	/* repeat-offset history */
+	uint32_t offset;
+	if (ofv > 3)
+	{
+		offset = ofv - 3;
+		T.rep[2] = T.rep[1]; T.rep[1] = T.rep[0]; T.rep[0] = offset;
+	}
+	else
+	{
+		const uint32_t idx = ofv - 1 + (llen == 0 ? 1u : 0u);       /* 0..3 */
+		if (idx == 0) offset = T.rep[0];
+		else
+		{
+			offset = idx < 3 ? T.rep[idx] : T.rep[0] - 1;
+			if (offset == 0) return ZSTD_ERR;
+			if (idx > 1) T.rep[2] = T.rep[1];
+			T.rep[1] = T.rep[0];
+			T.rep[0] = offset;
+		}
+	}
+	*llen_out = llen; *mlen_out = mlen; *offset_out = offset;
+	return 0;
+}
+
+CG_HD int zs_sequences_end(const ZsSeq *S) { return (S->nseq == 0 || S->r.pos == 0) ? 0 : ZSTD_ERR; }
+
+/* one compressed block, sequentially; dst/op: the frame's output so far; returns the new op or ZSTD_ERR */
+CG_HDN inline int64_t zs_compressed_block(ZstdTables &T, const uint8_t *src, uint32_t len, uint8_t *dst, uint32_t op, uint32_t cap,
+										  uint8_t *lit)
+{
+	uint32_t nlit = 0;
+	int used = zs_literals(T, src, len, lit, &nlit);
+	if (used < 0) return ZSTD_ERR;
+	ZsSeq S;
+	if (zs_sequences_begin(T, src + used, len - (uint32_t) used, &S) < 0) return ZSTD_ERR;
+	uint32_t litpos = 0;
+	for (uint32_t s = 0; s < S.nseq; s++)
+	{
+		uint32_t llen, mlen, offset;
+		if (zs_sequences_next(T, &S, &llen, &mlen, &offset) < 0) return ZSTD_ERR;
+		if (llen > nlit - litpos || llen > cap - op) return ZSTD_ERR;
+		for (uint32_t i = 0; i < llen; i++) dst[op + i] = lit[litpos + i];
+		op += llen; litpos += llen;
+		if (offset > op || mlen > cap - op) return ZSTD_ERR;
+		zs_copy_match(dst, op, offset, mlen);
+		op += mlen;
+	}
+	if (zs_sequences_end(&S) < 0) return ZSTD_ERR;
 	const uint32_t rest = nlit - litpos;
 	if (rest > cap - op) return ZSTD_ERR;
 	for (uint32_t i = 0; i < rest; i++) dst[op + i] = lit[litpos + i];
 	return (int64_t) op + rest;
 }
 
-/*
- * One frame (what ZSTD_compress emits): returns the number of bytes produced (the caller compares it
- * with decompressedValueSize, like columnar_compression.c:226-232) or ZSTD_ERR.  lit: scratch of
- * ZSTD_BLOCK_MAX bytes.
- */
-CG_HDN inline int64_t zs_decode_frame(ZstdTables &T, const uint8_t *src, uint32_t len, uint8_t *dst, uint32_t cap, uint8_t *lit)
+/* frame header; returns the offset of the first block or ZSTD_ERR; *fcs = content size or ~0 when absent */
+CG_HDN inline int zs_frame_header(const uint8_t *src, uint32_t len, uint32_t cap, uint64_t *fcs_out, int *checksum_out)
 {
 	if (len < 6) return ZSTD_ERR;
 	if (src[0] != 0x28 || src[1] != 0xB5 || src[2] != 0x2F || src[3] != 0xFD) return ZSTD_ERR;
 	const uint32_t fhd = src[4];
-	const uint32_t fcs_flag = fhd >> 6, single = (fhd >> 5) & 1u, checksum = (fhd >> 2) & 1u, dict_flag = fhd & 3u;
+	const uint32_t fcs_flag = fhd >> 6, single = (fhd >> 5) & 1u, dict_flag = fhd & 3u;
 	if (fhd & 0x08u) return ZSTD_ERR;                 /* reserved bit */
 	if (dict_flag) return ZSTD_ERR;                   /* dictionaries: never used by the columnar writer */
 	uint32_t pos = 5;
@@ -603,6 +650,24 @@ CG_HDN inline int64_t zs_decode_frame(ZstdTables &T, const uint8_t *src, uint32_
 	if (fcs_bytes == 2) fcs += 256;
 	pos += fcs_bytes;
 	if (fcs_bytes && fcs > cap) return ZSTD_ERR;
+	*fcs_out = fcs_bytes ? fcs : ~0ull;
+	*checksum_out = (int) ((fhd >> 2) & 1u);
+	return (int) pos;
+}
+
+/*
+ * One frame (what ZSTD_compress emits): returns the number of bytes produced (the caller compares it
+ * with decompressedValueSize, like columnar_compression.c:226-232) or ZSTD_ERR.  lit: scratch of
+ * ZSTD_BLOCK_MAX bytes.
+ */
+CG_HDN inline int64_t zs_decode_frame(ZstdTables &T, const uint8_t *src, uint32_t len, uint8_t *dst, uint32_t cap, uint8_t *lit)
+{
+	uint64_t fcs;
+	int checksum;
+	int hp = zs_frame_header(src, len, cap, &fcs, &checksum);
+	if (hp < 0) return ZSTD_ERR;
+	uint32_t pos = (uint32_t) hp;
+	const uint32_t fcs_bytes = fcs != ~0ull;
 	T.huf_log = 0; T.have_ll = T.have_of = T.have_ml = 0;
 	T.rep[0] = 1; T.rep[1] = 4; T.rep[2] = 8;
 	uint32_t op = 0;
