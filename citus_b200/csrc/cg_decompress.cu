@@ -363,8 +363,16 @@ static __device__ int64_t zstd_block_coop(ZstdTables &T, ZsShared &C, const uint
 		const uint32_t nb = min(32u, nseq - base);
 		if (lane == 0)
 		{
+			/* the iterator state lives in registers while the batch is decoded */
+			ZsSeq S = C.S;
 			int st = 0;
-			for (uint32_t j = 0; j < nb && st == 0; j++) st = zs_sequences_next(T, &C.S, &C.ll[j], &C.ml[j], &C.off[j]);
+			for (uint32_t j = 0; j < nb && st == 0; j++)
+			{
+				uint32_t a, b, c;
+				st = zs_sequences_next(T, &S, &a, &b, &c);
+				C.ll[j] = a; C.ml[j] = b; C.off[j] = c;
+			}
+			C.S = S;
 			C.status = st;
 		}
 		__syncwarp();

@@ -558,7 +558,7 @@ CG_HDN inline int zs_sequences_begin(ZstdTables &T, const uint8_t *p, uint32_t l
 	return S->r.pos < 0 ? ZSTD_ERR : 0;
 }
 
-CG_HDN inline int zs_sequences_next(ZstdTables &T, ZsSeq *S, uint32_t *llen_out, uint32_t *mlen_out, uint32_t *offset_out)
+CG_HD int zs_sequences_next(ZstdTables &T, ZsSeq *S, uint32_t *llen_out, uint32_t *mlen_out, uint32_t *offset_out)
 {
 	ZsBack &r = S->r;
 	/* one 32-bit load per table entry: symbol | nbits << 8 | base << 16 */
