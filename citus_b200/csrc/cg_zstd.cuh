@@ -53,7 +53,14 @@ struct ZstdTables
 	uint16_t next[256];         /* scratch: per-symbol state counters / rank starts */
 };
 
-CG_HD int zs_highbit(uint32_t v) { int r = -1; while (v) { v >>= 1; r++; } return r; }
+CG_HD int zs_highbit(uint32_t v)
+{
+#ifdef __CUDA_ARCH__
+	return 31 - __clz((int) v);      /* -1 for 0 */
+#else
+	int r = -1; while (v) { v >>= 1; r++; } return r;
+#endif
+}
 
 /* ---- forward bit reader (FSE table descriptions): LSB first ---- */
 struct ZsFwd { const uint8_t *p; uint32_t len; uint32_t bit; };
@@ -76,42 +83,54 @@ struct ZsBack
 {
 	const uint8_t *p;
 	uint32_t len;
-	int32_t pos;        /* number of unread bits; may go negative (zeros).  Streams are < 2^20 bytes. */
-	uint32_t w0, w1;    /* bits [win_lo, win_lo + 64) of the stream, so that most reads touch no memory */
-	int32_t win_lo;     /* multiple of 8 */
+	int32_t pos;        /* number of unread bits; may go negative (zeros).  Streams are < 2^24 bytes. */
+	uint32_t hi, lo;    /* the next unread bits, left aligned: bit 31 of hi is the bit just below the cursor */
+	int32_t avail;      /* how many of them are loaded (bits below the start of the stream count: they are zeros) */
 };
-/* 32 bits starting `sh` (< 32) bits into the 64-bit pair hi:lo */
-CG_HD uint32_t zs_extract(uint32_t lo, uint32_t hi, uint32_t sh)
+/* (hi:lo << sh) >> 32, 0 <= sh <= 31 */
+CG_HD uint32_t zs_shl_hi(uint32_t lo, uint32_t hi, uint32_t sh)
 {
 #ifdef __CUDA_ARCH__
-	return __funnelshift_r(lo, hi, sh);
+	return __funnelshift_l(lo, hi, sh);
 #else
-	return (uint32_t) ((((uint64_t) hi << 32) | lo) >> sh);
+	return (uint32_t) (((((uint64_t) hi << 32) | lo) << sh) >> 32);
 #endif
 }
-CG_HD void zs_back_refill(ZsBack &r, int32_t top)      /* make [top - 56, top) available (as far as the stream reaches) */
+/* window := bits [pos - 64, pos), left aligned, zeros below bit 0 */
+CG_HD void zs_back_refill(ZsBack &r)
 {
-	int32_t lo = ((top + 7) & ~7) - 64;                /* the window ends at the first byte boundary at or above `top` */
-	if (lo < 0) lo = 0;
-	const uint32_t byte = (uint32_t) lo >> 3;
-	r.win_lo = lo;
-#ifdef __CUDA_ARCH__
-	if (byte + 8 <= r.len)
+	const int32_t top = r.pos;
+	if (top <= 0) { r.hi = r.lo = 0; r.avail = 64; return; }
+	const uint32_t byte_hi = (uint32_t) (top + 7) >> 3;         /* bytes [byte_hi - 8, byte_hi) hold the window */
+	const uint32_t slack = byte_hi * 8u - (uint32_t) top;        /* 0..7 bits above the cursor */
+	uint32_t w0 = 0, w1 = 0;
+	if (byte_hi >= 8)
 	{
+		const uint8_t *q = r.p + byte_hi - 8;
+#ifdef __CUDA_ARCH__
 		/* 8 bytes at any alignment from three aligned words (arena slots are padded, the over-read stays inside) */
-		const uintptr_t a = (uintptr_t) (r.p + byte);
+		const uintptr_t a = (uintptr_t) q;
 		const uint32_t *aw = (const uint32_t *) (a & ~(uintptr_t) 3);
 		const uint32_t sh = (uint32_t) (a & 3u) * 8u;
 		const uint32_t x0 = aw[0], x1 = aw[1], x2 = aw[2];
-		r.w0 = __funnelshift_r(x0, x1, sh);
-		r.w1 = __funnelshift_r(x1, x2, sh);
-		return;
-	}
+		w0 = __funnelshift_r(x0, x1, sh);
+		w1 = __funnelshift_r(x1, x2, sh);
+#else
+		for (uint32_t i = 0; i < 4; i++) { w0 |= (uint32_t) q[i] << (8 * i); w1 |= (uint32_t) q[4 + i] << (8 * i); }
 #endif
-	uint32_t w0 = 0, w1 = 0;
-	for (uint32_t i = 0; i < 4 && byte + i < r.len; i++) w0 |= (uint32_t) r.p[byte + i] << (8 * i);
-	for (uint32_t i = 0; i < 4 && byte + 4 + i < r.len; i++) w1 |= (uint32_t) r.p[byte + 4 + i] << (8 * i);
-	r.w0 = w0; r.w1 = w1;
+	}
+	else
+	{
+		/* near the start of the stream: byte (byte_hi - 1) is the top byte, what is below byte 0 is zero */
+		for (uint32_t i = 0; i < byte_hi; i++)
+		{
+			const uint32_t at = 8u - byte_hi + i;                /* position of stream byte i inside the 8-byte window */
+			if (at < 4) w0 |= (uint32_t) r.p[i] << (8 * at); else w1 |= (uint32_t) r.p[i] << (8 * (at - 4));
+		}
+	}
+	r.hi = zs_shl_hi(w0, w1, slack);
+	r.lo = w0 << slack;
+	r.avail = 64 - (int32_t) slack;
 }
 CG_HD bool zs_back_init(ZsBack &r, const uint8_t *p, uint32_t len)
 {
@@ -119,30 +138,27 @@ CG_HD bool zs_back_init(ZsBack &r, const uint8_t *p, uint32_t len)
 	r.p = p;
 	r.len = len;
 	r.pos = (int32_t) (len - 1) * 8 + zs_highbit(p[len - 1]);
-	zs_back_refill(r, r.pos);
+	zs_back_refill(r);
 	return true;
 }
-/* bits [pos - n, pos), top bit first, zero below bit 0; n <= 31 */
-CG_HD uint32_t zs_back_peek_at(ZsBack &r, int32_t pos, int n)
+/* the n bits below the cursor, top bit first (1 <= n <= 31; bits below the start of the stream are zeros) */
+CG_HD uint32_t zs_back_peek(ZsBack &r, int n)
 {
-	const int32_t lo = pos - n;
-	if (lo < 0)
-	{
-		/* the read runs off the start of the stream: the missing low bits are zeros */
-		if (pos <= 0 || n == 0) return 0;
-		if (r.win_lo != 0) zs_back_refill(r, pos);
-		const uint32_t have = r.w0 & ((1u << pos) - 1u);          /* pos < n <= 31 */
-		return (have << (uint32_t) (-lo)) & ((1u << n) - 1u);
-	}
-	if (lo < r.win_lo || pos > r.win_lo + 64) zs_back_refill(r, pos);
-	const uint32_t off = (uint32_t) (lo - r.win_lo);
-	const uint32_t v = off < 32u ? zs_extract(r.w0, r.w1, off) : (r.w1 >> (off - 32u));
-	return v & ((1u << n) - 1u);
+	if (r.avail < n) zs_back_refill(r);
+	return r.hi >> (32 - n);
+}
+CG_HD void zs_back_skip(ZsBack &r, int n)      /* 0 <= n <= 31, n <= avail */
+{
+	r.hi = zs_shl_hi(r.lo, r.hi, (uint32_t) n);
+	r.lo <<= n;
+	r.avail -= n;
+	r.pos -= n;
 }
 CG_HD uint32_t zs_back_read(ZsBack &r, int n)
 {
-	uint32_t v = zs_back_peek_at(r, r.pos, n);
-	r.pos -= n;
+	if (n == 0) return 0;
+	const uint32_t v = zs_back_peek(r, n);
+	zs_back_skip(r, n);
 	return v;
 }
 
@@ -316,27 +332,27 @@ CG_HDN inline int zs_huf_stream(const ZstdTables &T, const uint8_t *src, uint32_
 	/* bytes up to a 4-byte boundary of `out`, then four symbols per store */
 	while (i < count && (((uintptr_t) (out + i)) & 3u) != 0)
 	{
-		const HufEntry h = T.huf[zs_back_peek_at(r, r.pos, log)];
+		const HufEntry h = T.huf[zs_back_peek(r, log)];
 		out[i++] = h.symbol;
-		r.pos -= h.nbits;
+		zs_back_skip(r, h.nbits);
 	}
 	for (; i + 4 <= count; i += 4)
 	{
 		uint32_t w = 0;
 		for (int k = 0; k < 4; k++)
 		{
-			const HufEntry h = T.huf[zs_back_peek_at(r, r.pos, log)];
+			const HufEntry h = T.huf[zs_back_peek(r, log)];
 			w |= (uint32_t) h.symbol << (8 * k);
-			r.pos -= h.nbits;
+			zs_back_skip(r, h.nbits);
 		}
 		*(uint32_t *) (out + i) = w;
 		if (r.pos < 0) return ZSTD_ERR;
 	}
 	for (; i < count; i++)
 	{
-		const HufEntry h = T.huf[zs_back_peek_at(r, r.pos, log)];
+		const HufEntry h = T.huf[zs_back_peek(r, log)];
 		out[i] = h.symbol;
-		r.pos -= h.nbits;
+		zs_back_skip(r, h.nbits);
 	}
 	return r.pos == 0 ? 0 : ZSTD_ERR;
 }
