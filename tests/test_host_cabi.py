@@ -298,3 +298,43 @@ def test_zstd_decoder_against_libzstd(cg, oracle):
             if len(comp) > 12:
                 n = capi.lib().cg_test_zstd_decode_host(src.ctypes.data, len(comp) - 1, dst.ctypes.data, len(data))
                 assert n != len(data), (name, level, "truncated")
+
+
+def test_zstd_hand_assembled_frames(cg, oracle):
+    """frames built by hand from RFC 8878 (no encoder involved): a raw block, an RLE block, two blocks,
+    and malformed variants; the library's decoder and libzstd (through the oracle) must agree"""
+    from citus_b200 import capi
+
+    def frame(blocks, fcs):
+        out = bytes([0x28, 0xB5, 0x2F, 0xFD, 0x20, fcs])            # magic, FHD: single segment + 1-byte content size
+        for i, (btype, size, payload) in enumerate(blocks):
+            hdr = (size << 3) | (btype << 1) | (1 if i == len(blocks) - 1 else 0)
+            out += hdr.to_bytes(3, "little") + payload
+        return out
+
+    def ours(data, cap):
+        src = np.frombuffer(data, np.uint8)
+        dst = np.zeros(cap + 8, np.uint8)
+        n = capi.lib().cg_test_zstd_decode_host(src.ctypes.data, len(data), dst.ctypes.data, cap)
+        return n, dst[:max(n, 0)].tobytes()
+
+    cases = [
+        (frame([(0, 5, b"hello")], 5), b"hello"),
+        (frame([(1, 7, b"z")], 7), b"z" * 7),
+        (frame([(0, 3, b"abc"), (1, 4, b"!")], 7), b"abc!!!!"),
+    ]
+    for data, want in cases:
+        n, got = ours(data, len(want))
+        assert n == len(want) and got == want
+        if oracle.lib().orc_have_zstd():
+            assert oracle.codec_decompress(oracle.COMP_ZSTD, data, len(want)) == want
+    bad = [
+        frame([(0, 5, b"hello")], 6),                                   # content size does not match
+        frame([(3, 5, b"hello")], 5),                                   # reserved block type
+        frame([(0, 5, b"hell")], 5),                                    # truncated
+        b"\x28\xB5\x2F\xFE" + frame([(0, 5, b"hello")], 5)[4:],         # wrong magic
+        frame([(0, 5, b"hello")], 5) + b"x",                            # trailing garbage
+    ]
+    for data in bad:
+        n, _ = ours(data, 16)
+        assert n < 0, data
