@@ -100,7 +100,6 @@ SYMBOLS = [
     ("cg_partial_dense_words_enqueue", C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     ("cg_partial_check", C.c_int, [_P]),
     ("cg_gen_set_compression", C.c_int, [C.c_int32]),
-    ("cg_test_zstd_decode_host", C.c_int64, [_P, C.c_uint32, _P, C.c_uint32]),
     ("cg_jit_launches", C.c_uint64, []),
     ("cg_jit_compiles", C.c_uint64, []),
     ("cg_jit_compile_check", C.c_int, [C.POINTER(CgScanDesc), C.POINTER(CgColumnDesc), C.c_int32, C.c_int64, C.c_int64, C.c_int64,

@@ -511,19 +511,6 @@ cg_zstd_kernel(uint8_t *arena, const DecodeItem *items, uint32_t nitems, uint8_t
 	}
 }
 
-/* the same decoder on the host: lets the -m "not gpu" tests check the bit-level format logic against
- * libzstd-compressed streams.  Test hook only: nothing in the library's data path calls it. */
-extern "C" int64_t cg_test_zstd_decode_host(const uint8_t *src, uint32_t len, uint8_t *dst, uint32_t cap)
-{
-	ZstdTables *T = new ZstdTables();
-	uint8_t *lit = new uint8_t[CGD_ZSTD_SCRATCH];
-	T->huf = (HufEntry *) (lit + ZSTD_BLOCK_MAX + 64);
-	int64_t n = zs_decode_frame(*T, src, len, dst, cap, lit);
-	delete[] lit;
-	delete T;
-	return n;
-}
-
 /* h_items: the host copy of the same items (which kernels are needed) */
 int cg_launch_decompress(CgContext *ctx, uint8_t *arena, const DecodeItem *items, const DecodeItem *h_items, uint64_t nitems,
 						 unsigned long long *err, unsigned long long flag, cudaStream_t stream)

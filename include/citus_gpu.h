@@ -393,10 +393,6 @@ int cg_write_relation(const CgColumnDesc *cols, int32_t natts, const int64_t *co
  * CG_COMPRESSION_LZ4 or CG_COMPRESSION_ZSTD (liblz4's LZ4_compress_default / libzstd's
  * ZSTD_compress at level 3, as the reference's CompressBuffer) */
 int cg_gen_set_compression(int32_t compression);
-/* Test hook: the library's Zstandard decoder (the code cg_zstd_kernel runs on one GPU lane) executed on
- * the host, so that the bit-level format logic can be checked against libzstd without a GPU.  Returns the
- * decoded size or -1.  Nothing in the data path calls it. */
-int64_t cg_test_zstd_decode_host(const uint8_t *src, uint32_t len, uint8_t *dst, uint32_t cap);
 int cg_gen_relation_view(const CgGenRelation *g, CgRelation *view);
 void cg_gen_relation_free(CgGenRelation *g);
 

@@ -264,7 +264,25 @@ def test_jit_generates_valid_sm100a_code_for_every_plan_form(cg):
 
 
 # --------------------------------------------------------------------------- Zstandard decoder (format logic on the host)
-def test_zstd_decoder_against_libzstd(cg, oracle):
+@pytest.fixture(scope="module")
+def zstd_host():
+    """tests/helpers/zstd_host.cpp: the decoder source of the GPU kernel compiled for the host (g++), a test-only
+    shared object -- libcitus_gpu.so itself has no host decoding path"""
+    import subprocess
+    out_dir = os.path.join(ROOT, "tests", "helpers", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libzstd_host.so")
+    src = os.path.join(ROOT, "tests", "helpers", "zstd_host.cpp")
+    hdr = os.path.join(ROOT, "citus_b200", "csrc", "cg_zstd.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", "-I", os.path.dirname(hdr), "-o", so, src])
+    L = C.CDLL(so)
+    L.zstd_decode_host.restype = C.c_longlong
+    L.zstd_decode_host.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint]
+    return L
+
+
+def test_zstd_decoder_against_libzstd(cg, oracle, zstd_host):
     """cg_zstd.cuh is sequential code one GPU lane runs; the same source is executed here on the host
     against streams produced by libzstd's ZSTD_compress (what the reference's CompressBuffer calls)"""
     from citus_b200 import capi
@@ -291,16 +309,16 @@ def test_zstd_decoder_against_libzstd(cg, oracle):
             assert comp is not None
             src = np.frombuffer(comp, np.uint8)
             dst = np.zeros(len(data) + 64, np.uint8)
-            n = capi.lib().cg_test_zstd_decode_host(src.ctypes.data, len(comp), dst.ctypes.data, len(data))
+            n = zstd_host.zstd_decode_host(src.ctypes.data, len(comp), dst.ctypes.data, len(data))
             assert n == len(data) and dst[:len(data)].tobytes() == data, (name, level)
             # damaged streams are rejected, never decoded to something else of the right size silently ... except
             # where the damage lands in unused bits; a truncated stream always fails
             if len(comp) > 12:
-                n = capi.lib().cg_test_zstd_decode_host(src.ctypes.data, len(comp) - 1, dst.ctypes.data, len(data))
+                n = zstd_host.zstd_decode_host(src.ctypes.data, len(comp) - 1, dst.ctypes.data, len(data))
                 assert n != len(data), (name, level, "truncated")
 
 
-def test_zstd_hand_assembled_frames(cg, oracle):
+def test_zstd_hand_assembled_frames(cg, oracle, zstd_host):
     """frames built by hand from RFC 8878 (no encoder involved): a raw block, an RLE block, two blocks,
     and malformed variants; the library's decoder and libzstd (through the oracle) must agree"""
     from citus_b200 import capi
@@ -315,7 +333,7 @@ def test_zstd_hand_assembled_frames(cg, oracle):
     def ours(data, cap):
         src = np.frombuffer(data, np.uint8)
         dst = np.zeros(cap + 8, np.uint8)
-        n = capi.lib().cg_test_zstd_decode_host(src.ctypes.data, len(data), dst.ctypes.data, cap)
+        n = zstd_host.zstd_decode_host(src.ctypes.data, len(data), dst.ctypes.data, cap)
         return n, dst[:max(n, 0)].tobytes()
 
     cases = [
