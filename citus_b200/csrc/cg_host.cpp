@@ -304,6 +304,9 @@ static int stripe_chunk_mask(const CgStripe &s, const CgSkipNode *nodes, const C
 	for (int c = 0; c < natts && c < 256; c++)      /* whereClauseVars, in attribute order */
 	{
 		if (!has_qual[c]) continue;
+		/* a column added after the stripe was written has no skip nodes: the reference gives it zeroed
+		 * nodes with hasMinMax = false (ReadStripeSkipList, columnar_metadata.c:753-760), which refute nothing */
+		if ((uint32_t) c >= s.column_count) continue;
 		for (uint32_t k = 0; k < s.chunk_count; k++)
 		{
 			const CgSkipNode &node = nodes[s.skipnode_base + (uint32_t) c * s.chunk_count + k];
@@ -1031,7 +1034,7 @@ static int plan_dma(const CgRelation *rel, const std::vector<int32_t> &staged,
 			if (select[si][k]) { if (first == UINT32_MAX) first = k; last = k; }
 		if (first == UINT32_MAX) continue;
 		/* raw offset of logical byte 0 of page p0[j] for staged column j */
-		std::vector<uint64_t> base(ns, 0), p0(ns, 0);
+		std::vector<uint64_t> base(ns, 0), p0(ns, 0), span_lo(ns, 1), span_hi(ns, 0);
 		struct Span { uint64_t b0, b1; size_t j; };
 		std::vector<Span> spans;
 		for (size_t j = 0; j < ns; j++)
@@ -1042,10 +1045,15 @@ static int plan_dma(const CgRelation *rel, const std::vector<int32_t> &staged,
 			const CgSkipNode &nl = rel->nodes[s.skipnode_base + (uint32_t) c * s.chunk_count + last];
 			uint64_t lb = s.file_offset + nf.exists_offset;
 			uint64_t le = s.file_offset + nl.value_offset + nl.value_length;
+			if (le < lb || nl.value_offset + nl.value_length < nl.value_offset)
+				return cg_set_error(CG_ECORRUPT, "chunk offsets of column %d run backwards in stripe %d", c, si);
+			span_lo[j] = lb; span_hi[j] = le;
 			if (le <= lb) le = lb + 1;
 			uint64_t b0 = lb / CG_BYTES_PER_PAGE, b1 = (le - 1) / CG_BYTES_PER_PAGE;
 			if (b1 >= rel->nblocks) return cg_set_error(CG_ECORRUPT, "attempt to read columnar data past end of relation");
-			/* pd_lower of the first and last page of the span (ReadFromBlock checks every page) */
+			/* pd_lower of the first and last page of the span (ReadFromBlock, columnar_storage.c:677, checks every
+			 * page; touching the header of each of the ~3 M pages of a 24 GB scan would cost more host time than
+			 * the copies themselves, so interior pages are trusted to be full) */
 			uint16_t lower;
 			memcpy(&lower, rel->pages + b1 * CG_BLCKSZ + 12, 2);
 			if (lower < CG_PAGE_HEADER + ((le - 1) % CG_BYTES_PER_PAGE) + 1)
@@ -1079,6 +1087,12 @@ static int plan_dma(const CgRelation *rel, const std::vector<int32_t> &staged,
 				const StageItem &it = sp.items[g * ns + j];
 				uint64_t exspan = it.wire_value_off - d.exists_off;
 				uint64_t vaspan = pad16(it.value_len) + 16;
+				/* every chunk buffer must lie inside the byte range its column's copy covers (the pageable path
+				 * reports the same images as past-pd_lower reads; here an unchecked offset would make the
+				 * realign kernel read arbitrary device memory) */
+				if ((it.exists_len && (it.exists_logical < span_lo[j] || it.exists_logical + it.exists_len > span_hi[j])) ||
+					(it.value_len && (it.value_logical < span_lo[j] || it.value_logical + it.value_len > span_hi[j])))
+					return cg_set_error(CG_ECORRUPT, "chunk buffer outside its column's byte range in stripe %d", si);
 				auto phys = [&](uint64_t logical) {
 					uint64_t rel0 = logical - p0[j] * CG_BYTES_PER_PAGE;
 					return base[j] + (rel0 / CG_BYTES_PER_PAGE) * CG_BLCKSZ + CG_PAGE_HEADER + rel0 % CG_BYTES_PER_PAGE;
@@ -1180,6 +1194,20 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 		if (!ctx->dma_done[mslot]) CG_CUDA(cudaEventCreateWithFlags(&ctx->dma_done[mslot], cudaEventDisableTiming));
 		if (!ctx->dma_copied) CG_CUDA(cudaEventCreateWithFlags(&ctx->dma_copied, cudaEventDisableTiming));
 		CG_CUDA(cudaEventSynchronize(ctx->dma_done[mslot]));      /* bounds the shards in flight; frees the slot */
+		/* once work on the slot's buffers has been enqueued, every exit path must leave dma_done[mslot] behind
+		 * that work: on an error return the copy and decode streams are drained and the event is recorded, so
+		 * the next user of the slot cannot free or overwrite buffers that are still being written */
+		struct SlotGuard
+		{
+			CgContext *ctx; int slot; bool armed = true; cudaStream_t side = nullptr;
+			~SlotGuard()
+			{
+				if (!armed) return;
+				cudaStreamSynchronize(ctx->copy);
+				if (side) cudaStreamSynchronize(side);
+				cudaEventRecord(ctx->dma_done[slot], ctx->compute);
+			}
+		} slot_guard{ctx, mslot};
 		if (ctx->meta_cap[mslot] < meta_bytes)
 		{
 			if (ctx->meta_pinned[mslot]) CG_CUDA(cudaFreeHost(ctx->meta_pinned[mslot]));
@@ -1308,6 +1336,7 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 				if (!ctx->decode_stream[ds]) CG_CUDA(cudaStreamCreateWithFlags(&ctx->decode_stream[ds], cudaStreamNonBlocking));
 				if (!ctx->decoded[mslot]) CG_CUDA(cudaEventCreateWithFlags(&ctx->decoded[mslot], cudaEventDisableTiming));
 				cudaStream_t side = ctx->decode_stream[ds];
+				slot_guard.side = side;
 				CG_CUDA(cudaStreamWaitEvent(side, ctx->dma_copied, 0));
 				rc = cg_launch_realign(d_raw, d_arena, (const RealignItem *) (d_meta + off_items), items.size(), side);
 				if (rc == CG_OK)
@@ -1341,8 +1370,9 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 		else
 			rc = stream_to_device(ctx, rel, sp, ns, d_arena, launch_block);
 		if (stats && rc == CG_OK) CG_CUDA(cudaEventRecord(ctx->ev_b, ctx->compute));
+		if (rc) return rc;                  /* slot_guard drains the side streams and records the event */
 		CG_CUDA(cudaEventRecord(ctx->dma_done[mslot], ctx->compute));
-		if (rc) return rc;
+		slot_guard.armed = false;
 	}
 	if (stats)
 	{

@@ -29,6 +29,19 @@ extern unsigned long long g_cg_launches;   /* kernels launched by this library (
 								cudaGetErrorString(e__), __FILE__, __LINE__);                 \
 	} while (0)
 
+/* stream-ordered scratch that is returned to the pool on every exit path */
+struct CgAsyncBuf
+{
+	void *p = nullptr;
+	cudaStream_t stream = nullptr;
+	CgAsyncBuf() {}
+	CgAsyncBuf(const CgAsyncBuf &) = delete;
+	CgAsyncBuf &operator=(const CgAsyncBuf &) = delete;
+	~CgAsyncBuf() { if (p) cudaFreeAsync(p, stream); }
+	cudaError_t alloc(size_t bytes, cudaStream_t s) { stream = s; return cudaMallocAsync(&p, bytes ? bytes : 8, s); }
+	template <typename T> T *as() const { return (T *) p; }
+};
+
 struct CgContext
 {
 	int device = -1;

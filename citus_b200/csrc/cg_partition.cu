@@ -89,8 +89,10 @@ cg_partition_index_kernel(const __grid_constant__ PartParams A)
 		else
 		{
 			int64_t k = A.keys[r];
-			int32_t searched = A.by_hash ? (A.key_len == 4 ? (int32_t) hash_bytes_uint32((uint32_t) (int32_t) k) : hashint8_dev(k))
-										 : (int32_t) k;
+			/* range partitioning compares the key itself: an int8 key outside the int4 interval bounds lies in no
+			 * interval ("could not find shard"), it must not be truncated into one */
+			int64_t searched = A.by_hash ? (int64_t) (A.key_len == 4 ? (int32_t) hash_bytes_uint32((uint32_t) (int32_t) k) : hashint8_dev(k))
+										 : (A.key_len == 4 ? (int64_t) (int32_t) k : k);
 			/* SearchCachedShardInterval */
 			int lower = 0, upper = A.P;
 			idx = -1;
@@ -232,8 +234,9 @@ extern "C" int cg_partition_index(const int64_t *d_keys, const uint8_t *d_nulls,
 	}
 	CG_CUDA(cudaMemcpyAsync(g_d_bounds, mins, sizeof(int32_t) * P, cudaMemcpyHostToDevice, ctx->compute));
 	CG_CUDA(cudaMemcpyAsync(g_d_bounds + CGP_MAX_P, maxs, sizeof(int32_t) * P, cudaMemcpyHostToDevice, ctx->compute));
-	unsigned long long *d_err = nullptr;
-	CG_CUDA(cudaMallocAsync((void **) &d_err, sizeof(unsigned long long), ctx->compute));
+	CgAsyncBuf err_buf;
+	CG_CUDA(err_buf.alloc(sizeof(unsigned long long), ctx->compute));
+	unsigned long long *d_err = err_buf.as<unsigned long long>();
 	CG_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned long long), ctx->compute));
 	CG_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int64_t) * P, ctx->compute));
 	if (n > 0)
@@ -249,7 +252,6 @@ extern "C" int cg_partition_index(const int64_t *d_keys, const uint8_t *d_nulls,
 	unsigned long long err = 0;
 	CG_CUDA(cudaMemcpyAsync(&err, d_err, sizeof err, cudaMemcpyDeviceToHost, ctx->compute));
 	CG_CUDA(cudaStreamSynchronize(ctx->compute));
-	CG_CUDA(cudaFreeAsync(d_err, ctx->compute));
 	if (err) return cg_set_error(CG_EINVAL, "could not find shard for partition column value (%llu rows)", err);
 	return CG_OK;
 }
@@ -332,15 +334,17 @@ extern "C" int cg_partition_scatter_ordered(const int32_t *d_index, int64_t n, i
 		}
 	}
 	int64_t nblocks = (n + CGP_ROWS_PER_BLOCK - 1) / CGP_ROWS_PER_BLOCK;
-	unsigned long long *d_block = nullptr, *d_tot = nullptr;
+	CgAsyncBuf block_buf, tot_buf, order_buf;
 	int32_t *d_order = nullptr;
-	CG_CUDA(cudaMallocAsync((void **) &d_block, sizeof(unsigned long long) * (size_t) std::max<int64_t>(nblocks, 1) * P, ctx->compute));
-	CG_CUDA(cudaMallocAsync((void **) &d_tot, sizeof(unsigned long long) * (2 * P + 1), ctx->compute));
+	CG_CUDA(block_buf.alloc(sizeof(unsigned long long) * (size_t) std::max<int64_t>(nblocks, 1) * P, ctx->compute));
+	CG_CUDA(tot_buf.alloc(sizeof(unsigned long long) * (2 * P + 1), ctx->compute));
+	unsigned long long *d_block = block_buf.as<unsigned long long>(), *d_tot = tot_buf.as<unsigned long long>();
 	unsigned long long *d_base = d_tot + P;
 	CG_CUDA(cudaMemsetAsync(d_tot, 0, sizeof(unsigned long long) * (2 * P + 1), ctx->compute));
 	if (h_order)
 	{
-		CG_CUDA(cudaMallocAsync((void **) &d_order, sizeof(int32_t) * P, ctx->compute));
+		CG_CUDA(order_buf.alloc(sizeof(int32_t) * P, ctx->compute));
+		d_order = order_buf.as<int32_t>();
 		CG_CUDA(cudaMemcpyAsync(d_order, h_order, sizeof(int32_t) * P, cudaMemcpyHostToDevice, ctx->compute));
 	}
 	if (n > 0)
@@ -369,9 +373,6 @@ extern "C" int cg_partition_scatter_ordered(const int32_t *d_index, int64_t n, i
 	CG_CUDA(cudaMemcpyAsync(base.data(), d_base, sizeof(unsigned long long) * (P + 1), cudaMemcpyDeviceToHost, ctx->compute));
 	CG_CUDA(cudaStreamSynchronize(ctx->compute));
 	for (int p = 0; p <= P; p++) h_offsets[p] = (int64_t) base[p];
-	CG_CUDA(cudaFreeAsync(d_block, ctx->compute));
-	CG_CUDA(cudaFreeAsync(d_tot, ctx->compute));
-	if (d_order) CG_CUDA(cudaFreeAsync(d_order, ctx->compute));
 	return CG_OK;
 }
 
@@ -466,8 +467,9 @@ extern "C" int cg_partition_copy_bytes(const int32_t *d_index, int64_t n, int32_
 	if (P < 1 || P > CGP_MAX_P) return cg_set_error(CG_EINVAL, "partition count %d out of range", P);
 	if (ncols < 1 || ncols > CGP_MAX_COLS) return cg_set_error(CG_EUNSUPPORTED, "1..%d columns", CGP_MAX_COLS);
 	if (n < 0 || !d_cols || !col_len || !rows_written || !bytes_written) return cg_set_error(CG_EINVAL, "bad argument");
-	unsigned long long *d_acc = nullptr;
-	CG_CUDA(cudaMallocAsync((void **) &d_acc, 2 * (size_t) P * sizeof(unsigned long long), ctx->compute));
+	CgAsyncBuf acc_buf;
+	CG_CUDA(acc_buf.alloc(2 * (size_t) P * sizeof(unsigned long long), ctx->compute));
+	unsigned long long *d_acc = acc_buf.as<unsigned long long>();
 	CG_CUDA(cudaMemsetAsync(d_acc, 0, 2 * (size_t) P * sizeof(unsigned long long), ctx->compute));
 	if (n > 0)
 	{
@@ -488,7 +490,6 @@ extern "C" int cg_partition_copy_bytes(const int32_t *d_index, int64_t n, int32_
 	std::vector<unsigned long long> h(2 * (size_t) P, 0);
 	CG_CUDA(cudaMemcpyAsync(h.data(), d_acc, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->compute));
 	CG_CUDA(cudaStreamSynchronize(ctx->compute));
-	CG_CUDA(cudaFreeAsync(d_acc, ctx->compute));
 	for (int p = 0; p < P; p++)
 	{
 		rows_written[p] = (int64_t) h[P + p];

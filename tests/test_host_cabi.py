@@ -356,3 +356,33 @@ def test_zstd_hand_assembled_frames(cg, oracle, zstd_host):
     for data in bad:
         n, _ = ours(data, 16)
         assert n < 0, data
+
+
+def test_qual_on_column_added_after_the_stripe_was_written(cg):
+    """ALTER TABLE ADD COLUMN: a stripe written with fewer columns than the relation has now has no skip
+    nodes for the new column; the reference gives it zeroed nodes without min/max (ReadStripeSkipList,
+    columnar_metadata.c:753-760), so a WHERE on that column skips no chunk group -- and must not read
+    another stripe's nodes (or past the node array)."""
+    from citus_b200 import capi
+    rng = np.random.default_rng(3)
+    n = 9000
+    a = np.arange(n)
+    b = rng.integers(0, 100, n)
+    rel2 = cg.Relation.write([8, 8], [a, b], stripe_row_limit=3000, chunk_row_limit=1000)
+    assert rel2.view.nstripes == 3 and rel2.view.stripes[0].column_count == 2
+    rel3 = cg.Relation.from_image(rel2.pages(), rel2.stripes_bytes(), rel2.nodes_bytes(), [8, 8, 8])
+    d = cg.make_desc([(2, "<", 5)], [], [cg.count_star()])
+    for si in range(3):
+        mask = np.zeros(3, np.uint8)
+        filtered = C.c_int64(-1)
+        capi.check(capi.lib().cg_selected_chunk_mask(C.byref(rel3.view), si, C.byref(d), mask.ctypes.data, C.byref(filtered)))
+        assert mask.tolist() == [1, 1, 1] and filtered.value == 0
+    # a qual on an existing column still skips: a >= 8000 leaves only the last chunk of the last stripe
+    d = cg.make_desc([(0, ">=", 8000), (2, "<", 5)], [], [cg.count_star()])
+    total = 0
+    for si in range(3):
+        mask = np.zeros(3, np.uint8)
+        filtered = C.c_int64(-1)
+        capi.check(capi.lib().cg_selected_chunk_mask(C.byref(rel3.view), si, C.byref(d), mask.ctypes.data, C.byref(filtered)))
+        total += filtered.value
+    assert total == 8
