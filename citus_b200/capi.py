@@ -21,6 +21,7 @@ CG_AGG_COUNT_STAR, CG_AGG_COUNT, CG_AGG_SUM, CG_AGG_MIN, CG_AGG_MAX = range(5)
 CG_WORD_ADD, CG_WORD_MIN, CG_WORD_MAX, CG_WORD_FADD, CG_WORD_FMIN, CG_WORD_FMAX = range(6)
 CG_GEN_UNIFORM, CG_GEN_SEQUENCE = 0, 1
 CG_MAX_QUALS, CG_MAX_AGGS, CG_MAX_GROUP_COLS = 8, 8, 2
+CG_MAX_QEXPR, CG_QX_AND, CG_QX_OR = 16, -1, -2
 
 
 class CgSkipNode(C.Structure):
@@ -69,7 +70,8 @@ class CgScanDesc(C.Structure):
     _fields_ = [("nquals", C.c_int32), ("quals", CgQual * CG_MAX_QUALS),
                 ("enable_qual_pushdown", C.c_int32), ("ngroup_cols", C.c_int32),
                 ("group_cols", C.c_int32 * CG_MAX_GROUP_COLS), ("naggs", C.c_int32),
-                ("aggs", CgAggSpec * CG_MAX_AGGS), ("expected_groups", C.c_int64)]
+                ("aggs", CgAggSpec * CG_MAX_AGGS), ("expected_groups", C.c_int64),
+                ("nqual_expr", C.c_int32), ("qual_expr", C.c_int8 * CG_MAX_QEXPR), ("reserved", C.c_int32)]
 
 
 class CgScanStats(C.Structure):
@@ -104,6 +106,9 @@ SYMBOLS = [
     ("cg_jit_compiles", C.c_uint64, []),
     ("cg_jit_compile_check", C.c_int, [C.POINTER(CgScanDesc), C.POINTER(CgColumnDesc), C.c_int32, C.c_int64, C.c_int64, C.c_int64,
                                       C.POINTER(C.c_int32), C.c_char_p, C.c_size_t]),
+    ("cg_jit_compile_check_nullable", C.c_int, [C.POINTER(CgScanDesc), C.POINTER(CgColumnDesc), C.c_int32, C.c_int64, C.c_int64,
+                                               C.c_int64, C.c_uint32, C.POINTER(C.c_int32), C.c_char_p, C.c_size_t]),
+    ("cg_set_option", C.c_int, [C.c_char_p, C.c_int64]),
     ("cg_numa_bind", C.c_int, [C.POINTER(C.c_int32)]),
     ("cg_numa_unbind", C.c_int, []),
     ("cg_profile_begin", C.c_int, []),

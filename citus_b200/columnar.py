@@ -31,6 +31,11 @@ def init(device: int = 0):
     _initialised = True
 
 
+def set_option(name: str, value: int):
+    """cg_set_option: "jit" 0/1/2, "force_general" 0/1"""
+    check(lib().cg_set_option(name.encode(), value))
+
+
 def numa_bind() -> int:
     """pin this thread (and the staging/generator threads created after it) to the CPUs of the
     device's NUMA node; returns the node or -1"""
@@ -206,8 +211,37 @@ def max_(col, is_float=False):
     return Agg(CG_AGG_MAX, [(col, 0, 1)], is_float)
 
 
+def flatten_where(where):
+    """WHERE as a nested tuple tree -- ("and" | "or", arm, arm, ...) over atoms (column, op, constant); a plain
+    list of atoms is their AND -- to (atoms, postfix tokens).  The tokens are empty for a plain AND-list."""
+    if not (isinstance(where, tuple) and where and where[0] in ("and", "or")):
+        return list(where), []
+    atoms, tokens = [], []
+
+    def walk(node):
+        if isinstance(node, tuple) and node and node[0] in ("and", "or"):
+            if len(node) < 2:
+                raise ValueError("empty boolean node")
+            walk(node[1])
+            for arm in node[2:]:
+                walk(arm)
+                tokens.append(capi.CG_QX_AND if node[0] == "and" else capi.CG_QX_OR)
+        else:
+            tokens.append(len(atoms))
+            atoms.append(tuple(node))
+
+    walk(where)
+    return atoms, tokens
+
+
 def make_desc(quals=(), group_cols=(), aggs=(), qual_pushdown=True, expected_groups=0, float_cols=()):
     d = CgScanDesc()
+    quals, tokens = flatten_where(quals)
+    if len(quals) > capi.CG_MAX_QUALS or len(tokens) > capi.CG_MAX_QEXPR:
+        raise capi.CitusGpuError(capi.CG_EUNSUPPORTED, "WHERE tree too large")
+    d.nqual_expr = len(tokens)
+    for i, t in enumerate(tokens):
+        d.qual_expr[i] = t
     d.nquals = len(quals)
     for i, (col, op, k) in enumerate(quals):
         d.quals[i].column = col

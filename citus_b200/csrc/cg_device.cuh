@@ -139,6 +139,42 @@ __device__ __forceinline__ bool qual_true(int64_t v, int op, int64_t k, bool isf
 	}
 }
 
+/*
+ * K3: the WHERE tree ([PG] ExecQual under ExecScan, columnar_customscan.c:1907-1913) under three-valued
+ * logic: an atom on a NULL input is not TRUE, AND/OR combine "is TRUE" bits (there is no NOT node: it is
+ * folded into the comparison operators), the row passes iff the root is TRUE.  Without a tree the atoms
+ * are an AND-list.
+ */
+template <int NCC>
+__device__ __forceinline__ bool eval_where(const KPlan &P, const int64_t (&v)[NCC], uint32_t nullmask)
+{
+	uint32_t truth = 0;
+#pragma unroll 1
+	for (int q = 0; q < P.nquals; q++)
+	{
+		int c = P.qcol[q];
+		bool isnull = (nullmask >> c) & 1u;
+		int64_t x = pick<NCC>(v, c);
+		bool t = P.isfloat[c] ? qual_true(x, P.qop[q], P.qk[q], true)
+							  : (((x >= P.qlo[q]) && (x <= P.qhi[q])) != (bool) P.qneg[q]);
+		truth |= (uint32_t) (t && !isnull) << q;
+	}
+	if (P.nqexpr == 0) return truth == (1u << P.nquals) - 1u;
+	uint32_t st = 0;
+#pragma unroll 1
+	for (int i = 0; i < P.nqexpr; i++)
+	{
+		int t = P.qexpr[i];
+		if (t >= 0) st = (st << 1) | ((truth >> t) & 1u);
+		else
+		{
+			uint32_t b = st & 1u, a = (st >> 1) & 1u;
+			st = ((st >> 2) << 1) | (t == CG_QX_AND ? (a & b) : (a | b));
+		}
+	}
+	return st & 1u;
+}
+
 /* home slot of a key in the open-addressing table: Fibonacci (multiply-shift) hashing, one
  * 64-bit multiply; hash_shift = 64 - log2(capacity).  Every kernel that touches a hash table
  * must use this one function. */

@@ -272,26 +272,46 @@ static int datum_cmp(int type_class, int64_t a, int64_t b)
  * on that column contradicts either half (backend/columnar/columnar_reader.c:1132-1187,
  * 1234-1260, 1358-1384).  A chunk without min/max (all NULL) is never skipped.
  */
+static bool atom_refuted(const CgSkipNode &node, int type_class, const CgQual &q)
+{
+	int64_t k = q.konst;
+	int cmin = datum_cmp(type_class, node.min_value, k);
+	int cmax = datum_cmp(type_class, node.max_value, k);
+	switch (q.op)
+	{
+		case CG_OP_LT: return cmin >= 0;
+		case CG_OP_LE: return cmin > 0;
+		case CG_OP_EQ: return cmin > 0 || cmax < 0;
+		case CG_OP_GE: return cmax < 0;
+		case CG_OP_GT: return cmax <= 0;
+		default: return false;   /* <> refutes nothing */
+	}
+}
+
+/* is the chunk's base constraint on column `col` refuted by the WHERE tree?  The implicit AND-list and an
+ * AND node are refuted when any arm is, an OR node when every arm is; an atom on another column is never
+ * refuted by this column's range (the reference tests one column's constraint at a time). */
 static bool chunk_refuted(const CgSkipNode &node, int type_class, int col, const CgScanDesc *d)
 {
 	if (!node.has_minmax) return false;
-	for (int q = 0; q < d->nquals; q++)
+	if (d->nqual_expr == 0)
 	{
-		if (d->quals[q].column != col) continue;
-		int64_t k = d->quals[q].konst;
-		int cmin = datum_cmp(type_class, node.min_value, k);
-		int cmax = datum_cmp(type_class, node.max_value, k);
-		switch (d->quals[q].op)
+		for (int q = 0; q < d->nquals; q++)
+			if (d->quals[q].column == col && atom_refuted(node, type_class, d->quals[q])) return true;
+		return false;
+	}
+	uint32_t st = 0;
+	for (int i = 0; i < d->nqual_expr; i++)
+	{
+		int t = d->qual_expr[i];
+		if (t >= 0) st = (st << 1) | (uint32_t) (d->quals[t].column == col && atom_refuted(node, type_class, d->quals[t]));
+		else
 		{
-			case CG_OP_LT: if (cmin >= 0) return true; break;
-			case CG_OP_LE: if (cmin > 0) return true; break;
-			case CG_OP_EQ: if (cmin > 0 || cmax < 0) return true; break;
-			case CG_OP_GE: if (cmax < 0) return true; break;
-			case CG_OP_GT: if (cmax <= 0) return true; break;
-			default: break;   /* <> refutes nothing */
+			uint32_t b = st & 1u, a = (st >> 1) & 1u;
+			st = ((st >> 2) << 1) | (t == CG_QX_AND ? (a | b) : (a & b));
 		}
 	}
-	return false;
+	return st & 1u;
 }
 
 static int stripe_chunk_mask(const CgStripe &s, const CgSkipNode *nodes, const CgColumnDesc *columns, int natts,
@@ -767,11 +787,22 @@ extern "C" uint64_t cg_shard_rows(const CgShard *sh) { return sh ? sh->rows : 0;
 /* ------------------------------------------------------------------------------ *
  *  Scan driver.
  * ------------------------------------------------------------------------------ */
+static int g_force_general = -1;
 static bool cg_force_general(void)
 {
-	static int v = -1;
-	if (v < 0) { const char *e = getenv("CG_FORCE_GENERAL_KERNEL"); v = (e && atoi(e)) ? 1 : 0; }
-	return v == 1;
+	if (g_force_general < 0) { const char *e = getenv("CG_FORCE_GENERAL_KERNEL"); g_force_general = (e && atoi(e)) ? 1 : 0; }
+	return g_force_general == 1;
+}
+
+/* run-time switches (the same ones the CG_* environment variables set at first use): which kernel family
+ * scans -- "jit" 0 = ahead-of-time kernels only, 1 = plan-specialised where no ahead-of-time specialisation
+ * applies (default), 2 = always; "force_general" 1 = the interpretive kernels for everything */
+extern "C" int cg_set_option(const char *name, int64_t value)
+{
+	if (!name) return cg_set_error(CG_EINVAL, "NULL option name");
+	if (strcmp(name, "jit") == 0) { cg_jit_set_level((int) value); return CG_OK; }
+	if (strcmp(name, "force_general") == 0) { g_force_general = value ? 1 : 0; return CG_OK; }
+	return cg_set_error(CG_EINVAL, "unknown option %s", name);
 }
 
 static int check_error_flags(CgPartial *p, unsigned long long flags)
@@ -837,10 +868,12 @@ extern "C" int cg_scan_shard(const CgShard *sh, const CgScanDesc *desc, CgPartia
 	CgShard *msh = const_cast<CgShard *>(sh);
 	std::vector<uint8_t> slots(plan.slot, plan.slot + plan.ncols);
 	bool same = msh->sel_valid && msh->sel_pushdown == desc->enable_qual_pushdown && msh->sel_nquals == desc->nquals &&
-				memcmp(msh->sel_quals, desc->quals, sizeof(CgQual) * desc->nquals) == 0 && msh->sel_slots == slots;
+				memcmp(msh->sel_quals, desc->quals, sizeof(CgQual) * desc->nquals) == 0 && msh->sel_slots == slots &&
+				msh->sel_nqexpr == desc->nqual_expr && memcmp(msh->sel_qexpr, desc->qual_expr, (size_t) desc->nqual_expr) == 0;
 	if (!same)
 	{
 		std::vector<uint32_t> fastl, slowl;
+		uint32_t nullmask = 0;
 		fastl.reserve(sh->nchunkgroups);
 		int64_t nfiltered = 0;
 		std::vector<uint8_t> mask;
@@ -858,7 +891,7 @@ extern "C" int cg_scan_shard(const CgShard *sh, const CgScanDesc *desc, CgPartia
 				for (int c = 0; c < plan.ncols; c++)
 				{
 					const DevChunkCol &d = sh->h_chunkcols[cg * ns + plan.slot[c]];
-					if (d.value_count != d.row_count) nulls = true;
+					if (d.value_count != d.row_count) { nulls = true; nullmask |= 1u << c; }
 				}
 				(nulls ? slowl : fastl).push_back((uint32_t) cg);
 			}
@@ -872,6 +905,9 @@ extern "C" int cg_scan_shard(const CgShard *sh, const CgScanDesc *desc, CgPartia
 		msh->sel_filtered = nfiltered;
 		msh->sel_pushdown = desc->enable_qual_pushdown;
 		msh->sel_nquals = desc->nquals;
+		msh->sel_nullmask = nullmask;
+		msh->sel_nqexpr = desc->nqual_expr;
+		memcpy(msh->sel_qexpr, desc->qual_expr, (size_t) desc->nqual_expr);
 		memcpy(msh->sel_quals, desc->quals, sizeof(CgQual) * desc->nquals);
 		msh->sel_slots = slots;
 		msh->sel_valid = true;
@@ -917,7 +953,7 @@ extern "C" int cg_scan_shard(const CgShard *sh, const CgScanDesc *desc, CgPartia
 			KPlan piece = plan;
 			piece.nselected = nfast;
 			bool launched = false, packed = false;
-			rc = cg_launch_scan_jit(ctx, piece, ctx->compute, &launched, &packed);
+			rc = cg_launch_scan_jit(ctx, piece, 0u, ctx->compute, &launched, &packed);
 			if (rc) return rc;
 			if (launched && packed)
 			{
@@ -931,12 +967,29 @@ extern "C" int cg_scan_shard(const CgShard *sh, const CgScanDesc *desc, CgPartia
 			nfast = 0;
 		if (nfast < plan.nselected)
 		{
-			/* chunk groups with NULLs (or everything, without the JIT): the interpretive kernels */
+			/* chunk groups with NULLs in a plan column: the plan-specialised kernel in its nullable form
+			 * (exists bitmap + rank directory addressing, columnar_reader.c:1506-1572); the interpretive
+			 * kernels only when the JIT is off or unavailable */
 			plan.selected = sh->d_selected + nfast;
 			plan.nselected -= nfast;
-			if (use_small) rc = cg_launch_scan_small(ctx, plan, all8, ctx->compute);
-			else rc = cg_launch_scan(ctx, plan, true, all8, ctx->compute);
-			if (rc) return rc;
+			bool launched = false, packed = false;
+			if (!cg_force_general())
+			{
+				rc = cg_launch_scan_jit(ctx, plan, sh->sel_nullmask ? sh->sel_nullmask : ~0u, ctx->compute, &launched, &packed);
+				if (rc) return rc;
+				if (launched && packed)
+				{
+					into->packed_dirty = true;
+					rc = after_packed_launch(ctx, into, true);
+					if (rc) return rc;
+				}
+			}
+			if (!launched)
+			{
+				if (use_small) rc = cg_launch_scan_small(ctx, plan, all8, ctx->compute);
+				else rc = cg_launch_scan(ctx, plan, true, all8, ctx->compute);
+				if (rc) return rc;
+			}
 		}
 		rc = cg_prof_mark(ctx, ctx->compute);
 		if (rc) return rc;
@@ -1239,7 +1292,17 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 		const bool use_small = cg_small_eligible(plan) && !cg_force_general();
 		const bool use_fast = !use_small && !sp.any_nulls && !cg_force_general() && cg_jit_level() < 2 &&
 							  cg_build_fast_plan(desc, plan, all8, &fast);
-		const bool try_jit = !use_fast && !sp.any_nulls && !cg_force_general();
+		const bool try_jit = !use_fast && !cg_force_general();
+		/* plan columns with NULLs somewhere in the planned chunk groups: the generated kernel takes the exists
+		 * bitmap + rank directory path for those (per chunk, uniformly), dense loads everywhere else */
+		uint32_t nullable = 0;
+		if (sp.any_nulls)
+			for (uint64_t g = 0; g < ncg; g++)
+				for (int c = 0; c < plan.ncols; c++)
+				{
+					const DevChunkCol &d = sp.cols[g * ns + plan.slot[c]];
+					if (d.value_count != d.row_count) nullable |= 1u << c;
+				}
 		if (stats) CG_CUDA(cudaEventRecord(ctx->ev_a, ctx->compute));
 		bool decode_done = false;          /* the DMA path may decode on a side stream before launch_block runs */
 		auto launch_block = [&](uint64_t cg0, uint64_t cg1, cudaEvent_t copied) -> int {
@@ -1264,7 +1327,7 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 				blk.selected = d_ids + cg0;
 				blk.nselected = (uint32_t) (cg1 - cg0);
 				bool packed = false;
-				r = cg_launch_scan_jit(ctx, blk, ctx->compute, &jitted, &packed);
+				r = cg_launch_scan_jit(ctx, blk, nullable, ctx->compute, &jitted, &packed);
 				if (r) return r;
 				if (jitted && packed) into->packed_dirty = true;
 			}

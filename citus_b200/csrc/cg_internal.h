@@ -127,7 +127,10 @@ struct CgShard
 	bool sel_valid = false;
 	int32_t sel_pushdown = 0, sel_nquals = 0;
 	CgQual sel_quals[CG_MAX_QUALS];
+	int32_t sel_nqexpr = 0;
+	int8_t sel_qexpr[CG_MAX_QEXPR];
 	int64_t sel_filtered = 0;
+	uint32_t sel_nullmask = 0;               /* plan columns that have NULLs in some chunk group of the second part */
 	/* the list is ordered [chunk groups without NULLs in the plan columns | the rest] */
 	std::vector<uint8_t> sel_slots;
 	uint32_t sel_nfast = 0;
@@ -216,6 +219,10 @@ struct KPlan
 	uint64_t *packed;
 	int32_t pack_shift;
 	int32_t pack_word;            /* accumulator word the packed sum belongs to */
+	/* WHERE tree in postfix form over the atoms above (0 tokens = AND of all atoms) */
+	int32_t nqexpr;
+	int8_t qexpr[CG_MAX_QEXPR];
+	int32_t pad_;
 };
 
 /* plan of the specialised kernel (cg_scan_fast.cu): column roles in fixed order
@@ -336,8 +343,11 @@ int cg_launch_merge(CgPartial *p, const int64_t *d_keys, const uint8_t *d_nulls,
 					int64_t nrows, cudaStream_t stream);
 
 /* cg_jit.cpp: plan-specialised kernels through NVRTC */
-int cg_jit_level(void);     /* CG_JIT: 0 = off, 1 = where no specialised ahead-of-time kernel applies (default), 2 = always */
-int cg_launch_scan_jit(CgContext *ctx, const KPlan &plan, cudaStream_t stream, bool *launched, bool *used_packed);
+int cg_jit_level(void);
+void cg_jit_set_level(int level);     /* CG_JIT: 0 = off, 1 = where no specialised ahead-of-time kernel applies (default), 2 = always */
+/* nullable: bit c set = plan column c may have NULLs in the chunk groups of this launch (the kernel then reads
+ * its exists bitmap + rank directory wherever a chunk's value_count differs from its row count) */
+int cg_launch_scan_jit(CgContext *ctx, const KPlan &plan, uint32_t nullable, cudaStream_t stream, bool *launched, bool *used_packed);
 
 /* cg_plan.cpp */
 int cg_partial_shape(CgPartial *p, const CgScanDesc *desc, const CgColumnDesc *columns, int32_t natts,

@@ -39,6 +39,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "cg_internal.h"
 
@@ -103,12 +104,13 @@ static bool load_drv()
 	return g_api.have_drv;
 }
 
+static int g_jit_level = -1;
 int cg_jit_level(void)
 {
-	static int level = -1;
-	if (level < 0) { const char *e = getenv("CG_JIT"); level = e ? atoi(e) : 1; }
-	return level;
+	if (g_jit_level < 0) { const char *e = getenv("CG_JIT"); g_jit_level = e ? atoi(e) : 1; }
+	return g_jit_level;
 }
+void cg_jit_set_level(int level) { g_jit_level = level < 0 ? 0 : level; }
 
 /* ------------------------------------------------------------------------------ *
  *  Code generation.
@@ -131,6 +133,7 @@ struct JitShape
 	size_t smem = 0;
 	bool packed = false;
 	int pack_agg = -1;
+	uint32_t nullable = 0;            /* plan columns read through exists bitmap + rank directory where a chunk has NULLs */
 };
 
 static void addf(std::string &s, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
@@ -147,8 +150,9 @@ static void addf(std::string &s, const char *fmt, ...)
 static bool agg_has_value(const KAgg &g) { return g.kind != CG_AGG_COUNT_STAR && g.kind != CG_AGG_COUNT; }
 static bool agg_two_limbs(const KAgg &g) { return g.kind == CG_AGG_SUM && !g.is_float && g.nlimbs == 2; }
 
-static void choose_shape(const KPlan &plan, JitShape *sh)
+static void choose_shape(const KPlan &plan, uint32_t nullable, JitShape *sh)
 {
+	sh->nullable = plan.ncols >= 32 ? nullable : (nullable & ((1u << plan.ncols) - 1u));
 	sh->kind = plan.mode == CG_MODE_GLOBAL ? JK_GLOBAL : JK_TABLE;
 	/* two rows per thread and step (one 16-byte load per 8-byte column), two steps loaded before any is
 	 * consumed: the best of the (R, U) grid on every probed shape (profiles/r01_probe_jit.txt) */
@@ -251,9 +255,10 @@ static void gen_prelude(std::string &s)
 		 "  int32_t ngroup; uint8_t gcol[%d]; int32_t naggs; KAgg aggs[%d];\n"
 		 "  int32_t mode; int32_t nwords; int32_t stride; uint64_t *table; int64_t *hkeys; uint64_t capacity; int32_t hash_shift;\n"
 		 "  int64_t key_min; int64_t key_min1; uint64_t range1; uint8_t wordop[%d]; unsigned long long *stats;\n"
-		 "  int8_t hot_of_word[%d]; int32_t nhot; uint64_t *packed; int32_t pack_shift; int32_t pack_word; };\n",
+		 "  int8_t hot_of_word[%d]; int32_t nhot; uint64_t *packed; int32_t pack_shift; int32_t pack_word;\n"
+		 "  int32_t nqexpr; int8_t qexpr[%d]; int32_t pad_; };\n",
 		 CG_KMAX_COLS, CG_KMAX_COLS, CG_KMAX_COLS, CG_MAX_QUALS, CG_MAX_QUALS, CG_MAX_QUALS, CG_MAX_QUALS, CG_MAX_QUALS, CG_MAX_QUALS,
-		 CG_MAX_GROUP_COLS, CG_MAX_AGGS, CG_KMAX_WORDS, CG_KMAX_WORDS);
+		 CG_MAX_GROUP_COLS, CG_MAX_AGGS, CG_KMAX_WORDS, CG_KMAX_WORDS, CG_MAX_QEXPR);
 	/* the text above must describe the host's structs exactly */
 	addf(s, "static_assert(sizeof(DevChunkCol) == %zu, \"DevChunkCol\");\n", sizeof(DevChunkCol));
 	addf(s, "static_assert(sizeof(KAgg) == %zu, \"KAgg\");\n", sizeof(KAgg));
@@ -265,6 +270,7 @@ static void gen_prelude(std::string &s)
 		"__device__ __forceinline__ uint64_t ld8(const void *p) { uint64_t a; asm(\"ld.global.nc.L1::no_allocate.u64 %0, [%1];\" : \"=l\"(a) : \"l\"(p)); return a; }\n"
 		"__device__ __forceinline__ uint64_t ld4(const void *p) { uint32_t a; asm(\"ld.global.nc.L1::no_allocate.u32 %0, [%1];\" : \"=r\"(a) : \"l\"(p)); return a; }\n"
 		"__device__ __forceinline__ uint64_t ld2(const void *p) { uint16_t a; asm(\"ld.global.nc.L1::no_allocate.u16 %0, [%1];\" : \"=h\"(a) : \"l\"(p)); return a; }\n"
+		"__device__ __forceinline__ uint64_t ld1(const void *p) { uint32_t a; asm(\"ld.global.nc.L1::no_allocate.u8 %0, [%1];\" : \"=r\"(a) : \"l\"(p)); return a; }\n"
 		"__device__ __forceinline__ void red_add(uint64_t *p, uint64_t v) { asm volatile(\"red.global.add.u64 [%0], %1;\" :: \"l\"(p), \"l\"(v) : \"memory\"); }\n"
 		"__device__ __forceinline__ int64_t smin64(int64_t a, int64_t b) { return a < b ? a : b; }\n"
 		"__device__ __forceinline__ int64_t smax64(int64_t a, int64_t b) { return a > b ? a : b; }\n"
@@ -287,14 +293,23 @@ static void gen_prelude(std::string &s)
 		"  raise_flag(P.stats, 1ull); return ~0ull; }\n";
 }
 
+static bool col_nullable(const JitShape &sh, int c) { return (sh.nullable >> c) & 1u; }
+
 /* value of plan column c, row j of step u, as an int64_t expression (widened like fetch_att) */
 static std::string col_value(const KPlan &plan, const JitShape &sh, int c, int u, int j)
 {
 	char raw[64];
 	int len = plan.len[c];
-	int word = j * len / 8, shift = (j * len % 8) * 8;
-	if (sh.R * len < 8) { word = 0; shift = j * len * 8; }
-	snprintf(raw, sizeof raw, "w%d_%d_%d", c, u, word);
+	int shift = 0;
+	if (col_nullable(sh, c))
+		snprintf(raw, sizeof raw, "x%d_%d_%d", c, u, j);     /* one zero-extended datum per row */
+	else
+	{
+		int word = j * len / 8;
+		shift = (j * len % 8) * 8;
+		if (sh.R * len < 8) { word = 0; shift = j * len * 8; }
+		snprintf(raw, sizeof raw, "w%d_%d_%d", c, u, word);
+	}
 	std::string x = raw;
 	char buf[256];
 	switch (len)
@@ -311,14 +326,34 @@ static std::string col_value(const KPlan &plan, const JitShape &sh, int c, int u
 
 static void gen_loads(std::string &s, const KPlan &plan, const JitShape &sh, int u)
 {
+	const char *T = "\t\t\t\t\t";
 	for (int c = 0; c < plan.ncols; c++)
 	{
-		int bytes = sh.R * plan.len[c];
+		const int len = plan.len[c];
+		if (col_nullable(sh, c))
+		{
+			/* K1 for a chunk with NULLs (DeserializeBoolArray / DeserializeDatumArray, columnar_reader.c:1506-1572):
+			 * NULL rows occupy no bytes of the value stream, so row -> value index = rank directory entry of the
+			 * row's 64-row block + popcount of the exists bits below it.  r is a multiple of R, so the R rows of
+			 * this step share one bitmap word; bits past the last row are zero padding. */
+			addf(s, "%sif (n%d) {\n", T, c);
+			addf(s, "%s\tconst uint64_t bw = ld8(b%d + (r >> 6));\n%s\tconst uint32_t sh = r & 63u;\n", T, c, T);
+			addf(s, "%s\tuint32_t vi = __ldg(k%d + (r >> 6)) + (uint32_t) __popcll(bw & ((1ull << sh) - 1ull));\n", T, c);
+			addf(s, "%s\te%d_%d = (uint32_t) (bw >> sh) & %uu;\n", T, c, u, (1u << sh.R) - 1u);
+			for (int j = 0; j < sh.R; j++)
+				addf(s, "%s\tif (e%d_%d & %uu) { x%d_%d_%d = ld%d(p%d + (uint64_t) vi * %d); vi++; }\n", T, c, u, 1u << j, c, u, j, len, c, len);
+			addf(s, "%s} else {\n%s\te%d_%d = %uu;\n", T, T, c, u, (1u << sh.R) - 1u);
+			for (int j = 0; j < sh.R; j++)
+				addf(s, "%s\tif (r + %d < rows) x%d_%d_%d = ld%d(p%d + (uint64_t) (r + %d) * %d);\n", T, j, c, u, j, len, c, j, len);
+			addf(s, "%s}\n", T);
+			continue;
+		}
+		int bytes = sh.R * len;
 		if (bytes >= 16)
 			for (int k = 0; k < bytes / 16; k++)
-				addf(s, "\t\t\t\t\tld16(p%d + (uint64_t) r * %d + %d, w%d_%d_%d, w%d_%d_%d);\n", c, plan.len[c], 16 * k, c, u, 2 * k, c, u, 2 * k + 1);
+				addf(s, "%sld16(p%d + (uint64_t) r * %d + %d, w%d_%d_%d, w%d_%d_%d);\n", T, c, len, 16 * k, c, u, 2 * k, c, u, 2 * k + 1);
 		else
-			addf(s, "\t\t\t\t\tw%d_%d_0 = ld%d(p%d + (uint64_t) r * %d);\n", c, u, bytes, c, plan.len[c]);
+			addf(s, "%sw%d_%d_0 = ld%d(p%d + (uint64_t) r * %d);\n", T, c, u, bytes, c, len);
 	}
 }
 
@@ -346,62 +381,180 @@ static std::string term_expr(const KAgg &g, int a)
 	return e;
 }
 
-/* the per-row block: extraction, WHERE list, group slot, transition functions */
+/* "an input of aggregate a is NULL" as an expression, or "" when no factor column is nullable */
+static std::string agg_null_expr(const KAgg &g, const JitShape &sh)
+{
+	std::string e;
+	for (int f = 0; f < g.nfactors; f++)
+	{
+		int c = g.pcol[f];
+		if (!col_nullable(sh, c)) continue;
+		bool dup = false;
+		for (int f2 = 0; f2 < f; f2++) if (g.pcol[f2] == c) dup = true;
+		if (dup) continue;
+		char buf[32];
+		snprintf(buf, sizeof buf, "z%d", c);
+		if (!e.empty()) e += " || ";
+		e += buf;
+	}
+	return e;
+}
+
+/* the WHERE tree over the atoms t<q> (an AND-list without a tree) */
+static std::string where_expr(const KPlan &plan)
+{
+	char buf[32];
+	if (plan.nquals == 0) return "true";
+	if (plan.nqexpr == 0)
+	{
+		std::string e;
+		for (int q = 0; q < plan.nquals; q++) { snprintf(buf, sizeof buf, "%st%d", q ? " && " : "", q); e += buf; }
+		return e;
+	}
+	std::vector<std::string> st;
+	for (int i = 0; i < plan.nqexpr; i++)
+	{
+		int t = plan.qexpr[i];
+		if (t >= 0) { snprintf(buf, sizeof buf, "t%d", t); st.push_back(buf); }
+		else
+		{
+			std::string b = st.back(); st.pop_back();
+			std::string a = st.back(); st.pop_back();
+			st.push_back("(" + a + (t == CG_QX_AND ? " && " : " || ") + b + ")");
+		}
+	}
+	return st.back();
+}
+
+/* updates of a group entry in global memory (`e` = its word pointer): the TABLE kind, and the NULL-key group of
+ * the SMALL kind.  with_packed: count(*) and the packed sum share one reduction on P.packed[slot]. */
+static void gen_table_updates(std::string &s, const KPlan &plan, const JitShape &sh, const char *C, bool with_packed,
+							  const std::vector<std::string> &an, const std::vector<std::string> &w0)
+{
+	if (with_packed)
+	{
+		const int pa = sh.pack_agg;
+		if (an[pa].empty())
+			addf(s, "%sred_add(P.packed + slot, ((uint64_t) it%d << P.pack_shift) + 1ull);\n", C, pa);
+		else
+			addf(s, "%sred_add(P.packed + slot, (an%d ? 0ull : ((uint64_t) it%d << P.pack_shift)) + 1ull);\n%sif (an%d) red_add(e + %d, 1ull);\n",
+				 C, pa, pa, C, pa, plan.aggs[pa].nullword);
+		addf(s, "%sg_rows++;\n", C);
+	}
+	else
+		addf(s, "%sred_add(e, 1ull);\n", C);
+	for (int a = 0; a < plan.naggs; a++)
+	{
+		const KAgg &g = plan.aggs[a];
+		if (g.kind == CG_AGG_COUNT_STAR || (with_packed && a == sh.pack_agg)) continue;
+		if (!an[a].empty()) addf(s, "%sif (an%d) red_add(e + %d, 1ull);\n", C, a, g.nullword);
+		if (!agg_has_value(g)) continue;
+		char p[32];
+		snprintf(p, sizeof p, "e + %d", g.word0);
+		std::string guard = an[a].empty() ? "" : ("if (!an" + std::to_string(a) + ") ");
+		if (agg_two_limbs(g))
+			addf(s, "%s%s{ %s red_add(e + %d, (uint64_t) (it%d >> 32)); }\n", C, guard.c_str(),
+				 op_apply_global(plan.wordop[g.word0], p, w0[a]).c_str(), g.word0 + 1, a);
+		else
+			addf(s, "%s%s{ %s }\n", C, guard.c_str(), op_apply_global(plan.wordop[g.word0], p, w0[a]).c_str());
+	}
+}
+
+/* the per-row block: extraction, WHERE tree, group slot, transition functions */
 static void gen_row(std::string &s, const KPlan &plan, const JitShape &sh, int u, int j)
 {
 	const char *T = "\t\t\t\t\t\t";
 	addf(s, "\t\t\t\t\tif (r + %d < rows) {\n", j);
 	for (int c = 0; c < plan.ncols; c++)
+	{
 		addf(s, "%sconst int64_t v%d = %s;\n", T, c, col_value(plan, sh, c, u, j).c_str());
-	/* K3: the WHERE list (no NULLs here, so two-valued) */
-	s += T; s += "bool pass = true;\n";
+		if (col_nullable(sh, c)) addf(s, "%sconst bool z%d = !((e%d_%d >> %d) & 1u);\n", T, c, c, u, j);
+	}
+	/* K3: the WHERE tree; an atom on a NULL input is not TRUE (three-valued logic) */
 	for (int q = 0; q < plan.nquals; q++)
 	{
 		int c = plan.qcol[q];
+		char nn[32] = "";
+		if (col_nullable(sh, c)) snprintf(nn, sizeof nn, "!z%d && ", c);
 		if (plan.isfloat[c])
 		{
 			const char *ops[] = {"<", "<=", "==", ">=", ">", "!="};
-			addf(s, "%spass = pass && (fcmp(v%d, P.qk[%d]) %s 0);\n", T, c, q, ops[plan.qop[q]]);
+			addf(s, "%sconst bool t%d = %s(fcmp(v%d, P.qk[%d]) %s 0);\n", T, q, nn, c, q, ops[plan.qop[q]]);
 		}
 		else if (plan.qneg[q])
-			addf(s, "%spass = pass && !((v%d >= P.qlo[%d]) && (v%d <= P.qhi[%d]));\n", T, c, q, c, q);
+			addf(s, "%sconst bool t%d = %s!((v%d >= P.qlo[%d]) && (v%d <= P.qhi[%d]));\n", T, q, nn, c, q, c, q);
 		else
-			addf(s, "%spass = pass && (v%d >= P.qlo[%d]) && (v%d <= P.qhi[%d]);\n", T, c, q, c, q);
+			addf(s, "%sconst bool t%d = %s(v%d >= P.qlo[%d]) && (v%d <= P.qhi[%d]);\n", T, q, nn, c, q, c, q);
 	}
+	addf(s, "%sconst bool pass = %s;\n", T, where_expr(plan).c_str());
 	addf(s, "%sif (!pass) removed++;\n%selse {\n", T, T);
 	const char *B = "\t\t\t\t\t\t\t";
-	/* group slot */
+	/* group slot; a NULL key is its own group (the entry behind the addressable ones) */
+	std::string zkey;
+	if (plan.mode != CG_MODE_GLOBAL)
+	{
+		if (plan.ngroup == 1) { if (col_nullable(sh, plan.gcol[0])) zkey = "z" + std::to_string(plan.gcol[0]); }
+		else
+		{
+			if (col_nullable(sh, plan.gcol[0])) zkey = "z" + std::to_string(plan.gcol[0]);
+			if (col_nullable(sh, plan.gcol[1])) zkey += (zkey.empty() ? "z" : " || z") + std::to_string(plan.gcol[1]);
+		}
+	}
 	if (plan.mode == CG_MODE_DENSE)
 	{
 		if (plan.ngroup == 1)
-			addf(s, "%suint64_t slot = (uint64_t) v%d - (uint64_t) P.key_min;\n%sbool ok = slot < P.capacity;\n", B, plan.gcol[0], B);
+		{
+			if (zkey.empty())
+				addf(s, "%suint64_t slot = (uint64_t) v%d - (uint64_t) P.key_min;\n%sbool ok = slot < P.capacity;\n", B, plan.gcol[0], B);
+			else
+				addf(s, "%suint64_t slot = %s ? P.capacity : (uint64_t) v%d - (uint64_t) P.key_min;\n%sbool ok = %s || slot < P.capacity;\n", B,
+					 zkey.c_str(), plan.gcol[0], B, zkey.c_str());
+			addf(s, "%sif (!ok) raise_flag(P.stats, %lluull);\n", B, (unsigned long long) CG_ERRFLAG_KEY_RANGE);
+		}
 		else
+		{
 			addf(s,
 				 "%sconst uint64_t ka = (uint64_t) (int64_t) (int32_t) v%d - (uint64_t) P.key_min, kb = (uint64_t) (int64_t) (int32_t) v%d - (uint64_t) P.key_min1;\n"
 				 "%suint64_t slot = ka * P.range1 + kb;\n%sbool ok = kb < P.range1 && slot < P.capacity;\n",
 				 B, plan.gcol[0], plan.gcol[1], B, B);
-		addf(s, "%sif (!ok) raise_flag(P.stats, %lluull);\n", B, (unsigned long long) CG_ERRFLAG_KEY_RANGE);
+			if (zkey.empty())
+				addf(s, "%sif (!ok) raise_flag(P.stats, %lluull);\n", B, (unsigned long long) CG_ERRFLAG_KEY_RANGE);
+			else
+				addf(s, "%sif (%s) { raise_flag(P.stats, %lluull); ok = false; }\n%selse if (!ok) raise_flag(P.stats, %lluull);\n", B, zkey.c_str(),
+					 (unsigned long long) CG_ERRFLAG_NULL_MULTIKEY, B, (unsigned long long) CG_ERRFLAG_KEY_RANGE);
+		}
 	}
 	else if (plan.mode == CG_MODE_HASH)
 	{
 		if (plan.ngroup == 1) addf(s, "%sconst int64_t key = v%d;\n", B, plan.gcol[0]);
 		else addf(s, "%sconst int64_t key = (int64_t) ((uint64_t) (uint32_t) v%d | ((uint64_t) (uint32_t) v%d << 32));\n", B, plan.gcol[0], plan.gcol[1]);
+		addf(s, "%suint64_t slot;\n", B);
+		if (!zkey.empty())
+		{
+			if (plan.ngroup == 1) addf(s, "%sif (%s) slot = P.capacity;\n%selse ", B, zkey.c_str(), B);
+			else addf(s, "%sif (%s) { raise_flag(P.stats, %lluull); slot = ~0ull; }\n%selse ", B, zkey.c_str(),
+					  (unsigned long long) CG_ERRFLAG_NULL_MULTIKEY, B);
+		}
+		else s += B;
 		addf(s,
-			 "%suint64_t slot;\n"
-			 "%sif (key == EMPTY_KEY) slot = P.capacity + 1;\n"
+			 "if (key == EMPTY_KEY) slot = P.capacity + 1;\n"
 			 "%selse { uint64_t h = ((uint64_t) key * 0x9E3779B97F4A7C15ull) >> P.hash_shift;\n"
 			 "%s  long long cur = (long long) __ldcg((unsigned long long *) (P.hkeys + h));\n"
 			 "%s  slot = (cur == key) ? h : hash_slot_slow(P, key, h); }\n"
-			 "%sbool ok = slot != ~0ull;\n", B, B, B, B, B, B);
+			 "%sbool ok = slot != ~0ull;\n", B, B, B, B);
 	}
 	else
 		addf(s, "%sconst bool ok = true;\n", B);
 	addf(s, "%sif (ok) {\n", B);
 	const char *C = "\t\t\t\t\t\t\t\t";
-	/* terms */
+	/* NULL-input flags and terms */
+	std::vector<std::string> an(plan.naggs), w0v(plan.naggs);
 	for (int a = 0; a < plan.naggs; a++)
 	{
 		const KAgg &g = plan.aggs[a];
+		if (g.kind == CG_AGG_COUNT_STAR) continue;
+		an[a] = agg_null_expr(g, sh);
+		if (!an[a].empty()) addf(s, "%sconst bool an%d = %s;\n", C, a, an[a].c_str());
 		if (!agg_has_value(g)) continue;
 		std::string e = term_expr(g, a);
 		if (g.is_float) addf(s, "%sconst double ft%d = %s;\n", C, a, e.c_str());
@@ -409,13 +562,10 @@ static void gen_row(std::string &s, const KPlan &plan, const JitShape &sh, int u
 		{
 			addf(s, "%sconst int64_t it%d = %s;\n", C, a, e.c_str());
 			if (g.kind == CG_AGG_SUM && g.nlimbs == 1)
-				addf(s, "%sif (it%d > P.aggs[%d].bound || it%d < -P.aggs[%d].bound) raise_flag(P.stats, %lluull);\n", C, a, a, a, a,
-					 (unsigned long long) CG_ERRFLAG_SUM_BOUND);
+				addf(s, "%sif (%s(it%d > P.aggs[%d].bound || it%d < -P.aggs[%d].bound)) raise_flag(P.stats, %lluull);\n", C,
+					 an[a].empty() ? "" : ("!an" + std::to_string(a) + " && ").c_str(), a, a, a, a, (unsigned long long) CG_ERRFLAG_SUM_BOUND);
 		}
-	}
-	/* the word-0 value an aggregate contributes */
-	auto w0 = [&](int a) -> std::string {
-		const KAgg &g = plan.aggs[a];
+		/* the word-0 value the aggregate contributes */
 		char buf[128];
 		if (g.kind == CG_AGG_SUM)
 		{
@@ -425,57 +575,68 @@ static void gen_row(std::string &s, const KPlan &plan, const JitShape &sh, int u
 		}
 		else if (g.is_float) snprintf(buf, sizeof buf, "f8_ordered(__double_as_longlong(ft%d))", a);
 		else snprintf(buf, sizeof buf, "(uint64_t) it%d", a);
-		return buf;
-	};
+		w0v[a] = buf;
+	}
 	if (sh.kind == JK_GLOBAL)
 	{
 		addf(s, "%sg_rows++;\n", C);
 		for (int a = 0; a < plan.naggs; a++)
 		{
 			const KAgg &g = plan.aggs[a];
+			if (g.kind == CG_AGG_COUNT_STAR) continue;
+			if (!an[a].empty()) addf(s, "%sif (an%d) g_n%d++;\n", C, a, a);
 			if (!agg_has_value(g)) continue;
 			char acc[32];
 			snprintf(acc, sizeof acc, "g_a%d_0", a);
-			addf(s, "%s%s = %s;\n", C, acc, op_combine(plan.wordop[g.word0], acc, w0(a)).c_str());
-			if (agg_two_limbs(g)) addf(s, "%sg_a%d_1 += (uint64_t) (it%d >> 32);\n", C, a, a);
+			std::string guard = an[a].empty() ? "" : ("if (!an" + std::to_string(a) + ") ");
+			if (agg_two_limbs(g))
+				addf(s, "%s%s{ %s = %s; g_a%d_1 += (uint64_t) (it%d >> 32); }\n", C, guard.c_str(), acc,
+					 op_combine(plan.wordop[g.word0], acc, w0v[a]).c_str(), a, a);
+			else
+				addf(s, "%s%s%s = %s;\n", C, guard.c_str(), acc, op_combine(plan.wordop[g.word0], acc, w0v[a]).c_str());
 		}
 	}
 	else if (sh.kind == JK_SMALL)
 	{
-		addf(s, "%suint64_t *e = mine + (uint32_t) slot * %du;\n%se[0] += 1ull;\n", C, sh.nhot * JIT_THREADS, C);
+		const char *D = C;
+		std::string inner = C;
+		if (!zkey.empty())
+		{
+			/* the NULL group has no shared-memory cells: (rare) global reductions on its table entry */
+			addf(s, "%sif (%s) {\n%s\tuint64_t *e = P.table + P.capacity * %dull;\n", C, zkey.c_str(), C, plan.stride);
+			std::string CC = std::string(C) + "\t";
+			gen_table_updates(s, plan, sh, CC.c_str(), false, an, w0v);
+			addf(s, "%s} else {\n", C);
+			inner += "\t";
+			D = inner.c_str();
+		}
+		addf(s, "%suint64_t *e = mine + (uint32_t) slot * %du;\n%se[0] += 1ull;\n", D, sh.nhot * JIT_THREADS, D);
 		for (int a = 0; a < plan.naggs; a++)
 		{
 			const KAgg &g = plan.aggs[a];
+			if (g.kind == CG_AGG_COUNT_STAR) continue;
+			/* NULL-input counters stay on global reductions (rare) */
+			if (!an[a].empty()) addf(s, "%sif (an%d) red_add(P.table + slot * %dull + %d, 1ull);\n", D, a, plan.stride, g.nullword);
 			if (!agg_has_value(g)) continue;
 			char cell[48];
 			snprintf(cell, sizeof cell, "e[%d]", sh.hot0[a] * JIT_THREADS);
+			std::string guard = an[a].empty() ? "" : ("if (!an" + std::to_string(a) + ") ");
 			if (g.kind == CG_AGG_SUM && !g.is_float)
 			{
-				if (sh.lane1[a]) addf(s, "%s%s += (uint64_t) it%d;\n", C, cell, a);
+				if (sh.lane1[a]) addf(s, "%s%s%s += (uint64_t) it%d;\n", D, guard.c_str(), cell, a);
 				else
-					addf(s, "%s%s += (uint64_t) (uint32_t) it%d;\n%se[%d] += (uint64_t) (it%d >> 32);\n", C, cell, a, C,
+					addf(s, "%s%s{ %s += (uint64_t) (uint32_t) it%d; e[%d] += (uint64_t) (it%d >> 32); }\n", D, guard.c_str(), cell, a,
 						 (sh.hot0[a] + 1) * JIT_THREADS, a);
 			}
 			else
-				addf(s, "%s%s = %s;\n", C, cell, op_combine(plan.wordop[g.word0], cell, w0(a)).c_str());
+				addf(s, "%s%s%s = %s;\n", D, guard.c_str(), cell, op_combine(plan.wordop[g.word0], cell, w0v[a]).c_str());
 		}
+		if (!zkey.empty()) addf(s, "%s}\n", C);
 	}
 	else
 	{
 		addf(s, "%suint64_t *e = P.table + slot * %dull;\n", C, plan.stride);
-		if (sh.packed)
-			addf(s, "%sred_add(P.packed + slot, ((uint64_t) it%d << P.pack_shift) + 1ull);\n%sg_rows++;\n", C, sh.pack_agg, C);
-		else
-			addf(s, "%sred_add(e, 1ull);\n", C);
-		for (int a = 0; a < plan.naggs; a++)
-		{
-			const KAgg &g = plan.aggs[a];
-			if (!agg_has_value(g) || (sh.packed && a == sh.pack_agg)) continue;
-			char p[32];
-			snprintf(p, sizeof p, "e + %d", g.word0);
-			addf(s, "%s%s\n", C, op_apply_global(plan.wordop[g.word0], p, w0(a)).c_str());
-			if (agg_two_limbs(g)) addf(s, "%sred_add(e + %d, (uint64_t) (it%d >> 32));\n", C, g.word0 + 1, a);
-		}
+		gen_table_updates(s, plan, sh, C, sh.packed, an, w0v);
 	}
 	addf(s, "%s}\n%s}\n\t\t\t\t\t}\n", B, T);
 }
@@ -491,6 +652,7 @@ static std::string gen_source(const KPlan &plan, const JitShape &sh)
 		for (int a = 0; a < plan.naggs; a++)
 		{
 			const KAgg &g = plan.aggs[a];
+			if (g.kind != CG_AGG_COUNT_STAR && !agg_null_expr(g, sh).empty()) addf(s, "\tuint64_t g_n%d = 0;\n", a);
 			if (!agg_has_value(g)) continue;
 			addf(s, "\tuint64_t g_a%d_0 = %s, g_a%d_1 = 0;\n", a, op_identity(plan.wordop[g.word0]), a);
 		}
@@ -512,7 +674,14 @@ static std::string gen_source(const KPlan &plan, const JitShape &sh)
 	addf(s, "\t\tconst DevChunkCol *cc = P.chunkcols + (uint64_t) P.selected[ci] * %dull;\n", plan.nstaged);
 	s += "\t\tconst uint32_t rows = __ldg(&cc[0].row_count);\n";
 	for (int c = 0; c < plan.ncols; c++)
+	{
 		addf(s, "\t\tconst uint8_t *p%d = P.arena + __ldg(&cc[%d].values_off);\n", c, plan.slot[c]);
+		if (col_nullable(sh, c))
+			addf(s, "\t\tconst uint64_t *b%d = (const uint64_t *) (P.arena + __ldg(&cc[%d].exists_off));\n"
+					"\t\tconst uint32_t *k%d = (const uint32_t *) (P.arena + __ldg(&cc[%d].rank_off));\n"
+					"\t\tconst bool n%d = __ldg(&cc[%d].value_count) != rows;\n",
+				 c, plan.slot[c], c, plan.slot[c], c, plan.slot[c]);
+	}
 	s += "\t\tscanned += (tid == 0) ? rows : 0;\n";
 	if (plan.ncols == 0)
 	{
@@ -525,6 +694,13 @@ static std::string gen_source(const KPlan &plan, const JitShape &sh)
 		for (int u = 0; u < sh.U; u++)
 			for (int c = 0; c < plan.ncols; c++)
 			{
+				if (col_nullable(sh, c))
+				{
+					s += "\t\t\tuint64_t ";
+					for (int k = 0; k < sh.R; k++) addf(s, "%sx%d_%d_%d = 0", k ? ", " : "", c, u, k);
+					addf(s, "; uint32_t e%d_%d = 0;\n", c, u);
+					continue;
+				}
 				int nw = sh.R * plan.len[c] / 8;
 				if (nw < 1) nw = 1;
 				s += "\t\t\tuint64_t ";
@@ -557,6 +733,8 @@ static std::string gen_source(const KPlan &plan, const JitShape &sh)
 		for (int a = 0; a < plan.naggs; a++)
 		{
 			const KAgg &g = plan.aggs[a];
+			if (g.kind != CG_AGG_COUNT_STAR && !agg_null_expr(g, sh).empty())
+				addf(s, "\t{ uint64_t n = wsum(g_n%d); if ((tid & 31) == 0 && n) red_add(P.table + %d, n); }\n", a, g.nullword);
 			if (!agg_has_value(g)) continue;
 			int op = plan.wordop[g.word0];
 			addf(s, "\t{ uint64_t x = g_a%d_0;\n\t  for (int o = 16; o > 0; o >>= 1) { uint64_t y = __shfl_xor_sync(0xffffffffu, x, o); x = %s; }\n", a,
@@ -658,10 +836,10 @@ static int compile_source(const std::string &src, std::string *cubin)
 }
 
 /* source of the kernel a plan would get (tests, EXPLAIN-style inspection) */
-int cg_jit_source_for(const KPlan &plan, std::string *src, int *kind)
+int cg_jit_source_for(const KPlan &plan, uint32_t nullable, std::string *src, int *kind)
 {
 	JitShape sh;
-	choose_shape(plan, &sh);
+	choose_shape(plan, nullable, &sh);
 	*src = gen_source(plan, sh);
 	if (kind) *kind = sh.kind;
 	return CG_OK;
@@ -672,14 +850,14 @@ int cg_jit_source_for(const KPlan &plan, std::string *src, int *kind)
  * (and CG_OK) when the JIT is unavailable -- the caller then uses its ahead-of-time kernels.
  * *used_packed tells the caller that packed words were written.
  */
-int cg_launch_scan_jit(CgContext *ctx, const KPlan &plan, cudaStream_t stream, bool *launched, bool *used_packed)
+int cg_launch_scan_jit(CgContext *ctx, const KPlan &plan, uint32_t nullable, cudaStream_t stream, bool *launched, bool *used_packed)
 {
 	*launched = false;
 	*used_packed = false;
 	if (cg_jit_level() <= 0 || plan.nselected == 0) return CG_OK;
 	if (!load_rtc() || !load_drv()) return CG_OK;
 	JitShape sh;
-	choose_shape(plan, &sh);
+	choose_shape(plan, nullable, &sh);
 	std::string src = gen_source(plan, sh);
 	/* one compilation per distinct source, also when several host threads scan at once */
 	std::unique_lock<std::mutex> lock(g_cache_mutex);
@@ -754,23 +932,42 @@ extern "C" uint64_t cg_jit_compiles(void) { return g_jit_compiles; }
  * the CPU-side check that every plan form produces valid sm_100a code.  kind: 0 plain
  * aggregate, 1 shared-memory cells, 2 global table.  source/source_len may be NULL/0.
  */
-extern "C" int cg_jit_compile_check(const CgScanDesc *desc, const CgColumnDesc *columns, int32_t natts, int64_t key_min,
-									int64_t key_max, int64_t max_rows, int32_t *kind, char *source, size_t source_len)
+extern "C" int cg_jit_compile_check_nullable(const CgScanDesc *desc, const CgColumnDesc *columns, int32_t natts, int64_t key_min,
+											 int64_t key_max, int64_t max_rows, uint32_t nullable_atts, int32_t *kind, char *source,
+											 size_t source_len)
 {
 	if (!desc || !columns) return cg_set_error(CG_EINVAL, "NULL argument");
 	CgPartial part;
 	int rc = cg_partial_shape(&part, desc, columns, natts, key_min, key_max, max_rows);
 	if (rc) return rc;
+	/* packing as cg_partial_create would choose it, so that the packed form of the generated code is checked too */
+	for (int a = 0; a < desc->naggs && !part.d_packed && (part.mode == CG_MODE_DENSE || part.mode == CG_MODE_HASH); a++)
+	{
+		const KAgg &k = part.aggs[a];
+		if (k.kind != CG_AGG_SUM || k.is_float || k.nlimbs != 1 || k.bound <= 0) continue;
+		part.d_packed = (uint64_t *) 16; part.pack_shift = 16; part.pack_word = k.word0; part.packing_enabled = true;
+	}
 	KPlan plan;
 	bool all8 = false;
 	rc = cg_build_plan(desc, columns, natts, nullptr, &part, &plan, &all8);
+	part.d_packed = nullptr;
 	if (rc) return rc;
 	plan.nstaged = natts;
+	/* attribute mask -> plan-column mask */
+	uint32_t nullable = 0;
+	for (int c = 0; c < plan.ncols; c++)
+		if (plan.slot[c] < 32 && ((nullable_atts >> plan.slot[c]) & 1u)) nullable |= 1u << c;
 	std::string src;
 	int k = 0;
-	cg_jit_source_for(plan, &src, &k);
+	cg_jit_source_for(plan, nullable, &src, &k);
 	if (kind) *kind = k;
 	if (source && source_len) { strncpy(source, src.c_str(), source_len - 1); source[source_len - 1] = '\0'; }
 	std::string cubin;
 	return compile_source(src, &cubin);
+}
+
+extern "C" int cg_jit_compile_check(const CgScanDesc *desc, const CgColumnDesc *columns, int32_t natts, int64_t key_min,
+									int64_t key_max, int64_t max_rows, int32_t *kind, char *source, size_t source_len)
+{
+	return cg_jit_compile_check_nullable(desc, columns, natts, key_min, key_max, max_rows, 0u, kind, source, source_len);
 }

@@ -50,6 +50,20 @@ static int validate_desc(const CgScanDesc *d, const CgColumnDesc *columns, int n
 		if (d->quals[q].op < CG_OP_LT || d->quals[q].op > CG_OP_NE)
 			return cg_set_error(CG_EINVAL, "qual %d: bad operator", q);
 	}
+	if (d->nqual_expr < 0 || d->nqual_expr > CG_MAX_QEXPR) return cg_set_error(CG_EINVAL, "nqual_expr %d out of range", d->nqual_expr);
+	if (d->nqual_expr > 0)
+	{
+		/* well-formed postfix: every operator finds two operands, one value is left */
+		int depth = 0;
+		for (int i = 0; i < d->nqual_expr; i++)
+		{
+			int t = d->qual_expr[i];
+			if (t >= 0) { if (t >= d->nquals) return cg_set_error(CG_EINVAL, "qual_expr refers to atom %d of %d", t, d->nquals); depth++; }
+			else if (t == CG_QX_AND || t == CG_QX_OR) { if (depth < 2) return cg_set_error(CG_EINVAL, "qual_expr: operator without operands"); depth--; }
+			else return cg_set_error(CG_EINVAL, "qual_expr: bad token %d", t);
+		}
+		if (depth != 1) return cg_set_error(CG_EINVAL, "qual_expr leaves %d values", depth);
+	}
 	for (int g = 0; g < d->ngroup_cols; g++)
 	{
 		int c = d->group_cols[g];
@@ -361,6 +375,8 @@ int cg_build_plan(const CgScanDesc *desc, const CgColumnDesc *columns, int natts
 			/* float4 column values are promoted to float8; so is the constant (already float8 bits) */
 		}
 	}
+	plan->nqexpr = desc->nqual_expr;
+	for (int i = 0; i < desc->nqual_expr; i++) plan->qexpr[i] = desc->qual_expr[i];
 	plan->ngroup = desc->ngroup_cols;
 	for (int g = 0; g < desc->ngroup_cols; g++)
 	{
@@ -412,7 +428,7 @@ int cg_build_plan(const CgScanDesc *desc, const CgColumnDesc *columns, int natts
  */
 bool cg_build_fast_plan(const CgScanDesc *desc, const KPlan &plan, bool all8, FPlan *fast)
 {
-	if (!all8 || plan.ngroup > 1) return false;
+	if (!all8 || plan.ngroup > 1 || plan.nqexpr != 0) return false;
 	for (int c = 0; c < plan.ncols; c++) if (plan.isfloat[c]) return false;
 	memset(fast, 0, sizeof *fast);
 	bool used[CG_KMAX_COLS] = {false};

@@ -81,18 +81,8 @@ template <int NCC, int NAC, int MODE>
 __device__ __forceinline__ void process_row(const KPlan &P, const int64_t (&v)[NCC], uint32_t nullmask,
 											ThreadAcc<NAC> &acc, uint32_t &removed)
 {
-	/* K3: WHERE list, three-valued: a NULL input makes the conjunct NULL and drops the row */
-	bool pass = true;
-#pragma unroll 1
-	for (int q = 0; q < P.nquals; q++)
-	{
-		int c = P.qcol[q];
-		bool isnull = (nullmask >> c) & 1u;
-		int64_t x = pick<NCC>(v, c);
-		bool t = P.isfloat[c] ? qual_true(x, P.qop[q], P.qk[q], true)
-							  : (((x >= P.qlo[q]) && (x <= P.qhi[q])) != (bool) P.qneg[q]);
-		pass = pass && !isnull && t;
-	}
+	/* K3: WHERE tree, three-valued: an atom on a NULL input is not TRUE */
+	const bool pass = eval_where<NCC>(P, v, nullmask);
 	if (!pass)
 	{
 		removed++;

@@ -66,18 +66,7 @@ struct RowTerms
 template <int NCC>
 __device__ __forceinline__ bool eval_quals(const KPlan &P, const int64_t (&v)[NCC], uint32_t nullmask)
 {
-	bool pass = true;
-	for (int q = 0; q < P.nquals; q++)
-	{
-		int c = P.qcol[q];
-		bool isnull = (nullmask >> c) & 1u;
-		int64_t x = pick<NCC>(v, c);
-		bool t;
-		if (P.isfloat[c]) t = qual_true(x, P.qop[q], P.qk[q], true);
-		else t = ((x >= P.qlo[q]) && (x <= P.qhi[q])) != (bool) P.qneg[q];
-		pass = pass && !isnull && t;
-	}
-	return pass;
+	return eval_where<NCC>(P, v, nullmask);
 }
 
 template <int NCC>

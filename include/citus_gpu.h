@@ -60,10 +60,17 @@ uint64_t cg_kernel_launches(void);
  * 2 global table; source (may be NULL) receives the generated CUDA. */
 uint64_t cg_jit_launches(void);
 uint64_t cg_jit_compiles(void);
+/* run-time switches, e.g. ("jit", 0 | 1 | 2), ("force_general", 0 | 1): which kernel family scans (tests and
+ * A/B measurements drive every family through the same C-ABI calls) */
+int cg_set_option(const char *name, int64_t value);
 struct CgScanDesc;
 struct CgColumnDesc;
 int cg_jit_compile_check(const struct CgScanDesc *desc, const struct CgColumnDesc *columns, int32_t natts, int64_t key_min,
 						 int64_t key_max, int64_t max_rows, int32_t *kind, char *source, size_t source_len);
+/* the same for the kernel form that reads NULL-bearing chunks: bit a of nullable_atts = attribute a may be NULL */
+int cg_jit_compile_check_nullable(const struct CgScanDesc *desc, const struct CgColumnDesc *columns, int32_t natts, int64_t key_min,
+								  int64_t key_max, int64_t max_rows, uint32_t nullable_atts, int32_t *kind, char *source,
+								  size_t source_len);
 /* Pin the calling thread (and threads it creates afterwards: the staging threads) to the CPUs
  * of the device's NUMA node, so that host pages it first-touches and the DMA reads of them stay
  * on the socket the GPU hangs off.  *node = the node, or -1 when nothing was changed (single
@@ -174,6 +181,12 @@ typedef struct CgAggSpec
 #define CG_MAX_QUALS 8
 #define CG_MAX_AGGS 8
 #define CG_MAX_GROUP_COLS 2
+/* WHERE as a boolean tree over the atoms quals[0..nquals): postfix tokens, >= 0 = atom index,
+ * CG_QX_AND / CG_QX_OR combine the two entries on top of the stack (PostgreSQL's BoolExpr; NOT is
+ * folded into the operators).  nqual_expr = 0 means the plain AND of all atoms. */
+#define CG_MAX_QEXPR 16
+#define CG_QX_AND (-1)
+#define CG_QX_OR (-2)
 
 typedef struct CgScanDesc
 {
@@ -185,6 +198,13 @@ typedef struct CgScanDesc
 	int32_t naggs;
 	CgAggSpec aggs[CG_MAX_AGGS];
 	int64_t expected_groups;        /* planner's group estimate; 0 = let the library size the table */
+	/* [PG] ExecQual over AND/OR trees (columnar_customscan.c:1907-1913): a row passes iff the tree is TRUE
+	 * under three-valued logic -- an atom on a NULL input is not TRUE.  Chunk-group skipping follows
+	 * predicate_refuted_by for the base constraint of ONE column at a time (columnar_reader.c:1132-1187):
+	 * an AND node is refuted when any arm is, an OR node when all arms are. */
+	int32_t nqual_expr;
+	int8_t qual_expr[CG_MAX_QEXPR];
+	int32_t reserved;
 } CgScanDesc;
 
 /* EXPLAIN ANALYZE counters (columnar_customscan.c:1966-1999 and ExecScan instrumentation) */

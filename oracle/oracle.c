@@ -1023,11 +1023,30 @@ static int orc_qual_cmp_true(int atttype, int64_t v, int op, int64_t k)
 }
 
 /*
+ * WHERE as a boolean tree over the atoms ([PG] BoolExpr AND / OR; NOT is folded into the operators):
+ * postfix tokens, >= 0 = atom index, -1 = AND, -2 = OR, set per thread right before a scan; no tokens =
+ * the atoms are an AND-list.
+ *   row:   [PG] ExecQual (execExprInterp.c) -- the row passes iff the tree is TRUE; under three-valued logic
+ *          without NOT that is: atom on a NULL input -> not TRUE, AND -> both TRUE, OR -> either TRUE
+ *   chunk: [PG] predicate_refuted_by (predtest.c) against the base constraint of ONE column
+ *          (columnar_reader.c:1132-1187 loops over whereClauseVars): the implicit AND-list and an AND clause
+ *          are refuted when any arm is, an OR clause when every arm is; an atom on another column never is
+ * Pinned by expected/columnar_chunk_filtering.out (pushdown_test: OR of equalities, OR of AND arms).
+ */
+static __thread int orc_nqexpr = 0;
+static __thread int8_t orc_qexpr[32];
+void orc_set_qual_expr(const int8_t *tokens, int n)
+{
+	orc_nqexpr = n < 0 ? 0 : (n > 32 ? 32 : n);
+	for (int i = 0; i < orc_nqexpr; i++) orc_qexpr[i] = tokens[i];
+}
+
+/*
  * columnar_reader.c:1132-1187 SelectedChunkMask + :1234 BuildBaseConstraint +
  * :1358 UpdateConstraint; [PG] predicate_refuted_by (predtest.c) restated for the
- * clause shapes the GPU path accepts: an AND-list of "col <op> const" with btree
- * operators.  The base constraint (col >= min AND col <= max) is refuted when one
- * clause on the same column refutes either half:
+ * clause shapes the GPU path accepts: "col <op> const" atoms with btree operators.
+ * The base constraint (col >= min AND col <= max) is refuted by an atom on the same column
+ * that contradicts either half:
  *    col <  k refutes col >= min  iff  min >= k
  *    col <= k refutes col >= min  iff  min >  k
  *    col =  k refutes either half iff  k < min or k > max
@@ -1036,28 +1055,66 @@ static int orc_qual_cmp_true(int atttype, int64_t v, int op, int64_t k)
  *    col <> k refutes nothing (no btree refutation from a range to <>)
  * Pinned by expected/columnar_chunk_filtering.out.
  */
+static int orc_atom_refuted(const OrcTable *t, const OrcSkipNode *node, int col, const OrcQual *q)
+{
+	if (q->col != col) return 0;
+	int ty = t->atttype[col];
+	int64_t k = q->konst;
+	int cmin = orc_datum_cmp(ty, node->min_value, k);
+	int cmax = orc_datum_cmp(ty, node->max_value, k);
+	switch (q->op)
+	{
+		case ORC_OP_LT: return cmin >= 0;
+		case ORC_OP_LE: return cmin > 0;
+		case ORC_OP_EQ: return cmin > 0 || cmax < 0;
+		case ORC_OP_GE: return cmax < 0;
+		case ORC_OP_GT: return cmax <= 0;
+		default: return 0;
+	}
+}
+
 static int orc_chunk_refuted(const OrcTable *t, const OrcSkipNode *node, int col,
 							 const OrcQual *quals, int nquals)
 {
 	if (!node->has_minmax) return 0;
-	int ty = t->atttype[col];
+	if (orc_nqexpr == 0)
+	{
+		for (int q = 0; q < nquals; q++)
+			if (orc_atom_refuted(t, node, col, &quals[q])) return 1;
+		return 0;
+	}
+	int st[32], sp = 0;
+	for (int i = 0; i < orc_nqexpr; i++)
+	{
+		int tok = orc_qexpr[i];
+		if (tok >= 0) st[sp++] = orc_atom_refuted(t, node, col, &quals[tok]);
+		else { int b = st[--sp], a = st[--sp]; st[sp++] = tok == -1 ? (a || b) : (a && b); }
+	}
+	return st[0];
+}
+
+/* [PG] ExecQual: is the WHERE tree TRUE for row i? */
+static int orc_row_passes(const OrcTable *t, const OrcQual *quals, int nquals, uint8_t **exists, int64_t **values, uint32_t i)
+{
+	int truth[32];
 	for (int q = 0; q < nquals; q++)
 	{
-		if (quals[q].col != col) continue;
-		int64_t k = quals[q].konst;
-		int cmin = orc_datum_cmp(ty, node->min_value, k);
-		int cmax = orc_datum_cmp(ty, node->max_value, k);
-		switch (quals[q].op)
-		{
-			case ORC_OP_LT: if (cmin >= 0) return 1; break;
-			case ORC_OP_LE: if (cmin > 0) return 1; break;
-			case ORC_OP_EQ: if (cmin > 0 || cmax < 0) return 1; break;
-			case ORC_OP_GE: if (cmax < 0) return 1; break;
-			case ORC_OP_GT: if (cmax <= 0) return 1; break;
-			default: break;
-		}
+		int c = quals[q].col;
+		truth[q] = exists[c][i] && orc_qual_cmp_true(t->atttype[c], values[c][i], quals[q].op, quals[q].konst);
 	}
-	return 0;
+	if (orc_nqexpr == 0)
+	{
+		for (int q = 0; q < nquals; q++) if (!truth[q]) return 0;
+		return 1;
+	}
+	int st[32], sp = 0;
+	for (int k = 0; k < orc_nqexpr; k++)
+	{
+		int tok = orc_qexpr[k];
+		if (tok >= 0) st[sp++] = truth[tok];
+		else { int b = st[--sp], a = st[--sp]; st[sp++] = tok == -1 ? (a && b) : (a || b); }
+	}
+	return st[0];
 }
 
 static inline uint64_t orc_mix64(uint64_t x)
@@ -1243,13 +1300,7 @@ int orc_scan_aggregate(const OrcTable *t, const OrcQual *quals, int nquals,
 			for (uint32_t i = 0; i < rowCount; i++)
 			{
 				res->rows_scanned++;
-				int pass = 1;
-				for (int q = 0; q < nquals && pass; q++)
-				{
-					int c = quals[q].col;
-					if (!exists[c][i]) pass = 0;
-					else if (!orc_qual_cmp_true(t->atttype[c], values[c][i], quals[q].op, quals[q].konst)) pass = 0;
-				}
+				int pass = orc_row_passes(t, quals, nquals, exists, values, i);
 				if (!pass) { res->rows_removed_by_filter++; continue; }
 				res->rows_passed++;
 

@@ -108,6 +108,8 @@ def lib():
         L.orc_result_counter.argtypes = [C.c_void_p, C.c_int]
         L.orc_result_group.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.orc_result_agg.argtypes = [C.c_void_p, C.c_int64, C.c_int] + [C.c_void_p] * 8
+        L.orc_set_qual_expr.restype = None
+        L.orc_set_qual_expr.argtypes = [C.c_void_p, C.c_int]
         L.orc_scan_aggregate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                          C.c_void_p, C.c_int, C.c_void_p]
         L.orc_combine.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -374,7 +376,11 @@ class Table:
 
     # --- scan ------------------------------------------------------------
     def scan(self, quals=(), group_cols=(), aggs=(), qual_pushdown=True, into: "Result | None" = None):
-        """quals: [(col, op_str, const)]; returns Result (accumulating into `into` if given)."""
+        """quals: [(col, op_str, const)] (an AND-list) or a nested tuple tree ("and" | "or", arm, ...) over such
+        atoms; returns Result (accumulating into `into` if given)."""
+        quals, tokens = flatten_where(quals)
+        tk = (C.c_int8 * max(1, len(tokens)))(*tokens)
+        lib().orc_set_qual_expr(tk, len(tokens))        # per thread, read by the scan below
         qa = (Qual * max(1, len(quals)))()
         for i, (col, op, k) in enumerate(quals):
             qa[i].col = col
@@ -389,6 +395,27 @@ class Table:
         _check(lib().orc_scan_aggregate(self.h, qa, len(quals), 1 if qual_pushdown else 0,
                                         ga, len(group_cols), sa, len(aggs), res.h))
         return res
+
+
+def flatten_where(where):
+    """nested ("and" | "or", arm, ...) tree over (col, op, const) atoms -> (atoms, postfix tokens: >= 0 atom,
+    -1 AND, -2 OR); a plain list of atoms is their AND and has no tokens"""
+    if not (isinstance(where, tuple) and where and where[0] in ("and", "or")):
+        return list(where), []
+    atoms, tokens = [], []
+
+    def walk(node):
+        if isinstance(node, tuple) and node and node[0] in ("and", "or"):
+            walk(node[1])
+            for arm in node[2:]:
+                walk(arm)
+                tokens.append(-1 if node[0] == "and" else -2)
+        else:
+            tokens.append(len(atoms))
+            atoms.append(tuple(node))
+
+    walk(where)
+    return atoms, tokens
 
 
 class Result:

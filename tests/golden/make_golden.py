@@ -137,6 +137,16 @@ def main():
                                            "groups_removed": 5, "actual_rows": 184567}
     assert "(actual rows=184567 loops=1)" in text and "Columnar Chunk Groups Removed by Filter: 5" in text
 
+    # OR clauses pushed down to the chunk-group filter (pushdown_test: a = 1..200000, b NULL, stripe 2000, chunk
+    # group 1000): WHERE text, "Rows Removed by Filter", "Columnar Chunk Groups Removed by Filter", sum(a)
+    pd = []
+    for where in ("a = 204356 or a = 104356 or a = 76556", "a = 194356 or a = 104356 or a = 76556",
+                  "(a > 1000 and a < 10000) or (a > 20000 and a < 50000)"):
+        m = re.search(r"SELECT sum\(a\) FROM pushdown_test (?:WHERE|where) " + re.escape(where) + r";\n.*?Rows Removed by Filter: (\d+)\n.*?"
+                      r"Columnar Chunk Groups Removed by Filter: (\d+)\n.*?\n\s+sum\s*\n-+\n\s+(\d+)", text, re.S)
+        pd.append({"where": where, "rows_removed": int(m.group(1)), "groups_removed": int(m.group(2)), "sum": int(m.group(3))})
+    exp["pushdown_or"] = pd
+
     # columnar_query (expected/columnar_query.out:9-29) + data/contestants.{1,2}.csv
     ratings, countries = [], []
     for fi in (1, 2):

@@ -602,3 +602,96 @@ def test_join_count_sum_matches_row_at_a_time_join(cg, oracle):
         got = cg.join_count_sum(d[0].data_ptr(), d[1].data_ptr(), nb, d[2].data_ptr(), d[3].data_ptr(), npr,
                                 d_build_nulls=d[4].data_ptr(), d_probe_nulls=d[5].data_ptr())
         assert got == want, (nb, npr, domain)
+
+
+# --------------------------------------------------------------------------- NULL-bearing chunk groups on the fast paths
+@pytest.fixture
+def kernel_family(cg):
+    """runs a test body once per kernel family through the same C-ABI calls"""
+    def use(name):
+        cg.set_option("jit", {"jit": 1, "jit_always": 2, "aot": 0, "general": 0}[name])
+        cg.set_option("force_general", 1 if name == "general" else 0)
+    yield use
+    cg.set_option("jit", 1)
+    cg.set_option("force_general", 0)
+
+
+@pytest.mark.parametrize("family", ["jit", "jit_always", "aot", "general"])
+@pytest.mark.parametrize("path", ["shard", "e2e", "dma"])
+def test_c2_with_nulls_on_every_kernel_family(cg, oracle, kernel_family, family, path):
+    """C2 with 5 % NULLs in v (and, second pass, NULLs in the key and the filter column too).
+    count(*) counts the row, sum(v) skips it (strict transition function), a NULL filter input drops the
+    row, a NULL key is its own group -- bit-exact against the oracle on every kernel family and staging path"""
+    from citus_b200 import capi
+    kernel_family(family)
+    for nulls in ((0, 0, 50000), (20000, 30000, 50000)):
+        cols = [(8, 0, 0, 3000, nulls[0]), (8, 0, 0, 100, nulls[1]), (8, 0, -10**9, 10**9, nulls[2])] + [(8, 0, 0, 1 << 40, 0)] * 2
+        rel = cg.Relation.generate(cols, 123_457, seed=77 + nulls[0], stripe_row_limit=30000, chunk_row_limit=5000)
+        aggs = [cg.sum_(2), cg.count_star(), cg.count(2)]
+        jit0 = capi.lib().cg_jit_launches()
+        for force_hash in (False, True):
+            run_both(cg, oracle, rel, [(1, "<", 50)], [0], aggs, chunk_row_limit=5000, force_hash=force_hash,
+                     e2e=False if path == "shard" else path)
+        if family in ("jit", "jit_always"):
+            assert capi.lib().cg_jit_launches() > jit0       # the NULL-bearing chunk groups ran on the generated kernel
+        else:
+            assert capi.lib().cg_jit_launches() == jit0
+
+
+@pytest.mark.parametrize("family", ["jit", "general"])
+def test_nulls_in_plain_and_small_domain_aggregates(cg, oracle, kernel_family, family):
+    """NULL inputs in a plain aggregate (thread registers) and in a tiny key domain (shared-memory cells),
+    mixed widths, min/max/count(x), a NULL group key on the small-domain table"""
+    kernel_family(family)
+    cols = [(8, 0, -1000, 1000, 100000), (4, 0, 0, 100, 50000), (2, 0, 0, 5, 150000), (1, 0, -50, 50, 300000),
+            (8, 0, -2**40, 2**40, 10000)]
+    rel = cg.Relation.generate(cols, 77_777, seed=5, stripe_row_limit=20000, chunk_row_limit=3000)
+    aggs = [cg.sum_(0), cg.count_star(), cg.count(3), cg.min_(4), cg.max_(0), cg.sum_(3)]
+    run_both(cg, oracle, rel, [(1, "<", 70)], [], aggs, chunk_row_limit=3000)
+    run_both(cg, oracle, rel, [(1, "<", 70)], [2], aggs, chunk_row_limit=3000)
+    run_both(cg, oracle, rel, [(1, ">=", 10)], [2], aggs, chunk_row_limit=3000, e2e=True)
+
+
+# --------------------------------------------------------------------------- WHERE trees (R10)
+@pytest.mark.parametrize("family", ["jit", "general"])
+def test_or_clause_goldens_through_the_gpu(cg, oracle, expected, kernel_family, family):
+    """expected/columnar_chunk_filtering.out pushdown_test: Rows Removed by Filter, Columnar Chunk Groups
+    Removed by Filter and sum(a) of the three OR queries"""
+    kernel_family(family)
+    a = np.arange(1, 200001)
+    rel = cg.Relation.write([4, 4], [a, np.zeros_like(a)], [None, np.ones(a.shape[0], np.uint8)],
+                            stripe_row_limit=2000, chunk_row_limit=1000)
+    trees = {
+        "a = 204356 or a = 104356 or a = 76556": ("or", (0, "=", 204356), (0, "=", 104356), (0, "=", 76556)),
+        "a = 194356 or a = 104356 or a = 76556": ("or", (0, "=", 194356), (0, "=", 104356), (0, "=", 76556)),
+        "(a > 1000 and a < 10000) or (a > 20000 and a < 50000)":
+            ("or", ("and", (0, ">", 1000), (0, "<", 10000)), ("and", (0, ">", 20000), (0, "<", 50000))),
+    }
+    for g in expected["pushdown_or"]:
+        for e2e in (False, True):
+            st, got = run_both(cg, oracle, rel, trees[g["where"]], [], [cg.sum_(0)], chunk_row_limit=1000, e2e=e2e)
+            assert st.chunk_groups_filtered == g["groups_removed"]
+            assert st.rows_removed_by_filter == g["rows_removed"]
+            assert got[0][0]["sum"] == g["sum"]
+
+
+@pytest.mark.parametrize("family", ["jit", "general"])
+def test_where_trees_with_nulls_and_groups(cg, oracle, kernel_family, family):
+    """three-valued logic under OR: FALSE OR NULL drops the row, TRUE OR NULL keeps it; trees over several
+    columns, float atoms, GROUP BY on a direct-indexed and a hash table"""
+    kernel_family(family)
+    rng = np.random.default_rng(21)
+    n = 60_000
+    k = rng.integers(0, 500, n)
+    x = rng.integers(-100, 100, n)
+    y = rng.integers(0, 1000, n)
+    f = rng.normal(size=n)
+    nx = (rng.random(n) < 0.2).astype(np.uint8)
+    ny = (rng.random(n) < 0.1).astype(np.uint8)
+    rel = cg.Relation.write([8, 4, 8, 8], [k, x, y, f], [None, nx, ny, None], type_classes=[0, 0, 0, 1],
+                            stripe_row_limit=20000, chunk_row_limit=4000)
+    where = ("and", ("or", (1, "<", -50), (2, ">", 900), ("and", (3, ">", 0.5), (1, "<>", 7))), (0, "<", 450))
+    aggs = [cg.sum_(2), cg.count_star(), cg.count(1), cg.max_(1)]
+    for force_hash in (False, True):
+        run_both(cg, oracle, rel, where, [0], aggs, chunk_row_limit=4000, force_hash=force_hash, float_cols=(3,))
+    run_both(cg, oracle, rel, where, [], aggs, chunk_row_limit=4000, float_cols=(3,), e2e=True)

@@ -386,3 +386,91 @@ def test_qual_on_column_added_after_the_stripe_was_written(cg):
         capi.check(capi.lib().cg_selected_chunk_mask(C.byref(rel3.view), si, C.byref(d), mask.ctypes.data, C.byref(filtered)))
         total += filtered.value
     assert total == 8
+
+
+def test_where_tree_chunk_mask_matches_reference_goldens(cg, expected):
+    """SelectedChunkMask over OR / AND trees on the host (cg_selected_chunk_mask): the pushdown_test goldens of
+    expected/columnar_chunk_filtering.out; malformed trees are refused"""
+    from citus_b200 import capi
+    a = np.arange(1, 200001)
+    rel = cg.Relation.write([4, 4], [a, np.zeros_like(a)], [None, np.ones(a.shape[0], np.uint8)],
+                            stripe_row_limit=2000, chunk_row_limit=1000)
+    trees = {
+        "a = 204356 or a = 104356 or a = 76556": ("or", (0, "=", 204356), (0, "=", 104356), (0, "=", 76556)),
+        "a = 194356 or a = 104356 or a = 76556": ("or", (0, "=", 194356), (0, "=", 104356), (0, "=", 76556)),
+        "(a > 1000 and a < 10000) or (a > 20000 and a < 50000)":
+            ("or", ("and", (0, ">", 1000), (0, "<", 10000)), ("and", (0, ">", 20000), (0, "<", 50000))),
+    }
+    for g in expected["pushdown_or"]:
+        d = cg.make_desc(trees[g["where"]], [], [cg.sum_(0)])
+        total = 0
+        for si in range(rel.view.nstripes):
+            mask = np.zeros(rel.view.stripes[si].chunk_count, np.uint8)
+            f = C.c_int64()
+            capi.check(capi.lib().cg_selected_chunk_mask(C.byref(rel.view), si, C.byref(d), mask.ctypes.data, C.byref(f)))
+            total += f.value
+        assert total == g["groups_removed"]
+    d = cg.make_desc(("or", (0, "=", 1), (0, "=", 2)), [], [cg.count_star()])
+    d.qual_expr[2] = 5                         # refers to an atom that does not exist
+    kmin, kmax, rows = C.c_int64(), C.c_int64(), C.c_int64()
+    bounds = (C.c_int64 * 8)()
+    kind = C.c_int32()
+    cols = (capi.CgColumnDesc * 2)()
+    cols[0].attlen = cols[1].attlen = 4
+    assert capi.lib().cg_jit_compile_check(C.byref(d), cols, 2, 0, -1, 10, C.byref(kind), None, 0) == capi.CG_EINVAL
+    d = cg.make_desc(("or", (0, "=", 1), (0, "=", 2)), [], [cg.count_star()])
+    d.nqual_expr = 2                           # operands left on the stack
+    assert capi.lib().cg_jit_compile_check(C.byref(d), cols, 2, 0, -1, 10, C.byref(kind), None, 0) == capi.CG_EINVAL
+
+
+def _jit_check_nullable(cg, quals, group, aggs, lens, kmin, kmax, rows, nullable, float_cols=()):
+    from citus_b200 import capi
+    d = cg.make_desc(quals, group, aggs, float_cols=float_cols)
+    cols = (capi.CgColumnDesc * len(lens))()
+    for i, l in enumerate(lens):
+        cols[i].attlen, cols[i].type_class = l, (1 if i in float_cols else 0)
+    kind = C.c_int32(-1)
+    buf = C.create_string_buffer(1 << 19)
+    rc = capi.lib().cg_jit_compile_check_nullable(C.byref(d), cols, len(lens), kmin, kmax, rows, nullable, C.byref(kind), buf, len(buf))
+    assert rc == 0, capi.lib().cg_last_error().decode()
+    return kind.value, buf.value.decode()
+
+
+def test_jit_nullable_and_where_tree_forms_compile(cg):
+    """the generated kernels' NULL-aware form (exists bitmap + rank directory, columnar_reader.c:1506-1572) and
+    WHERE trees, for every table kind and column width"""
+    try:
+        C.CDLL("libnvrtc.so.12")
+    except OSError:
+        pytest.skip("libnvrtc missing")
+    a = [cg.sum_(2), cg.count_star()]
+    a[0].term_abs_bound = 10**9
+    # C2 with NULLs in v: packed word gets count only for a NULL input, the NULL-input counter one more reduction
+    kind, src = _jit_check_nullable(cg, [(1, "<", 50)], [0], a, [8] * 8, 0, 999_999, 10**9, 0b100)
+    assert kind == 2 and "__popcll(bw" in src and "an0 ? 0ull" in src and "const bool n2" in src and "const bool n0" not in src
+    # every column nullable: NULL key -> the entry behind the table, NULL qual input -> atom not TRUE
+    kind, src = _jit_check_nullable(cg, [(1, "<", 50)], [0], a, [8] * 8, 0, 999_999, 10**9, 0b111)
+    assert "z1 ? P.capacity" in src and "!z0 && " in src
+    # hash table, OR tree with an AND arm, count(x), min, narrow columns
+    kind, src = _jit_check_nullable(cg, ("or", (1, "<", 50), ("and", (3, ">", 5), (3, "<", 9))), [0],
+                                    a + [cg.count(3), cg.min_(4)], [8, 8, 8, 4, 2, 1], 0, -1, 10**9, 0b111111)
+    assert kind == 2 and "(t0 || (t1 && t2))" in src and "ld4(" in src and "ld2(" in src
+    # plain aggregate: NULL-input counters in registers
+    kind, src = _jit_check_nullable(cg, [(1, "<", 50)], [], [cg.sum_(2), cg.count_star(), cg.count(3), cg.min_(4), cg.max_(5)],
+                                    [8, 4, 2, 1, 8, 8], 0, -1, 10**9, 0b111111)
+    assert kind == 0 and "g_n2++" in src and "ld1(" in src
+    # Q1 shape with NULLs everywhere: shared-memory cells, NULL multi-key is flagged
+    q1 = [cg.sum_(0), cg.sum_(1), cg.Agg(2, [(1, 0, 1), (2, 100, -1)]), cg.Agg(2, [(1, 0, 1), (2, 100, -1), (3, 100, 1)]),
+          cg.sum_(2), cg.count_star()]
+    for x, b in zip(q1, (5100, 10_500_000, 10**9, 2 * 10**11, 11, 0)):
+        x.term_abs_bound = b
+    kind, src = _jit_check_nullable(cg, [(6, "<=", -486)], [4, 5], q1, [8, 8, 8, 8, 1, 1, 4, 4], 65 | (70 << 32), 67 | (71 << 32),
+                                    6 * 10**8, 0xff)
+    assert kind == 1 and "raise_flag(P.stats, 2ull)" in src
+    # one nullable group column on shared-memory cells: the NULL group goes to its global entry
+    kind, src = _jit_check_nullable(cg, [(6, "<=", -486)], [4], q1, [8, 8, 8, 8, 1, 1, 4, 4], 65, 67, 6 * 10**8, 0xff)
+    assert kind == 1 and "P.table + P.capacity *" in src
+    # float columns
+    kind, src = _jit_check_nullable(cg, [(1, "<", 0.5)], [0], [cg.sum_(1, True), cg.min_(2, True), cg.count_star()], [8, 8, 4], 0, -1,
+                                    10**6, 0b111, float_cols=(1, 2))
+    assert kind == 2 and "fcmp(" in src

@@ -364,3 +364,26 @@ def test_join_restatement_against_brute_force(oracle):
         cnt += len(m)
         tot += sum(int(x) + int(y) for x in m)
     assert joined == cnt and total == tot
+
+
+def test_or_clauses_pushdown_goldens(oracle, expected):
+    """expected/columnar_chunk_filtering.out, pushdown_test: OR clauses reach the chunk-group filter
+    (predicate_refuted_by: an OR clause is refuted when every arm is) and ExecQual re-checks every row"""
+    t = oracle.Table([4, 4], stripe_row_limit=2000, chunk_row_limit=1000)
+    a = np.arange(1, 200001)
+    t.insert([a, np.zeros_like(a)], nulls=[None, np.ones(a.shape[0], np.uint8)])
+    trees = {
+        "a = 204356 or a = 104356 or a = 76556": ("or", (0, "=", 204356), (0, "=", 104356), (0, "=", 76556)),
+        "a = 194356 or a = 104356 or a = 76556": ("or", (0, "=", 194356), (0, "=", 104356), (0, "=", 76556)),
+        "(a > 1000 and a < 10000) or (a > 20000 and a < 50000)":
+            ("or", ("and", (0, ">", 1000), (0, "<", 10000)), ("and", (0, ">", 20000), (0, "<", 50000))),
+    }
+    assert len(expected["pushdown_or"]) == 3
+    for g in expected["pushdown_or"]:
+        r = t.scan(trees[g["where"]], [], [oracle.sum_(0)])
+        assert r.chunk_groups_filtered == g["groups_removed"]
+        assert r.rows_removed_by_filter == g["rows_removed"]
+        assert r.groups()[0][0]["sum"] == g["sum"]
+    # an OR over two columns is never refuted by one column's range; a NULL arm is not TRUE
+    r = t.scan(("or", (0, "=", 5), (1, "=", 0)), [], [oracle.count_star()])
+    assert r.chunk_groups_filtered == 0 and r.rows_passed == 1
