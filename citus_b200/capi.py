@@ -14,7 +14,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libcitus_gpu.so")
 
-CG_OK, CG_EINVAL, CG_ECUDA, CG_ENOMEM, CG_ECORRUPT, CG_ETABLEFULL, CG_EUNSUPPORTED, CG_ERETRY_UNPACKED = range(8)
+CG_OK, CG_EINVAL, CG_ECUDA, CG_ENOMEM, CG_ECORRUPT, CG_ETABLEFULL, CG_EUNSUPPORTED, CG_ERETRY_UNPACKED, CG_ECOMM = range(9)
+CG_COMM_ID_BYTES = 128
+CG_COMM_SUM, CG_COMM_MIN, CG_COMM_MAX = 0, 1, 2
 CG_TYPE_INT, CG_TYPE_FLOAT = 0, 1
 CG_OP = {"<": 0, "<=": 1, "=": 2, ">=": 3, ">": 4, "<>": 5}
 CG_AGG_COUNT_STAR, CG_AGG_COUNT, CG_AGG_SUM, CG_AGG_MIN, CG_AGG_MAX = range(5)
@@ -147,6 +149,19 @@ SYMBOLS = [
                                     C.c_uint32, C.POINTER(_P)]),
     ("cg_gen_relation_view", C.c_int, [_P, C.POINTER(CgRelation)]),
     ("cg_gen_relation_free", None, [_P]),
+    ("cg_comm_unique_id", C.c_int, [_P]),
+    ("cg_comm_init", C.c_int, [_P, C.c_int32, C.c_int32]),
+    ("cg_comm_rank", C.c_int, [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    ("cg_comm_destroy", C.c_int, []),
+    ("cg_comm_barrier", C.c_int, []),
+    ("cg_comm_allreduce_i64", C.c_int, [_P, C.c_int32, C.c_int32]),
+    ("cg_comm_combine", C.c_int, [_P, C.c_int32, C.c_int32]),
+    ("cg_comm_repartition_exchange", C.c_int, [C.c_int32, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P,
+                                              C.POINTER(C.c_int64)]),
+    ("cg_comm_exchange_wait", C.c_int, [C.c_int32]),
+    ("cg_comm_exchange_result", C.c_int, [C.c_int32, _P, C.POINTER(C.c_int64), _P, C.POINTER(C.c_int32), C.POINTER(C.c_uint64),
+                                         C.POINTER(C.c_double)]),
+    ("cg_comm_exchange_plan", C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.POINTER(C.c_int32)]),
 ]
 
 _lib = None

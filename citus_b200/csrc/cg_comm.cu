@@ -1,0 +1,571 @@
+/*
+ * cg_comm.cu -- the exchange steps of the path, behind the C-ABI, over NCCL (NVLink 5 / NVSwitch).
+ *
+ * The reference moves partial results and repartitioned rows as libpq result rows and COPY files:
+ *   executor/adaptive_executor.c:3964-4189 ReceiveResults  (one HeapTuple per partial row into the
+ *       coordinator's tuplestore, then the combine query's HashAggregate,
+ *       planner/multi_logical_optimizer.c:1807-1885, 2231-2275)
+ *   executor/partitioned_intermediate_results.c:115-298 worker_partition_query_result  (P files per task)
+ *   executor/intermediate_results.c:789-1045 fetch_intermediate_results / read_intermediate_results
+ * Here one process drives one GPU (a PostgreSQL backend is one process), the per-GPU partial aggregates
+ * and the partition-contiguous rows already sit in HBM, and the exchange is a collective on the library's
+ * streams:
+ *   cg_comm_combine               coord_combine of the commutative / associative built-ins: one ncclReduce of
+ *                                 the accumulator array (the 8-byte packed words when nothing else was
+ *                                 written) to the coordinator rank; row gather + merge kernel otherwise
+ *   cg_comm_repartition_exchange  MAP_OUTPUT_FETCH: routing + scatter + one grouped ncclSend/ncclRecv of all
+ *                                 columns, counts exchanged on the device side of a second stream
+ * libnccl is resolved at first use (dlopen): a process that already carries a copy (torch bundles one) keeps
+ * using that one; a CPU-only process never loads it.
+ */
+#include <dlfcn.h>
+#include <nccl.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "cg_internal.h"
+
+/* ---------------------------------------------------------------------------------- */
+static struct NcclApi
+{
+	bool tried = false, ok = false;
+	decltype(&ncclGetUniqueId) GetUniqueId;
+	decltype(&ncclCommInitRank) CommInitRank;
+	decltype(&ncclCommDestroy) CommDestroy;
+	decltype(&ncclGetErrorString) GetErrorString;
+	decltype(&ncclReduce) Reduce;
+	decltype(&ncclAllReduce) AllReduce;
+	decltype(&ncclAllGather) AllGather;
+	decltype(&ncclSend) Send;
+	decltype(&ncclRecv) Recv;
+	decltype(&ncclGroupStart) GroupStart;
+	decltype(&ncclGroupEnd) GroupEnd;
+	decltype(&ncclGetVersion) GetVersion;
+} g_nccl;
+
+static bool load_nccl()
+{
+	if (g_nccl.tried) return g_nccl.ok;
+	g_nccl.tried = true;
+	void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);     /* the copy the process already has */
+	if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+	if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+	if (!h) return false;
+#define CG_NCCL_SYM(field, name) g_nccl.field = (decltype(g_nccl.field)) dlsym(h, name)
+	CG_NCCL_SYM(GetUniqueId, "ncclGetUniqueId"); CG_NCCL_SYM(CommInitRank, "ncclCommInitRank"); CG_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+	CG_NCCL_SYM(GetErrorString, "ncclGetErrorString"); CG_NCCL_SYM(Reduce, "ncclReduce"); CG_NCCL_SYM(AllReduce, "ncclAllReduce");
+	CG_NCCL_SYM(AllGather, "ncclAllGather"); CG_NCCL_SYM(Send, "ncclSend"); CG_NCCL_SYM(Recv, "ncclRecv");
+	CG_NCCL_SYM(GroupStart, "ncclGroupStart"); CG_NCCL_SYM(GroupEnd, "ncclGroupEnd"); CG_NCCL_SYM(GetVersion, "ncclGetVersion");
+#undef CG_NCCL_SYM
+	g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.GetErrorString && g_nccl.Reduce &&
+				g_nccl.AllReduce && g_nccl.AllGather && g_nccl.Send && g_nccl.Recv && g_nccl.GroupStart && g_nccl.GroupEnd;
+	return g_nccl.ok;
+}
+
+#define CG_NCCL(call)                                                                                       \
+	do {                                                                                                    \
+		ncclResult_t r__ = (call);                                                                          \
+		if (r__ != ncclSuccess)                                                                             \
+			return cg_set_error(CG_ECOMM, "%s failed: %s (%s:%d)", #call, g_nccl.GetErrorString(r__), __FILE__, __LINE__); \
+	} while (0)
+
+struct CgComm
+{
+	bool ready = false;
+	int rank = 0, nranks = 1;
+	ncclComm_t comm = nullptr;
+	cudaStream_t side = nullptr;        /* agreements and the repartition exchange: never behind the scans */
+	int64_t *h_small = nullptr;         /* pinned */
+	int64_t *d_small = nullptr;
+	size_t small_words = 0;
+	cudaEvent_t ev_scatter = nullptr, ev_index = nullptr;
+	/* row gather of the combine */
+	CgContext::DevBuf gather;
+	/* repartition slots */
+	struct Slot
+	{
+		CgContext::DevBuf send, recv, index;
+		cudaEvent_t done = nullptr, t0 = nullptr, t1 = nullptr;
+		int64_t recv_rows = 0;
+		int32_t ncols = 0;
+		std::vector<int64_t> part_counts;   /* [nlocal][nranks] rows of each local partition by source rank */
+		uint64_t sent_bytes = 0;
+	};
+	Slot slots[4];
+};
+static CgComm g_comm;
+
+static int comm_ensure_small(size_t words)
+{
+	if (g_comm.small_words >= words) return CG_OK;
+	if (g_comm.h_small) cudaFreeHost(g_comm.h_small);
+	cudaFree(g_comm.d_small);
+	g_comm.h_small = nullptr; g_comm.d_small = nullptr; g_comm.small_words = 0;
+	size_t cap = std::max<size_t>(words, 4096);
+	CG_CUDA(cudaHostAlloc((void **) &g_comm.h_small, cap * sizeof(int64_t), cudaHostAllocDefault));
+	CG_CUDA(cudaMalloc((void **) &g_comm.d_small, cap * sizeof(int64_t)));
+	g_comm.small_words = cap;
+	return CG_OK;
+}
+
+static int devbuf_grow(CgContext::DevBuf *b, size_t bytes)
+{
+	if (b->cap >= bytes) return CG_OK;
+	if (b->p) CG_CUDA(cudaFree(b->p));
+	b->p = nullptr; b->cap = 0;
+	size_t cap = bytes + bytes / 8 + 4096;
+	if (cudaMalloc((void **) &b->p, cap) != cudaSuccess)
+	{
+		cudaGetLastError();
+		return cg_set_error(CG_ENOMEM, "cudaMalloc of %zu bytes for an exchange buffer failed", cap);
+	}
+	b->cap = cap;
+	return CG_OK;
+}
+
+extern "C" int cg_comm_unique_id(uint8_t *id)
+{
+	if (!id) return cg_set_error(CG_EINVAL, "NULL id");
+	if (!load_nccl()) return cg_set_error(CG_ECOMM, "libnccl.so.2 is not available");
+	static_assert(sizeof(ncclUniqueId) == CG_COMM_ID_BYTES, "ncclUniqueId size");
+	ncclUniqueId u;
+	CG_NCCL(g_nccl.GetUniqueId(&u));
+	memcpy(id, &u, sizeof u);
+	return CG_OK;
+}
+
+extern "C" int cg_comm_init(const uint8_t *id, int32_t rank, int32_t nranks)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx) return CG_EINVAL;
+	if (g_comm.ready) return cg_set_error(CG_EINVAL, "communicator already initialised (rank %d of %d)", g_comm.rank, g_comm.nranks);
+	if (nranks < 1 || rank < 0 || rank >= nranks) return cg_set_error(CG_EINVAL, "rank %d of %d", rank, nranks);
+	g_comm.rank = rank; g_comm.nranks = nranks;
+	{
+		/* highest priority: its few thread blocks are scheduled as soon as any scan block retires */
+		int lo = 0, hi = 0;
+		CG_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+		CG_CUDA(cudaStreamCreateWithPriority(&g_comm.side, cudaStreamNonBlocking, hi));
+	}
+	CG_CUDA(cudaEventCreateWithFlags(&g_comm.ev_scatter, cudaEventDisableTiming));
+	CG_CUDA(cudaEventCreateWithFlags(&g_comm.ev_index, cudaEventDisableTiming));
+	if (nranks > 1)
+	{
+		if (!id) return cg_set_error(CG_EINVAL, "NULL id");
+		if (!load_nccl()) return cg_set_error(CG_ECOMM, "libnccl.so.2 is not available");
+		ncclUniqueId u;
+		memcpy(&u, id, sizeof u);
+		CG_NCCL(g_nccl.CommInitRank(&g_comm.comm, nranks, u, rank));
+	}
+	g_comm.ready = true;
+	return CG_OK;
+}
+
+extern "C" int cg_comm_rank(int32_t *rank, int32_t *nranks)
+{
+	if (!g_comm.ready) return cg_set_error(CG_EINVAL, "cg_comm_init() has not been called");
+	if (rank) *rank = g_comm.rank;
+	if (nranks) *nranks = g_comm.nranks;
+	return CG_OK;
+}
+
+extern "C" int cg_comm_destroy(void)
+{
+	if (!g_comm.ready) return CG_OK;
+	cudaStreamSynchronize(g_comm.side);
+	if (g_comm.comm) g_nccl.CommDestroy(g_comm.comm);
+	g_comm.comm = nullptr;
+	for (CgComm::Slot &s : g_comm.slots)
+	{
+		cudaFree(s.send.p); cudaFree(s.recv.p); cudaFree(s.index.p);
+		s.send = s.recv = s.index = CgContext::DevBuf();
+		if (s.done) cudaEventDestroy(s.done);
+		if (s.t0) cudaEventDestroy(s.t0);
+		if (s.t1) cudaEventDestroy(s.t1);
+		s.done = s.t0 = s.t1 = nullptr;
+	}
+	cudaFree(g_comm.gather.p); g_comm.gather = CgContext::DevBuf();
+	if (g_comm.h_small) cudaFreeHost(g_comm.h_small);
+	cudaFree(g_comm.d_small);
+	g_comm.h_small = nullptr; g_comm.d_small = nullptr; g_comm.small_words = 0;
+	cudaEventDestroy(g_comm.ev_scatter); cudaEventDestroy(g_comm.ev_index);
+	cudaStreamDestroy(g_comm.side);
+	g_comm.ready = false;
+	return CG_OK;
+}
+
+/*
+ * Small host-side agreement: values[i] <- op over ranks of values[i].  Runs on the side stream, so it never
+ * queues behind scan kernels: the host of every rank learns the result while its GPU is still busy.
+ */
+static int comm_agree(int64_t *values, int n, ncclRedOp_t op)
+{
+	if (g_comm.nranks == 1) return CG_OK;
+	int rc = comm_ensure_small((size_t) n);
+	if (rc) return rc;
+	memcpy(g_comm.h_small, values, sizeof(int64_t) * n);
+	CG_CUDA(cudaMemcpyAsync(g_comm.d_small, g_comm.h_small, sizeof(int64_t) * n, cudaMemcpyHostToDevice, g_comm.side));
+	CG_NCCL(g_nccl.AllReduce(g_comm.d_small, g_comm.d_small, (size_t) n, ncclInt64, op, g_comm.comm, g_comm.side));
+	CG_CUDA(cudaMemcpyAsync(g_comm.h_small, g_comm.d_small, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, g_comm.side));
+	CG_CUDA(cudaStreamSynchronize(g_comm.side));
+	memcpy(values, g_comm.h_small, sizeof(int64_t) * n);
+	return CG_OK;
+}
+
+extern "C" int cg_comm_allreduce_i64(int64_t *values, int32_t n, int32_t op)
+{
+	if (!g_comm.ready) return cg_set_error(CG_EINVAL, "cg_comm_init() has not been called");
+	if (!values || n < 0 || n > 4096) return cg_set_error(CG_EINVAL, "bad argument");
+	ncclRedOp_t o = op == CG_COMM_SUM ? ncclSum : op == CG_COMM_MIN ? ncclMin : op == CG_COMM_MAX ? ncclMax : ncclNumOps;
+	if (o == ncclNumOps) return cg_set_error(CG_EINVAL, "bad reduction op %d", op);
+	return comm_agree(values, n, o);
+}
+
+/* all ranks' device work up to here is complete when the call returns on any rank */
+extern "C" int cg_comm_barrier(void)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx) return CG_EINVAL;
+	if (!g_comm.ready) return cg_set_error(CG_EINVAL, "cg_comm_init() has not been called");
+	CG_CUDA(cudaStreamSynchronize(ctx->compute));
+	int64_t one = 1;
+	int rc = comm_agree(&one, 1, ncclSum);
+	if (rc) return rc;
+	return CG_OK;
+}
+
+/* ---------------------------------------------------------------------------------- *
+ *  Combine.
+ * ---------------------------------------------------------------------------------- */
+/* the words behind an accumulator array that travel with it: [0] rows pending in packed words,
+ * [1 + b] number of ranks whose kernels raised error bit b */
+__global__ void cg_comm_tail_write_kernel(uint64_t *tail, const unsigned long long *stats, int with_pending)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	tail[0] = with_pending ? (uint64_t) (stats[CG_STAT_PACKED_ADDED] - stats[CG_STAT_PACKED_DRAINED]) : 0ull;
+	const unsigned long long flags = stats[2];
+	for (int b = 0; b < 8; b++) tail[1 + b] = (flags >> b) & 1ull;
+	for (int b = 9; b < CG_COMM_TAIL; b++) tail[b] = 0;
+}
+
+__global__ void cg_comm_tail_absorb_kernel(uint64_t *tail, unsigned long long *stats, int with_pending)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	if (with_pending) stats[CG_STAT_PACKED_ADDED] = stats[CG_STAT_PACKED_DRAINED] + tail[0];
+	unsigned long long flags = 0;
+	for (int b = 0; b < 8; b++) if (tail[1 + b]) flags |= 1ull << b;
+	stats[2] |= flags;
+	for (int b = 0; b < CG_COMM_TAIL; b++) tail[b] = 0;
+}
+
+extern "C" int cg_comm_combine(CgPartial *p, int32_t root, int32_t local_status)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx) return CG_EINVAL;
+	if (!g_comm.ready) return cg_set_error(CG_EINVAL, "cg_comm_init() has not been called");
+	if (!p) return cg_set_error(CG_EINVAL, "NULL partial");
+	if (root < 0 || root >= g_comm.nranks) return cg_set_error(CG_EINVAL, "root %d of %d ranks", root, g_comm.nranks);
+	if (g_comm.nranks == 1) return local_status ? cg_set_error(local_status, "rank 0 failed before the combine") : CG_OK;
+
+	bool additive = true;
+	for (int w = 0; w < p->nwords; w++) if (p->wordop[w] != CG_WORD_ADD) additive = false;
+	const bool dense = (p->mode == CG_MODE_DENSE || p->mode == CG_MODE_GLOBAL) && additive;
+
+	if (!dense)
+	{
+		/* sparse keys or min/max words: compacted rows travel to the coordinator rank, which merges them
+		 * (cg_merge_kernel).  The local partial is made current and checked first, so that what the ranks
+		 * agree on includes every kernel-raised error. */
+		int64_t nrows = 0;
+		int st = local_status;
+		if (st == 0) st = cg_partial_ngroups(p, &nrows);
+		const size_t row_bytes = sizeof(int64_t) + sizeof(uint64_t) * (size_t) p->nwords + 8;   /* key + words + NULL flag (padded) */
+		int rc = comm_ensure_small((size_t) 2 * g_comm.nranks + 2);
+		if (rc) return rc;
+		g_comm.h_small[0] = st; g_comm.h_small[1] = nrows;
+		CG_CUDA(cudaMemcpyAsync(g_comm.d_small, g_comm.h_small, 2 * sizeof(int64_t), cudaMemcpyHostToDevice, g_comm.side));
+		CG_NCCL(g_nccl.AllGather(g_comm.d_small, g_comm.d_small + 2, 2, ncclInt64, g_comm.comm, g_comm.side));
+		CG_CUDA(cudaMemcpyAsync(g_comm.h_small + 2, g_comm.d_small + 2, 2 * sizeof(int64_t) * g_comm.nranks, cudaMemcpyDeviceToHost, g_comm.side));
+		CG_CUDA(cudaStreamSynchronize(g_comm.side));
+		std::vector<int64_t> rows(g_comm.nranks);
+		int failed = -1, failed_code = 0;
+		for (int r = 0; r < g_comm.nranks; r++)
+		{
+			rows[r] = g_comm.h_small[2 + 2 * r + 1];
+			if (g_comm.h_small[2 + 2 * r] != 0 && failed < 0) { failed = r; failed_code = (int) g_comm.h_small[2 + 2 * r]; }
+		}
+		if (failed >= 0)
+		{
+			if (failed == g_comm.rank) return failed_code;      /* own message is already set */
+			return cg_set_error(failed_code, "rank %d failed before the combine (code %d)", failed, failed_code);
+		}
+		/* layout of one rank's rows in the gather buffer: keys | words | nulls, each 16-byte aligned */
+		auto seg = [&](int64_t n, size_t *off_words, size_t *off_nulls) {
+			size_t k = ((size_t) n * sizeof(int64_t) + 15) & ~(size_t) 15;
+			size_t w = ((size_t) n * p->nwords * sizeof(uint64_t) + 15) & ~(size_t) 15;
+			size_t z = ((size_t) n + 15) & ~(size_t) 15;
+			*off_words = k; *off_nulls = k + w;
+			return k + w + z;
+		};
+		(void) row_bytes;
+		if (g_comm.rank != root)
+		{
+			size_t ow, on;
+			size_t bytes = seg(nrows, &ow, &on);
+			rc = devbuf_grow(&g_comm.gather, std::max<size_t>(bytes, 64));
+			if (rc) return rc;
+			uint8_t *b = g_comm.gather.p;
+			int64_t got = 0;
+			rc = cg_partial_export_device(p, nrows, (int64_t *) b, b + on, (uint64_t *) (b + ow), &got);
+			if (rc) return rc;
+			if (nrows > 0)
+			{
+				CG_NCCL(g_nccl.Send(b, bytes, ncclUint8, root, g_comm.comm, ctx->compute));
+			}
+			return CG_OK;
+		}
+		size_t total = 0;
+		std::vector<size_t> base(g_comm.nranks, 0);
+		for (int r = 0; r < g_comm.nranks; r++)
+		{
+			if (r == root) continue;
+			size_t ow, on;
+			base[r] = total;
+			total += seg(rows[r], &ow, &on);
+		}
+		rc = devbuf_grow(&g_comm.gather, std::max<size_t>(total, 64));
+		if (rc) return rc;
+		CG_NCCL(g_nccl.GroupStart());
+		for (int r = 0; r < g_comm.nranks; r++)
+		{
+			if (r == root || rows[r] == 0) continue;
+			size_t ow, on;
+			size_t bytes = seg(rows[r], &ow, &on);
+			ncclResult_t e = g_nccl.Recv(g_comm.gather.p + base[r], bytes, ncclUint8, r, g_comm.comm, ctx->compute);
+			if (e != ncclSuccess) { g_nccl.GroupEnd(); return cg_set_error(CG_ECOMM, "ncclRecv failed: %s", g_nccl.GetErrorString(e)); }
+		}
+		CG_NCCL(g_nccl.GroupEnd());
+		for (int r = 0; r < g_comm.nranks; r++)
+		{
+			if (r == root || rows[r] == 0) continue;
+			size_t ow, on;
+			seg(rows[r], &ow, &on);
+			uint8_t *b = g_comm.gather.p + base[r];
+			rc = cg_launch_merge(p, (const int64_t *) b, b + on, (const uint64_t *) (b + ow), rows[r], ctx->compute);
+			if (rc) return rc;
+		}
+		return CG_OK;
+	}
+
+	/* identical direct-indexed layouts with additive words: agree (off the scan stream) on what to reduce */
+	int64_t agree[4] = {local_status, p->wide_dirty ? 1 : 0, p->packed_dirty ? 1 : 0,
+						(int64_t) (p->entries * 1000003ull + (uint64_t) p->stride * 31ull + (uint64_t) p->pack_shift)};
+	int64_t lay_min = agree[3];
+	int rc = comm_agree(agree, 4, ncclMax);
+	if (rc) return rc;
+	if (agree[0] != 0)
+	{
+		if (local_status != 0) return local_status;
+		return cg_set_error((int) agree[0], "another rank failed before the combine (code %d)", (int) agree[0]);
+	}
+	rc = comm_agree(&lay_min, 1, ncclMin);
+	if (rc) return rc;
+	if (lay_min != agree[3]) return cg_set_error(CG_EINVAL, "the partials of the ranks do not share one layout");
+	const bool any_wide = agree[1] != 0, any_packed = agree[2] != 0;
+	if (any_packed && !any_wide && p->d_packed)
+	{
+		/* every rank only wrote packed words: 8 bytes per group travel instead of the wide entry */
+		uint64_t *tail = p->d_packed + p->entries;
+		cg_comm_tail_write_kernel<<<1, 32, 0, ctx->compute>>>(tail, p->d_stats, 1);
+		CG_CUDA(cudaGetLastError()); g_cg_launches++;
+		CG_NCCL(g_nccl.Reduce(p->d_packed, p->d_packed, (size_t) p->entries + CG_COMM_TAIL, ncclInt64, ncclSum, root, g_comm.comm, ctx->compute));
+		if (g_comm.rank == root)
+		{
+			cg_comm_tail_absorb_kernel<<<1, 32, 0, ctx->compute>>>(tail, p->d_stats, 1);
+			CG_CUDA(cudaGetLastError()); g_cg_launches++;
+			p->packed_dirty = true;
+		}
+		return CG_OK;
+	}
+	rc = cg_launch_drain(p, ctx->compute);
+	if (rc) return rc;
+	uint64_t *tail = p->d_table + p->entries * (uint64_t) p->stride;
+	cg_comm_tail_write_kernel<<<1, 32, 0, ctx->compute>>>(tail, p->d_stats, 0);
+	CG_CUDA(cudaGetLastError()); g_cg_launches++;
+	CG_NCCL(g_nccl.Reduce(p->d_table, p->d_table, (size_t) (p->entries * (uint64_t) p->stride) + CG_COMM_TAIL, ncclInt64, ncclSum, root,
+						  g_comm.comm, ctx->compute));
+	if (g_comm.rank == root)
+	{
+		cg_comm_tail_absorb_kernel<<<1, 32, 0, ctx->compute>>>(tail, p->d_stats, 0);
+		CG_CUDA(cudaGetLastError()); g_cg_launches++;
+		p->wide_dirty = true;
+	}
+	return CG_OK;
+}
+
+/* ---------------------------------------------------------------------------------- *
+ *  Repartition exchange.
+ * ---------------------------------------------------------------------------------- */
+/* partition p is owned by rank p mod nranks (the reference assigns merge tasks round-robin over the worker
+ * nodes, planner/multi_physical_planner.c:4826-4950); positions in the send buffer are destination-major */
+extern "C" int cg_comm_exchange_plan(int32_t P, int32_t nranks, int32_t rank, const int64_t *counts /* [nranks][P] */,
+									 int32_t *position /* [P] */, int64_t *send_rows /* [nranks] */,
+									 int64_t *recv_rows /* [nranks] */, int64_t *local_part_counts /* [nlocal][nranks] */,
+									 int32_t *nlocal_out)
+{
+	if (P < 1 || nranks < 1 || rank < 0 || rank >= nranks || !position) return cg_set_error(CG_EINVAL, "bad exchange plan arguments");
+	int pos = 0;
+	for (int r = 0; r < nranks; r++)
+		for (int p = r; p < P; p += nranks) position[p] = pos++;
+	int nlocal = 0;
+	for (int p = rank; p < P; p += nranks) nlocal++;
+	if (nlocal_out) *nlocal_out = nlocal;
+	if (!counts) return CG_OK;
+	for (int r = 0; r < nranks; r++)
+	{
+		int64_t s = 0, v = 0;
+		for (int p = r; p < P; p += nranks) s += counts[(size_t) rank * P + p];      /* what this rank routes to r */
+		for (int p = rank; p < P; p += nranks) v += counts[(size_t) r * P + p];      /* what r routes to this rank */
+		if (send_rows) send_rows[r] = s;
+		if (recv_rows) recv_rows[r] = v;
+	}
+	if (local_part_counts)
+	{
+		int i = 0;
+		for (int p = rank; p < P; p += nranks, i++)
+			for (int r = 0; r < nranks; r++) local_part_counts[(size_t) i * nranks + r] = counts[(size_t) r * P + p];
+	}
+	return CG_OK;
+}
+
+extern "C" int cg_comm_repartition_exchange(int32_t slot, const int64_t *const *d_cols, const uint8_t *d_key_nulls, int64_t n,
+											int32_t ncols, int32_t key_len, int32_t P, const int32_t *mins, const int32_t *maxs,
+											int64_t *recv_rows_out)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx) return CG_EINVAL;
+	if (!g_comm.ready) return cg_set_error(CG_EINVAL, "cg_comm_init() has not been called");
+	if (slot < 0 || slot >= 4) return cg_set_error(CG_EINVAL, "slot %d", slot);
+	if (ncols < 1 || ncols > 8 || !d_cols || n < 0) return cg_set_error(CG_EINVAL, "bad argument");
+	CgComm::Slot &S = g_comm.slots[slot];
+	const int W = g_comm.nranks, me = g_comm.rank;
+	if (!S.done)
+	{
+		CG_CUDA(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
+		CG_CUDA(cudaEventCreate(&S.t0));
+		CG_CUDA(cudaEventCreate(&S.t1));
+	}
+	/* routing (hashint4/8 -> token ranges) and the histogram, on the compute stream */
+	int rc = devbuf_grow(&S.index, (size_t) std::max<int64_t>(n, 1) * sizeof(int32_t) + (size_t) (P + 1) * sizeof(int64_t) + 64);
+	if (rc) return rc;
+	int32_t *d_index = (int32_t *) S.index.p;
+	int64_t *d_counts = (int64_t *) (S.index.p + (((size_t) std::max<int64_t>(n, 1) * sizeof(int32_t) + 15) & ~(size_t) 15));
+	rc = cg_partition_index_async(d_cols[0], d_key_nulls, n, key_len, 1, mins, maxs, P, d_index, d_counts);
+	if (rc) return rc;
+	CG_CUDA(cudaEventRecord(g_comm.ev_index, ctx->compute));
+	/* the counts of every rank, exchanged on the side stream while the scatter runs */
+	rc = comm_ensure_small((size_t) P * (W + 1) + 8);
+	if (rc) return rc;
+	CG_CUDA(cudaStreamWaitEvent(g_comm.side, g_comm.ev_index, 0));
+	if (W > 1)
+		CG_NCCL(g_nccl.AllGather(d_counts, g_comm.d_small, (size_t) P, ncclInt64, g_comm.comm, g_comm.side));
+	else
+		CG_CUDA(cudaMemcpyAsync(g_comm.d_small, d_counts, sizeof(int64_t) * P, cudaMemcpyDeviceToDevice, g_comm.side));
+	CG_CUDA(cudaMemcpyAsync(g_comm.h_small, g_comm.d_small, sizeof(int64_t) * P * W, cudaMemcpyDeviceToHost, g_comm.side));
+	/* scatter into destination-major order */
+	std::vector<int32_t> position(P);
+	int nlocal = 0;
+	cg_comm_exchange_plan(P, W, me, nullptr, position.data(), nullptr, nullptr, nullptr, &nlocal);
+	rc = devbuf_grow(&S.send, (size_t) std::max<int64_t>(n, 1) * sizeof(int64_t) * ncols);
+	if (rc) return rc;
+	std::vector<int64_t *> outs(ncols);
+	for (int c = 0; c < ncols; c++) outs[c] = (int64_t *) S.send.p + (size_t) c * n;
+	rc = cg_partition_scatter_async(d_index, n, P, position.data(), d_cols, ncols, outs.data());
+	if (rc) return rc;
+	CG_CUDA(cudaEventRecord(g_comm.ev_scatter, ctx->compute));
+	CG_CUDA(cudaStreamSynchronize(g_comm.side));               /* counts are on the host; the scatter keeps running */
+	std::vector<int64_t> counts((size_t) W * P), send_rows(W), recv_rows(W);
+	int64_t unroutable = 0;
+	for (int r = 0; r < W; r++)
+	{
+		memcpy(&counts[(size_t) r * P], g_comm.h_small + (size_t) r * (P + 1), sizeof(int64_t) * P);
+		unroutable += g_comm.h_small[(size_t) r * (P + 1) + P];
+	}
+	if (unroutable)         /* every rank sees the same counters: all fail together, nobody waits in the exchange */
+		return cg_set_error(CG_EINVAL, "could not find shard for partition column value (%lld rows)", (long long) unroutable);
+	S.part_counts.assign((size_t) std::max(nlocal, 1) * W, 0);
+	cg_comm_exchange_plan(P, W, me, counts.data(), position.data(), send_rows.data(), recv_rows.data(), S.part_counts.data(), &nlocal);
+	int64_t total_recv = 0;
+	for (int r = 0; r < W; r++) total_recv += recv_rows[r];
+	rc = devbuf_grow(&S.recv, (size_t) std::max<int64_t>(total_recv, 1) * sizeof(int64_t) * ncols);
+	if (rc) return rc;
+	S.recv_rows = total_recv;
+	S.ncols = ncols;
+	S.sent_bytes = 0;
+	CG_CUDA(cudaStreamWaitEvent(g_comm.side, g_comm.ev_scatter, 0));
+	CG_CUDA(cudaEventRecord(S.t0, g_comm.side));
+	if (W == 1)
+	{
+		for (int c = 0; c < ncols; c++)
+			CG_CUDA(cudaMemcpyAsync((int64_t *) S.recv.p + (size_t) c * total_recv, outs[c], sizeof(int64_t) * (size_t) n,
+									cudaMemcpyDeviceToDevice, g_comm.side));
+	}
+	else
+	{
+		/* one group for all columns and all peers: NCCL fuses it into one all-to-all over NVLink */
+		CG_NCCL(g_nccl.GroupStart());
+		int64_t soff = 0, roff = 0;
+		for (int r = 0; r < W; r++)
+		{
+			for (int c = 0; c < ncols; c++)
+			{
+				ncclResult_t e = ncclSuccess;
+				if (send_rows[r] > 0)
+					e = g_nccl.Send(outs[c] + soff, (size_t) send_rows[r], ncclInt64, r, g_comm.comm, g_comm.side);
+				if (e == ncclSuccess && recv_rows[r] > 0)
+					e = g_nccl.Recv((int64_t *) S.recv.p + (size_t) c * total_recv + roff, (size_t) recv_rows[r], ncclInt64, r, g_comm.comm,
+									g_comm.side);
+				if (e != ncclSuccess) { g_nccl.GroupEnd(); return cg_set_error(CG_ECOMM, "ncclSend/Recv failed: %s", g_nccl.GetErrorString(e)); }
+			}
+			if (r != me) S.sent_bytes += (uint64_t) send_rows[r] * sizeof(int64_t) * ncols;
+			soff += send_rows[r]; roff += recv_rows[r];
+		}
+		CG_NCCL(g_nccl.GroupEnd());
+	}
+	CG_CUDA(cudaEventRecord(S.t1, g_comm.side));
+	CG_CUDA(cudaEventRecord(S.done, g_comm.side));
+	if (recv_rows_out) *recv_rows_out = total_recv;
+	return CG_OK;
+}
+
+/* the compute stream (the join that follows) waits for the slot's exchange on the device; the host does not block */
+extern "C" int cg_comm_exchange_wait(int32_t slot)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx) return CG_EINVAL;
+	if (slot < 0 || slot >= 4 || !g_comm.slots[slot].done) return cg_set_error(CG_EINVAL, "no exchange in slot %d", slot);
+	CG_CUDA(cudaStreamWaitEvent(ctx->compute, g_comm.slots[slot].done, 0));
+	return CG_OK;
+}
+
+extern "C" int cg_comm_exchange_result(int32_t slot, int64_t **d_cols /* [ncols] */, int64_t *nrows, int64_t *part_counts,
+									   int32_t *nlocal, uint64_t *sent_bytes, double *exchange_ms)
+{
+	if (slot < 0 || slot >= 4 || !g_comm.slots[slot].done) return cg_set_error(CG_EINVAL, "no exchange in slot %d", slot);
+	CgComm::Slot &S = g_comm.slots[slot];
+	if (d_cols) for (int c = 0; c < S.ncols; c++) d_cols[c] = (int64_t *) S.recv.p + (size_t) c * S.recv_rows;
+	if (nrows) *nrows = S.recv_rows;
+	if (nlocal) *nlocal = (int32_t) (S.part_counts.size() / (size_t) g_comm.nranks);
+	if (part_counts) memcpy(part_counts, S.part_counts.data(), S.part_counts.size() * sizeof(int64_t));
+	if (sent_bytes) *sent_bytes = S.sent_bytes;
+	if (exchange_ms)
+	{
+		CG_CUDA(cudaEventSynchronize(S.t1));
+		float ms = 0;
+		CG_CUDA(cudaEventElapsedTime(&ms, S.t0, S.t1));
+		*exchange_ms = ms;
+	}
+	return CG_OK;
+}

@@ -821,19 +821,33 @@ static int check_error_flags(CgPartial *p, unsigned long long flags)
 	return CG_OK;
 }
 
+/* CG_PACK_DRAIN_EVERY = n restores a drain every n packed launches (A/B measurements) */
 static int drain_every(void)
 {
-	static int v = -1;
-	if (v < 0) { const char *e = getenv("CG_PACK_DRAIN_EVERY"); v = e ? atoi(e) : 4; if (v < 1) v = 1; }
+	static int v = -2;
+	if (v == -2) { const char *e = getenv("CG_PACK_DRAIN_EVERY"); v = e ? atoi(e) : 0; if (v < 0) v = 0; }
 	return v;
 }
 
-/* bookkeeping after a scan launch that may have used the packed words */
-static int after_packed_launch(CgContext *ctx, CgPartial *p, bool used_packed)
+/*
+ * Bookkeeping after a scan launch.  Packed words are drained into the wide accumulators when a group could
+ * have come near 2^C rows since the last drain: rows scanned since then exceed capacity * 2^C / 32 (uniform
+ * keys would be a factor 32 under the limit; a skewed key that still overflows is detected exactly and
+ * reported as CG_ERETRY_UNPACKED).  For C2 (1 M groups, C = 16) that is 2 G rows: a 1 B-row query never
+ * drains before its result is read, and a combine can ship the 8-byte packed words alone.
+ * packed_only = the launch wrote nothing but packed words.
+ */
+static int after_launch(CgContext *ctx, CgPartial *p, bool used_packed, bool packed_only, uint64_t rows)
 {
+	if (!(used_packed && packed_only)) p->wide_dirty = true;
 	if (!used_packed) return CG_OK;
 	p->packed_dirty = true;
-	if (++p->launches_since_drain >= drain_every()) return cg_launch_drain(p, ctx->compute);
+	p->launches_since_drain++;
+	p->rows_since_drain += rows;
+	const int every = drain_every();
+	if (every > 0) return p->launches_since_drain >= every ? cg_launch_drain(p, ctx->compute) : CG_OK;
+	const double limit = (double) p->capacity * (double) (1ull << p->pack_shift) / 32.0;
+	if ((double) p->rows_since_drain > limit) return cg_launch_drain(p, ctx->compute);
 	return CG_OK;
 }
 
@@ -873,6 +887,7 @@ extern "C" int cg_scan_shard(const CgShard *sh, const CgScanDesc *desc, CgPartia
 	if (!same)
 	{
 		std::vector<uint32_t> fastl, slowl;
+		uint64_t rows_fast = 0, rows_slow = 0;
 		uint32_t nullmask = 0;
 		fastl.reserve(sh->nchunkgroups);
 		int64_t nfiltered = 0;
@@ -894,6 +909,7 @@ extern "C" int cg_scan_shard(const CgShard *sh, const CgScanDesc *desc, CgPartia
 					if (d.value_count != d.row_count) { nulls = true; nullmask |= 1u << c; }
 				}
 				(nulls ? slowl : fastl).push_back((uint32_t) cg);
+				(nulls ? rows_slow : rows_fast) += sh->cg_rows[cg];
 			}
 		}
 		msh->sel_nfast = (uint32_t) fastl.size();
@@ -906,6 +922,8 @@ extern "C" int cg_scan_shard(const CgShard *sh, const CgScanDesc *desc, CgPartia
 		msh->sel_pushdown = desc->enable_qual_pushdown;
 		msh->sel_nquals = desc->nquals;
 		msh->sel_nullmask = nullmask;
+		msh->sel_rows_fast = rows_fast;
+		msh->sel_rows_total = rows_fast + rows_slow;
 		msh->sel_nqexpr = desc->nqual_expr;
 		memcpy(msh->sel_qexpr, desc->qual_expr, (size_t) desc->nqual_expr);
 		memcpy(msh->sel_quals, desc->quals, sizeof(CgQual) * desc->nquals);
@@ -944,7 +962,7 @@ extern "C" int cg_scan_shard(const CgShard *sh, const CgScanDesc *desc, CgPartia
 			fast.nselected = nfast;
 			rc = cg_launch_scan_fast(ctx, fast, ctx->compute);
 			if (rc) return rc;
-			rc = after_packed_launch(ctx, into, fast.packed != nullptr);
+			rc = after_launch(ctx, into, fast.packed != nullptr, fast.nsums == 1, sh->sel_rows_fast);
 			if (rc) return rc;
 		}
 		else if (nfast > 0 && !cg_force_general())
@@ -952,13 +970,12 @@ extern "C" int cg_scan_shard(const CgShard *sh, const CgScanDesc *desc, CgPartia
 			/* no ahead-of-time specialisation for this shape: the plan-specialised (NVRTC) kernel */
 			KPlan piece = plan;
 			piece.nselected = nfast;
-			bool launched = false, packed = false;
-			rc = cg_launch_scan_jit(ctx, piece, 0u, ctx->compute, &launched, &packed);
+			bool launched = false, packed = false, ponly = false;
+			rc = cg_launch_scan_jit(ctx, piece, 0u, ctx->compute, &launched, &packed, &ponly);
 			if (rc) return rc;
-			if (launched && packed)
+			if (launched)
 			{
-				into->packed_dirty = true;
-				rc = after_packed_launch(ctx, into, true);
+				rc = after_launch(ctx, into, packed, ponly, sh->sel_rows_fast);
 				if (rc) return rc;
 			}
 			if (!launched) nfast = 0;
@@ -972,15 +989,14 @@ extern "C" int cg_scan_shard(const CgShard *sh, const CgScanDesc *desc, CgPartia
 			 * kernels only when the JIT is off or unavailable */
 			plan.selected = sh->d_selected + nfast;
 			plan.nselected -= nfast;
-			bool launched = false, packed = false;
+			bool launched = false, packed = false, ponly = false;
 			if (!cg_force_general())
 			{
-				rc = cg_launch_scan_jit(ctx, plan, sh->sel_nullmask ? sh->sel_nullmask : ~0u, ctx->compute, &launched, &packed);
+				rc = cg_launch_scan_jit(ctx, plan, sh->sel_nullmask ? sh->sel_nullmask : ~0u, ctx->compute, &launched, &packed, &ponly);
 				if (rc) return rc;
-				if (launched && packed)
+				if (launched)
 				{
-					into->packed_dirty = true;
-					rc = after_packed_launch(ctx, into, true);
+					rc = after_launch(ctx, into, packed, ponly, sh->sel_rows_total - sh->sel_rows_fast);
 					if (rc) return rc;
 				}
 			}
@@ -989,6 +1005,7 @@ extern "C" int cg_scan_shard(const CgShard *sh, const CgScanDesc *desc, CgPartia
 				if (use_small) rc = cg_launch_scan_small(ctx, plan, all8, ctx->compute);
 				else rc = cg_launch_scan(ctx, plan, true, all8, ctx->compute);
 				if (rc) return rc;
+				into->wide_dirty = true;
 			}
 		}
 		rc = cg_prof_mark(ctx, ctx->compute);
@@ -1305,6 +1322,7 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 				}
 		if (stats) CG_CUDA(cudaEventRecord(ctx->ev_a, ctx->compute));
 		bool decode_done = false;          /* the DMA path may decode on a side stream before launch_block runs */
+		auto block_rows = [&](uint64_t cg0, uint64_t cg1) { uint64_t n = 0; for (uint64_t g = cg0; g < cg1; g++) n += sp.cg_rows[g]; return n; };
 		auto launch_block = [&](uint64_t cg0, uint64_t cg1, cudaEvent_t copied) -> int {
 			CG_CUDA(cudaStreamWaitEvent(ctx->compute, copied, 0));
 			/* K7: compressed value streams of the block -> their value slots */
@@ -1326,10 +1344,10 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 				KPlan blk = plan;
 				blk.selected = d_ids + cg0;
 				blk.nselected = (uint32_t) (cg1 - cg0);
-				bool packed = false;
-				r = cg_launch_scan_jit(ctx, blk, nullable, ctx->compute, &jitted, &packed);
+				bool packed = false, ponly = false;
+				r = cg_launch_scan_jit(ctx, blk, nullable, ctx->compute, &jitted, &packed, &ponly);
 				if (r) return r;
-				if (jitted && packed) into->packed_dirty = true;
+				if (jitted) { r = after_launch(ctx, into, packed, ponly, block_rows(cg0, cg1)); if (r) return r; }
 			}
 			if (jitted) { }
 			else if (use_small)
@@ -1338,6 +1356,7 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 				blk.selected = d_ids + cg0;
 				blk.nselected = (uint32_t) (cg1 - cg0);
 				r = cg_launch_scan_small(ctx, blk, all8, ctx->compute);
+				into->wide_dirty = true;
 			}
 			else if (use_fast)
 			{
@@ -1345,7 +1364,7 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 				blk.selected = d_ids + cg0;
 				blk.nselected = (uint32_t) (cg1 - cg0);
 				r = cg_launch_scan_fast(ctx, blk, ctx->compute);
-				if (r == CG_OK && blk.packed) into->packed_dirty = true;
+				if (r == CG_OK) r = after_launch(ctx, into, blk.packed != nullptr, blk.nsums == 1, block_rows(cg0, cg1));
 			}
 			else
 			{
@@ -1353,6 +1372,7 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 				blk.selected = d_ids + cg0;
 				blk.nselected = (uint32_t) (cg1 - cg0);
 				r = cg_launch_scan(ctx, blk, sp.any_nulls, all8, ctx->compute);
+				into->wide_dirty = true;
 			}
 			if (r) return r;
 			return cg_prof_mark(ctx, ctx->compute);

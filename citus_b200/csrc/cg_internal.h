@@ -134,6 +134,7 @@ struct CgShard
 	/* the list is ordered [chunk groups without NULLs in the plan columns | the rest] */
 	std::vector<uint8_t> sel_slots;
 	uint32_t sel_nfast = 0;
+	uint64_t sel_rows_fast = 0, sel_rows_total = 0;   /* rows of the first part / of the whole selection */
 	uint64_t algorithmic_bytes_per_cg_col(uint64_t cg, int slot) const
 	{
 		const DevChunkCol &c = h_chunkcols[cg * staged.size() + slot];
@@ -263,6 +264,7 @@ struct FPlan
 #define CG_ERRFLAG_KEY_RANGE 4ull
 #define CG_ERRFLAG_SUM_BOUND 8ull
 #define CG_ERRFLAG_DECOMPRESS 16ull
+#define CG_COMM_TAIL 16           /* words behind an accumulator array that travel with it in a combine (cg_comm.cu) */
 #define CG_STAT_PACKED_ADDED 3
 #define CG_STAT_PACKED_DRAINED 4
 
@@ -290,7 +292,9 @@ struct CgPartial
 	int pack_word = 0;
 	bool packing_enabled = false;
 	bool packed_dirty = false;
+	bool wide_dirty = false;        /* the wide accumulator words hold something (not only the packed words) */
 	int launches_since_drain = 0;
+	uint64_t rows_since_drain = 0;  /* rows scanned into packed words since the last drain (upper bound) */
 	/* scratch for export */
 	int64_t *d_out_keys = nullptr;
 	uint64_t *d_out_words = nullptr;
@@ -347,7 +351,15 @@ int cg_jit_level(void);
 void cg_jit_set_level(int level);     /* CG_JIT: 0 = off, 1 = where no specialised ahead-of-time kernel applies (default), 2 = always */
 /* nullable: bit c set = plan column c may have NULLs in the chunk groups of this launch (the kernel then reads
  * its exists bitmap + rank directory wherever a chunk's value_count differs from its row count) */
-int cg_launch_scan_jit(CgContext *ctx, const KPlan &plan, uint32_t nullable, cudaStream_t stream, bool *launched, bool *used_packed);
+int cg_launch_scan_jit(CgContext *ctx, const KPlan &plan, uint32_t nullable, cudaStream_t stream, bool *launched, bool *used_packed,
+					   bool *packed_only = nullptr);
+
+/* cg_partition.cu: the same without host synchronisation (counts stay on the device; d_counts has P + 1 words,
+ * the last one counts rows whose hash fell in no interval) */
+int cg_partition_index_async(const int64_t *d_keys, const uint8_t *d_nulls, int64_t n, int32_t key_len, int32_t by_hash,
+							 const int32_t *mins, const int32_t *maxs, int32_t P, int32_t *d_index, int64_t *d_counts);
+int cg_partition_scatter_async(const int32_t *d_index, int64_t n, int32_t P, const int32_t *h_order, const int64_t *const *d_cols,
+							   int32_t ncols, int64_t *const *d_out);
 
 /* cg_plan.cpp */
 int cg_partial_shape(CgPartial *p, const CgScanDesc *desc, const CgColumnDesc *columns, int32_t natts,

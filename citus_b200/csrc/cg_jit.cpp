@@ -850,10 +850,12 @@ int cg_jit_source_for(const KPlan &plan, uint32_t nullable, std::string *src, in
  * (and CG_OK) when the JIT is unavailable -- the caller then uses its ahead-of-time kernels.
  * *used_packed tells the caller that packed words were written.
  */
-int cg_launch_scan_jit(CgContext *ctx, const KPlan &plan, uint32_t nullable, cudaStream_t stream, bool *launched, bool *used_packed)
+int cg_launch_scan_jit(CgContext *ctx, const KPlan &plan, uint32_t nullable, cudaStream_t stream, bool *launched, bool *used_packed,
+					   bool *packed_only)
 {
 	*launched = false;
 	*used_packed = false;
+	if (packed_only) *packed_only = false;
 	if (cg_jit_level() <= 0 || plan.nselected == 0) return CG_OK;
 	if (!load_rtc() || !load_drv()) return CG_OK;
 	JitShape sh;
@@ -921,6 +923,15 @@ int cg_launch_scan_jit(CgContext *ctx, const KPlan &plan, uint32_t nullable, cud
 	}
 	*launched = true;
 	*used_packed = sh.packed;
+	if (packed_only && sh.packed)
+	{
+		/* nothing but the packed word is written when the plan is count(*) + the packed sum over NULL-free inputs */
+		bool only = true;
+		for (int a = 0; a < plan.naggs; a++)
+			if (plan.aggs[a].kind != CG_AGG_COUNT_STAR && a != sh.pack_agg) only = false;
+		if (!agg_null_expr(plan.aggs[sh.pack_agg], sh).empty()) only = false;
+		*packed_only = only;
+	}
 	return CG_OK;
 }
 

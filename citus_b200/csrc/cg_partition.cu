@@ -19,6 +19,9 @@
  * src/backend/access/hash/hashfunc.c (Jenkins lookup3 final mix); pinned by the
  * reference goldens through the oracle (tests/test_oracle_golden.py).
  */
+#include <algorithm>
+#include <vector>
+
 #include "cg_internal.h"
 
 #define CGP_THREADS 256
@@ -216,27 +219,31 @@ cg_partition_scatter_kernel(const __grid_constant__ ScatterParams A)
 static int32_t *g_d_bounds = nullptr;
 static int g_bounds_cap = 0;
 
-extern "C" int cg_partition_index(const int64_t *d_keys, const uint8_t *d_nulls, int64_t n, int32_t key_len,
-								  int32_t by_hash, const int32_t *mins, const int32_t *maxs, int32_t P,
-								  int32_t *d_index, int64_t *d_counts)
+static int partition_index_enqueue(CgContext *ctx, const int64_t *d_keys, const uint8_t *d_nulls, int64_t n, int32_t key_len,
+								   int32_t by_hash, const int32_t *mins, const int32_t *maxs, int32_t P, int32_t *d_index,
+								   int64_t *d_counts, unsigned long long *d_err)
 {
-	CgContext *ctx = cg_ctx();
-	if (!ctx) return CG_EINVAL;
 	if (P <= 0) return cg_set_error(CG_EINVAL, "number of partitions cannot be 0");
 	if (P > CGP_MAX_P) return cg_set_error(CG_EUNSUPPORTED, "more than %d partitions", CGP_MAX_P);
 	if (key_len != 4 && key_len != 8) return cg_set_error(CG_EINVAL, "key_len must be 4 or 8");
-	if (n < 0 || !d_keys || !d_index || !d_counts || !mins || !maxs) return cg_set_error(CG_EINVAL, "bad argument");
+	if (n < 0 || (n > 0 && !d_keys) || !d_index || !d_counts || !mins || !maxs) return cg_set_error(CG_EINVAL, "bad argument");
 	if (g_bounds_cap < 2 * P + 2)
 	{
 		cudaFree(g_d_bounds);
 		CG_CUDA(cudaMalloc(&g_d_bounds, sizeof(int32_t) * (2 * CGP_MAX_P + 2)));
 		g_bounds_cap = 2 * CGP_MAX_P + 2;
 	}
-	CG_CUDA(cudaMemcpyAsync(g_d_bounds, mins, sizeof(int32_t) * P, cudaMemcpyHostToDevice, ctx->compute));
-	CG_CUDA(cudaMemcpyAsync(g_d_bounds + CGP_MAX_P, maxs, sizeof(int32_t) * P, cudaMemcpyHostToDevice, ctx->compute));
-	CgAsyncBuf err_buf;
-	CG_CUDA(err_buf.alloc(sizeof(unsigned long long), ctx->compute));
-	unsigned long long *d_err = err_buf.as<unsigned long long>();
+	/* the interval bounds go through a pinned bounce buffer: a pageable source would make the copy synchronous */
+	static int32_t *h_bounds = nullptr;
+	if (!h_bounds) CG_CUDA(cudaHostAlloc((void **) &h_bounds, sizeof(int32_t) * 2 * CGP_MAX_P, cudaHostAllocDefault));
+	static cudaEvent_t bounds_free = nullptr;
+	if (!bounds_free) CG_CUDA(cudaEventCreateWithFlags(&bounds_free, cudaEventDisableTiming));
+	CG_CUDA(cudaEventSynchronize(bounds_free));
+	memcpy(h_bounds, mins, sizeof(int32_t) * P);
+	memcpy(h_bounds + CGP_MAX_P, maxs, sizeof(int32_t) * P);
+	CG_CUDA(cudaMemcpyAsync(g_d_bounds, h_bounds, sizeof(int32_t) * P, cudaMemcpyHostToDevice, ctx->compute));
+	CG_CUDA(cudaMemcpyAsync(g_d_bounds + CGP_MAX_P, h_bounds + CGP_MAX_P, sizeof(int32_t) * P, cudaMemcpyHostToDevice, ctx->compute));
+	CG_CUDA(cudaEventRecord(bounds_free, ctx->compute));
 	CG_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned long long), ctx->compute));
 	CG_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int64_t) * P, ctx->compute));
 	if (n > 0)
@@ -249,6 +256,29 @@ extern "C" int cg_partition_index(const int64_t *d_keys, const uint8_t *d_nulls,
 		cg_partition_index_kernel<<<(unsigned) nblocks, CGP_THREADS, 3 * P * sizeof(int32_t), ctx->compute>>>(A);
 		CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	}
+	return CG_OK;
+}
+
+int cg_partition_index_async(const int64_t *d_keys, const uint8_t *d_nulls, int64_t n, int32_t key_len, int32_t by_hash,
+							 const int32_t *mins, const int32_t *maxs, int32_t P, int32_t *d_index, int64_t *d_counts)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx) return CG_EINVAL;
+	return partition_index_enqueue(ctx, d_keys, d_nulls, n, key_len, by_hash, mins, maxs, P, d_index, d_counts,
+								   (unsigned long long *) (d_counts + P));
+}
+
+extern "C" int cg_partition_index(const int64_t *d_keys, const uint8_t *d_nulls, int64_t n, int32_t key_len,
+								  int32_t by_hash, const int32_t *mins, const int32_t *maxs, int32_t P,
+								  int32_t *d_index, int64_t *d_counts)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx) return CG_EINVAL;
+	CgAsyncBuf err_buf;
+	CG_CUDA(err_buf.alloc(sizeof(unsigned long long), ctx->compute));
+	unsigned long long *d_err = err_buf.as<unsigned long long>();
+	int rc = partition_index_enqueue(ctx, d_keys, d_nulls, n, key_len, by_hash, mins, maxs, P, d_index, d_counts, d_err);
+	if (rc) return rc;
 	unsigned long long err = 0;
 	CG_CUDA(cudaMemcpyAsync(&err, d_err, sizeof err, cudaMemcpyDeviceToHost, ctx->compute));
 	CG_CUDA(cudaStreamSynchronize(ctx->compute));
@@ -315,12 +345,11 @@ __global__ void cg_block_count_kernel(const int32_t *index, const int32_t *order
 	for (int p = threadIdx.x; p < P; p += CGP_THREADS) block_counts[(uint64_t) blockIdx.x * P + p] = s_count[p];
 }
 
-extern "C" int cg_partition_scatter_ordered(const int32_t *d_index, int64_t n, int32_t P, const int32_t *h_order,
-											const int64_t *const *d_cols, int32_t ncols, int64_t *const *d_out,
-											int64_t *h_offsets)
+/* enqueues histogram -> scan -> scatter on the compute stream; *d_base_out (device, [P + 1], valid until the
+ * scratch is returned to the pool in stream order) are the partition offsets in output order */
+static int partition_scatter_enqueue(CgContext *ctx, const int32_t *d_index, int64_t n, int32_t P, const int32_t *h_order,
+									 const int64_t *const *d_cols, int32_t ncols, int64_t *const *d_out, int64_t *h_offsets)
 {
-	CgContext *ctx = cg_ctx();
-	if (!ctx) return CG_EINVAL;
 	if (P <= 0 || P > CGP_MAX_P) return cg_set_error(CG_EINVAL, "bad partition count %d", P);
 	if (ncols < 0 || ncols > 8) return cg_set_error(CG_EUNSUPPORTED, "at most 8 payload columns per call");
 	if (n < 0) return cg_set_error(CG_EINVAL, "negative row count");
@@ -343,9 +372,17 @@ extern "C" int cg_partition_scatter_ordered(const int32_t *d_index, int64_t n, i
 	CG_CUDA(cudaMemsetAsync(d_tot, 0, sizeof(unsigned long long) * (2 * P + 1), ctx->compute));
 	if (h_order)
 	{
+		/* P ints as a kernel-argument-sized copy: through a pinned bounce buffer so that the copy is asynchronous */
+		static int32_t *h_pin = nullptr;
+		static cudaEvent_t pin_free = nullptr;
+		if (!h_pin) CG_CUDA(cudaHostAlloc((void **) &h_pin, sizeof(int32_t) * CGP_MAX_P, cudaHostAllocDefault));
+		if (!pin_free) CG_CUDA(cudaEventCreateWithFlags(&pin_free, cudaEventDisableTiming));
+		CG_CUDA(cudaEventSynchronize(pin_free));
+		memcpy(h_pin, h_order, sizeof(int32_t) * P);
 		CG_CUDA(order_buf.alloc(sizeof(int32_t) * P, ctx->compute));
 		d_order = order_buf.as<int32_t>();
-		CG_CUDA(cudaMemcpyAsync(d_order, h_order, sizeof(int32_t) * P, cudaMemcpyHostToDevice, ctx->compute));
+		CG_CUDA(cudaMemcpyAsync(d_order, h_pin, sizeof(int32_t) * P, cudaMemcpyHostToDevice, ctx->compute));
+		CG_CUDA(cudaEventRecord(pin_free, ctx->compute));
 	}
 	if (n > 0)
 	{
@@ -369,11 +406,32 @@ extern "C" int cg_partition_scatter_ordered(const int32_t *d_index, int64_t n, i
 		cg_partition_scatter_kernel<<<(unsigned) nblocks, CGP_THREADS, (CGP_THREADS / 32) * P * sizeof(unsigned long long), ctx->compute>>>(S);
 		CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	}
-	std::vector<unsigned long long> base(P + 1, 0);
-	CG_CUDA(cudaMemcpyAsync(base.data(), d_base, sizeof(unsigned long long) * (P + 1), cudaMemcpyDeviceToHost, ctx->compute));
-	CG_CUDA(cudaStreamSynchronize(ctx->compute));
-	for (int p = 0; p <= P; p++) h_offsets[p] = (int64_t) base[p];
+	if (h_offsets)
+	{
+		std::vector<unsigned long long> base(P + 1, 0);
+		CG_CUDA(cudaMemcpyAsync(base.data(), d_base, sizeof(unsigned long long) * (P + 1), cudaMemcpyDeviceToHost, ctx->compute));
+		CG_CUDA(cudaStreamSynchronize(ctx->compute));
+		for (int p = 0; p <= P; p++) h_offsets[p] = (int64_t) base[p];
+	}
 	return CG_OK;
+}
+
+int cg_partition_scatter_async(const int32_t *d_index, int64_t n, int32_t P, const int32_t *h_order, const int64_t *const *d_cols,
+							   int32_t ncols, int64_t *const *d_out)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx) return CG_EINVAL;
+	return partition_scatter_enqueue(ctx, d_index, n, P, h_order, d_cols, ncols, d_out, nullptr);
+}
+
+extern "C" int cg_partition_scatter_ordered(const int32_t *d_index, int64_t n, int32_t P, const int32_t *h_order,
+											const int64_t *const *d_cols, int32_t ncols, int64_t *const *d_out,
+											int64_t *h_offsets)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx) return CG_EINVAL;
+	if (!h_offsets) return cg_set_error(CG_EINVAL, "NULL offsets");
+	return partition_scatter_enqueue(ctx, d_index, n, P, h_order, d_cols, ncols, d_out, h_offsets);
 }
 
 extern "C" int cg_partition_scatter(const int32_t *d_index, int64_t n, int32_t P, const int64_t *const *d_cols,

@@ -229,7 +229,8 @@ extern "C" int cg_partial_create(const CgScanDesc *desc, const CgColumnDesc *col
 	CgPartial *p = new CgPartial();
 	int rc = cg_partial_shape(p, desc, columns, natts, key_min, key_max, max_rows);
 	if (rc) { delete p; return rc; }
-	size_t bytes = (size_t) p->entries * p->stride * sizeof(uint64_t);
+	/* CG_COMM_TAIL words behind the accumulator words travel with them in a combine (cg_comm.cu) */
+	size_t bytes = ((size_t) p->entries * p->stride + CG_COMM_TAIL) * sizeof(uint64_t);
 	size_t key_bytes = p->mode == CG_MODE_HASH ? (((size_t) p->entries * sizeof(int64_t) + 255) & ~(size_t) 255) : 0;
 	if (cudaMalloc(&p->d_table, bytes + key_bytes) != cudaSuccess)
 	{
@@ -259,7 +260,7 @@ extern "C" int cg_partial_create(const CgScanDesc *desc, const CgColumnDesc *col
 			int Cbits = (63 - R) / 2;
 			if (Cbits < 12) continue;
 			if (Cbits > 24) Cbits = 24;
-			if (cudaMalloc(&p->d_packed, (size_t) p->entries * sizeof(uint64_t)) != cudaSuccess)
+			if (cudaMalloc(&p->d_packed, ((size_t) p->entries + CG_COMM_TAIL) * sizeof(uint64_t)) != cudaSuccess)
 			{
 				cg_partial_free(p);
 				return cg_set_error(CG_ENOMEM, "cudaMalloc for the packed accumulators failed");

@@ -548,9 +548,12 @@ int cg_launch_table_init(CgPartial *p, cudaStream_t stream)
 	cg_table_init_kernel<<<blocks, 256, 0, stream>>>(v);
 	CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	CG_CUDA(cudaMemsetAsync(p->d_stats, 0, 8 * sizeof(unsigned long long), stream));
-	if (p->d_packed) CG_CUDA(cudaMemsetAsync(p->d_packed, 0, (size_t) p->entries * sizeof(uint64_t), stream));
+	CG_CUDA(cudaMemsetAsync(p->d_table + total, 0, CG_COMM_TAIL * sizeof(uint64_t), stream));
+	if (p->d_packed) CG_CUDA(cudaMemsetAsync(p->d_packed, 0, ((size_t) p->entries + CG_COMM_TAIL) * sizeof(uint64_t), stream));
 	p->packed_dirty = false;
+	p->wide_dirty = false;
 	p->launches_since_drain = 0;
+	p->rows_since_drain = 0;
 	return CG_OK;
 }
 
@@ -646,5 +649,6 @@ int cg_launch_merge(CgPartial *p, const int64_t *d_keys, const uint8_t *d_nulls,
 	if (blocks > 148 * 8) blocks = 148 * 8;
 	cg_merge_kernel<<<blocks, 256, 0, stream>>>(plan, d_keys, d_nulls, d_words, nrows);
 	CG_CUDA(cudaGetLastError()); g_cg_launches++;
+	p->wide_dirty = true;
 	return CG_OK;
 }

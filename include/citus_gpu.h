@@ -28,6 +28,7 @@ extern "C" {
 #define CG_ETABLEFULL 5    /* group table too small: retry with a larger expected_groups */
 #define CG_EUNSUPPORTED 6  /* valid SQL, but outside what the GPU path handles: caller falls
                             * back to the reference's row-at-a-time executor */
+#define CG_ECOMM 8          /* NCCL / communicator error, or another rank failed the query */
 #define CG_ERETRY_UNPACKED 7 /* an optimistic packed accumulator overflowed (see cg_partial_set_packing):
                             * nothing wrong was returned; call cg_partial_set_packing(p, 0),
                             * cg_partial_reset(p) and scan again */
@@ -363,6 +364,48 @@ int cg_join_count_sum(const int64_t *d_build_keys, const uint8_t *d_build_nulls,
 					  int64_t nbuild, const int64_t *d_probe_keys, const uint8_t *d_probe_nulls,
 					  const int64_t *d_probe_payload, int64_t nprobe, int64_t *joined_rows, int64_t *sum_hi,
 					  uint64_t *sum_lo);
+
+/* ---------------------------------------------------------------------------------- *
+ *  Exchange steps across GPUs (one process per GPU; NCCL over NVLink / NVSwitch on the library's streams).
+ *  Replaces the libpq funnel of the adaptive executor for GPU-resident results
+ *  (executor/adaptive_executor.c:3964-4189 ReceiveResults + the combine query's HashAggregate,
+ *  planner/multi_logical_optimizer.c:1807-1885, 2231-2275) and the file exchange of a repartition
+ *  (executor/partitioned_intermediate_results.c:115-298, executor/intermediate_results.c:789-1045).
+ * ---------------------------------------------------------------------------------- */
+#define CG_COMM_ID_BYTES 128
+/* rank 0 creates the id; the caller ships the bytes to every rank (over the coordinator's connections) */
+int cg_comm_unique_id(uint8_t *id /* [CG_COMM_ID_BYTES] */);
+int cg_comm_init(const uint8_t *id, int32_t rank, int32_t nranks);    /* collective; after cg_init; id may be NULL when nranks = 1 */
+int cg_comm_rank(int32_t *rank, int32_t *nranks);
+int cg_comm_destroy(void);
+int cg_comm_barrier(void);
+enum { CG_COMM_SUM = 0, CG_COMM_MIN = 1, CG_COMM_MAX = 2 };
+/* small host-side agreement (plan constants such as the key range; timings): values[i] <- op over ranks */
+int cg_comm_allreduce_i64(int64_t *values, int32_t n, int32_t op);
+/* Coordinator-side combine: after the call the partial of rank `root` holds the combined aggregate.  Collective:
+ * EVERY rank calls it, passing the status of its own scans in local_status -- a rank that failed still takes
+ * part, and every rank then returns an error instead of some of them hanging in a collective.  Direct-indexed
+ * tables with additive words are reduced in place (the packed words alone when nothing else was written);
+ * other tables send their compacted rows to the root, which merges them.  Asynchronous on the library's
+ * stream: errors raised by kernels of any rank surface on the root at the next call that reads the partial. */
+int cg_comm_combine(CgPartial *p, int32_t root, int32_t local_status);
+/* Hash repartition of this rank's rows (column 0 = the key) into P partitions, partition p owned by rank
+ * p mod nranks: routing (cg_partition_index), scatter into destination-major order and ONE grouped
+ * ncclSend/ncclRecv of all columns on a second stream, so that the next table's routing and scatter overlap
+ * this table's exchange.  Results live in the slot (0..3) until its next use. */
+int cg_comm_repartition_exchange(int32_t slot, const int64_t *const *d_cols, const uint8_t *d_key_nulls, int64_t n,
+								 int32_t ncols, int32_t key_len, int32_t P, const int32_t *mins, const int32_t *maxs,
+								 int64_t *recv_rows);
+int cg_comm_exchange_wait(int32_t slot);      /* the library's compute stream waits (on the device) for the slot's exchange */
+/* received columns (device pointers), rows, rows of every local partition by source rank [nlocal][nranks],
+ * bytes sent to other ranks and the duration of the exchange on its stream; any pointer may be NULL */
+int cg_comm_exchange_result(int32_t slot, int64_t **d_cols, int64_t *nrows, int64_t *part_counts, int32_t *nlocal,
+							uint64_t *sent_bytes, double *exchange_ms);
+/* the host-side plan of an exchange (exposed for tests): position[p] = place of partition p in destination-major
+ * order; from counts[nranks][P] the rows this rank sends to / receives from every rank and the rows of its local
+ * partitions by source rank.  counts may be NULL (positions and nlocal only). */
+int cg_comm_exchange_plan(int32_t P, int32_t nranks, int32_t rank, const int64_t *counts, int32_t *position,
+						  int64_t *send_rows, int64_t *recv_rows, int64_t *local_part_counts, int32_t *nlocal);
 
 /* exact bounds from the skip lists (min/max of every chunk that survives chunk-group
  * skipping): the packed group key range and |argument| of every aggregate (0 = unknown,

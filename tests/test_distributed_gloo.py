@@ -1,11 +1,12 @@
-"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: shard -> rank assignment, the
-dense-table reduce and the variable-length row all-gather of the combine step
-(citus_b200/distributed.py).  The merge kernel itself is covered by the -m gpu tests."""
+"""world_size-2 gloo tests (CPU) of the host logic of the multi-GPU path: shard -> rank assignment, the algebra
+that makes a plain int64 sum-reduce an exact combine (two-limb 128-bit sums, packed count+sum words with the
+rows-added check), and the exchange plan of the repartition (cg_comm_exchange_plan, C, no GPU needed): what
+rank a plans to send to rank b is what b plans to receive from a.  The NCCL collectives themselves run in the
+-m gpu tests / tools/multigpu_check.py."""
 import os
 import socket
 
 import numpy as np
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -24,6 +25,8 @@ def _worker(rank, world, port, out):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
+        from citus_b200 import build
+        build.build()
         from citus_b200 import distributed as cgd
         # 1. every shard is owned by exactly one rank (shard s -> rank s mod world)
         mine = cgd.shards_of_rank(32, rank, world)
@@ -34,14 +37,15 @@ def _worker(rank, world, port, out):
         assert torch.stack(owners).sum(0).eq(1).all()
         assert all(s % world == rank for s in mine)
 
-        # 2. dense accumulator arrays with identical layout reduce by plain int64 sums; the
-        #    two-word form of a 128-bit sum needs no carries between the words
+        # 2. what ncclReduce(sum, int64) does to the accumulator words: the two-limb form of a 128-bit sum needs
+        #    no carries between the words; packed (sum << C) + count words add up exactly while counts stay < 2^C,
+        #    and the rows-added word that travels with them proves it
         rng = np.random.default_rng(100 + rank)
         v = rng.integers(-2**62, 2**62, size=1000)
         lo = torch.from_numpy((v & 0xffffffff).astype(np.int64))
         hi = torch.from_numpy((v >> 32).astype(np.int64))
         words = torch.stack([torch.ones(1000, dtype=torch.int64), lo, hi], dim=1).reshape(-1).contiguous()
-        cgd.reduce_dense_words(words, dst=0)
+        dist.reduce(words, dst=0, op=dist.ReduceOp.SUM)
         allv = [torch.zeros(1000, dtype=torch.int64) for _ in range(world)]
         dist.all_gather(allv, torch.from_numpy(v))
         if rank == 0:
@@ -50,26 +54,50 @@ def _worker(rank, world, port, out):
                 want = sum(int(a[i]) for a in allv)
                 got = int(w[i, 1]) + (int(w[i, 2]) << 32)
                 assert got == want and w[i, 0] == world
+        Cbits = 16
+        cnt = rng.integers(0, 300, size=500)
+        sums = rng.integers(-10**9, 10**9, size=500) * cnt
+        packed = torch.from_numpy(((sums << Cbits) + cnt).astype(np.int64))
+        tail = torch.tensor([int(cnt.sum())], dtype=torch.int64)
+        buf = torch.cat([packed, tail])
+        dist.reduce(buf, dst=0, op=dist.ReduceOp.SUM)
+        both = [torch.zeros(1000, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(both, torch.from_numpy(np.concatenate([sums, cnt])))
+        if rank == 0:
+            w = buf.numpy()
+            n = w[:500] & ((1 << Cbits) - 1)
+            s = (w[:500] - n) >> Cbits
+            assert np.array_equal(n, sum(b.numpy()[500:] for b in both))
+            assert np.array_equal(s, sum(b.numpy()[:500] for b in both))
+            assert int(n.sum()) == int(w[500])          # drained counts == rows added: no count field overflowed
 
-        # 3. all-gather of partial rows of different lengths
-        n = 5 + 3 * rank
-        nw = 3
-        keys = torch.arange(n, dtype=torch.int64) + 1000 * rank
-        nulls = torch.zeros(n, dtype=torch.uint8)
-        nulls[0] = 1
-        w = (torch.arange(n * nw, dtype=torch.int64) + 7 * rank)
-        ks, ns, ws, counts = cgd.allgather_rows(keys, nulls, w, nw)
-        assert counts == [5 + 3 * r for r in range(world)]
-        start = 0
+        # 3. the repartition's exchange plan, computed by the C library on every rank from the same counts matrix
+        P = 7
+        counts_mine = torch.from_numpy(rng.integers(0, 1000, size=P))
+        gathered = [torch.zeros(P, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(gathered, counts_mine)
+        counts = torch.stack(gathered).numpy()
+        pos, send, recv, local = cgd.exchange_plan(P, world, rank, counts)
+        owners = [p % world for p in range(P)]
+        assert sorted(pos.tolist()) == list(range(P))
+        order = np.argsort(pos)                                   # partitions in send-buffer order: destination-major
+        assert [owners[p] for p in order] == sorted(owners)
         for r in range(world):
-            c = counts[r]
-            assert ks[start:start + c].tolist() == (torch.arange(c) + 1000 * r).tolist()
-            assert ws[start * nw:(start + c) * nw].tolist() == (torch.arange(c * nw) + 7 * r).tolist()
-            assert int(ns[start]) == 1 and int(ns[start + 1:start + c].sum()) == 0
-            start += c
+            assert send[r] == sum(int(counts[rank, p]) for p in range(P) if p % world == r)
+            assert recv[r] == sum(int(counts[r, p]) for p in range(P) if p % world == rank)
+        plans = [torch.zeros(2 * world, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(plans, torch.from_numpy(np.concatenate([send, recv])))
+        for a in range(world):
+            for b in range(world):
+                assert int(plans[a][b]) == int(plans[b][world + a])        # a sends to b what b receives from a
+        mine_parts = [p for p in range(P) if p % world == rank]
+        assert local.shape == (len(mine_parts), world)
+        for i, p in enumerate(mine_parts):
+            assert local[i].tolist() == counts[:, p].tolist()
         out.put((rank, "ok"))
     except Exception as e:          # noqa
-        out.put((rank, repr(e)))
+        import traceback
+        out.put((rank, traceback.format_exc()))
     finally:
         dist.destroy_process_group()
 

@@ -90,7 +90,8 @@ def run_both(cg, oracle, rel, quals=(), group_cols=(), aggs=(), chunk_row_limit=
         st = agg.scan_shard(shard)
         shard.free()
     t = oracle_table(oracle, rel, chunk_row_limit)
-    r = t.scan(list(quals), list(group_cols), to_oracle_aggs(oracle, aggs), qual_pushdown=pushdown)
+    is_tree = isinstance(quals, tuple) and len(quals) > 0 and quals[0] in ("and", "or")
+    r = t.scan(quals if is_tree else list(quals), list(group_cols), to_oracle_aggs(oracle, aggs), qual_pushdown=pushdown)
     assert st.rows_scanned == r.rows_scanned
     assert st.rows_removed_by_filter == r.rows_removed_by_filter
     assert st.chunk_groups_filtered == r.chunk_groups_filtered
