@@ -136,6 +136,14 @@ class Relation:
         v.natts = natts
         return self
 
+    def prefix(self, nstripes: int) -> "Relation":
+        """the first `nstripes` stripes of this relation as a relation of its own (shares the image)"""
+        r = Relation()
+        r._keep = [self]
+        C.memmove(C.byref(r.view), C.byref(self.view), C.sizeof(CgRelation))
+        r.view.nstripes = max(0, min(nstripes, self.view.nstripes))
+        return r
+
     def register(self):
         """pin the page image (cudaHostRegister): cg_scan_relation then uses DMA staging"""
         check(lib().cg_relation_register(C.byref(self.view)))

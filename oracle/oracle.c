@@ -956,6 +956,43 @@ void orc_insert(OrcTable *t, const int64_t *const *cols, const uint8_t *const *c
 	free(vals); free(nulls);
 }
 
+/*
+ * Synthetic rows for the benchmark's reference arm, written through the same row-at-a-time writer.  The
+ * counter-based formula is the benchmark's own (include/citus_gpu.h cg_gen_relation), restated here so that
+ * the reference arm builds its shards without loading the product library:
+ *    value(row, col) = lo + splitmix64(seed ^ col << 56 ^ (first_row + row)) % (hi - lo)
+ *    null(row, col)  = splitmix64(~seed ^ col << 56 ^ (first_row + row)) % 1000000 < null_ppm
+ * kind 1 = the sequence lo + first_row + row.
+ */
+typedef struct OrcGenColumn { int32_t attlen; int32_t kind; int64_t lo; int64_t hi; uint32_t null_ppm; uint32_t reserved; } OrcGenColumn;
+
+uint64_t orc_splitmix64(uint64_t x);
+
+void orc_gen_insert(OrcTable *t, const OrcGenColumn *cols, int64_t nrows, uint64_t first_row, uint64_t seed)
+{
+	int64_t *vals = malloc(sizeof(int64_t) * (size_t) t->natts);
+	uint8_t *nulls = malloc((size_t) t->natts);
+	for (int64_t i = 0; i < nrows; i++)
+	{
+		uint64_t row = first_row + (uint64_t) i;
+		for (int c = 0; c < t->natts; c++)
+		{
+			const OrcGenColumn *g = &cols[c];
+			nulls[c] = g->null_ppm ? (orc_splitmix64(~seed ^ ((uint64_t) c << 56) ^ row) % 1000000ull < g->null_ppm) : 0;
+			if (g->kind == 1) vals[c] = g->lo + (int64_t) row;
+			else
+			{
+				uint64_t span = (uint64_t) (g->hi - g->lo);
+				uint64_t h = orc_splitmix64(seed ^ ((uint64_t) c << 56) ^ row);
+				vals[c] = g->lo + (int64_t) (span ? h % span : 0);
+			}
+		}
+		orc_write_row(t, vals, nulls);
+	}
+	orc_flush_stripe(t);
+	free(vals); free(nulls);
+}
+
 /* accessors for the ctypes wrapper / for handing the image to the product code */
 const uint8_t *orc_table_pages(const OrcTable *t) { return t->pages; }
 uint64_t orc_table_nblocks(const OrcTable *t) { return t->nblocks; }
@@ -1187,6 +1224,22 @@ int64_t orc_result_counter(const OrcScanResult *r, int which)
 		case 1: return r->rows_removed_by_filter;
 		case 2: return r->chunk_groups_filtered;
 		default: return r->rows_passed;
+	}
+}
+
+/* all groups at once: keys[n], key_nulls[n], and per (group, aggregate) sum_hi / sum_lo / count [n * nagg] */
+void orc_result_export(const OrcScanResult *r, int64_t *keys, uint8_t *key_nulls, int64_t *sum_hi, uint64_t *sum_lo, int64_t *count)
+{
+	for (int64_t g = 0; g < r->ngroups; g++)
+	{
+		keys[g] = r->keys[g]; key_nulls[g] = r->key_nulls[g];
+		for (int a = 0; a < r->nagg; a++)
+		{
+			const OrcAggState *s = &r->states[g * r->nagg + a];
+			sum_hi[g * r->nagg + a] = (int64_t) (s->isum >> 64);
+			sum_lo[g * r->nagg + a] = (uint64_t) s->isum;
+			count[g * r->nagg + a] = s->count;
+		}
 	}
 }
 

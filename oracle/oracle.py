@@ -332,6 +332,17 @@ class Table:
             np_ = (C.c_void_p * self.natts)(*[None if x is None else x.ctypes.data for x in keep])
         lib().orc_insert(self.h, cp, np_, n)
 
+    def generate(self, columns, nrows, seed, first_row=0):
+        """synthetic rows through the row-at-a-time writer; columns = [(attlen, kind, lo, hi, null_ppm)], the same
+        counter-based formula as the benchmark's generator (cg_gen_relation)"""
+        arr = (GenColumn * len(columns))()
+        for i, (attlen, kind, lo, hi, null_ppm) in enumerate(columns):
+            arr[i].attlen, arr[i].kind, arr[i].lo, arr[i].hi, arr[i].null_ppm = attlen, kind, lo, hi, null_ppm
+        L = lib()
+        L.orc_gen_insert.restype = None
+        L.orc_gen_insert.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_uint64]
+        L.orc_gen_insert(self.h, arr, nrows, first_row, seed)
+
     # --- image accessors -------------------------------------------------
     def pages(self) -> np.ndarray:
         nb = lib().orc_table_nblocks(self.h)
@@ -418,6 +429,11 @@ def flatten_where(where):
     return atoms, tokens
 
 
+class GenColumn(C.Structure):
+    _fields_ = [("attlen", C.c_int32), ("kind", C.c_int32), ("lo", C.c_int64), ("hi", C.c_int64),
+                ("null_ppm", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 class Result:
     def __init__(self, aggs):
         self.aggs = aggs
@@ -447,6 +463,18 @@ class Result:
     def combine(self, other: "Result"):
         sa = (AggSpec * max(1, len(self.aggs)))(*[a.spec() for a in self.aggs])
         _check(lib().orc_combine(self.h, other.h, sa))
+
+    def export_arrays(self):
+        """all groups as numpy arrays: keys[n], key_nulls[n], sum_hi / sum_lo / count [n][naggs]"""
+        n = lib().orc_result_ngroups(self.h)
+        na = max(len(self.aggs), 1)
+        keys, kn = np.zeros(n, np.int64), np.zeros(n, np.uint8)
+        hi, lo, cnt = np.zeros((n, na), np.int64), np.zeros((n, na), np.uint64), np.zeros((n, na), np.int64)
+        L = lib()
+        L.orc_result_export.restype = None
+        L.orc_result_export.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        L.orc_result_export(self.h, keys.ctypes.data, kn.ctypes.data, hi.ctypes.data, lo.ctypes.data, cnt.ctypes.data)
+        return dict(n=n, keys=keys, key_nulls=kn, sum_hi=hi, sum_lo=lo, count=cnt)
 
     def groups(self):
         """dict: key (int or None for the NULL group) -> list per aggregate of dicts
