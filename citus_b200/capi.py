@@ -99,6 +99,7 @@ SYMBOLS = [
     ("cg_set_stream", C.c_int, [C.c_void_p]),
     ("cg_kernel_launches", C.c_uint64, []),
     ("cg_partition_copy_bytes", C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    ("cg_partition_copy_serialize", C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
     ("cg_join_count_sum", C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                    C.POINTER(C.c_uint64)]),
     ("cg_partial_dense_words_enqueue", C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
@@ -149,6 +150,9 @@ SYMBOLS = [
                                     C.c_uint32, C.POINTER(_P)]),
     ("cg_gen_relation_view", C.c_int, [_P, C.POINTER(CgRelation)]),
     ("cg_gen_relation_free", None, [_P]),
+    ("cg_partial_merge_values", C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
+    ("cg_agg_column", C.c_int, [C.c_int32, C.c_int32, _P, _P, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                               C.POINTER(C.c_uint64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("cg_comm_unique_id", C.c_int, [_P]),
     ("cg_comm_init", C.c_int, [_P, C.c_int32, C.c_int32]),
     ("cg_comm_rank", C.c_int, [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

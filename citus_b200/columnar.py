@@ -484,6 +484,18 @@ def partition_copy_bytes(d_index_ptr, n, P, d_col_ptrs, col_lens, binary, d_null
     return rows, nbytes
 
 
+def partition_copy_serialize(d_index_ptr, n, P, d_col_ptrs, col_lens, binary, d_out_ptr, out_capacity, d_null_ptrs=None,
+                             generate_empty_results=False):
+    """the P partition files (COPY text / binary) back to back in the device buffer; returns file offsets [P + 1]"""
+    cols = (C.c_void_p * len(d_col_ptrs))(*d_col_ptrs)
+    nulls = (C.c_void_p * len(d_col_ptrs))(*(d_null_ptrs or [None] * len(d_col_ptrs)))
+    lens = (C.c_int32 * len(d_col_ptrs))(*col_lens)
+    offs = np.zeros(P + 1, np.int64)
+    check(lib().cg_partition_copy_serialize(d_index_ptr, n, P, cols, nulls, lens, len(d_col_ptrs), 1 if binary else 0,
+                                            1 if generate_empty_results else 0, d_out_ptr, out_capacity, offs.ctypes.data))
+    return offs
+
+
 def partition_scatter(d_index_ptr, n, P, d_col_ptrs, d_out_ptrs, order=None):
     """stable scatter into partition-contiguous order; order[p] = output position of partition p"""
     cols = (C.c_void_p * len(d_col_ptrs))(*d_col_ptrs)

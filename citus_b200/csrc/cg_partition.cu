@@ -557,3 +557,245 @@ extern "C" int cg_partition_copy_bytes(const int32_t *d_index, int64_t n, int32_
 	}
 	return CG_OK;
 }
+
+/* ------------------------------------------------------------------------------ *
+ *  R18: the partition files themselves.  TaskFileDestReceiver (worker/worker_sql_task_protocol.c:91-251) appends every
+ *  row of a partition, in arrival order, to that partition's file in PostgreSQL's COPY format (commands/multi_copy.c
+ *  AppendCopyRowData / AppendCopyBinaryHeaders / AppendCopyBinaryFooters):
+ *    text    fields separated by '\t', row ended by '\n', NULL as "\N", integers in decimal (pg_lltoa)
+ *    binary  "PGCOPY\n\377\r\n\0" + int32 flags 0 + int32 extension length 0, then per row int16 field count and per
+ *            field int32 length (-1 = NULL) + the value in network byte order, then int16 -1
+ *  Here every row's byte length is known before anything is written (cg_partition_copy_bytes_kernel's arithmetic), so a
+ *  row's place in its file is a segmented prefix sum in input order -- per block and partition (shared memory), across
+ *  blocks (cg_partition_scan2_kernel), inside a warp step (peers of the same partition to the left) -- and all rows are
+ *  formatted in parallel straight into one device buffer that holds the P files back to back.
+ * ------------------------------------------------------------------------------ */
+struct CopyWriteParams
+{
+	const int32_t *index;
+	int64_t n;
+	int32_t P, ncols, binary;
+	const int64_t *cols[CGP_MAX_COLS];
+	const uint8_t *nulls[CGP_MAX_COLS];
+	int32_t len[CGP_MAX_COLS];
+	uint32_t *row_len;                         /* [n] */
+	unsigned long long *block_bytes;           /* [nblocks][P]: bytes of the block's rows per partition, then their start offsets */
+	const unsigned long long *file_start;      /* [P]: offset of the first ROW byte of partition p in the output */
+	uint8_t *out;
+};
+
+__device__ __forceinline__ unsigned int copy_row_len(const CopyWriteParams &A, int64_t r)
+{
+	unsigned int b = A.binary ? 2u : 0u;
+	for (int c = 0; c < A.ncols; c++)
+	{
+		bool isnull = A.nulls[c] && A.nulls[c][r];
+		if (A.binary) b += 4u + (isnull ? 0u : (unsigned int) A.len[c]);
+		else b += 1u + (isnull ? 2u : decimal_text_len(A.cols[c][r]));
+	}
+	return b;
+}
+
+__global__ void __launch_bounds__(CGP_THREADS)
+cg_copy_len_kernel(const __grid_constant__ CopyWriteParams A)
+{
+	extern __shared__ unsigned int s_bytes[];            /* [P] */
+	for (int p = threadIdx.x; p < A.P; p += CGP_THREADS) s_bytes[p] = 0;
+	__syncthreads();
+	int64_t base = (int64_t) blockIdx.x * CGP_ROWS_PER_BLOCK;
+	for (int i = threadIdx.x; i < CGP_ROWS_PER_BLOCK; i += CGP_THREADS)
+	{
+		int64_t r = base + i;
+		if (r >= A.n) break;
+		unsigned int b = copy_row_len(A, r);
+		A.row_len[r] = b;
+		atomicAdd(&s_bytes[A.index[r]], b);
+	}
+	__syncthreads();
+	for (int p = threadIdx.x; p < A.P; p += CGP_THREADS) A.block_bytes[(uint64_t) blockIdx.x * A.P + p] = s_bytes[p];
+}
+
+__device__ __forceinline__ uint8_t *put_be(uint8_t *p, uint64_t v, int bytes)
+{
+	for (int i = bytes - 1; i >= 0; i--) *p++ = (uint8_t) (v >> (8 * i));
+	return p;
+}
+
+__device__ __forceinline__ uint8_t *put_decimal(uint8_t *p, int64_t v)
+{
+	unsigned long long a = v < 0 ? 0ull - (unsigned long long) v : (unsigned long long) v;
+	if (v < 0) *p++ = '-';
+	unsigned int digits = decimal_text_len(v) - (v < 0 ? 1u : 0u);
+	for (int i = (int) digits - 1; i >= 0; i--) { p[i] = (uint8_t) ('0' + a % 10ull); a /= 10ull; }
+	return p + digits;
+}
+
+__global__ void __launch_bounds__(CGP_THREADS)
+cg_copy_write_kernel(const __grid_constant__ CopyWriteParams A)
+{
+	extern __shared__ unsigned long long s_run[];        /* [warps][P] running byte offsets */
+	constexpr int WARPS = CGP_THREADS / 32;
+	constexpr int SEG = CGP_ROWS_PER_BLOCK / WARPS;
+	const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	unsigned long long *mine = s_run + warp * A.P;
+	for (int p = lane; p < A.P; p += 32) mine[p] = 0;
+	__syncwarp();
+	const int64_t seg0 = (int64_t) blockIdx.x * CGP_ROWS_PER_BLOCK + (int64_t) warp * SEG;
+	/* pass A: bytes of this warp's segment per partition (the row of shared memory is warp-private) */
+	for (int step = 0; step < SEG; step += 32)
+	{
+		int64_t r = seg0 + step + lane;
+		int idx = r < A.n ? A.index[r] : -1;
+		unsigned int len = r < A.n ? A.row_len[r] : 0u;
+		unsigned peers = __match_any_sync(0xffffffffu, idx);
+		unsigned int total = 0;
+		for (int src = 0; src < 32; src++)
+		{
+			unsigned int v = __shfl_sync(0xffffffffu, len, src);
+			if ((peers >> src) & 1u) total += v;
+		}
+		if (idx >= 0 && lane == (unsigned) (__ffs(peers) - 1)) mine[idx] += total;
+		__syncwarp();
+	}
+	__syncthreads();
+	for (int p = threadIdx.x; p < A.P; p += CGP_THREADS)
+	{
+		unsigned long long run = A.file_start[p] + A.block_bytes[(uint64_t) blockIdx.x * A.P + p];
+		for (int w = 0; w < WARPS; w++)
+		{
+			unsigned long long c = s_run[w * A.P + p];
+			s_run[w * A.P + p] = run;
+			run += c;
+		}
+	}
+	__syncthreads();
+	/* pass B: format every row at its place */
+	for (int step = 0; step < SEG; step += 32)
+	{
+		int64_t r = seg0 + step + lane;
+		int idx = r < A.n ? A.index[r] : -1;
+		unsigned int len = r < A.n ? A.row_len[r] : 0u;
+		unsigned peers = __match_any_sync(0xffffffffu, idx);
+		unsigned int before = 0, total = 0;
+		for (int src = 0; src < 32; src++)
+		{
+			unsigned int v = __shfl_sync(0xffffffffu, len, src);
+			if ((peers >> src) & 1u) { total += v; if ((unsigned) src < lane) before += v; }
+		}
+		if (idx >= 0)
+		{
+			uint8_t *p = A.out + mine[idx] + before;
+			if (A.binary)
+			{
+				p = put_be(p, (uint64_t) A.ncols, 2);
+				for (int c = 0; c < A.ncols; c++)
+				{
+					if (A.nulls[c] && A.nulls[c][r]) p = put_be(p, 0xffffffffull, 4);
+					else { p = put_be(p, (uint64_t) A.len[c], 4); p = put_be(p, (uint64_t) A.cols[c][r], A.len[c]); }
+				}
+			}
+			else
+				for (int c = 0; c < A.ncols; c++)
+				{
+					if (A.nulls[c] && A.nulls[c][r]) { *p++ = '\\'; *p++ = 'N'; }
+					else p = put_decimal(p, A.cols[c][r]);
+					*p++ = (c + 1 < A.ncols) ? '\t' : '\n';
+				}
+		}
+		__syncwarp();
+		if (idx >= 0 && lane == (unsigned) (__ffs(peers) - 1)) mine[idx] += total;
+		__syncwarp();
+	}
+}
+
+__global__ void cg_copy_frame_kernel(uint8_t *out, const unsigned long long *file_begin, const unsigned long long *file_end, const uint8_t *present, int P)
+{
+	int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= P || !present[p]) return;
+	const uint8_t sig[19] = {'P', 'G', 'C', 'O', 'P', 'Y', '\n', 0xff, '\r', '\n', 0, 0, 0, 0, 0, 0, 0, 0, 0};
+	for (int i = 0; i < 19; i++) out[file_begin[p] + i] = sig[i];
+	out[file_end[p] - 2] = 0xff; out[file_end[p] - 1] = 0xff;
+}
+
+extern "C" int cg_partition_copy_serialize(const int32_t *d_index, int64_t n, int32_t P, const int64_t *const *d_cols,
+										   const uint8_t *const *d_nulls, const int32_t *col_len, int32_t ncols, int32_t binary,
+										   int32_t generate_empty_results, uint8_t *d_out, int64_t out_capacity,
+										   int64_t *file_offsets /* [P + 1] */)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx) return CG_EINVAL;
+	if (P < 1 || P > CGP_MAX_P) return cg_set_error(CG_EINVAL, "partition count %d out of range", P);
+	if (ncols < 1 || ncols > CGP_MAX_COLS) return cg_set_error(CG_EUNSUPPORTED, "1..%d columns", CGP_MAX_COLS);
+	if (n < 0 || !d_cols || !col_len || !file_offsets) return cg_set_error(CG_EINVAL, "bad argument");
+	for (int c = 0; c < ncols; c++)
+		if (binary && col_len[c] != 2 && col_len[c] != 4 && col_len[c] != 8) return cg_set_error(CG_EUNSUPPORTED, "binary width %d", col_len[c]);
+	const int64_t nblocks = (n + CGP_ROWS_PER_BLOCK - 1) / CGP_ROWS_PER_BLOCK;
+	CgAsyncBuf len_buf, block_buf, tot_buf;
+	CG_CUDA(len_buf.alloc(sizeof(uint32_t) * (size_t) std::max<int64_t>(n, 1), ctx->compute));
+	CG_CUDA(block_buf.alloc(sizeof(unsigned long long) * (size_t) std::max<int64_t>(nblocks, 1) * P, ctx->compute));
+	CG_CUDA(tot_buf.alloc(sizeof(unsigned long long) * (4 * (size_t) P + 4), ctx->compute));
+	unsigned long long *d_tot = tot_buf.as<unsigned long long>();
+	CG_CUDA(cudaMemsetAsync(d_tot, 0, sizeof(unsigned long long) * (4 * (size_t) P + 4), ctx->compute));
+	CopyWriteParams A;
+	memset(&A, 0, sizeof A);
+	A.index = d_index; A.n = n; A.P = P; A.ncols = ncols; A.binary = binary ? 1 : 0;
+	for (int c = 0; c < ncols; c++) { A.cols[c] = d_cols[c]; A.nulls[c] = d_nulls ? d_nulls[c] : nullptr; A.len[c] = col_len[c]; }
+	A.row_len = len_buf.as<uint32_t>(); A.block_bytes = block_buf.as<unsigned long long>(); A.out = d_out;
+	std::vector<unsigned long long> totals(P, 0);
+	if (n > 0)
+	{
+		cg_copy_len_kernel<<<(unsigned) nblocks, CGP_THREADS, P * sizeof(unsigned int), ctx->compute>>>(A);
+		CG_CUDA(cudaGetLastError()); g_cg_launches++;
+		cg_partition_scan2_kernel<<<P, 1024, 0, ctx->compute>>>(A.block_bytes, d_tot, nblocks, P);
+		CG_CUDA(cudaGetLastError()); g_cg_launches++;
+		CG_CUDA(cudaMemcpyAsync(totals.data(), d_tot, sizeof(unsigned long long) * P, cudaMemcpyDeviceToHost, ctx->compute));
+		CG_CUDA(cudaStreamSynchronize(ctx->compute));
+	}
+	/* file layout: [header][rows][trailer] per partition, back to back; a partition without rows has no file content unless
+	 * generate_empty_results (lazy start-up of the receivers, partitioned_intermediate_results.c:234) */
+	std::vector<unsigned long long> begin(P), rows_at(P), end(P);
+	std::vector<uint8_t> present(P);
+	unsigned long long off = 0;
+	for (int p = 0; p < P; p++)
+	{
+		present[p] = binary && (totals[p] > 0 || generate_empty_results);
+		begin[p] = off;
+		rows_at[p] = off + (present[p] ? 19 : 0);
+		end[p] = rows_at[p] + totals[p] + (present[p] ? 2 : 0);
+		off = end[p];
+		file_offsets[p] = (int64_t) begin[p];
+	}
+	file_offsets[P] = (int64_t) off;
+	if ((int64_t) off > out_capacity || (off > 0 && !d_out))
+		return cg_set_error(CG_EINVAL, "the partition files need %llu bytes, the output buffer holds %lld", off, (long long) out_capacity);
+	if (off == 0) return CG_OK;
+	unsigned long long *d_rows_at = d_tot + P, *d_begin = d_tot + 2 * P, *d_end = d_tot + 3 * P;
+	uint8_t *d_present = (uint8_t *) (d_tot + 4 * P);
+	static unsigned long long *h_pin = nullptr;
+	if (!h_pin) CG_CUDA(cudaHostAlloc((void **) &h_pin, sizeof(unsigned long long) * (4 * CGP_MAX_P + 4), cudaHostAllocDefault));
+	memcpy(h_pin, rows_at.data(), sizeof(unsigned long long) * P);
+	memcpy(h_pin + P, begin.data(), sizeof(unsigned long long) * P);
+	memcpy(h_pin + 2 * P, end.data(), sizeof(unsigned long long) * P);
+	memcpy(h_pin + 3 * P, present.data(), (size_t) P);
+	CG_CUDA(cudaMemcpyAsync(d_rows_at, h_pin, sizeof(unsigned long long) * 3 * P + (size_t) P, cudaMemcpyHostToDevice, ctx->compute));
+	A.file_start = d_rows_at;
+	if (n > 0)
+	{
+		static bool smem_configured = false;
+		if (!smem_configured)
+		{
+			CG_CUDA(cudaFuncSetAttribute(cg_copy_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+										 (int) ((CGP_THREADS / 32) * CGP_MAX_P * sizeof(unsigned long long))));
+			smem_configured = true;
+		}
+		cg_copy_write_kernel<<<(unsigned) nblocks, CGP_THREADS, (CGP_THREADS / 32) * P * sizeof(unsigned long long), ctx->compute>>>(A);
+		CG_CUDA(cudaGetLastError()); g_cg_launches++;
+	}
+	if (binary)
+	{
+		cg_copy_frame_kernel<<<(P + 127) / 128, 128, 0, ctx->compute>>>(d_out, d_begin, d_end, d_present, P);
+		CG_CUDA(cudaGetLastError()); g_cg_launches++;
+	}
+	CG_CUDA(cudaStreamSynchronize(ctx->compute));
+	return CG_OK;
+}

@@ -81,7 +81,9 @@ int cg_numa_unbind(void);
 void cg_shutdown(void);
 
 /* ---------------------------------------------------------------------------------- *
- *  Relation metadata, binary-compatible with what the reference keeps per stripe/chunk.
+ *  Relation metadata: field-for-field what the reference keeps per stripe / chunk, in this header's own
+ *  layout (NOT memory-compatible with ColumnChunkSkipNode / StripeMetadata: Datum min / max become int64 or
+ *  float8 bits, bool / enum fields become int32); pg_glue/gpu_columnar_agg.c build_relation_image() converts.
  * ---------------------------------------------------------------------------------- */
 
 /* include/columnar/columnar_compression.h:17-27 CompressionType */
@@ -292,6 +294,19 @@ int cg_partial_fetch(CgPartial *p, int64_t capacity, int64_t *keys, uint8_t *key
 					 int64_t *sum_hi, uint64_t *sum_lo, int64_t *count, int64_t *minmax,
 					 double *fsum, int64_t *ngroups);
 
+/* The inverse of cg_partial_fetch: partial-aggregate ROWS held on the host (group key + per aggregate the 128-bit
+ * sum, count, min / max, float sum; arrays [nrows * naggs] laid out like cg_partial_fetch's) are folded into p by the
+ * combine kernel.  What the coordinator does with the per-shard result rows it receives (adaptive_executor.c:3964-4189
+ * ReceiveResults -> TupleDestination) in place of a CPU HashAggregate over them.  Arrays an aggregate list does not
+ * need may be NULL.  count[] of a sum / min / max is its number of non-NULL inputs (0 = the partial was SQL NULL). */
+int cg_partial_merge_values(CgPartial *p, int64_t nrows, const int64_t *keys, const uint8_t *key_nulls, const int64_t *sum_hi,
+							const uint64_t *sum_lo, const int64_t *count, const int64_t *minmax, const double *fsum);
+/* count / exact sum / min / max of one host column (attlen 1, 2, 4, 8; float4 is widened to float8 for min / max; a float
+ * sum is not computed: its result depends on the order) in one pass: the batch step of the worker_partial_agg /
+ * coord_combine_agg shims (utils/aggregate_utils.c:501-607, 820-1003), which otherwise pay one fmgr call per row. */
+int cg_agg_column(int32_t attlen, int32_t is_float, const void *values, const uint8_t *isnull, int64_t n, int64_t *count,
+				  int64_t *sum_hi, uint64_t *sum_lo, int64_t *min_value, int64_t *max_value);
+
 /* Raw accumulator export / merge, for the combine step and for collectives.
  * A partial is `nwords` 64-bit accumulator words per group; every word is combined
  * with one commutative op (add / min / max / float add), so partials of different
@@ -353,6 +368,13 @@ int cg_partition_scatter_ordered(const int32_t *d_index, int64_t n, int32_t P, c
 int cg_partition_copy_bytes(const int32_t *d_index, int64_t n, int32_t P, const int64_t *const *d_cols,
 							const uint8_t *const *d_nulls, const int32_t *col_len, int32_t ncols, int32_t binary,
 							int32_t generate_empty_results, int64_t *rows_written, int64_t *bytes_written);
+
+/* The partition files themselves (what TaskFileDestReceiver writes, worker/worker_sql_task_protocol.c:91-251): the COPY text or
+ * binary encoding of every row, rows of a partition in input order, the P files back to back in the device buffer d_out
+ * (out_capacity bytes); file p is [file_offsets[p], file_offsets[p + 1]).  Sizes equal cg_partition_copy_bytes'. */
+int cg_partition_copy_serialize(const int32_t *d_index, int64_t n, int32_t P, const int64_t *const *d_cols,
+								const uint8_t *const *d_nulls, const int32_t *col_len, int32_t ncols, int32_t binary,
+								int32_t generate_empty_results, uint8_t *d_out, int64_t out_capacity, int64_t *file_offsets /* [P + 1] */);
 
 /* The merge side of a dual-repartition join for the aggregate query
  *     SELECT count(*), sum(b.payload + p.payload) FROM build b JOIN probe p USING (key)

@@ -165,6 +165,40 @@ def partition_rows(keys, nulls, keytype, method, mins, maxs):
     return idx, rows
 
 
+def copy_files(index, cols, col_lens, P, binary, nulls=None, generate_empty_results=False):
+    """the partition files TaskFileDestReceiver writes (worker/worker_sql_task_protocol.c:91-251; [PG] COPY text /
+    binary row encoding, commands/multi_copy.c AppendCopyRowData / AppendCopyBinaryHeaders / -Footers), row at a time:
+    text = decimal fields joined by TAB, NULL as \\N, LF per row; binary = 19-byte header, per row int16 field count +
+    per field int32 length (-1 NULL) + big-endian value, int16 -1 trailer.  Returns P bytes objects."""
+    import struct
+    files = [bytearray() for _ in range(P)]
+    started = [False] * P
+    n = len(index)
+    for r in range(n):
+        p = int(index[r])
+        f = files[p]
+        if binary and not started[p]:
+            f += b"PGCOPY\n\377\r\n\0" + struct.pack(">ii", 0, 0)
+        started[p] = True
+        if binary:
+            f += struct.pack(">h", len(cols))
+            for c, col in enumerate(cols):
+                if nulls is not None and nulls[c] is not None and nulls[c][r]:
+                    f += struct.pack(">i", -1)
+                else:
+                    f += struct.pack(">i", col_lens[c]) + int(col[r]).to_bytes(col_lens[c], "big", signed=True)
+        else:
+            fields = ["\\N" if (nulls is not None and nulls[c] is not None and nulls[c][r]) else str(int(col[r]))
+                      for c, col in enumerate(cols)]
+            f += ("\t".join(fields) + "\n").encode()
+    for p in range(P):
+        if binary and (started[p] or generate_empty_results):
+            if not started[p]:
+                files[p] += b"PGCOPY\n\377\r\n\0" + struct.pack(">ii", 0, 0)
+            files[p] += struct.pack(">h", -1)
+    return [bytes(f) for f in files]
+
+
 def join_count_sum(bkeys, bpay, pkeys, ppay, bnulls=None, pnulls=None):
     """(joined rows, exact sum(b.payload + p.payload)) of the MERGE task's hash join, row at a time"""
     arrs = [np.ascontiguousarray(a, np.int64) for a in (bkeys, bpay, pkeys, ppay)]

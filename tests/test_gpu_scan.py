@@ -696,3 +696,56 @@ def test_where_trees_with_nulls_and_groups(cg, oracle, kernel_family, family):
     for force_hash in (False, True):
         run_both(cg, oracle, rel, where, [0], aggs, chunk_row_limit=4000, force_hash=force_hash, float_cols=(3,))
     run_both(cg, oracle, rel, where, [], aggs, chunk_row_limit=4000, float_cols=(3,), e2e=True)
+
+
+# --------------------------------------------------------------------------- R18: the partition files themselves
+def test_copy_serializer_writes_the_reference_files(cg, oracle, expected):
+    """cg_partition_copy_serialize: the COPY text / binary bytes of every partition file -- golden sizes
+    (21/14/5/9 and 93/57/39/75) and byte-for-byte the oracle's row-at-a-time files, incl. NULLs, negative
+    numbers, empty partitions (lazy start-up vs generate_empty_results) and 200 000 rows over 32 partitions"""
+    import torch
+
+    def files_of(idx_t, n, P, cols, lens, binary, nulls=None, gen_empty=False):
+        dcols = [torch.from_numpy(np.ascontiguousarray(c, np.int64)).cuda() for c in cols]
+        dn = None if nulls is None else [None if x is None else torch.from_numpy(np.ascontiguousarray(x, np.uint8)).cuda() for x in nulls]
+        rows, nbytes = cg.partition_copy_bytes(idx_t.data_ptr(), n, P, [c.data_ptr() for c in dcols], lens, binary=binary,
+                                               d_null_ptrs=None if dn is None else [None if x is None else x.data_ptr() for x in dn],
+                                               generate_empty_results=gen_empty)
+        total = int(nbytes.sum())
+        out = torch.zeros(max(total, 1) + 64, dtype=torch.uint8, device="cuda")
+        offs = cg.partition_copy_serialize(idx_t.data_ptr(), n, P, [c.data_ptr() for c in dcols], lens, binary, out.data_ptr(), total,
+                                           d_null_ptrs=None if dn is None else [None if x is None else x.data_ptr() for x in dn],
+                                           generate_empty_results=gen_empty)
+        assert np.array_equal(np.diff(offs), nbytes)
+        host = out.cpu().numpy().tobytes()
+        assert host[total:total + 64] == b"\0" * 64                      # nothing written past the files
+        return [host[offs[p]:offs[p + 1]] for p in range(P)], rows, nbytes
+
+    i = np.arange(1, 11)
+    idx, cnt, _ = _partition(cg, i, None, 4, "hash", expected["squares_hash_mins"], expected["squares_hash_maxs"])
+    files, rows, nbytes = files_of(idx, 10, 4, [i, i * i], [4, 4], False)
+    assert [[p, int(rows[p]), len(files[p])] for p in range(4)] == expected["squares_hash_text"]
+    assert files == oracle.copy_files(idx.cpu().numpy(), [i, i * i], [4, 4], 4, False)
+    idx, cnt, _ = _partition(cg, i * i, None, 4, "range", [0, 21, 41, 61], [20, 40, 60, 100])
+    files, rows, nbytes = files_of(idx, 10, 4, [i, i * i], [4, 4], True)
+    assert [[p, int(rows[p]), len(files[p])] for p in range(4)] == expected["squares_range_binary"]
+    assert files == oracle.copy_files(idx.cpu().numpy(), [i, i * i], [4, 4], 4, True)
+    # larger, with NULLs, negative values, 8-byte and 2-byte binary fields, partitions that receive nothing
+    rng = np.random.default_rng(8)
+    n, P = 200_000, 32
+    k = rng.integers(-2**40, 2**40, n)
+    a = rng.integers(-30000, 30000, n)
+    b = rng.integers(-2**62, 2**62, n)
+    na = (rng.random(n) < 0.1).astype(np.uint8)
+    mins, maxs = oracle.synthetic_intervals(P)
+    idx, cnt, _ = _partition(cg, k, None, 8, "hash", mins, maxs)
+    hidx = idx.cpu().numpy()
+    for binary in (False, True):
+        files, rows, nbytes = files_of(idx, n, P, [k, a, b], [8, 2, 8], binary, nulls=[None, na, None])
+        assert files == oracle.copy_files(hidx, [k, a, b], [8, 2, 8], P, binary, nulls=[None, na, None])
+    few = np.array([5, 6, 7])
+    idx, cnt, _ = _partition(cg, few, None, 8, "range", [0, 100, 200], [99, 199, 299])
+    for gen_empty in (False, True):
+        files, rows, nbytes = files_of(idx, 3, 3, [few], [8], True, gen_empty=gen_empty)
+        assert files == oracle.copy_files(idx.cpu().numpy(), [few], [8], 3, True, generate_empty_results=gen_empty)
+        assert len(files[1]) == (21 if gen_empty else 0)

@@ -387,3 +387,17 @@ def test_or_clauses_pushdown_goldens(oracle, expected):
     # an OR over two columns is never refuted by one column's range; a NULL arm is not TRUE
     r = t.scan(("or", (0, "=", 5), (1, "=", 0)), [], [oracle.count_star()])
     assert r.chunk_groups_filtered == 0 and r.rows_passed == 1
+
+
+def test_copy_files_match_the_golden_byte_counts(oracle, expected):
+    """expected/partitioned_intermediate_results.out: bytes_written of the text files (21/14/5/9) and the binary
+    files (93/57/39/75) of the squares table -- now from the oracle's actual file contents"""
+    i = np.arange(1, 11)
+    idx, _ = oracle.partition_rows(i, None, 4, "h", expected["squares_hash_mins"], expected["squares_hash_maxs"])
+    files = oracle.copy_files(idx, [i, i * i], [4, 4], 4, binary=False)
+    assert [[p, int((idx == p).sum()), len(files[p])] for p in range(4)] == expected["squares_hash_text"]
+    assert files[int(idx[0])].startswith(b"1\t1\n") or b"1\t1\n" in files[int(idx[0])]
+    idx, _ = oracle.partition_rows(i * i, None, 4, "r", [0, 21, 41, 61], [20, 40, 60, 100])
+    files = oracle.copy_files(idx, [i, i * i], [4, 4], 4, binary=True)
+    assert [[p, int((idx == p).sum()), len(files[p])] for p in range(4)] == expected["squares_range_binary"]
+    assert files[0][:11] == b"PGCOPY\n\xff\r\n\0" and files[0][-2:] == b"\xff\xff"
