@@ -865,16 +865,21 @@ def run_c4(env, args):
         sums[tname] = (int(k.sum()), int(pay.sum()))
     torch.cuda.synchronize()
 
-    def step():
+    def shuffle():
         got_r = cgd.repartition_exchange(0, [tables["r"][0].data_ptr(), tables["r"][1].data_ptr()], n, P)
         got_s = cgd.repartition_exchange(1, [tables["s"][0].data_ptr(), tables["s"][1].data_ptr()], n, P)
         cgd.exchange_wait(0)
         cgd.exchange_wait(1)
+        return got_r, got_s
+
+    def step():
+        got_r, got_s = shuffle()
         r0, r1 = cgd.exchange_result(0, 2), cgd.exchange_result(1, 2)
         joined, jsum = cg.join_count_sum(r0["cols"][0], r0["cols"][1], r0["nrows"], r1["cols"][0], r1["cols"][1], r1["nrows"])
         return joined, jsum, got_r, got_s
 
-    ms, clocks, launches, _, _, last = env.timed(step, args.leg_steps, 2, profile=False)
+    shuffle_ms, sclocks, slaunches, _, _, _ = env.timed(shuffle, args.leg_steps, 2, profile=False)     # the config's metric: the shuffle
+    ms, clocks, launches, _, _, last = env.timed(step, max(args.leg_steps // 2, 2), 1, profile=False)  # shuffle + merge-side join
     joined, jsum, got_r, got_s = last
     r0, r1 = cgd.exchange_result(0, 2, timing=True), cgd.exchange_result(1, 2, timing=True)
     ex_ms = env.max_over_ranks(max(r0["exchange_ms"], r1["exchange_ms"]))
@@ -937,17 +942,20 @@ def run_c4(env, args):
     total_sum = tj[1] + (tj[2] << 32) + (tj[3] << 64)
     hbm_bytes = 2 * rows * 32                     # read 16 + write 16 B/row on the map side
     return {"workload": "C4: hash repartition of r(k,x), s(k,y), 256M rows each, P=32, + merge-side join count(*), sum(x+y)",
-            "n_gpus": world, "rows_per_s": 2 * rows / (ms / 1e3), "ms_per_step": ms, "partitions": P,
+            "n_gpus": world, "rows_per_s": 2 * rows / (shuffle_ms / 1e3), "ms_per_step": shuffle_ms, "partitions": P,
+            "step": "routing + scatter + all-to-all of both tables (the shuffle); the join is timed on top of it below",
+            "shuffle_plus_join": {"rows_per_s": 2 * rows / (ms / 1e3), "ms_per_step": ms, "join_ms": ms - shuffle_ms},
             "exchange_ms": ex_ms, "nvlink_gbs": (sent / 1e9) / (ex_ms / 1e3) if world > 1 and ex_ms > 0 else None,
             "nvlink_bytes": int(sent), "nvlink_peak_note": "900 GB/s per direction and GPU (NVLink 5)",
-            "hbm_gbs_map_side": hbm_bytes / 1e9 / (ms / 1e3) / world,
-            "frac": hbm_bytes / 1e9 / (ms / 1e3) / world / env.peak,
-            "frac_note": "whole step (routing + scatter + exchange + join) against 32 B/row of map-side HBM traffic",
+            "hbm_gbs_map_side": hbm_bytes / 1e9 / (shuffle_ms / 1e3) / world,
+            "frac": hbm_bytes / 1e9 / (shuffle_ms / 1e3) / world / env.peak,
+            "frac_note": "the whole shuffle step (routing + scatter + exchange of both tables) against SURVEY 8(d)'s 32 B/row of map-side "
+                         "HBM traffic per GPU",
             "joined_rows": int(tj[0]), "sum_x_plus_y": str(total_sum), "bit_exact": tj[4] == 0,
             "checks": "key and payload checksums conserved, every received row belongs to a partition this rank owns, routing and the "
                       "join bit-exact against the oracle on 1 M rows, join count and 128-bit sum equal an independent scatter_add/gather "
                       "computation at full size",
-            "clocks": clocks, "gpu_launches": launches, "cpu_arm": cpu}
+            "clocks": sclocks, "gpu_launches": slaunches, "cpu_arm": cpu}
 
 
 def cgd_device_view(torch, ptr, n):

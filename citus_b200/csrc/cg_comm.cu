@@ -457,24 +457,11 @@ extern "C" int cg_comm_repartition_exchange(int32_t slot, const int64_t *const *
 		CG_CUDA(cudaEventCreate(&S.t0));
 		CG_CUDA(cudaEventCreate(&S.t1));
 	}
-	/* routing (hashint4/8 -> token ranges) and the histogram, on the compute stream */
-	int rc = devbuf_grow(&S.index, (size_t) std::max<int64_t>(n, 1) * sizeof(int32_t) + (size_t) (P + 1) * sizeof(int64_t) + 64);
+	/* routing (hashint4/8 -> token ranges) + histogram, then the scatter into destination-major order, on the compute
+	 * stream; the counts of every rank are exchanged on the side stream while the scatter runs */
+	int rc = devbuf_grow(&S.index, (size_t) (P + 1) * sizeof(int64_t) + 64);
 	if (rc) return rc;
-	int32_t *d_index = (int32_t *) S.index.p;
-	int64_t *d_counts = (int64_t *) (S.index.p + (((size_t) std::max<int64_t>(n, 1) * sizeof(int32_t) + 15) & ~(size_t) 15));
-	rc = cg_partition_index_async(d_cols[0], d_key_nulls, n, key_len, 1, mins, maxs, P, d_index, d_counts);
-	if (rc) return rc;
-	CG_CUDA(cudaEventRecord(g_comm.ev_index, ctx->compute));
-	/* the counts of every rank, exchanged on the side stream while the scatter runs */
-	rc = comm_ensure_small((size_t) P * (W + 1) + 8);
-	if (rc) return rc;
-	CG_CUDA(cudaStreamWaitEvent(g_comm.side, g_comm.ev_index, 0));
-	if (W > 1)
-		CG_NCCL(g_nccl.AllGather(d_counts, g_comm.d_small, (size_t) P, ncclInt64, g_comm.comm, g_comm.side));
-	else
-		CG_CUDA(cudaMemcpyAsync(g_comm.d_small, d_counts, sizeof(int64_t) * P, cudaMemcpyDeviceToDevice, g_comm.side));
-	CG_CUDA(cudaMemcpyAsync(g_comm.h_small, g_comm.d_small, sizeof(int64_t) * P * W, cudaMemcpyDeviceToHost, g_comm.side));
-	/* scatter into destination-major order */
+	int64_t *d_counts = (int64_t *) S.index.p;
 	std::vector<int32_t> position(P);
 	int nlocal = 0;
 	cg_comm_exchange_plan(P, W, me, nullptr, position.data(), nullptr, nullptr, nullptr, &nlocal);
@@ -482,9 +469,19 @@ extern "C" int cg_comm_repartition_exchange(int32_t slot, const int64_t *const *
 	if (rc) return rc;
 	std::vector<int64_t *> outs(ncols);
 	for (int c = 0; c < ncols; c++) outs[c] = (int64_t *) S.send.p + (size_t) c * n;
-	rc = cg_partition_scatter_async(d_index, n, P, position.data(), d_cols, ncols, outs.data());
+	rc = cg_partition_route_scatter_async(d_cols[0], d_key_nulls, n, key_len, 1, mins, maxs, P, position.data(), d_cols, ncols, outs.data(),
+										  d_counts, g_comm.ev_index);
 	if (rc) return rc;
 	CG_CUDA(cudaEventRecord(g_comm.ev_scatter, ctx->compute));
+	/* (P counts + the "could not find shard" counter) of every rank */
+	rc = comm_ensure_small((size_t) (P + 1) * (W + 1) + 8);
+	if (rc) return rc;
+	CG_CUDA(cudaStreamWaitEvent(g_comm.side, g_comm.ev_index, 0));
+	if (W > 1)
+		CG_NCCL(g_nccl.AllGather(d_counts, g_comm.d_small, (size_t) P + 1, ncclInt64, g_comm.comm, g_comm.side));
+	else
+		CG_CUDA(cudaMemcpyAsync(g_comm.d_small, d_counts, sizeof(int64_t) * (P + 1), cudaMemcpyDeviceToDevice, g_comm.side));
+	CG_CUDA(cudaMemcpyAsync(g_comm.h_small, g_comm.d_small, sizeof(int64_t) * (P + 1) * W, cudaMemcpyDeviceToHost, g_comm.side));
 	CG_CUDA(cudaStreamSynchronize(g_comm.side));               /* counts are on the host; the scatter keeps running */
 	std::vector<int64_t> counts((size_t) W * P), send_rows(W), recv_rows(W);
 	int64_t unroutable = 0;

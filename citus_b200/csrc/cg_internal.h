@@ -361,6 +361,11 @@ int cg_partition_index_async(const int64_t *d_keys, const uint8_t *d_nulls, int6
 int cg_partition_scatter_async(const int32_t *d_index, int64_t n, int32_t P, const int32_t *h_order, const int64_t *const *d_cols,
 							   int32_t ncols, int64_t *const *d_out);
 
+int cg_partition_route_scatter_async(const int64_t *d_keys, const uint8_t *d_nulls, int64_t n, int32_t key_len, int32_t by_hash,
+									 const int32_t *mins, const int32_t *maxs, int32_t P, const int32_t *h_order,
+									 const int64_t *const *d_cols, int32_t ncols, int64_t *const *d_out, int64_t *d_counts,
+									 cudaEvent_t after_counts);
+
 /* cg_plan.cpp */
 int cg_partial_shape(CgPartial *p, const CgScanDesc *desc, const CgColumnDesc *columns, int32_t natts,
 					 int64_t key_min, int64_t key_max, int64_t max_rows);

@@ -216,6 +216,201 @@ cg_partition_scatter_kernel(const __grid_constant__ ScatterParams A)
 	}
 }
 
+/*
+ * The scatter the repartition uses: same stable order, but (1) the partition of a row may be computed on the fly from
+ * its key (ROUTE: hashint4/8 + interval search, no index array is ever written or read), and (2) rows are first placed
+ * in partition order inside the block's shared memory and leave it as runs -- a block's rows of one partition are
+ * contiguous in the output, 4096 / P rows on average -- so global stores are coalesced 128-byte lines instead of one
+ * 8-byte store per row and column.  Traffic per row: keys once for the histogram + every column read once and written
+ * once (32 B/row for two columns, + 8 B for the routing pass).
+ */
+struct RouteParams
+{
+	const int64_t *keys;
+	const uint8_t *nulls;
+	int32_t key_len, by_hash;
+	const int32_t *mins, *maxs;      /* device, [P] */
+};
+
+struct StagedScatterParams
+{
+	const int32_t *index;            /* NULL in ROUTE mode */
+	RouteParams route;
+	int64_t n;
+	int32_t P, ncols;
+	const unsigned long long *block_offsets;   /* [nblocks][P] in output order */
+	const unsigned long long *part_base;       /* [P] in output order */
+	const int32_t *order;                      /* [P] output position of partition p, or NULL */
+	unsigned long long *errors;                /* ROUTE: rows whose hash lies in no interval */
+	const int64_t *cols[8];
+	int64_t *out[8];
+};
+
+__device__ __forceinline__ int route_row(const RouteParams &R, const int32_t *s_min, const int32_t *s_max, int P, int64_t r, bool *unroutable)
+{
+	if (R.nulls && R.nulls[r]) return 0;
+	const int64_t k = R.keys[r];
+	const int64_t searched = R.by_hash ? (int64_t) (R.key_len == 4 ? (int32_t) hash_bytes_uint32((uint32_t) (int32_t) k) : hashint8_dev(k))
+									   : (R.key_len == 4 ? (int64_t) (int32_t) k : k);
+	int lower = 0, upper = P;
+	while (lower < upper)
+	{
+		int middle = (lower + upper) / 2;
+		if (searched < s_min[middle]) { upper = middle; continue; }
+		if (searched <= s_max[middle]) return middle;
+		lower = middle + 1;
+	}
+	*unroutable = true;
+	return 0;
+}
+
+/* routing + histogram without materialising the index: block_counts[b][position(p)], counts[p] (partition order), errors */
+__global__ void __launch_bounds__(CGP_THREADS)
+cg_route_hist_kernel(const RouteParams R, int64_t n, int P, const int32_t *order, unsigned long long *block_counts,
+					 unsigned long long *counts, unsigned long long *errors)
+{
+	extern __shared__ unsigned int s_hist[];      /* [P] counts, [P] mins, [P] maxs */
+	int32_t *s_min = (int32_t *) (s_hist + P), *s_max = s_min + P;
+	for (int p = threadIdx.x; p < P; p += CGP_THREADS) { s_hist[p] = 0; s_min[p] = R.mins[p]; s_max[p] = R.maxs[p]; }
+	__syncthreads();
+	const int64_t base = (int64_t) blockIdx.x * CGP_ROWS_PER_BLOCK;
+	unsigned int nbad = 0;
+	for (int i = threadIdx.x; i < CGP_ROWS_PER_BLOCK; i += CGP_THREADS)
+	{
+		int64_t r = base + i;
+		if (r >= n) break;
+		bool bad = false;
+		atomicAdd(&s_hist[route_row(R, s_min, s_max, P, r, &bad)], 1u);
+		nbad += bad ? 1u : 0u;
+	}
+	if (nbad) atomicAdd(errors, (unsigned long long) nbad);
+	__syncthreads();
+	for (int p = threadIdx.x; p < P; p += CGP_THREADS)
+	{
+		unsigned int c = s_hist[p];
+		block_counts[(uint64_t) blockIdx.x * P + (order ? order[p] : p)] = c;
+		if (c) atomicAdd(counts + p, (unsigned long long) c);
+	}
+}
+
+template <bool ROUTE>
+__global__ void __launch_bounds__(CGP_THREADS)
+cg_scatter_staged_kernel(const __grid_constant__ StagedScatterParams A)
+{
+	constexpr int WARPS = CGP_THREADS / 32;
+	constexpr int SEG = CGP_ROWS_PER_BLOCK / WARPS;
+	constexpr int STEPS = SEG / 32;
+	extern __shared__ unsigned long long s_mem[];
+	unsigned long long *s_stage = s_mem;                                        /* [4096] one column of the block, in partition order */
+	unsigned long long *s_gbase = s_stage + CGP_ROWS_PER_BLOCK;                 /* [P] global position of the block's first row of p */
+	unsigned int *s_lstart = (unsigned int *) (s_gbase + A.P);                  /* [P + 1] local position of the block's first row of p */
+	unsigned int *s_cnt = s_lstart + A.P + 1;                                   /* [WARPS][P] per-warp counts, then running local offsets */
+	int32_t *s_min = (int32_t *) (s_cnt + WARPS * A.P), *s_max = s_min + A.P;   /* ROUTE: interval bounds */
+	const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	unsigned int *mine = s_cnt + warp * A.P;
+	for (int p = threadIdx.x; p < WARPS * A.P; p += CGP_THREADS) s_cnt[p] = 0;
+	if (ROUTE)
+		for (int p = threadIdx.x; p < A.P; p += CGP_THREADS) { s_min[p] = A.route.mins[p]; s_max[p] = A.route.maxs[p]; }
+	__syncthreads();
+	const int64_t seg0 = (int64_t) blockIdx.x * CGP_ROWS_PER_BLOCK + (int64_t) warp * SEG;
+	short idx[STEPS];
+	unsigned short lpos[STEPS];
+	bool bad = false;
+	/* pass A: partition of every row of this warp's segment, per-warp histogram (match.any groups the lanes of a step) */
+#pragma unroll
+	for (int st = 0; st < STEPS; st++)
+	{
+		const int64_t r = seg0 + st * 32 + lane;
+		int p = -1;
+		if (r < A.n)
+		{
+			p = ROUTE ? route_row(A.route, s_min, s_max, A.P, r, &bad) : A.index[r];
+			if (A.order) p = A.order[p];
+		}
+		idx[st] = (short) p;
+		const unsigned peers = __match_any_sync(0xffffffffu, p);
+		if (p >= 0 && lane == (unsigned) (__ffs(peers) - 1)) mine[p] += __popc(peers);
+		__syncwarp();
+	}
+	(void) bad;                     /* unroutable rows were counted (and reported) by the histogram pass */
+	__syncthreads();
+	/* block totals per partition -> local starts (exclusive scan over P), global bases, per-warp running offsets */
+	{
+		const int per = (A.P + CGP_THREADS - 1) / CGP_THREADS;
+		const int p0 = threadIdx.x * per, p1 = min(p0 + per, A.P);
+		unsigned int local = 0;
+		for (int p = p0; p < p1; p++)
+			for (int w = 0; w < WARPS; w++) local += s_cnt[w * A.P + p];
+		/* exclusive scan of `local` over the 256 threads: warp scan + warp totals through s_lstart's tail (reused below) */
+		unsigned int incl = local;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			unsigned int y = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= (unsigned) o) incl += y;
+		}
+		__shared__ unsigned int s_warp_tot[WARPS];
+		if (lane == 31) s_warp_tot[warp] = incl;
+		__syncthreads();
+		unsigned int before = incl - local;
+		for (unsigned w = 0; w < warp; w++) before += s_warp_tot[w];
+		unsigned int run = before;
+		for (int p = p0; p < p1; p++)
+		{
+			s_lstart[p] = run;
+			s_gbase[p] = A.part_base[p] + A.block_offsets[(uint64_t) blockIdx.x * A.P + p];
+			unsigned int wrun = run;
+			for (int w = 0; w < WARPS; w++)
+			{
+				unsigned int c = s_cnt[w * A.P + p];
+				s_cnt[w * A.P + p] = wrun;
+				wrun += c;
+			}
+			run = wrun;
+		}
+		if (threadIdx.x == CGP_THREADS - 1) s_lstart[A.P] = run;          /* rows in this block (threads past P contribute 0) */
+	}
+	__syncthreads();
+	const unsigned int block_rows = s_lstart[A.P];
+	/* pass B: local position of every row (input order inside a partition) */
+#pragma unroll
+	for (int st = 0; st < STEPS; st++)
+	{
+		const int p = idx[st];
+		const unsigned peers = __match_any_sync(0xffffffffu, p);
+		if (p >= 0) lpos[st] = (unsigned short) (mine[p] + __popc(peers & ((1u << lane) - 1u)));
+		__syncwarp();
+		if (p >= 0 && lane == (unsigned) (__ffs(peers) - 1)) mine[p] += __popc(peers);
+		__syncwarp();
+	}
+	/* column by column: into partition order in shared memory, out as coalesced runs */
+	for (int c = 0; c < A.ncols; c++)
+	{
+		__syncthreads();
+#pragma unroll
+		for (int st = 0; st < STEPS; st++)
+			if (idx[st] >= 0) s_stage[lpos[st]] = (unsigned long long) A.cols[c][seg0 + st * 32 + lane];
+		__syncthreads();
+		for (unsigned int j = threadIdx.x; j < block_rows; j += CGP_THREADS)
+		{
+			/* the partition whose local range holds j: the last p with s_lstart[p] <= j */
+			int lo = 0, hi = A.P;
+			while (hi - lo > 1)
+			{
+				int mid = (lo + hi) >> 1;
+				if (s_lstart[mid] <= j) lo = mid; else hi = mid;
+			}
+			A.out[c][s_gbase[lo] + (j - s_lstart[lo])] = (int64_t) s_stage[j];
+		}
+	}
+}
+
+static size_t staged_scatter_smem(int P)
+{
+	return sizeof(unsigned long long) * (CGP_ROWS_PER_BLOCK + (size_t) P) + sizeof(unsigned int) * ((size_t) P + 1 + (CGP_THREADS / 32) * (size_t) P) +
+		   sizeof(int32_t) * 2 * (size_t) P + 16;
+}
+
 static int32_t *g_d_bounds = nullptr;
 static int g_bounds_cap = 0;
 
@@ -392,18 +587,17 @@ static int partition_scatter_enqueue(CgContext *ctx, const int32_t *d_index, int
 		CG_CUDA(cudaGetLastError()); g_cg_launches++;
 		cg_partition_base_kernel<<<1, 32, 0, ctx->compute>>>(d_tot, d_base, P);
 		CG_CUDA(cudaGetLastError()); g_cg_launches++;
-		ScatterParams S;
+		StagedScatterParams S;
 		memset(&S, 0, sizeof S);
 		S.index = d_index; S.n = n; S.P = P; S.ncols = ncols; S.block_offsets = d_block; S.part_base = d_base; S.order = d_order;
 		for (int c = 0; c < ncols; c++) { S.cols[c] = d_cols[c]; S.out[c] = d_out[c]; }
 		static bool smem_configured = false;
 		if (!smem_configured)
 		{
-			CG_CUDA(cudaFuncSetAttribute(cg_partition_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-										 (int) ((CGP_THREADS / 32) * CGP_MAX_P * sizeof(unsigned long long))));
+			CG_CUDA(cudaFuncSetAttribute(cg_scatter_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) staged_scatter_smem(CGP_MAX_P)));
 			smem_configured = true;
 		}
-		cg_partition_scatter_kernel<<<(unsigned) nblocks, CGP_THREADS, (CGP_THREADS / 32) * P * sizeof(unsigned long long), ctx->compute>>>(S);
+		cg_scatter_staged_kernel<false><<<(unsigned) nblocks, CGP_THREADS, staged_scatter_smem(P), ctx->compute>>>(S);
 		CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	}
 	if (h_offsets)
@@ -422,6 +616,80 @@ int cg_partition_scatter_async(const int32_t *d_index, int64_t n, int32_t P, con
 	CgContext *ctx = cg_ctx();
 	if (!ctx) return CG_EINVAL;
 	return partition_scatter_enqueue(ctx, d_index, n, P, h_order, d_cols, ncols, d_out, nullptr);
+}
+
+/* routing + scatter without an index array (the repartition exchange): d_counts[P] rows per partition and d_counts[P] =
+ * rows whose hash lies in no interval are ready on the compute stream after the first kernel; the caller records an
+ * event between the two phases through `after_counts` */
+int cg_partition_route_scatter_async(const int64_t *d_keys, const uint8_t *d_nulls, int64_t n, int32_t key_len, int32_t by_hash,
+									 const int32_t *mins, const int32_t *maxs, int32_t P, const int32_t *h_order,
+									 const int64_t *const *d_cols, int32_t ncols, int64_t *const *d_out, int64_t *d_counts,
+									 cudaEvent_t after_counts)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx) return CG_EINVAL;
+	if (P <= 0 || P > CGP_MAX_P) return cg_set_error(CG_EINVAL, "bad partition count %d", P);
+	if (key_len != 4 && key_len != 8) return cg_set_error(CG_EINVAL, "key_len must be 4 or 8");
+	if (ncols < 1 || ncols > 8 || n < 0 || !d_counts || !mins || !maxs || !h_order) return cg_set_error(CG_EINVAL, "bad argument");
+	if (g_bounds_cap < 2 * P + 2)
+	{
+		cudaFree(g_d_bounds);
+		CG_CUDA(cudaMalloc(&g_d_bounds, sizeof(int32_t) * (2 * CGP_MAX_P + 2)));
+		g_bounds_cap = 2 * CGP_MAX_P + 2;
+	}
+	/* interval bounds + output positions through a pinned bounce buffer (asynchronous copies) */
+	static int32_t *h_pin = nullptr;
+	static cudaEvent_t pin_free = nullptr;
+	if (!h_pin) CG_CUDA(cudaHostAlloc((void **) &h_pin, sizeof(int32_t) * 3 * CGP_MAX_P, cudaHostAllocDefault));
+	if (!pin_free) CG_CUDA(cudaEventCreateWithFlags(&pin_free, cudaEventDisableTiming));
+	CG_CUDA(cudaEventSynchronize(pin_free));
+	memcpy(h_pin, mins, sizeof(int32_t) * P);
+	memcpy(h_pin + CGP_MAX_P, maxs, sizeof(int32_t) * P);
+	memcpy(h_pin + 2 * CGP_MAX_P, h_order, sizeof(int32_t) * P);
+	const int64_t nblocks = (n + CGP_ROWS_PER_BLOCK - 1) / CGP_ROWS_PER_BLOCK;
+	CgAsyncBuf block_buf, tot_buf, order_buf;
+	CG_CUDA(block_buf.alloc(sizeof(unsigned long long) * (size_t) std::max<int64_t>(nblocks, 1) * P, ctx->compute));
+	CG_CUDA(tot_buf.alloc(sizeof(unsigned long long) * (2 * P + 1), ctx->compute));
+	CG_CUDA(order_buf.alloc(sizeof(int32_t) * P, ctx->compute));
+	unsigned long long *d_block = block_buf.as<unsigned long long>(), *d_tot = tot_buf.as<unsigned long long>(), *d_base = d_tot + P;
+	int32_t *d_order = order_buf.as<int32_t>();
+	CG_CUDA(cudaMemcpyAsync(g_d_bounds, h_pin, sizeof(int32_t) * P, cudaMemcpyHostToDevice, ctx->compute));
+	CG_CUDA(cudaMemcpyAsync(g_d_bounds + CGP_MAX_P, h_pin + CGP_MAX_P, sizeof(int32_t) * P, cudaMemcpyHostToDevice, ctx->compute));
+	CG_CUDA(cudaMemcpyAsync(d_order, h_pin + 2 * CGP_MAX_P, sizeof(int32_t) * P, cudaMemcpyHostToDevice, ctx->compute));
+	CG_CUDA(cudaEventRecord(pin_free, ctx->compute));
+	CG_CUDA(cudaMemsetAsync(d_tot, 0, sizeof(unsigned long long) * (2 * P + 1), ctx->compute));
+	CG_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int64_t) * (P + 1), ctx->compute));
+	RouteParams R;
+	R.keys = d_keys; R.nulls = d_nulls; R.key_len = key_len; R.by_hash = by_hash; R.mins = g_d_bounds; R.maxs = g_d_bounds + CGP_MAX_P;
+	if (n > 0)
+	{
+		cg_route_hist_kernel<<<(unsigned) nblocks, CGP_THREADS, 3 * P * sizeof(int32_t), ctx->compute>>>(R, n, P, d_order, d_block,
+																										  (unsigned long long *) d_counts,
+																										  (unsigned long long *) (d_counts + P));
+		CG_CUDA(cudaGetLastError()); g_cg_launches++;
+	}
+	if (after_counts) CG_CUDA(cudaEventRecord(after_counts, ctx->compute));
+	if (n > 0)
+	{
+		cg_partition_scan2_kernel<<<P, 1024, 0, ctx->compute>>>(d_block, d_tot, nblocks, P);
+		CG_CUDA(cudaGetLastError()); g_cg_launches++;
+		cg_partition_base_kernel<<<1, 32, 0, ctx->compute>>>(d_tot, d_base, P);
+		CG_CUDA(cudaGetLastError()); g_cg_launches++;
+		StagedScatterParams S;
+		memset(&S, 0, sizeof S);
+		S.route = R; S.n = n; S.P = P; S.ncols = ncols; S.block_offsets = d_block; S.part_base = d_base; S.order = d_order;
+		S.errors = (unsigned long long *) (d_counts + P);
+		for (int c = 0; c < ncols; c++) { S.cols[c] = d_cols[c]; S.out[c] = d_out[c]; }
+		static bool smem_configured = false;
+		if (!smem_configured)
+		{
+			CG_CUDA(cudaFuncSetAttribute(cg_scatter_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) staged_scatter_smem(CGP_MAX_P)));
+			smem_configured = true;
+		}
+		cg_scatter_staged_kernel<true><<<(unsigned) nblocks, CGP_THREADS, staged_scatter_smem(P), ctx->compute>>>(S);
+		CG_CUDA(cudaGetLastError()); g_cg_launches++;
+	}
+	return CG_OK;
 }
 
 extern "C" int cg_partition_scatter_ordered(const int32_t *d_index, int64_t n, int32_t P, const int32_t *h_order,
