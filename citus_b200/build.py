@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libcitus_gpu.so")
-SOURCES = ["cg_scan.cu", "cg_decompress.cu", "cg_scan_fast.cu", "cg_scan_small.cu", "cg_partition.cu", "cg_join.cu", "cg_comm.cu", "cg_values.cu", "cg_host.cpp", "cg_plan.cpp", "cg_numeric.cpp", "cg_gen.cpp", "cg_jit.cpp"]
+SOURCES = ["cg_scan.cu", "cg_decompress.cu", "cg_scan_fast.cu", "cg_scan_small.cu", "cg_partition.cu", "cg_join.cu", "cg_comm.cu", "cg_values.cu", "cg_varlena.cu", "cg_host.cpp", "cg_plan.cpp", "cg_numeric.cpp", "cg_gen.cpp", "cg_jit.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

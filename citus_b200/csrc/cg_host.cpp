@@ -492,6 +492,9 @@ struct StagePlan
 	std::vector<uint64_t> cg_begin;     /* arena offset where each chunk group starts; [ncg+1] */
 	std::vector<DecodeItem> decode;     /* compressed value streams, in chunk-group order */
 	std::vector<uint32_t> dec_first;    /* first decode item of each chunk group; [ncg+1] */
+	std::vector<VarlenaItem> varlena;   /* varlena value streams to decode to fixed width, in chunk-group order */
+	std::vector<uint32_t> vl_first;     /* first varlena item of each chunk group; [ncg+1] */
+	std::vector<uint32_t> stream_bytes; /* per (chunk group, staged column): uncompressed value-stream bytes (the algorithmic bytes) */
 	uint64_t wire_bytes = 0;            /* the chunk-group regions: what travels host -> device */
 	uint64_t arena_bytes = 0;           /* wire_bytes + the decompressed value slots */
 	uint64_t rows = 0;
@@ -513,6 +516,7 @@ static int plan_staging(const CgRelation *rel, const std::vector<int32_t> &stage
 			uint32_t rows = (uint32_t) rel->nodes[s.skipnode_base + k].row_count;
 			sp->cg_begin.push_back(off);
 			sp->dec_first.push_back((uint32_t) sp->decode.size());
+			sp->vl_first.push_back((uint32_t) sp->varlena.size());
 			sp->cg_rows.push_back(rows);
 			sp->rows += rows;
 			for (size_t j = 0; j < ns; j++)
@@ -541,7 +545,13 @@ static int plan_staging(const CgRelation *rel, const std::vector<int32_t> &stage
 					if (n.row_count != rows) return cg_set_error(CG_ECORRUPT, "row count mismatch in chunk group");
 					if (n.exists_length * 8 < rows) return cg_set_error(CG_ECORRUPT, "insufficient data for reading boolean array");
 					int len = rel->columns[c].attlen;
-					if (n.decompressed_size % len != 0 || n.decompressed_size / len > rows ||
+					const bool varlena = len < 0;
+					if (varlena)
+					{
+						if (comp == CG_COMPRESSION_NONE && n.value_length != n.decompressed_size)
+							return cg_set_error(CG_ECORRUPT, "value stream length mismatch in a varlena chunk");
+					}
+					else if (n.decompressed_size % len != 0 || n.decompressed_size / len > rows ||
 						(comp == CG_COMPRESSION_NONE && n.value_length != n.decompressed_size))
 						return cg_set_error(CG_ECORRUPT, "value stream of %llu bytes does not fit %u rows of %d bytes",
 											(unsigned long long) n.decompressed_size, rows, len);
@@ -552,7 +562,18 @@ static int plan_staging(const CgRelation *rel, const std::vector<int32_t> &stage
 					it.value_logical = s.file_offset + n.value_offset;
 					it.exists_len = (uint32_t) n.exists_length;
 					it.value_len = (uint32_t) n.value_length;
-					d.value_count = (uint32_t) (n.decompressed_size / len);
+					if (varlena)
+					{
+						/* the number of values of a varlena chunk is the number of set exists bits (NULL rows occupy no bytes) */
+						std::vector<uint8_t> bits(n.exists_length);
+						if (n.exists_length && storage_read(rel->pages, rel->nblocks, it.exists_logical, bits.data(), n.exists_length))
+							return cg_set_error(CG_ECORRUPT, "attempt to read columnar data past pd_lower / end of relation");
+						uint32_t nn = 0;
+						for (uint32_t r = 0; r < rows; r++) nn += (bits[r >> 3] >> (r & 7)) & 1u;
+						d.value_count = nn;
+					}
+					else
+						d.value_count = (uint32_t) (n.decompressed_size / len);
 				}
 				d.exists_off = off; off += pad16(std::max<uint64_t>((rows + 7) / 8, it.exists_len)) + 16;
 				d.values_off = off; off += pad16(it.value_len) + 16;
@@ -571,6 +592,16 @@ static int plan_staging(const CgRelation *rel, const std::vector<int32_t> &stage
 					d.rank_off = off; off += pad16(4ull * ((rows + 63) / 64));
 					sp->any_nulls = true;
 				}
+				if ((uint32_t) c < s.column_count && cg_is_varlena(rel->columns[c]))
+				{
+					/* src / dst are assigned below: src = the on-disk stream or its decompressed slot */
+					VarlenaItem vi;
+					vi.src = comp != CG_COMPRESSION_NONE ? ~0ull : it.wire_value_off; vi.dst = sp->cols.size();
+					vi.raw_len = (uint32_t) rawlen; vi.count = d.value_count;
+					vi.kind = (uint32_t) cg_type_class(rel->columns[c]); vi.scale = (uint32_t) cg_type_scale(rel->columns[c]);
+					sp->varlena.push_back(vi);
+				}
+				sp->stream_bytes.push_back((uint32_t) rawlen);
 				sp->cols.push_back(d);
 				sp->items.push_back(it);
 			}
@@ -578,6 +609,7 @@ static int plan_staging(const CgRelation *rel, const std::vector<int32_t> &stage
 	}
 	sp->cg_begin.push_back(off);
 	sp->dec_first.push_back((uint32_t) sp->decode.size());
+	sp->vl_first.push_back((uint32_t) sp->varlena.size());
 	sp->wire_bytes = off;
 	for (DecodeItem &di : sp->decode)
 	{
@@ -585,6 +617,15 @@ static int plan_staging(const CgRelation *rel, const std::vector<int32_t> &stage
 		d.values_off = off;
 		di.dst = off;
 		off += di.padded;
+	}
+	for (VarlenaItem &vi : sp->varlena)
+	{
+		/* the decoded fixed-width array; the stream it is decoded from is where values_off pointed so far */
+		DevChunkCol &d = sp->cols[vi.dst];
+		if (vi.src == ~0ull) vi.src = d.values_off;
+		d.values_off = off;
+		vi.dst = off;
+		off += pad16((uint64_t) vi.count * (vi.kind == CG_TYPE_NUMERIC ? 8 : 1)) + 16;
 	}
 	sp->arena_bytes = off;
 	return CG_OK;
@@ -695,7 +736,8 @@ extern "C" int cg_shard_stage(const CgRelation *rel, const int32_t *columns, int
 	for (int c : sh->staged)
 	{
 		int l = rel->columns[c].attlen;
-		if (l != 1 && l != 2 && l != 4 && l != 8) { delete sh; return cg_set_error(CG_EUNSUPPORTED, "column %d: attlen %d", c, l); }
+		if (l != 1 && l != 2 && l != 4 && l != 8 && !(l == -1 && (cg_type_class(rel->columns[c]) == CG_TYPE_NUMERIC || cg_type_class(rel->columns[c]) == CG_TYPE_BPCHAR1)))
+		{ delete sh; return cg_set_error(CG_EUNSUPPORTED, "column %d: attlen %d", c, l); }
 	}
 
 	StagePlan sp;
@@ -706,6 +748,7 @@ extern "C" int cg_shard_stage(const CgRelation *rel, const int32_t *columns, int
 	sh->nchunkgroups = sp.cg_rows.size();
 	sh->cg_rows = sp.cg_rows;
 	sh->h_chunkcols = sp.cols;
+	sh->h_stream_bytes = sp.stream_bytes;
 	sh->arena_bytes = sp.arena_bytes;
 	sh->stripes.assign(rel->stripes, rel->stripes + rel->nstripes);
 	sh->nodes.assign(rel->nodes, rel->nodes + rel->nnodes);
@@ -723,23 +766,33 @@ extern "C" int cg_shard_stage(const CgRelation *rel, const int32_t *columns, int
 	if (e != cudaSuccess) { cg_shard_free(sh); return cg_set_error(CG_ECUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(e)); }
 	/* compressed value streams are decoded block by block behind the H2D copies (K7) */
 	DecodeItem *d_decode = nullptr;
-	if (!sp.decode.empty())
+	VarlenaItem *d_varlena = nullptr;
+	if (!sp.decode.empty() || !sp.varlena.empty())
 	{
-		if (cudaMalloc(&d_decode, sp.decode.size() * sizeof(DecodeItem)) != cudaSuccess ||
-			cudaMemcpy(d_decode, sp.decode.data(), sp.decode.size() * sizeof(DecodeItem), cudaMemcpyHostToDevice) != cudaSuccess ||
+		if ((!sp.decode.empty() && (cudaMalloc(&d_decode, sp.decode.size() * sizeof(DecodeItem)) != cudaSuccess ||
+									cudaMemcpy(d_decode, sp.decode.data(), sp.decode.size() * sizeof(DecodeItem), cudaMemcpyHostToDevice) != cudaSuccess)) ||
+			(!sp.varlena.empty() && (cudaMalloc(&d_varlena, sp.varlena.size() * sizeof(VarlenaItem)) != cudaSuccess ||
+									 cudaMemcpy(d_varlena, sp.varlena.data(), sp.varlena.size() * sizeof(VarlenaItem), cudaMemcpyHostToDevice) != cudaSuccess)) ||
 			cudaMemsetAsync(ctx->d_stage_err, 0, sizeof(unsigned long long), ctx->compute) != cudaSuccess)
 		{
-			cudaFree(d_decode);
+			cudaFree(d_decode); cudaFree(d_varlena);
 			cg_shard_free(sh);
 			return cg_set_error(CG_ECUDA, "staging the decode list failed: %s", cudaGetErrorString(cudaGetLastError()));
 		}
 	}
 	rc = stream_to_device(ctx, rel, sp, ns, sh->d_arena, [&](uint64_t cg0, uint64_t cg1, cudaEvent_t copied) -> int {
 		uint32_t f = sp.dec_first[cg0], l = sp.dec_first[cg1];
-		if (f == l) return CG_OK;
+		uint32_t vf = sp.vl_first[cg0], vl = sp.vl_first[cg1];
+		if (f == l && vf == vl) return CG_OK;
 		CG_CUDA(cudaStreamWaitEvent(ctx->compute, copied, 0));
-		return cg_launch_decompress(ctx, sh->d_arena, d_decode + f, sp.decode.data() + f, l - f, ctx->d_stage_err, CG_ERRFLAG_DECOMPRESS,
-									ctx->compute);
+		int r = CG_OK;
+		if (f != l)
+			r = cg_launch_decompress(ctx, sh->d_arena, d_decode + f, sp.decode.data() + f, l - f, ctx->d_stage_err, CG_ERRFLAG_DECOMPRESS,
+									 ctx->compute);
+		/* varlena value streams (decompressed first when they were compressed) -> dense fixed-width arrays */
+		if (r == CG_OK && vf != vl)
+			r = cg_launch_varlena_decode(ctx, sh->d_arena, d_varlena + vf, vl - vf, ctx->d_stage_err, CG_ERRFLAG_VARLENA, ctx->compute);
+		return r;
 	});
 	if (rc == CG_OK && sp.any_nulls)
 	{
@@ -759,14 +812,16 @@ extern "C" int cg_shard_stage(const CgRelation *rel, const int32_t *columns, int
 		cudaStreamSynchronize(ctx->copy);
 		cudaStreamSynchronize(ctx->compute);
 	}
-	if (rc == CG_OK && d_decode)
+	if (rc == CG_OK && (d_decode || d_varlena))
 	{
 		unsigned long long flags = 0;
 		cudaError_t e2 = cudaMemcpy(&flags, ctx->d_stage_err, sizeof flags, cudaMemcpyDeviceToHost);
 		if (e2 != cudaSuccess) rc = cg_set_error(CG_ECUDA, "%s", cudaGetErrorString(e2));
 		else if (flags & CG_ERRFLAG_DECOMPRESS) rc = cg_set_error(CG_ECORRUPT, "cannot decompress the buffer");
+		else if (flags & CG_ERRFLAG_VARLENA) rc = cg_set_error(CG_EUNSUPPORTED, "a numeric value is NaN, has more fractional digits than the column's scale or "
+																					"does not fit 64 bits, or a varlena stream is malformed");
 	}
-	cudaFree(d_decode);
+	cudaFree(d_decode); cudaFree(d_varlena);
 	if (rc) { cg_shard_free(sh); return rc; }
 	*out = sh;
 	return CG_OK;
@@ -818,6 +873,9 @@ static int check_error_flags(CgPartial *p, unsigned long long flags)
 		return cg_set_error(CG_EINVAL, "sum argument exceeds term_abs_bound");
 	if (flags & CG_ERRFLAG_DECOMPRESS)
 		return cg_set_error(CG_ECORRUPT, "cannot decompress the buffer");
+	if (flags & CG_ERRFLAG_VARLENA)
+		return cg_set_error(CG_EUNSUPPORTED, "a numeric value is NaN, has more fractional digits than the column's scale or does not fit 64 bits, "
+											 "or a varlena stream is malformed");
 	return CG_OK;
 }
 
@@ -888,7 +946,7 @@ extern "C" int cg_scan_shard(const CgShard *sh, const CgScanDesc *desc, CgPartia
 	{
 		std::vector<uint32_t> fastl, slowl;
 		uint64_t rows_fast = 0, rows_slow = 0;
-		uint32_t nullmask = 0;
+		uint32_t nullmask = 0, max_cg_rows = 0;
 		fastl.reserve(sh->nchunkgroups);
 		int64_t nfiltered = 0;
 		std::vector<uint8_t> mask;
@@ -910,6 +968,7 @@ extern "C" int cg_scan_shard(const CgShard *sh, const CgScanDesc *desc, CgPartia
 				}
 				(nulls ? slowl : fastl).push_back((uint32_t) cg);
 				(nulls ? rows_slow : rows_fast) += sh->cg_rows[cg];
+				max_cg_rows = std::max(max_cg_rows, sh->cg_rows[cg]);
 			}
 		}
 		msh->sel_nfast = (uint32_t) fastl.size();
@@ -922,6 +981,7 @@ extern "C" int cg_scan_shard(const CgShard *sh, const CgScanDesc *desc, CgPartia
 		msh->sel_pushdown = desc->enable_qual_pushdown;
 		msh->sel_nquals = desc->nquals;
 		msh->sel_nullmask = nullmask;
+		msh->sel_max_cg_rows = max_cg_rows;
 		msh->sel_rows_fast = rows_fast;
 		msh->sel_rows_total = rows_fast + rows_slow;
 		msh->sel_nqexpr = desc->nqual_expr;
@@ -949,6 +1009,7 @@ extern "C" int cg_scan_shard(const CgShard *sh, const CgScanDesc *desc, CgPartia
 		plan.nstaged = (int32_t) sh->staged.size();
 		plan.selected = sh->d_selected;
 		plan.nselected = (uint32_t) selected.size();
+		plan.max_cg_rows = sh->sel_max_cg_rows;
 		FPlan fast;
 		const bool use_small = cg_small_eligible(plan) && !cg_force_general();
 		bool use_fast = !use_small && !cg_force_general() && cg_jit_level() < 2 && cg_build_fast_plan(desc, plan, all8, &fast);
@@ -1231,7 +1292,7 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 		for (int c = 0; c < plan.ncols; c++)
 		{
 			const DevChunkCol &d = sp.cols[g * ns + plan.slot[c]];
-			bytes += (uint64_t) d.value_count * plan.len[c] + (d.row_count + 7) / 8;
+			bytes += (uint64_t) sp.stream_bytes[g * ns + plan.slot[c]] + (d.row_count + 7) / 8;
 		}
 
 	uint8_t *d_arena = nullptr;
@@ -1256,9 +1317,11 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 		const size_t ids_bytes = ncg * sizeof(uint32_t);
 		const size_t items_bytes = items.size() * sizeof(RealignItem);
 		const size_t dec_bytes = sp.decode.size() * sizeof(DecodeItem);
+		const size_t vl_bytes = sp.varlena.size() * sizeof(VarlenaItem);
 		const size_t off_ids = (cols_bytes + 15) & ~15ull, off_items = off_ids + ((ids_bytes + 15) & ~15ull);
 		const size_t off_dec = off_items + ((items_bytes + 15) & ~15ull);
-		const size_t meta_bytes = off_dec + dec_bytes + 64;
+		const size_t off_vl = off_dec + ((dec_bytes + 15) & ~15ull);
+		const size_t meta_bytes = off_vl + vl_bytes + 64;
 		const int mslot = ctx->dma_slot;
 		ctx->dma_slot = (mslot + 1) % CgContext::kDmaDepth;
 		if (!ctx->dma_done[mslot]) CG_CUDA(cudaEventCreateWithFlags(&ctx->dma_done[mslot], cudaEventDisableTiming));
@@ -1298,13 +1361,16 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 		for (uint64_t g = 0; g < ncg; g++) ((uint32_t *) (hm + off_ids))[g] = (uint32_t) g;
 		if (items_bytes) memcpy(hm + off_items, items.data(), items_bytes);
 		if (dec_bytes) memcpy(hm + off_dec, sp.decode.data(), dec_bytes);
+		if (vl_bytes) memcpy(hm + off_vl, sp.varlena.data(), vl_bytes);
 		CG_CUDA(cudaMemcpyAsync(d_meta, hm, meta_bytes, cudaMemcpyHostToDevice, ctx->copy));
 		d_cols = (DevChunkCol *) d_meta;
 		d_ids = (uint32_t *) (d_meta + off_ids);
 		const DecodeItem *d_decode = (const DecodeItem *) (d_meta + off_dec);
+		const VarlenaItem *d_varlena = (const VarlenaItem *) (d_meta + off_vl);
 		plan.arena = d_arena;
 		plan.chunkcols = d_cols;
 		plan.nstaged = (int32_t) ns;
+		for (uint32_t r : sp.cg_rows) plan.max_cg_rows = std::max(plan.max_cg_rows, r);
 		FPlan fast;
 		const bool use_small = cg_small_eligible(plan) && !cg_force_general();
 		const bool use_fast = !use_small && !sp.any_nulls && !cg_force_general() && cg_jit_level() < 2 &&
@@ -1328,8 +1394,13 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 			/* K7: compressed value streams of the block -> their value slots */
 			int r = CG_OK;
 			if (!decode_done)
+			{
 				r = cg_launch_decompress(ctx, d_arena, d_decode + sp.dec_first[cg0], sp.decode.data() + sp.dec_first[cg0],
 										 sp.dec_first[cg1] - sp.dec_first[cg0], into->d_stats + 2, CG_ERRFLAG_DECOMPRESS, ctx->compute);
+				if (r == CG_OK)
+					r = cg_launch_varlena_decode(ctx, d_arena, d_varlena + sp.vl_first[cg0], sp.vl_first[cg1] - sp.vl_first[cg0], into->d_stats + 2,
+												 CG_ERRFLAG_VARLENA, ctx->compute);
+			}
 			if (r) return r;
 			if (sp.any_nulls)
 			{
@@ -1411,7 +1482,7 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 			/* zstd decoders share one literal scratch area: they stay on the compute stream */
 			bool has_zstd = false;
 			for (const DecodeItem &di : sp.decode) if (di.kind == CG_COMPRESSION_ZSTD) { has_zstd = true; break; }
-			if (!sp.decode.empty() && !trace && !has_zstd)
+			if ((!sp.decode.empty() || !sp.varlena.empty()) && !trace && !has_zstd)
 			{
 				/* de-framing and decompression run on one of two side streams, the scan follows on the
 				 * compute stream: the decode of this shard overlaps the decode (and scan) of the previous one */
@@ -1425,6 +1496,8 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 				if (rc == CG_OK)
 					rc = cg_launch_decompress(ctx, d_arena, d_decode, sp.decode.data(), sp.decode.size(), into->d_stats + 2,
 											  CG_ERRFLAG_DECOMPRESS, side);
+				if (rc == CG_OK)
+					rc = cg_launch_varlena_decode(ctx, d_arena, d_varlena, sp.varlena.size(), into->d_stats + 2, CG_ERRFLAG_VARLENA, side);
 				if (rc) return rc;
 				CG_CUDA(cudaEventRecord(ctx->decoded[mslot], side));
 				ready = ctx->decoded[mslot];

@@ -116,6 +116,7 @@ struct CgShard
 	uint64_t arena_bytes = 0;
 	DevChunkCol *d_chunkcols = nullptr;      /* [nchunkgroups][nstaged] */
 	std::vector<DevChunkCol> h_chunkcols;
+	std::vector<uint32_t> h_stream_bytes;    /* uncompressed value-stream bytes per (chunk group, staged column) */
 	std::vector<uint32_t> cg_rows;           /* rows per chunk group */
 	/* host copy of the metadata needed for chunk-group skipping */
 	std::vector<CgStripe> stripes;
@@ -134,11 +135,12 @@ struct CgShard
 	/* the list is ordered [chunk groups without NULLs in the plan columns | the rest] */
 	std::vector<uint8_t> sel_slots;
 	uint32_t sel_nfast = 0;
+	uint32_t sel_max_cg_rows = 0;
 	uint64_t sel_rows_fast = 0, sel_rows_total = 0;   /* rows of the first part / of the whole selection */
 	uint64_t algorithmic_bytes_per_cg_col(uint64_t cg, int slot) const
 	{
 		const DevChunkCol &c = h_chunkcols[cg * staged.size() + slot];
-		return (uint64_t) c.value_count * columns[staged[slot]].attlen + (c.row_count + 7) / 8;
+		return (uint64_t) h_stream_bytes[cg * staged.size() + slot] + (c.row_count + 7) / 8;
 	}
 };
 
@@ -223,7 +225,11 @@ struct KPlan
 	/* WHERE tree in postfix form over the atoms above (0 tokens = AND of all atoms) */
 	int32_t nqexpr;
 	int8_t qexpr[CG_MAX_QEXPR];
-	int32_t pad_;
+	/* work units: a chunk group is cut into `slices` row ranges of slice_rows rows (the last one shorter) when a launch has
+	 * too few chunk groups to fill the GPU (small shards); 1 = one unit per chunk group */
+	int32_t slices;
+	uint32_t slice_rows;
+	uint32_t max_cg_rows;         /* largest chunk group of the launch (host-known; 0 = unknown: no slicing) */
 };
 
 /* plan of the specialised kernel (cg_scan_fast.cu): column roles in fixed order
@@ -253,7 +259,22 @@ struct FPlan
 	uint64_t *packed;             /* non-NULL: count(*) and sum number pack_sum share one word */
 	int32_t pack_shift;
 	int32_t pack_sum;
+	int32_t slices;               /* see KPlan */
+	uint32_t slice_rows;
+	uint32_t max_cg_rows;
 };
+/* how many row ranges a chunk group is cut into so that `nselected` chunk groups give a launch of `grid_full` CTAs at least two
+ * units per CTA; step = rows one CTA iteration covers (slice boundaries stay multiples of it) */
+static inline void cg_choose_slices(uint32_t nselected, uint32_t grid_full, uint32_t step, uint32_t max_chunk_rows, int32_t *slices, uint32_t *slice_rows)
+{
+	uint32_t s = nselected ? (2u * grid_full + nselected - 1) / nselected : 1u;
+	uint32_t max_s = (max_chunk_rows + step - 1) / step;
+	if (s > max_s) s = max_s;
+	if (s < 1) s = 1;
+	uint32_t rows = ((max_chunk_rows + s - 1) / s + step - 1) / step * step;
+	*slices = (int32_t) ((max_chunk_rows + rows - 1) / rows);
+	*slice_rows = rows;
+}
 
 #define CG_FAST_PAIRED 1u       /* pair lanes so that one reduction instruction covers both words of a group */
 #define CG_FAST_NO_HINTS 2u     /* disable the L2 eviction hints (A/B measurements) */
@@ -264,6 +285,7 @@ struct FPlan
 #define CG_ERRFLAG_KEY_RANGE 4ull
 #define CG_ERRFLAG_SUM_BOUND 8ull
 #define CG_ERRFLAG_DECOMPRESS 16ull
+#define CG_ERRFLAG_VARLENA 32ull
 #define CG_COMM_TAIL 16           /* words behind an accumulator array that travel with it in a combine (cg_comm.cu) */
 #define CG_STAT_PACKED_ADDED 3
 #define CG_STAT_PACKED_DRAINED 4
@@ -331,6 +353,25 @@ struct DecodeItem
 };
 int cg_launch_decompress(CgContext *ctx, uint8_t *arena, const DecodeItem *items, const DecodeItem *h_items, uint64_t nitems,
 						 unsigned long long *err, unsigned long long flag, cudaStream_t stream);
+
+/* cg_varlena.cu: one varlena value stream (arena offset src, raw_len bytes: the on-disk stream, or its decompressed
+ * slot) to decode into a dense fixed-width array of `count` values at arena offset dst */
+struct VarlenaItem
+{
+	uint64_t src;
+	uint64_t dst;
+	uint32_t raw_len;
+	uint32_t count;
+	uint32_t kind;      /* CG_TYPE_NUMERIC / CG_TYPE_BPCHAR1 */
+	uint32_t scale;
+};
+int cg_launch_varlena_decode(CgContext *ctx, uint8_t *arena, const VarlenaItem *items, uint64_t nitems, unsigned long long *err,
+							 unsigned long long flag, cudaStream_t stream);
+/* class and numeric scale of a column; the width the scan kernels see (a varlena column is decoded to a fixed width) */
+static inline int cg_type_class(const CgColumnDesc &c) { return c.type_class & 0xff; }
+static inline int cg_type_scale(const CgColumnDesc &c) { return c.type_class >> 8; }
+static inline bool cg_is_varlena(const CgColumnDesc &c) { return c.attlen < 0; }
+static inline int cg_decoded_len(const CgColumnDesc &c) { return c.attlen > 0 ? c.attlen : (cg_type_class(c) == CG_TYPE_NUMERIC ? 8 : 1); }
 
 /* cg_scan_small.cu */
 bool cg_small_eligible(const KPlan &plan);

@@ -256,7 +256,7 @@ static void gen_prelude(std::string &s)
 		 "  int32_t mode; int32_t nwords; int32_t stride; uint64_t *table; int64_t *hkeys; uint64_t capacity; int32_t hash_shift;\n"
 		 "  int64_t key_min; int64_t key_min1; uint64_t range1; uint8_t wordop[%d]; unsigned long long *stats;\n"
 		 "  int8_t hot_of_word[%d]; int32_t nhot; uint64_t *packed; int32_t pack_shift; int32_t pack_word;\n"
-		 "  int32_t nqexpr; int8_t qexpr[%d]; int32_t pad_; };\n",
+		 "  int32_t nqexpr; int8_t qexpr[%d]; int32_t slices; uint32_t slice_rows; uint32_t max_cg_rows; };\n",
 		 CG_KMAX_COLS, CG_KMAX_COLS, CG_KMAX_COLS, CG_MAX_QUALS, CG_MAX_QUALS, CG_MAX_QUALS, CG_MAX_QUALS, CG_MAX_QUALS, CG_MAX_QUALS,
 		 CG_MAX_GROUP_COLS, CG_MAX_AGGS, CG_KMAX_WORDS, CG_KMAX_WORDS, CG_MAX_QEXPR);
 	/* the text above must describe the host's structs exactly */
@@ -670,27 +670,33 @@ static std::string gen_source(const KPlan &plan, const JitShape &sh)
 		}
 		addf(s, "\t\t\tdefault: break;\n\t\t}\n\t\ts_acc[(size_t) i * %d + tid] = id;\n\t}\n\tuint64_t *mine = s_acc + tid;\n", JIT_THREADS);
 	}
-	s += "\tfor (uint32_t ci = blockIdx.x; ci < P.nselected; ci += gridDim.x)\n\t{\n";
+	/* work unit = (chunk group, row range [row0, rows)): launches with few chunk groups cut them into slices */
+	s += "\tconst uint32_t nunits = P.nselected * (uint32_t) P.slices;\n"
+		 "\tfor (uint32_t unit = blockIdx.x; unit < nunits; unit += gridDim.x)\n\t{\n"
+		 "\t\tconst uint32_t ci = P.slices == 1 ? unit : unit / (uint32_t) P.slices;\n"
+		 "\t\tconst uint32_t sl = P.slices == 1 ? 0u : unit - ci * (uint32_t) P.slices;\n";
 	addf(s, "\t\tconst DevChunkCol *cc = P.chunkcols + (uint64_t) P.selected[ci] * %dull;\n", plan.nstaged);
-	s += "\t\tconst uint32_t rows = __ldg(&cc[0].row_count);\n";
+	s += "\t\tconst uint32_t chunk_rows = __ldg(&cc[0].row_count);\n"
+		 "\t\tconst uint32_t row0 = sl * P.slice_rows;\n"
+		 "\t\tconst uint32_t rows = min(chunk_rows, row0 + P.slice_rows);\n";
 	for (int c = 0; c < plan.ncols; c++)
 	{
 		addf(s, "\t\tconst uint8_t *p%d = P.arena + __ldg(&cc[%d].values_off);\n", c, plan.slot[c]);
 		if (col_nullable(sh, c))
 			addf(s, "\t\tconst uint64_t *b%d = (const uint64_t *) (P.arena + __ldg(&cc[%d].exists_off));\n"
 					"\t\tconst uint32_t *k%d = (const uint32_t *) (P.arena + __ldg(&cc[%d].rank_off));\n"
-					"\t\tconst bool n%d = __ldg(&cc[%d].value_count) != rows;\n",
+					"\t\tconst bool n%d = __ldg(&cc[%d].value_count) != chunk_rows;\n",
 				 c, plan.slot[c], c, plan.slot[c], c, plan.slot[c]);
 	}
-	s += "\t\tscanned += (tid == 0) ? rows : 0;\n";
+	s += "\t\tscanned += (tid == 0 && sl == 0) ? chunk_rows : 0;\n";
 	if (plan.ncols == 0)
 	{
 		/* count(*) without any column */
-		s += "\t\tif (tid == 0) g_rows += rows;\n\t}\n";
+		s += "\t\tif (tid == 0 && sl == 0) g_rows += chunk_rows;\n\t}\n";
 	}
 	else
 	{
-		addf(s, "\t\tfor (uint32_t base = 0; base < rows; base += %du)\n\t\t{\n", JIT_THREADS * sh.R * sh.U);
+		addf(s, "\t\tfor (uint32_t base = row0; base < rows; base += %du)\n\t\t{\n", JIT_THREADS * sh.R * sh.U);
 		for (int u = 0; u < sh.U; u++)
 			for (int c = 0; c < plan.ncols; c++)
 			{
@@ -908,7 +914,13 @@ int cg_launch_scan_jit(CgContext *ctx, const KPlan &plan, uint32_t nullable, cud
 		KPlan piece = plan;
 		piece.selected = plan.selected + first;
 		piece.nselected = std::min(plan.nselected - first, max_cgs_per_launch);
-		uint32_t grid = std::min(grid_full, piece.nselected);
+		piece.slices = 1; piece.slice_rows = 1u << 30;
+		if (piece.nselected < 2 * grid_full && plan.max_cg_rows > 0)
+		{
+			/* the step is a multiple of 64 rows, so slices start on a word of the exists bitmaps / rank directories */
+			cg_choose_slices(piece.nselected, grid_full, (uint32_t) (JIT_THREADS * sh.R * sh.U), plan.max_cg_rows, &piece.slices, &piece.slice_rows);
+		}
+		uint32_t grid = (uint32_t) std::min<uint64_t>(grid_full, (uint64_t) piece.nselected * (uint64_t) piece.slices);
 		void *args[] = {&piece};
 		int e = g_api.launch(k->fn, grid, 1, 1, JIT_THREADS, 1, 1, (unsigned) sh.smem, (void *) stream, args, nullptr);
 		if (e != 0)

@@ -38,6 +38,16 @@ static int validate_desc(const CgScanDesc *d, const CgColumnDesc *columns, int n
 	for (int c = 0; c < natts; c++)
 	{
 		int l = columns[c].attlen;
+		const int cls = cg_type_class(columns[c]);
+		if (l == -1)
+		{
+			if (cls != CG_TYPE_NUMERIC && cls != CG_TYPE_BPCHAR1)
+				return cg_set_error(CG_EUNSUPPORTED, "column %d: varlena type other than numeric(p,s) / char(1)", c);
+			if (cls == CG_TYPE_NUMERIC && (cg_type_scale(columns[c]) < 0 || cg_type_scale(columns[c]) > 18))
+				return cg_set_error(CG_EUNSUPPORTED, "column %d: numeric scale %d", c, cg_type_scale(columns[c]));
+			continue;
+		}
+		if (cls == CG_TYPE_NUMERIC || cls == CG_TYPE_BPCHAR1) return cg_set_error(CG_EINVAL, "column %d: varlena class with attlen %d", c, l);
 		if (l != 1 && l != 2 && l != 4 && l != 8)
 			return cg_set_error(CG_EUNSUPPORTED, "column %d: attlen %d (only fixed-width by-value types)", c, l);
 		if (columns[c].type_class == CG_TYPE_FLOAT && l != 4 && l != 8)
@@ -70,7 +80,7 @@ static int validate_desc(const CgScanDesc *d, const CgColumnDesc *columns, int n
 		if (c < 0 || c >= natts) return cg_set_error(CG_EINVAL, "group column %d out of range", c);
 		if (columns[c].type_class == CG_TYPE_FLOAT)
 			return cg_set_error(CG_EUNSUPPORTED, "GROUP BY on a float column");
-		if (d->ngroup_cols == 2 && columns[c].attlen > 4)
+		if (d->ngroup_cols == 2 && cg_decoded_len(columns[c]) > 4)
 			return cg_set_error(CG_EUNSUPPORTED, "two-column GROUP BY needs columns of at most 4 bytes");
 	}
 	for (int a = 0; a < d->naggs; a++)
@@ -337,7 +347,7 @@ int cg_build_plan(const CgScanDesc *desc, const CgColumnDesc *columns, int natts
 		int slot = slot_of_att ? (*slot_of_att)[att] : att;
 		if (slot < 0) return -2;
 		plan->slot[ncols] = (uint8_t) slot;
-		plan->len[ncols] = (uint8_t) columns[att].attlen;
+		plan->len[ncols] = (uint8_t) cg_decoded_len(columns[att]);       /* a varlena column reaches the kernels decoded to a fixed width */
 		plan->isfloat[ncols] = (uint8_t) (columns[att].type_class == CG_TYPE_FLOAT);
 		pcol_of_att[att] = ncols;
 		return ncols++;
@@ -376,6 +386,7 @@ int cg_build_plan(const CgScanDesc *desc, const CgColumnDesc *columns, int natts
 			/* float4 column values are promoted to float8; so is the constant (already float8 bits) */
 		}
 	}
+	plan->slices = 1; plan->slice_rows = 1u << 30; plan->max_cg_rows = 0;
 	plan->nqexpr = desc->nqual_expr;
 	for (int i = 0; i < desc->nqual_expr; i++) plan->qexpr[i] = desc->qual_expr[i];
 	plan->ngroup = desc->ngroup_cols;
@@ -524,6 +535,7 @@ bool cg_build_fast_plan(const CgScanDesc *desc, const KPlan &plan, bool all8, FP
 	fast->table = plan.table; fast->hkeys = plan.hkeys; fast->capacity = plan.capacity; fast->stride = plan.stride;
 	fast->hash_shift = plan.hash_shift;
 	fast->key_min = plan.key_min; fast->stats = plan.stats;
+	fast->slices = 1; fast->slice_rows = 1u << 30; fast->max_cg_rows = plan.max_cg_rows;
 	(void) desc;
 	return true;
 }

@@ -264,21 +264,27 @@ cg_scan_fast_kernel(const __grid_constant__ FPlan P)
 	/* hash tables with single-word sums: lane-paired updates (decided per launch, uniform) */
 	const bool paired = (MODE == CG_MODE_HASH) && !PACK && NS > 0 && (P.flags & CG_FAST_PAIRED);
 
-	for (uint32_t ci = blockIdx.x; ci < P.nselected; ci += gridDim.x)
+	/* work unit = (chunk group, row range): small launches cut chunk groups into slices so that every SM has work */
+	const uint32_t nunits = P.nselected * (uint32_t) P.slices;
+	for (uint32_t unit = blockIdx.x; unit < nunits; unit += gridDim.x)
 	{
+		const uint32_t ci = P.slices == 1 ? unit : unit / (uint32_t) P.slices;
+		const uint32_t sl = P.slices == 1 ? 0u : unit - ci * (uint32_t) P.slices;
 		const DevChunkCol *cc = P.chunkcols + (uint64_t) P.selected[ci] * (uint64_t) P.nstaged;
-		const uint32_t rows = __ldg(&cc[0].row_count);
+		const uint32_t chunk_rows = __ldg(&cc[0].row_count);
+		const uint32_t row0 = sl * P.slice_rows;
+		const uint32_t rows = min(chunk_rows, row0 + P.slice_rows);       /* this unit covers rows [row0, rows) */
 		const uint8_t *vp[NCA];
 #pragma unroll
 		for (int c = 0; c < NC; c++) vp[c] = P.arena + __ldg(&cc[P.slot[c]].values_off);
-		scanned += (tid == 0) ? rows : 0;
+		scanned += (tid == 0 && sl == 0) ? chunk_rows : 0;
 		if (NC == 0)
 		{
 			/* count(*) without any column: every row of the chunk group passes */
-			if (tid == 0) acc.rows += rows;
+			if (tid == 0 && sl == 0) acc.rows += chunk_rows;
 			continue;
 		}
-		for (uint32_t base = 0; base < rows; base += CGF_THREADS * 2 * U)
+		for (uint32_t base = row0; base < rows; base += CGF_THREADS * 2 * U)
 		{
 			int64_t v0[U][NCA], v1[U][NCA];
 #pragma unroll
@@ -419,9 +425,14 @@ static int launch_fast_variant(CgContext *ctx, const FPlan &plan, cudaStream_t s
 		if (occ < 1) occ = 1;
 	}
 	uint32_t grid = (uint32_t) (ctx->sm_count * occ);
-	if (grid > plan.nselected) grid = plan.nselected;
+	FPlan launch = plan;
+	launch.slices = 1; launch.slice_rows = 1u << 30;
+	if (plan.nselected < 2 * grid && plan.max_cg_rows > 0)
+		cg_choose_slices(plan.nselected, grid, CGF_THREADS * 2 * U, plan.max_cg_rows, &launch.slices, &launch.slice_rows);
+	const uint64_t units = (uint64_t) plan.nselected * (uint64_t) launch.slices;
+	if (grid > units) grid = (uint32_t) units;
 	if (grid == 0) return CG_OK;
-	cg_scan_fast_kernel<NQ, MODE, NS, PACK, U><<<grid, CGF_THREADS, 0, stream>>>(plan);
+	cg_scan_fast_kernel<NQ, MODE, NS, PACK, U><<<grid, CGF_THREADS, 0, stream>>>(launch);
 	CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	return CG_OK;
 }

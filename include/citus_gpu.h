@@ -121,13 +121,20 @@ typedef struct CgStripe
 	uint32_t skipnode_base;     /* node(col,chunk) = nodes[skipnode_base + col*chunk_count + chunk] */
 } CgStripe;
 
-enum { CG_TYPE_INT = 0, CG_TYPE_FLOAT = 1 };
+enum { CG_TYPE_INT = 0, CG_TYPE_FLOAT = 1,
+	   /* by-reference (varlena) types whose values are scaled integers or one character: attlen = -1.
+		* numeric(p, s): type_class = CG_TYPE_NUMERIC | s << 8; the column then behaves like an int8 column holding
+		* value * 10^s (aggregate results carry the scale; cg_numeric_out prints them), a value with more fractional
+		* digits than s, NaN or outside int64 fails the scan with CG_EUNSUPPORTED.  char(1): CG_TYPE_BPCHAR1, behaves
+		* like a 1-byte integer column holding the character. */
+	   CG_TYPE_NUMERIC = 2, CG_TYPE_BPCHAR1 = 3 };
+#define CG_TYPE_NUMERIC_SCALE(s) (CG_TYPE_NUMERIC | ((s) << 8))
 
 /* the slice of the TupleDesc the path needs (Form_pg_attribute attlen / attalign / type class) */
 typedef struct CgColumnDesc
 {
-	int32_t attlen;     /* 1, 2, 4, 8: fixed-width by-value types */
-	int32_t type_class; /* CG_TYPE_* */
+	int32_t attlen;     /* 1, 2, 4, 8: fixed-width by-value types; -1: varlena (CG_TYPE_NUMERIC / CG_TYPE_BPCHAR1 only) */
+	int32_t type_class; /* CG_TYPE_* (low byte) | numeric scale << 8 */
 } CgColumnDesc;
 
 /* A columnar relation as the reader sees it: the main fork's 8 KB pages (as they sit in

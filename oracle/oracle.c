@@ -43,7 +43,13 @@ enum { ORC_COMP_NONE = 0, ORC_COMP_PGLZ = 1, ORC_COMP_LZ4 = 2, ORC_COMP_ZSTD = 3
 
 /* column type classes (fixed-width by-value types only; by-reference types are
  * SURVEY.md 8(f) row 4, "next") */
-enum { ORC_T_INT = 0, ORC_T_FLOAT = 1 };
+enum { ORC_T_INT = 0, ORC_T_FLOAT = 1,
+	   /* SURVEY.md 8(f) row 4, first slice: by-reference types whose VALUES are scaled integers / one character.
+		* attlen is -1 (varlena), attalign 'i'; the low byte of atttype is the class, the rest the numeric scale:
+		* a numeric(p, s) column holds value * 10^s as an int64 Datum in this file; char(1) holds the byte. */
+	   ORC_T_NUMERIC = 2, ORC_T_BPCHAR1 = 3 };
+#define ORC_TCLASS(t) ((t) & 0xff)
+#define ORC_TSCALE(t) ((t) >> 8)
 
 /* comparison operators of a pushed-down / row qual "col <op> const" */
 enum { ORC_OP_LT = 0, ORC_OP_LE = 1, ORC_OP_EQ = 2, ORC_OP_GE = 3, ORC_OP_GT = 4, ORC_OP_NE = 5 };
@@ -604,6 +610,149 @@ static inline int64_t orc_fetch_att(const uint8_t *p, int len, int atttype)
 	return v;
 }
 
+
+/* ------------------------------------------------------------------------- *
+ *  [PG] varlena headers (varatt.h, little-endian): 1-byte header when bit 0 is set (total length = header >> 1,
+ *  at most 127), else a 4-byte header (total length = header >> 2).  columnar_reader.c:1557-1565 advances by
+ *  att_addlength_datum = VARSIZE_ANY and then aligns to the type's alignment ('i' = 4 for numeric, bpchar, text).
+ *  [PG] numeric on-disk format (numeric.c): base-10000 digits d[0..n) with value = sum d[i] * 10000^(weight - i);
+ *    short: uint16 header = 0x8000 | sign 0x2000 | dscale << 7 | weight sign 0x0040 | weight & 0x3F, when
+ *           dscale <= 63 and -64 <= weight <= 63; long: uint16 sign (0x0000 / 0x4000, 0xC000 = NaN) | dscale, int16 weight.
+ *    Leading and trailing zero digits are stripped; zero is no digits, weight 0, positive.
+ *  PARITY: the reference repository holds no golden on-disk numeric bytes (the format is PostgreSQL's); what is
+ *  pinned is decode(encode(x)) = x here and the TPC-H Q1/Q6 goldens computed through these columns.
+ * ------------------------------------------------------------------------- */
+static int orc_varlena_total(const uint8_t *p)
+{
+	if (p[0] & 1) return p[0] >> 1;
+	uint32_t h; memcpy(&h, p, 4);
+	return (int) (h >> 2);
+}
+static int orc_varlena_hdr(const uint8_t *p) { return (p[0] & 1) ? 1 : 4; }
+
+static int orc_varlena_wrap(uint8_t *out, const uint8_t *payload, int n, int short_header)
+{
+	if (short_header && n + 1 <= 127) { out[0] = (uint8_t) (((n + 1) << 1) | 1); memcpy(out + 1, payload, (size_t) n); return n + 1; }
+	uint32_t h = (uint32_t) (n + 4) << 2;
+	memcpy(out, &h, 4); memcpy(out + 4, payload, (size_t) n);
+	return n + 4;
+}
+
+/* scaled integer (value * 10^scale) -> numeric datum (with its varlena header); returns the datum's length */
+static int orc_numeric_encode(int64_t scaled, int scale, int short_header, uint8_t *out)
+{
+	int neg = scaled < 0;
+	unsigned __int128 a = neg ? (unsigned __int128) (-(int128) scaled) : (unsigned __int128) scaled;
+	unsigned __int128 p10 = 1;
+	for (int i = 0; i < scale; i++) p10 *= 10;
+	unsigned __int128 ip = a / p10, fp = a % p10;
+	int16_t digits[32]; int nd = 0;
+	/* integer part, most significant base-10000 digit first */
+	int16_t tmp[16]; int nt = 0;
+	while (ip > 0) { tmp[nt++] = (int16_t) (ip % 10000); ip /= 10000; }
+	int weight = nt - 1;
+	for (int i = nt - 1; i >= 0; i--) digits[nd++] = tmp[i];
+	/* fraction: `scale` decimal digits, right-padded with zeros to a multiple of 4 */
+	int fgroups = (scale + 3) / 4;
+	for (int i = scale; i < fgroups * 4; i++) fp *= 10;
+	for (int g = fgroups - 1; g >= 0; g--) { tmp[g] = (int16_t) (fp % 10000); fp /= 10000; }
+	for (int g = 0; g < fgroups; g++) digits[nd++] = tmp[g];
+	/* strip leading / trailing zero digits (make_result / strip_var) */
+	int first = 0;
+	while (first < nd && digits[first] == 0) { first++; weight--; }
+	while (nd > first && digits[nd - 1] == 0) nd--;
+	int n = nd - first;
+	if (n == 0) { weight = 0; neg = 0; }
+	uint8_t body[80]; int len = 0;
+	if (scale <= 0x3F && weight >= -64 && weight <= 63)
+	{
+		uint16_t h = (uint16_t) (0x8000 | (neg ? 0x2000 : 0) | (scale << 7) | (weight < 0 ? 0x0040 : 0) | (weight & 0x003F));
+		memcpy(body, &h, 2); len = 2;
+	}
+	else
+	{
+		uint16_t sd = (uint16_t) ((neg ? 0x4000 : 0x0000) | (scale & 0x3FFF));
+		int16_t w = (int16_t) weight;
+		memcpy(body, &sd, 2); memcpy(body + 2, &w, 2); len = 4;
+	}
+	for (int i = 0; i < n; i++) { memcpy(body + len, &digits[first + i], 2); len += 2; }
+	return orc_varlena_wrap(out, body, len, short_header);
+}
+
+/* numeric datum -> value * 10^scale; -1 if it is NaN / has more fractional digits than the scale / overflows int64 */
+static int orc_numeric_decode(const uint8_t *datum, int scale, int64_t *out)
+{
+	int total = orc_varlena_total(datum), hdr = orc_varlena_hdr(datum);
+	const uint8_t *p = datum + hdr;
+	int n = total - hdr;
+	if (n < 2) return -1;
+	uint16_t h; memcpy(&h, p, 2);
+	int neg, weight, nd;
+	const uint8_t *dp;
+	if ((h & 0xC000) == 0x8000)
+	{
+		neg = (h & 0x2000) != 0;
+		weight = (h & 0x0040) ? (int) (h & 0x003F) - 64 : (int) (h & 0x003F);     /* sign-extended 7-bit weight */
+		dp = p + 2; nd = (n - 2) / 2;
+	}
+	else
+	{
+		if ((h & 0xC000) == 0xC000) return -1;                                   /* NaN / infinity */
+		neg = (h & 0xC000) == 0x4000;
+		int16_t w; memcpy(&w, p + 2, 2); weight = w;
+		dp = p + 4; nd = (n - 4) / 2;
+	}
+	int128 acc = 0;
+	for (int i = 0; i < nd; i++) { int16_t d; memcpy(&d, dp + 2 * i, 2); acc = acc * 10000 + d; }
+	/* acc * 10000^(weight - (nd - 1)) * 10^scale must be an integer */
+	int e10 = 4 * (weight - (nd - 1)) + scale;
+	if (nd == 0) { *out = 0; return 0; }
+	while (e10 > 0) { acc *= 10; e10--; if (acc > (int128) INT64_MAX * 4) return -1; }
+	while (e10 < 0) { if (acc % 10 != 0) return -1; acc /= 10; e10++; }
+	if (acc > (int128) INT64_MAX) return -1;
+	*out = neg ? -(int64_t) acc : (int64_t) acc;
+	return 0;
+}
+
+/* stored form of a row value for a varlena class; returns the datum's length */
+static int orc_varlena_encode(int atttype, int64_t v, int short_header, uint8_t *out)
+{
+	if (ORC_TCLASS(atttype) == ORC_T_NUMERIC) return orc_numeric_encode(v, ORC_TSCALE(atttype), short_header, out);
+	uint8_t ch = (uint8_t) v;                        /* char(1): the blank-padded string of length 1 */
+	return orc_varlena_wrap(out, &ch, 1, short_header);
+}
+
+static int orc_varlena_decode(int atttype, const uint8_t *datum, int64_t *out)
+{
+	if (ORC_TCLASS(atttype) == ORC_T_NUMERIC) return orc_numeric_decode(datum, ORC_TSCALE(atttype), out);
+	if (orc_varlena_total(datum) - orc_varlena_hdr(datum) != 1) return -1;
+	*out = (int64_t) (int8_t) datum[orc_varlena_hdr(datum)];
+	return 0;
+}
+
+/* columnar_reader.c:1542-1572 DeserializeDatumArray, one datum: fetch_att (by-value) or the varlena at the current
+ * offset (by-reference; its VALUE is decoded here because this file keeps every Datum as an int64), then
+ * att_addlength_datum + att_align_nominal */
+static int orc_read_datum(const OrcTable *t, int c, const uint8_t *buf, uint32_t *off, uint64_t limit, int64_t *v)
+{
+	int len = t->attlen[c], al = orc_align_of(t->attalign[c]);
+	if (len < 0)
+	{
+		if ((uint64_t) *off + 1 > limit) return -1;
+		len = orc_varlena_total(buf + *off);
+		if (len < orc_varlena_hdr(buf + *off) || (uint64_t) *off + (uint64_t) len > limit) return -1;
+		if (orc_varlena_decode(t->atttype[c], buf + *off, v)) return -2;
+	}
+	else
+		*v = orc_fetch_att(buf + *off, len, t->atttype[c]);
+	*off += (uint32_t) len;
+	*off = (*off + (uint32_t) al - 1) & ~((uint32_t) al - 1);
+	return 0;
+}
+
+static int orc_short_varlena_headers = 0;    /* 1: data as read back from heap tuples (packed 1-byte headers); 0: as produced by input functions */
+void orc_set_short_varlena_headers(int on) { orc_short_varlena_headers = on; }
+
 OrcTable *orc_table_create(int natts, const int *attlen, const int *atttype,
 						   uint64_t stripe_row_limit, uint32_t chunk_row_limit,
 						   int compression, int compression_level)
@@ -617,7 +766,7 @@ OrcTable *orc_table_create(int natts, const int *attlen, const int *atttype,
 	{
 		t->attlen[c] = attlen[c];
 		t->atttype[c] = atttype[c];
-		t->attalign[c] = attlen[c] == 1 ? 'c' : attlen[c] == 2 ? 's' : attlen[c] == 4 ? 'i' : 'd';
+		t->attalign[c] = attlen[c] < 0 ? 'i' : attlen[c] == 1 ? 'c' : attlen[c] == 2 ? 's' : attlen[c] == 4 ? 'i' : 'd';
 	}
 	t->stripe_row_limit = stripe_row_limit;  /* columnar.c:29 default 150000 */
 	t->chunk_row_limit = chunk_row_limit;    /* columnar.c:30 default 10000 */
@@ -643,7 +792,7 @@ OrcTable *orc_table_create(int natts, const int *attlen, const int *atttype,
 	for (int c = 0; c < natts; c++)
 	{
 		t->w_exists[c] = calloc(chunk_row_limit, 1);
-		t->w_chunk_cap[c] = (uint64_t) chunk_row_limit * 8;
+		t->w_chunk_cap[c] = (uint64_t) chunk_row_limit * (attlen[c] < 0 ? 32 : 8);
 		t->w_chunk_values[c] = malloc(t->w_chunk_cap[c]);
 		t->w_exists_buf[c] = calloc(t->w_max_chunks, sizeof(uint8_t *));
 		t->w_exists_len[c] = calloc(t->w_max_chunks, sizeof(uint64_t));
@@ -896,7 +1045,9 @@ void orc_write_row(OrcTable *t, const int64_t *values, const uint8_t *nulls)
 		}
 		else
 		{
+			uint8_t vbuf[96];
 			int len = t->attlen[c];
+			if (len < 0) len = orc_varlena_encode(t->atttype[c], values[c], orc_short_varlena_headers, vbuf);     /* VARSIZE_ANY(datum) */
 			int aligned = (len + orc_align_of(t->attalign[c]) - 1) & ~(orc_align_of(t->attalign[c]) - 1);
 			t->w_exists[c][chunkRowIndex] = 1;
 			if (t->w_chunk_len[c] + (uint64_t) aligned > t->w_chunk_cap[c])
@@ -907,7 +1058,9 @@ void orc_write_row(OrcTable *t, const int64_t *values, const uint8_t *nulls)
 			uint8_t *p = t->w_chunk_values[c] + t->w_chunk_len[c];
 			memset(p, 0, (size_t) aligned);
 			int64_t v = values[c];
-			if (t->atttype[c] == ORC_T_FLOAT && len == 4)
+			if (t->attlen[c] < 0)
+				memcpy(p, vbuf, (size_t) len);
+			else if (t->atttype[c] == ORC_T_FLOAT && len == 4)
 			{
 				double d; memcpy(&d, &v, 8);
 				float f = (float) d; memcpy(p, &f, 4);
@@ -1296,9 +1449,10 @@ int orc_scan_aggregate(const OrcTable *t, const OrcQual *quals, int nquals,
 			exists[c] = malloc(maxChunkRows);
 			values[c] = malloc(sizeof(int64_t) * maxChunkRows);
 		}
-	uint8_t *rawbuf = malloc((size_t) maxChunkRows * 8 * 2 + 1024 * 1024);
-	uint64_t rawcap = (uint64_t) maxChunkRows * 8 * 2 + 1024 * 1024;
-	uint8_t *valbuf = malloc((size_t) maxChunkRows * 8 + 16);
+	/* a varlena numeric(15,2) datum is at most 4 + 2 + 2 * 5 bytes, padded to 16 */
+	uint8_t *rawbuf = malloc((size_t) maxChunkRows * 32 * 2 + 1024 * 1024);
+	uint64_t rawcap = (uint64_t) maxChunkRows * 32 * 2 + 1024 * 1024;
+	uint8_t *valbuf = malloc((size_t) maxChunkRows * 32 + 16);
 	uint8_t *bitbuf = malloc(maxChunkRows / 8 + 16);
 	int rc = 0;
 
@@ -1329,7 +1483,7 @@ int orc_scan_aggregate(const OrcTable *t, const OrcQual *quals, int nquals,
 				if (orc_storage_read(t->pages, t->nblocks, s->file_offset + node->exists_offset, bitbuf, node->exists_length)) { rc = -1; break; }
 				if (node->value_length > rawcap) { rawcap = node->value_length * 2; rawbuf = realloc(rawbuf, rawcap); }
 				if (orc_storage_read(t->pages, t->nblocks, s->file_offset + node->value_offset, rawbuf, node->value_length)) { rc = -1; break; }
-				if (node->decompressed_size > (uint64_t) maxChunkRows * 8) { rc = -1; snprintf(orc_errbuf, sizeof orc_errbuf, "value buffer too large"); break; }
+				if (node->decompressed_size > (uint64_t) maxChunkRows * 32) { rc = -1; snprintf(orc_errbuf, sizeof orc_errbuf, "value buffer too large"); break; }
 				if (orc_decompress(rawbuf, node->value_length, node->compression_type, node->decompressed_size, valbuf)) { rc = -1; break; }
 
 				/* DeserializeBoolArray */
@@ -1338,14 +1492,12 @@ int orc_scan_aggregate(const OrcTable *t, const OrcQual *quals, int nquals,
 					exists[c][i] = (bitbuf[i / 8] & (1 << (i % 8))) != 0;
 				/* DeserializeDatumArray: fetch_att, advance by attlen, align */
 				uint32_t off = 0;
-				int len = t->attlen[c], al = orc_align_of(t->attalign[c]);
 				for (uint32_t i = 0; i < rowCount; i++)
 				{
 					if (!exists[c][i]) continue;
-					values[c][i] = orc_fetch_att(valbuf + off, len, t->atttype[c]);
-					off += (uint32_t) len;
-					off = (off + (uint32_t) al - 1) & ~((uint32_t) al - 1);
-					if (off > node->decompressed_size) { rc = -1; snprintf(orc_errbuf, sizeof orc_errbuf, "insufficient data left in datum buffer"); break; }
+					int e = orc_read_datum(t, c, valbuf, &off, node->decompressed_size, &values[c][i]);
+					if (e == -2) { rc = -1; snprintf(orc_errbuf, sizeof orc_errbuf, "numeric value outside the column's scale / int64 range"); break; }
+					if (e || off > node->decompressed_size) { rc = -1; snprintf(orc_errbuf, sizeof orc_errbuf, "insufficient data left in datum buffer"); break; }
 				}
 			}
 			if (rc) break;
@@ -1464,7 +1616,7 @@ int orc_decode_all(const OrcTable *t, int64_t **out_values, uint8_t **out_nulls,
 {
 	int64_t row = 0;
 	uint8_t *rawbuf = NULL; uint64_t rawcap = 0;
-	uint8_t *valbuf = malloc((size_t) t->chunk_row_limit * 8 + 16);
+	uint8_t *valbuf = malloc((size_t) t->chunk_row_limit * 32 + 16);
 	uint8_t *bitbuf = malloc(t->chunk_row_limit / 8 + 16);
 	for (int si = 0; si < t->nstripes; si++)
 	{
@@ -1480,16 +1632,13 @@ int orc_decode_all(const OrcTable *t, int64_t **out_values, uint8_t **out_nulls,
 				if (orc_storage_read(t->pages, t->nblocks, s->file_offset + node->value_offset, rawbuf, node->value_length)) return -1;
 				if (orc_decompress(rawbuf, node->value_length, node->compression_type, node->decompressed_size, valbuf)) return -1;
 				uint32_t off = 0;
-				int len = t->attlen[c], al = orc_align_of(t->attalign[c]);
 				for (uint32_t i = 0; i < rowCount; i++)
 				{
 					int ex = (bitbuf[i / 8] & (1 << (i % 8))) != 0;
 					out_nulls[c][row + i] = !ex;
 					out_values[c][row + i] = 0;
 					if (!ex) continue;
-					out_values[c][row + i] = orc_fetch_att(valbuf + off, len, t->atttype[c]);
-					off += (uint32_t) len;
-					off = (off + (uint32_t) al - 1) & ~((uint32_t) al - 1);
+					if (orc_read_datum(t, c, valbuf, &off, node->decompressed_size, &out_values[c][row + i])) return -1;
 				}
 			}
 			row += rowCount;

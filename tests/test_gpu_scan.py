@@ -749,3 +749,99 @@ def test_copy_serializer_writes_the_reference_files(cg, oracle, expected):
         files, rows, nbytes = files_of(idx, 3, 3, [few], [8], True, gen_empty=gen_empty)
         assert files == oracle.copy_files(idx.cpu().numpy(), [few], [8], 3, True, generate_empty_results=gen_empty)
         assert len(files[1]) == (21 if gen_empty else 0)
+
+
+# --------------------------------------------------------------------------- (f)-4: varlena numeric / char(1) columns
+NUM2 = 2 | (2 << 8)          # numeric with scale 2 (decimal(15,2)); 3 = char(1)
+
+
+def _lineitem_varlena_rels(cg, oracle, li, short_headers, compression):
+    """the reference's own lineitem column types (test/regress/sql/multi_create_table.sql:12-28): decimal(15,2) for
+    quantity / extendedprice / discount / tax, char(1) for the flags -- written as varlena datums by the oracle's writer"""
+    mins, maxs = oracle.synthetic_intervals(2)
+    idx, _ = oracle.partition_rows(li["l_orderkey"], None, 8, "h", mins, maxs)
+    cols = ["l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_returnflag", "l_linestatus", "l_shipdate", "l_suppkey"]
+    attlen = [-1, -1, -1, -1, -1, -1, 4, 4]
+    atttype = [NUM2, NUM2, NUM2, NUM2, 3, 3, 0, 0]
+    rels = []
+    oracle.lib().orc_set_short_varlena_headers(1 if short_headers else 0)
+    try:
+        for s in range(2):
+            t = oracle.Table(attlen, atttype, stripe_row_limit=2000, chunk_row_limit=1000, compression=compression)
+            t.insert([li[c][idx == s] for c in cols])
+            rels.append(cg.Relation.from_image(t.pages(), t.stripes_array(), t.nodes_array(), attlen, atttype))
+    finally:
+        oracle.lib().orc_set_short_varlena_headers(0)
+    return rels
+
+
+@pytest.mark.parametrize("path", ["shard", "e2e", "dma"])
+@pytest.mark.parametrize("compression", ["none", "lz4"])
+@pytest.mark.parametrize("short_headers", [False, True])
+def test_tpch_goldens_on_varlena_numeric_and_char_columns(cg, oracle, expected, lineitem, short_headers, compression, path):
+    """TPC-H Q1 + Q6 (expected/multi_tpch_query1.out, multi_tpch_query6.out) over decimal(15,2) / char(1) columns stored
+    as varlena value streams (4-byte and packed 1-byte headers, plain and lz4-compressed): decoded on the GPU
+    (cg_varlena_decode_kernel) into the fixed-width form the fused kernels scan"""
+    if compression == "lz4" and not oracle.lib().orc_have_lz4():
+        pytest.skip("liblz4 missing")
+    comp = {"none": oracle.COMP_NONE, "lz4": oracle.COMP_LZ4}[compression]
+    e2e = False if path == "shard" else (True if path == "e2e" else "dma")
+    rels = _lineitem_varlena_rels(cg, oracle, lineitem, short_headers, comp)
+    quals = [(6, ">=", pgdate("1994-01-01")), (6, "<", pgdate("1995-01-01")), (2, ">=", 5), (2, "<=", 7), (0, "<", 2400)]
+    aggs = [cg.Agg(2, [(1, 0, 1), (2, 0, 1)])]
+    total = 0
+    for rel in rels:
+        _, got = run_both(cg, oracle, rel, quals=quals, aggs=aggs, chunk_row_limit=1000, e2e=e2e)
+        total += got[0][0]["sum"]
+    assert cg.numeric_out(total, 4) == expected["tpch_q6"]
+    quals = [(6, "<=", pgdate("1998-09-02"))]
+    aggs = [cg.sum_(0), cg.sum_(1), cg.Agg(2, [(1, 0, 1), (2, 100, -1)]),
+            cg.Agg(2, [(1, 0, 1), (2, 100, -1), (3, 100, 1)]), cg.sum_(2), cg.count_star()]
+    merged = {}
+    for rel in rels:
+        _, got = run_both(cg, oracle, rel, quals=quals, group_cols=[4, 5], aggs=aggs, chunk_row_limit=1000, expected_groups=16, e2e=e2e)
+        for k, per in got.items():
+            acc = merged.setdefault(k, [dict(sum=0, count=0) for _ in aggs])
+            for a in range(len(aggs)):
+                acc[a]["sum"] += per[a]["sum"]
+                acc[a]["count"] += per[a]["count"]
+    rows = []
+    for key, v in sorted(merged.items(), key=lambda kv: (kv[0] & 0xffffffff, kv[0] >> 32)):
+        rows.append([chr(key & 0xff), chr((key >> 32) & 0xff), cg.numeric_out(v[0]["sum"], 2), cg.numeric_out(v[1]["sum"], 2),
+                     cg.numeric_out(v[2]["sum"], 4), cg.numeric_out(v[3]["sum"], 6), cg.numeric_div_out(v[0]["sum"], 2, v[0]["count"]),
+                     cg.numeric_div_out(v[1]["sum"], 2, v[1]["count"]), cg.numeric_div_out(v[4]["sum"], 2, v[4]["count"]), str(v[5]["count"])])
+    assert rows == expected["tpch_q1"]
+
+
+def test_varlena_columns_with_nulls_wide_values_and_bad_scale(cg, oracle):
+    """NULLs in varlena columns (rank directory over the decoded array), values up to 10^17, negative numbers, zero; a value
+    with more fractional digits than the declared scale is refused (CG_EUNSUPPORTED), never rounded"""
+    from citus_b200 import capi
+    rng = np.random.default_rng(4)
+    n = 25_000
+    a = rng.integers(-10**17, 10**17, n)
+    a[:6] = [0, 1, -1, 10**17, -10**17, 99]
+    b = rng.integers(0, 50, n)
+    f = rng.integers(65, 70, n)
+    na = (rng.random(n) < 0.15).astype(np.uint8)
+    nf = (rng.random(n) < 0.05).astype(np.uint8)
+    NUM4 = 2 | (4 << 8)
+    for short in (False, True):
+        oracle.lib().orc_set_short_varlena_headers(1 if short else 0)
+        try:
+            t = oracle.Table([-1, 8, -1], [NUM4, 0, 3], stripe_row_limit=6000, chunk_row_limit=1500)
+            t.insert([a, b, f], nulls=[na, None, nf])
+        finally:
+            oracle.lib().orc_set_short_varlena_headers(0)
+        rel = cg.Relation.from_image(t.pages(), t.stripes_array(), t.nodes_array(), [-1, 8, -1], [NUM4, 0, 3])
+        aggs = [cg.sum_(0), cg.count_star(), cg.count(0), cg.min_(0), cg.max_(0), cg.count(2)]
+        run_both(cg, oracle, rel, [(1, "<", 40)], [2], aggs, chunk_row_limit=1500)
+        run_both(cg, oracle, rel, [(0, ">", 0)], [], aggs, chunk_row_limit=1500, e2e=True)
+    # the same bytes declared as numeric with scale 2: values like 0.0123 are not representable -> refused
+    rel = cg.Relation.from_image(t.pages(), t.stripes_array(), t.nodes_array(), [-1, 8, -1], [NUM2, 0, 3])
+    d = cg.make_desc([], [], [cg.sum_(0)])
+    agg = cg.GpuColumnarAgg(d, rel.column_descs(), 0, -1, n)
+    with pytest.raises(capi.CitusGpuError) as ei:
+        agg.scan_relation(rel)
+        agg.groups()
+    assert ei.value.code == capi.CG_EUNSUPPORTED
