@@ -1585,19 +1585,49 @@ static int pending_errors(CgContext *ctx, CgPartial *p)
 	return CG_OK;
 }
 
+/*
+ * Makes the result rows of a partial: surfaces kernel-raised errors, compacts the occupied groups into (keys, NULL flags,
+ * accumulator words) and returns their number -- with ONE host synchronisation.  Two forms:
+ *   packed-direct  a direct-indexed table that only ever received packed words (the C2 shape, also after an NCCL reduce
+ *                  of the packed words): the rows are decoded straight from the 8-byte packed words; the wide table is
+ *                  neither read nor written (it is still in its initial state and stays so across cg_partial_reset)
+ *   general        drain of any packed words into the wide accumulators, then the compaction of the wide table
+ * out_* may be NULL (count only).
+ */
+static int export_rows(CgContext *ctx, CgPartial *p, uint64_t capacity, int64_t *d_keys, uint8_t *d_nulls, uint64_t *d_words, int64_t *nrows)
+{
+	unsigned long long st[5], counts[2] = {0, 0};
+	const bool direct = p->d_packed && p->packed_dirty && !p->wide_dirty && p->mode == CG_MODE_DENSE && p->desc.ngroup_cols == 1;
+	int rc;
+	if (direct)
+		rc = cg_launch_export_packed(p, capacity, d_keys, d_nulls, d_words, p->d_out_count, ctx->compute);
+	else
+	{
+		rc = cg_launch_drain(p, ctx->compute);
+		if (rc == CG_OK) rc = cg_launch_export(p, capacity, d_keys, d_nulls, d_words, p->d_out_count, ctx->compute);
+	}
+	if (rc) return rc;
+	CG_CUDA(cudaMemcpyAsync(st, p->d_stats, sizeof st, cudaMemcpyDeviceToHost, ctx->compute));
+	CG_CUDA(cudaMemcpyAsync(counts, p->d_out_count, sizeof counts, cudaMemcpyDeviceToHost, ctx->compute));
+	CG_CUDA(cudaStreamSynchronize(ctx->compute));
+	rc = check_error_flags(p, st[2]);
+	if (rc) return rc;
+	/* every row added to a packed word must have come out again (drained earlier, or decoded just now) */
+	const unsigned long long out = st[CG_STAT_PACKED_DRAINED] + (direct ? counts[1] : 0ull);
+	if (st[CG_STAT_PACKED_ADDED] != out)
+		return cg_set_error(CG_ERETRY_UNPACKED,
+							"packed accumulators overflowed (%llu rows added, %llu decoded): a group received >= 2^%d rows "
+							"between drains; disable packing, reset and rescan",
+							st[CG_STAT_PACKED_ADDED], out, p->pack_shift);
+	*nrows = (int64_t) counts[0];
+	return CG_OK;
+}
+
 extern "C" int cg_partial_ngroups(CgPartial *p, int64_t *ngroups)
 {
 	CgContext *ctx = cg_ctx();
 	if (!ctx || !p) return CG_EINVAL;
-	int rc = pending_errors(ctx, p);
-	if (rc) return rc;
-	rc = cg_launch_export(p, 0, nullptr, nullptr, nullptr, p->d_out_count, ctx->compute);
-	if (rc) return rc;
-	unsigned long long n = 0;
-	CG_CUDA(cudaMemcpyAsync(&n, p->d_out_count, sizeof n, cudaMemcpyDeviceToHost, ctx->compute));
-	CG_CUDA(cudaStreamSynchronize(ctx->compute));
-	*ngroups = (int64_t) n;
-	return CG_OK;
+	return export_rows(ctx, p, 0, nullptr, nullptr, nullptr, ngroups);
 }
 
 static inline uint64_t f8_unordered(uint64_t u)
@@ -1611,16 +1641,13 @@ extern "C" int cg_partial_fetch(CgPartial *p, int64_t capacity, int64_t *keys, u
 {
 	CgContext *ctx = cg_ctx();
 	if (!ctx || !p) return CG_EINVAL;
-	int rc = pending_errors(ctx, p);
-	if (rc) return rc;
 	if (capacity < 0) return cg_set_error(CG_EINVAL, "negative capacity");
-	rc = ensure_out(p, std::max<uint64_t>((uint64_t) capacity, 1));
+	int rc = ensure_out(p, std::max<uint64_t>((uint64_t) capacity, 1));
 	if (rc) return rc;
-	rc = cg_launch_export(p, (uint64_t) capacity, p->d_out_keys, p->d_out_nulls, p->d_out_words, p->d_out_count, ctx->compute);
+	int64_t nrows = 0;
+	rc = export_rows(ctx, p, (uint64_t) capacity, p->d_out_keys, p->d_out_nulls, p->d_out_words, &nrows);
 	if (rc) return rc;
-	unsigned long long n = 0;
-	CG_CUDA(cudaMemcpyAsync(&n, p->d_out_count, sizeof n, cudaMemcpyDeviceToHost, ctx->compute));
-	CG_CUDA(cudaStreamSynchronize(ctx->compute));
+	unsigned long long n = (unsigned long long) nrows;
 	if (ngroups) *ngroups = (int64_t) n;
 	if ((int64_t) n > capacity)
 		return cg_set_error(CG_EINVAL, "%llu groups do not fit the caller's capacity %lld", n, (long long) capacity);
@@ -1693,13 +1720,10 @@ extern "C" int cg_partial_export_device(CgPartial *p, int64_t capacity, int64_t 
 {
 	CgContext *ctx = cg_ctx();
 	if (!ctx || !p) return CG_EINVAL;
-	int rc = pending_errors(ctx, p);
+	int64_t got = 0;
+	int rc = export_rows(ctx, p, (uint64_t) capacity, d_keys, d_key_nulls, d_words, &got);
 	if (rc) return rc;
-	rc = cg_launch_export(p, (uint64_t) capacity, d_keys, d_key_nulls, d_words, p->d_out_count, ctx->compute);
-	if (rc) return rc;
-	unsigned long long n = 0;
-	CG_CUDA(cudaMemcpyAsync(&n, p->d_out_count, sizeof n, cudaMemcpyDeviceToHost, ctx->compute));
-	CG_CUDA(cudaStreamSynchronize(ctx->compute));
+	unsigned long long n = (unsigned long long) got;
 	if (nrows) *nrows = (int64_t) n;
 	if ((int64_t) n > capacity) return cg_set_error(CG_EINVAL, "%llu rows exceed capacity %lld", n, (long long) capacity);
 	return CG_OK;

@@ -315,6 +315,7 @@ struct CgPartial
 	bool packing_enabled = false;
 	bool packed_dirty = false;
 	bool wide_dirty = false;        /* the wide accumulator words hold something (not only the packed words) */
+	bool table_initialised = false;
 	int launches_since_drain = 0;
 	uint64_t rows_since_drain = 0;  /* rows scanned into packed words since the last drain (upper bound) */
 	/* scratch for export */
@@ -384,6 +385,8 @@ int cg_launch_rank(CgContext *ctx, const uint8_t *arena, const DevChunkCol *chun
 int cg_launch_table_init(CgPartial *p, cudaStream_t stream);
 int cg_launch_export(CgPartial *p, uint64_t out_capacity, int64_t *d_keys, uint8_t *d_nulls, uint64_t *d_words,
 					 unsigned long long *d_count, cudaStream_t stream);
+int cg_launch_export_packed(CgPartial *p, uint64_t out_capacity, int64_t *d_keys, uint8_t *d_nulls, uint64_t *d_words,
+							unsigned long long *d_count, cudaStream_t stream);
 int cg_launch_merge(CgPartial *p, const int64_t *d_keys, const uint8_t *d_nulls, const uint64_t *d_words,
 					int64_t nrows, cudaStream_t stream);
 

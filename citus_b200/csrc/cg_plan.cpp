@@ -249,7 +249,7 @@ extern "C" int cg_partial_create(const CgScanDesc *desc, const CgColumnDesc *col
 	}
 	if (key_bytes) p->d_hkeys = (int64_t *) ((uint8_t *) p->d_table + bytes);
 	if (cudaMalloc(&p->d_stats, 8 * sizeof(unsigned long long)) != cudaSuccess ||
-		cudaMalloc(&p->d_out_count, sizeof(unsigned long long)) != cudaSuccess)
+		cudaMalloc(&p->d_out_count, 2 * sizeof(unsigned long long)) != cudaSuccess)
 	{
 		cg_partial_free(p);
 		return cg_set_error(CG_ENOMEM, "cudaMalloc failed");

@@ -542,11 +542,17 @@ int cg_launch_table_init(CgPartial *p, cudaStream_t stream)
 {
 	TableView v = view_of(p);
 	uint64_t total = v.entries * (uint64_t) v.stride;
-	unsigned blocks = (unsigned) ((total + 255) / 256);
-	if (blocks > 148 * 16) blocks = 148 * 16;
-	if (blocks == 0) blocks = 1;
-	cg_table_init_kernel<<<blocks, 256, 0, stream>>>(v);
-	CG_CUDA(cudaGetLastError()); g_cg_launches++;
+	/* a direct-indexed table whose wide words were never written since the last initialisation (packed words only) is
+	 * still in its initial state: a reset only clears the packed words and the counters */
+	if (!(p->table_initialised && !p->wide_dirty && p->mode != CG_MODE_HASH))
+	{
+		unsigned blocks = (unsigned) ((total + 255) / 256);
+		if (blocks > 148 * 16) blocks = 148 * 16;
+		if (blocks == 0) blocks = 1;
+		cg_table_init_kernel<<<blocks, 256, 0, stream>>>(v);
+		CG_CUDA(cudaGetLastError()); g_cg_launches++;
+		p->table_initialised = true;
+	}
 	CG_CUDA(cudaMemsetAsync(p->d_stats, 0, 8 * sizeof(unsigned long long), stream));
 	CG_CUDA(cudaMemsetAsync(p->d_table + total, 0, CG_COMM_TAIL * sizeof(uint64_t), stream));
 	if (p->d_packed) CG_CUDA(cudaMemsetAsync(p->d_packed, 0, ((size_t) p->entries + CG_COMM_TAIL) * sizeof(uint64_t), stream));
@@ -599,11 +605,54 @@ int cg_launch_export(CgPartial *p, uint64_t out_capacity, int64_t *d_keys, uint8
 					 unsigned long long *d_count, cudaStream_t stream)
 {
 	TableView v = view_of(p);
-	CG_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), stream));
+	CG_CUDA(cudaMemsetAsync(d_count, 0, 2 * sizeof(unsigned long long), stream));
 	unsigned blocks = (unsigned) ((v.entries + 255) / 256);
 	if (blocks > 148 * 16) blocks = 148 * 16;
 	if (blocks == 0) blocks = 1;
 	cg_export_kernel<<<blocks, 256, 0, stream>>>(v, out_capacity, d_keys, d_nulls, d_words, d_count);
+	CG_CUDA(cudaGetLastError()); g_cg_launches++;
+	return CG_OK;
+}
+
+/*
+ * Result rows straight from the packed words of a direct-indexed table whose wide accumulators were never written:
+ * word = (sum << C) + n  ->  rows n, sum; every other accumulator word is its identity.  count[0] = groups, count[1] =
+ * rows decoded (the overflow check: it must equal the rows the scan kernels added).
+ */
+__global__ void cg_export_packed_kernel(const __grid_constant__ TableView T, const uint64_t *packed, int shift, int pack_word,
+										uint64_t out_capacity, int64_t *keys, uint8_t *nulls, uint64_t *words, unsigned long long *count)
+{
+	const uint64_t mask = (1ull << shift) - 1ull;
+	unsigned long long decoded = 0;
+	for (uint64_t e = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; e < T.entries; e += (uint64_t) gridDim.x * blockDim.x)
+	{
+		const uint64_t w = packed[e];
+		if (w == 0) continue;
+		const uint64_t n = w & mask;
+		const int64_t sum = (int64_t) (w - n) >> shift;
+		decoded += n;
+		if (n == 0) continue;                          /* only reachable after an overflow, which the caller detects */
+		unsigned long long pos = atomicAdd(count, 1ull);
+		if (pos >= out_capacity) continue;
+		if (keys) keys[pos] = e == T.capacity ? 0 : T.key_min + (int64_t) e;
+		if (nulls) nulls[pos] = e == T.capacity ? 1 : 0;
+		if (words)
+			for (int x = 0; x < T.nwords; x++)
+				words[pos * (uint64_t) T.nwords + x] = x == 0 ? n : x == pack_word ? (uint64_t) sum : word_identity(T.wordop[x]);
+	}
+	for (int o = 16; o > 0; o >>= 1) decoded += __shfl_xor_sync(0xffffffffu, decoded, o);
+	if ((threadIdx.x & 31) == 0 && decoded) atomicAdd(count + 1, decoded);
+}
+
+int cg_launch_export_packed(CgPartial *p, uint64_t out_capacity, int64_t *d_keys, uint8_t *d_nulls, uint64_t *d_words,
+							unsigned long long *d_count, cudaStream_t stream)
+{
+	TableView v = view_of(p);
+	CG_CUDA(cudaMemsetAsync(d_count, 0, 2 * sizeof(unsigned long long), stream));
+	unsigned blocks = (unsigned) ((v.entries + 255) / 256);
+	if (blocks > 148 * 16) blocks = 148 * 16;
+	if (blocks == 0) blocks = 1;
+	cg_export_packed_kernel<<<blocks, 256, 0, stream>>>(v, p->d_packed, p->pack_shift, p->pack_word, out_capacity, d_keys, d_nulls, d_words, d_count);
 	CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	return CG_OK;
 }
