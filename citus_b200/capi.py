@@ -150,6 +150,7 @@ SYMBOLS = [
                                     C.c_uint32, C.POINTER(_P)]),
     ("cg_gen_relation_view", C.c_int, [_P, C.POINTER(CgRelation)]),
     ("cg_gen_relation_free", None, [_P]),
+    ("cg_join_rows", C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, C.c_int64, C.c_int64, _P, _P, _P, C.POINTER(C.c_int64)]),
     ("cg_partial_merge_values", C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
     ("cg_agg_column", C.c_int, [C.c_int32, C.c_int32, _P, _P, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                C.POINTER(C.c_uint64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

@@ -467,6 +467,16 @@ def join_count_sum(d_build_keys, d_build_payload, nbuild, d_probe_keys, d_probe_
     return rows.value, (hi.value << 64) + lo.value
 
 
+def join_rows(d_build_keys, d_build_payload, nbuild, d_probe_keys, d_probe_payload, nprobe, capacity=0, d_out=(None, None, None),
+              d_build_nulls=None, d_probe_nulls=None):
+    """rows of the equi-join into the caller's device arrays (key, build payload, probe payload); returns the row count
+    (capacity 0: count only)"""
+    n = C.c_int64()
+    check(lib().cg_join_rows(d_build_keys, d_build_nulls, d_build_payload, nbuild, d_probe_keys, d_probe_nulls, d_probe_payload, nprobe,
+                             capacity, d_out[0], d_out[1], d_out[2], C.byref(n)))
+    return n.value
+
+
 def set_writer_compression(name: str):
     """columnar.compression for Relation.generate / Relation.write: "none", "lz4" or "zstd" (level 3)"""
     check(lib().cg_gen_set_compression({"none": 0, "lz4": 2, "zstd": 3}[name]))

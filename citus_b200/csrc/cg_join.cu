@@ -187,3 +187,206 @@ extern "C" int cg_join_count_sum(const int64_t *d_build_keys, const uint8_t *d_b
 	*sum_hi = (int64_t) (uint64_t) (total >> 64);
 	return CG_OK;
 }
+
+/* ------------------------------------------------------------------------------ *
+ *  The same join emitting its rows:
+ *      SELECT b.key, b.payload, p.payload FROM build b JOIN probe p USING (key)
+ *  for plans whose join output is not aggregated right away (the MERGE task of planner/multi_physical_planner.c:
+ *  4304-4328 hands PostgreSQL's HashJoin output to whatever sits above it).  Build: every build row is linked into the
+ *  chain of its key's slot (head[slot] <- row, next[row] <- old head: one atomic exchange per row) and the slot counts its
+ *  rows.  Probe pass 1 looks the key up and records how many rows it joins; an exclusive prefix sum over the probe rows
+ *  gives every probe row its place in the output; pass 2 walks the chain and writes the rows.  Row order is unspecified,
+ *  as for any hash join.
+ * ------------------------------------------------------------------------------ */
+struct JoinRowsTable
+{
+	long long *keys;              /* [cap + 1] */
+	unsigned int *count;          /* [cap + 1] build rows with this key */
+	long long *head;              /* [cap + 1] first build row of the chain, -1 = none */
+	long long *next;              /* [nbuild] */
+	unsigned long long cap;
+	int shift;
+	unsigned long long *errors;
+};
+
+__device__ __forceinline__ unsigned long long join_rows_find(const JoinRowsTable &T, long long key, bool insert)
+{
+	if (key == CGJ_EMPTY) return T.cap;
+	unsigned long long h = join_home(key, T.shift);
+	for (unsigned long long probes = 0; probes <= T.cap; probes++)
+	{
+		long long cur = (long long) __ldcg((unsigned long long *) T.keys + h);
+		if (cur == key) return h;
+		if (cur == CGJ_EMPTY)
+		{
+			if (!insert) return ~0ull;
+			long long old = (long long) atomicCAS((unsigned long long *) T.keys + h, (unsigned long long) CGJ_EMPTY, (unsigned long long) key);
+			if (old == CGJ_EMPTY || old == key) return h;
+		}
+		h = (h + 1) & (T.cap - 1);
+	}
+	return ~0ull;
+}
+
+__global__ void cg_join_rows_init_kernel(JoinRowsTable T)
+{
+	for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i <= T.cap; i += (unsigned long long) gridDim.x * blockDim.x)
+	{
+		T.keys[i] = CGJ_EMPTY; T.count[i] = 0; T.head[i] = -1;
+	}
+}
+
+__global__ void __launch_bounds__(CGJ_THREADS)
+cg_join_rows_build_kernel(JoinRowsTable T, const long long *keys, const uint8_t *nulls, long long n)
+{
+	for (long long r = (long long) blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long) gridDim.x * blockDim.x)
+	{
+		if (nulls && nulls[r]) continue;
+		unsigned long long slot = join_rows_find(T, keys[r], true);
+		if (slot == ~0ull) { atomicAdd(T.errors, 1ull); continue; }
+		atomicAdd(T.count + slot, 1u);
+		T.next[r] = (long long) atomicExch((unsigned long long *) T.head + slot, (unsigned long long) r);
+	}
+}
+
+/* matches[r] = rows probe row r joins; block sums for the scan */
+__global__ void __launch_bounds__(CGJ_THREADS)
+cg_join_rows_count_kernel(JoinRowsTable T, const long long *keys, const uint8_t *nulls, long long n, unsigned int *matches,
+						  unsigned long long *block_sums)
+{
+	__shared__ unsigned long long s_sum[CGJ_THREADS / 32];
+	const long long r = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned int m = 0;
+	if (r < n && !(nulls && nulls[r]))
+	{
+		unsigned long long slot = join_rows_find(T, keys[r], false);
+		if (slot != ~0ull) m = T.count[slot];
+	}
+	if (r < n) matches[r] = m;
+	unsigned long long w = join_wsum((unsigned long long) m);
+	if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = w;
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		unsigned long long t = 0;
+		for (int i = 0; i < CGJ_THREADS / 32; i++) t += s_sum[i];
+		block_sums[blockIdx.x] = t;
+	}
+}
+
+/* exclusive scan of the block sums by one block (nblocks is n / 256: up to ~1 M entries, a few hundred microseconds) */
+__global__ void __launch_bounds__(1024)
+cg_join_rows_scan_kernel(unsigned long long *block_sums, long long nblocks, unsigned long long *total)
+{
+	__shared__ unsigned long long s[1024];
+	const long long per = (nblocks + 1023) / 1024;
+	const long long b0 = (long long) threadIdx.x * per, b1 = b0 + per < nblocks ? b0 + per : nblocks;
+	unsigned long long local = 0;
+	for (long long b = b0; b < b1; b++) local += block_sums[b];
+	s[threadIdx.x] = local;
+	__syncthreads();
+	for (int off = 1; off < 1024; off <<= 1)
+	{
+		unsigned long long v = threadIdx.x >= (unsigned) off ? s[threadIdx.x - off] : 0;
+		__syncthreads();
+		s[threadIdx.x] += v;
+		__syncthreads();
+	}
+	unsigned long long run = s[threadIdx.x] - local;
+	for (long long b = b0; b < b1; b++) { unsigned long long c = block_sums[b]; block_sums[b] = run; run += c; }
+	if (threadIdx.x == 1023) *total = s[1023];
+}
+
+__global__ void __launch_bounds__(CGJ_THREADS)
+cg_join_rows_emit_kernel(JoinRowsTable T, const long long *bpay, const long long *keys, const uint8_t *nulls, const long long *ppay, long long n,
+						 const unsigned int *matches, const unsigned long long *block_offsets, unsigned long long capacity,
+						 long long *out_key, long long *out_bpay, long long *out_ppay)
+{
+	__shared__ unsigned long long s_warp[CGJ_THREADS / 32];
+	const long long r = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const unsigned int m = r < n ? matches[r] : 0u;
+	/* place of this row's first output row: block offset + exclusive scan inside the block */
+	unsigned long long incl = m;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1)
+	{
+		unsigned long long y = __shfl_up_sync(0xffffffffu, incl, o);
+		if (lane >= (unsigned) o) incl += y;
+	}
+	if (lane == 31) s_warp[warp] = incl;
+	__syncthreads();
+	unsigned long long pos = block_offsets[blockIdx.x] + incl - m;
+	for (unsigned w = 0; w < warp; w++) pos += s_warp[w];
+	if (m == 0) return;
+	const long long key = keys[r];
+	const unsigned long long slot = join_rows_find(T, key, false);
+	const long long y = ppay[r];
+	for (long long b = T.head[slot]; b >= 0; b = T.next[b], pos++)
+		if (pos < capacity)
+		{
+			out_key[pos] = key; out_bpay[pos] = bpay[b]; out_ppay[pos] = y;
+		}
+}
+
+extern "C" int cg_join_rows(const int64_t *d_build_keys, const uint8_t *d_build_nulls, const int64_t *d_build_payload, int64_t nbuild,
+							const int64_t *d_probe_keys, const uint8_t *d_probe_nulls, const int64_t *d_probe_payload, int64_t nprobe,
+							int64_t capacity, int64_t *d_out_key, int64_t *d_out_build_payload, int64_t *d_out_probe_payload, int64_t *nrows)
+{
+	CgContext *ctx = cg_ctx();
+	if (!ctx) return CG_EINVAL;
+	if (nbuild < 0 || nprobe < 0 || capacity < 0 || !nrows) return cg_set_error(CG_EINVAL, "bad argument");
+	if ((nbuild > 0 && (!d_build_keys || !d_build_payload)) || (nprobe > 0 && (!d_probe_keys || !d_probe_payload)))
+		return cg_set_error(CG_EINVAL, "NULL column");
+	if (capacity > 0 && (!d_out_key || !d_out_build_payload || !d_out_probe_payload)) return cg_set_error(CG_EINVAL, "NULL output column");
+	*nrows = 0;
+	if (nbuild == 0 || nprobe == 0) return CG_OK;
+	JoinRowsTable T;
+	T.cap = 1024;
+	while (T.cap < 2ull * (uint64_t) nbuild) T.cap <<= 1;
+	T.shift = 64;
+	for (unsigned long long c = T.cap; c > 1; c >>= 1) T.shift--;
+	const long long nblocks = (nprobe + CGJ_THREADS - 1) / CGJ_THREADS;
+	auto a16 = [](size_t x) { return (x + 63) & ~(size_t) 63; };
+	const size_t kb = a16((T.cap + 1) * 8), cb = a16((T.cap + 1) * 4), hb = a16((T.cap + 1) * 8), nb = a16((size_t) nbuild * 8),
+				 mb = a16((size_t) nprobe * 4), bb = a16((size_t) nblocks * 8);
+	CgAsyncBuf mem;
+	if (mem.alloc(kb + cb + hb + nb + mb + bb + 64, ctx->compute) != cudaSuccess)
+	{
+		cudaGetLastError();
+		return cg_set_error(CG_ENOMEM, "cudaMallocAsync of %zu bytes for the join failed", kb + cb + hb + nb + mb + bb);
+	}
+	uint8_t *d = mem.as<uint8_t>();
+	T.keys = (long long *) d; T.count = (unsigned int *) (d + kb); T.head = (long long *) (d + kb + cb); T.next = (long long *) (d + kb + cb + hb);
+	unsigned int *d_matches = (unsigned int *) (d + kb + cb + hb + nb);
+	unsigned long long *d_block = (unsigned long long *) (d + kb + cb + hb + nb + mb);
+	unsigned long long *d_tot = (unsigned long long *) (d + kb + cb + hb + nb + mb + bb);     /* [0] total rows, [1] errors */
+	T.errors = d_tot + 1;
+	CG_CUDA(cudaMemsetAsync(d_tot, 0, 16, ctx->compute));
+	const unsigned blocks = (unsigned) (ctx->sm_count * 8);
+	cg_join_rows_init_kernel<<<blocks, CGJ_THREADS, 0, ctx->compute>>>(T);
+	CG_CUDA(cudaGetLastError()); g_cg_launches++;
+	cg_join_rows_build_kernel<<<blocks, CGJ_THREADS, 0, ctx->compute>>>(T, (const long long *) d_build_keys, d_build_nulls, (long long) nbuild);
+	CG_CUDA(cudaGetLastError()); g_cg_launches++;
+	cg_join_rows_count_kernel<<<(unsigned) nblocks, CGJ_THREADS, 0, ctx->compute>>>(T, (const long long *) d_probe_keys, d_probe_nulls, (long long) nprobe,
+																				  d_matches, d_block);
+	CG_CUDA(cudaGetLastError()); g_cg_launches++;
+	cg_join_rows_scan_kernel<<<1, 1024, 0, ctx->compute>>>(d_block, nblocks, d_tot);
+	CG_CUDA(cudaGetLastError()); g_cg_launches++;
+	unsigned long long h[2] = {0, 0};
+	CG_CUDA(cudaMemcpyAsync(h, d_tot, sizeof h, cudaMemcpyDeviceToHost, ctx->compute));
+	CG_CUDA(cudaStreamSynchronize(ctx->compute));
+	if (h[1]) return cg_set_error(CG_ETABLEFULL, "join table overflow (%llu rows)", h[1]);
+	*nrows = (int64_t) h[0];
+	if ((int64_t) h[0] > capacity)
+		return capacity == 0 ? CG_OK : cg_set_error(CG_EINVAL, "%llu joined rows exceed the caller's capacity %lld", h[0], (long long) capacity);
+	if (h[0] == 0) return CG_OK;
+	cg_join_rows_emit_kernel<<<(unsigned) nblocks, CGJ_THREADS, 0, ctx->compute>>>(T, (const long long *) d_build_payload, (const long long *) d_probe_keys,
+																				 d_probe_nulls, (const long long *) d_probe_payload, (long long) nprobe,
+																				 d_matches, d_block, (unsigned long long) capacity,
+																				 (long long *) d_out_key, (long long *) d_out_build_payload,
+																				 (long long *) d_out_probe_payload);
+	CG_CUDA(cudaGetLastError()); g_cg_launches++;
+	CG_CUDA(cudaStreamSynchronize(ctx->compute));
+	return CG_OK;
+}

@@ -436,6 +436,13 @@ int cg_comm_exchange_result(int32_t slot, int64_t **d_cols, int64_t *nrows, int6
 int cg_comm_exchange_plan(int32_t P, int32_t nranks, int32_t rank, const int64_t *counts, int32_t *position,
 						  int64_t *send_rows, int64_t *recv_rows, int64_t *local_part_counts, int32_t *nlocal);
 
+/* The same join emitting its rows -- SELECT b.key, b.payload, p.payload FROM build b JOIN probe p USING (key) -- into device
+ * arrays of `capacity` rows owned by the caller (row order unspecified, NULL keys join nothing).  *nrows = the number of
+ * joined rows; with capacity 0 nothing is written (size the arrays, call again); a too small capacity is CG_EINVAL. */
+int cg_join_rows(const int64_t *d_build_keys, const uint8_t *d_build_nulls, const int64_t *d_build_payload, int64_t nbuild,
+				 const int64_t *d_probe_keys, const uint8_t *d_probe_nulls, const int64_t *d_probe_payload, int64_t nprobe,
+				 int64_t capacity, int64_t *d_out_key, int64_t *d_out_build_payload, int64_t *d_out_probe_payload, int64_t *nrows);
+
 /* exact bounds from the skip lists (min/max of every chunk that survives chunk-group
  * skipping): the packed group key range and |argument| of every aggregate (0 = unknown,
  * e.g. a chunk without min/max).  Feed them to cg_partial_create / CgAggSpec.term_abs_bound. */
