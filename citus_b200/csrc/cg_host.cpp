@@ -895,6 +895,15 @@ static int drain_every(void)
  * drains before its result is read, and a combine can ship the 8-byte packed words alone.
  * packed_only = the launch wrote nothing but packed words.
  */
+/* a partial that was read (rows decoded straight from its packed words) and is scanned into again: fold the packed words
+ * into the wide accumulators first, as a read used to do, so that reads bound what a packed word accumulates */
+static int before_scan(CgContext *ctx, CgPartial *p)
+{
+	if (!p->read_packed_direct) return CG_OK;
+	p->read_packed_direct = false;
+	return cg_launch_drain(p, ctx->compute);
+}
+
 static int after_launch(CgContext *ctx, CgPartial *p, bool used_packed, bool packed_only, uint64_t rows)
 {
 	if (!(used_packed && packed_only)) p->wide_dirty = true;
@@ -933,6 +942,8 @@ extern "C" int cg_scan_shard(const CgShard *sh, const CgScanDesc *desc, CgPartia
 	KPlan plan;
 	bool all8 = false;
 	int rc = cg_build_plan(desc, sh->columns.data(), sh->natts, &sh->slot_of_att, into, &plan, &all8);
+	if (rc) return rc;
+	rc = before_scan(ctx, into);
 	if (rc) return rc;
 
 	/* K2 on the host: SelectedChunkMask per stripe.  The list of surviving chunk groups is
@@ -1267,6 +1278,8 @@ extern "C" int cg_scan_relation(const CgRelation *rel, const CgScanDesc *desc, C
 	bool all8 = false;
 	rc = cg_build_plan(desc, rel->columns, rel->natts, &slot_of_att, into, &plan, &all8);
 	if (rc) return rc;
+	rc = before_scan(ctx, into);
+	if (rc) return rc;
 
 	std::vector<std::vector<uint8_t>> select(rel->nstripes);
 	int64_t filtered = 0;
@@ -1600,7 +1613,10 @@ static int export_rows(CgContext *ctx, CgPartial *p, uint64_t capacity, int64_t 
 	const bool direct = p->d_packed && p->packed_dirty && !p->wide_dirty && p->mode == CG_MODE_DENSE && p->desc.ngroup_cols == 1;
 	int rc;
 	if (direct)
+	{
 		rc = cg_launch_export_packed(p, capacity, d_keys, d_nulls, d_words, p->d_out_count, ctx->compute);
+		p->read_packed_direct = true;
+	}
 	else
 	{
 		rc = cg_launch_drain(p, ctx->compute);

@@ -217,12 +217,17 @@ cg_partition_scatter_kernel(const __grid_constant__ ScatterParams A)
 }
 
 /*
- * The scatter the repartition uses: same stable order, but (1) the partition of a row may be computed on the fly from
- * its key (ROUTE: hashint4/8 + interval search, no index array is ever written or read), and (2) rows are first placed
- * in partition order inside the block's shared memory and leave it as runs -- a block's rows of one partition are
- * contiguous in the output, 4096 / P rows on average -- so global stores are coalesced 128-byte lines instead of one
- * 8-byte store per row and column.  Traffic per row: keys once for the histogram + every column read once and written
- * once (32 B/row for two columns, + 8 B for the routing pass).
+ * The scatter the repartition uses.  Same stable order as above, built for instruction count (both kernels of the first
+ * version were issue-bound: 420 instructions per row, profiles/README.md):
+ *   routing   hashint4/8, then -- when the intervals are the uniform ones the planner generates
+ *             (GenerateSyntheticShardIntervalArray, planner/multi_physical_planner.c:4667-4701) -- the reference's own
+ *             shortcut CalculateUniformHashRangeIndex (utils/shardinterval_utils.c:424-452): (hash - INT32_MIN) / increment,
+ *             a shift when P is a power of two; the interval search only for arbitrary bounds.  Done ONCE, in the histogram
+ *             pass, which leaves a 2-byte partition number per row for the scatter pass.
+ *   ranks     one match.any per row (pass A); its rank and group size travel to pass B in a register
+ *   output    rows are placed in partition order in shared memory and leave as runs (a block's rows of one partition are
+ *             contiguous in the output): coalesced stores; the partition of a local position is a 2-byte lookup
+ * Traffic per row and table: keys 8 B + 2 B written (histogram pass), 2 B + every column read and written once.
  */
 struct RouteParams
 {
@@ -230,18 +235,18 @@ struct RouteParams
 	const uint8_t *nulls;
 	int32_t key_len, by_hash;
 	const int32_t *mins, *maxs;      /* device, [P] */
+	uint32_t uniform_inc;            /* != 0: uniform hash intervals of this width */
+	int32_t uniform_shift;           /* >= 0: the width is 2^shift */
 };
 
 struct StagedScatterParams
 {
-	const int32_t *index;            /* NULL in ROUTE mode */
-	RouteParams route;
+	const void *index;               /* uint16_t[n] (repartition) or int32_t[n] (public API) */
 	int64_t n;
 	int32_t P, ncols;
 	const unsigned long long *block_offsets;   /* [nblocks][P] in output order */
 	const unsigned long long *part_base;       /* [P] in output order */
-	const int32_t *order;                      /* [P] output position of partition p, or NULL */
-	unsigned long long *errors;                /* ROUTE: rows whose hash lies in no interval */
+	const int32_t *order;                      /* [P] output position of partition p, or NULL (already applied / identity) */
 	const int64_t *cols[8];
 	int64_t *out[8];
 };
@@ -250,6 +255,13 @@ __device__ __forceinline__ int route_row(const RouteParams &R, const int32_t *s_
 {
 	if (R.nulls && R.nulls[r]) return 0;
 	const int64_t k = R.keys[r];
+	if (R.by_hash && R.uniform_inc)
+	{
+		const uint32_t h = R.key_len == 4 ? hash_bytes_uint32((uint32_t) (int32_t) k) : (uint32_t) hashint8_dev(k);
+		const uint32_t u = h ^ 0x80000000u;                                   /* hash - INT32_MIN */
+		const uint32_t idx = R.uniform_shift >= 0 ? (u >> R.uniform_shift) : (u / R.uniform_inc);
+		return (int) (idx < (uint32_t) P ? idx : (uint32_t) P - 1u);           /* the last interval is widened to INT32_MAX */
+	}
 	const int64_t searched = R.by_hash ? (int64_t) (R.key_len == 4 ? (int32_t) hash_bytes_uint32((uint32_t) (int32_t) k) : hashint8_dev(k))
 									   : (R.key_len == 4 ? (int64_t) (int32_t) k : k);
 	int lower = 0, upper = P;
@@ -264,36 +276,44 @@ __device__ __forceinline__ int route_row(const RouteParams &R, const int32_t *s_
 	return 0;
 }
 
-/* routing + histogram without materialising the index: block_counts[b][position(p)], counts[p] (partition order), errors */
+/* routing + histogram: index16[r] = output POSITION of the row's partition, block_counts[b][position], counts[p] (partition
+ * order), errors */
 __global__ void __launch_bounds__(CGP_THREADS)
-cg_route_hist_kernel(const RouteParams R, int64_t n, int P, const int32_t *order, unsigned long long *block_counts,
+cg_route_hist_kernel(const RouteParams R, int64_t n, int P, const int32_t *order, uint16_t *index16, unsigned long long *block_counts,
 					 unsigned long long *counts, unsigned long long *errors)
 {
-	extern __shared__ unsigned int s_hist[];      /* [P] counts, [P] mins, [P] maxs */
-	int32_t *s_min = (int32_t *) (s_hist + P), *s_max = s_min + P;
-	for (int p = threadIdx.x; p < P; p += CGP_THREADS) { s_hist[p] = 0; s_min[p] = R.mins[p]; s_max[p] = R.maxs[p]; }
+	extern __shared__ unsigned int s_hist[];      /* [P] counts (by position), [P] mins, [P] maxs, [P] order */
+	int32_t *s_min = (int32_t *) (s_hist + P), *s_max = s_min + P, *s_ord = s_max + P;
+	for (int p = threadIdx.x; p < P; p += CGP_THREADS)
+	{
+		s_hist[p] = 0; s_ord[p] = order ? order[p] : p;
+		if (!R.uniform_inc || !R.by_hash) { s_min[p] = R.mins[p]; s_max[p] = R.maxs[p]; }
+	}
 	__syncthreads();
 	const int64_t base = (int64_t) blockIdx.x * CGP_ROWS_PER_BLOCK;
 	unsigned int nbad = 0;
+#pragma unroll 4
 	for (int i = threadIdx.x; i < CGP_ROWS_PER_BLOCK; i += CGP_THREADS)
 	{
 		int64_t r = base + i;
 		if (r >= n) break;
 		bool bad = false;
-		atomicAdd(&s_hist[route_row(R, s_min, s_max, P, r, &bad)], 1u);
+		const int pos = s_ord[route_row(R, s_min, s_max, P, r, &bad)];
+		index16[r] = (uint16_t) pos;
+		atomicAdd(&s_hist[pos], 1u);
 		nbad += bad ? 1u : 0u;
 	}
 	if (nbad) atomicAdd(errors, (unsigned long long) nbad);
 	__syncthreads();
 	for (int p = threadIdx.x; p < P; p += CGP_THREADS)
 	{
-		unsigned int c = s_hist[p];
-		block_counts[(uint64_t) blockIdx.x * P + (order ? order[p] : p)] = c;
+		const unsigned int c = s_hist[s_ord[p]];
+		block_counts[(uint64_t) blockIdx.x * P + s_ord[p]] = c;
 		if (c) atomicAdd(counts + p, (unsigned long long) c);
 	}
 }
 
-template <bool ROUTE>
+template <typename IndexT>
 __global__ void __launch_bounds__(CGP_THREADS)
 cg_scatter_staged_kernel(const __grid_constant__ StagedScatterParams A)
 {
@@ -302,21 +322,18 @@ cg_scatter_staged_kernel(const __grid_constant__ StagedScatterParams A)
 	constexpr int STEPS = SEG / 32;
 	extern __shared__ unsigned long long s_mem[];
 	unsigned long long *s_stage = s_mem;                                        /* [4096] one column of the block, in partition order */
-	unsigned long long *s_gbase = s_stage + CGP_ROWS_PER_BLOCK;                 /* [P] global position of the block's first row of p */
-	unsigned int *s_lstart = (unsigned int *) (s_gbase + A.P);                  /* [P + 1] local position of the block's first row of p */
-	unsigned int *s_cnt = s_lstart + A.P + 1;                                   /* [WARPS][P] per-warp counts, then running local offsets */
-	int32_t *s_min = (int32_t *) (s_cnt + WARPS * A.P), *s_max = s_min + A.P;   /* ROUTE: interval bounds */
+	unsigned long long *s_gbase = s_stage + CGP_ROWS_PER_BLOCK;                 /* [P] global position of the block's first row of p, minus its local start */
+	unsigned int *s_cnt = (unsigned int *) (s_gbase + A.P);                     /* [WARPS][P] per-warp counts, then running local offsets */
+	uint16_t *s_part = (uint16_t *) (s_cnt + WARPS * A.P);                      /* [4096] partition of every local position */
 	const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	unsigned int *mine = s_cnt + warp * A.P;
 	for (int p = threadIdx.x; p < WARPS * A.P; p += CGP_THREADS) s_cnt[p] = 0;
-	if (ROUTE)
-		for (int p = threadIdx.x; p < A.P; p += CGP_THREADS) { s_min[p] = A.route.mins[p]; s_max[p] = A.route.maxs[p]; }
 	__syncthreads();
 	const int64_t seg0 = (int64_t) blockIdx.x * CGP_ROWS_PER_BLOCK + (int64_t) warp * SEG;
+	const IndexT *index = (const IndexT *) A.index;
 	short idx[STEPS];
-	unsigned short lpos[STEPS];
-	bool bad = false;
-	/* pass A: partition of every row of this warp's segment, per-warp histogram (match.any groups the lanes of a step) */
+	unsigned short rk[STEPS];          /* rank among the lanes of the same partition in this step | group size << 5 */
+	/* pass A: per-warp histogram; one match.any per row */
 #pragma unroll
 	for (int st = 0; st < STEPS; st++)
 	{
@@ -324,24 +341,26 @@ cg_scatter_staged_kernel(const __grid_constant__ StagedScatterParams A)
 		int p = -1;
 		if (r < A.n)
 		{
-			p = ROUTE ? route_row(A.route, s_min, s_max, A.P, r, &bad) : A.index[r];
+			p = (int) index[r];
 			if (A.order) p = A.order[p];
 		}
 		idx[st] = (short) p;
 		const unsigned peers = __match_any_sync(0xffffffffu, p);
-		if (p >= 0 && lane == (unsigned) (__ffs(peers) - 1)) mine[p] += __popc(peers);
+		const unsigned rank = __popc(peers & ((1u << lane) - 1u)), size = __popc(peers);
+		rk[st] = (unsigned short) (rank | (size << 5));
+		if (p >= 0 && rank == 0) mine[p] += size;
 		__syncwarp();
 	}
-	(void) bad;                     /* unroutable rows were counted (and reported) by the histogram pass */
 	__syncthreads();
 	/* block totals per partition -> local starts (exclusive scan over P), global bases, per-warp running offsets */
+	__shared__ unsigned int s_warp_tot[WARPS];
+	__shared__ unsigned int s_block_rows;
 	{
 		const int per = (A.P + CGP_THREADS - 1) / CGP_THREADS;
 		const int p0 = threadIdx.x * per, p1 = min(p0 + per, A.P);
 		unsigned int local = 0;
 		for (int p = p0; p < p1; p++)
 			for (int w = 0; w < WARPS; w++) local += s_cnt[w * A.P + p];
-		/* exclusive scan of `local` over the 256 threads: warp scan + warp totals through s_lstart's tail (reused below) */
 		unsigned int incl = local;
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1)
@@ -349,38 +368,38 @@ cg_scatter_staged_kernel(const __grid_constant__ StagedScatterParams A)
 			unsigned int y = __shfl_up_sync(0xffffffffu, incl, o);
 			if (lane >= (unsigned) o) incl += y;
 		}
-		__shared__ unsigned int s_warp_tot[WARPS];
 		if (lane == 31) s_warp_tot[warp] = incl;
 		__syncthreads();
-		unsigned int before = incl - local;
-		for (unsigned w = 0; w < warp; w++) before += s_warp_tot[w];
-		unsigned int run = before;
+		unsigned int run = incl - local;
+		for (unsigned w = 0; w < warp; w++) run += s_warp_tot[w];
 		for (int p = p0; p < p1; p++)
 		{
-			s_lstart[p] = run;
-			s_gbase[p] = A.part_base[p] + A.block_offsets[(uint64_t) blockIdx.x * A.P + p];
-			unsigned int wrun = run;
+			s_gbase[p] = A.part_base[p] + A.block_offsets[(uint64_t) blockIdx.x * A.P + p] - run;
 			for (int w = 0; w < WARPS; w++)
 			{
 				unsigned int c = s_cnt[w * A.P + p];
-				s_cnt[w * A.P + p] = wrun;
-				wrun += c;
+				s_cnt[w * A.P + p] = run;
+				run += c;
 			}
-			run = wrun;
 		}
-		if (threadIdx.x == CGP_THREADS - 1) s_lstart[A.P] = run;          /* rows in this block (threads past P contribute 0) */
+		if (threadIdx.x == CGP_THREADS - 1) s_block_rows = run;
 	}
 	__syncthreads();
-	const unsigned int block_rows = s_lstart[A.P];
+	const unsigned int block_rows = s_block_rows;
 	/* pass B: local position of every row (input order inside a partition) */
+	unsigned short lpos[STEPS];
 #pragma unroll
 	for (int st = 0; st < STEPS; st++)
 	{
 		const int p = idx[st];
-		const unsigned peers = __match_any_sync(0xffffffffu, p);
-		if (p >= 0) lpos[st] = (unsigned short) (mine[p] + __popc(peers & ((1u << lane) - 1u)));
+		const unsigned rank = rk[st] & 31u;
+		if (p >= 0)
+		{
+			lpos[st] = (unsigned short) (mine[p] + rank);
+			s_part[lpos[st]] = (uint16_t) p;
+		}
 		__syncwarp();
-		if (p >= 0 && lane == (unsigned) (__ffs(peers) - 1)) mine[p] += __popc(peers);
+		if (p >= 0 && rank == 0) mine[p] += rk[st] >> 5;
 		__syncwarp();
 	}
 	/* column by column: into partition order in shared memory, out as coalesced runs */
@@ -392,23 +411,29 @@ cg_scatter_staged_kernel(const __grid_constant__ StagedScatterParams A)
 			if (idx[st] >= 0) s_stage[lpos[st]] = (unsigned long long) A.cols[c][seg0 + st * 32 + lane];
 		__syncthreads();
 		for (unsigned int j = threadIdx.x; j < block_rows; j += CGP_THREADS)
-		{
-			/* the partition whose local range holds j: the last p with s_lstart[p] <= j */
-			int lo = 0, hi = A.P;
-			while (hi - lo > 1)
-			{
-				int mid = (lo + hi) >> 1;
-				if (s_lstart[mid] <= j) lo = mid; else hi = mid;
-			}
-			A.out[c][s_gbase[lo] + (j - s_lstart[lo])] = (int64_t) s_stage[j];
-		}
+			A.out[c][s_gbase[s_part[j]] + j] = (int64_t) s_stage[j];
 	}
 }
 
 static size_t staged_scatter_smem(int P)
 {
-	return sizeof(unsigned long long) * (CGP_ROWS_PER_BLOCK + (size_t) P) + sizeof(unsigned int) * ((size_t) P + 1 + (CGP_THREADS / 32) * (size_t) P) +
-		   sizeof(int32_t) * 2 * (size_t) P + 16;
+	return sizeof(unsigned long long) * (CGP_ROWS_PER_BLOCK + (size_t) P) + sizeof(unsigned int) * ((CGP_THREADS / 32) * (size_t) P) +
+		   sizeof(uint16_t) * CGP_ROWS_PER_BLOCK + 16;
+}
+
+/* are [mins, maxs] the uniform hash intervals of width floor(2^32 / P), the last one widened to INT32_MAX? */
+static void detect_uniform(const int32_t *mins, const int32_t *maxs, int P, RouteParams *R)
+{
+	R->uniform_inc = 0; R->uniform_shift = -1;
+	const uint64_t inc = (1ull << 32) / (uint64_t) P;
+	for (int i = 0; i < P; i++)
+	{
+		const int64_t lo = (int64_t) INT32_MIN + (int64_t) i * (int64_t) inc;
+		const int64_t hi = i == P - 1 ? (int64_t) INT32_MAX : lo + (int64_t) inc - 1;
+		if (mins[i] != lo || maxs[i] != hi) return;
+	}
+	R->uniform_inc = (uint32_t) inc;
+	for (int sft = 0; sft < 32; sft++) if ((1ull << sft) == inc) R->uniform_shift = sft;
 }
 
 static int32_t *g_d_bounds = nullptr;
@@ -594,10 +619,10 @@ static int partition_scatter_enqueue(CgContext *ctx, const int32_t *d_index, int
 		static bool smem_configured = false;
 		if (!smem_configured)
 		{
-			CG_CUDA(cudaFuncSetAttribute(cg_scatter_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) staged_scatter_smem(CGP_MAX_P)));
+			CG_CUDA(cudaFuncSetAttribute(cg_scatter_staged_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) staged_scatter_smem(CGP_MAX_P)));
 			smem_configured = true;
 		}
-		cg_scatter_staged_kernel<false><<<(unsigned) nblocks, CGP_THREADS, staged_scatter_smem(P), ctx->compute>>>(S);
+		cg_scatter_staged_kernel<int32_t><<<(unsigned) nblocks, CGP_THREADS, staged_scatter_smem(P), ctx->compute>>>(S);
 		CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	}
 	if (h_offsets)
@@ -647,12 +672,14 @@ int cg_partition_route_scatter_async(const int64_t *d_keys, const uint8_t *d_nul
 	memcpy(h_pin + CGP_MAX_P, maxs, sizeof(int32_t) * P);
 	memcpy(h_pin + 2 * CGP_MAX_P, h_order, sizeof(int32_t) * P);
 	const int64_t nblocks = (n + CGP_ROWS_PER_BLOCK - 1) / CGP_ROWS_PER_BLOCK;
-	CgAsyncBuf block_buf, tot_buf, order_buf;
+	CgAsyncBuf block_buf, tot_buf, order_buf, idx_buf;
 	CG_CUDA(block_buf.alloc(sizeof(unsigned long long) * (size_t) std::max<int64_t>(nblocks, 1) * P, ctx->compute));
 	CG_CUDA(tot_buf.alloc(sizeof(unsigned long long) * (2 * P + 1), ctx->compute));
 	CG_CUDA(order_buf.alloc(sizeof(int32_t) * P, ctx->compute));
+	CG_CUDA(idx_buf.alloc(sizeof(uint16_t) * (size_t) std::max<int64_t>(n, 1), ctx->compute));
 	unsigned long long *d_block = block_buf.as<unsigned long long>(), *d_tot = tot_buf.as<unsigned long long>(), *d_base = d_tot + P;
 	int32_t *d_order = order_buf.as<int32_t>();
+	uint16_t *d_idx16 = idx_buf.as<uint16_t>();
 	CG_CUDA(cudaMemcpyAsync(g_d_bounds, h_pin, sizeof(int32_t) * P, cudaMemcpyHostToDevice, ctx->compute));
 	CG_CUDA(cudaMemcpyAsync(g_d_bounds + CGP_MAX_P, h_pin + CGP_MAX_P, sizeof(int32_t) * P, cudaMemcpyHostToDevice, ctx->compute));
 	CG_CUDA(cudaMemcpyAsync(d_order, h_pin + 2 * CGP_MAX_P, sizeof(int32_t) * P, cudaMemcpyHostToDevice, ctx->compute));
@@ -661,9 +688,10 @@ int cg_partition_route_scatter_async(const int64_t *d_keys, const uint8_t *d_nul
 	CG_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int64_t) * (P + 1), ctx->compute));
 	RouteParams R;
 	R.keys = d_keys; R.nulls = d_nulls; R.key_len = key_len; R.by_hash = by_hash; R.mins = g_d_bounds; R.maxs = g_d_bounds + CGP_MAX_P;
+	detect_uniform(mins, maxs, P, &R);
 	if (n > 0)
 	{
-		cg_route_hist_kernel<<<(unsigned) nblocks, CGP_THREADS, 3 * P * sizeof(int32_t), ctx->compute>>>(R, n, P, d_order, d_block,
+		cg_route_hist_kernel<<<(unsigned) nblocks, CGP_THREADS, 4 * P * sizeof(int32_t), ctx->compute>>>(R, n, P, d_order, d_idx16, d_block,
 																										  (unsigned long long *) d_counts,
 																										  (unsigned long long *) (d_counts + P));
 		CG_CUDA(cudaGetLastError()); g_cg_launches++;
@@ -677,16 +705,15 @@ int cg_partition_route_scatter_async(const int64_t *d_keys, const uint8_t *d_nul
 		CG_CUDA(cudaGetLastError()); g_cg_launches++;
 		StagedScatterParams S;
 		memset(&S, 0, sizeof S);
-		S.route = R; S.n = n; S.P = P; S.ncols = ncols; S.block_offsets = d_block; S.part_base = d_base; S.order = d_order;
-		S.errors = (unsigned long long *) (d_counts + P);
+		S.index = d_idx16; S.n = n; S.P = P; S.ncols = ncols; S.block_offsets = d_block; S.part_base = d_base; S.order = nullptr;
 		for (int c = 0; c < ncols; c++) { S.cols[c] = d_cols[c]; S.out[c] = d_out[c]; }
 		static bool smem_configured = false;
 		if (!smem_configured)
 		{
-			CG_CUDA(cudaFuncSetAttribute(cg_scatter_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) staged_scatter_smem(CGP_MAX_P)));
+			CG_CUDA(cudaFuncSetAttribute(cg_scatter_staged_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) staged_scatter_smem(CGP_MAX_P)));
 			smem_configured = true;
 		}
-		cg_scatter_staged_kernel<true><<<(unsigned) nblocks, CGP_THREADS, staged_scatter_smem(P), ctx->compute>>>(S);
+		cg_scatter_staged_kernel<uint16_t><<<(unsigned) nblocks, CGP_THREADS, staged_scatter_smem(P), ctx->compute>>>(S);
 		CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	}
 	return CG_OK;

@@ -558,21 +558,39 @@ int cg_launch_table_init(CgPartial *p, cudaStream_t stream)
 	if (p->d_packed) CG_CUDA(cudaMemsetAsync(p->d_packed, 0, ((size_t) p->entries + CG_COMM_TAIL) * sizeof(uint64_t), stream));
 	p->packed_dirty = false;
 	p->wide_dirty = false;
+	p->read_packed_direct = false;
 	p->launches_since_drain = 0;
 	p->rows_since_drain = 0;
 	return CG_OK;
 }
 
+/* place of an occupied entry in the compacted output: one atomic per warp (the lanes of a warp walk consecutive entries) */
+__device__ __forceinline__ unsigned long long export_position(bool occupied, unsigned long long *count)
+{
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned m = __ballot_sync(0xffffffffu, occupied);
+	if (m == 0) return 0;
+	const int leader = __ffs(m) - 1;
+	unsigned long long first = 0;
+	if ((int) lane == leader) first = atomicAdd(count, (unsigned long long) __popc(m));
+	first = __shfl_sync(0xffffffffu, first, leader);
+	return first + __popc(m & ((1u << lane) - 1u));
+}
+
 __global__ void cg_export_kernel(const __grid_constant__ TableView T, uint64_t out_capacity, int64_t *keys,
 								 uint8_t *nulls, uint64_t *words, unsigned long long *count)
 {
-	for (uint64_t e = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; e < T.entries; e += (uint64_t) gridDim.x * blockDim.x)
+	/* every lane of a warp runs the same number of iterations (the warp-wide ballot needs them all) */
+	for (uint64_t base = (uint64_t) blockIdx.x * blockDim.x; base < T.entries; base += (uint64_t) gridDim.x * blockDim.x)
 	{
-		const uint64_t *ent = T.table + e * (uint64_t) T.stride;
-		bool occupied;
+		const uint64_t e = base + threadIdx.x;
+		const bool valid = e < T.entries;
+		const uint64_t *ent = T.table + (valid ? e : 0) * (uint64_t) T.stride;
+		bool occupied = false;
 		int64_t key = 0;
 		bool key_null = false;
-		if (T.mode == CG_MODE_HASH)
+		if (!valid) { }
+		else if (T.mode == CG_MODE_HASH)
 		{
 			if (e < T.capacity) { key = T.hkeys[e]; occupied = key != CG_HASH_EMPTY; }
 			else { occupied = ent[0] > 0; key_null = (e == T.capacity); key = key_null ? 0 : CG_HASH_EMPTY; }
@@ -591,9 +609,8 @@ __global__ void cg_export_kernel(const __grid_constant__ TableView T, uint64_t o
 		}
 		else
 			occupied = true;    /* plain aggregate: exactly one result row, even over no input */
-		if (!occupied) continue;
-		unsigned long long pos = atomicAdd(count, 1ull);
-		if (pos >= out_capacity) continue;
+		const unsigned long long pos = export_position(occupied, count);
+		if (!occupied || pos >= out_capacity) continue;
 		if (keys) keys[pos] = key;
 		if (nulls) nulls[pos] = key_null ? 1 : 0;
 		if (words)
@@ -624,16 +641,16 @@ __global__ void cg_export_packed_kernel(const __grid_constant__ TableView T, con
 {
 	const uint64_t mask = (1ull << shift) - 1ull;
 	unsigned long long decoded = 0;
-	for (uint64_t e = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; e < T.entries; e += (uint64_t) gridDim.x * blockDim.x)
+	for (uint64_t base = (uint64_t) blockIdx.x * blockDim.x; base < T.entries; base += (uint64_t) gridDim.x * blockDim.x)
 	{
-		const uint64_t w = packed[e];
-		if (w == 0) continue;
+		const uint64_t e = base + threadIdx.x;
+		const uint64_t w = e < T.entries ? packed[e] : 0ull;
 		const uint64_t n = w & mask;
 		const int64_t sum = (int64_t) (w - n) >> shift;
 		decoded += n;
-		if (n == 0) continue;                          /* only reachable after an overflow, which the caller detects */
-		unsigned long long pos = atomicAdd(count, 1ull);
-		if (pos >= out_capacity) continue;
+		/* n == 0 with w != 0 is only reachable after an overflow, which the caller detects */
+		const unsigned long long pos = export_position(n != 0, count);
+		if (n == 0 || pos >= out_capacity) continue;
 		if (keys) keys[pos] = e == T.capacity ? 0 : T.key_min + (int64_t) e;
 		if (nulls) nulls[pos] = e == T.capacity ? 1 : 0;
 		if (words)

@@ -407,6 +407,7 @@ int cg_launch_drain(CgPartial *p, cudaStream_t stream)
 	cg_drain_kernel<<<blocks, 256, 0, stream>>>(p->d_packed, p->d_table, p->entries, p->stride, p->pack_word, p->pack_shift, p->d_stats);
 	CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	p->packed_dirty = false;
+	p->read_packed_direct = false;
 	p->wide_dirty = true;
 	p->launches_since_drain = 0;
 	p->rows_since_drain = 0;
