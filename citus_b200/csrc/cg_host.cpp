@@ -857,6 +857,7 @@ extern "C" int cg_set_option(const char *name, int64_t value)
 	if (!name) return cg_set_error(CG_EINVAL, "NULL option name");
 	if (strcmp(name, "jit") == 0) { cg_jit_set_level((int) value); return CG_OK; }
 	if (strcmp(name, "force_general") == 0) { g_force_general = value ? 1 : 0; return CG_OK; }
+	if (strcmp(name, "realign_tma") == 0) { cg_realign_set_tma((int) value); return CG_OK; }
 	return cg_set_error(CG_EINVAL, "unknown option %s", name);
 }
 

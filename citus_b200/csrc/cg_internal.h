@@ -340,6 +340,7 @@ struct RealignItem
 	uint32_t len;       /* bytes to copy */
 	uint32_t padded;    /* slot size: bytes beyond len are zeroed */
 };
+void cg_realign_set_tma(int on);
 int cg_launch_realign(const uint8_t *raw, uint8_t *arena, const RealignItem *items, uint64_t nitems, cudaStream_t stream);
 
 /* cg_decompress.cu: one compressed value stream (arena offset src, comp_len bytes) to decode into its

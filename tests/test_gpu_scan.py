@@ -891,3 +891,18 @@ def test_join_rows_matches_a_row_at_a_time_join(cg, oracle):
         cg.join_rows(d[0].data_ptr(), d[1].data_ptr(), nb, d[2].data_ptr(), d[3].data_ptr(), npr, capacity=n - 1,
                      d_out=[o.data_ptr() for o in out], d_build_nulls=dbn.data_ptr(), d_probe_nulls=dpn.data_ptr())
     assert cg.join_rows(d[0].data_ptr(), d[1].data_ptr(), 0, d[2].data_ptr(), d[3].data_ptr(), npr) == 0
+
+
+@pytest.mark.parametrize("tma", [1, 0])
+def test_dma_realign_kernels_agree(cg, oracle, tma):
+    """pinned pages -> whole-page DMA -> de-framing on the GPU, with the sm_100 bulk-copy pipeline (cp.async.bulk + mbarrier) and
+    with the plain-load kernel: ragged chunk sizes so that buffers start at every byte alignment and straddle page headers"""
+    cg.set_option("realign_tma", tma)
+    try:
+        cols = [(8, 0, 0, 500, 0), (4, 0, 0, 100, 20000), (2, 0, -1000, 1000, 0), (1, 0, -50, 50, 100000), (8, 0, -10**9, 10**9, 50000)]
+        for rows, chunk in ((54_321, 1777), (100_003, 10_000), (999, 1000)):
+            rel = cg.Relation.generate(cols, rows, seed=rows, stripe_row_limit=chunk * 7, chunk_row_limit=chunk)
+            aggs = [cg.sum_(4), cg.count_star(), cg.min_(2), cg.max_(3), cg.count(1)]
+            run_both(cg, oracle, rel, [(1, "<", 70)], [0], aggs, chunk_row_limit=chunk, e2e="dma")
+    finally:
+        cg.set_option("realign_tma", 1)
