@@ -337,8 +337,8 @@ static void gen_loads(std::string &s, const KPlan &plan, const JitShape &sh, int
 			 * row's 64-row block + popcount of the exists bits below it.  r is a multiple of R, so the R rows of
 			 * this step share one bitmap word; bits past the last row are zero padding. */
 			addf(s, "%sif (n%d) {\n", T, c);
-			addf(s, "%s\tconst uint64_t bw = ld8(b%d + (r >> 6));\n%s\tconst uint32_t sh = r & 63u;\n", T, c, T);
-			addf(s, "%s\tuint32_t vi = __ldg(k%d + (r >> 6)) + (uint32_t) __popcll(bw & ((1ull << sh) - 1ull));\n", T, c);
+			addf(s, "%s\tconst uint64_t bw = sb%d[(r >> 6) - wfirst];\n%s\tconst uint32_t sh = r & 63u;\n", T, c, T);
+			addf(s, "%s\tuint32_t vi = sk%d[(r >> 6) - wfirst] + (uint32_t) __popcll(bw & ((1ull << sh) - 1ull));\n", T, c);
 			addf(s, "%s\te%d_%d = (uint32_t) (bw >> sh) & %uu;\n", T, c, u, (1u << sh.R) - 1u);
 			for (int j = 0; j < sh.R; j++)
 				addf(s, "%s\tif (e%d_%d & %uu) { x%d_%d_%d = ld%d(p%d + (uint64_t) vi * %d); vi++; }\n", T, c, u, 1u << j, c, u, j, len, c, len);
@@ -656,10 +656,14 @@ static std::string gen_source(const KPlan &plan, const JitShape &sh)
 			if (!agg_has_value(g)) continue;
 			addf(s, "\tuint64_t g_a%d_0 = %s, g_a%d_1 = 0;\n", a, op_identity(plan.wordop[g.word0]), a);
 		}
+	if (sh.kind == JK_SMALL || sh.nullable)
+		s += "\textern __shared__ uint64_t s_acc[];\n";
+	if (sh.kind != JK_SMALL && sh.nullable)
+		s += "\tuint64_t *s_nb = s_acc;\n";
 	if (sh.kind == JK_SMALL)
 	{
-		s += "\textern __shared__ uint64_t s_acc[];\n";
 		addf(s, "\tconst uint32_t cells = (uint32_t) P.capacity * %du;\n", sh.nhot);
+		if (sh.nullable) addf(s, "\tuint64_t *s_nb = s_acc + (size_t) cells * %d;\n", JIT_THREADS);
 		addf(s, "\tfor (uint32_t i = 0; i < cells; i++) {\n\t\tuint64_t id = 0ull;\n\t\tswitch (i %% %du) {\n", sh.nhot);
 		for (int a = 0; a < plan.naggs; a++)
 		{
@@ -669,6 +673,21 @@ static std::string gen_source(const KPlan &plan, const JitShape &sh)
 				addf(s, "\t\t\tcase %d: id = %s; break;\n", sh.hot0[a], op_identity(plan.wordop[g.word0]));
 		}
 		addf(s, "\t\t\tdefault: break;\n\t\t}\n\t\ts_acc[(size_t) i * %d + tid] = id;\n\t}\n\tuint64_t *mine = s_acc + tid;\n", JIT_THREADS);
+	}
+	if (sh.nullable)
+	{
+		/* exists bitmap words and rank directory entries of the unit's rows are staged in shared memory once per unit: the
+		 * per-row lookups then cost shared-memory latency and the value loads depend on nothing in global memory */
+		int nn = 0;
+		for (int c = 0; c < plan.ncols; c++) if (col_nullable(sh, c)) nn++;
+		s += "\tconst uint32_t NW = P.max_cg_rows / 64u + 2u;\n";
+		int ni = 0;
+		for (int c = 0; c < plan.ncols; c++)
+			if (col_nullable(sh, c))
+			{
+				addf(s, "\tuint64_t *sb%d = s_nb + %du * NW;\n\tuint32_t *sk%d = (uint32_t *) (s_nb + %du * NW) + %du * NW;\n", c, ni, c, nn, ni);
+				ni++;
+			}
 	}
 	/* work unit = (chunk group, row range [row0, rows)): launches with few chunk groups cut them into slices */
 	s += "\tconst uint32_t nunits = P.nselected * (uint32_t) P.slices;\n"
@@ -687,6 +706,15 @@ static std::string gen_source(const KPlan &plan, const JitShape &sh)
 					"\t\tconst uint32_t *k%d = (const uint32_t *) (P.arena + __ldg(&cc[%d].rank_off));\n"
 					"\t\tconst bool n%d = __ldg(&cc[%d].value_count) != chunk_rows;\n",
 				 c, plan.slot[c], c, plan.slot[c], c, plan.slot[c]);
+	}
+	if (sh.nullable)
+	{
+		s += "\t\tconst uint32_t wfirst = row0 >> 6, wcount = rows > row0 ? ((rows + 63u) >> 6) - wfirst : 0u;\n\t\t__syncthreads();\n";
+		for (int c = 0; c < plan.ncols; c++)
+			if (col_nullable(sh, c))
+				addf(s, "\t\tif (n%d) for (uint32_t i = tid; i < wcount; i += %du) { sb%d[i] = b%d[wfirst + i]; sk%d[i] = k%d[wfirst + i]; }\n", c,
+					 JIT_THREADS, c, c, c, c);
+		s += "\t\t__syncthreads();\n";
 	}
 	s += "\t\tscanned += (tid == 0 && sl == 0) ? chunk_rows : 0;\n";
 	if (plan.ncols == 0)
@@ -886,16 +914,27 @@ int cg_launch_scan_jit(CgContext *ctx, const KPlan &plan, uint32_t nullable, cud
 		}
 		if (getenv("CG_JIT_DUMP")) fprintf(stderr, "%s\n", src.c_str());
 	}
-	if (sh.smem > k->smem_configured || k->occupancy == 0)
+	/* dynamic shared memory: the SMALL kind's cells + the staged exists bitmaps / rank directories of nullable columns */
+	KPlan sized = plan;
+	size_t smem = sh.smem;
+	if (sh.nullable)
 	{
-		if (sh.smem > 48 * 1024)
+		int nn = 0;
+		for (int c = 0; c < plan.ncols; c++) if (col_nullable(sh, c)) nn++;
+		if (sized.max_cg_rows == 0) sized.max_cg_rows = (uint32_t) JIT_MAX_CHUNK_ROWS;
+		smem += (size_t) nn * (sized.max_cg_rows / 64u + 2u) * 12u + 16u;
+	}
+	if (smem > 220 * 1024) { lock.unlock(); return CG_OK; }        /* does not fit: the caller's ahead-of-time kernels take it */
+	if (smem > k->smem_configured || k->occupancy == 0)
+	{
+		if (smem > 48 * 1024)
 		{
-			int e = g_api.setattr(k->fn, CG_CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int) sh.smem);
-			if (e != 0) return cg_set_error(CG_ECUDA, "cuFuncSetAttribute(%zu bytes of shared memory) failed: %d", sh.smem, e);
+			int e = g_api.setattr(k->fn, CG_CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int) smem);
+			if (e != 0) return cg_set_error(CG_ECUDA, "cuFuncSetAttribute(%zu bytes of shared memory) failed: %d", smem, e);
 		}
-		k->smem_configured = sh.smem;
+		k->smem_configured = smem;
 		int occ = 0;
-		if (g_api.occupancy(&occ, k->fn, JIT_THREADS, sh.smem) != 0 || occ < 1) occ = 1;
+		if (g_api.occupancy(&occ, k->fn, JIT_THREADS, smem) != 0 || occ < 1) occ = 1;
 		k->occupancy = occ;
 	}
 	lock.unlock();
@@ -911,7 +950,7 @@ int cg_launch_scan_jit(CgContext *ctx, const KPlan &plan, uint32_t nullable, cud
 	}
 	for (uint32_t first = 0; first < plan.nselected; )
 	{
-		KPlan piece = plan;
+		KPlan piece = sized;
 		piece.selected = plan.selected + first;
 		piece.nselected = std::min(plan.nselected - first, max_cgs_per_launch);
 		piece.slices = 1; piece.slice_rows = 1u << 30;
@@ -922,7 +961,7 @@ int cg_launch_scan_jit(CgContext *ctx, const KPlan &plan, uint32_t nullable, cud
 		}
 		uint32_t grid = (uint32_t) std::min<uint64_t>(grid_full, (uint64_t) piece.nselected * (uint64_t) piece.slices);
 		void *args[] = {&piece};
-		int e = g_api.launch(k->fn, grid, 1, 1, JIT_THREADS, 1, 1, (unsigned) sh.smem, (void *) stream, args, nullptr);
+		int e = g_api.launch(k->fn, grid, 1, 1, JIT_THREADS, 1, 1, (unsigned) smem, (void *) stream, args, nullptr);
 		if (e != 0)
 		{
 			const char *msg = nullptr;
