@@ -465,10 +465,11 @@ extern "C" int cg_comm_repartition_exchange(int32_t slot, const int64_t *const *
 	std::vector<int32_t> position(P);
 	int nlocal = 0;
 	cg_comm_exchange_plan(P, W, me, nullptr, position.data(), nullptr, nullptr, nullptr, &nlocal);
-	rc = devbuf_grow(&S.send, (size_t) std::max<int64_t>(n, 1) * sizeof(int64_t) * ncols);
+	/* one rank: the scatter's output IS the received table (no exchange); else it is the send buffer */
+	rc = devbuf_grow(W == 1 ? &S.recv : &S.send, (size_t) std::max<int64_t>(n, 1) * sizeof(int64_t) * ncols);
 	if (rc) return rc;
 	std::vector<int64_t *> outs(ncols);
-	for (int c = 0; c < ncols; c++) outs[c] = (int64_t *) S.send.p + (size_t) c * n;
+	for (int c = 0; c < ncols; c++) outs[c] = (int64_t *) (W == 1 ? S.recv.p : S.send.p) + (size_t) c * n;
 	rc = cg_partition_route_scatter_async(d_cols[0], d_key_nulls, n, key_len, 1, mins, maxs, P, position.data(), d_cols, ncols, outs.data(),
 										  d_counts, g_comm.ev_index);
 	if (rc) return rc;
@@ -496,8 +497,11 @@ extern "C" int cg_comm_repartition_exchange(int32_t slot, const int64_t *const *
 	cg_comm_exchange_plan(P, W, me, counts.data(), position.data(), send_rows.data(), recv_rows.data(), S.part_counts.data(), &nlocal);
 	int64_t total_recv = 0;
 	for (int r = 0; r < W; r++) total_recv += recv_rows[r];
-	rc = devbuf_grow(&S.recv, (size_t) std::max<int64_t>(total_recv, 1) * sizeof(int64_t) * ncols);
-	if (rc) return rc;
+	if (W > 1)
+	{
+		rc = devbuf_grow(&S.recv, (size_t) std::max<int64_t>(total_recv, 1) * sizeof(int64_t) * ncols);
+		if (rc) return rc;
+	}
 	S.recv_rows = total_recv;
 	S.ncols = ncols;
 	S.sent_bytes = 0;
@@ -505,9 +509,7 @@ extern "C" int cg_comm_repartition_exchange(int32_t slot, const int64_t *const *
 	CG_CUDA(cudaEventRecord(S.t0, g_comm.side));
 	if (W == 1)
 	{
-		for (int c = 0; c < ncols; c++)
-			CG_CUDA(cudaMemcpyAsync((int64_t *) S.recv.p + (size_t) c * total_recv, outs[c], sizeof(int64_t) * (size_t) n,
-									cudaMemcpyDeviceToDevice, g_comm.side));
+		/* nothing to move: total_recv == n and the scatter wrote the receive buffer */
 	}
 	else
 	{

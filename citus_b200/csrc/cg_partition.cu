@@ -314,7 +314,7 @@ cg_route_hist_kernel(const RouteParams R, int64_t n, int P, const int32_t *order
 }
 
 template <typename IndexT>
-__global__ void __launch_bounds__(CGP_THREADS)
+__global__ void __launch_bounds__(CGP_THREADS, 4)     /* <= 64 registers: four CTAs per SM (the first build used 80 -> three) */
 cg_scatter_staged_kernel(const __grid_constant__ StagedScatterParams A)
 {
 	constexpr int WARPS = CGP_THREADS / 32;
@@ -537,6 +537,82 @@ cg_partition_scan2_kernel(unsigned long long *block_counts, unsigned long long *
 	if (threadIdx.x == 1023) totals[p] = s_sum[1023];
 }
 
+/*
+ * The same scan with all SMs: the blocks are cut into chunks of CGP_SCAN_CHUNK; pass 1 sums every (partition, chunk),
+ * pass 2 scans the chunk sums of a partition (one warp) and yields its total, pass 3 rewrites every chunk as offsets.
+ */
+#define CGP_SCAN_CHUNK 2048
+__global__ void __launch_bounds__(256)
+cg_partition_scan_sum_kernel(const unsigned long long *block_counts, unsigned long long *chunk_sums, int64_t nblocks, int P, int nchunks)
+{
+	__shared__ unsigned long long s_w[8];
+	const int p = blockIdx.x % P, c = blockIdx.x / P;
+	const int64_t b0 = (int64_t) c * CGP_SCAN_CHUNK, b1 = b0 + CGP_SCAN_CHUNK < nblocks ? b0 + CGP_SCAN_CHUNK : nblocks;
+	unsigned long long local = 0;
+	for (int64_t b = b0 + threadIdx.x; b < b1; b += 256) local += block_counts[b * P + p];
+	for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+	if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = local;
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		unsigned long long t = 0;
+		for (int i = 0; i < 8; i++) t += s_w[i];
+		chunk_sums[(size_t) p * nchunks + c] = t;
+	}
+}
+
+__global__ void cg_partition_scan_chunks_kernel(unsigned long long *chunk_sums, unsigned long long *totals, int P, int nchunks)
+{
+	const int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= P) return;
+	unsigned long long run = 0;
+	for (int c = 0; c < nchunks; c++) { unsigned long long v = chunk_sums[(size_t) p * nchunks + c]; chunk_sums[(size_t) p * nchunks + c] = run; run += v; }
+	totals[p] = run;
+}
+
+__global__ void __launch_bounds__(256)
+cg_partition_scan_apply_kernel(unsigned long long *block_counts, const unsigned long long *chunk_sums, int64_t nblocks, int P, int nchunks)
+{
+	__shared__ unsigned long long s_w[8];
+	const int p = blockIdx.x % P, c = blockIdx.x / P;
+	const int64_t b0 = (int64_t) c * CGP_SCAN_CHUNK, b1 = b0 + CGP_SCAN_CHUNK < nblocks ? b0 + CGP_SCAN_CHUNK : nblocks;
+	const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	unsigned long long run = chunk_sums[(size_t) p * nchunks + c];
+	for (int64_t base = b0; base < b1; base += 256)
+	{
+		const int64_t b = base + threadIdx.x;
+		const unsigned long long v = b < b1 ? block_counts[b * P + p] : 0ull;
+		unsigned long long incl = v;
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			unsigned long long y = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= (unsigned) o) incl += y;
+		}
+		if (lane == 31) s_w[warp] = incl;
+		__syncthreads();
+		unsigned long long before = run + incl - v;
+		unsigned long long tile = 0;
+		for (unsigned w = 0; w < 8; w++) { if (w < warp) before += s_w[w]; tile += s_w[w]; }
+		if (b < b1) block_counts[b * P + p] = before;
+		run += tile;
+		__syncthreads();
+	}
+}
+
+static int partition_scan_blocks(CgContext *ctx, unsigned long long *d_block, unsigned long long *d_tot, int64_t nblocks, int P, CgAsyncBuf *scratch)
+{
+	const int nchunks = (int) ((nblocks + CGP_SCAN_CHUNK - 1) / CGP_SCAN_CHUNK);
+	CG_CUDA(scratch->alloc(sizeof(unsigned long long) * (size_t) P * (size_t) std::max(nchunks, 1), ctx->compute));
+	unsigned long long *d_chunks = scratch->as<unsigned long long>();
+	cg_partition_scan_sum_kernel<<<(unsigned) (P * nchunks), 256, 0, ctx->compute>>>(d_block, d_chunks, nblocks, P, nchunks);
+	CG_CUDA(cudaGetLastError()); g_cg_launches++;
+	cg_partition_scan_chunks_kernel<<<(P + 127) / 128, 128, 0, ctx->compute>>>(d_chunks, d_tot, P, nchunks);
+	CG_CUDA(cudaGetLastError()); g_cg_launches++;
+	cg_partition_scan_apply_kernel<<<(unsigned) (P * nchunks), 256, 0, ctx->compute>>>(d_block, d_chunks, nblocks, P, nchunks);
+	CG_CUDA(cudaGetLastError()); g_cg_launches++;
+	return CG_OK;
+}
+
 __global__ void cg_partition_base_kernel(const unsigned long long *totals, unsigned long long *base, int P)
 {
 	if (threadIdx.x == 0 && blockIdx.x == 0)
@@ -583,7 +659,7 @@ static int partition_scatter_enqueue(CgContext *ctx, const int32_t *d_index, int
 		}
 	}
 	int64_t nblocks = (n + CGP_ROWS_PER_BLOCK - 1) / CGP_ROWS_PER_BLOCK;
-	CgAsyncBuf block_buf, tot_buf, order_buf;
+	CgAsyncBuf block_buf, tot_buf, order_buf, chunk_buf;
 	int32_t *d_order = nullptr;
 	CG_CUDA(block_buf.alloc(sizeof(unsigned long long) * (size_t) std::max<int64_t>(nblocks, 1) * P, ctx->compute));
 	CG_CUDA(tot_buf.alloc(sizeof(unsigned long long) * (2 * P + 1), ctx->compute));
@@ -608,8 +684,8 @@ static int partition_scatter_enqueue(CgContext *ctx, const int32_t *d_index, int
 	{
 		cg_block_count_kernel<<<(unsigned) nblocks, CGP_THREADS, P * sizeof(unsigned int), ctx->compute>>>(d_index, d_order, n, P, d_block);
 		CG_CUDA(cudaGetLastError()); g_cg_launches++;
-		cg_partition_scan2_kernel<<<P, 1024, 0, ctx->compute>>>(d_block, d_tot, nblocks, P);
-		CG_CUDA(cudaGetLastError()); g_cg_launches++;
+		int src_ = partition_scan_blocks(ctx, d_block, d_tot, nblocks, P, &chunk_buf);
+		if (src_) return src_;
 		cg_partition_base_kernel<<<1, 32, 0, ctx->compute>>>(d_tot, d_base, P);
 		CG_CUDA(cudaGetLastError()); g_cg_launches++;
 		StagedScatterParams S;
@@ -672,7 +748,7 @@ int cg_partition_route_scatter_async(const int64_t *d_keys, const uint8_t *d_nul
 	memcpy(h_pin + CGP_MAX_P, maxs, sizeof(int32_t) * P);
 	memcpy(h_pin + 2 * CGP_MAX_P, h_order, sizeof(int32_t) * P);
 	const int64_t nblocks = (n + CGP_ROWS_PER_BLOCK - 1) / CGP_ROWS_PER_BLOCK;
-	CgAsyncBuf block_buf, tot_buf, order_buf, idx_buf;
+	CgAsyncBuf block_buf, tot_buf, order_buf, idx_buf, chunk_buf;
 	CG_CUDA(block_buf.alloc(sizeof(unsigned long long) * (size_t) std::max<int64_t>(nblocks, 1) * P, ctx->compute));
 	CG_CUDA(tot_buf.alloc(sizeof(unsigned long long) * (2 * P + 1), ctx->compute));
 	CG_CUDA(order_buf.alloc(sizeof(int32_t) * P, ctx->compute));
@@ -699,8 +775,8 @@ int cg_partition_route_scatter_async(const int64_t *d_keys, const uint8_t *d_nul
 	if (after_counts) CG_CUDA(cudaEventRecord(after_counts, ctx->compute));
 	if (n > 0)
 	{
-		cg_partition_scan2_kernel<<<P, 1024, 0, ctx->compute>>>(d_block, d_tot, nblocks, P);
-		CG_CUDA(cudaGetLastError()); g_cg_launches++;
+		int src_ = partition_scan_blocks(ctx, d_block, d_tot, nblocks, P, &chunk_buf);
+		if (src_) return src_;
 		cg_partition_base_kernel<<<1, 32, 0, ctx->compute>>>(d_tot, d_base, P);
 		CG_CUDA(cudaGetLastError()); g_cg_launches++;
 		StagedScatterParams S;
