@@ -119,6 +119,7 @@ void cg_jit_set_level(int level) { g_jit_level = level < 0 ? 0 : level; }
 /* a lane's private 64-bit sum cell is exact while |term| * rows-per-lane < 2^63; launches are cut so
  * that no lane sees more rows than this */
 #define JIT_LANE_ROWS_CAP (1ll << 22)
+#define JIT_NARROW_ROWS_CAP 160ll   /* four 10 000-row chunk groups per CTA: 40 rows per lane each */
 #define JIT_MAX_CHUNK_ROWS 100000ll    /* chunk_group_row_limit's upper bound (columnar.c:50-51) */
 
 enum { JK_GLOBAL = 0, JK_SMALL = 1, JK_TABLE = 2 };
@@ -130,6 +131,15 @@ struct JitShape
 	int nhot = 0;                     /* SMALL: cells per group */
 	int hot0[CG_MAX_AGGS];            /* SMALL: first cell of the aggregate, -1 = none */
 	bool lane1[CG_MAX_AGGS];          /* SMALL: integer sum kept in one cell per lane */
+	/* SMALL, narrow cells: a lane sees at most lane_rows_cap rows per launch, so a sum whose |term| * cap < 2^31 needs only
+	 * 32 bits there; two such sums (or the row count and one sum) share one 64-bit cell and one shared-memory update:
+	 * half 1 = high 32 bits (two's complement), half 0 = low 32 bits holding sum(term + bias) (non-negative, so that it never
+	 * borrows from the high half; the bias times the group's row count is taken off at the flush), -1 = a cell of its own */
+	int half[CG_MAX_AGGS];
+	int64_t bias[CG_MAX_AGGS];
+	int rows_partner = -1;            /* aggregate in the high half of cell 0 (whose low half counts the rows), -1 = none */
+	long long lane_rows_cap = (1ll << 22);
+	int min_blocks = 0;               /* __launch_bounds__ second argument, 0 = none */
 	size_t smem = 0;
 	bool packed = false;
 	int pack_agg = -1;
@@ -150,6 +160,8 @@ static void addf(std::string &s, const char *fmt, ...)
 static bool agg_has_value(const KAgg &g) { return g.kind != CG_AGG_COUNT_STAR && g.kind != CG_AGG_COUNT; }
 static bool agg_two_limbs(const KAgg &g) { return g.kind == CG_AGG_SUM && !g.is_float && g.nlimbs == 2; }
 
+static std::string agg_null_expr(const KAgg &g, const JitShape &sh);
+
 static void choose_shape(const KPlan &plan, uint32_t nullable, JitShape *sh)
 {
 	sh->nullable = plan.ncols >= 32 ? nullable : (nullable & ((1u << plan.ncols) - 1u));
@@ -163,14 +175,41 @@ static void choose_shape(const KPlan &plan, uint32_t nullable, JitShape *sh)
 		if (r && (atoi(r) == 2 || atoi(r) == 4)) sh->R = atoi(r);
 		if (u && atoi(u) >= 1 && atoi(u) <= 4) sh->U = atoi(u);
 	}
-	for (int a = 0; a < CG_MAX_AGGS; a++) { sh->hot0[a] = -1; sh->lane1[a] = false; }
+	for (int a = 0; a < CG_MAX_AGGS; a++) { sh->hot0[a] = -1; sh->lane1[a] = false; sh->half[a] = -1; sh->bias[a] = 0; }
 	if (plan.mode == CG_MODE_DENSE)
 	{
+		static int narrow_on = -1;
+		if (narrow_on < 0) { const char *e = getenv("CG_JIT_NARROW"); narrow_on = e ? atoi(e) : 1; }
+		/* candidates for 32-bit halves */
+		int cand[CG_MAX_AGGS], ncand = 0;
+		for (int a = 0; a < plan.naggs && narrow_on; a++)
+		{
+			const KAgg &g = plan.aggs[a];
+			if (g.kind == CG_AGG_SUM && !g.is_float && g.tbound > 0 && (__int128) g.tbound * JIT_NARROW_ROWS_CAP < ((__int128) 1 << 31)) cand[ncand++] = a;
+		}
+		bool taken[CG_MAX_AGGS] = {false};
 		int nhot = 1;
+		if (ncand > 0)
+		{
+			/* cell 0: rows (low) + the first candidate (high) */
+			sh->rows_partner = cand[0]; sh->hot0[cand[0]] = 0; sh->half[cand[0]] = 1; sh->lane1[cand[0]] = true; taken[cand[0]] = true;
+			/* further cells: a candidate without nullable inputs in the low half (biased), another one in the high half */
+			for (int i = 1; i < ncand; i++)
+			{
+				const int x = cand[i];
+				if (taken[x] || !agg_null_expr(plan.aggs[x], *sh).empty()) continue;
+				int y = -1;
+				for (int j = 1; j < ncand; j++) if (j != i && !taken[cand[j]]) { y = cand[j]; break; }
+				if (y < 0) break;
+				sh->hot0[x] = nhot; sh->half[x] = 0; sh->bias[x] = plan.aggs[x].tbound; sh->lane1[x] = true; taken[x] = true;
+				sh->hot0[y] = nhot; sh->half[y] = 1; sh->lane1[y] = true; taken[y] = true;
+				nhot++;
+			}
+		}
 		for (int a = 0; a < plan.naggs; a++)
 		{
 			const KAgg &g = plan.aggs[a];
-			if (!agg_has_value(g)) continue;
+			if (!agg_has_value(g) || taken[a]) continue;
 			sh->hot0[a] = nhot;
 			if (g.kind == CG_AGG_SUM && !g.is_float)
 			{
@@ -190,6 +229,17 @@ static void choose_shape(const KPlan &plan, uint32_t nullable, JitShape *sh)
 			sh->kind = JK_SMALL;
 			sh->nhot = nhot;
 			sh->smem = bytes;
+			if (ncand > 0) sh->lane_rows_cap = JIT_NARROW_ROWS_CAP;
+			/* registers: four CTAs per SM when their cells fit (the compiler is held to 64 registers) */
+			if (bytes + 4096 <= 55 * 1024) sh->min_blocks = 4;
+			const char *mb = getenv("CG_JIT_MINB");
+			if (mb) sh->min_blocks = atoi(mb);
+		}
+		else
+		{
+			/* not the shared-memory kind after all: no narrow cells */
+			for (int a = 0; a < CG_MAX_AGGS; a++) { sh->half[a] = -1; sh->bias[a] = 0; }
+			sh->rows_partner = -1;
 		}
 	}
 	if (sh->kind == JK_TABLE && plan.packed)
@@ -610,7 +660,10 @@ static void gen_row(std::string &s, const KPlan &plan, const JitShape &sh, int u
 			inner += "\t";
 			D = inner.c_str();
 		}
-		addf(s, "%suint64_t *e = mine + (uint32_t) slot * %du;\n%se[0] += 1ull;\n", D, sh.nhot * JIT_THREADS, D);
+		addf(s, "%suint64_t *e = mine + (uint32_t) slot * %du;\n", D, sh.nhot * JIT_THREADS);
+		/* one update per cell: the contributions of the (at most two) aggregates that share it are added together */
+		std::vector<std::string> cellexpr(sh.nhot);
+		cellexpr[0] = "1ull";
 		for (int a = 0; a < plan.naggs; a++)
 		{
 			const KAgg &g = plan.aggs[a];
@@ -618,6 +671,16 @@ static void gen_row(std::string &s, const KPlan &plan, const JitShape &sh, int u
 			/* NULL-input counters stay on global reductions (rare) */
 			if (!an[a].empty()) addf(s, "%sif (an%d) red_add(P.table + slot * %dull + %d, 1ull);\n", D, a, plan.stride, g.nullword);
 			if (!agg_has_value(g)) continue;
+			if (sh.half[a] >= 0)
+			{
+				char buf[160];
+				if (sh.half[a] == 1) snprintf(buf, sizeof buf, "((uint64_t) it%d << 32)", a);
+				else snprintf(buf, sizeof buf, "(uint64_t) (uint32_t) (it%d + %lldll)", a, (long long) sh.bias[a]);
+				std::string term = an[a].empty() ? std::string(buf) : ("(an" + std::to_string(a) + " ? 0ull : " + buf + ")");
+				std::string &ce = cellexpr[sh.hot0[a]];
+				ce = ce.empty() ? term : (ce + " + " + term);
+				continue;
+			}
 			char cell[48];
 			snprintf(cell, sizeof cell, "e[%d]", sh.hot0[a] * JIT_THREADS);
 			std::string guard = an[a].empty() ? "" : ("if (!an" + std::to_string(a) + ") ");
@@ -631,6 +694,8 @@ static void gen_row(std::string &s, const KPlan &plan, const JitShape &sh, int u
 			else
 				addf(s, "%s%s%s = %s;\n", D, guard.c_str(), cell, op_combine(plan.wordop[g.word0], cell, w0v[a]).c_str());
 		}
+		for (int k = 0; k < sh.nhot; k++)
+			if (!cellexpr[k].empty()) addf(s, "%se[%d] += %s;\n", D, k * JIT_THREADS, cellexpr[k].c_str());
 		if (!zkey.empty()) addf(s, "%s}\n", C);
 	}
 	else
@@ -646,7 +711,10 @@ static std::string gen_source(const KPlan &plan, const JitShape &sh)
 	std::string s;
 	s.reserve(32768);
 	gen_prelude(s);
-	addf(s, "extern \"C\" __global__ void __launch_bounds__(%d) cg_jit_scan(const __grid_constant__ KPlan P)\n{\n", JIT_THREADS);
+	if (sh.min_blocks > 0)
+		addf(s, "extern \"C\" __global__ void __launch_bounds__(%d, %d) cg_jit_scan(const __grid_constant__ KPlan P)\n{\n", JIT_THREADS, sh.min_blocks);
+	else
+		addf(s, "extern \"C\" __global__ void __launch_bounds__(%d) cg_jit_scan(const __grid_constant__ KPlan P)\n{\n", JIT_THREADS);
 	s += "\tconst uint32_t tid = threadIdx.x;\n\tuint32_t removed = 0;\n\tunsigned long long scanned = 0;\n\tuint64_t g_rows = 0;\n";
 	if (sh.kind == JK_GLOBAL)
 		for (int a = 0; a < plan.naggs; a++)
@@ -787,12 +855,41 @@ static std::string gen_source(const KPlan &plan, const JitShape &sh)
 		addf(s, "\t__syncthreads();\n\tfor (uint32_t i = tid; i < cells; i += %d) {\n\t\tconst uint64_t *col = s_acc + (size_t) i * %d;\n"
 				"\t\tuint64_t *ge = P.table + (uint64_t) (i / %du) * %dull;\n\t\tswitch (i %% %du) {\n",
 			 JIT_THREADS, JIT_THREADS, sh.nhot, plan.stride, sh.nhot);
-		addf(s, "\t\t\tcase 0: { uint64_t x = 0; for (uint32_t k = 0; k < %d; k++) x += col[(k + tid) %% %d]; if (x) red_add(ge, x); break; }\n",
-			 JIT_THREADS, JIT_THREADS);
+		/* emits the statements that add the exact lane total `S` (int64_t) of aggregate a to the group's table words */
+		auto add_total = [&](int a) -> std::string {
+			const KAgg &g = plan.aggs[a];
+			char b[256];
+			if (g.nlimbs == 2)
+				snprintf(b, sizeof b, "{ const uint64_t l_ = (uint64_t) (uint32_t) S, h_ = (uint64_t) (S >> 32); if (l_) red_add(ge + %d, l_); if (h_) red_add(ge + %d, h_); }",
+						 g.word0, g.word0 + 1);
+			else
+				snprintf(b, sizeof b, "{ if (S) red_add(ge + %d, (uint64_t) S); }", g.word0);
+			return b;
+		};
+		if (sh.rows_partner < 0)
+			addf(s, "\t\t\tcase 0: { uint64_t x = 0; for (uint32_t k = 0; k < %d; k++) x += col[(k + tid) %% %d]; if (x) red_add(ge, x); break; }\n",
+				 JIT_THREADS, JIT_THREADS);
+		else
+			addf(s, "\t\t\tcase 0: { uint64_t r_ = 0; int64_t S = 0; for (uint32_t k = 0; k < %d; k++) { const uint64_t x = col[(k + tid) %% %d]; r_ += (uint32_t) x; S += (int64_t) (int32_t) (uint32_t) (x >> 32); }\n"
+					"\t\t\t\tif (r_) red_add(ge, r_); %s break; }\n",
+				 JIT_THREADS, JIT_THREADS, add_total(sh.rows_partner).c_str());
+		/* paired cells: low half = sum(term + bias) of aggregate x over the group's rows of a lane, high half = aggregate y */
+		for (int cell = 1; cell < sh.nhot; cell++)
+		{
+			int x = -1, y = -1;
+			for (int a = 0; a < plan.naggs; a++)
+				if (sh.hot0[a] == cell && sh.half[a] == 0) x = a; else if (sh.hot0[a] == cell && sh.half[a] == 1) y = a;
+			if (x < 0 || y < 0) continue;
+			addf(s, "\t\t\tcase %d: { uint64_t lo_ = 0, r_ = 0; int64_t hi_ = 0; const uint64_t *rows_ = s_acc + (size_t) (i - %d) * %d;\n"
+					"\t\t\t\tfor (uint32_t k = 0; k < %d; k++) { const uint64_t v_ = col[(k + tid) %% %d]; lo_ += (uint32_t) v_; hi_ += (int64_t) (int32_t) (uint32_t) (v_ >> 32); r_ += (uint32_t) rows_[(k + tid) %% %d]; }\n"
+					"\t\t\t\t{ const int64_t S = (int64_t) lo_ - (int64_t) r_ * %lldll; %s }\n"
+					"\t\t\t\t{ const int64_t S = hi_; %s } break; }\n",
+				 cell, cell, JIT_THREADS, JIT_THREADS, JIT_THREADS, JIT_THREADS, (long long) sh.bias[x], add_total(x).c_str(), add_total(y).c_str());
+		}
 		for (int a = 0; a < plan.naggs; a++)
 		{
 			const KAgg &g = plan.aggs[a];
-			if (!agg_has_value(g)) continue;
+			if (!agg_has_value(g) || sh.half[a] >= 0) continue;
 			int op = plan.wordop[g.word0];
 			char p[32];
 			snprintf(p, sizeof p, "ge + %d", g.word0);
@@ -943,8 +1040,10 @@ int cg_launch_scan_jit(CgContext *ctx, const KPlan &plan, uint32_t nullable, cud
 	uint32_t max_cgs_per_launch = UINT32_MAX;
 	if (sh.kind == JK_SMALL)
 	{
-		int64_t rows_per_cg_lane = ((JIT_MAX_CHUNK_ROWS + JIT_THREADS * sh.R - 1) / (JIT_THREADS * sh.R)) * sh.R;
-		int64_t cgs_per_cta = JIT_LANE_ROWS_CAP / rows_per_cg_lane;
+		const int64_t cg_rows = plan.max_cg_rows ? (int64_t) plan.max_cg_rows : JIT_MAX_CHUNK_ROWS;
+		int64_t rows_per_cg_lane = ((cg_rows + JIT_THREADS * sh.R - 1) / (JIT_THREADS * sh.R)) * sh.R;
+		int64_t cgs_per_cta = sh.lane_rows_cap / rows_per_cg_lane;
+		if (cgs_per_cta < 1) { fprintf(stderr, "[cg] jit: chunk groups of %lld rows exceed the narrow cells' per-lane row cap\n", (long long) cg_rows); return CG_OK; }
 		int64_t cap = cgs_per_cta * (int64_t) grid_full;
 		if (cap < (int64_t) UINT32_MAX) max_cgs_per_launch = (uint32_t) cap;
 	}
