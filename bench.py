@@ -76,6 +76,7 @@ def parse():
                    help="columnar.compression of the synthetic shards (BASELINE configs use none; lz4/zstd exercise the GPU decoders)")
     p.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to the CPUs of its GPU's NUMA node")
     p.add_argument("--leg-steps", type=int, default=5)
+    p.add_argument("--leg-timeout", type=float, default=240.0, help="deadline in seconds for each extra leg")
     return p.parse_args()
 
 
@@ -414,8 +415,10 @@ class Env:
         return ms, clocks, int(launches), int(nscan.value), float(ktotal.value), out
 
 
-def make_partial(env, rels, quals, group, aggs, total_rows, expected_groups=0):
-    """plan constants from the skip lists (key range, |term| bounds), agreed over the ranks, and the group table"""
+def make_partial(env, rels, quals, group, aggs, total_rows, expected_groups=0, columns=None):
+    """plan constants from the skip lists (key range, |term| bounds), agreed over the ranks, and the group table.
+    A rank that owns no shard of the relation (world > shard count) still builds the same table and takes part in
+    every collective: `columns` (the generator's column list) gives it the column descriptors."""
     cg = env.cg
     desc = cg.make_desc(quals, group, aggs, expected_groups=expected_groups)
     two = len(group) == 2
@@ -447,8 +450,8 @@ def make_partial(env, rels, quals, group, aggs, total_rows, expected_groups=0):
     for a, b in zip(aggs, bounds):
         a.term_abs_bound = b
     desc = cg.make_desc(quals, group, aggs, expected_groups=expected_groups)
-    some = next(iter(rels.values()))
-    return cg.GpuColumnarAgg(desc, some.column_descs(), kmin, kmax, total_rows), desc
+    coldescs = next(iter(rels.values())).column_descs() if rels else [(c[0], 0) for c in columns]
+    return cg.GpuColumnarAgg(desc, coldescs, kmin, kmax, total_rows), desc
 
 
 def _s32(x):
@@ -545,7 +548,7 @@ def run_c2(env, args, nulls=False, headline=True):
         columns[2] = (8, 0, -10**9, 10**9, 50000)            # 5 % NULLs in v
     rels = generate_shards(env, columns, my_shards, rows_per_shard, SEED, args.compression if headline else "none")
     aggs = [cg.sum_(2), cg.count_star()]
-    partial, desc = make_partial(env, rels, C2_QUALS, C2_GROUP, aggs, total_rows)
+    partial, desc = make_partial(env, rels, C2_QUALS, C2_GROUP, aggs, total_rows, columns=columns)
     nw, ops, dense, cap = partial.layout()
     log(f"rank {rank}: group table dense={dense} capacity={cap} words={nw}")
     t0 = time.time()
@@ -721,7 +724,7 @@ def run_c1(env, args):
     from oracle import oracle as orc
     for name, quals in (("random_b", [(1, "<", 250_000)]), ("sorted_filter", [(3, "<", rows // 4)])):
         aggs = [cg.sum_(0), cg.count_star()]
-        partial, desc = make_partial(env, rels, quals, [], aggs, rows)
+        partial, desc = make_partial(env, rels, quals, [], aggs, rows, columns=cols)
         algo = []
         partial.reset()
         skipped = 0
@@ -761,7 +764,7 @@ def run_c1(env, args):
         out[name] = {"rows_per_s": rows / (ms / 1e3), "ms_per_step": ms, "frac": rf["frac"], "achieved_gbs": rf["achieved"],
                      "bytes_per_launch": avg, "avg_launch_ms": rf["avg_launch_ms"], "chunk_groups_skipped": int(tot[4]),
                      "bit_exact": ok, "clocks": clocks, "gpu_launches": launches,
-                     "cpu_arm": {"value": tot[2] / max(tot[3] / 1e6 / max(world, 1), 1e-9), "unit": "rows/s", "kind": "port",
+                     "cpu_arm": {"value": tot[2] / max(tot[3] / 1e6 / max(min(world, nsh), 1), 1e-9), "unit": "rows/s", "kind": "port",
                                  "cores": nthreads * min(world, nsh), "sample": f"all {rows} rows, one thread per shard"}}
         partial.free()
     for sh in shards.values():
@@ -807,7 +810,7 @@ def run_c5(env, args):
     attlen = [c[0] for c in LINEITEM]
     out = {}
     for name, q in tpch_queries(cg).items():
-        partial, desc = make_partial(env, rels, q["quals"], q["group"], q["aggs"], per * NSHARDS, expected_groups=16)
+        partial, desc = make_partial(env, rels, q["quals"], q["group"], q["aggs"], per * NSHARDS, expected_groups=16, columns=LINEITEM)
         algo = []
         partial.reset()
         for s in mine:
@@ -982,14 +985,39 @@ def run_ours(args, rank, world, local_rank):
         line = run_c2(env, args)
         extra = {}
         if not args.no_extra:
+            # The headline is measured; the extra legs must not be able to lose it.  Each leg runs under a deadline: if
+            # a rank is still inside the leg when it expires (a collective a peer never entered), rank 0 prints the line
+            # with what it has and every rank leaves.  After each leg the ranks agree (gloo) on whether it failed anywhere.
+            state = {"name": None, "timer": None}
+
+            def expire():
+                log(f"rank {rank}: leg {state['name']} passed its {args.leg_timeout}s deadline; giving up on the extra legs")
+                if rank == 0:
+                    extra[state["name"]] = {"error": f"deadline of {args.leg_timeout}s passed"}
+                    line["extra"] = extra
+                    emit(line)
+                os._exit(0)
+
             for name in ("c2null", "c1", "c5", "c4"):
                 t0 = time.time()
+                state["name"] = name
+                state["timer"] = threading.Timer(args.leg_timeout, expire)
+                state["timer"].daemon = True
+                state["timer"].start()
+                failed = 0
                 try:
                     leg = LEGS[name](env, args)
                 except Exception as e:          # noqa -- a leg must not take the headline down with it
                     import traceback
                     log(f"rank {rank}: leg {name} failed:\n{traceback.format_exc()}")
                     leg = {"error": repr(e)} if rank == 0 else None
+                    failed = 1
+                if world > 1:                   # a peer stuck in a collective never arrives here: the deadline ends the run
+                    t = env.torch.tensor([failed])
+                    env.dist.all_reduce(t)
+                    if int(t[0]) and not failed and rank == 0:
+                        leg = {"error": f"leg failed on {int(t[0])} rank(s)"}
+                state["timer"].cancel()
                 if rank == 0:
                     if name == "c2null" and leg and "error" not in leg:
                         leg = {k: leg[k] for k in ("value", "unit", "ms_per_step", "steps", "roofline", "clocks", "gpu_launches",
