@@ -609,6 +609,15 @@ def run_c2(env, args, nulls=False, headline=True):
     ms, clocks, all_launches, nscan, ktotal, last = env.timed(step, steps, warmup)
     ngroups = last[0] if last else 0
     value = total_rows / (ms / 1e3)
+    combine = None
+    if world > 1:
+        combine = {"data_path": "peer window: every rank's packed words mapped into every rank (CUDA IPC); rank s sums slice s over "
+                                "NVLink into the root's window; flag barriers in peer memory" if cgd.peer_window() else "ncclReduce"}
+        if headline and cgd.peer_window():          # the same step with NCCL carrying the combine, for the record
+            cg.set_option("peer_window", 0)
+            combine["ms_per_step_with_ncclReduce"] = env.timed(step, steps, warmup, profile=False)[0]
+            cg.set_option("peer_window", 1)
+            step()
     avg_bytes = float(np.mean(algo_bytes)) if algo_bytes else 0.0
     kernel = ("cg_jit_scan nullable form (exists bitmap + rank directory; fused decode+filter+partial aggregate)" if nulls else
               "cg_scan_fast_kernel<1,DENSE,1> (fused decode+filter+partial aggregate)")
@@ -699,6 +708,8 @@ def run_c2(env, args, nulls=False, headline=True):
             "hbm_gbs_whole_step": total_rows * C2_BYTES_PER_ROW / (ms / 1e3) / 1e9 / world,
             "packed_accumulators": not state["unpacked"],
         }
+        if combine is not None:
+            line["combine"] = combine
         if parity is not None:
             line["parity_full_size"] = parity
     for sh in shards.values():
@@ -881,11 +892,16 @@ def run_c4(env, args):
         joined, jsum = cg.join_count_sum(r0["cols"][0], r0["cols"][1], r0["nrows"], r1["cols"][0], r1["cols"][1], r1["nrows"])
         return joined, jsum, got_r, got_s
 
+    nccl_shuffle_ms = None
+    if world > 1 and cgd.peer_window():                  # the same shuffle with NCCL send/recv as the data path, for the record
+        cg.set_option("peer_window", 0)
+        nccl_shuffle_ms = env.timed(shuffle, args.leg_steps, 2, profile=False)[0]
+        cg.set_option("peer_window", 1)
     shuffle_ms, sclocks, slaunches, _, _, _ = env.timed(shuffle, args.leg_steps, 2, profile=False)     # the config's metric: the shuffle
     ms, clocks, launches, _, _, last = env.timed(step, max(args.leg_steps // 2, 2), 1, profile=False)  # shuffle + merge-side join
     joined, jsum, got_r, got_s = last
     r0, r1 = cgd.exchange_result(0, 2, timing=True), cgd.exchange_result(1, 2, timing=True)
-    ex_ms = env.max_over_ranks(max(r0["exchange_ms"], r1["exchange_ms"]))
+    ex_ms = env.max_over_ranks(r0["exchange_ms"] + r1["exchange_ms"])       # the two tables' exchanges run one after the other
     sent = env.sum_over_ranks([r0["sent_bytes"] + r1["sent_bytes"]])[0]
     # ---- checks: conservation, ownership, routing vs the oracle, the join vs an independent computation
     ok = True
@@ -948,6 +964,9 @@ def run_c4(env, args):
             "n_gpus": world, "rows_per_s": 2 * rows / (shuffle_ms / 1e3), "ms_per_step": shuffle_ms, "partitions": P,
             "step": "routing + scatter + all-to-all of both tables (the shuffle); the join is timed on top of it below",
             "shuffle_plus_join": {"rows_per_s": 2 * rows / (ms / 1e3), "ms_per_step": ms, "join_ms": ms - shuffle_ms},
+            "data_path": ("peer window: the scatter kernel stores rows into the owners' receive buffers over NVLink (CUDA IPC)"
+                          if world > 1 and cgd.peer_window() else "grouped ncclSend/ncclRecv" if world > 1 else "local"),
+            "ms_per_step_with_nccl_sendrecv": nccl_shuffle_ms,
             "exchange_ms": ex_ms, "nvlink_gbs": (sent / 1e9) / (ex_ms / 1e3) if world > 1 and ex_ms > 0 else None,
             "nvlink_bytes": int(sent), "nvlink_peak_note": "900 GB/s per direction and GPU (NVLink 5)",
             "hbm_gbs_map_side": hbm_bytes / 1e9 / (shuffle_ms / 1e3) / world,

@@ -159,6 +159,7 @@ SYMBOLS = [
     ("cg_comm_rank", C.c_int, [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     ("cg_comm_destroy", C.c_int, []),
     ("cg_comm_barrier", C.c_int, []),
+    ("cg_comm_peer_window", C.c_int, []),
     ("cg_comm_allreduce_i64", C.c_int, [_P, C.c_int32, C.c_int32]),
     ("cg_comm_combine", C.c_int, [_P, C.c_int32, C.c_int32]),
     ("cg_comm_repartition_exchange", C.c_int, [C.c_int32, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P,

@@ -15,6 +15,13 @@
  *                                 written) to the coordinator rank; row gather + merge kernel otherwise
  *   cg_comm_repartition_exchange  MAP_OUTPUT_FETCH: routing + scatter + one grouped ncclSend/ncclRecv of all
  *                                 columns, counts exchanged on the device side of a second stream
+ * Peer window (one node, NVLink): every rank owns one cudaMalloc'ed window that all other ranks map with CUDA IPC.
+ *   combine      the packed accumulator words are reduced by the ranks themselves: rank s sums slice s of all
+ *                windows with loads over NVLink and stores the total into the coordinator rank's window (a
+ *                reduce-scatter whose scatter target is one rank); two flag barriers in peer memory order it
+ *   repartition  the scatter kernel stores every row straight into the receive buffer of the rank that owns the
+ *                row's partition: routing, scatter and all-to-all are one pass, no send buffer, no second kernel
+ * NCCL stays underneath for bootstrap (handles, counts, agreements) and as the path when IPC mapping is refused.
  * libnccl is resolved at first use (dlopen): a process that already carries a copy (torch bundles one) keeps
  * using that one; a CPU-only process never loads it.
  */
@@ -71,10 +78,27 @@ static bool load_nccl()
 			return cg_set_error(CG_ECOMM, "%s failed: %s (%s:%d)", #call, g_nccl.GetErrorString(r__), __FILE__, __LINE__); \
 	} while (0)
 
+#define CG_WIN_FLAG_BYTES 4096                       /* uint64 flags[8 kinds][CG_MAX_RANKS], kinds: 0 reduce-in, 1 reduce-out, 2 + slot exchange */
+#define CG_WIN_WORDS ((size_t) 4 << 20)              /* 4 Mi packed words (32 MB) per direction */
+
+struct PeerFlags
+{
+	unsigned long long *peer[CG_MAX_RANKS];          /* flag page of every rank (own included) */
+	unsigned int *status;                            /* mapped host word: != 0 after a wait timed out */
+	int me, nranks;
+};
+
 struct CgComm
 {
 	bool ready = false;
 	int rank = 0, nranks = 1;
+	/* peer window */
+	bool win_ok = false;
+	int use_peer = 1;                   /* cg_set_option("peer_window", 0) keeps everything on NCCL */
+	uint8_t *win = nullptr;
+	uint8_t *win_peer[CG_MAX_RANKS] = {};
+	unsigned int *h_status = nullptr, *d_status = nullptr;
+	unsigned long long epoch[8] = {};
 	ncclComm_t comm = nullptr;
 	cudaStream_t side = nullptr;        /* agreements and the repartition exchange: never behind the scans */
 	int64_t *h_small = nullptr;         /* pinned */
@@ -87,6 +111,9 @@ struct CgComm
 	struct Slot
 	{
 		CgContext::DevBuf send, recv, index;
+		uint8_t *recv_peer[CG_MAX_RANKS] = {};   /* the receive buffers of all ranks, mapped here (peer window mode) */
+		bool recv_shared = false;
+		size_t recv_agreed = 0;                  /* bytes every rank's receive buffer has (the same everywhere) */
 		cudaEvent_t done = nullptr, t0 = nullptr, t1 = nullptr;
 		int64_t recv_rows = 0;
 		int32_t ncols = 0;
@@ -125,6 +152,205 @@ static int devbuf_grow(CgContext::DevBuf *b, size_t bytes)
 	return CG_OK;
 }
 
+
+static int comm_agree(int64_t *values, int n, ncclRedOp_t op);
+
+/* ---------------------------------------------------------------------------------- *
+ *  Peer window: CUDA IPC mappings of the other ranks' buffers, and barriers in them.
+ * ---------------------------------------------------------------------------------- */
+/* maps `mine` (the base of a cudaMalloc'ed allocation, or NULL when this rank has none) of every rank into this
+ * process.  Collective.  *ok is the same on every rank: false leaves nothing mapped. */
+static int comm_share(void *mine, uint8_t **peers, bool *ok)
+{
+	const int W = g_comm.nranks, me = g_comm.rank;
+	*ok = false;
+	for (int r = 0; r < CG_MAX_RANKS; r++) peers[r] = nullptr;
+	cudaIpcMemHandle_t h;
+	memset(&h, 0, sizeof h);
+	int64_t good = 1;
+	if (!mine || cudaIpcGetMemHandle(&h, mine) != cudaSuccess) { cudaGetLastError(); good = 0; }
+	static_assert(sizeof(cudaIpcMemHandle_t) % sizeof(int64_t) == 0, "handle size");
+	const size_t hw = sizeof(cudaIpcMemHandle_t) / sizeof(int64_t);
+	int rc = comm_ensure_small(hw * (size_t) (W + 1));
+	if (rc) return rc;
+	memcpy(g_comm.h_small + hw * W, &h, sizeof h);
+	CG_CUDA(cudaMemcpyAsync(g_comm.d_small + hw * W, g_comm.h_small + hw * W, sizeof h, cudaMemcpyHostToDevice, g_comm.side));
+	CG_NCCL(g_nccl.AllGather(g_comm.d_small + hw * W, g_comm.d_small, hw, ncclInt64, g_comm.comm, g_comm.side));
+	CG_CUDA(cudaMemcpyAsync(g_comm.h_small, g_comm.d_small, sizeof h * (size_t) W, cudaMemcpyDeviceToHost, g_comm.side));
+	CG_CUDA(cudaStreamSynchronize(g_comm.side));
+	std::vector<cudaIpcMemHandle_t> all(W);
+	memcpy(all.data(), g_comm.h_small, sizeof h * (size_t) W);
+	rc = comm_agree(&good, 1, ncclMin);
+	if (rc) return rc;
+	if (!good) return CG_OK;
+	for (int r = 0; r < W; r++)
+	{
+		if (r == me) { peers[r] = (uint8_t *) mine; continue; }
+		void *q = nullptr;
+		if (cudaIpcOpenMemHandle(&q, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); good = 0; break; }
+		peers[r] = (uint8_t *) q;
+	}
+	rc = comm_agree(&good, 1, ncclMin);
+	if (rc) return rc;
+	if (!good)
+	{
+		for (int r = 0; r < W; r++)
+		{
+			if (r != me && peers[r]) cudaIpcCloseMemHandle(peers[r]);
+			peers[r] = nullptr;
+		}
+		cudaGetLastError();
+		return CG_OK;
+	}
+	*ok = true;
+	return CG_OK;
+}
+
+static void comm_unshare(uint8_t **peers)
+{
+	for (int r = 0; r < CG_MAX_RANKS; r++)
+	{
+		if (r != g_comm.rank && peers[r]) cudaIpcCloseMemHandle(peers[r]);
+		peers[r] = nullptr;
+	}
+	cudaGetLastError();
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+	unsigned long long v;
+	asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+
+/* One warp.  Everything this rank's stream did before is visible to the ranks that see the flag; returns when every
+ * rank has arrived at `epoch` of barrier `kind`.  Epochs only grow.  A wait that lasts 4 s gives up and raises the
+ * status word: the host fails the next call instead of the GPU spinning for ever behind a rank that died. */
+__global__ void cg_peer_barrier_kernel(const PeerFlags F, int kind, unsigned long long epoch)
+{
+	const int t = threadIdx.x;
+	__threadfence_system();
+	if (t < F.nranks)
+	{
+		st_release_sys(F.peer[t] + kind * CG_MAX_RANKS + F.me, epoch);
+		const unsigned long long *flag = F.peer[F.me] + kind * CG_MAX_RANKS + t;
+		const unsigned long long t0 = global_timer_ns();
+		while (ld_acquire_sys(flag) < epoch)
+		{
+			if (global_timer_ns() - t0 > 4000000000ull)
+			{
+				*(volatile unsigned int *) F.status = 1u + (unsigned) kind;
+				break;
+			}
+		}
+	}
+	__threadfence_system();
+}
+
+__global__ void __launch_bounds__(256) cg_peer_copy_kernel(const unsigned long long *src, unsigned long long *dst, size_t words)
+{
+	const size_t stride = (size_t) gridDim.x * 256;
+	for (size_t i = (size_t) blockIdx.x * 256 + threadIdx.x; i < words; i += stride) dst[i] = src[i];
+}
+
+struct PeerReduce
+{
+	const unsigned long long *in[CG_MAX_RANKS];      /* the input windows of all ranks */
+	unsigned long long *out;                         /* the coordinator rank's output window */
+	size_t begin, end;                               /* this rank's slice (even bounds) */
+	int nranks;
+};
+
+/* slice [begin, end) of the sum over the ranks' windows -> the coordinator rank's output window.  The inputs are read
+ * with volatile loads: other GPUs wrote them, and the same addresses carry new values every combine. */
+__global__ void __launch_bounds__(256) cg_peer_reduce_kernel(const __grid_constant__ PeerReduce A)
+{
+	const size_t stride = (size_t) gridDim.x * 512;
+	for (size_t i = A.begin + 2 * ((size_t) blockIdx.x * 256 + threadIdx.x); i < A.end; i += stride)
+	{
+		unsigned long long a = 0, b = 0;
+#pragma unroll 4
+		for (int r = 0; r < A.nranks; r++)
+		{
+			unsigned long long x, y;
+			asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "l"(A.in[r] + i) : "memory");
+			a += x; b += y;
+		}
+		asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(A.out + i), "l"(a), "l"(b) : "memory");
+	}
+}
+
+static PeerFlags comm_flags()
+{
+	PeerFlags F;
+	memset(&F, 0, sizeof F);
+	for (int r = 0; r < g_comm.nranks; r++) F.peer[r] = (unsigned long long *) g_comm.win_peer[r];
+	F.status = g_comm.d_status; F.me = g_comm.rank; F.nranks = g_comm.nranks;
+	return F;
+}
+
+static int comm_peer_barrier(int kind, cudaStream_t stream)
+{
+	const unsigned long long e = ++g_comm.epoch[kind];
+	cg_peer_barrier_kernel<<<1, 32, 0, stream>>>(comm_flags(), kind, e);
+	CG_CUDA(cudaGetLastError()); g_cg_launches++;
+	return CG_OK;
+}
+
+static int comm_check_status()
+{
+	if (g_comm.h_status && *(volatile unsigned int *) g_comm.h_status)
+		return cg_set_error(CG_ECOMM, "a wait on another rank in the peer window timed out (barrier kind %u)", *g_comm.h_status - 1u);
+	return CG_OK;
+}
+
+static inline unsigned long long *win_in(int r) { return (unsigned long long *) (g_comm.win_peer[r] + CG_WIN_FLAG_BYTES); }
+static inline unsigned long long *win_out(int r) { return win_in(r) + CG_WIN_WORDS; }
+
+/* the window of this rank and its mappings everywhere: collective, at communicator start */
+static int comm_window_setup()
+{
+	g_comm.win_ok = false;
+	if (g_comm.nranks < 2 || g_comm.nranks > CG_MAX_RANKS) return CG_OK;
+	const char *e = getenv("CG_PEER_WINDOW");
+	int64_t want = (e && atoi(e) == 0) ? 0 : 1;
+	int rc = comm_agree(&want, 1, ncclMin);
+	if (rc) return rc;
+	if (!want) return CG_OK;
+	const size_t bytes = CG_WIN_FLAG_BYTES + 2 * CG_WIN_WORDS * sizeof(unsigned long long);
+	if (cudaMalloc((void **) &g_comm.win, bytes) != cudaSuccess) { cudaGetLastError(); g_comm.win = nullptr; }
+	if (g_comm.win)
+	{
+		CG_CUDA(cudaMemsetAsync(g_comm.win, 0, CG_WIN_FLAG_BYTES, g_comm.side));
+		CG_CUDA(cudaStreamSynchronize(g_comm.side));
+	}
+	if (!g_comm.h_status)
+	{
+		CG_CUDA(cudaHostAlloc((void **) &g_comm.h_status, sizeof(unsigned int), cudaHostAllocMapped));
+		*g_comm.h_status = 0;
+		CG_CUDA(cudaHostGetDevicePointer((void **) &g_comm.d_status, g_comm.h_status, 0));
+	}
+	rc = comm_share(g_comm.win, g_comm.win_peer, &g_comm.win_ok);
+	if (rc) return rc;
+	if (!g_comm.win_ok && g_comm.win) { cudaFree(g_comm.win); g_comm.win = nullptr; }
+	for (int k = 0; k < 8; k++) g_comm.epoch[k] = 0;
+	return CG_OK;
+}
+
+/* 1 = peer window in use, 0 = NCCL only */
+extern "C" int cg_comm_peer_window(void) { return g_comm.ready && g_comm.win_ok && g_comm.use_peer; }
+void cg_comm_set_peer_window(int on) { g_comm.use_peer = on ? 1 : 0; }
+
 extern "C" int cg_comm_unique_id(uint8_t *id)
 {
 	if (!id) return cg_set_error(CG_EINVAL, "NULL id");
@@ -158,6 +384,8 @@ extern "C" int cg_comm_init(const uint8_t *id, int32_t rank, int32_t nranks)
 		ncclUniqueId u;
 		memcpy(&u, id, sizeof u);
 		CG_NCCL(g_nccl.CommInitRank(&g_comm.comm, nranks, u, rank));
+		int rc = comm_window_setup();
+		if (rc) return rc;
 	}
 	g_comm.ready = true;
 	return CG_OK;
@@ -175,6 +403,16 @@ extern "C" int cg_comm_destroy(void)
 {
 	if (!g_comm.ready) return CG_OK;
 	cudaStreamSynchronize(g_comm.side);
+	if (CgContext *ctx = cg_ctx()) cudaStreamSynchronize(ctx->compute);
+	/* mappings of other ranks' memory go first; nobody frees what a peer may still have mapped */
+	for (CgComm::Slot &s : g_comm.slots)
+		if (s.recv_shared) { comm_unshare(s.recv_peer); s.recv_shared = false; }
+	if (g_comm.win_ok) comm_unshare(g_comm.win_peer);
+	if (g_comm.comm && g_comm.nranks > 1) { int64_t one = 1; comm_agree(&one, 1, ncclSum); }
+	if (g_comm.win) cudaFree(g_comm.win);
+	g_comm.win = nullptr; g_comm.win_ok = false;
+	if (g_comm.h_status) cudaFreeHost(g_comm.h_status);
+	g_comm.h_status = nullptr; g_comm.d_status = nullptr;
 	if (g_comm.comm) g_nccl.CommDestroy(g_comm.comm);
 	g_comm.comm = nullptr;
 	for (CgComm::Slot &s : g_comm.slots)
@@ -360,10 +598,13 @@ extern "C" int cg_comm_combine(CgPartial *p, int32_t root, int32_t local_status)
 	}
 
 	/* identical direct-indexed layouts with additive words: agree (off the scan stream) on what to reduce */
-	int64_t agree[4] = {local_status, p->wide_dirty ? 1 : 0, p->packed_dirty ? 1 : 0,
-						(int64_t) (p->entries * 1000003ull + (uint64_t) p->stride * 31ull + (uint64_t) p->pack_shift)};
+	int rc = comm_check_status();
+	if (rc) return rc;
+	int64_t agree[5] = {local_status, p->wide_dirty ? 1 : 0, p->packed_dirty ? 1 : 0,
+						(int64_t) (p->entries * 1000003ull + (uint64_t) p->stride * 31ull + (uint64_t) p->pack_shift),
+						(g_comm.win_ok && g_comm.use_peer) ? 0 : 1};
 	int64_t lay_min = agree[3];
-	int rc = comm_agree(agree, 4, ncclMax);
+	rc = comm_agree(agree, 5, ncclMax);
 	if (rc) return rc;
 	if (agree[0] != 0)
 	{
@@ -373,13 +614,50 @@ extern "C" int cg_comm_combine(CgPartial *p, int32_t root, int32_t local_status)
 	rc = comm_agree(&lay_min, 1, ncclMin);
 	if (rc) return rc;
 	if (lay_min != agree[3]) return cg_set_error(CG_EINVAL, "the partials of the ranks do not share one layout");
-	const bool any_wide = agree[1] != 0, any_packed = agree[2] != 0;
+	const bool any_wide = agree[1] != 0, any_packed = agree[2] != 0, peer = agree[4] == 0;
 	if (any_packed && !any_wide && p->d_packed)
 	{
 		/* every rank only wrote packed words: 8 bytes per group travel instead of the wide entry */
 		uint64_t *tail = p->d_packed + p->entries;
+		const size_t L = (size_t) p->entries + CG_COMM_TAIL;
 		cg_comm_tail_write_kernel<<<1, 32, 0, ctx->compute>>>(tail, p->d_stats, 1);
 		CG_CUDA(cudaGetLastError()); g_cg_launches++;
+		if (peer && L <= CG_WIN_WORDS)
+		{
+			/* the ranks reduce among themselves over NVLink: words -> own window; barrier; rank s sums slice s of all
+			 * windows into the coordinator's output window; barrier; the coordinator takes the total */
+			const int W = g_comm.nranks, me = g_comm.rank;
+			const unsigned copy_grid = (unsigned) std::min<size_t>((L + 255) / 256, 148 * 8);
+			cg_peer_copy_kernel<<<copy_grid, 256, 0, ctx->compute>>>((const unsigned long long *) p->d_packed, win_in(me), L);
+			CG_CUDA(cudaGetLastError()); g_cg_launches++;
+			rc = comm_peer_barrier(0, ctx->compute);
+			if (rc) return rc;
+			const size_t L2 = (L + 1) & ~(size_t) 1;
+			const size_t chunk = (((L2 + W - 1) / W) + 1) & ~(size_t) 1;
+			PeerReduce A;
+			memset(&A, 0, sizeof A);
+			for (int r = 0; r < W; r++) A.in[r] = win_in(r);
+			A.out = win_out(root);
+			A.begin = std::min(L2, (size_t) me * chunk); A.end = std::min(L2, A.begin + chunk);
+			A.nranks = W;
+			if (A.end > A.begin)
+			{
+				const unsigned grid = (unsigned) std::min<size_t>((A.end - A.begin + 511) / 512, 148 * 8);
+				cg_peer_reduce_kernel<<<grid, 256, 0, ctx->compute>>>(A);
+				CG_CUDA(cudaGetLastError()); g_cg_launches++;
+			}
+			rc = comm_peer_barrier(1, ctx->compute);
+			if (rc) return rc;
+			if (me == root)
+			{
+				cg_peer_copy_kernel<<<copy_grid, 256, 0, ctx->compute>>>(win_out(me), (unsigned long long *) p->d_packed, L);
+				CG_CUDA(cudaGetLastError()); g_cg_launches++;
+				cg_comm_tail_absorb_kernel<<<1, 32, 0, ctx->compute>>>(tail, p->d_stats, 1);
+				CG_CUDA(cudaGetLastError()); g_cg_launches++;
+				p->packed_dirty = true;
+			}
+			return CG_OK;
+		}
 		CG_NCCL(g_nccl.Reduce(p->d_packed, p->d_packed, (size_t) p->entries + CG_COMM_TAIL, ncclInt64, ncclSum, root, g_comm.comm, ctx->compute));
 		if (g_comm.rank == root)
 		{
@@ -440,6 +718,107 @@ extern "C" int cg_comm_exchange_plan(int32_t P, int32_t nranks, int32_t rank, co
 	return CG_OK;
 }
 
+
+/* ---- peer-window form of the exchange: the scatter stores into the owners' receive buffers ---- */
+struct PeerExchange
+{
+	CgComm::Slot *S;
+	int64_t *d_counts;
+	int32_t P, ncols, nlocal;
+	const int32_t *position;
+	int64_t total_recv;
+};
+
+static int peer_exchange_hook(void *arg, CgPeerScatter *out)
+{
+	PeerExchange *X = (PeerExchange *) arg;
+	CgComm::Slot &S = *X->S;
+	CgContext *ctx = cg_ctx();
+	const int W = g_comm.nranks, me = g_comm.rank, P = X->P;
+	int rc = comm_ensure_small((size_t) (P + 1) * (W + 1) + 8);
+	if (rc) return rc;
+	CG_CUDA(cudaStreamWaitEvent(g_comm.side, g_comm.ev_index, 0));
+	CG_NCCL(g_nccl.AllGather(X->d_counts, g_comm.d_small, (size_t) P + 1, ncclInt64, g_comm.comm, g_comm.side));
+	CG_CUDA(cudaMemcpyAsync(g_comm.h_small, g_comm.d_small, sizeof(int64_t) * (P + 1) * W, cudaMemcpyDeviceToHost, g_comm.side));
+	CG_CUDA(cudaStreamSynchronize(g_comm.side));
+	/* every rank now holds every rank's counts: all of them take the same decisions below without talking again.
+	 * Every rank has also passed its routing kernel, which its stream runs after whatever read this slot's previous
+	 * contents: the receive buffers may be overwritten. */
+	std::vector<int64_t> counts((size_t) W * P);
+	int64_t unroutable = 0;
+	for (int r = 0; r < W; r++)
+	{
+		memcpy(&counts[(size_t) r * P], g_comm.h_small + (size_t) r * (P + 1), sizeof(int64_t) * P);
+		unroutable += g_comm.h_small[(size_t) r * (P + 1) + P];
+	}
+	if (unroutable)
+		return cg_set_error(CG_EINVAL, "could not find shard for partition column value (%lld rows)", (long long) unroutable);
+	std::vector<int64_t> M((size_t) W * W, 0);                   /* M[r][d] rows rank r routes to rank d */
+	for (int r = 0; r < W; r++)
+		for (int p = 0; p < P; p++) M[(size_t) r * W + p % W] += counts[(size_t) r * P + p];
+	std::vector<int64_t> total(W, 0);
+	int64_t need_rows = 0;
+	for (int d = 0; d < W; d++)
+	{
+		for (int r = 0; r < W; r++) total[d] += M[(size_t) r * W + d];
+		need_rows = std::max(need_rows, total[d]);
+	}
+	const size_t need = (size_t) std::max<int64_t>(need_rows, 1) * sizeof(int64_t) * X->ncols;
+	if (!S.recv_shared || need > S.recv_agreed)
+	{
+		/* one size for all ranks: grow together, map again.  Rare: the first exchange of a slot, or a larger table. */
+		CG_CUDA(cudaStreamSynchronize(ctx->compute));
+		if (S.recv_shared) { comm_unshare(S.recv_peer); S.recv_shared = false; }
+		int64_t one = 1;
+		rc = comm_agree(&one, 1, ncclSum);                       /* nobody frees while a peer still has the old buffer mapped */
+		if (rc) return rc;
+		if (S.recv.p) CG_CUDA(cudaFree(S.recv.p));
+		S.recv = CgContext::DevBuf();
+		const size_t cap = need + need / 8 + 4096;
+		void *q = nullptr;
+		if (cudaMalloc(&q, cap) != cudaSuccess) { cudaGetLastError(); q = nullptr; }
+		bool ok = false;
+		rc = comm_share(q, S.recv_peer, &ok);
+		if (rc) return rc;
+		if (!ok)
+		{
+			if (q) cudaFree(q);
+			g_comm.win_ok = false;                                /* the next call takes the NCCL path */
+			return cg_set_error(q ? CG_ECOMM : CG_ENOMEM, "a receive buffer of %zu bytes could not be %s on every rank", cap, q ? "mapped" : "allocated");
+		}
+		S.recv.p = (uint8_t *) q; S.recv.cap = cap;
+		S.recv_shared = true; S.recv_agreed = cap;
+	}
+	std::vector<int64_t> send_rows(W), recv_rows(W);
+	S.part_counts.assign((size_t) std::max(X->nlocal, 1) * W, 0);
+	std::vector<int32_t> position(P);
+	int nlocal = 0;
+	cg_comm_exchange_plan(P, W, me, counts.data(), position.data(), send_rows.data(), recv_rows.data(), S.part_counts.data(), &nlocal);
+	X->total_recv = total[me];
+	S.recv_rows = total[me];
+	S.ncols = X->ncols;
+	S.sent_bytes = 0;
+	memset(out, 0, sizeof *out);
+	out->nranks = W;
+	int64_t soff = 0;
+	int pos = 0;
+	for (int d = 0; d < W; d++)
+	{
+		int64_t roff = 0;
+		for (int r = 0; r < me; r++) roff += M[(size_t) r * W + d];
+		out->base[d] = (int64_t *) S.recv_peer[d];
+		out->stride[d] = total[d];
+		out->adj[d] = roff - soff;
+		out->pos_begin[d] = pos;
+		for (int p = d; p < P; p += W) pos++;
+		soff += M[(size_t) me * W + d];
+		if (d != me) S.sent_bytes += (uint64_t) M[(size_t) me * W + d] * sizeof(int64_t) * X->ncols;
+	}
+	out->pos_begin[W] = pos;
+	CG_CUDA(cudaEventRecord(S.t0, ctx->compute));
+	return CG_OK;
+}
+
 extern "C" int cg_comm_repartition_exchange(int32_t slot, const int64_t *const *d_cols, const uint8_t *d_key_nulls, int64_t n,
 											int32_t ncols, int32_t key_len, int32_t P, const int32_t *mins, const int32_t *maxs,
 											int64_t *recv_rows_out)
@@ -465,6 +844,33 @@ extern "C" int cg_comm_repartition_exchange(int32_t slot, const int64_t *const *
 	std::vector<int32_t> position(P);
 	int nlocal = 0;
 	cg_comm_exchange_plan(P, W, me, nullptr, position.data(), nullptr, nullptr, nullptr, &nlocal);
+	rc = comm_check_status();
+	if (rc) return rc;
+	if (W > 1 && g_comm.win_ok && g_comm.use_peer)
+	{
+		/* routing + histogram; counts of all ranks (side stream, while the offset scan runs); then ONE kernel that is
+		 * both the scatter and the all-to-all: rows leave shared memory as runs into the owner's receive buffer */
+		PeerExchange X;
+		X.S = &S; X.d_counts = d_counts; X.P = P; X.ncols = ncols; X.nlocal = nlocal; X.position = position.data(); X.total_recv = 0;
+		CgScatterHook hook = {peer_exchange_hook, &X};
+		rc = cg_partition_route_scatter_async(d_cols[0], d_key_nulls, n, key_len, 1, mins, maxs, P, position.data(), d_cols, ncols, nullptr,
+											  d_counts, g_comm.ev_index, &hook);
+		if (rc) return rc;
+		rc = comm_peer_barrier(2 + slot, ctx->compute);          /* every rank's rows have landed everywhere */
+		if (rc) return rc;
+		CG_CUDA(cudaEventRecord(S.t1, ctx->compute));
+		CG_CUDA(cudaEventRecord(S.done, ctx->compute));
+		if (recv_rows_out) *recv_rows_out = X.total_recv;
+		return CG_OK;
+	}
+	if (S.recv_shared)
+	{
+		/* the slot was used in peer-window mode before: its buffer goes back to being private */
+		comm_unshare(S.recv_peer); S.recv_shared = false; S.recv_agreed = 0;
+		int64_t one = 1;
+		rc = comm_agree(&one, 1, ncclSum);
+		if (rc) return rc;
+	}
 	/* one rank: the scatter's output IS the received table (no exchange); else it is the send buffer */
 	rc = devbuf_grow(W == 1 ? &S.recv : &S.send, (size_t) std::max<int64_t>(n, 1) * sizeof(int64_t) * ncols);
 	if (rc) return rc;

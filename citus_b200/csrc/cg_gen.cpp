@@ -363,7 +363,12 @@ static int write_relation(const Source &src, const CgColumnDesc *cols, int natts
 	}
 	g->nblocks = std::max<uint64_t>(2, (reserved + CG_BYTES_PER_PAGE - 1) / CG_BYTES_PER_PAGE);
 	g->pages = (uint8_t *) aligned_alloc(4096, g->nblocks * CG_BLCKSZ);
-	if (!g->pages) { delete g; return cg_set_error(CG_ENOMEM, "cannot allocate %llu pages", (unsigned long long) g->nblocks); }
+	if (!g->pages)
+	{
+		const unsigned long long nblocks = g->nblocks;
+		delete g;
+		return cg_set_error(CG_ENOMEM, "cannot allocate %llu pages", nblocks);
+	}
 
 	/* metapage + empty block (columnar_storage.c:57-89) */
 	memset(g->pages, 0, 2 * CG_BLCKSZ);

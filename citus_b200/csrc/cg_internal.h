@@ -407,10 +407,33 @@ int cg_partition_index_async(const int64_t *d_keys, const uint8_t *d_nulls, int6
 int cg_partition_scatter_async(const int32_t *d_index, int64_t n, int32_t P, const int32_t *h_order, const int64_t *const *d_cols,
 							   int32_t ncols, int64_t *const *d_out);
 
+/* Scatter straight into the receive buffers of other ranks (peer-mapped memory).  Output positions are
+ * destination-major: positions [pos_begin[d], pos_begin[d + 1]) belong to rank d, whose buffer holds column c at
+ * base[d] + c * stride[d]; a row the local scatter would place at index i of the send order lands at adj[d] + i. */
+#define CG_MAX_RANKS 16
+struct CgPeerScatter
+{
+	int64_t *base[CG_MAX_RANKS];
+	int64_t stride[CG_MAX_RANKS];
+	int64_t adj[CG_MAX_RANKS];
+	int32_t pos_begin[CG_MAX_RANKS + 1];
+	int32_t nranks;
+};
+/* called after routing, the histogram and the offset scan are enqueued and before the scatter is launched: the
+ * caller exchanges the counts and says where the rows go */
+struct CgScatterHook
+{
+	int (*fn)(void *arg, CgPeerScatter *out);
+	void *arg;
+};
+
 int cg_partition_route_scatter_async(const int64_t *d_keys, const uint8_t *d_nulls, int64_t n, int32_t key_len, int32_t by_hash,
 									 const int32_t *mins, const int32_t *maxs, int32_t P, const int32_t *h_order,
 									 const int64_t *const *d_cols, int32_t ncols, int64_t *const *d_out, int64_t *d_counts,
-									 cudaEvent_t after_counts);
+									 cudaEvent_t after_counts, const CgScatterHook *peer_hook = nullptr);
+
+/* cg_comm.cu */
+void cg_comm_set_peer_window(int on);
 
 /* cg_plan.cpp */
 int cg_partial_shape(CgPartial *p, const CgScanDesc *desc, const CgColumnDesc *columns, int32_t natts,

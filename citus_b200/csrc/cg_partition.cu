@@ -313,9 +313,9 @@ cg_route_hist_kernel(const RouteParams R, int64_t n, int P, const int32_t *order
 	}
 }
 
-template <typename IndexT>
+template <typename IndexT, bool PEER>
 __global__ void __launch_bounds__(CGP_THREADS, 4)     /* <= 64 registers: four CTAs per SM (the first build used 80 -> three) */
-cg_scatter_staged_kernel(const __grid_constant__ StagedScatterParams A)
+cg_scatter_staged_kernel(const __grid_constant__ StagedScatterParams A, const __grid_constant__ CgPeerScatter B)
 {
 	constexpr int WARPS = CGP_THREADS / 32;
 	constexpr int SEG = CGP_ROWS_PER_BLOCK / WARPS;
@@ -325,6 +325,7 @@ cg_scatter_staged_kernel(const __grid_constant__ StagedScatterParams A)
 	unsigned long long *s_gbase = s_stage + CGP_ROWS_PER_BLOCK;                 /* [P] global position of the block's first row of p, minus its local start */
 	unsigned int *s_cnt = (unsigned int *) (s_gbase + A.P);                     /* [WARPS][P] per-warp counts, then running local offsets */
 	uint16_t *s_part = (uint16_t *) (s_cnt + WARPS * A.P);                      /* [4096] partition of every local position */
+	unsigned long long *s_optr = (unsigned long long *) (s_part + CGP_ROWS_PER_BLOCK);   /* PEER: [P] address of output index 0 of p, this column */
 	const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	unsigned int *mine = s_cnt + warp * A.P;
 	for (int p = threadIdx.x; p < WARPS * A.P; p += CGP_THREADS) s_cnt[p] = 0;
@@ -409,16 +410,35 @@ cg_scatter_staged_kernel(const __grid_constant__ StagedScatterParams A)
 #pragma unroll
 		for (int st = 0; st < STEPS; st++)
 			if (idx[st] >= 0) s_stage[lpos[st]] = (unsigned long long) A.cols[c][seg0 + st * 32 + lane];
+		if (PEER)
+		{
+			/* the rank that owns position p, and where this block's rows of p start in that rank's receive buffer */
+			for (int p = threadIdx.x; p < A.P; p += CGP_THREADS)
+			{
+				int d = 0;
+				while (d + 1 < B.nranks && p >= B.pos_begin[d + 1]) d++;
+				s_optr[p] = (unsigned long long) B.base[d] +
+							8ull * ((unsigned long long) ((long long) c * B.stride[d] + B.adj[d]) + s_gbase[p]);
+			}
+		}
 		__syncthreads();
-		for (unsigned int j = threadIdx.x; j < block_rows; j += CGP_THREADS)
-			A.out[c][s_gbase[s_part[j]] + j] = (int64_t) s_stage[j];
+		if (PEER)
+		{
+			for (unsigned int j = threadIdx.x; j < block_rows; j += CGP_THREADS)
+				((int64_t *) s_optr[s_part[j]])[j] = (int64_t) s_stage[j];          /* runs of one partition: coalesced stores over NVLink */
+		}
+		else
+		{
+			for (unsigned int j = threadIdx.x; j < block_rows; j += CGP_THREADS)
+				A.out[c][s_gbase[s_part[j]] + j] = (int64_t) s_stage[j];
+		}
 	}
 }
 
-static size_t staged_scatter_smem(int P)
+static size_t staged_scatter_smem(int P, bool peer = false)
 {
 	return sizeof(unsigned long long) * (CGP_ROWS_PER_BLOCK + (size_t) P) + sizeof(unsigned int) * ((CGP_THREADS / 32) * (size_t) P) +
-		   sizeof(uint16_t) * CGP_ROWS_PER_BLOCK + 16;
+		   sizeof(uint16_t) * CGP_ROWS_PER_BLOCK + (peer ? sizeof(unsigned long long) * (size_t) P : 0) + 16;
 }
 
 /* are [mins, maxs] the uniform hash intervals of width floor(2^32 / P), the last one widened to INT32_MAX? */
@@ -695,10 +715,11 @@ static int partition_scatter_enqueue(CgContext *ctx, const int32_t *d_index, int
 		static bool smem_configured = false;
 		if (!smem_configured)
 		{
-			CG_CUDA(cudaFuncSetAttribute(cg_scatter_staged_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) staged_scatter_smem(CGP_MAX_P)));
+			CG_CUDA(cudaFuncSetAttribute(cg_scatter_staged_kernel<int32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) staged_scatter_smem(CGP_MAX_P)));
 			smem_configured = true;
 		}
-		cg_scatter_staged_kernel<int32_t><<<(unsigned) nblocks, CGP_THREADS, staged_scatter_smem(P), ctx->compute>>>(S);
+		static const CgPeerScatter no_peer = {};
+		cg_scatter_staged_kernel<int32_t, false><<<(unsigned) nblocks, CGP_THREADS, staged_scatter_smem(P), ctx->compute>>>(S, no_peer);
 		CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	}
 	if (h_offsets)
@@ -725,7 +746,7 @@ int cg_partition_scatter_async(const int32_t *d_index, int64_t n, int32_t P, con
 int cg_partition_route_scatter_async(const int64_t *d_keys, const uint8_t *d_nulls, int64_t n, int32_t key_len, int32_t by_hash,
 									 const int32_t *mins, const int32_t *maxs, int32_t P, const int32_t *h_order,
 									 const int64_t *const *d_cols, int32_t ncols, int64_t *const *d_out, int64_t *d_counts,
-									 cudaEvent_t after_counts)
+									 cudaEvent_t after_counts, const CgScatterHook *peer_hook)
 {
 	CgContext *ctx = cg_ctx();
 	if (!ctx) return CG_EINVAL;
@@ -782,15 +803,34 @@ int cg_partition_route_scatter_async(const int64_t *d_keys, const uint8_t *d_nul
 		StagedScatterParams S;
 		memset(&S, 0, sizeof S);
 		S.index = d_idx16; S.n = n; S.P = P; S.ncols = ncols; S.block_offsets = d_block; S.part_base = d_base; S.order = nullptr;
-		for (int c = 0; c < ncols; c++) { S.cols[c] = d_cols[c]; S.out[c] = d_out[c]; }
+		for (int c = 0; c < ncols; c++) { S.cols[c] = d_cols[c]; S.out[c] = d_out ? d_out[c] : nullptr; }
 		static bool smem_configured = false;
 		if (!smem_configured)
 		{
-			CG_CUDA(cudaFuncSetAttribute(cg_scatter_staged_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) staged_scatter_smem(CGP_MAX_P)));
+			CG_CUDA(cudaFuncSetAttribute(cg_scatter_staged_kernel<uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) staged_scatter_smem(CGP_MAX_P)));
+			CG_CUDA(cudaFuncSetAttribute(cg_scatter_staged_kernel<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) staged_scatter_smem(CGP_MAX_P, true)));
 			smem_configured = true;
 		}
-		cg_scatter_staged_kernel<uint16_t><<<(unsigned) nblocks, CGP_THREADS, staged_scatter_smem(P), ctx->compute>>>(S);
+		if (peer_hook)
+		{
+			CgPeerScatter B;
+			memset(&B, 0, sizeof B);
+			int hrc = peer_hook->fn(peer_hook->arg, &B);     /* the host learns every rank's counts here; the kernels above keep running */
+			if (hrc) return hrc;
+			cg_scatter_staged_kernel<uint16_t, true><<<(unsigned) nblocks, CGP_THREADS, staged_scatter_smem(P, true), ctx->compute>>>(S, B);
+		}
+		else
+		{
+			static const CgPeerScatter no_peer = {};
+			cg_scatter_staged_kernel<uint16_t, false><<<(unsigned) nblocks, CGP_THREADS, staged_scatter_smem(P), ctx->compute>>>(S, no_peer);
+		}
 		CG_CUDA(cudaGetLastError()); g_cg_launches++;
+	}
+	else if (peer_hook)
+	{
+		CgPeerScatter B;
+		int hrc = peer_hook->fn(peer_hook->arg, &B);         /* no local rows: the counts are still exchanged (a collective) */
+		if (hrc) return hrc;
 	}
 	return CG_OK;
 }

@@ -60,6 +60,12 @@ def barrier():
     check(lib().cg_comm_barrier())
 
 
+def peer_window() -> bool:
+    """True when the combine and the repartition exchange run through the IPC-mapped peer window (NVLink loads and
+    stores by the library's kernels); False when NCCL carries the data"""
+    return bool(lib().cg_comm_peer_window())
+
+
 def allreduce(values, op="max"):
     """host-side agreement over ranks: list of python ints -> list of python ints"""
     a = np.asarray(values, np.int64).copy()

@@ -395,7 +395,10 @@ int cg_join_count_sum(const int64_t *d_build_keys, const uint8_t *d_build_nulls,
 					  uint64_t *sum_lo);
 
 /* ---------------------------------------------------------------------------------- *
- *  Exchange steps across GPUs (one process per GPU; NCCL over NVLink / NVSwitch on the library's streams).
+ *  Exchange steps across GPUs (one process per GPU on one node; NVLink / NVSwitch, on the library's streams).
+ *  Data moves through a peer window -- every rank's buffers mapped into every other rank with CUDA IPC, written
+ *  and read by the library's own kernels -- with NCCL underneath for bootstrap, counts and agreements, and as the
+ *  data path when the mapping is refused or switched off (cg_set_option("peer_window", 0) on every rank).
  *  Replaces the libpq funnel of the adaptive executor for GPU-resident results
  *  (executor/adaptive_executor.c:3964-4189 ReceiveResults + the combine query's HashAggregate,
  *  planner/multi_logical_optimizer.c:1807-1885, 2231-2275) and the file exchange of a repartition
@@ -408,20 +411,24 @@ int cg_comm_init(const uint8_t *id, int32_t rank, int32_t nranks);    /* collect
 int cg_comm_rank(int32_t *rank, int32_t *nranks);
 int cg_comm_destroy(void);
 int cg_comm_barrier(void);
+int cg_comm_peer_window(void);               /* 1: the peer window carries the combine and the exchange; 0: NCCL does */
 enum { CG_COMM_SUM = 0, CG_COMM_MIN = 1, CG_COMM_MAX = 2 };
 /* small host-side agreement (plan constants such as the key range; timings): values[i] <- op over ranks */
 int cg_comm_allreduce_i64(int64_t *values, int32_t n, int32_t op);
 /* Coordinator-side combine: after the call the partial of rank `root` holds the combined aggregate.  Collective:
  * EVERY rank calls it, passing the status of its own scans in local_status -- a rank that failed still takes
  * part, and every rank then returns an error instead of some of them hanging in a collective.  Direct-indexed
- * tables with additive words are reduced in place (the packed words alone when nothing else was written);
+ * tables with additive words are reduced in place (the packed words alone when nothing else was written -- then by
+ * the ranks themselves: rank s sums slice s of every rank's words over NVLink into the root's window);
  * other tables send their compacted rows to the root, which merges them.  Asynchronous on the library's
  * stream: errors raised by kernels of any rank surface on the root at the next call that reads the partial. */
 int cg_comm_combine(CgPartial *p, int32_t root, int32_t local_status);
 /* Hash repartition of this rank's rows (column 0 = the key) into P partitions, partition p owned by rank
- * p mod nranks: routing (cg_partition_index), scatter into destination-major order and ONE grouped
- * ncclSend/ncclRecv of all columns on a second stream, so that the next table's routing and scatter overlap
- * this table's exchange.  Results live in the slot (0..3) until its next use. */
+ * p mod nranks.  Peer window: routing + histogram, the counts of all ranks, then ONE kernel that is scatter and
+ * all-to-all at once -- rows leave shared memory as runs straight into the owner's receive buffer.  NCCL path:
+ * scatter into destination-major order and one grouped ncclSend/ncclRecv of all columns on a second stream, so
+ * that the next table's routing and scatter overlap this table's exchange.  Results live in the slot (0..3)
+ * until its next use. */
 int cg_comm_repartition_exchange(int32_t slot, const int64_t *const *d_cols, const uint8_t *d_key_nulls, int64_t n,
 								 int32_t ncols, int32_t key_len, int32_t P, const int32_t *mins, const int32_t *maxs,
 								 int64_t *recv_rows);

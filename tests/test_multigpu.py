@@ -1,6 +1,7 @@
-"""Two-GPU tests of the exchange steps behind the C-ABI (cg_comm_*: NCCL inside libcitus_gpu.so): the combine in
-its three forms (packed words, wide table, row gather + merge), error agreement (a failed rank fails every rank
-instead of hanging the others), and the repartition exchange + merge-side join -- all bit-exact against the oracle.
+"""Two-GPU tests of the exchange steps behind the C-ABI (cg_comm_* inside libcitus_gpu.so): the combine in its three
+forms (packed words, wide table, row gather + merge), error agreement (a failed rank fails every rank instead of
+hanging the others), and the repartition exchange + merge-side join -- all bit-exact against the oracle, once through
+the IPC-mapped peer window (the library's own kernels load and store over NVLink) and once with NCCL as the data path.
 Needs >= 2 GPUs: skipped on the single-GPU box (run with `gpurun --gpus 2 -- python -m pytest tests/test_multigpu.py -m gpu`)."""
 import os
 import socket
@@ -79,66 +80,84 @@ def _worker(rank, world, port, out):
                 _groups_equal(got, w, len(aggs))
             cgd.barrier()
 
-        c2 = [(8, 0, 0, 3000, 0), (8, 0, 0, 100, 0), (8, 0, -10**9, 10**9, 0)]
-        c2n = [(8, 0, 0, 3000, 20000), (8, 0, 0, 100, 0), (8, 0, -10**9, 10**9, 50000)]
-        oa = [orc.sum_(2), orc.count_star()]
-        run(c2, [(1, "<", 50)], [0], lambda: [cg.sum_(2), cg.count_star()], oa)                    # packed words only
-        run(c2n, [(1, "<", 50)], [0], lambda: [cg.sum_(2), cg.count_star()], oa)                   # NULLs: wide table reduce
-        run(c2n, [(1, "<", 50)], [0], lambda: [cg.sum_(2), cg.count_star()], oa, force_hash=True)  # hash: row gather + merge
-        run(c2, [(1, "<", 50)], [], lambda: [cg.sum_(2), cg.count_star()], oa)                     # plain aggregate
+        for mode in (1, 0, 1):                       # peer window, NCCL, and back (the slots' buffers change hands)
+          cg.set_option("peer_window", mode)
+          if mode:
+              assert cgd.peer_window(), "CUDA IPC mapping of the peer window was refused on this box"
+          else:
+              assert not cgd.peer_window()
+          c2 = [(8, 0, 0, 3000, 0), (8, 0, 0, 100, 0), (8, 0, -10**9, 10**9, 0)]
+          c2n = [(8, 0, 0, 3000, 20000), (8, 0, 0, 100, 0), (8, 0, -10**9, 10**9, 50000)]
+          oa = [orc.sum_(2), orc.count_star()]
+          run(c2, [(1, "<", 50)], [0], lambda: [cg.sum_(2), cg.count_star()], oa)                    # packed words only
+          run(c2n, [(1, "<", 50)], [0], lambda: [cg.sum_(2), cg.count_star()], oa)                   # NULLs: wide table reduce
+          run(c2n, [(1, "<", 50)], [0], lambda: [cg.sum_(2), cg.count_star()], oa, force_hash=True)  # hash: row gather + merge
+          run(c2, [(1, "<", 50)], [], lambda: [cg.sum_(2), cg.count_star()], oa)                     # plain aggregate
 
-        # error agreement: rank 1 reports a failed scan; EVERY rank gets an error, nobody hangs
-        d = cg.make_desc([(1, "<", 50)], [0], [cg.sum_(2), cg.count_star()])
-        agg = cg.GpuColumnarAgg(d, [(8, 0)] * 3, 0, 2999, 1000)
-        try:
-            cgd.combine_partials(agg, dst=0, local_status=capi.CG_ECORRUPT if rank == 1 else 0)
-            raise AssertionError("combine succeeded although a rank failed")
-        except capi.CitusGpuError as e:
-            assert e.code == capi.CG_ECORRUPT
-        cgd.barrier()
+          # error agreement: rank 1 reports a failed scan; EVERY rank gets an error, nobody hangs
+          d = cg.make_desc([(1, "<", 50)], [0], [cg.sum_(2), cg.count_star()])
+          agg = cg.GpuColumnarAgg(d, [(8, 0)] * 3, 0, 2999, 1000)
+          try:
+              cgd.combine_partials(agg, dst=0, local_status=capi.CG_ECORRUPT if rank == 1 else 0)
+              raise AssertionError("combine succeeded although a rank failed")
+          except capi.CitusGpuError as e:
+              assert e.code == capi.CG_ECORRUPT
+          cgd.barrier()
 
-        # repartition exchange + merge-side join against the oracle
-        g = torch.Generator(device="cuda")
-        P, n = 8, 200_000
-        tabs = {}
-        for name, seed in (("r", 1), ("s", 2)):
-            g.manual_seed(seed * 100 + rank)
-            k = torch.randint(0, 40_000, (n,), dtype=torch.int64, device="cuda", generator=g)
-            v = torch.randint(-(1 << 40), 1 << 40, (n,), dtype=torch.int64, device="cuda", generator=g)
-            tabs[name] = (k, v)
-        cgd.repartition_exchange(0, [tabs["r"][0].data_ptr(), tabs["r"][1].data_ptr()], n, P)
-        cgd.repartition_exchange(1, [tabs["s"][0].data_ptr(), tabs["s"][1].data_ptr()], n, P)
-        cgd.exchange_wait(0)
-        cgd.exchange_wait(1)
-        r0, r1 = cgd.exchange_result(0, 2, timing=True), cgd.exchange_result(1, 2, timing=True)
-        joined, jsum = cg.join_count_sum(r0["cols"][0], r0["cols"][1], r0["nrows"], r1["cols"][0], r1["cols"][1], r1["nrows"])
-        # every rank's input, gathered on the host, through the oracle's routing and row-at-a-time join
-        allk = {}
-        for name in ("r", "s"):
-            ks = [torch.zeros(n, dtype=torch.int64) for _ in range(world)]
-            vs = [torch.zeros(n, dtype=torch.int64) for _ in range(world)]
-            dist.all_gather(ks, tabs[name][0].cpu())
-            dist.all_gather(vs, tabs[name][1].cpu())
-            allk[name] = (torch.cat(ks).numpy(), torch.cat(vs).numpy())
-        mins, maxs = cgd.synthetic_intervals(P)
-        wi_r, _ = orc.partition_rows(allk["r"][0], None, 8, "h", mins, maxs)
-        wi_s, _ = orc.partition_rows(allk["s"][0], None, 8, "h", mins, maxs)
-        sel_r, sel_s = (wi_r % world) == rank, (wi_s % world) == rank
-        assert r0["nrows"] == int(sel_r.sum()) and r1["nrows"] == int(sel_s.sum())
-        # per local partition, rows by source rank
-        mine_parts = [p for p in range(P) if p % world == rank]
-        for i, p in enumerate(mine_parts):
-            for src in range(world):
-                assert r0["part_counts"][i, src] == int(((wi_r == p) & (np.arange(world * n) // n == src)).sum())
-        wj, ws = orc.join_count_sum(allk["r"][0][sel_r], allk["r"][1][sel_r], allk["s"][0][sel_s], allk["s"][1][sel_s])
-        assert (joined, jsum) == (wj, ws), (joined, wj)
-        # the received rows are exactly the oracle's rows of this rank's partitions (as multisets)
-        rk = torch.as_tensor(np.sort(allk["r"][0][sel_r]))
-        class V:
-            def __init__(s, p, n):
-                s.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (p, False), "version": 2}
-        got_k = torch.as_tensor(V(r0["cols"][0], r0["nrows"]), device="cuda").cpu().sort().values
-        assert torch.equal(got_k, rk)
+          # repartition exchange + merge-side join against the oracle
+          g = torch.Generator(device="cuda")
+          P, n = 8, 200_000
+          tabs = {}
+          for name, seed in (("r", 1), ("s", 2)):
+              g.manual_seed(seed * 100 + rank)
+              k = torch.randint(0, 40_000, (n,), dtype=torch.int64, device="cuda", generator=g)
+              v = torch.randint(-(1 << 40), 1 << 40, (n,), dtype=torch.int64, device="cuda", generator=g)
+              tabs[name] = (k, v)
+          cgd.repartition_exchange(0, [tabs["r"][0].data_ptr(), tabs["r"][1].data_ptr()], n, P)
+          cgd.repartition_exchange(1, [tabs["s"][0].data_ptr(), tabs["s"][1].data_ptr()], n, P)
+          cgd.exchange_wait(0)
+          cgd.exchange_wait(1)
+          r0, r1 = cgd.exchange_result(0, 2, timing=True), cgd.exchange_result(1, 2, timing=True)
+          joined, jsum = cg.join_count_sum(r0["cols"][0], r0["cols"][1], r0["nrows"], r1["cols"][0], r1["cols"][1], r1["nrows"])
+          # every rank's input, gathered on the host, through the oracle's routing and row-at-a-time join
+          allk = {}
+          for name in ("r", "s"):
+              ks = [torch.zeros(n, dtype=torch.int64) for _ in range(world)]
+              vs = [torch.zeros(n, dtype=torch.int64) for _ in range(world)]
+              dist.all_gather(ks, tabs[name][0].cpu())
+              dist.all_gather(vs, tabs[name][1].cpu())
+              allk[name] = (torch.cat(ks).numpy(), torch.cat(vs).numpy())
+          mins, maxs = cgd.synthetic_intervals(P)
+          wi_r, _ = orc.partition_rows(allk["r"][0], None, 8, "h", mins, maxs)
+          wi_s, _ = orc.partition_rows(allk["s"][0], None, 8, "h", mins, maxs)
+          sel_r, sel_s = (wi_r % world) == rank, (wi_s % world) == rank
+          assert r0["nrows"] == int(sel_r.sum()) and r1["nrows"] == int(sel_s.sum())
+          # per local partition, rows by source rank
+          mine_parts = [p for p in range(P) if p % world == rank]
+          for i, p in enumerate(mine_parts):
+              for src in range(world):
+                  assert r0["part_counts"][i, src] == int(((wi_r == p) & (np.arange(world * n) // n == src)).sum())
+          wj, ws = orc.join_count_sum(allk["r"][0][sel_r], allk["r"][1][sel_r], allk["s"][0][sel_s], allk["s"][1][sel_s])
+          assert (joined, jsum) == (wj, ws), (joined, wj)
+          # the received rows are exactly the oracle's rows of this rank's partitions (as multisets)
+          rk = torch.as_tensor(np.sort(allk["r"][0][sel_r]))
+          class V:
+              def __init__(s, p, n):
+                  s.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (p, False), "version": 2}
+          got_k = torch.as_tensor(V(r0["cols"][0], r0["nrows"]), device="cuda").cpu()
+          got_v = torch.as_tensor(V(r0["cols"][1], r0["nrows"]), device="cuda").cpu()
+          assert torch.equal(got_k.sort().values, rk)
+          want_pairs = np.sort(allk["r"][0][sel_r] * 1000003 ^ allk["r"][1][sel_r])       # key and payload stay together
+          assert np.array_equal(np.sort(got_k.numpy() * 1000003 ^ got_v.numpy()), want_pairs)
+          # rows of one local partition from one source rank are contiguous, in (source rank, partition) order
+          gi, _ = orc.partition_rows(got_k.numpy(), None, 8, "h", mins, maxs)
+          off = 0
+          for src in range(world):
+              for i, p in enumerate(mine_parts):
+                  c = int(r0["part_counts"][i, src])
+                  assert (gi[off:off + c] == p).all(), (src, p)
+                  off += c
+          assert off == r0["nrows"]
         cgd.destroy()
         out.put((rank, "ok"))
     except Exception:          # noqa
