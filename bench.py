@@ -606,18 +606,50 @@ def run_c2(env, args, nulls=False, headline=True):
     checked_step()
 
     steps, warmup = (args.steps, args.warmup) if headline else (args.leg_steps, 3)
+    combine = None
+    if world > 1:
+        # which data path carries the combine is decided by measurement: a few steps each way, every rank sees the same
+        # max-over-ranks times and therefore picks the same one
+        combine = {}
+        if cgd.peer_window():
+            calib = {}
+            for mode in (1, 0):
+                cg.set_option("peer_window", mode)
+                calib[mode] = env.timed(step, max(5, steps // 2), 3, profile=False)[0]
+            best = 1 if calib[1] <= calib[0] else 0
+            cg.set_option("peer_window", best)
+            step()
+            combine["calibration_ms_per_step"] = {"peer_window": calib[1], "ncclReduce": calib[0]}
+        combine["data_path"] = ("peer window: every rank's packed words mapped into every rank (CUDA IPC); rank s sums slice s over "
+                                "NVLink into the root's window; flag barriers in peer memory") if cgd.peer_window() else "ncclReduce"
     ms, clocks, all_launches, nscan, ktotal, last = env.timed(step, steps, warmup)
     ngroups = last[0] if last else 0
     value = total_rows / (ms / 1e3)
-    combine = None
-    if world > 1:
-        combine = {"data_path": "peer window: every rank's packed words mapped into every rank (CUDA IPC); rank s sums slice s over "
-                                "NVLink into the root's window; flag barriers in peer memory" if cgd.peer_window() else "ncclReduce"}
-        if headline and cgd.peer_window():          # the same step with NCCL carrying the combine, for the record
-            cg.set_option("peer_window", 0)
-            combine["ms_per_step_with_ncclReduce"] = env.timed(step, steps, warmup, profile=False)[0]
-            cg.set_option("peer_window", 1)
-            step()
+    if world > 1 and headline:
+        # where a step's time goes on this rank (events between the phases; outside the timed loop)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        acc = np.zeros(3)
+        reps = 10
+        for _ in range(reps):
+            env.barrier()
+            ev[0].record()
+            partial.reset()
+            for s in my_shards:
+                partial.scan_shard(shards[s], want_stats=False)
+            ev[1].record()
+            cgd.combine_partials(partial, dst=0, local_status=0)
+            ev[2].record()
+            if rank == 0:
+                partial.export_device(out_keys.data_ptr(), out_nulls.data_ptr(), out_words.data_ptr(), NKEYS + 2)
+            ev[3].record()
+            torch.cuda.synchronize()
+            acc += [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
+        acc /= reps
+        scan_max = env.max_over_ranks(float(acc[0]))
+        combine["phases_ms_rank0"] = {"reset_and_scans": float(acc[0]), "combine_incl_wait_for_slowest_rank": float(acc[1]),
+                                      "export_on_root": float(acc[2]), "reset_and_scans_max_over_ranks": scan_max,
+                                      "note": "every step starts at a barrier here, so waiting for the slowest rank shows up in the "
+                                              "combine phase; in the timed loop the ranks run ahead of the root"}
     avg_bytes = float(np.mean(algo_bytes)) if algo_bytes else 0.0
     kernel = ("cg_jit_scan nullable form (exists bitmap + rank directory; fused decode+filter+partial aggregate)" if nulls else
               "cg_scan_fast_kernel<1,DENSE,1> (fused decode+filter+partial aggregate)")
@@ -716,6 +748,8 @@ def run_c2(env, args, nulls=False, headline=True):
         sh.free()
     partial.free()
     del rels, shards
+    if world > 1:
+        cg.set_option("peer_window", 1)          # the next leg measures its own choice
     return line
 
 
@@ -893,11 +927,14 @@ def run_c4(env, args):
         return joined, jsum, got_r, got_s
 
     nccl_shuffle_ms = None
-    if world > 1 and cgd.peer_window():                  # the same shuffle with NCCL send/recv as the data path, for the record
+    if world > 1 and cgd.peer_window():                  # the same shuffle with NCCL send/recv as the data path
         cg.set_option("peer_window", 0)
         nccl_shuffle_ms = env.timed(shuffle, args.leg_steps, 2, profile=False)[0]
         cg.set_option("peer_window", 1)
     shuffle_ms, sclocks, slaunches, _, _, _ = env.timed(shuffle, args.leg_steps, 2, profile=False)     # the config's metric: the shuffle
+    if nccl_shuffle_ms is not None and nccl_shuffle_ms < shuffle_ms:          # measured choice, the same on every rank
+        cg.set_option("peer_window", 0)
+        shuffle_ms, sclocks, slaunches, _, _, _ = env.timed(shuffle, args.leg_steps, 2, profile=False)
     ms, clocks, launches, _, _, last = env.timed(step, max(args.leg_steps // 2, 2), 1, profile=False)  # shuffle + merge-side join
     joined, jsum, got_r, got_s = last
     r0, r1 = cgd.exchange_result(0, 2, timing=True), cgd.exchange_result(1, 2, timing=True)
@@ -956,6 +993,9 @@ def run_c4(env, args):
     del cnt_r, sum_r, c, term
     lo, mid, hi = jsum & 0xFFFFFFFF, (jsum >> 32) & 0xFFFFFFFF, jsum >> 64
     tj = env.sum_over_ranks([joined, lo, mid, hi, 0 if ok else 1])
+    peer_path = world > 1 and cgd.peer_window()
+    if world > 1:
+        cg.set_option("peer_window", 1)
     if rank != 0:
         return None
     total_sum = tj[1] + (tj[2] << 32) + (tj[3] << 64)
@@ -965,7 +1005,7 @@ def run_c4(env, args):
             "step": "routing + scatter + all-to-all of both tables (the shuffle); the join is timed on top of it below",
             "shuffle_plus_join": {"rows_per_s": 2 * rows / (ms / 1e3), "ms_per_step": ms, "join_ms": ms - shuffle_ms},
             "data_path": ("peer window: the scatter kernel stores rows into the owners' receive buffers over NVLink (CUDA IPC)"
-                          if world > 1 and cgd.peer_window() else "grouped ncclSend/ncclRecv" if world > 1 else "local"),
+                          if peer_path else "grouped ncclSend/ncclRecv" if world > 1 else "local"),
             "ms_per_step_with_nccl_sendrecv": nccl_shuffle_ms,
             "exchange_ms": ex_ms, "nvlink_gbs": (sent / 1e9) / (ex_ms / 1e3) if world > 1 and ex_ms > 0 else None,
             "nvlink_bytes": int(sent), "nvlink_peak_note": "900 GB/s per direction and GPU (NVLink 5)",

@@ -1626,9 +1626,14 @@ static int export_rows(CgContext *ctx, CgPartial *p, uint64_t capacity, int64_t 
 		if (rc == CG_OK) rc = cg_launch_export(p, capacity, d_keys, d_nulls, d_words, p->d_out_count, ctx->compute);
 	}
 	if (rc) return rc;
-	CG_CUDA(cudaMemcpyAsync(st, p->d_stats, sizeof st, cudaMemcpyDeviceToHost, ctx->compute));
-	CG_CUDA(cudaMemcpyAsync(counts, p->d_out_count, sizeof counts, cudaMemcpyDeviceToHost, ctx->compute));
+	/* both read-backs land in pinned memory: truly asynchronous copies, one wait (a pageable destination makes
+	 * every small copy a blocking round trip of its own) */
+	if (!p->h_ret) CG_CUDA(cudaHostAlloc((void **) &p->h_ret, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
+	CG_CUDA(cudaMemcpyAsync(p->h_ret, p->d_stats, sizeof st, cudaMemcpyDeviceToHost, ctx->compute));
+	CG_CUDA(cudaMemcpyAsync(p->h_ret + 5, p->d_out_count, sizeof counts, cudaMemcpyDeviceToHost, ctx->compute));
 	CG_CUDA(cudaStreamSynchronize(ctx->compute));
+	memcpy(st, p->h_ret, sizeof st);
+	memcpy(counts, p->h_ret + 5, sizeof counts);
 	rc = check_error_flags(p, st[2]);
 	if (rc) return rc;
 	/* every row added to a packed word must have come out again (drained earlier, or decoded just now) */

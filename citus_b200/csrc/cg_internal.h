@@ -316,6 +316,7 @@ struct CgPartial
 	bool packed_dirty = false;
 	bool wide_dirty = false;        /* the wide accumulator words hold something (not only the packed words) */
 	bool table_initialised = false;
+	unsigned long long *h_ret = nullptr;    /* pinned: statistics + row counts read back by export_rows */
 	bool read_packed_direct = false; /* result rows were decoded from the packed words since the last drain */
 	int launches_since_drain = 0;
 	uint64_t rows_since_drain = 0;  /* rows scanned into packed words since the last drain (upper bound) */

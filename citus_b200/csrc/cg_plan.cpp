@@ -292,6 +292,7 @@ extern "C" void cg_partial_free(CgPartial *p)
 	cudaFree(p->d_table); cudaFree(p->d_stats); cudaFree(p->d_out_keys); cudaFree(p->d_out_words); cudaFree(p->d_packed);
 	cudaFree(p->d_out_nulls); cudaFree(p->d_out_count);
 	if (p->h_out) cudaFreeHost(p->h_out);
+	if (p->h_ret) cudaFreeHost(p->h_ret);
 	delete p;
 }
 
