@@ -627,29 +627,37 @@ def run_c2(env, args, nulls=False, headline=True):
     value = total_rows / (ms / 1e3)
     if world > 1 and headline:
         # where a step's time goes on this rank (events between the phases; outside the timed loop)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        acc = np.zeros(3)
-        reps = 10
-        for _ in range(reps):
-            env.barrier()
-            ev[0].record()
-            partial.reset()
-            for s in my_shards:
-                partial.scan_shard(shards[s], want_stats=False)
-            ev[1].record()
-            cgd.combine_partials(partial, dst=0, local_status=0)
-            ev[2].record()
-            if rank == 0:
-                partial.export_device(out_keys.data_ptr(), out_nulls.data_ptr(), out_words.data_ptr(), NKEYS + 2)
-            ev[3].record()
-            torch.cuda.synchronize()
-            acc += [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
-        acc /= reps
-        scan_max = env.max_over_ranks(float(acc[0]))
-        combine["phases_ms_rank0"] = {"reset_and_scans": float(acc[0]), "combine_incl_wait_for_slowest_rank": float(acc[1]),
-                                      "export_on_root": float(acc[2]), "reset_and_scans_max_over_ranks": scan_max,
-                                      "note": "every step starts at a barrier here, so waiting for the slowest rank shows up in the "
-                                              "combine phase; in the timed loop the ranks run ahead of the root"}
+        def phases(reps=10):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            acc = np.zeros(3)
+            for _ in range(reps):
+                env.barrier()
+                ev[0].record()
+                partial.reset()
+                for s in my_shards:
+                    partial.scan_shard(shards[s], want_stats=False)
+                ev[1].record()
+                cgd.combine_partials(partial, dst=0, local_status=0)
+                ev[2].record()
+                if rank == 0:
+                    partial.export_device(out_keys.data_ptr(), out_nulls.data_ptr(), out_words.data_ptr(), NKEYS + 2)
+                ev[3].record()
+                torch.cuda.synchronize()
+                acc += [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
+            acc /= reps
+            return {"reset_and_scans": float(acc[0]), "combine_incl_wait_for_slowest_rank": float(acc[1]),
+                    "export_on_root": float(acc[2]), "reset_and_scans_max_over_ranks": env.max_over_ranks(float(acc[0]))}
+
+        chosen = 1 if cgd.peer_window() else 0
+        combine["phases_ms_rank0"] = phases()
+        combine["phases_ms_rank0"]["note"] = ("every step starts at a barrier here, so waiting for the slowest rank shows up in the "
+                                              "combine phase; in the timed loop the ranks run ahead of the root")
+        if "calibration_ms_per_step" in combine:         # the other data path, for the record
+            cg.set_option("peer_window", 1 - chosen)
+            step()
+            combine["phases_ms_rank0_other_path"] = phases()
+            cg.set_option("peer_window", chosen)
+            step()
     avg_bytes = float(np.mean(algo_bytes)) if algo_bytes else 0.0
     kernel = ("cg_jit_scan nullable form (exists bitmap + rank directory; fused decode+filter+partial aggregate)" if nulls else
               "cg_scan_fast_kernel<1,DENSE,1> (fused decode+filter+partial aggregate)")

@@ -16,9 +16,10 @@
  *   cg_comm_repartition_exchange  MAP_OUTPUT_FETCH: routing + scatter + one grouped ncclSend/ncclRecv of all
  *                                 columns, counts exchanged on the device side of a second stream
  * Peer window (one node, NVLink): every rank owns one cudaMalloc'ed window that all other ranks map with CUDA IPC.
- *   combine      the packed accumulator words are reduced by the ranks themselves: rank s sums slice s of all
- *                windows with loads over NVLink and stores the total into the coordinator rank's window (a
- *                reduce-scatter whose scatter target is one rank); two flag barriers in peer memory order it
+ *   combine      the packed accumulator words are reduced by the ranks themselves: every rank stores slice s of its
+ *                words into rank s's window, rank s sums the rows it received and stores the total into the
+ *                coordinator rank's window (a reduce-scatter whose scatter target is one rank; stores only --
+ *                a remote load is a round trip); two flag barriers in peer memory order it
  *   repartition  the scatter kernel stores every row straight into the receive buffer of the rank that owns the
  *                row's partition: routing, scatter and all-to-all are one pass, no send buffer, no second kernel
  * NCCL stays underneath for bootstrap (handles, counts, agreements) and as the path when IPC mapping is refused.
@@ -245,9 +246,10 @@ __global__ void cg_peer_barrier_kernel(const PeerFlags F, int kind, unsigned lon
 		st_release_sys(F.peer[t] + kind * CG_MAX_RANKS + F.me, epoch);
 		const unsigned long long *flag = F.peer[F.me] + kind * CG_MAX_RANKS + t;
 		const unsigned long long t0 = global_timer_ns();
+		unsigned int polls = 0;
 		while (ld_acquire_sys(flag) < epoch)
 		{
-			if (global_timer_ns() - t0 > 4000000000ull)
+			if ((++polls & 0x3ffu) == 0 && global_timer_ns() - t0 > 4000000000ull)      /* the timer is slow to read: rarely */
 			{
 				*(volatile unsigned int *) F.status = 1u + (unsigned) kind;
 				break;
@@ -263,30 +265,53 @@ __global__ void __launch_bounds__(256) cg_peer_copy_kernel(const unsigned long l
 	for (size_t i = (size_t) blockIdx.x * 256 + threadIdx.x; i < words; i += stride) dst[i] = src[i];
 }
 
+/* All traffic between GPUs is stores (a remote store is posted; a remote load is a round trip):
+ *   push     word i of this rank goes to the rank that owns slice i / chunk, into row `me` of that rank's input window
+ *   reduce   the owner sums the nranks rows of its slice (local loads) and stores the total into the coordinator's
+ *            output window */
+struct PeerPush
+{
+	unsigned long long *in[CG_MAX_RANKS];            /* the input windows of all ranks: [nranks][chunk] words each */
+	const unsigned long long *src;
+	size_t words, chunk;                             /* this rank's words; slice length (even) */
+	int me, nranks;
+};
+
+__global__ void __launch_bounds__(256) cg_peer_push_kernel(const __grid_constant__ PeerPush A)
+{
+	const size_t total = A.chunk * (size_t) A.nranks;
+	const size_t stride = (size_t) gridDim.x * 512;
+	for (size_t i = 2 * ((size_t) blockIdx.x * 256 + threadIdx.x); i < total; i += stride)
+	{
+		const unsigned long long a = i < A.words ? A.src[i] : 0ull, b = i + 1 < A.words ? A.src[i + 1] : 0ull;
+		const size_t s = i / A.chunk;                /* chunk is even: both words have the same owner */
+		unsigned long long *dst = A.in[s] + (size_t) A.me * A.chunk + (i - s * A.chunk);
+		asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(a), "l"(b) : "memory");
+	}
+}
+
 struct PeerReduce
 {
-	const unsigned long long *in[CG_MAX_RANKS];      /* the input windows of all ranks */
-	unsigned long long *out;                         /* the coordinator rank's output window */
-	size_t begin, end;                               /* this rank's slice (even bounds) */
+	const unsigned long long *in;                    /* this rank's input window */
+	unsigned long long *out;                         /* the coordinator's output window + this rank's slice begin */
+	size_t chunk, len;                               /* row pitch; words of the slice that exist */
 	int nranks;
 };
 
-/* slice [begin, end) of the sum over the ranks' windows -> the coordinator rank's output window.  The inputs are read
- * with volatile loads: other GPUs wrote them, and the same addresses carry new values every combine. */
 __global__ void __launch_bounds__(256) cg_peer_reduce_kernel(const __grid_constant__ PeerReduce A)
 {
 	const size_t stride = (size_t) gridDim.x * 512;
-	for (size_t i = A.begin + 2 * ((size_t) blockIdx.x * 256 + threadIdx.x); i < A.end; i += stride)
+	for (size_t j = 2 * ((size_t) blockIdx.x * 256 + threadIdx.x); j < A.len; j += stride)
 	{
 		unsigned long long a = 0, b = 0;
 #pragma unroll 4
 		for (int r = 0; r < A.nranks; r++)
 		{
-			unsigned long long x, y;
-			asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "l"(A.in[r] + i) : "memory");
+			unsigned long long x, y;             /* other GPUs wrote these words: not through L1 */
+			asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "l"(A.in + (size_t) r * A.chunk + j) : "memory");
 			a += x; b += y;
 		}
-		asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(A.out + i), "l"(a), "l"(b) : "memory");
+		asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(A.out + j), "l"(a), "l"(b) : "memory");
 	}
 }
 
@@ -622,27 +647,29 @@ extern "C" int cg_comm_combine(CgPartial *p, int32_t root, int32_t local_status)
 		const size_t L = (size_t) p->entries + CG_COMM_TAIL;
 		cg_comm_tail_write_kernel<<<1, 32, 0, ctx->compute>>>(tail, p->d_stats, 1);
 		CG_CUDA(cudaGetLastError()); g_cg_launches++;
-		if (peer && L <= CG_WIN_WORDS)
+		const int W = g_comm.nranks, me = g_comm.rank;
+		const size_t L2 = (L + 1) & ~(size_t) 1;
+		const size_t chunk = (((L2 + W - 1) / W) + 1) & ~(size_t) 1;
+		if (peer && chunk * W <= CG_WIN_WORDS)
 		{
-			/* the ranks reduce among themselves over NVLink: words -> own window; barrier; rank s sums slice s of all
-			 * windows into the coordinator's output window; barrier; the coordinator takes the total */
-			const int W = g_comm.nranks, me = g_comm.rank;
-			const unsigned copy_grid = (unsigned) std::min<size_t>((L + 255) / 256, 148 * 8);
-			cg_peer_copy_kernel<<<copy_grid, 256, 0, ctx->compute>>>((const unsigned long long *) p->d_packed, win_in(me), L);
+			/* the ranks reduce among themselves over NVLink: every rank pushes slice s of its words to rank s; barrier;
+			 * rank s sums what it received into the coordinator's output window; barrier; the coordinator takes the total */
+			PeerPush U;
+			memset(&U, 0, sizeof U);
+			for (int r = 0; r < W; r++) U.in[r] = win_in(r);
+			U.src = (const unsigned long long *) p->d_packed; U.words = L; U.chunk = chunk; U.me = me; U.nranks = W;
+			const unsigned push_grid = (unsigned) std::min<size_t>((chunk * W + 511) / 512, 148 * 8);
+			cg_peer_push_kernel<<<push_grid, 256, 0, ctx->compute>>>(U);
 			CG_CUDA(cudaGetLastError()); g_cg_launches++;
 			rc = comm_peer_barrier(0, ctx->compute);
 			if (rc) return rc;
-			const size_t L2 = (L + 1) & ~(size_t) 1;
-			const size_t chunk = (((L2 + W - 1) / W) + 1) & ~(size_t) 1;
-			PeerReduce A;
-			memset(&A, 0, sizeof A);
-			for (int r = 0; r < W; r++) A.in[r] = win_in(r);
-			A.out = win_out(root);
-			A.begin = std::min(L2, (size_t) me * chunk); A.end = std::min(L2, A.begin + chunk);
-			A.nranks = W;
-			if (A.end > A.begin)
+			const size_t begin = std::min(L2, (size_t) me * chunk), end = std::min(L2, begin + chunk);
+			if (end > begin)
 			{
-				const unsigned grid = (unsigned) std::min<size_t>((A.end - A.begin + 511) / 512, 148 * 8);
+				PeerReduce A;
+				memset(&A, 0, sizeof A);
+				A.in = win_in(me); A.out = win_out(root) + begin; A.chunk = chunk; A.len = end - begin; A.nranks = W;
+				const unsigned grid = (unsigned) std::min<size_t>((A.len + 511) / 512, 148 * 8);
 				cg_peer_reduce_kernel<<<grid, 256, 0, ctx->compute>>>(A);
 				CG_CUDA(cudaGetLastError()); g_cg_launches++;
 			}
@@ -650,6 +677,7 @@ extern "C" int cg_comm_combine(CgPartial *p, int32_t root, int32_t local_status)
 			if (rc) return rc;
 			if (me == root)
 			{
+				const unsigned copy_grid = (unsigned) std::min<size_t>((L + 255) / 256, 148 * 8);
 				cg_peer_copy_kernel<<<copy_grid, 256, 0, ctx->compute>>>(win_out(me), (unsigned long long *) p->d_packed, L);
 				CG_CUDA(cudaGetLastError()); g_cg_launches++;
 				cg_comm_tail_absorb_kernel<<<1, 32, 0, ctx->compute>>>(tail, p->d_stats, 1);

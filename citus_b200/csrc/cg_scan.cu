@@ -697,17 +697,28 @@ int cg_launch_table_init(CgPartial *p, cudaStream_t stream)
 	return CG_OK;
 }
 
-/* place of an occupied entry in the compacted output: one atomic per warp (the lanes of a warp walk consecutive entries) */
+/* place of an occupied entry in the compacted output: ONE atomic per block and iteration (256 consecutive entries).  A
+ * per-warp atomic is 31 k same-address atomics for a million groups -- tens of microseconds on one L2 line, more than
+ * the kernel's memory traffic.  Every thread of the block calls this the same number of times. */
 __device__ __forceinline__ unsigned long long export_position(bool occupied, unsigned long long *count)
 {
-	const unsigned lane = threadIdx.x & 31u;
+	__shared__ unsigned int s_warp[32];
+	__shared__ unsigned long long s_base;
+	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31u) >> 5;
 	const unsigned m = __ballot_sync(0xffffffffu, occupied);
-	if (m == 0) return 0;
-	const int leader = __ffs(m) - 1;
-	unsigned long long first = 0;
-	if ((int) lane == leader) first = atomicAdd(count, (unsigned long long) __popc(m));
-	first = __shfl_sync(0xffffffffu, first, leader);
-	return first + __popc(m & ((1u << lane) - 1u));
+	if (lane == 0) s_warp[warp] = __popc(m);
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		unsigned int total = 0;
+		for (unsigned w = 0; w < nwarps; w++) total += s_warp[w];
+		s_base = total ? atomicAdd(count, (unsigned long long) total) : 0ull;
+	}
+	__syncthreads();
+	unsigned long long pos = s_base + __popc(m & ((1u << lane) - 1u));
+	for (unsigned w = 0; w < warp; w++) pos += s_warp[w];
+	__syncthreads();                      /* the next iteration overwrites the shared words */
+	return pos;
 }
 
 __global__ void cg_export_kernel(const __grid_constant__ TableView T, uint64_t out_capacity, int64_t *keys,
@@ -791,7 +802,15 @@ __global__ void cg_export_packed_kernel(const __grid_constant__ TableView T, con
 				words[pos * (uint64_t) T.nwords + x] = x == 0 ? n : x == pack_word ? (uint64_t) sum : word_identity(T.wordop[x]);
 	}
 	for (int o = 16; o > 0; o >>= 1) decoded += __shfl_xor_sync(0xffffffffu, decoded, o);
-	if ((threadIdx.x & 31) == 0 && decoded) atomicAdd(count + 1, decoded);
+	__shared__ unsigned long long s_dec[32];
+	if ((threadIdx.x & 31) == 0) s_dec[threadIdx.x >> 5] = decoded;
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		unsigned long long t = 0;
+		for (unsigned w = 0; w < (blockDim.x + 31u) >> 5; w++) t += s_dec[w];
+		if (t) atomicAdd(count + 1, t);
+	}
 }
 
 int cg_launch_export_packed(CgPartial *p, uint64_t out_capacity, int64_t *d_keys, uint8_t *d_nulls, uint64_t *d_words,
