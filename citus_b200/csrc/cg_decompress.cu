@@ -39,6 +39,7 @@
 #include <stdlib.h>
 
 #include "cg_internal.h"
+#include "cg_lz4_lane.cuh"
 #include "cg_zstd.cuh"
 
 #define CGD_WARPS 4
@@ -47,6 +48,7 @@
 #define CGD_RING 256u
 #define CGD_WIN 2048u
 #define CGD_CHUNK 256u
+#define CG_LZ4_LANES_DEFAULT 0      /* cg_set_option("lz4_lanes", 1) / CG_LZ4_LANES=1: the lane-per-stream LZ4 kernel */
 
 struct Stream
 {
@@ -269,7 +271,7 @@ static __device__ bool pglz_stream(Stream &s, Out &o, uint32_t rawlen)
  * (124 ms vs 11.7 ms per 9375-stream shard); with one copy the groups mostly stay converged. */
 __global__ void __launch_bounds__(CGD_WARPS * 32)
 cg_decompress_kernel(uint8_t *arena, const DecodeItem *items, uint32_t nitems, unsigned long long *err,
-					 unsigned long long flag)
+					 unsigned long long flag, int skip_lz4)
 {
 	__shared__ __align__(16) uint8_t rings[CGD_WARPS * CGD_GROUPS][CGD_RING];
 	__shared__ __align__(16) uint8_t wins[CGD_WARPS * CGD_GROUPS][CGD_WIN];
@@ -279,6 +281,7 @@ cg_decompress_kernel(uint8_t *arena, const DecodeItem *items, uint32_t nitems, u
 	if (idx >= nitems) return;
 	const DecodeItem it = items[idx];
 	if (it.kind == CG_COMPRESSION_ZSTD) return;                     /* cg_zstd_kernel's */
+	if (skip_lz4 && it.kind == CG_COMPRESSION_LZ4) return;          /* cg_lz4_lane_kernel's */
 	Stream s;
 	s.src = arena + it.src;
 	s.len = it.comp_len;
@@ -511,21 +514,63 @@ cg_zstd_kernel(uint8_t *arena, const DecodeItem *items, uint32_t nitems, uint8_t
 	}
 }
 
+/*
+ * LZ4, a lane per stream (cg_lz4_lane.cuh).  One warp per CTA with its 32 KB of interleaved windows; only the first
+ * `active` lanes of a warp take a stream: a launch has ~10^4 streams, which is two full warps per SM -- too few to hide
+ * the latency of the dependent shared-memory steps of a sequence -- so the streams are spread over more, emptier
+ * warps (an idle lane costs nothing, an idle scheduler does).
+ */
+__global__ void __launch_bounds__(32)
+cg_lz4_lane_kernel(uint8_t *arena, const DecodeItem *items, uint32_t nitems, unsigned long long *err, unsigned long long flag,
+				   uint32_t active)
+{
+	__shared__ __align__(16) uint8_t win[CGL_WIN * CGL_LANES];
+	if (threadIdx.x >= active) return;
+	const uint32_t idx = blockIdx.x * active + threadIdx.x;
+	if (idx >= nitems) return;
+	const DecodeItem it = items[idx];
+	if (it.kind != CG_COMPRESSION_LZ4) return;
+	Lz4Lane L;
+	L.src = arena + it.src; L.clen = it.comp_len;
+	L.dst = arena + it.dst; L.rawlen = it.raw_len;
+	L.wb = win + 4u * threadIdx.x;
+	if (!cgl_decode(L, it.padded))
+	{
+		for (uint32_t i = 0; i < it.padded; i++) L.dst[i] = 0;
+		atomicOr(err, flag);
+	}
+}
+
+static int g_lz4_lanes = -1;
+void cg_decompress_set_lz4_lanes(int on) { g_lz4_lanes = on < 0 ? -1 : (on ? 1 : 0); }      /* < 0: back to the default */
+
 /* h_items: the host copy of the same items (which kernels are needed) */
 int cg_launch_decompress(CgContext *ctx, uint8_t *arena, const DecodeItem *items, const DecodeItem *h_items, uint64_t nitems,
 						 unsigned long long *err, unsigned long long flag, cudaStream_t stream)
 {
 	if (nitems == 0) return CG_OK;
-	bool any_lz = false, any_zstd = false;
+	if (g_lz4_lanes < 0) { const char *e = getenv("CG_LZ4_LANES"); g_lz4_lanes = e ? (atoi(e) ? 1 : 0) : CG_LZ4_LANES_DEFAULT; }
+	bool any_lz = false, any_zstd = false, any_lz4 = false;
 	for (uint64_t i = 0; i < nitems; i++)
 	{
-		if (h_items[i].kind == CG_COMPRESSION_ZSTD) any_zstd = true; else any_lz = true;
+		if (h_items[i].kind == CG_COMPRESSION_ZSTD) any_zstd = true;
+		else if (h_items[i].kind == CG_COMPRESSION_LZ4 && g_lz4_lanes) any_lz4 = true;
+		else any_lz = true;
+	}
+	if (any_lz4)
+	{
+		/* about eight warps per SM, 4..32 streams per warp */
+		uint32_t active = 32;
+		while (active > 4 && (nitems + active - 1) / active < (uint64_t) ctx->sm_count * 8) active >>= 1;
+		const unsigned blocks = (unsigned) ((nitems + active - 1) / active);
+		cg_lz4_lane_kernel<<<blocks, 32, 0, stream>>>(arena, items, (uint32_t) nitems, err, flag, active);
+		CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	}
 	if (any_lz)
 	{
 		const unsigned per_block = CGD_WARPS * CGD_GROUPS;
 		unsigned blocks = (unsigned) ((nitems + per_block - 1) / per_block);
-		cg_decompress_kernel<<<blocks, CGD_WARPS * 32, 0, stream>>>(arena, items, (uint32_t) nitems, err, flag);
+		cg_decompress_kernel<<<blocks, CGD_WARPS * 32, 0, stream>>>(arena, items, (uint32_t) nitems, err, flag, g_lz4_lanes);
 		CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	}
 	if (any_zstd)

@@ -851,7 +851,8 @@ static bool cg_force_general(void)
 
 /* run-time switches (the same ones the CG_* environment variables set at first use): which kernel family
  * scans -- "jit" 0 = ahead-of-time kernels only, 1 = plan-specialised where no ahead-of-time specialisation
- * applies (default), 2 = always; "force_general" 1 = the interpretive kernels for everything; "peer_window" 0 = the
+ * applies (default), 2 = always; "force_general" 1 = the interpretive kernels for everything; "lz4_lanes" 1 / 0 = LZ4 value
+ * streams are decoded a lane per stream / eight lanes per stream; "peer_window" 0 = the
  * combine and the repartition exchange stay on NCCL instead of the IPC-mapped peer window (set it on every rank) */
 extern "C" int cg_set_option(const char *name, int64_t value)
 {
@@ -859,6 +860,7 @@ extern "C" int cg_set_option(const char *name, int64_t value)
 	if (strcmp(name, "jit") == 0) { cg_jit_set_level((int) value); return CG_OK; }
 	if (strcmp(name, "force_general") == 0) { g_force_general = value ? 1 : 0; return CG_OK; }
 	if (strcmp(name, "realign_tma") == 0) { cg_realign_set_tma((int) value); return CG_OK; }
+	if (strcmp(name, "lz4_lanes") == 0) { cg_decompress_set_lz4_lanes((int) value); return CG_OK; }
 	if (strcmp(name, "peer_window") == 0) { cg_comm_set_peer_window((int) value); return CG_OK; }     /* the same value on every rank */
 	return cg_set_error(CG_EINVAL, "unknown option %s", name);
 }

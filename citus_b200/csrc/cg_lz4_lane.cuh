@@ -1,0 +1,183 @@
+/*
+ * cg_lz4_lane.cuh -- an LZ4 block decoder in which ONE GPU lane decodes one value stream from start to end
+ * (and, for the CPU-side format tests, the host runs the same source: every function is __host__ __device__).
+ *
+ * Replaces the COMPRESSION_LZ4 arm of DecompressBuffer, backend/columnar/columnar_compression.c:186-208
+ * (LZ4_decompress_safe(buffer, out, len, decompressedSize) must return exactly decompressedSize); the block
+ * format is the published one, restated at the top of cg_decompress.cu.
+ *
+ * Why a lane per stream: the eight-lanes-per-stream kernel in cg_decompress.cu is bound by instruction issue --
+ * about 150 warp instructions per sequence, and a sequence of a columnar value stream is ~8 bytes (a few literal
+ * bytes of a value and a match for the bytes it shares with its neighbours), so most of those instructions
+ * coordinate lanes that have nothing to copy.  Here a warp instruction advances 32 streams, nothing is
+ * coordinated, and an overlapping match is an ordinary sequential copy.
+ *
+ * The last CGL_WIN decoded bytes of a stream live in a window in shared memory; windows of the 32 lanes are
+ * interleaved word by word (word w of lane l at [w * 32 + l]): lanes that work at the same position of their
+ * streams -- the common case, the streams of a launch are alike -- hit 32 different banks.  A match that reaches
+ * back further than the window reads the arena (behind a flush).  The window leaves for the arena in aligned
+ * 16-byte stores.
+ */
+#ifndef CG_LZ4_LANE_CUH
+#define CG_LZ4_LANE_CUH
+
+#include <stdint.h>
+#include <string.h>
+
+#ifndef CG_HD
+#ifdef __CUDACC__
+#define CG_HD __host__ __device__ __forceinline__
+#else
+#define CG_HD inline
+#endif
+#endif
+
+#define CGL_WIN 1024u           /* bytes of window per lane */
+#define CGL_PIECE 256u          /* a copy advances in pieces of at most this many bytes; < CGL_WIN - 16 */
+#define CGL_LANES 32u
+
+struct Lz4Lane
+{
+	const uint8_t *src;         /* the compressed stream */
+	uint32_t clen;
+	uint8_t *dst;               /* 16-byte aligned slot of `padded` bytes */
+	uint32_t rawlen;
+	uint8_t *wb;                /* window: byte b of the lane's word w is wb[w * 4 * CGL_LANES + b] */
+	uint32_t op;                /* bytes decoded */
+	uint32_t flushed;           /* bytes already in dst (multiple of 16) */
+	uint32_t zero_offset;       /* out: the stream was refused because a match has offset 0 (see cgl_decode) */
+};
+
+CG_HD uint32_t cgl_at(uint32_t pos)
+{
+	return ((pos & (CGL_WIN - 1u)) >> 2) * (4u * CGL_LANES) + (pos & 3u);
+}
+
+/* window -> dst for [flushed, upto rounded down to 16) */
+CG_HD void cgl_flush(Lz4Lane &L, uint32_t upto)
+{
+	upto &= ~15u;
+	for (uint32_t pos = L.flushed; pos < upto; pos += 16u)
+	{
+		uint32_t w[4];
+		for (int k = 0; k < 4; k++) w[k] = *(const uint32_t *) (L.wb + cgl_at(pos + 4u * k));
+#ifdef __CUDA_ARCH__
+		*(uint4 *) (L.dst + pos) = make_uint4(w[0], w[1], w[2], w[3]);
+#else
+		memcpy(L.dst + pos, w, 16);
+#endif
+	}
+	if (upto > L.flushed) L.flushed = upto;
+}
+
+/* before m <= CGL_PIECE more bytes are written: nothing unflushed may be overwritten */
+CG_HD void cgl_room(Lz4Lane &L, uint32_t m)
+{
+	if (L.op + m - L.flushed > CGL_WIN) cgl_flush(L, L.op);
+}
+
+CG_HD void cgl_literals(Lz4Lane &L, uint32_t ip, uint32_t n)
+{
+	while (n)
+	{
+		const uint32_t m = n < CGL_PIECE ? n : CGL_PIECE;
+		cgl_room(L, m);
+		for (uint32_t i = 0; i < m; i++) L.wb[cgl_at(L.op + i)] = L.src[ip + i];
+		L.op += m; ip += m; n -= m;
+	}
+}
+
+/* n bytes from `off` bytes back (1 <= off <= op); byte by byte in stream order, which is LZ77's overlap rule */
+CG_HD void cgl_match(Lz4Lane &L, uint32_t off, uint32_t n)
+{
+	while (n)
+	{
+		const uint32_t m = n < CGL_PIECE ? n : CGL_PIECE;
+		if (off < CGL_WIN)
+		{
+			/* the source of byte w is w - off: its window slot is overwritten by byte w - off + CGL_WIN > w */
+			cgl_room(L, m);
+			if ((off & 3u) == 0 && m >= 8u)
+			{
+				/* source and target share their alignment: whole words once the target is aligned */
+				uint32_t i = 0;
+				for (; ((L.op + i) & 3u) != 0; i++) L.wb[cgl_at(L.op + i)] = L.wb[cgl_at(L.op + i - off)];
+				for (; i + 4u <= m; i += 4u)
+					*(uint32_t *) (L.wb + cgl_at(L.op + i)) = *(const uint32_t *) (L.wb + cgl_at(L.op + i - off));
+				for (; i < m; i++) L.wb[cgl_at(L.op + i)] = L.wb[cgl_at(L.op + i - off)];
+			}
+			else
+				for (uint32_t i = 0; i < m; i++) L.wb[cgl_at(L.op + i)] = L.wb[cgl_at(L.op + i - off)];
+		}
+		else
+		{
+			/* far match: its source left the window; after the flush it is in dst: the piece reads
+			 * [op - off, op - off + m), m <= CGL_PIECE < off - 15, all below the flushed mark (op & ~15) */
+			cgl_flush(L, L.op);
+			cgl_room(L, m);
+			const uint8_t *from = L.dst + (L.op - off);
+			for (uint32_t i = 0; i < m; i++) L.wb[cgl_at(L.op + i)] = from[i];
+		}
+		L.op += m; n -= m;
+	}
+}
+
+/* true: the slot holds exactly rawlen decoded bytes followed by zeros up to `padded`.  false: malformed stream
+ * (nothing outside the slot was written; the caller zero-fills it).  Agrees with LZ4_decompress_safe on every
+ * stream (tools/lz4_lane_fuzz.cpp) except one kind of damage: a match with offset 0, which liblz4 1.9 "decodes" to
+ * whatever the output buffer held before the call and which is refused here. */
+CG_HD bool cgl_decode(Lz4Lane &L, uint32_t padded)
+{
+	uint32_t ip = 0;
+	const uint32_t clen = L.clen, rawlen = L.rawlen;
+	L.op = 0; L.flushed = 0; L.zero_offset = 0;
+	if (clen == 0) return false;
+	if (rawlen == 0 && !(clen == 1 && L.src[0] == 0)) return false;      /* liblz4's rule for an empty output */
+	for (;;)
+	{
+		if (ip >= clen) return false;
+		const uint32_t token = L.src[ip++];
+		uint32_t lit = token >> 4;
+		if (lit == 15u)
+		{
+			uint32_t b;
+			do
+			{
+				if (ip >= clen) return false;
+				b = L.src[ip++];
+				lit += b;
+				if (lit > rawlen) return false;
+			} while (b == 255u);
+		}
+		if (lit > clen - ip || lit > rawlen - L.op) return false;
+		cgl_literals(L, ip, lit);
+		ip += lit;
+		if (ip == clen) break;                       /* the last sequence stops after its literals */
+		if (clen - ip < 2u) return false;
+		const uint32_t off = (uint32_t) L.src[ip] | ((uint32_t) L.src[ip + 1] << 8);
+		ip += 2;
+		uint32_t ml = token & 15u;
+		if (ml == 15u)
+		{
+			uint32_t b;
+			do
+			{
+				if (ip >= clen) return false;
+				b = L.src[ip++];
+				ml += b;
+				if (ml > rawlen) return false;
+			} while (b == 255u);
+		}
+		ml += 4u;
+		if (off == 0) L.zero_offset = 1;
+		if (off == 0 || off > L.op || ml > rawlen - L.op) return false;
+		cgl_match(L, off, ml);
+	}
+	if (L.op != rawlen) return false;
+	cgl_flush(L, L.op);
+	for (uint32_t i = L.flushed; i < rawlen; i++) L.dst[i] = L.wb[cgl_at(i)];
+	for (uint32_t i = rawlen; i < padded; i++) L.dst[i] = 0;
+	return true;
+}
+
+#endif

@@ -263,6 +263,117 @@ def test_jit_generates_valid_sm100a_code_for_every_plan_form(cg):
     assert "fcmp(v" in src and "f8_ordered" in src and "__uint_as_float" in src
 
 
+# --------------------------------------------------------------------------- lane-per-stream LZ4 decoder (on the host)
+@pytest.fixture(scope="module")
+def lz4_lane_host():
+    """tests/helpers/lz4_lane_host.cpp: the decoder source of cg_lz4_lane_kernel compiled for the host (g++), a
+    test-only shared object -- libcitus_gpu.so itself has no host decoding path"""
+    import subprocess
+    out_dir = os.path.join(ROOT, "tests", "helpers", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "liblz4_lane_host.so")
+    src = os.path.join(ROOT, "tests", "helpers", "lz4_lane_host.cpp")
+    hdr = os.path.join(ROOT, "citus_b200", "csrc", "cg_lz4_lane.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-g", "-shared", "-fPIC", "-x", "c++", "-I", os.path.dirname(hdr), "-o", so, src])
+    L = C.CDLL(so)
+    L.lz4_lane_decode_host.restype = C.c_int
+    L.lz4_lane_decode_host.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_uint, C.c_uint]
+    return L
+
+
+def _lz4_lane_decode(lib, comp, rawlen, lane=0, slack=48):
+    padded = (rawlen + 15) // 16 * 16 + 16
+    src = np.frombuffer(bytes(comp) + bytes(16), np.uint8).copy()
+    dst = np.full(padded + slack, 0xEE, np.uint8)
+    ok = lib.lz4_lane_decode_host(src.ctypes.data, len(comp), dst.ctypes.data, rawlen, padded, lane)
+    assert (dst[padded:] == 0xEE).all(), "wrote past the slot"
+    return ok, dst[:padded]
+
+
+def test_lz4_lane_decoder_against_liblz4(oracle, lz4_lane_host):
+    """cg_lz4_lane.cuh is sequential code one GPU lane runs per value stream; the same source is executed here against
+    streams produced by liblz4's LZ4_compress_default (what the reference's CompressBuffer calls): literal runs and
+    matches of every length class, offsets inside and beyond the 1 KB window, overlapping matches, stream sizes around
+    the window / piece / 16-byte flush boundaries; truncated and damaged streams are rejected or decode to the wrong
+    bytes of the right size only where liblz4 itself would"""
+    if not oracle.lib().orc_have_lz4():
+        pytest.skip("liblz4 missing")
+    rng = np.random.default_rng(5)
+    cases = {
+        "empty": b"", "one byte": b"x", "15 bytes": bytes(range(15)), "zeros 100k": bytes(100_000),
+        "period 3": (b"abc" * 40_000)[:100_000], "period 1021 (beyond the window)": bytes(rng.integers(0, 256, 1021, dtype=np.uint8)) * 90,
+        "period 1024": bytes(rng.integers(0, 256, 1024, dtype=np.uint8)) * 90, "period 5000": bytes(rng.integers(0, 256, 5000, dtype=np.uint8)) * 20,
+        "period 60000 (max offsets)": bytes(rng.integers(0, 256, 60_000, dtype=np.uint8)) * 3,
+        "C2 key column": rng.integers(0, 10**6, 10_000).astype(np.int64).tobytes(),
+        "C2 f column": rng.integers(0, 100, 10_000).astype(np.int64).tobytes(),
+        "C2 v column": rng.integers(-10**9, 10**9, 10_000).astype(np.int64).tobytes(),
+        "int4 dates": rng.integers(-2922, -365, 10_000).astype(np.int32).tobytes(),
+        "incompressible": rng.integers(0, 256, 80_000).astype(np.uint8).tobytes(),
+        "text": (b"the quick brown fox jumps over the lazy dog. " * 3000)[:100_000],
+        "runs": np.repeat(rng.integers(0, 100, 200), 500).astype(np.int8).tobytes(),
+        "sorted ids": np.arange(10_000, dtype=np.int64).tobytes(),
+    }
+    for n in (2, 3, 12, 13, 16, 17, 31, 255, 256, 257, 270, 271, 272, 1008, 1023, 1024, 1025, 1039, 1040, 1041, 1279, 1280, 1281,
+              4095, 4096, 65_535, 65_536, 65_537, 80_000):
+        cases[f"mixed n={n}"] = (rng.integers(0, 50, n) * rng.integers(0, 2, n)).astype(np.uint8).tobytes()
+        cases[f"sparse n={n}"] = (rng.integers(0, 256, n) * (rng.integers(0, 40, n) == 0)).astype(np.uint8).tobytes()
+    for name, data in cases.items():
+        comp = oracle.codec_compress(oracle.COMP_LZ4, data, 0)
+        assert comp is not None
+        for lane in (0, 7, 31):
+            ok, out = _lz4_lane_decode(lz4_lane_host, comp, len(data), lane)
+            assert ok == 1 and out[:len(data)].tobytes() == data and not out[len(data):].any(), (name, lane)
+        # a truncated stream never decodes to the full size; a wrong expected size is refused
+        if len(comp) > 1:
+            ok, _ = _lz4_lane_decode(lz4_lane_host, comp[:-1], len(data))
+            assert ok == 0, (name, "truncated")
+        ok, _ = _lz4_lane_decode(lz4_lane_host, comp, len(data) + 1)
+        assert ok == 0, (name, "one byte more expected")
+        if len(data) > 0:
+            ok, _ = _lz4_lane_decode(lz4_lane_host, comp, len(data) - 1)
+            assert ok == 0, (name, "one byte less expected")
+    # damaged streams: whatever happens stays inside the slot (checked by _lz4_lane_decode) and agrees with liblz4
+    for name in ("C2 key column", "text", "period 5000", "mixed n=4096"):
+        data = cases[name]
+        comp = bytearray(oracle.codec_compress(oracle.COMP_LZ4, data, 0))
+        for _ in range(300):
+            bad = bytearray(comp)
+            for _ in range(int(rng.integers(1, 4))):
+                bad[int(rng.integers(0, len(bad)))] = int(rng.integers(0, 256))
+            ok, out = _lz4_lane_decode(lz4_lane_host, bytes(bad), len(data))
+            try:
+                ref = oracle.codec_decompress(oracle.COMP_LZ4, bytes(bad), len(data))
+            except oracle.OracleError:
+                ref = None
+            if ok == -1:
+                continue        # a match with offset 0: refused here; liblz4 copies what the output buffer held before
+            assert (ok == 1) == (ref is not None), name
+            if ok == 1:
+                assert out[:len(data)].tobytes() == ref, name
+
+
+def test_lz4_lane_hand_assembled_blocks(lz4_lane_host):
+    """known-answer blocks: the golden of tests/test_oracle_golden.py, maximum-length codes, offset == position"""
+    # [token: 1 literal | match 10-4]['a'][offset 1] [token: 5 literals]['aaaaa'] -> 16 x 'a'
+    blk = bytes([0x16, ord("a"), 1, 0, 0x50]) + b"aaaaa"
+    ok, out = _lz4_lane_decode(lz4_lane_host, blk, 16)
+    assert ok == 1 and out[:16].tobytes() == b"a" * 16
+    # literal length 15 + 255 + 3 = 273 and a match of 4 + 15 + 255 + 255 + 7 = 536 bytes at offset 273 (the whole prefix), then 5 literals
+    lits = bytes((i * 7) & 0xff for i in range(273))
+    blk = bytes([0xFF, 255, 3]) + lits + bytes([273 & 0xff, 273 >> 8, 255, 255, 7]) + bytes([0x50]) + b"vwxyz"
+    want = lits + (lits * 2)[:536] + b"vwxyz"
+    ok, out = _lz4_lane_decode(lz4_lane_host, blk, len(want))
+    assert ok == 1 and out[:len(want)].tobytes() == want
+    # offset 0, offset beyond the output, match past the expected size, literals past the stream: all refused
+    for bad, raw in ((bytes([0x10, 1, 0, 0, 0x00]), 8), (bytes([0x10, 1, 2, 0, 0x00]), 8), (bytes([0x1F, 1, 1, 0, 200, 0x00]), 20),
+                     (bytes([0x50, 1, 2]), 5), (b"", 0)):
+        ok, _ = _lz4_lane_decode(lz4_lane_host, bad, raw)
+        assert ok != 1
+    # an empty output is exactly the one-byte block [0] (liblz4's rule)
+    assert _lz4_lane_decode(lz4_lane_host, bytes([0]), 0)[0] == 1 and _lz4_lane_decode(lz4_lane_host, bytes([0x03]), 0)[0] != 1
+
+
 # --------------------------------------------------------------------------- Zstandard decoder (format logic on the host)
 @pytest.fixture(scope="module")
 def zstd_host():
