@@ -542,6 +542,8 @@ cg_lz4_lane_kernel(uint8_t *arena, const DecodeItem *items, uint32_t nitems, uns
 }
 
 static int g_lz4_lanes = -1;
+static int g_lz4_lane_warps = 8;          /* warps per SM the lane kernel spreads a launch over */
+void cg_decompress_set_lz4_lane_warps(int n) { g_lz4_lane_warps = n < 1 ? 1 : n > 64 ? 64 : n; }
 void cg_decompress_set_lz4_lanes(int on) { g_lz4_lanes = on < 0 ? -1 : (on ? 1 : 0); }      /* < 0: back to the default */
 
 /* h_items: the host copy of the same items (which kernels are needed) */
@@ -559,9 +561,9 @@ int cg_launch_decompress(CgContext *ctx, uint8_t *arena, const DecodeItem *items
 	}
 	if (any_lz4)
 	{
-		/* about eight warps per SM, 4..32 streams per warp */
+		/* about g_lz4_lane_warps (8) warps per SM, 4..32 streams per warp */
 		uint32_t active = 32;
-		while (active > 4 && (nitems + active - 1) / active < (uint64_t) ctx->sm_count * 8) active >>= 1;
+		while (active > 4 && (nitems + active - 1) / active < (uint64_t) ctx->sm_count * (uint64_t) g_lz4_lane_warps) active >>= 1;
 		const unsigned blocks = (unsigned) ((nitems + active - 1) / active);
 		cg_lz4_lane_kernel<<<blocks, 32, 0, stream>>>(arena, items, (uint32_t) nitems, err, flag, active);
 		CG_CUDA(cudaGetLastError()); g_cg_launches++;

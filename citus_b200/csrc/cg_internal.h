@@ -356,6 +356,7 @@ struct DecodeItem
 	uint32_t kind;      /* CG_COMPRESSION_LZ4 / CG_COMPRESSION_PGLZ / CG_COMPRESSION_ZSTD */
 };
 void cg_decompress_set_lz4_lanes(int on);
+void cg_decompress_set_lz4_lane_warps(int n);
 int cg_launch_decompress(CgContext *ctx, uint8_t *arena, const DecodeItem *items, const DecodeItem *h_items, uint64_t nitems,
 						 unsigned long long *err, unsigned long long flag, cudaStream_t stream);
 

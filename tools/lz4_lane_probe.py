@@ -25,6 +25,7 @@ if len(sys.argv) > 2 and sys.argv[1] == "--summarise":
     for k, v in out.items():
         avg = sum(v) / len(v)
         print(f"{k}: {len(v)} launches, {avg:.1f} us average = {decoded / avg / 1e3:.1f} GB/s decoded (750 MB per launch)")
+        print("   per launch (us):", " ".join(f"{x:.0f}" for x in v))
     sys.exit(0)
 
 import bench  # noqa: E402
@@ -35,8 +36,10 @@ cg.set_writer_compression("lz4")
 rels = {s: cg.Relation.generate(list(bench.C2_COLUMNS), 31_250_000, seed=bench.SEED, first_row=s * 31_250_000,
                                 stripe_row_limit=bench.STRIPE_ROWS, chunk_row_limit=bench.CHUNK_ROWS, nthreads=32) for s in range(2)}
 cg.set_writer_compression("none")
-for mode in (0, 1, 0, 1):
+# launch order (two launches each): groups, lanes at 8 warps/SM, groups, lanes at 8, then lanes at 2, 4, 16 warps/SM
+for mode, warps in ((0, 8), (1, 8), (0, 8), (1, 8), (1, 2), (1, 4), (1, 16)):
     cg.set_option("lz4_lanes", mode)
+    cg.set_option("lz4_lane_warps", warps)
     for s in rels:
         sh = cg.Shard(rels[s], [0, 1, 2])
         sh.free()
