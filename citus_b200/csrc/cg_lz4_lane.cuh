@@ -35,6 +35,9 @@
 #define CGL_WIN 1024u           /* bytes of window per lane */
 #define CGL_PIECE 256u          /* a copy advances in pieces of at most this many bytes; < CGL_WIN - 16 */
 #define CGL_LANES 32u
+#define CGL_AHEAD 48u           /* the 8-byte copies may leave up to this many bytes of garbage beyond `op`: they land
+                                 * where later bytes go, and in the oldest bytes of the window, which therefore serves
+                                 * matches up to CGL_WIN - CGL_AHEAD back */
 
 struct Lz4Lane
 {
@@ -76,8 +79,75 @@ CG_HD void cgl_room(Lz4Lane &L, uint32_t m)
 	if (L.op + m - L.flushed > CGL_WIN) cgl_flush(L, L.op);
 }
 
+/* ---- eight bytes at a time ---- */
+CG_HD uint32_t cgl_funnel(uint32_t lo, uint32_t hi, uint32_t bits)      /* low word of (hi:lo) >> bits, bits in 0, 8, 16, 24 */
+{
+#ifdef __CUDA_ARCH__
+	return __funnelshift_r(lo, hi, bits);
+#else
+	return bits ? (lo >> bits) | (hi << (32u - bits)) : lo;
+#endif
+}
+
+/* the 8 bytes at p; [p rounded down to 8, + 16) must be readable */
+CG_HD uint64_t cgl_load8(const uint8_t *p)
+{
+#ifdef __CUDA_ARCH__
+	const unsigned long long a = (unsigned long long) p;
+	const uint64_t *q = (const uint64_t *) (a & ~7ull);
+	const uint32_t sh = (uint32_t) (a & 7ull) * 8u;
+	const uint64_t lo = q[0], hi = q[1];
+	return sh ? (lo >> sh) | (hi << (64u - sh)) : lo;
+#else
+	uint64_t v;
+	memcpy(&v, p, 8);
+	return v;
+#endif
+}
+
+CG_HD uint32_t cgl_word_at(uint32_t pos) { return ((pos & (CGL_WIN - 1u)) >> 2) * (4u * CGL_LANES); }
+
+/* the 8 window bytes at position pos (any alignment) */
+CG_HD uint64_t cgl_win_read8(const Lz4Lane &L, uint32_t pos)
+{
+	const uint32_t w0 = *(const uint32_t *) (L.wb + cgl_word_at(pos)), w1 = *(const uint32_t *) (L.wb + cgl_word_at(pos + 4u));
+	const uint32_t sh = (pos & 3u) * 8u;
+	if (sh == 0) return (uint64_t) w0 | ((uint64_t) w1 << 32);
+	const uint32_t w2 = *(const uint32_t *) (L.wb + cgl_word_at(pos + 8u));
+	return (uint64_t) cgl_funnel(w0, w1, sh) | ((uint64_t) cgl_funnel(w1, w2, sh) << 32);
+}
+
+/* v's 8 bytes to window positions [pos, pos + 8); the bytes below pos in pos's word are kept, up to 3 bytes beyond
+ * pos + 8 are overwritten with zeros */
+CG_HD void cgl_win_write8(Lz4Lane &L, uint32_t pos, uint64_t v)
+{
+	const uint32_t sh = (pos & 3u) * 8u, lo = (uint32_t) v, hi = (uint32_t) (v >> 32);
+	if (sh == 0)
+	{
+		*(uint32_t *) (L.wb + cgl_word_at(pos)) = lo;
+		*(uint32_t *) (L.wb + cgl_word_at(pos + 4u)) = hi;
+		return;
+	}
+	uint32_t *p0 = (uint32_t *) (L.wb + cgl_word_at(pos));
+	*p0 = (*p0 & ((1u << sh) - 1u)) | (lo << sh);
+	*(uint32_t *) (L.wb + cgl_word_at(pos + 4u)) = cgl_funnel(lo, hi, 32u - sh);
+	*(uint32_t *) (L.wb + cgl_word_at(pos + 8u)) = hi >> (32u - sh);
+}
+
+CG_HD void cgl_room8(Lz4Lane &L)
+{
+	if (L.op + CGL_AHEAD - L.flushed > CGL_WIN) cgl_flush(L, L.op);
+}
+
 CG_HD void cgl_literals(Lz4Lane &L, uint32_t ip, uint32_t n)
 {
+	/* 8 bytes at a time while the loads stay inside the stream, then byte by byte */
+	while (n >= 8u && (ip & ~7u) + 16u <= L.clen)
+	{
+		cgl_room8(L);
+		cgl_win_write8(L, L.op, cgl_load8(L.src + ip));
+		L.op += 8u; ip += 8u; n -= 8u;
+	}
 	while (n)
 	{
 		const uint32_t m = n < CGL_PIECE ? n : CGL_PIECE;
@@ -87,37 +157,60 @@ CG_HD void cgl_literals(Lz4Lane &L, uint32_t ip, uint32_t n)
 	}
 }
 
-/* n bytes from `off` bytes back (1 <= off <= op); byte by byte in stream order, which is LZ77's overlap rule */
+/* n bytes from `off` bytes back (1 <= off <= op), LZ77's overlap rule: byte i is out[op - off + (i mod off)] */
 CG_HD void cgl_match(Lz4Lane &L, uint32_t off, uint32_t n)
 {
+	if (off <= CGL_WIN - CGL_AHEAD)
+	{
+		/* the source of byte w is w - off: its window slot is overwritten by byte w - off + CGL_WIN > w (or by what an
+		 * 8-byte copy left up to CGL_AHEAD bytes beyond its end, hence the margin) */
+		if (off >= 8u)
+		{
+			/* 8 bytes per step never read a byte of the same step; the last step may write beyond the match */
+			while (n)
+			{
+				const uint32_t m = n < 8u ? n : 8u;
+				cgl_room8(L);
+				cgl_win_write8(L, L.op, cgl_win_read8(L, L.op - off));
+				L.op += m; n -= m;
+			}
+			return;
+		}
+		if (off == 1u || off == 2u || off == 4u)
+		{
+			/* a run: the period divides 8, so every 8-byte step stores the same pattern */
+			uint64_t v = cgl_win_read8(L, L.op - off);
+			if (off == 1u) v = (v & 0xffull) * 0x0101010101010101ull;
+			else if (off == 2u) v = (v & 0xffffull) * 0x0001000100010001ull;
+			else v = (v & 0xffffffffull) * 0x0000000100000001ull;
+			while (n)
+			{
+				const uint32_t m = n < 8u ? n : 8u;
+				cgl_room8(L);
+				cgl_win_write8(L, L.op, v);
+				L.op += m; n -= m;
+			}
+			return;
+		}
+		while (n)                                        /* periods 3, 5, 6, 7: byte by byte */
+		{
+			const uint32_t m = n < CGL_PIECE ? n : CGL_PIECE;
+			cgl_room(L, m);
+			for (uint32_t i = 0; i < m; i++) L.wb[cgl_at(L.op + i)] = L.wb[cgl_at(L.op + i - off)];
+			L.op += m; n -= m;
+		}
+		return;
+	}
 	while (n)
 	{
+		/* far match: its source left the window; after the flush it is in dst: the piece reads
+		 * [op - off, op - off + m), m <= CGL_PIECE < off - 15 (off > CGL_WIN - CGL_AHEAD), all below the flushed
+		 * mark (op & ~15) */
 		const uint32_t m = n < CGL_PIECE ? n : CGL_PIECE;
-		if (off < CGL_WIN)
-		{
-			/* the source of byte w is w - off: its window slot is overwritten by byte w - off + CGL_WIN > w */
-			cgl_room(L, m);
-			if ((off & 3u) == 0 && m >= 8u)
-			{
-				/* source and target share their alignment: whole words once the target is aligned */
-				uint32_t i = 0;
-				for (; ((L.op + i) & 3u) != 0; i++) L.wb[cgl_at(L.op + i)] = L.wb[cgl_at(L.op + i - off)];
-				for (; i + 4u <= m; i += 4u)
-					*(uint32_t *) (L.wb + cgl_at(L.op + i)) = *(const uint32_t *) (L.wb + cgl_at(L.op + i - off));
-				for (; i < m; i++) L.wb[cgl_at(L.op + i)] = L.wb[cgl_at(L.op + i - off)];
-			}
-			else
-				for (uint32_t i = 0; i < m; i++) L.wb[cgl_at(L.op + i)] = L.wb[cgl_at(L.op + i - off)];
-		}
-		else
-		{
-			/* far match: its source left the window; after the flush it is in dst: the piece reads
-			 * [op - off, op - off + m), m <= CGL_PIECE < off - 15, all below the flushed mark (op & ~15) */
-			cgl_flush(L, L.op);
-			cgl_room(L, m);
-			const uint8_t *from = L.dst + (L.op - off);
-			for (uint32_t i = 0; i < m; i++) L.wb[cgl_at(L.op + i)] = from[i];
-		}
+		cgl_flush(L, L.op);
+		cgl_room(L, m);
+		const uint8_t *from = L.dst + (L.op - off);
+		for (uint32_t i = 0; i < m; i++) L.wb[cgl_at(L.op + i)] = from[i];
 		L.op += m; n -= m;
 	}
 }
@@ -135,6 +228,31 @@ CG_HD bool cgl_decode(Lz4Lane &L, uint32_t padded)
 	if (rawlen == 0 && !(clen == 1 && L.src[0] == 0)) return false;      /* liblz4's rule for an empty output */
 	for (;;)
 	{
+		/*
+		 * The common sequence of a columnar value stream -- up to 5 literal bytes, a match of 4..18 bytes that starts at
+		 * least 8 bytes back and inside the window -- in a handful of word operations: ONE 8-byte load holds the token,
+		 * the literals and the offset; literals and match move 8 bytes at a time (what a copy writes beyond its end is
+		 * overwritten by the next one).  Everything else, and the last 16 bytes of the stream, take the general path.
+		 */
+		while ((ip & ~7u) + 16u <= clen)
+		{
+			const uint64_t v = cgl_load8(L.src + ip);
+			const uint32_t token = (uint32_t) v & 0xffu, lit = token >> 4, mlc = token & 15u;
+			if (lit > 5u || mlc == 15u) break;
+			const uint32_t off = (uint32_t) (v >> (8u * (1u + lit))) & 0xffffu, ml = mlc + 4u;
+			const uint32_t mp = L.op + lit;                         /* where the match starts */
+			if (off < 8u || off > CGL_WIN - CGL_AHEAD || off > mp || lit + ml > rawlen - L.op) break;
+			cgl_room8(L);
+			cgl_win_write8(L, L.op, v >> 8);
+			cgl_win_write8(L, mp, cgl_win_read8(L, mp - off));
+			if (ml > 8u)
+			{
+				cgl_win_write8(L, mp + 8u, cgl_win_read8(L, mp + 8u - off));
+				if (ml > 16u) cgl_win_write8(L, mp + 16u, cgl_win_read8(L, mp + 16u - off));
+			}
+			L.op = mp + ml;
+			ip += 3u + lit;
+		}
 		if (ip >= clen) return false;
 		const uint32_t token = L.src[ip++];
 		uint32_t lit = token >> 4;
