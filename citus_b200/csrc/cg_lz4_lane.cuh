@@ -105,6 +105,23 @@ CG_HD uint64_t cgl_load8(const uint8_t *p)
 #endif
 }
 
+/* the same from the output slot: bytes this lane stored earlier (as 16-byte vectors), hence volatile -- the loads
+ * must neither be moved above those stores nor be served from a stale L1 line */
+CG_HD uint64_t cgl_load8_slot(const uint8_t *p)
+{
+#ifdef __CUDA_ARCH__
+	const unsigned long long a = (unsigned long long) p;
+	const volatile uint64_t *q = (const volatile uint64_t *) (a & ~7ull);
+	const uint32_t sh = (uint32_t) (a & 7ull) * 8u;
+	const uint64_t lo = q[0], hi = q[1];
+	return sh ? (lo >> sh) | (hi << (64u - sh)) : lo;
+#else
+	uint64_t v;
+	memcpy(&v, p, 8);
+	return v;
+#endif
+}
+
 CG_HD uint32_t cgl_word_at(uint32_t pos) { return ((pos & (CGL_WIN - 1u)) >> 2) * (4u * CGL_LANES); }
 
 /* the 8 window bytes at position pos (any alignment) */
@@ -157,6 +174,34 @@ CG_HD void cgl_literals(Lz4Lane &L, uint32_t ip, uint32_t n)
 	}
 }
 
+/* a match whose source is in the window (off <= CGL_WIN - CGL_AHEAD), 8 bytes per step.  A step never reads a byte it
+ * writes when the distance is >= 8.  A shorter distance means the output is periodic with period `off`: the first 8
+ * bytes are the period replicated, and from then on the same bytes are found D = off * ceil(8 / off) >= 8 back (the
+ * periodic region [op - off, op + 8) is off + 8 > D bytes long).  The last step may write beyond the match. */
+CG_HD void cgl_match_win(Lz4Lane &L, uint32_t off, uint32_t n)
+{
+	uint32_t dist = off;
+	if (off < 8u)
+	{
+		cgl_room8(L);
+		uint64_t v = cgl_win_read8(L, L.op - off) & ((1ull << (8u * off)) - 1ull);
+		uint32_t s = 8u * off;
+		v |= v << s; s <<= 1;
+		if (s < 64u) { v |= v << s; s <<= 1; if (s < 64u) v |= v << s; }
+		cgl_win_write8(L, L.op, v);
+		const uint32_t m = n < 8u ? n : 8u;
+		L.op += m; n -= m;
+		dist = off * ((7u + off) / off);
+	}
+	while (n)
+	{
+		const uint32_t m = n < 8u ? n : 8u;
+		cgl_room8(L);
+		cgl_win_write8(L, L.op, cgl_win_read8(L, L.op - dist));
+		L.op += m; n -= m;
+	}
+}
+
 /* n bytes from `off` bytes back (1 <= off <= op), LZ77's overlap rule: byte i is out[op - off + (i mod off)] */
 CG_HD void cgl_match(Lz4Lane &L, uint32_t off, uint32_t n)
 {
@@ -164,53 +209,17 @@ CG_HD void cgl_match(Lz4Lane &L, uint32_t off, uint32_t n)
 	{
 		/* the source of byte w is w - off: its window slot is overwritten by byte w - off + CGL_WIN > w (or by what an
 		 * 8-byte copy left up to CGL_AHEAD bytes beyond its end, hence the margin) */
-		if (off >= 8u)
-		{
-			/* 8 bytes per step never read a byte of the same step; the last step may write beyond the match */
-			while (n)
-			{
-				const uint32_t m = n < 8u ? n : 8u;
-				cgl_room8(L);
-				cgl_win_write8(L, L.op, cgl_win_read8(L, L.op - off));
-				L.op += m; n -= m;
-			}
-			return;
-		}
-		if (off == 1u || off == 2u || off == 4u)
-		{
-			/* a run: the period divides 8, so every 8-byte step stores the same pattern */
-			uint64_t v = cgl_win_read8(L, L.op - off);
-			if (off == 1u) v = (v & 0xffull) * 0x0101010101010101ull;
-			else if (off == 2u) v = (v & 0xffffull) * 0x0001000100010001ull;
-			else v = (v & 0xffffffffull) * 0x0000000100000001ull;
-			while (n)
-			{
-				const uint32_t m = n < 8u ? n : 8u;
-				cgl_room8(L);
-				cgl_win_write8(L, L.op, v);
-				L.op += m; n -= m;
-			}
-			return;
-		}
-		while (n)                                        /* periods 3, 5, 6, 7: byte by byte */
-		{
-			const uint32_t m = n < CGL_PIECE ? n : CGL_PIECE;
-			cgl_room(L, m);
-			for (uint32_t i = 0; i < m; i++) L.wb[cgl_at(L.op + i)] = L.wb[cgl_at(L.op + i - off)];
-			L.op += m; n -= m;
-		}
+		cgl_match_win(L, off, n);
 		return;
 	}
+	/* far match: its source left the window, but it is in the slot once the window is flushed: 8 bytes per step from
+	 * dst (this lane's own earlier stores; one L2 round trip per step).  A step reads [op - off, op - off + 8) with
+	 * off > CGL_WIN - CGL_AHEAD, which lies below the flushed mark as long as op - flushed stays small. */
 	while (n)
 	{
-		/* far match: its source left the window; after the flush it is in dst: the piece reads
-		 * [op - off, op - off + m), m <= CGL_PIECE < off - 15 (off > CGL_WIN - CGL_AHEAD), all below the flushed
-		 * mark (op & ~15) */
-		const uint32_t m = n < CGL_PIECE ? n : CGL_PIECE;
-		cgl_flush(L, L.op);
-		cgl_room(L, m);
-		const uint8_t *from = L.dst + (L.op - off);
-		for (uint32_t i = 0; i < m; i++) L.wb[cgl_at(L.op + i)] = from[i];
+		const uint32_t m = n < 8u ? n : 8u;
+		if (L.op - L.flushed >= 16u) cgl_flush(L, L.op);
+		cgl_win_write8(L, L.op, cgl_load8_slot(L.dst + (L.op - off)));
 		L.op += m; n -= m;
 	}
 }
@@ -229,8 +238,8 @@ CG_HD bool cgl_decode(Lz4Lane &L, uint32_t padded)
 	for (;;)
 	{
 		/*
-		 * The common sequence of a columnar value stream -- up to 5 literal bytes, a match of 4..18 bytes that starts at
-		 * least 8 bytes back and inside the window -- in a handful of word operations: ONE 8-byte load holds the token,
+		 * The common sequence of a columnar value stream -- up to 5 literal bytes and a match of 4..18 bytes -- in a
+		 * handful of word operations: ONE 8-byte load holds the token,
 		 * the literals and the offset; literals and match move 8 bytes at a time (what a copy writes beyond its end is
 		 * overwritten by the next one).  Everything else, and the last 16 bytes of the stream, take the general path.
 		 */
@@ -241,16 +250,11 @@ CG_HD bool cgl_decode(Lz4Lane &L, uint32_t padded)
 			if (lit > 5u || mlc == 15u) break;
 			const uint32_t off = (uint32_t) (v >> (8u * (1u + lit))) & 0xffffu, ml = mlc + 4u;
 			const uint32_t mp = L.op + lit;                         /* where the match starts */
-			if (off < 8u || off > CGL_WIN - CGL_AHEAD || off > mp || lit + ml > rawlen - L.op) break;
+			if (off == 0 || off > mp || lit + ml > rawlen - L.op) break;
 			cgl_room8(L);
 			cgl_win_write8(L, L.op, v >> 8);
-			cgl_win_write8(L, mp, cgl_win_read8(L, mp - off));
-			if (ml > 8u)
-			{
-				cgl_win_write8(L, mp + 8u, cgl_win_read8(L, mp + 8u - off));
-				if (ml > 16u) cgl_win_write8(L, mp + 16u, cgl_win_read8(L, mp + 16u - off));
-			}
-			L.op = mp + ml;
+			L.op = mp;
+			cgl_match(L, off, ml);
 			ip += 3u + lit;
 		}
 		if (ip >= clen) return false;
