@@ -515,16 +515,16 @@ cg_zstd_kernel(uint8_t *arena, const DecodeItem *items, uint32_t nitems, uint8_t
 }
 
 /*
- * LZ4, a lane per stream (cg_lz4_lane.cuh).  One warp per CTA with its 32 KB of interleaved windows; only the first
- * `active` lanes of a warp take a stream: a launch has ~10^4 streams, which is two full warps per SM -- too few to hide
- * the latency of the dependent shared-memory steps of a sequence -- so the streams are spread over more, emptier
- * warps (an idle lane costs nothing, an idle scheduler does).
+ * LZ4, a lane per stream (cg_lz4_lane.cuh).  One warp per CTA; only its first `active` lanes take a stream, and their
+ * windows (CGL_WIN bytes each, interleaved) are the CTA's dynamic shared memory.  Lanes of a warp that are in different
+ * phases of a sequence run one after the other, and a launch has ~10^4 streams against ~9500 warp slots on the GPU:
+ * one stream per warp (active = 1) whenever the streams fit, more per warp only when they do not.
  */
 __global__ void __launch_bounds__(32)
 cg_lz4_lane_kernel(uint8_t *arena, const DecodeItem *items, uint32_t nitems, unsigned long long *err, unsigned long long flag,
 				   uint32_t active)
 {
-	__shared__ __align__(16) uint8_t win[CGL_WIN * CGL_LANES];
+	extern __shared__ __align__(16) uint8_t lane_win[];
 	if (threadIdx.x >= active) return;
 	const uint32_t idx = blockIdx.x * active + threadIdx.x;
 	if (idx >= nitems) return;
@@ -533,7 +533,7 @@ cg_lz4_lane_kernel(uint8_t *arena, const DecodeItem *items, uint32_t nitems, uns
 	Lz4Lane L;
 	L.src = arena + it.src; L.clen = it.comp_len;
 	L.dst = arena + it.dst; L.rawlen = it.raw_len;
-	L.wb = win + 4u * threadIdx.x;
+	L.wb = lane_win + 4u * threadIdx.x; L.wstride = 4u * active;
 	if (!cgl_decode(L, it.padded))
 	{
 		for (uint32_t i = 0; i < it.padded; i++) L.dst[i] = 0;
@@ -542,7 +542,7 @@ cg_lz4_lane_kernel(uint8_t *arena, const DecodeItem *items, uint32_t nitems, uns
 }
 
 static int g_lz4_lanes = -1;
-static int g_lz4_lane_warps = 8;          /* warps per SM the lane kernel spreads a launch over */
+static int g_lz4_lane_warps = 32;         /* warps (= one-warp CTAs) per SM the lane kernel may spread a launch over */
 void cg_decompress_set_lz4_lane_warps(int n) { g_lz4_lane_warps = n < 1 ? 1 : n > 64 ? 64 : n; }
 void cg_decompress_set_lz4_lanes(int on) { g_lz4_lanes = on < 0 ? -1 : (on ? 1 : 0); }      /* < 0: back to the default */
 
@@ -561,11 +561,11 @@ int cg_launch_decompress(CgContext *ctx, uint8_t *arena, const DecodeItem *items
 	}
 	if (any_lz4)
 	{
-		/* about g_lz4_lane_warps (8) warps per SM, 4..32 streams per warp */
-		uint32_t active = 32;
-		while (active > 4 && (nitems + active - 1) / active < (uint64_t) ctx->sm_count * (uint64_t) g_lz4_lane_warps) active >>= 1;
+		/* as few streams per warp as fit into g_lz4_lane_warps (32: the CTA slots of an SM) warps per SM */
+		uint32_t active = 1;
+		while (active < 32 && (nitems + active - 1) / active > (uint64_t) ctx->sm_count * (uint64_t) g_lz4_lane_warps) active <<= 1;
 		const unsigned blocks = (unsigned) ((nitems + active - 1) / active);
-		cg_lz4_lane_kernel<<<blocks, 32, 0, stream>>>(arena, items, (uint32_t) nitems, err, flag, active);
+		cg_lz4_lane_kernel<<<blocks, 32, (size_t) CGL_WIN * active, stream>>>(arena, items, (uint32_t) nitems, err, flag, active);
 		CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	}
 	if (any_lz)

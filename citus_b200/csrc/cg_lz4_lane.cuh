@@ -12,9 +12,11 @@
  * coordinate lanes that have nothing to copy.  Here a warp instruction advances 32 streams, nothing is
  * coordinated, and an overlapping match is an ordinary sequential copy.
  *
- * The last CGL_WIN decoded bytes of a stream live in a window in shared memory; windows of the 32 lanes are
- * interleaved word by word (word w of lane l at [w * 32 + l]): lanes that work at the same position of their
- * streams -- the common case, the streams of a launch are alike -- hit 32 different banks.  A match that reaches
+ * The last CGL_WIN decoded bytes of a stream live in a window in shared memory; the windows of the lanes of a warp
+ * that decode are interleaved word by word (word w of lane l at [w * lanes + l]): lanes that work at the same position
+ * of their streams hit different banks.  How many lanes of a warp decode is the launch's choice (cg_decompress.cu):
+ * lanes of one warp that are in different phases of a sequence execute one after the other, so when a launch has
+ * fewer streams than the GPU has warp slots, one stream per warp is fastest.  A match that reaches
  * back further than the window reads the arena (behind a flush).  The window leaves for the arena in aligned
  * 16-byte stores.
  */
@@ -45,16 +47,15 @@ struct Lz4Lane
 	uint32_t clen;
 	uint8_t *dst;               /* 16-byte aligned slot of `padded` bytes */
 	uint32_t rawlen;
-	uint8_t *wb;                /* window: byte b of the lane's word w is wb[w * 4 * CGL_LANES + b] */
+	uint8_t *wb;                /* window: byte b of the lane's word w is wb[w * wstride + b] */
+	uint32_t wstride;           /* 4 * (number of lanes whose windows are interleaved) */
 	uint32_t op;                /* bytes decoded */
 	uint32_t flushed;           /* bytes already in dst (multiple of 16) */
 	uint32_t zero_offset;       /* out: the stream was refused because a match has offset 0 (see cgl_decode) */
 };
 
-CG_HD uint32_t cgl_at(uint32_t pos)
-{
-	return ((pos & (CGL_WIN - 1u)) >> 2) * (4u * CGL_LANES) + (pos & 3u);
-}
+#define cgl_at(pos) ((((pos) & (CGL_WIN - 1u)) >> 2) * L.wstride + ((pos) & 3u))
+#define cgl_word_at(pos) ((((pos) & (CGL_WIN - 1u)) >> 2) * L.wstride)
 
 /* window -> dst for [flushed, upto rounded down to 16) */
 CG_HD void cgl_flush(Lz4Lane &L, uint32_t upto)
@@ -122,7 +123,6 @@ CG_HD uint64_t cgl_load8_slot(const uint8_t *p)
 #endif
 }
 
-CG_HD uint32_t cgl_word_at(uint32_t pos) { return ((pos & (CGL_WIN - 1u)) >> 2) * (4u * CGL_LANES); }
 
 /* the 8 window bytes at position pos (any alignment) */
 CG_HD uint64_t cgl_win_read8(const Lz4Lane &L, uint32_t pos)

@@ -12,7 +12,7 @@ extern "C" int lz4_lane_decode_host(const unsigned char *src, unsigned len, unsi
 	unsigned char *win = (unsigned char *) malloc(CGL_WIN * CGL_LANES);
 	for (unsigned i = 0; i < CGL_WIN * CGL_LANES; i++) win[i] = 0xA5;       /* stale bytes must never be read */
 	Lz4Lane L;
-	L.src = src; L.clen = len; L.dst = dst; L.rawlen = rawlen; L.wb = win + 4u * (lane % CGL_LANES);
+	L.src = src; L.clen = len; L.dst = dst; L.rawlen = rawlen; L.wb = win + 4u * (lane % CGL_LANES); L.wstride = 4u * CGL_LANES;
 	const bool ok = cgl_decode(L, padded);
 	free(win);
 	return ok ? 1 : (L.zero_offset ? -1 : 0);       /* -1: refused for a match with offset 0 */

@@ -55,7 +55,7 @@ int main(int argc, char **argv)
 		unsigned char *ref = (unsigned char *) malloc(expect + 1);
 		memset(win, 0xA5, CGL_WIN * CGL_LANES);
 		Lz4Lane L;
-		L.src = src; L.clen = (uint32_t) len; L.dst = dst; L.rawlen = (uint32_t) expect; L.wb = win + 4u * (rand() % CGL_LANES);
+		L.src = src; L.clen = (uint32_t) len; L.dst = dst; L.rawlen = (uint32_t) expect; { const unsigned lanes = 1u << (rand() % 6); L.wstride = 4u * lanes; L.wb = win + 4u * (rand() % lanes); }
 		bool good = cgl_decode(L, padded);
 		int r = dec((const char *) src, (char *) ref, len, expect);
 		bool ref_good = r == expect;

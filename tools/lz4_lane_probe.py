@@ -36,8 +36,9 @@ cg.set_writer_compression("lz4")
 rels = {s: cg.Relation.generate(list(bench.C2_COLUMNS), 31_250_000, seed=bench.SEED, first_row=s * 31_250_000,
                                 stripe_row_limit=bench.STRIPE_ROWS, chunk_row_limit=bench.CHUNK_ROWS, nthreads=32) for s in range(2)}
 cg.set_writer_compression("none")
-# launch order (two launches each): groups, lanes at 8 warps/SM, groups, lanes at 8, then lanes at 2, 4, 16 warps/SM
-for mode, warps in ((0, 8), (1, 8), (0, 8), (1, 8), (1, 2), (1, 4), (1, 16)):
+# launch order (ten launches each): groups, lanes at <= 32 warps/SM (one stream per warp here), then 6 (4 streams per
+# warp), 3 (8 per warp), 1 (32 per warp)
+for mode, warps in ((0, 32), (1, 32), (1, 6), (1, 3), (1, 1)):
     cg.set_option("lz4_lanes", mode)
     cg.set_option("lz4_lane_warps", warps)
     for s in rels:
