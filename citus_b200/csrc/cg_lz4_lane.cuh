@@ -34,7 +34,7 @@
 #endif
 #endif
 
-#define CGL_WIN 1024u           /* bytes of window per lane */
+#define CGL_WIN 2048u           /* bytes of window per lane */
 #define CGL_PIECE 256u          /* a copy advances in pieces of at most this many bytes; < CGL_WIN - 16 */
 #define CGL_LANES 32u
 #define CGL_AHEAD 48u           /* the 8-byte copies may leave up to this many bytes of garbage beyond `op`: they land

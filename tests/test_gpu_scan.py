@@ -388,20 +388,22 @@ def test_compressed_chunks(cg, oracle, comp, path, lz4_kernel):
 
 @pytest.mark.parametrize("lz4_kernel", ["lanes", "groups"], indirect=True)
 def test_lz4_matches_beyond_the_window(cg, oracle, lz4_kernel):
-    """value streams whose matches reach back 1.6 KB, 40 KB and (int2) 8 KB -- beyond the 1 KB window of the
-    lane-per-stream decoder and the 2 KB window of the eight-lane one -- next to streams of one long overlapping match"""
+    """value streams whose matches reach back 1.6 KB, 40 KB and (int2) 8 KB -- beyond the 2 KB windows of both
+    LZ4 decoders -- next to streams of one long overlapping match"""
     if not oracle.lib().orc_have_lz4():
         pytest.skip("liblz4 missing")
     rng = np.random.default_rng(11)
     n = 70_001
     base200, base5000 = rng.integers(-2**40, 2**40, 200), rng.integers(-2**40, 2**40, 5000)
     cols = [
-        (base200[np.arange(n) % 200], 8, None),                          # period 1600 bytes
+        (base200[np.arange(n) % 200], 8, None),                          # period 1600 bytes (inside the window)
+        (base5000[np.arange(n) % 255], 8, None),                         # period 2040 bytes (just beyond the reach of 2000)
         (base5000[np.arange(n) % 5000], 8, None),                        # period 40000 bytes
         (rng.integers(-30000, 30000, 4_000).astype(np.int64)[np.arange(n) % 4_000], 2, None),     # period 8000 bytes
         (np.zeros(n, np.int64), 8, None),                                # one match over the whole stream
         (rng.integers(0, 50, n), 8, (rng.random(n) < 0.3)),
     ]
+    cols = cols[:1] + cols[2:] + cols[1:2]          # the extra column goes last: the queries below address columns 0..4
     t = oracle.Table([c[1] for c in cols], stripe_row_limit=30_000, chunk_row_limit=10_000, compression=oracle.COMP_LZ4)
     t.insert([c[0] for c in cols], [None if c[2] is None else c[2].astype(np.uint8) for c in cols])
     rel = cg.Relation.from_image(t.pages(), t.stripes_array(), t.nodes_array(), [c[1] for c in cols])
@@ -409,7 +411,7 @@ def test_lz4_matches_beyond_the_window(cg, oracle, lz4_kernel):
         run_both(cg, oracle, rel, quals=[(4, "<", 25)], group_cols=[4],
                  aggs=[cg.count_star(), cg.sum_(0), cg.sum_(1), cg.sum_(2), cg.sum_(3), cg.min_(1), cg.max_(0)],
                  chunk_row_limit=10_000, e2e=e2e)
-        run_both(cg, oracle, rel, aggs=[cg.count_star(), cg.sum_(0), cg.sum_(1), cg.sum_(2), cg.count(4)], chunk_row_limit=10_000, e2e=e2e)
+        run_both(cg, oracle, rel, aggs=[cg.count_star(), cg.sum_(0), cg.sum_(1), cg.sum_(2), cg.count(4), cg.sum_(5)], chunk_row_limit=10_000, e2e=e2e)
 
 
 @pytest.mark.parametrize("comp,lz4_kernel", [("lz4", "lanes"), ("lz4", "groups"), ("pglz", "lanes"), ("zstd", "lanes")],

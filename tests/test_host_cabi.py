@@ -294,7 +294,7 @@ def _lz4_lane_decode(lib, comp, rawlen, lane=0, slack=48):
 def test_lz4_lane_decoder_against_liblz4(oracle, lz4_lane_host):
     """cg_lz4_lane.cuh is sequential code one GPU lane runs per value stream; the same source is executed here against
     streams produced by liblz4's LZ4_compress_default (what the reference's CompressBuffer calls): literal runs and
-    matches of every length class, offsets inside and beyond the 1 KB window, overlapping matches, stream sizes around
+    matches of every length class, offsets inside and beyond the 2 KB window, overlapping matches, stream sizes around
     the window / piece / 16-byte flush boundaries; truncated and damaged streams are rejected or decode to the wrong
     bytes of the right size only where liblz4 itself would"""
     if not oracle.lib().orc_have_lz4():
@@ -303,7 +303,9 @@ def test_lz4_lane_decoder_against_liblz4(oracle, lz4_lane_host):
     cases = {
         "empty": b"", "one byte": b"x", "15 bytes": bytes(range(15)), "zeros 100k": bytes(100_000),
         "period 3": (b"abc" * 40_000)[:100_000], "period 1021 (beyond the window)": bytes(rng.integers(0, 256, 1021, dtype=np.uint8)) * 90,
-        "period 1024": bytes(rng.integers(0, 256, 1024, dtype=np.uint8)) * 90, "period 5000": bytes(rng.integers(0, 256, 5000, dtype=np.uint8)) * 20,
+        "period 1024": bytes(rng.integers(0, 256, 1024, dtype=np.uint8)) * 90,
+        **{f"period {p} (around the window's reach)": bytes(rng.integers(0, 256, p, dtype=np.uint8)) * 40 for p in (1999, 2000, 2001, 2047, 2048, 2049)},
+        "period 5000": bytes(rng.integers(0, 256, 5000, dtype=np.uint8)) * 20,
         "period 60000 (max offsets)": bytes(rng.integers(0, 256, 60_000, dtype=np.uint8)) * 3,
         "C2 key column": rng.integers(0, 10**6, 10_000).astype(np.int64).tobytes(),
         "C2 f column": rng.integers(0, 100, 10_000).astype(np.int64).tobytes(),
@@ -314,7 +316,7 @@ def test_lz4_lane_decoder_against_liblz4(oracle, lz4_lane_host):
         "runs": np.repeat(rng.integers(0, 100, 200), 500).astype(np.int8).tobytes(),
         "sorted ids": np.arange(10_000, dtype=np.int64).tobytes(),
     }
-    for n in (2, 3, 12, 13, 16, 17, 31, 255, 256, 257, 270, 271, 272, 1008, 1023, 1024, 1025, 1039, 1040, 1041, 1279, 1280, 1281,
+    for n in (2, 3, 12, 13, 16, 17, 31, 255, 256, 257, 270, 271, 272, 1008, 1023, 1024, 1025, 1039, 1040, 1041, 1279, 1280, 1281, 2000, 2047, 2048, 2049, 2063, 2064, 2065, 2303, 2304,
               4095, 4096, 65_535, 65_536, 65_537, 80_000):
         cases[f"mixed n={n}"] = (rng.integers(0, 50, n) * rng.integers(0, 2, n)).astype(np.uint8).tobytes()
         cases[f"sparse n={n}"] = (rng.integers(0, 256, n) * (rng.integers(0, 40, n) == 0)).astype(np.uint8).tobytes()
