@@ -515,30 +515,46 @@ cg_zstd_kernel(uint8_t *arena, const DecodeItem *items, uint32_t nitems, uint8_t
 }
 
 /*
- * LZ4, a lane per stream (cg_lz4_lane.cuh).  Two warps per CTA (an SM holds 32 CTAs but 64 warps); only the first
- * `active` lanes of a warp take a stream, and their windows (CGL_WIN bytes each, interleaved) are the CTA's dynamic
- * shared memory.  Lanes of a warp that are in different phases of a sequence run one after the other -- measured on 1875
- * streams of 80 KB: 5.2 ms with one stream per warp, 9.5 ms with four, 17.4 ms with eight, 39 ms with 32 (the
- * eight-lanes-per-stream kernel: 10.4 ms) -- and a shard has ~10^4 streams against 9472 warp slots on the GPU: one
- * stream per warp whenever the streams fit, more per warp only when they do not.
+ * LZ4, a lane per stream (cg_lz4_lane.cuh).  CGL_CTA_WARPS warps per CTA; the first `active` lanes of a warp take a
+ * stream each, and their windows (CGL_WIN bytes each, interleaved) are the CTA's dynamic shared memory.
+ *
+ * What was measured on 1875 streams of 80 KB (profiles/README.md): lanes that each run their whole stream drift apart,
+ * a warp then executes them one after the other -- 5.1 ms with one stream per warp, 9.4 ms with four, 17 ms with eight,
+ * 39 ms with 32 (the eight-lanes-per-stream kernel: 10.4 ms) -- and one stream per warp, the fastest of those, leaves
+ * 31 of 32 SIMD lanes idle: a whole shard (9375 streams = 63 warps per SM) is then bound by instruction issue at 16 ms.
+ * Hence the step form: every lane decodes ONE sequence, then the warp re-converges (__syncwarp), so that the lanes
+ * execute the common path of a sequence together.
  */
-#define CGL_CTA_WARPS 2u
+#define CGL_CTA_WARPS 1u
 __global__ void __launch_bounds__(CGL_CTA_WARPS * 32)
 cg_lz4_lane_kernel(uint8_t *arena, const DecodeItem *items, uint32_t nitems, unsigned long long *err, unsigned long long flag,
-				   uint32_t active)
+				   uint32_t active, int lockstep)
 {
 	extern __shared__ __align__(16) uint8_t lane_win[];
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-	if (lane >= active) return;
 	const uint32_t idx = (blockIdx.x * CGL_CTA_WARPS + warp) * active + lane;
-	if (idx >= nitems) return;
-	const DecodeItem it = items[idx];
-	if (it.kind != CG_COMPRESSION_LZ4) return;
+	DecodeItem it;
+	memset(&it, 0, sizeof it);
+	it.kind = 0xffffffffu;
+	if (lane < active && idx < nitems) it = items[idx];
+	const bool mine = it.kind == CG_COMPRESSION_LZ4;
 	Lz4Lane L;
 	L.src = arena + it.src; L.clen = it.comp_len;
 	L.dst = arena + it.dst; L.rawlen = it.raw_len;
-	L.wb = lane_win + (size_t) warp * CGL_WIN * active + 4u * lane; L.wstride = 4u * active;
-	if (!cgl_decode(L, it.padded))
+	L.wb = lane_win + (size_t) warp * CGL_WIN * active + 4u * (lane < active ? lane : 0u); L.wstride = 4u * active;
+	int st = mine ? cgl_begin(L) : CGL_DONE;
+	if (lockstep)
+	{
+		while (__any_sync(0xffffffffu, st == CGL_MORE))
+		{
+			if (st == CGL_MORE) st = cgl_step(L);
+			__syncwarp();
+		}
+	}
+	else
+		while (st == CGL_MORE) st = cgl_step(L);
+	if (!mine) return;
+	if (!(st == CGL_DONE && cgl_finish(L, it.padded)))
 	{
 		for (uint32_t i = 0; i < it.padded; i++) L.dst[i] = 0;
 		atomicOr(err, flag);
@@ -546,8 +562,8 @@ cg_lz4_lane_kernel(uint8_t *arena, const DecodeItem *items, uint32_t nitems, uns
 }
 
 static int g_lz4_lanes = -1;
-static int g_lz4_lane_warps = 64;         /* warps per SM the lane kernel may spread a launch over */
-void cg_decompress_set_lz4_lane_warps(int n) { g_lz4_lane_warps = n < 1 ? 1 : n > 64 ? 64 : n; }
+static int g_lz4_lane_warps = 0;          /* > 0: as few streams per warp as fit into that many warps per SM, each lane on its own; 0: 32 streams per warp in step */
+void cg_decompress_set_lz4_lane_warps(int n) { g_lz4_lane_warps = n < 0 ? 0 : n > 64 ? 64 : n; }
 void cg_decompress_set_lz4_lanes(int on) { g_lz4_lanes = on < 0 ? -1 : (on ? 1 : 0); }      /* < 0: back to the default */
 
 /* h_items: the host copy of the same items (which kernels are needed) */
@@ -565,9 +581,14 @@ int cg_launch_decompress(CgContext *ctx, uint8_t *arena, const DecodeItem *items
 	}
 	if (any_lz4)
 	{
-		/* as few streams per warp as fit into g_lz4_lane_warps (64: all warp slots of an SM) warps per SM */
-		uint32_t active = 1;
-		while (active < 32 && (nitems + active - 1) / active > (uint64_t) ctx->sm_count * (uint64_t) g_lz4_lane_warps) active <<= 1;
+		uint32_t active = 32;
+		int lockstep = 1;
+		if (g_lz4_lane_warps > 0)
+		{
+			/* (probe) as few streams per warp as fit into g_lz4_lane_warps warps per SM, every lane on its own */
+			active = 1; lockstep = 0;
+			while (active < 32 && (nitems + active - 1) / active > (uint64_t) ctx->sm_count * (uint64_t) g_lz4_lane_warps) active <<= 1;
+		}
 		const uint64_t per_cta = (uint64_t) CGL_CTA_WARPS * active;
 		const unsigned blocks = (unsigned) ((nitems + per_cta - 1) / per_cta);
 		const size_t smem = (size_t) CGL_WIN * active * CGL_CTA_WARPS;
@@ -577,7 +598,7 @@ int cg_launch_decompress(CgContext *ctx, uint8_t *arena, const DecodeItem *items
 			CG_CUDA(cudaFuncSetAttribute(cg_lz4_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (CGL_WIN * 32u * CGL_CTA_WARPS)));
 			configured = true;
 		}
-		cg_lz4_lane_kernel<<<blocks, CGL_CTA_WARPS * 32, smem, stream>>>(arena, items, (uint32_t) nitems, err, flag, active);
+		cg_lz4_lane_kernel<<<blocks, CGL_CTA_WARPS * 32, smem, stream>>>(arena, items, (uint32_t) nitems, err, flag, active, lockstep);
 		CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	}
 	if (any_lz)

@@ -49,6 +49,7 @@ struct Lz4Lane
 	uint32_t rawlen;
 	uint8_t *wb;                /* window: byte b of the lane's word w is wb[w * wstride + b] */
 	uint32_t wstride;           /* 4 * (number of lanes whose windows are interleaved) */
+	uint32_t ip;                /* bytes of the stream consumed */
 	uint32_t op;                /* bytes decoded */
 	uint32_t flushed;           /* bytes already in dst (multiple of 16) */
 	uint32_t zero_offset;       /* out: the stream was refused because a match has offset 0 (see cgl_decode) */
@@ -224,82 +225,110 @@ CG_HD void cgl_match(Lz4Lane &L, uint32_t off, uint32_t n)
 	}
 }
 
-/* true: the slot holds exactly rawlen decoded bytes followed by zeros up to `padded`.  false: malformed stream
- * (nothing outside the slot was written; the caller zero-fills it).  Agrees with LZ4_decompress_safe on every
- * stream (tools/lz4_lane_fuzz.cpp) except one kind of damage: a match with offset 0, which liblz4 1.9 "decodes" to
- * whatever the output buffer held before the call and which is refused here. */
-CG_HD bool cgl_decode(Lz4Lane &L, uint32_t padded)
+/*
+ * The decoder as a state machine, one sequence per step, so that the lanes of a warp can take their steps together
+ * (cg_lz4_lane_kernel re-converges them after every step; the host tests just loop).
+ *   cgl_begin   CGL_MORE, or CGL_BAD for a stream that cannot be valid
+ *   cgl_step    one sequence: CGL_MORE, CGL_DONE after the last one, CGL_BAD
+ *   cgl_finish  after CGL_DONE: true when exactly rawlen bytes came out; the window's rest and the padding are written
+ * Agrees with LZ4_decompress_safe on every stream (tools/lz4_lane_fuzz.cpp) except one kind of damage: a match with
+ * offset 0, which liblz4 1.9 "decodes" to whatever the output buffer held before the call and which is refused here.
+ */
+#define CGL_MORE 0
+#define CGL_DONE 1
+#define CGL_BAD (-1)
+
+CG_HD int cgl_begin(Lz4Lane &L)
 {
-	uint32_t ip = 0;
+	L.ip = 0; L.op = 0; L.flushed = 0; L.zero_offset = 0;
+	if (L.clen == 0) return CGL_BAD;
+	if (L.rawlen == 0 && !(L.clen == 1 && L.src[0] == 0)) return CGL_BAD;      /* liblz4's rule for an empty output */
+	return CGL_MORE;
+}
+
+CG_HD int cgl_step(Lz4Lane &L)
+{
+	uint32_t ip = L.ip;
 	const uint32_t clen = L.clen, rawlen = L.rawlen;
-	L.op = 0; L.flushed = 0; L.zero_offset = 0;
-	if (clen == 0) return false;
-	if (rawlen == 0 && !(clen == 1 && L.src[0] == 0)) return false;      /* liblz4's rule for an empty output */
-	for (;;)
+	/*
+	 * The common sequence of a columnar value stream -- up to 5 literal bytes and a match of 4..18 bytes -- in a
+	 * handful of word operations: ONE 8-byte load holds the token, the literals and the offset; literals and match move
+	 * 8 bytes at a time (what a copy writes beyond its end is overwritten by the next one).  Everything else, and the
+	 * last 16 bytes of the stream, take the general path below.
+	 */
+	if ((ip & ~7u) + 16u <= clen)
 	{
-		/*
-		 * The common sequence of a columnar value stream -- up to 5 literal bytes and a match of 4..18 bytes -- in a
-		 * handful of word operations: ONE 8-byte load holds the token,
-		 * the literals and the offset; literals and match move 8 bytes at a time (what a copy writes beyond its end is
-		 * overwritten by the next one).  Everything else, and the last 16 bytes of the stream, take the general path.
-		 */
-		while ((ip & ~7u) + 16u <= clen)
+		const uint64_t v = cgl_load8(L.src + ip);
+		const uint32_t token = (uint32_t) v & 0xffu, lit = token >> 4, mlc = token & 15u;
+		const uint32_t off = (uint32_t) (v >> (8u * (1u + (lit <= 5u ? lit : 0u)))) & 0xffffu, ml = mlc + 4u;
+		const uint32_t mp = L.op + lit;                         /* where the match starts */
+		if (lit <= 5u && mlc != 15u && off != 0 && off <= mp && lit + ml <= rawlen - L.op)
 		{
-			const uint64_t v = cgl_load8(L.src + ip);
-			const uint32_t token = (uint32_t) v & 0xffu, lit = token >> 4, mlc = token & 15u;
-			if (lit > 5u || mlc == 15u) break;
-			const uint32_t off = (uint32_t) (v >> (8u * (1u + lit))) & 0xffffu, ml = mlc + 4u;
-			const uint32_t mp = L.op + lit;                         /* where the match starts */
-			if (off == 0 || off > mp || lit + ml > rawlen - L.op) break;
 			cgl_room8(L);
 			cgl_win_write8(L, L.op, v >> 8);
 			L.op = mp;
 			cgl_match(L, off, ml);
-			ip += 3u + lit;
+			L.ip = ip + 3u + lit;
+			return CGL_MORE;
 		}
-		if (ip >= clen) return false;
-		const uint32_t token = L.src[ip++];
-		uint32_t lit = token >> 4;
-		if (lit == 15u)
-		{
-			uint32_t b;
-			do
-			{
-				if (ip >= clen) return false;
-				b = L.src[ip++];
-				lit += b;
-				if (lit > rawlen) return false;
-			} while (b == 255u);
-		}
-		if (lit > clen - ip || lit > rawlen - L.op) return false;
-		cgl_literals(L, ip, lit);
-		ip += lit;
-		if (ip == clen) break;                       /* the last sequence stops after its literals */
-		if (clen - ip < 2u) return false;
-		const uint32_t off = (uint32_t) L.src[ip] | ((uint32_t) L.src[ip + 1] << 8);
-		ip += 2;
-		uint32_t ml = token & 15u;
-		if (ml == 15u)
-		{
-			uint32_t b;
-			do
-			{
-				if (ip >= clen) return false;
-				b = L.src[ip++];
-				ml += b;
-				if (ml > rawlen) return false;
-			} while (b == 255u);
-		}
-		ml += 4u;
-		if (off == 0) L.zero_offset = 1;
-		if (off == 0 || off > L.op || ml > rawlen - L.op) return false;
-		cgl_match(L, off, ml);
 	}
-	if (L.op != rawlen) return false;
+	if (ip >= clen) return CGL_BAD;
+	const uint32_t token = L.src[ip++];
+	uint32_t lit = token >> 4;
+	if (lit == 15u)
+	{
+		uint32_t b;
+		do
+		{
+			if (ip >= clen) return CGL_BAD;
+			b = L.src[ip++];
+			lit += b;
+			if (lit > rawlen) return CGL_BAD;
+		} while (b == 255u);
+	}
+	if (lit > clen - ip || lit > rawlen - L.op) return CGL_BAD;
+	cgl_literals(L, ip, lit);
+	ip += lit;
+	if (ip == clen) { L.ip = ip; return CGL_DONE; }     /* the last sequence stops after its literals */
+	if (clen - ip < 2u) return CGL_BAD;
+	const uint32_t off = (uint32_t) L.src[ip] | ((uint32_t) L.src[ip + 1] << 8);
+	ip += 2;
+	uint32_t ml = token & 15u;
+	if (ml == 15u)
+	{
+		uint32_t b;
+		do
+		{
+			if (ip >= clen) return CGL_BAD;
+			b = L.src[ip++];
+			ml += b;
+			if (ml > rawlen) return CGL_BAD;
+		} while (b == 255u);
+	}
+	ml += 4u;
+	if (off == 0) L.zero_offset = 1;
+	if (off == 0 || off > L.op || ml > rawlen - L.op) return CGL_BAD;
+	cgl_match(L, off, ml);
+	L.ip = ip;
+	return CGL_MORE;
+}
+
+CG_HD bool cgl_finish(Lz4Lane &L, uint32_t padded)
+{
+	if (L.op != L.rawlen) return false;
 	cgl_flush(L, L.op);
-	for (uint32_t i = L.flushed; i < rawlen; i++) L.dst[i] = L.wb[cgl_at(i)];
-	for (uint32_t i = rawlen; i < padded; i++) L.dst[i] = 0;
+	for (uint32_t i = L.flushed; i < L.rawlen; i++) L.dst[i] = L.wb[cgl_at(i)];
+	for (uint32_t i = L.rawlen; i < padded; i++) L.dst[i] = 0;
 	return true;
+}
+
+/* the whole stream on one lane.  true: the slot holds exactly rawlen decoded bytes followed by zeros up to `padded`;
+ * false: malformed stream (nothing outside the slot was written; the caller zero-fills it) */
+CG_HD bool cgl_decode(Lz4Lane &L, uint32_t padded)
+{
+	int st = cgl_begin(L);
+	while (st == CGL_MORE) st = cgl_step(L);
+	return st == CGL_DONE && cgl_finish(L, padded);
 }
 
 #endif
