@@ -48,7 +48,8 @@
 #define CGD_RING 256u
 #define CGD_WIN 2048u
 #define CGD_CHUNK 256u
-#define CG_LZ4_LANES_DEFAULT 0      /* cg_set_option("lz4_lanes", 1) / CG_LZ4_LANES=1: the lane-per-stream LZ4 kernel */
+#define CG_LZ4_LANES_DEFAULT 2      /* 2 = by launch size (see cg_lz4_lane_kernel); cg_set_option("lz4_lanes", 1 / 0) / CG_LZ4_LANES force one kernel */
+#define CG_LZ4_LANES_MAX_WARPS_PER_SM 16
 
 struct Stream
 {
@@ -515,15 +516,19 @@ cg_zstd_kernel(uint8_t *arena, const DecodeItem *items, uint32_t nitems, uint8_t
 }
 
 /*
- * LZ4, a lane per stream (cg_lz4_lane.cuh).  CGL_CTA_WARPS warps per CTA; the first `active` lanes of a warp take a
- * stream each, and their windows (CGL_WIN bytes each, interleaved) are the CTA's dynamic shared memory.
+ * LZ4, a lane per stream (cg_lz4_lane.cuh).  One warp per CTA; the first `active` lanes of the warp take a stream each,
+ * and their windows (CGL_WIN bytes each, interleaved) are the CTA's dynamic shared memory.
  *
- * What was measured on 1875 streams of 80 KB (profiles/README.md): lanes that each run their whole stream drift apart,
- * a warp then executes them one after the other -- 5.1 ms with one stream per warp, 9.4 ms with four, 17 ms with eight,
- * 39 ms with 32 (the eight-lanes-per-stream kernel: 10.4 ms) -- and one stream per warp, the fastest of those, leaves
- * 31 of 32 SIMD lanes idle: a whole shard (9375 streams = 63 warps per SM) is then bound by instruction issue at 16 ms.
- * Hence the step form: every lane decodes ONE sequence, then the warp re-converges (__syncwarp), so that the lanes
- * execute the common path of a sequence together.
+ * What was measured on launches of 1875 streams of 80 KB (one block of a shard; profiles/README.md):
+ *   eight lanes per stream (cg_decompress_kernel)             10.4 ms
+ *   a lane per stream, one stream per warp                      5.1 ms   <- the form used for launches of this size
+ *   ..., 4 / 8 / 32 streams per warp, every lane on its own    9.4 / 17 / 39 ms (lanes drift apart; a warp runs them
+ *                                                              one after the other)
+ *   ..., 32 streams per warp, re-converged after every sequence 21 ms (the branches of a step still run one after
+ *                                                              the other, each with its own load latencies)
+ * and on a whole shard in one launch (9375 streams, the DMA path): one stream per warp is 63 warps per SM with 31 of 32
+ * SIMD lanes idle -- bound by instruction issue at ~16 ms against 10.4 ms for the eight-lane kernel.  So: the lane
+ * kernel for launches of up to 16 warps per SM, the eight-lane kernel above that ("lz4_lanes" -1, the default).
  */
 #define CGL_CTA_WARPS 1u
 __global__ void __launch_bounds__(CGL_CTA_WARPS * 32)
@@ -562,30 +567,31 @@ cg_lz4_lane_kernel(uint8_t *arena, const DecodeItem *items, uint32_t nitems, uns
 }
 
 static int g_lz4_lanes = -1;
-static int g_lz4_lane_warps = 0;          /* > 0: as few streams per warp as fit into that many warps per SM, each lane on its own; 0: 32 streams per warp in step */
+static int g_lz4_lane_warps = 64;         /* > 0: as few streams per warp as fit into that many warps per SM, each lane on its own; 0: 32 streams per warp in step (probe) */
 void cg_decompress_set_lz4_lane_warps(int n) { g_lz4_lane_warps = n < 0 ? 0 : n > 64 ? 64 : n; }
-void cg_decompress_set_lz4_lanes(int on) { g_lz4_lanes = on < 0 ? -1 : (on ? 1 : 0); }      /* < 0: back to the default */
+void cg_decompress_set_lz4_lanes(int on) { g_lz4_lanes = on < 0 ? -1 : (on > 1 ? 2 : on); }      /* < 0: back to the default */
 
 /* h_items: the host copy of the same items (which kernels are needed) */
 int cg_launch_decompress(CgContext *ctx, uint8_t *arena, const DecodeItem *items, const DecodeItem *h_items, uint64_t nitems,
 						 unsigned long long *err, unsigned long long flag, cudaStream_t stream)
 {
 	if (nitems == 0) return CG_OK;
-	if (g_lz4_lanes < 0) { const char *e = getenv("CG_LZ4_LANES"); g_lz4_lanes = e ? (atoi(e) ? 1 : 0) : CG_LZ4_LANES_DEFAULT; }
+	if (g_lz4_lanes < 0) { const char *e = getenv("CG_LZ4_LANES"); g_lz4_lanes = e ? atoi(e) : CG_LZ4_LANES_DEFAULT; if (g_lz4_lanes < 0 || g_lz4_lanes > 2) g_lz4_lanes = CG_LZ4_LANES_DEFAULT; }
+	const int use_lanes = g_lz4_lanes == 2 ? (nitems <= (uint64_t) ctx->sm_count * CG_LZ4_LANES_MAX_WARPS_PER_SM ? 1 : 0) : g_lz4_lanes;
 	bool any_lz = false, any_zstd = false, any_lz4 = false;
 	for (uint64_t i = 0; i < nitems; i++)
 	{
 		if (h_items[i].kind == CG_COMPRESSION_ZSTD) any_zstd = true;
-		else if (h_items[i].kind == CG_COMPRESSION_LZ4 && g_lz4_lanes) any_lz4 = true;
+		else if (h_items[i].kind == CG_COMPRESSION_LZ4 && use_lanes) any_lz4 = true;
 		else any_lz = true;
 	}
 	if (any_lz4)
 	{
 		uint32_t active = 32;
-		int lockstep = 1;
+		int lockstep = 1;                         /* g_lz4_lane_warps == 0 (probe): 32 streams per warp, in step */
 		if (g_lz4_lane_warps > 0)
 		{
-			/* (probe) as few streams per warp as fit into g_lz4_lane_warps warps per SM, every lane on its own */
+			/* as few streams per warp as fit into g_lz4_lane_warps warps per SM, every lane on its own */
 			active = 1; lockstep = 0;
 			while (active < 32 && (nitems + active - 1) / active > (uint64_t) ctx->sm_count * (uint64_t) g_lz4_lane_warps) active <<= 1;
 		}
@@ -605,7 +611,7 @@ int cg_launch_decompress(CgContext *ctx, uint8_t *arena, const DecodeItem *items
 	{
 		const unsigned per_block = CGD_WARPS * CGD_GROUPS;
 		unsigned blocks = (unsigned) ((nitems + per_block - 1) / per_block);
-		cg_decompress_kernel<<<blocks, CGD_WARPS * 32, 0, stream>>>(arena, items, (uint32_t) nitems, err, flag, g_lz4_lanes);
+		cg_decompress_kernel<<<blocks, CGD_WARPS * 32, 0, stream>>>(arena, items, (uint32_t) nitems, err, flag, use_lanes);
 		CG_CUDA(cudaGetLastError()); g_cg_launches++;
 	}
 	if (any_zstd)

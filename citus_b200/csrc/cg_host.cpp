@@ -852,7 +852,7 @@ static bool cg_force_general(void)
 /* run-time switches (the same ones the CG_* environment variables set at first use): which kernel family
  * scans -- "jit" 0 = ahead-of-time kernels only, 1 = plan-specialised where no ahead-of-time specialisation
  * applies (default), 2 = always; "force_general" 1 = the interpretive kernels for everything; "lz4_lanes" 1 / 0 = LZ4 value
- * streams are decoded a lane per stream / eight lanes per stream; "peer_window" 0 = the
+ * streams are decoded a lane per stream / eight lanes per stream, 2 or < 0 = by launch size (default); "peer_window" 0 = the
  * combine and the repartition exchange stay on NCCL instead of the IPC-mapped peer window (set it on every rank) */
 extern "C" int cg_set_option(const char *name, int64_t value)
 {

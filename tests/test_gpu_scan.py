@@ -358,13 +358,13 @@ def _compressed_relation(cg, oracle, comp, n, seed, stripe=150000, chunk=10000):
 @pytest.fixture
 def lz4_kernel(cg, request):
     """"lanes" = a lane per stream (cg_lz4_lane_kernel), "groups" = eight lanes per stream (cg_decompress_kernel)"""
-    cg.set_option("lz4_lanes", 1 if request.param == "lanes" else 0)
+    cg.set_option("lz4_lanes", {"lanes": 1, "groups": 0, "auto": 2}[request.param])
     yield request.param
     cg.set_option("lz4_lanes", -1)          # back to the library's default
 
 
 @pytest.mark.parametrize("path", ["shard", "e2e", "dma"])
-@pytest.mark.parametrize("comp,lz4_kernel", [("lz4", "lanes"), ("lz4", "groups"), ("pglz", "lanes"), ("zstd", "lanes")],
+@pytest.mark.parametrize("comp,lz4_kernel", [("lz4", "lanes"), ("lz4", "groups"), ("lz4", "auto"), ("pglz", "auto"), ("zstd", "auto")],
                          indirect=["lz4_kernel"])
 def test_compressed_chunks(cg, oracle, comp, path, lz4_kernel):
     if comp == "lz4" and not oracle.lib().orc_have_lz4():
