@@ -168,6 +168,7 @@ SYMBOLS = [
     ("cg_comm_exchange_result", C.c_int, [C.c_int32, _P, C.POINTER(C.c_int64), _P, C.POINTER(C.c_int32), C.POINTER(C.c_uint64),
                                          C.POINTER(C.c_double)]),
     ("cg_comm_exchange_plan", C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.POINTER(C.c_int32)]),
+    ("cg_comm_peer_plan", C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
 ]
 
 _lib = None

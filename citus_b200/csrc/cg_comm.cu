@@ -747,6 +747,48 @@ extern "C" int cg_comm_exchange_plan(int32_t P, int32_t nranks, int32_t rank, co
 }
 
 
+/*
+ * Where a rank's rows land when the scatter stores straight into the owners' receive buffers.  Pure host arithmetic
+ * over the counts every rank holds after the count exchange (counts[r * P + p] = rows of partition p on rank r), so it
+ * has a CPU test (tests/test_distributed_gloo.py).  The receive buffer of rank d holds, per column, the rows in
+ * (source rank, local partition) order -- the layout the grouped ncclSend/ncclRecv path produces.  For this rank:
+ *   pos_begin[d], pos_begin[d + 1]   the output positions (cg_comm_exchange_plan) that belong to rank d
+ *   total[d]                         rows rank d receives = the column stride of its buffer
+ *   adj[d]                           a row the local scatter would put at index i of the send order lands at adj[d] + i
+ *                                    of rank d's column (rows of lower ranks come first, rows for lower ranks do not count)
+ */
+extern "C" int cg_comm_peer_plan(int32_t P, int32_t nranks, int32_t rank, const int64_t *counts, int32_t *pos_begin /* [nranks + 1] */,
+								 int64_t *total /* [nranks] */, int64_t *adj /* [nranks] */)
+{
+	if (P < 1 || nranks < 1 || rank < 0 || rank >= nranks || !counts || !pos_begin || !total || !adj)
+		return cg_set_error(CG_EINVAL, "bad peer plan arguments");
+	std::vector<int64_t> M((size_t) nranks * nranks, 0);            /* M[r][d] rows rank r routes to rank d */
+	for (int r = 0; r < nranks; r++)
+		for (int p = 0; p < P; p++)
+		{
+			if (counts[(size_t) r * P + p] < 0) return cg_set_error(CG_EINVAL, "negative row count");
+			M[(size_t) r * nranks + p % nranks] += counts[(size_t) r * P + p];
+		}
+	int64_t soff = 0;
+	int pos = 0;
+	for (int d = 0; d < nranks; d++)
+	{
+		int64_t roff = 0, t = 0;
+		for (int r = 0; r < nranks; r++)
+		{
+			if (r < rank) roff += M[(size_t) r * nranks + d];
+			t += M[(size_t) r * nranks + d];
+		}
+		total[d] = t;
+		adj[d] = roff - soff;
+		pos_begin[d] = pos;
+		for (int p = d; p < P; p += nranks) pos++;
+		soff += M[(size_t) rank * nranks + d];
+	}
+	pos_begin[nranks] = pos;
+	return CG_OK;
+}
+
 /* ---- peer-window form of the exchange: the scatter stores into the owners' receive buffers ---- */
 struct PeerExchange
 {
@@ -781,16 +823,12 @@ static int peer_exchange_hook(void *arg, CgPeerScatter *out)
 	}
 	if (unroutable)
 		return cg_set_error(CG_EINVAL, "could not find shard for partition column value (%lld rows)", (long long) unroutable);
-	std::vector<int64_t> M((size_t) W * W, 0);                   /* M[r][d] rows rank r routes to rank d */
-	for (int r = 0; r < W; r++)
-		for (int p = 0; p < P; p++) M[(size_t) r * W + p % W] += counts[(size_t) r * P + p];
-	std::vector<int64_t> total(W, 0);
+	std::vector<int64_t> total(W, 0), adj(W, 0);
+	std::vector<int32_t> pos_begin(W + 1, 0);
+	rc = cg_comm_peer_plan(P, W, me, counts.data(), pos_begin.data(), total.data(), adj.data());
+	if (rc) return rc;
 	int64_t need_rows = 0;
-	for (int d = 0; d < W; d++)
-	{
-		for (int r = 0; r < W; r++) total[d] += M[(size_t) r * W + d];
-		need_rows = std::max(need_rows, total[d]);
-	}
+	for (int d = 0; d < W; d++) need_rows = std::max(need_rows, total[d]);
 	const size_t need = (size_t) std::max<int64_t>(need_rows, 1) * sizeof(int64_t) * X->ncols;
 	if (!S.recv_shared || need > S.recv_agreed)
 	{
@@ -828,21 +866,15 @@ static int peer_exchange_hook(void *arg, CgPeerScatter *out)
 	S.sent_bytes = 0;
 	memset(out, 0, sizeof *out);
 	out->nranks = W;
-	int64_t soff = 0;
-	int pos = 0;
 	for (int d = 0; d < W; d++)
 	{
-		int64_t roff = 0;
-		for (int r = 0; r < me; r++) roff += M[(size_t) r * W + d];
 		out->base[d] = (int64_t *) S.recv_peer[d];
 		out->stride[d] = total[d];
-		out->adj[d] = roff - soff;
-		out->pos_begin[d] = pos;
-		for (int p = d; p < P; p += W) pos++;
-		soff += M[(size_t) me * W + d];
-		if (d != me) S.sent_bytes += (uint64_t) M[(size_t) me * W + d] * sizeof(int64_t) * X->ncols;
+		out->adj[d] = adj[d];
+		out->pos_begin[d] = pos_begin[d];
+		if (d != me) S.sent_bytes += (uint64_t) send_rows[d] * sizeof(int64_t) * X->ncols;
 	}
-	out->pos_begin[W] = pos;
+	out->pos_begin[W] = pos_begin[W];
 	CG_CUDA(cudaEventRecord(S.t0, ctx->compute));
 	return CG_OK;
 }

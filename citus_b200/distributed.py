@@ -117,6 +117,16 @@ def exchange_result(slot: int, ncols: int, timing=False):
                 sent_bytes=sent.value, exchange_ms=ms.value if timing else None)
 
 
+def peer_plan(partition_count: int, world: int, rank_: int, counts):
+    """cg_comm_peer_plan: (pos_begin[world + 1], total[world], adj[world]) -- where this rank's rows land when the scatter
+    stores straight into the owners' receive buffers"""
+    counts = np.ascontiguousarray(counts, np.int64)
+    pos_begin, total, adj = np.zeros(world + 1, np.int32), np.zeros(world, np.int64), np.zeros(world, np.int64)
+    check(lib().cg_comm_peer_plan(partition_count, world, rank_, counts.ctypes.data, pos_begin.ctypes.data, total.ctypes.data,
+                                  adj.ctypes.data))
+    return pos_begin, total, adj
+
+
 def exchange_plan(partition_count: int, world: int, rank_: int, counts=None):
     """cg_comm_exchange_plan: (position[P], send_rows[world], recv_rows[world], local_part_counts[nlocal][world])"""
     pos = np.zeros(partition_count, np.int32)

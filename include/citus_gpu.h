@@ -442,6 +442,11 @@ int cg_comm_exchange_result(int32_t slot, int64_t **d_cols, int64_t *nrows, int6
  * partitions by source rank.  counts may be NULL (positions and nlocal only). */
 int cg_comm_exchange_plan(int32_t P, int32_t nranks, int32_t rank, const int64_t *counts, int32_t *position,
 						  int64_t *send_rows, int64_t *recv_rows, int64_t *local_part_counts, int32_t *nlocal);
+/* peer-window form: where this rank's rows land in the receive buffers of the ranks (pure host arithmetic over the
+ * exchanged counts, counts[r * P + p]).  Positions [pos_begin[d], pos_begin[d + 1]) belong to rank d; rank d's buffer
+ * has a column stride of total[d] rows; a row at index i of this rank's send order lands at adj[d] + i. */
+int cg_comm_peer_plan(int32_t P, int32_t nranks, int32_t rank, const int64_t *counts, int32_t *pos_begin /* [nranks + 1] */,
+					  int64_t *total /* [nranks] */, int64_t *adj /* [nranks] */);
 
 /* The same join emitting its rows -- SELECT b.key, b.payload, p.payload FROM build b JOIN probe p USING (key) -- into device
  * arrays of `capacity` rows owned by the caller (row order unspecified, NULL keys join nothing).  *nrows = the number of

@@ -94,6 +94,34 @@ def _worker(rank, world, port, out):
         assert local.shape == (len(mine_parts), world)
         for i, p in enumerate(mine_parts):
             assert local[i].tolist() == counts[:, p].tolist()
+        # 4. the peer-window form: every rank scatters straight into the owners' receive buffers.  Each rank computes
+        # where its rows land (cg_comm_peer_plan) and "stores" row labels into a model of the buffers, exchanged here
+        # over gloo; every buffer must come out exactly filled, in (source rank, local partition) order -- the
+        # layout of the send/recv form -- with the column stride cg_comm_peer_plan reports
+        pos_begin, total, adj = cgd.peer_plan(P, world, rank, counts)
+        assert pos_begin[0] == 0 and pos_begin[world] == P
+        sends = []                                                # per destination: (index in that rank's column, label)
+        idx_in_send_order = 0
+        for q in range(P):                                        # output positions = send order, destination-major
+            p = int(order[q])
+            d = int(np.searchsorted(pos_begin, q, side="right") - 1)
+            assert d == p % world
+            for k in range(int(counts[rank, p])):
+                sends.append((d, int(adj[d]) + idx_in_send_order, rank * 10**9 + p * 10**6 + k))
+                idx_in_send_order += 1
+        box = [None] * world
+        dist.all_gather_object(box, sends)
+        got = {}
+        for lst in box:
+            for d, i, label in lst:
+                if d == rank:
+                    assert i not in got, "two rows stored to one place"
+                    got[i] = label
+        assert total[rank] == recv.sum() and sorted(got) == list(range(int(total[rank])))
+        want = [r * 10**9 + p * 10**6 + k for r in range(world) for p in mine_parts for k in range(int(counts[r, p]))]
+        assert [got[i] for i in range(len(want))] == want
+        for d in range(world):
+            assert total[d] == sum(int(counts[r, p]) for r in range(world) for p in range(P) if p % world == d)
         out.put((rank, "ok"))
     except Exception as e:          # noqa
         import traceback

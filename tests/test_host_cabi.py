@@ -263,6 +263,41 @@ def test_jit_generates_valid_sm100a_code_for_every_plan_form(cg):
     assert "fcmp(v" in src and "f8_ordered" in src and "__uint_as_float" in src
 
 
+# --------------------------------------------------------------------------- repartition exchange, peer-window layout
+@pytest.mark.parametrize("P,W", [(32, 8), (32, 2), (7, 4), (3, 8), (1, 1), (33, 16), (32, 5)])
+def test_peer_plan_fills_every_receive_buffer_in_order(P, W):
+    """cg_comm_peer_plan (pure host arithmetic): all W ranks of a repartition modelled in one process.  Every rank
+    "stores" its rows where the plan says; every receive buffer must come out exactly filled, in (source rank, local
+    partition) order, which is the layout of the ncclSend/ncclRecv form and what cg_comm_exchange_result describes"""
+    from citus_b200 import distributed as cgd
+    rng = np.random.default_rng(P * 100 + W)
+    counts = rng.integers(0, 50, size=(W, P)) * (rng.random((W, P)) < 0.8)          # some empty partitions
+    bufs = [dict() for _ in range(W)]
+    totals = None
+    for me in range(W):
+        pos, send, recv, local = cgd.exchange_plan(P, W, me, counts)
+        pos_begin, total, adj = cgd.peer_plan(P, W, me, counts)
+        totals = total if totals is None else totals
+        assert np.array_equal(total, totals)                       # every rank computes the same strides
+        order = np.argsort(pos)
+        i = 0
+        for q in range(P):
+            p = int(order[q])
+            d = int(np.searchsorted(pos_begin, q, side="right") - 1)
+            assert d == p % W
+            for k in range(int(counts[me, p])):
+                at = int(adj[d]) + i
+                assert at not in bufs[d]
+                bufs[d][at] = (me, p, k)
+                i += 1
+        assert i == int(send.sum())
+    for d in range(W):
+        parts = [p for p in range(P) if p % W == d]
+        want = [(r, p, k) for r in range(W) for p in parts for k in range(int(counts[r, p]))]
+        assert int(totals[d]) == len(want) and sorted(bufs[d]) == list(range(len(want)))
+        assert [bufs[d][i] for i in range(len(want))] == want
+
+
 # --------------------------------------------------------------------------- lane-per-stream LZ4 decoder (on the host)
 @pytest.fixture(scope="module")
 def lz4_lane_host():
