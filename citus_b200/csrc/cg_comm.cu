@@ -795,7 +795,6 @@ struct PeerExchange
 	CgComm::Slot *S;
 	int64_t *d_counts;
 	int32_t P, ncols, nlocal;
-	const int32_t *position;
 	int64_t total_recv;
 };
 
@@ -911,7 +910,7 @@ extern "C" int cg_comm_repartition_exchange(int32_t slot, const int64_t *const *
 		/* routing + histogram; counts of all ranks (side stream, while the offset scan runs); then ONE kernel that is
 		 * both the scatter and the all-to-all: rows leave shared memory as runs into the owner's receive buffer */
 		PeerExchange X;
-		X.S = &S; X.d_counts = d_counts; X.P = P; X.ncols = ncols; X.nlocal = nlocal; X.position = position.data(); X.total_recv = 0;
+		X.S = &S; X.d_counts = d_counts; X.P = P; X.ncols = ncols; X.nlocal = nlocal; X.total_recv = 0;
 		CgScatterHook hook = {peer_exchange_hook, &X};
 		rc = cg_partition_route_scatter_async(d_cols[0], d_key_nulls, n, key_len, 1, mins, maxs, P, position.data(), d_cols, ncols, nullptr,
 											  d_counts, g_comm.ev_index, &hook);

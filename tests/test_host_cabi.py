@@ -263,6 +263,17 @@ def test_jit_generates_valid_sm100a_code_for_every_plan_form(cg):
     assert "fcmp(v" in src and "f8_ordered" in src and "__uint_as_float" in src
 
 
+def test_run_time_options_are_named(cg):
+    """cg_set_option: every documented switch is accepted, anything else is an error (no silent typos)"""
+    from citus_b200 import capi
+    for name, value in (("jit", 1), ("force_general", 0), ("realign_tma", 1), ("peer_window", 1), ("lz4_lanes", -1), ("lz4_lane_warps", 64)):
+        cg.set_option(name, value)
+    with pytest.raises(capi.CitusGpuError) as e:
+        cg.set_option("lz4_lane", 1)
+    assert e.value.code == capi.CG_EINVAL
+    assert capi.lib().cg_comm_peer_window() == 0          # no communicator in this process
+
+
 # --------------------------------------------------------------------------- repartition exchange, peer-window layout
 @pytest.mark.parametrize("P,W", [(32, 8), (32, 2), (7, 4), (3, 8), (1, 1), (33, 16), (32, 5)])
 def test_peer_plan_fills_every_receive_buffer_in_order(P, W):

@@ -18,11 +18,12 @@ cg.init(0)
 print("numa node", cg.numa_bind())
 torch.cuda.set_stream(torch.cuda.Stream())
 cg.use_torch_stream()
-rels = bench.generate_shards(cg, list(range(nshards)), rows, 32)
+rels = {s: cg.Relation.generate(list(bench.C2_COLUMNS), rows, seed=bench.SEED, first_row=s * rows, stripe_row_limit=bench.STRIPE_ROWS,
+                                chunk_row_limit=bench.CHUNK_ROWS, nthreads=32) for s in range(nshards)}
 aggs = [cg.sum_(2), cg.count_star()]
-desc = cg.make_desc(bench.QUALS, bench.GROUP, aggs)
+desc = cg.make_desc(bench.C2_QUALS, bench.C2_GROUP, aggs)
 aggs[0].term_abs_bound = max(cg.relation_bounds(r, desc)[2][0] for r in rels.values())
-desc = cg.make_desc(bench.QUALS, bench.GROUP, aggs)
+desc = cg.make_desc(bench.C2_QUALS, bench.C2_GROUP, aggs)
 partial = cg.GpuColumnarAgg(desc, rels[0].column_descs(), 0, bench.NKEYS - 1, rows * nshards)
 for r in rels.values():
     r.register()

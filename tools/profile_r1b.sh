@@ -1,4 +1,5 @@
 #!/bin/bash
+# round-1 record: tools/tpch_bench.py named below was that round's driver; `bench.py --workload c5` replaced it
 # round-1 (second session) evidence run on one GPU: TPC-H SF100 through the plan-specialised kernels,
 # ncu launch lists, and full captures of the NVRTC kernels (Q1, Q6) and of the decompression kernel.
 set -x
