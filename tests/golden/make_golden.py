@@ -161,6 +161,16 @@ def main():
     exp["contestant_avg"] = table_rows(cq, r"^SELECT avg\(rating\), stddev_samp\(rating\) FROM contestant;")[0][0]
     exp["contestant_group_avg"] = table_rows(cq, r"^SELECT country, avg\(rating\) FROM contestant WHERE rating > 2200")
 
+    # aggregate_support (expected/aggregate_support.out:121-128, 312-322): aggdata(id, key, val, valf) with NULLs in val;
+    # sum(val) GROUP BY key is NULL for the groups whose val is NULL in every row
+    asup = f"{REF}/expected/aggregate_support.out"
+    ins = re.search(r"insert into aggdata \(id, key, val, valf\) values (.*?);\n", open(asup).read()).group(1)
+    rows = [[None if x.strip() == "NULL" else float(x) if "." in x else int(x) for x in t.split(",")]
+            for t in re.findall(r"\(([^)]*)\)", ins)]
+    exp["aggdata_rows"] = rows
+    exp["aggdata_sum_val_by_key"] = [[int(r[0]), None if r[2] == "" else int(r[2])]
+                                     for r in table_rows(asup, r"^SELECT key, internalsum\(val\), sum\(val\) from aggdata group by key order by key;")]
+
     with open(os.path.join(HERE, "expected.json"), "w") as f:
         json.dump(exp, f, indent=1, sort_keys=True)
     print("wrote", n, "lineitem rows and", len(exp), "golden entries")

@@ -250,6 +250,30 @@ def test_contestant_aggregates(oracle, expected):
     assert got == expected["contestant_group_avg"]
 
 
+def test_sum_is_null_when_every_input_is_null(oracle, expected):
+    """expected/aggregate_support.out:121-128, 312-322: aggdata(id, key, val, valf) hash-distributed on id, NULLs in val;
+    SELECT key, sum(val) ... GROUP BY key is NULL (not 0) for keys 5 and 6, whose val is NULL in every row -- through
+    worker partials per shard and the coordinator's sum(sum) like the reference plans it"""
+    rows = expected["aggdata_rows"]
+    ids = np.array([r[0] for r in rows]); keys = np.array([r[1] for r in rows])
+    val = np.array([0 if r[2] is None else r[2] for r in rows]); val_null = np.array([r[2] is None for r in rows], np.uint8)
+    mins, maxs = oracle.synthetic_intervals(4)
+    shard_of, _ = oracle.partition_rows(ids, None, 4, "h", mins, maxs)          # create_distributed_table('aggdata', 'id')
+    aggs = [oracle.sum_(2), oracle.count(2), oracle.count_star()]
+    total = oracle.Result(aggs)
+    for s in range(4):
+        sel = shard_of == s
+        if not sel.any():
+            continue
+        t = oracle.Table([4, 4, 4])
+        t.insert([ids[sel], keys[sel], val[sel]], [None, None, val_null[sel]])
+        total.combine(t.scan(group_cols=[1], aggs=aggs))
+    got = [[int(k), (None if g[0]["count"] == 0 else int(g[0]["sum"]))] for k, g in sorted(total.groups().items())]
+    assert got == expected["aggdata_sum_val_by_key"]
+    assert {int(k): g[1]["count"] for k, g in total.groups().items()} == {1: 1, 2: 3, 3: 1, 5: 0, 6: 0, 7: 1, 9: 1}      # count(val)
+    assert sum(g[2]["count"] for g in total.groups().values()) == len(rows)                                           # count(*)
+
+
 def _lineitem_shards(oracle, li):
     """lineitem is hash-distributed on l_orderkey with shard_count 2 (sql/multi_create_table.sql:30)"""
     mins, maxs = oracle.synthetic_intervals(2)
