@@ -61,8 +61,14 @@ uint64_t cg_kernel_launches(void);
  * 2 global table; source (may be NULL) receives the generated CUDA. */
 uint64_t cg_jit_launches(void);
 uint64_t cg_jit_compiles(void);
-/* run-time switches, e.g. ("jit", 0 | 1 | 2), ("force_general", 0 | 1): which kernel family scans (tests and
- * A/B measurements drive every family through the same C-ABI calls) */
+/* run-time switches (tests and A/B measurements drive every kernel family through the same C-ABI calls):
+ *   "jit" 0 | 1 | 2, "force_general" 0 | 1     which kernel family scans
+ *   "realign_tma" 0 | 1                         cp.async.bulk or plain-load form of the page realign kernel
+ *   "lz4_lanes" 0 | 1 | 2 (< 0 = default = 2)    LZ4 streams: eight lanes per stream | a lane per stream | by launch size
+ *   "lz4_lane_warps" n                          (probe) warps per SM the lane-per-stream kernel spreads a launch over
+ *   "peer_window" 0 | 1                         exchange steps over NCCL | over the IPC-mapped peer window; the same
+ *                                               value on every rank
+ * An unknown name is CG_EINVAL. */
 int cg_set_option(const char *name, int64_t value);
 struct CgScanDesc;
 struct CgColumnDesc;
