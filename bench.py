@@ -327,7 +327,8 @@ def run_reference(args, rank, world):
         "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "int64", "data": "synthetic", "config": c2_config(args, f"shard s -> GPU s mod {args.gpus}"),
-        "reference_arm": "host cores, one pinned thread per shard",
+        "reference_arm": "host cores, one pinned thread per shard: the reference's own parallelism for this workload -- one backend per "
+                         "shard task, and a columnar scan is not parallel-aware (columnar_customscan.c:365-366, 417-421, 1337)",
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": nthreads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU restatement of the reference path (oracle/oracle.c): PostgreSQL/Citus cannot be built here",
